@@ -1,0 +1,371 @@
+"""CPU oracle for the MSMDFusion voxel-space fusion hot path.
+
+TEST INFRASTRUCTURE ONLY -- see oracle/README.md.  Only ``tests/``,
+``__graft_entry__.smoke()`` and the ``cpu_baseline`` / ``--impl reference`` legs of
+``bench.py`` may import this module; the product package ``msmdfusion_b200`` never does.
+
+Each function restates the reference algorithm and cites the reference file:line it
+follows (paths relative to ``/root/reference``).  Heavy loops live in
+``oracle/c/msmd_oracle.c`` (gcc, OpenMP); light index logic is numpy.
+
+Parity pinning ("Oracle"):
+* ``hard_voxelize``  -- pinned against the reference's own CPU op compiled from
+  ``/root/reference`` (``oracle/_ref``), the numba ``VoxelGenerator`` and its
+  known-answer test.
+* FPS / ball query -- pinned against the inline vectors of
+  ``tests/test_models/test_common_modules/test_pointnet_ops.py``.
+* sparse conv / sparse_add / modality split / GMA-conv -- the arithmetic lives in the
+  un-vendored spconv v2.1.21; no reference test pins results there ("parity unpinned" by
+  the reference).  The restatement is pinned against an independent dense
+  ``torch.nn.functional.conv3d`` oracle instead.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+from . import build as _build
+
+_LIB = None
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        path = _build.build_port()
+        L = ctypes.CDLL(path)
+        i32p = ctypes.POINTER(ctypes.c_int)
+        f32p = ctypes.POINTER(ctypes.c_float)
+        L.orc_hard_voxelize.restype = ctypes.c_int
+        L.orc_hard_voxelize.argtypes = [f32p, ctypes.c_int, ctypes.c_int, f32p, f32p, ctypes.c_int,
+                                        ctypes.c_int, f32p, i32p, i32p]
+        L.orc_grid_size.argtypes = [f32p, f32p, i32p]
+        L.orc_conv_out_shape.argtypes = [i32p] * 6
+        L.orc_subm_rulebook.restype = ctypes.c_int
+        L.orc_subm_rulebook.argtypes = [i32p, ctypes.c_int, i32p, i32p, i32p, i32p]
+        L.orc_conv_rulebook.restype = ctypes.c_int
+        L.orc_conv_rulebook.argtypes = [i32p, ctypes.c_int, i32p, i32p, i32p, i32p, i32p, i32p,
+                                        ctypes.c_int, i32p]
+        L.orc_spconv_fwd.restype = ctypes.c_int
+        L.orc_spconv_fwd.argtypes = [f32p, f32p, i32p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                     ctypes.c_int, f32p]
+        L.orc_fps_block.restype = ctypes.c_int
+        L.orc_fps_block.argtypes = [ctypes.c_int]
+        L.orc_fps.restype = ctypes.c_int
+        L.orc_fps.argtypes = [f32p, ctypes.c_int, ctypes.c_int, f32p, i32p]
+        L.orc_ball_query.restype = ctypes.c_int
+        L.orc_ball_query.argtypes = [f32p, ctypes.c_int, f32p, ctypes.c_int, ctypes.c_float,
+                                     ctypes.c_float, ctypes.c_int, i32p]
+        L.orc_nn_search.restype = ctypes.c_int
+        L.orc_nn_search.argtypes = [i32p, ctypes.c_int, i32p, ctypes.c_int, f32p, i32p]
+        L.orc_num_threads.restype = ctypes.c_int
+        _LIB = L
+    return _LIB
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def _fp(a):
+    return a.ctypes.data_as(ctypes.POINTER(ctypes.c_float))
+
+
+def _ip(a):
+    return a.ctypes.data_as(ctypes.POINTER(ctypes.c_int))
+
+
+def num_threads():
+    return lib().orc_num_threads()
+
+
+# --------------------------------------------------------------------------------------
+# a1: hard_voxelize  (mmdet3d/ops/voxel/src/voxelization_cpu.cpp:43-142,
+#                     mmdet3d/ops/voxel/voxelize.py:13-59)
+# --------------------------------------------------------------------------------------
+def grid_size(voxel_size, coors_range):
+    g = np.zeros(3, np.int32)
+    vs, cr = _f32(voxel_size), _f32(coors_range)
+    lib().orc_grid_size(_fp(vs), _fp(cr), _ip(g))
+    return g  # (x, y, z)
+
+
+def hard_voxelize(points, voxel_size, coors_range, max_points, max_voxels):
+    """Returns (voxels[:V], coors[:V] (z,y,x), num_points[:V]) like voxelize.py:54-59."""
+    points = _f32(points)
+    N, C = points.shape
+    vs, cr = _f32(voxel_size), _f32(coors_range)
+    cap = max(1, min(N, max_voxels))  # only the first voxel_num rows are ever written
+    voxels = np.zeros((cap, max_points, C), np.float32)
+    coors = np.zeros((cap, 3), np.int32)
+    num = np.zeros((cap,), np.int32)
+    v = lib().orc_hard_voxelize(_fp(points), N, C, _fp(vs), _fp(cr), int(max_points),
+                                int(max_voxels), _fp(voxels), _ip(coors), _ip(num))
+    assert v >= 0
+    return voxels[:v], coors[:v], num[:v]
+
+
+def hard_voxelize_ref(points, voxel_size, coors_range, max_points, max_voxels):
+    """The reference's OWN CPU op (compiled from /root/reference into oracle/_ref)."""
+    import importlib.util
+    import torch
+    so = _build.ref_so_path() or _build.build_ref()
+    if so is None:
+        raise RuntimeError('oracle/_ref is not built and /root/reference is absent')
+    spec = importlib.util.spec_from_file_location(_build.REF_NAME, so)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    pts = torch.from_numpy(_f32(points))
+    voxels = pts.new_zeros((max_voxels, max_points, pts.size(1)))
+    coors = pts.new_zeros((max_voxels, 3), dtype=torch.int)
+    num = pts.new_zeros((max_voxels,), dtype=torch.int)
+    v = mod.hard_voxelize(pts, voxels, coors, num, [float(x) for x in voxel_size],
+                          [float(x) for x in coors_range], int(max_points), int(max_voxels), 3)
+    return voxels[:v].numpy(), coors[:v].numpy(), num[:v].numpy()
+
+
+# a3: HardSimpleVFE.forward (mmdet3d/models/voxel_encoders/voxel_encoder.py:44-46)
+def hard_simple_vfe(voxels, num_points, num_features):
+    s = voxels[:, :, :num_features].sum(axis=1, dtype=np.float32)
+    return np.ascontiguousarray(s / num_points.astype(np.float32).reshape(-1, 1))
+
+
+# --------------------------------------------------------------------------------------
+# a5: spconv-2.x SparseConvolution.forward  (API copy bug_fix/conv.py:185-462)
+# --------------------------------------------------------------------------------------
+def _triple(v):
+    if isinstance(v, (list, tuple, np.ndarray)):
+        assert len(v) == 3
+        return [int(x) for x in v]
+    return [int(v)] * 3
+
+
+def conv_out_shape(shape, ksize, stride, padding, dilation):
+    out = np.zeros(3, np.int32)
+    args = [_i32(_triple(a)) for a in (shape, ksize, stride, padding, dilation)]
+    lib().orc_conv_out_shape(*[_ip(a) for a in args], _ip(out))
+    return [int(x) for x in out]
+
+
+def subm_rulebook(indices, spatial_shape, ksize=3, dilation=1):
+    indices = _i32(indices)
+    N = indices.shape[0]
+    ks, dl, sh = _i32(_triple(ksize)), _i32(_triple(dilation)), _i32(_triple(spatial_shape))
+    K = int(np.prod(ks))
+    pair = np.empty((K, N), np.int32)
+    r = lib().orc_subm_rulebook(_ip(indices), N, _ip(sh), _ip(ks), _ip(dl), _ip(pair))
+    assert r == 0
+    return pair
+
+
+def conv_rulebook(indices, spatial_shape, ksize, stride, padding, dilation=1):
+    """Returns (out_indices (N_out,4) ascending linear order, pair_fwd (K,N_out), out_shape)."""
+    indices = _i32(indices)
+    N = indices.shape[0]
+    ks, st, pd, dl = (_i32(_triple(a)) for a in (ksize, stride, padding, dilation))
+    sh = _i32(_triple(spatial_shape))
+    K = int(np.prod(ks))
+    cap = max(1, N * K)
+    out_idx = np.empty((cap, 4), np.int32)
+    pair = np.empty((K * cap,), np.int32)
+    n = lib().orc_conv_rulebook(_ip(indices), N, _ip(sh), _ip(ks), _ip(st), _ip(pd), _ip(dl),
+                                _ip(out_idx), cap, _ip(pair))
+    assert n >= 0
+    return (out_idx[:n].copy(), pair[:K * n].reshape(K, n).copy(),
+            conv_out_shape(spatial_shape, ksize, stride, padding, dilation))
+
+
+def spconv_fwd(features, weight, pair_fwd):
+    """features (N_in,Cin); weight KRSC [Cout,kz,ky,kx,Cin]; pair_fwd (K,N_out)."""
+    features, weight, pair_fwd = _f32(features), _f32(weight), _i32(pair_fwd)
+    cout, cin = weight.shape[0], weight.shape[-1]
+    K, n_out = pair_fwd.shape
+    assert int(np.prod(weight.shape[1:-1])) == K and features.shape[1] == cin
+    out = np.empty((n_out, cout), np.float32)
+    r = lib().orc_spconv_fwd(_fp(features), _fp(weight), _ip(pair_fwd), n_out, cin, cout, K, _fp(out))
+    assert r == 0
+    return out
+
+
+def batchnorm_eval(x, weight, bias, mean, var, eps):
+    """torch.nn.BatchNorm1d in eval mode over active-voxel rows."""
+    inv = (1.0 / np.sqrt(var.astype(np.float32) + np.float32(eps))).astype(np.float32)
+    return ((x - mean.astype(np.float32)) * inv * weight.astype(np.float32)
+            + bias.astype(np.float32)).astype(np.float32)
+
+
+# a16: SparseConvTensor.dense()  (spconv-1.x equivalent mmdet3d/ops/spconv/structure.py:54-66)
+def dense(indices, features, spatial_shape, batch_size):
+    C = features.shape[1]
+    D, H, W = spatial_shape
+    out = np.zeros((batch_size, D, H, W, C), np.float32)
+    idx = indices.astype(np.int64)
+    out[idx[:, 0], idx[:, 1], idx[:, 2], idx[:, 3]] = features
+    return np.ascontiguousarray(out.transpose(0, 4, 1, 2, 3))
+
+
+# a14: Fsp.sparse_add (call site sparse_multimodal_encoder_painting.py:455).
+# spconv v2.1.21 implements it as torch.sparse_coo_tensor(a)+(b) -> .coalesce(): output rows
+# sorted ascending by (b,z,y,x), features of coincident voxels summed.
+def sparse_add(idx_a, feat_a, idx_b, feat_b, spatial_shape):
+    D, H, W = spatial_shape
+    idx = np.concatenate([idx_a, idx_b], 0).astype(np.int64)
+    feat = np.concatenate([feat_a, feat_b], 0).astype(np.float32)
+    lin = ((idx[:, 0] * D + idx[:, 1]) * H + idx[:, 2]) * W + idx[:, 3]
+    order = np.argsort(lin, kind='stable')
+    lin_s = lin[order]
+    uniq, start = np.unique(lin_s, return_index=True)
+    out_feat = np.add.reduceat(feat[order], start, axis=0).astype(np.float32)
+    out_idx = idx[order][start].astype(np.int32)
+    return out_idx, out_feat
+
+
+# --------------------------------------------------------------------------------------
+# a17 / a18 / a13: FPS, ball query, nearest-3D-voxel assignment
+# --------------------------------------------------------------------------------------
+def fps_block(n):
+    return lib().orc_fps_block(int(n))
+
+
+def furthest_point_sample(xyz, m):
+    """xyz (n,3) f32 -> idx (m,) i32.  furthest_point_sample_cuda.cu:25-140 incl. tie-break."""
+    xyz = _f32(xyz)
+    n = xyz.shape[0]
+    temp = np.full((n,), 1e10, np.float32)  # furthest_point_sample.py:28
+    idx = np.zeros((m,), np.int32)
+    r = lib().orc_fps(_fp(xyz), n, int(m), _fp(temp), _ip(idx))
+    assert r == 0
+    return idx
+
+
+def ball_query(min_radius, max_radius, nsample, xyz, center_xyz):
+    """ball_query_cuda.cu:11-55; xyz (n,3) candidates, center_xyz (m,3) -> (m,nsample) i32."""
+    xyz, center_xyz = _f32(xyz), _f32(center_xyz)
+    idx = np.zeros((center_xyz.shape[0], nsample), np.int32)  # ball_query.py:35
+    lib().orc_ball_query(_fp(xyz), xyz.shape[0], _fp(center_xyz), center_xyz.shape[0],
+                         float(min_radius), float(max_radius), int(nsample), _ip(idx))
+    return idx
+
+
+def nn_search(query_zyx, key_zyx):
+    q, k = _i32(query_zyx), _i32(key_zyx)
+    val = np.empty((q.shape[0],), np.float32)
+    idx = np.empty((q.shape[0],), np.int32)
+    lib().orc_nn_search(_ip(q), q.shape[0], _ip(k), k.shape[0], _fp(val), _ip(idx))
+    return val, idx
+
+
+def fps_nn_fast(query, key, fps_num, radius, max_cluster_samples, dist_thresh):
+    """sparse_multimodal_encoder_painting.py:276-323.
+
+    query (Q,4) / key (Nk,4) int (b,z,y,x) of ONE sample -> (Q,) int64, -1 = unassigned.
+    The final duplicate-index scatter (:321) leaves the winner undefined in the reference;
+    this restatement fixes "the LAST (representative, slot) pair in row-major order wins",
+    which is what a sequential index_put_ produces.
+    """
+    Q = query.shape[0]
+    out = np.full((Q,), -1, np.int64)
+    q = query[:, 1:]
+    k = key[:, 1:]
+    if Q <= fps_num:
+        val, idx = nn_search(q, k)
+        valid = val < np.float32(dist_thresh)
+        out[valid] = idx[valid]
+        return out
+    qf = q.astype(np.float32)
+    repr_idx = furthest_point_sample(qf, fps_num)
+    repr_q = q[repr_idx]
+    val, nn_idx = nn_search(repr_q, k)
+    valid = val < np.float32(dist_thresh)
+    group = ball_query(0, radius, max_cluster_samples, qf, repr_q.astype(np.float32)).astype(np.int64)
+    exp_nn = np.repeat(nn_idx.astype(np.int64), max_cluster_samples)
+    exp_valid = np.repeat(valid, max_cluster_samples)
+    g = group.reshape(-1)
+    out[g[exp_valid]] = exp_nn[exp_valid]  # numpy: last write wins (sequential)
+    return out
+
+
+# --------------------------------------------------------------------------------------
+# a11: voxel_modality_split + type_assign (mmdet3d/models/detectors/MSMDFusion.py:27-45,251-325)
+# --------------------------------------------------------------------------------------
+def float_key(coords_zyx):
+    """MSMDFusion.py:271-272: int32 tensor * python float -> float32 arithmetic
+    (mul, mul, add, add; no FMA)."""
+    c = coords_zyx.astype(np.float32)
+    a = c[:, 0] * np.float32(1e6)
+    b = c[:, 1] * np.float32(1e3)
+    return ((a + b).astype(np.float32) + c[:, 2]).astype(np.float32)
+
+
+def type_assign(v3, v2):
+    """MSMDFusion.py:27-45 two-pointer merge on sorted keys."""
+    t3 = np.zeros(v3.shape[0], np.float32)
+    t2 = np.zeros(v2.shape[0], np.float32)
+    i = j = 0
+    n, m = v3.shape[0], v2.shape[0]
+    while i < n and j < m:
+        if v3[i] < v2[j]:
+            i += 1
+        elif v3[i] == v2[j]:
+            t3[i] = 1
+            t2[j] = 1
+            i += 1
+            j += 1
+        else:
+            j += 1
+    return t3, t2
+
+
+def voxel_modality_split(coord_3d, coord_2d, batch_size):
+    """Returns (coord_3d_mix (N,5), coord_2d_mix (M,5), syn_mix_3d, syn_mix_2d).
+
+    torch.sort is unstable (MSMDFusion.py:274-275); this restatement uses a STABLE sort
+    (ties ordered by original row), one of the outcomes the reference can produce.
+    The previous-sample-length offset quirk (:294-295,313-314) is reproduced.
+    """
+    c3_out, c2_out, s3, s2 = [], [], [], []
+    last3 = last2 = 0
+    for b in range(batch_size):
+        m3 = coord_3d[:, 0] == b
+        m2 = coord_2d[:, 0] == b
+        bc3 = coord_3d[m3][:, 1:]
+        bc2 = coord_2d[m2][:, 1:]
+        k3, k2 = float_key(bc3), float_key(bc2)
+        i3 = np.argsort(k3, kind='stable')
+        i2 = np.argsort(k2, kind='stable')
+        t3, t2 = type_assign(k3[i3], k2[i2])
+        s3.append(i3[np.nonzero(t3)[0]] + last3)
+        s2.append(i2[np.nonzero(t2)[0]] + last2)
+        mix3 = np.zeros(bc3.shape[0], np.int32)
+        mix2 = np.zeros(bc2.shape[0], np.int32)
+        mix3[i3] = t3.astype(np.int32)
+        mix2[i2] = t2.astype(np.int32)
+        c3_out.append(np.concatenate([np.full((bc3.shape[0], 1), b, np.int32), mix3[:, None], bc3], 1))
+        c2_out.append(np.concatenate([np.full((bc2.shape[0], 1), b, np.int32), mix2[:, None], bc2], 1))
+        last3, last2 = bc3.shape[0], bc2.shape[0]
+    return (np.concatenate(c3_out, 0).astype(np.int32), np.concatenate(c2_out, 0).astype(np.int32),
+            np.concatenate(s3, 0).astype(np.int64), np.concatenate(s2, 0).astype(np.int64))
+
+
+# --------------------------------------------------------------------------------------
+# a9: get_foreground2D gather + gate  (MSMDFusion.py:169-238)
+# --------------------------------------------------------------------------------------
+def lift_gather(img_feat, fg_pixels, fg_points, lidar2img, score_w, score_b, input_w):
+    """One camera.  img_feat (C,h,w) f32; fg_pixels (M,3) f32 (u,v,depth) in network-input
+    pixels; fg_points (M,15) f32; lidar2img (4,4) f64; score_net Linear(C+17 -> 1).
+    Returns (M, 15 + C) f32 with the feature part multiplied by the ReLU gate."""
+    C, h, w = img_feat.shape
+    downscale = w / input_w                       # :181  python float
+    pix = fg_pixels * downscale                   # :207  float32 array * python float
+    pix_l = pix.astype(np.int64)                  # :208  .long() truncates toward 0
+    cw, ch = pix_l[:, 0], pix_l[:, 1]
+    feat = img_feat.transpose(1, 2, 0)[ch, cw]    # :212
+    depth = fg_pixels[:, 2:3].astype(np.float32)
+    trans = np.repeat(lidar2img.reshape(1, 16).astype(np.float32), feat.shape[0], 0)  # :205,216
+    score_in = np.concatenate([feat, depth, trans], 1).astype(np.float32)
+    score = np.maximum(score_in @ score_w.reshape(-1, 1).astype(np.float32) + np.float32(score_b), 0)
+    return np.concatenate([fg_points.astype(np.float32), feat * score], 1).astype(np.float32)
