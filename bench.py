@@ -1,0 +1,332 @@
+#!/usr/bin/env python
+"""bench.py -- scenes/s of the MSMDFusion voxel-space hot path on B200 (contract: see DESIGN.md).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--profile S|L]
+
+A "step" is one pass of the hot path over one synthetic nuScenes-shaped scene:
+  hard_voxelize (+fused HardSimpleVFE mean) -> SparseEncoder (21 sparse convs, BN, ReLU)
+  -> dense()  ==  the LiDAR branch of transfusion_nusc_voxel_L / MSMDFusion_nusc_voxel_LC
+(BASELINE.json configs[1]).  One scene per GPU, no data-path collective (weak scaling).
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = 'nuScenes-shape scenes/sec forward (LiDAR voxel hot path: hard_voxelize+VFE+SparseEncoder+dense)'
+UNIT = 'scenes/s'
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--profile', default='S', choices=['S', 'L'],
+                    help='S: single 32-beam sweep (~30 k points); L: 10 sweeps (~285 k points)')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d['hbm_gbs']), float(d.get('bf16_tflops', 1590.0)), 'measured'
+    return 6650.0, 1590.0, 'fallback'
+
+
+def workload_name(profile):
+    return ('transfusion_nusc_voxel_L LiDAR hot path, synthetic %s scene'
+            % ('30k-pt single-sweep' if profile == 'S' else '285k-pt 10-sweep'))
+
+
+def hotpath_cfg():
+    from msmdfusion_b200 import Config
+    return Config.fromfile(os.path.join(ROOT, 'configs', 'msmd_lc_hotpath.py')).hotpath
+
+
+# ------------------------------------------------------------------------------------------
+# clocks sampler (nvidia-smi in the background during the timed region)
+# ------------------------------------------------------------------------------------------
+class Clocks:
+    Q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q, '--format=csv,noheader,nounits',
+                 '-lms', '100'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(',')]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, f[2:6]):
+                if val.lower().startswith('active'):
+                    reasons.add(nm)
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+# ------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------
+def build_pipeline(device):
+    import msmdfusion_b200 as m
+    from msmdfusion_b200 import registry
+    cfg = hotpath_cfg()
+    torch.manual_seed(0)
+    enc = registry.build_middle_encoder(cfg.pts_middle_encoder).to(device).eval()
+    layer = m.Voxelization(**cfg.pts_voxel_layer).eval()
+    return cfg, layer, enc
+
+
+def conv_layer_bytes_flops(records):
+    """Algorithmic bytes / flops of each sparse-conv launch:
+    bytes = 4*(N_in*Cin + N_out*Cout + K*Cin*Cout) + 4*K*N_out ; flops = 2*P*Cin*Cout."""
+    tot_b = tot_f = 0.0
+    for r in records:
+        tot_b += 4.0 * (r['n_in'] * r['cin'] + r['n_out'] * r['cout'] + r['kvol'] * r['cin'] * r['cout']) \
+            + 4.0 * r['kvol'] * r['n_out'] + (4.0 * r['n_out'] * r['cout'] if r['residual'] else 0.0)
+        tot_f += 2.0 * r['pairs'] * r['cin'] * r['cout']
+    return tot_b, tot_f
+
+
+def run_ours(args, rank, world, device):
+    import torch.distributed as dist
+    from msmdfusion_b200 import _cabi, ops, synthetic
+    cfg, layer, enc = build_pipeline(device)
+    pts_np = synthetic.lidar_scene(seed=rank, sweeps=1 if args.profile == 'S' else 10)
+    pts_host = torch.from_numpy(pts_np).pin_memory()
+    pts_dev = pts_host.to(device)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)  # > 126 MB L2
+
+    def step(points):
+        with torch.no_grad():
+            mean, coors, _ = layer.forward_mean(points, 5, batch_idx=0)
+            spatial, feats = enc(mean, coors, 1)
+        return spatial, feats
+
+    def sync_all():
+        torch.cuda.synchronize(device)
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize(device)
+
+    for _ in range(max(args.warmup, 3)):
+        step(pts_dev)
+    sync_all()
+
+    # ---- device-resident timing: K steps, L2 flushed between steps, CUDA events per step ----
+    clocks = Clocks(torch.cuda.current_device())
+    clocks.start()
+    launches0 = _cabi.lib().msmd_launch_count()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    sync_all()
+    for s, e in ev:
+        flush.zero_()
+        s.record()
+        spatial, feats = step(pts_dev)
+        e.record()
+    sync_all()
+    launches = _cabi.lib().msmd_launch_count() - launches0
+    dev_ms = sum(s.elapsed_time(e) for s, e in ev)
+
+    # ---- end to end: pinned host points -> H2D -> hot path -> D2H of a result checksum ----
+    ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    checksum = 0.0
+    sync_all()
+    for s, e in ev2:
+        flush.zero_()
+        s.record()
+        p = pts_host.to(device, non_blocking=True)
+        spatial, feats = step(p)
+        checksum = float(spatial.sum().item())  # device -> host read of the step result
+        e.record()
+    sync_all()
+    clk = clocks.stop()
+    e2e_ms = sum(s.elapsed_time(e) for s, e in ev2)
+
+    t = torch.tensor([dev_ms, e2e_ms], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_ms = float(t[0]), float(t[1])
+
+    # ---- per-kernel timing of the dominant kernel (sparse conv), live, CUDA events ----
+    roof = None
+    if rank == 0:
+        ops.PROFILE = []
+        for _ in range(3):
+            flush.zero_()
+            step(pts_dev)
+        torch.cuda.synchronize(device)
+        recs = ops.PROFILE
+        ops.PROFILE = None
+        for r in recs:
+            r['ms'] = r['start'].elapsed_time(r['end'])
+            r['pairs'] = int((r.pop('pair') >= 0).sum().item())
+        conv = [r for r in recs if r['op'] == 'spconv_fwd']
+        b, f = conv_layer_bytes_flops(conv)
+        conv_ms = sum(r['ms'] for r in conv)
+        hbm, bf16, src = peaks()
+        gbs = b / (conv_ms * 1e-3) / 1e9 if conv_ms else 0.0
+        roof = {'bound': 'hbm', 'achieved': round(gbs, 2), 'peak': hbm, 'unit': 'GB/s',
+                'frac': round(gbs / hbm, 4), 'traffic': None, 'peak_source': src,
+                'kernel': 'spconv_fwd_simt_kernel (21 launches/scene, summed)',
+                'kernel_ms_per_step': round(conv_ms / 3, 4),
+                'algorithmic_bytes_per_step': b / 3, 'algorithmic_flops_per_step': f / 3,
+                'achieved_tflops': round(f / (conv_ms * 1e-3) / 1e12, 3) if conv_ms else 0.0,
+                'note': 'fp32 FFMA path; the C>=64 layers are FFMA-bound, not HBM-bound (DESIGN.md)'}
+    n_vox = int(feats[0].indices.shape[0])
+    return dict(dev_ms=dev_ms, e2e_ms=e2e_ms, launches=int(launches), clocks=clk, roofline=roof,
+                points=int(pts_np.shape[0]), voxels=n_vox, checksum=checksum,
+                h2d=int(pts_np.nbytes), d2h=4)
+
+
+# ------------------------------------------------------------------------------------------
+# CPU arm: the reference's own CPU hard_voxelize (oracle/_ref, compiled from the reference
+# sources) + the oracle port of the un-vendored spconv-2.x arithmetic, all host threads.
+# ------------------------------------------------------------------------------------------
+def cpu_pass(profile, seed=0):
+    from msmdfusion_b200 import registry, synthetic
+    from oracle import build as obuild
+    from oracle import cpu
+    from oracle import model as omodel
+    cfg = hotpath_cfg()
+    torch.manual_seed(0)
+    enc = registry.build_middle_encoder(cfg.pts_middle_encoder).eval()  # weights only (host tensors)
+    sd = {k: v.numpy() for k, v in enc.state_dict().items()}
+    pts = synthetic.lidar_scene(seed=seed, sweeps=1 if profile == 'S' else 10)
+    use_ref = obuild.ref_so_path() is not None
+    vox = cpu.hard_voxelize_ref if use_ref else cpu.hard_voxelize
+
+    def one():
+        t0 = time.perf_counter()
+        v, c, n = vox(pts, synthetic.VOXEL_SIZE, synthetic.POINT_CLOUD_RANGE, 10, 160000)
+        t1 = time.perf_counter()
+        mean = cpu.hard_simple_vfe(v, n, 5)
+        coors = np.concatenate([np.zeros((c.shape[0], 1), np.int32), c], 1)
+        omodel.sparse_encoder(sd, dict(cfg.pts_middle_encoder), mean, coors, 1)
+        return time.perf_counter() - t0, t1 - t0
+
+    kind = 'reference' if use_ref else 'port'
+    desc = ('hard_voxelize = %s; spconv-2.x SparseEncoder arithmetic = oracle/c port (spconv is not '
+            'vendored in the reference), OpenMP' % ('reference CPU op (oracle/_ref)' if use_ref else 'oracle port'))
+    return one, cpu.num_threads(), kind, desc, int(pts.shape[0])
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get('RANK', 0))
+    local_rank = int(os.environ.get('LOCAL_RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+
+    if args.impl == 'reference':
+        if rank != 0:
+            return 0
+        one, cores, kind, desc, npts = cpu_pass(args.profile)
+        for _ in range(min(args.warmup, 1)):
+            one()
+        times = [one()[0] for _ in range(max(1, min(args.steps, 8)))]
+        val = 1.0 / float(np.mean(times))
+        line = {'impl': 'reference', 'metric': METRIC, 'value': val, 'unit': UNIT, 'n_gpus': args.gpus,
+                'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 / val,
+                'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+                'data': 'synthetic',
+                'config': {'workload': workload_name(args.profile), 'points': npts,
+                           'timed_steps': len(times)},
+                'cpu_baseline': {'value': val, 'unit': UNIT, 'cores': cores, 'kind': kind,
+                                 'sample': '%d whole-scene passes; %s' % (len(times), desc)},
+                'e2e': {'value': val, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+        print(json.dumps(line))
+        return 0
+
+    if not torch.cuda.is_available():
+        print(json.dumps({'error': 'bench.py needs a CUDA device; msmdfusion_b200 has no CPU fallback'}))
+        return 1
+    import torch.distributed as dist
+    device = torch.device('cuda', local_rank)
+    torch.cuda.set_device(device)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=device)
+    res = run_ours(args, rank, world, device)
+
+    cpu_base = None
+    if rank == 0 and not args.no_cpu_baseline:
+        one, cores, kind, desc, _ = cpu_pass(args.profile)
+        one()
+        tt = [one() for _ in range(2 if args.profile == 'S' else 1)]
+        cpu_base = {'value': 1.0 / float(np.mean([t[0] for t in tt])), 'unit': UNIT, 'cores': cores,
+                    'kind': kind, 'sample': '%d whole-scene passes of the same workload; %s; '
+                    'voxelize leg alone %.1f ms on 1 core' % (len(tt), desc, 1e3 * np.mean([t[1] for t in tt]))}
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank != 0:
+        return 0
+    K = args.steps
+    value = world * K / (res['dev_ms'] * 1e-3)
+    line = {
+        'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': K, 'warmup': max(args.warmup, 3),
+        'ms_per_step': res['dev_ms'] / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': workload_name(args.profile), 'points_per_scene': res['points'],
+                   'voxels_per_scene': res['voxels'], 'scenes_per_gpu_per_step': 1, 'parallelism': 'dp%d' % world,
+                   'l2': 'flushed between steps (256 MiB memset, outside the per-step events)',
+                   'weights': 'random init (spconv default), BN eval'},
+        'e2e': {'value': world * K / (res['e2e_ms'] * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': res['h2d'],
+                'd2h_bytes_per_step': res['d2h'],
+                'note': 'pinned host points -> H2D -> Voxelization.forward_mean -> SparseEncoder -> '
+                        'checksum of spatial_features read back'},
+        'gpu_launches': res['launches'],
+        'clocks': res['clocks'],
+        'roofline': res['roofline'],
+        'cpu_baseline': cpu_base,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+if __name__ == '__main__':
+    sys.exit(main())

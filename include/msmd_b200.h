@@ -47,6 +47,8 @@ typedef void* msmd_stream_t; /* cudaStream_t */
 
 MSMD_API const char* msmd_last_error(void);
 MSMD_API int msmd_abi_version(void);
+/* number of CUDA kernels this library has launched in this process (bench.py's gpu_launches) */
+MSMD_API unsigned long long msmd_launch_count(void);
 
 /* ------------------------------------------------------------------------------------
  * hard_voxelize (+ fused HardSimpleVFE mean)

@@ -1,0 +1,16 @@
+"""msmdfusion_b200 -- B200-native (sm_100a) implementation of MSMDFusion's voxel-space fusion
+hot path behind the reference's mmdet3d registry / spconv operator surface.
+
+Layout: ``csrc/`` hand-written CUDA + the C ABI (include/msmd_b200.h); ``_cabi.py`` ctypes
+binding; ``ops.py`` tensor-level wrappers; the remaining modules mirror the reference's
+Python interface for this path.  There is no CPU fallback.
+"""
+from . import registry  # noqa: F401
+from .registry import (CONV_LAYERS, DETECTORS, FUSION_LAYERS, MIDDLE_ENCODERS,  # noqa: F401
+                       VOXEL_ENCODERS, Config, build_from_cfg)
+from . import spconv  # noqa: F401
+from .sparse_block import SparseBasicBlock, make_sparse_convmodule  # noqa: F401
+from .sparse_encoder import SparseEncoder  # noqa: F401
+from .voxel import HardSimpleVFE, Voxelization, hard_voxelize, voxelization  # noqa: F401
+
+__version__ = '0.1.0'

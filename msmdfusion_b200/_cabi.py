@@ -1,0 +1,109 @@
+"""ctypes binding of libmsmd_b200.so (the C ABI declared in include/msmd_b200.h).
+
+This is the only place the product touches native code.  There is no CPU fallback: if
+the shared library is missing or an entry point fails, a RuntimeError is raised.
+PyTorch is used for device memory and streams only.
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, '_C', 'libmsmd_b200.so')
+
+_c_int_p = ctypes.POINTER(ctypes.c_int)
+_c_float_p = ctypes.POINTER(ctypes.c_float)
+_vp = ctypes.c_void_p
+_i = ctypes.c_int
+_sz = ctypes.c_size_t
+
+# name -> (restype, argtypes).  Device pointers travel as void*; host arrays as int*/float*.
+SIGNATURES = {
+    'msmd_last_error': (ctypes.c_char_p, []),
+    'msmd_abi_version': (_i, []),
+    'msmd_launch_count': (ctypes.c_ulonglong, []),
+    'msmd_hard_voxelize_workspace': (_sz, [_i]),
+    'msmd_hard_voxelize': (_i, [_vp, _i, _i, _c_float_p, _c_float_p, _i, _i, _vp, _vp, _i, _i, _vp,
+                                _vp, _i, _vp, _vp, _sz, _vp]),
+    'msmd_grid_num_words': (_sz, [_i, _c_int_p]),
+    'msmd_scan_workspace': (_sz, []),
+    'msmd_grid_build': (_i, [_vp, _i, _i, _c_int_p, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    'msmd_rulebook_subm': (_i, [_vp, _i, _i, _c_int_p, _c_int_p, _c_int_p, _vp, _vp, _vp, _vp, _vp]),
+    'msmd_conv_out_shape': (_i, [_c_int_p] * 6),
+    'msmd_rulebook_conv_outputs': (_i, [_vp, _i, _i, _c_int_p, _c_int_p, _c_int_p, _c_int_p,
+                                        _c_int_p, _vp, _vp, _vp, _vp, _sz, _vp]),
+    'msmd_rulebook_conv_pairs': (_i, [_vp, _vp, _i, _i, _c_int_p, _c_int_p, _c_int_p, _c_int_p,
+                                      _c_int_p, _vp, _vp, _vp, _vp, _vp, _vp]),
+    'msmd_spconv_pack_weight': (_i, [_vp, _i, _i, _i, _vp, _vp]),
+    'msmd_spconv_fwd': (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _vp]),
+    'msmd_to_dense': (_i, [_vp, _vp, _i, _i, _i, _c_int_p, _vp, _vp]),
+}
+
+_LIB = None
+
+
+def lib():
+    """Load the shared library (once).  Fails loudly when it has not been built."""
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f'{LIB_PATH} is missing: build it with `python -m msmdfusion_b200.build` '
+                '(or __graft_entry__.build()).  msmdfusion_b200 has no CPU fallback.')
+        L = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        if L.msmd_abi_version() != 1:
+            raise RuntimeError('libmsmd_b200.so ABI version mismatch')
+        _LIB = L
+    return _LIB
+
+
+def check(status, what):
+    if status != 0:
+        msg = lib().msmd_last_error().decode(errors='replace')
+        raise RuntimeError(f'{what} failed ({status}): {msg}')
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL).  The tensor must be contiguous CUDA memory."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError('msmdfusion_b200 ops need CUDA tensors (there is no CPU fallback)')
+    if not t.is_contiguous():
+        raise RuntimeError('msmdfusion_b200 ops need contiguous tensors')
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def stream(device=None):
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def ints(vals):
+    return (ctypes.c_int * len(vals))(*[int(v) for v in vals])
+
+
+def floats(vals):
+    return (ctypes.c_float * len(vals))(*[float(v) for v in vals])
+
+
+class _Scratch:
+    """Per-device grow-only scratch buffers (stream-ordered reuse on the current stream)."""
+
+    def __init__(self):
+        self.buf = {}
+
+    def get(self, device, nbytes, slot='ws'):
+        key = (torch.device(device).index, slot)
+        b = self.buf.get(key)
+        if b is None or b.numel() < nbytes:
+            b = torch.empty(max(int(nbytes), 1 << 16), dtype=torch.uint8, device=device)
+            self.buf[key] = b
+        return b
+
+
+scratch = _Scratch()

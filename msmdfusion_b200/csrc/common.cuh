@@ -13,6 +13,7 @@ namespace msmd {
 // and leaves a message retrievable through msmd_last_error().
 // ---------------------------------------------------------------------------------
 void set_error(const char* fmt, ...);
+void count_launch(int n);  // bumps the counter msmd_launch_count() reports
 
 #define MSMD_CUDA_OK(expr)                                                              \
   do {                                                                                  \
@@ -32,7 +33,11 @@ void set_error(const char* fmt, ...);
     }                                                                                   \
   } while (0)
 
-#define MSMD_LAUNCH_OK() MSMD_CUDA_OK(cudaGetLastError())
+#define MSMD_LAUNCH_OK()                  \
+  do {                                    \
+    ::msmd::count_launch(1);              \
+    MSMD_CUDA_OK(cudaGetLastError());     \
+  } while (0)
 
 static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }

@@ -83,6 +83,7 @@ static inline cudaError_t device_exclusive_scan(F f, O o, int n, ScanTemp<T> tmp
   blocks = ceil_div(n, chunk);
   scan_reduce_kernel<T, F><<<blocks, kScanThreads, 0, stream>>>(f, n, chunk, tmp);
   scan_apply_kernel<T, F, O><<<blocks, kScanThreads, 0, stream>>>(f, o, n, chunk, tmp);
+  count_launch(2);
   return cudaGetLastError();
 }
 

@@ -1,0 +1,364 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same seeded
+inputs.  Bit-exact for voxel indices / rulebooks / copied points; fp32 features within 1e-4
+(the tolerance BASELINE.json's north_star states)."""
+import glob
+import os
+import zlib
+
+import numpy as np
+import pytest
+import torch
+
+import msmdfusion_b200 as m
+from msmdfusion_b200 import ops, registry, synthetic
+from oracle import cpu
+from oracle import model as omodel
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+FEAT_TOL = 1e-4
+
+
+def dev():
+    return torch.device('cuda:0')
+
+
+def cuda(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(dev())
+
+
+def run_voxelize(pts, vs, rng, max_points, max_voxels, mean_features=0):
+    v, c, n, mean = ops.hard_voxelize(cuda(pts), vs, rng, max_points, max_voxels, want_voxels=True,
+                                      mean_features=mean_features)
+    torch.cuda.synchronize()
+    return v.cpu().numpy(), c.cpu().numpy(), n.cpu().numpy(), (mean.cpu().numpy() if mean is not None else None)
+
+
+VOX_CASES = [
+    # (name, points fn, voxel_size, range, max_points, max_voxels)
+    ('cfg1_1k', lambda: synthetic.random_points(1000, 5, seed=0), synthetic.VOXEL_SIZE,
+     synthetic.POINT_CLOUD_RANGE, 10, 160000),
+    ('sweep_s', lambda: synthetic.lidar_scene(0, 1), synthetic.VOXEL_SIZE, synthetic.POINT_CLOUD_RANGE, 10, 160000),
+    ('sweep_s_train_cap', lambda: synthetic.lidar_scene(1, 1), synthetic.VOXEL_SIZE,
+     synthetic.POINT_CLOUD_RANGE, 10, 120000),
+    ('overflow', lambda: synthetic.lidar_scene(2, 1), synthetic.VOXEL_SIZE, synthetic.POINT_CLOUD_RANGE, 10, 5000),
+    ('overflow_tiny', lambda: synthetic.lidar_scene(2, 1)[:4000], synthetic.VOXEL_SIZE,
+     synthetic.POINT_CLOUD_RANGE, 2, 7),
+    ('dense_voxels', lambda: synthetic.random_points(20000, 4, seed=3, pc_range=[0, 0, 0, 4, 4, 2]),
+     [0.5, 0.5, 0.5], [0, 0, 0, 4, 4, 2], 10, 20000),
+    ('max_points_1', lambda: synthetic.random_points(5000, 5, seed=4, pc_range=[0, 0, 0, 4, 4, 2]),
+     [0.5, 0.5, 0.5], [0, 0, 0, 4, 4, 2], 1, 20000),
+    ('max_points_1000', lambda: np.random.RandomState(0).rand(1000, 4).astype(np.float32),
+     [0.5, 0.5, 0.5], [0, -40, -3, 70.4, 40, 1], 1000, 20000),
+    ('virtual_c64_x2', lambda: synthetic.random_points(30000, 64, seed=5), [0.15, 0.15, 0.4],
+     synthetic.POINT_CLOUD_RANGE, 10, 160000),
+    ('virtual_c64_x8', lambda: synthetic.random_points(30000, 64, seed=6), [0.6, 0.6, 1.6],
+     synthetic.POINT_CLOUD_RANGE, 10, 160000),
+    ('all_outside', lambda: synthetic.random_points(500, 5, seed=7) + 1000.0, synthetic.VOXEL_SIZE,
+     synthetic.POINT_CLOUD_RANGE, 10, 160000),
+    ('single_point', lambda: np.array([[0.1, 0.2, 0.3, 1, 0]], np.float32), synthetic.VOXEL_SIZE,
+     synthetic.POINT_CLOUD_RANGE, 10, 160000),
+    ('zeros_100', lambda: np.zeros((100, 64), np.float32), synthetic.VOXEL_SIZE,
+     synthetic.POINT_CLOUD_RANGE, 10, 160000),  # MSMDFusion.py:376-380 empty-sample padding
+    ('nan_inf', lambda: np.array([[np.nan, 0, 0, 1, 0], [np.inf, 0, 0, 1, 0], [0, -np.inf, 0, 1, 0],
+                                  [1, 1, 1, 1, 0], [1e30, 1, 1, 1, 0]], np.float32), synthetic.VOXEL_SIZE,
+     synthetic.POINT_CLOUD_RANGE, 10, 160000),
+]
+
+
+@pytest.mark.parametrize('case', VOX_CASES, ids=[c[0] for c in VOX_CASES])
+def test_hard_voxelize_bit_exact(case):
+    _, fn, vs, rng, mp, mv = case
+    pts = fn()
+    ev, ec, en = cpu.hard_voxelize(pts, vs, rng, mp, mv)
+    F = min(pts.shape[1], 64)
+    gv, gc, gn, gmean = run_voxelize(pts, vs, rng, mp, mv, mean_features=F)
+    assert gc.shape == ec.shape, f'voxel_num {gc.shape[0]} != {ec.shape[0]}'
+    assert np.array_equal(gc, ec)
+    assert np.array_equal(gn, en)
+    assert np.array_equal(gv, ev)  # copied rows and zero padding, bit for bit
+    if ec.shape[0]:
+        emean = cpu.hard_simple_vfe(ev, en, F)
+        assert np.allclose(gmean, emean, rtol=1e-6, atol=1e-6)
+
+
+def test_hard_voxelize_empty_input():
+    pts = np.zeros((0, 5), np.float32)
+    gv, gc, gn, _ = run_voxelize(pts, synthetic.VOXEL_SIZE, synthetic.POINT_CLOUD_RANGE, 10, 100)
+    assert gv.shape == (0, 10, 5) and gc.shape == (0, 3) and gn.shape == (0,)
+
+
+@pytest.mark.parametrize('path', sorted(glob.glob(os.path.join(GOLDEN, 'voxelize_*.npz'))), ids=os.path.basename)
+def test_hard_voxelize_reference_golden(path):
+    """Fixtures produced by the reference's own CPU op (tests/golden/make_golden.py)."""
+    from test_oracle import golden_points
+    g = np.load(path)
+    pts = golden_points(path)
+    gv, gc, gn, _ = run_voxelize(pts, g['voxel_size'], g['coors_range'], int(g['max_points']),
+                                 int(g['max_voxels']))
+    assert np.array_equal(gc, g['coors'].astype(np.int32))
+    assert np.array_equal(gn, g['num_points'].astype(np.int32))
+    assert np.uint32(zlib.crc32(np.ascontiguousarray(gv).tobytes())) == g['voxels_crc']
+
+
+def test_voxelization_module_and_dropin_function():
+    pts = synthetic.lidar_scene(5, 1)
+    layer = m.Voxelization(synthetic.VOXEL_SIZE, synthetic.POINT_CLOUD_RANGE, 10, (120000, 160000)).eval()
+    v, c, n = layer(cuda(pts))
+    ev, ec, en = cpu.hard_voxelize(pts, synthetic.VOXEL_SIZE, synthetic.POINT_CLOUD_RANGE, 10, 160000)
+    assert np.array_equal(c.cpu().numpy(), ec) and np.array_equal(n.cpu().numpy(), en)
+    assert np.array_equal(v.cpu().numpy(), ev)
+    # reference-style call with caller-allocated zeroed buffers (voxelization.h:61-78)
+    p = cuda(pts)
+    voxels = p.new_zeros((160000, 10, 5))
+    coors = p.new_zeros((160000, 3), dtype=torch.int)
+    num = p.new_zeros((160000,), dtype=torch.int)
+    k = m.hard_voxelize(p, voxels, coors, num, synthetic.VOXEL_SIZE, synthetic.POINT_CLOUD_RANGE, 10, 160000, 3)
+    assert k == ec.shape[0]
+    assert np.array_equal(coors[:k].cpu().numpy(), ec) and int(num[k:].abs().sum()) == 0
+    # fused mean path
+    mean, c4, n2 = layer.forward_mean(p, 5, batch_idx=3)
+    assert np.array_equal(c4[:, 1:].cpu().numpy(), ec) and int((c4[:, 0] != 3).sum()) == 0
+    assert np.allclose(mean.cpu().numpy(), cpu.hard_simple_vfe(ev, en, 5), rtol=1e-6, atol=1e-6)
+
+
+def test_hard_voxelize_full_size_properties():
+    """Profile L (10 sweeps, ~285 k points): size-independent properties + the oracle."""
+    pts = synthetic.lidar_scene(7, 10)
+    gv, gc, gn, _ = run_voxelize(pts, synthetic.VOXEL_SIZE, synthetic.POINT_CLOUD_RANGE, 10, 160000)
+    lin = (gc[:, 0].astype(np.int64) * 1440 + gc[:, 1]) * 1440 + gc[:, 2]
+    assert np.unique(lin).shape[0] == lin.shape[0]            # coordinates unique
+    assert gn.min() >= 1 and gn.max() <= 10
+    for j in range(10):                                        # zero padding beyond num_points
+        assert np.all(gv[gn <= j, j] == 0)
+    ev, ec, en = cpu.hard_voxelize(pts, synthetic.VOXEL_SIZE, synthetic.POINT_CLOUD_RANGE, 10, 160000)
+    assert np.array_equal(gc, ec) and np.array_equal(gn, en) and np.array_equal(gv, ev)
+
+
+# ----------------------------------------------------------------------------------------------
+# rulebooks
+# ----------------------------------------------------------------------------------------------
+def scene_indices(seed=0, sweeps=1, batch=1):
+    idx = []
+    for b in range(batch):
+        pts = synthetic.lidar_scene(seed + b, sweeps)
+        _, c, _ = cpu.hard_voxelize(pts, synthetic.VOXEL_SIZE, synthetic.POINT_CLOUD_RANGE, 10, 160000)
+        idx.append(np.concatenate([np.full((c.shape[0], 1), b, np.int32), c], 1))
+    return np.concatenate(idx, 0)
+
+
+def random_indices(rng, batch, shape, n):
+    D, H, W = shape
+    lin = rng.choice(batch * D * H * W, size=n, replace=False)
+    rng.shuffle(lin)
+    return np.stack([lin // (D * H * W), (lin // (H * W)) % D, (lin // W) % H, lin % W], 1).astype(np.int32)
+
+
+SUBM_CASES = [([7, 12, 10], 2, 300, 3, 1), ([7, 12, 10], 1, 500, (3, 1, 1), 1), ([9, 33, 65], 3, 4000, 3, 2),
+              ([5, 31, 37], 2, 1500, (1, 3, 3), 1), ([41, 100, 100], 1, 20000, 3, 1)]
+
+
+@pytest.mark.parametrize('shape,batch,n,ksize,dil', SUBM_CASES)
+def test_subm_rulebook_bit_exact(shape, batch, n, ksize, dil):
+    idx = random_indices(np.random.default_rng(n), batch, shape, n)
+    grid = ops.grid_build(cuda(idx), batch, shape, need_perm=True)
+    pair = ops.rulebook_subm(cuda(idx), grid, ksize, dil).cpu().numpy()
+    assert int(grid.num_active.item()) == n
+    assert np.array_equal(pair, cpu.subm_rulebook(idx, shape, ksize, dil))
+
+
+def test_subm_rulebook_scene_bit_exact():
+    idx = scene_indices(0, 1, batch=2)
+    shape = [41, 1440, 1440]
+    grid = ops.grid_build(cuda(idx), 2, shape)
+    pair = ops.rulebook_subm(cuda(idx), grid, 3, 1).cpu().numpy()
+    assert np.array_equal(pair, cpu.subm_rulebook(idx, shape, 3, 1))
+
+
+def test_subm_duplicate_coordinates_largest_row_wins():
+    idx = np.array([[0, 1, 1, 1], [0, 1, 1, 2], [0, 1, 1, 1], [0, 2, 2, 2]], np.int32)
+    grid = ops.grid_build(cuda(idx), 1, [4, 4, 4])
+    pair = ops.rulebook_subm(cuda(idx), grid, 3, 1).cpu().numpy()
+    assert np.array_equal(pair, cpu.subm_rulebook(idx, [4, 4, 4], 3, 1))
+    assert pair[13, 0] == 2 and pair[13, 2] == 2
+
+
+CONV_CASES = [([9, 14, 11], 2, 400, 3, 2, 1), ([9, 14, 11], 2, 400, 3, 2, (0, 1, 1)),
+              ([5, 18, 18], 2, 600, (3, 1, 1), (2, 1, 1), 0), ([8, 16, 12], 1, 300, 2, 2, 0),
+              ([9, 14, 11], 1, 200, 3, 1, 0), ([9, 14, 11], 3, 700, 3, (1, 2, 3), (1, 0, 2)),
+              ([41, 128, 160], 2, 30000, 3, 2, 1)]
+
+
+@pytest.mark.parametrize('shape,batch,n,ksize,stride,pad', CONV_CASES)
+def test_conv_rulebook_bit_exact(shape, batch, n, ksize, stride, pad):
+    idx = random_indices(np.random.default_rng(n + 1), batch, shape, n)
+    grid = ops.grid_build(cuda(idx), batch, shape)
+    out_idx, pair, out_grid = ops.rulebook_conv(cuda(idx), grid, ksize, stride, pad, 1)
+    e_idx, e_pair, e_shape = cpu.conv_rulebook(idx, shape, ksize, stride, pad, 1)
+    assert out_grid.spatial_shape == e_shape
+    assert np.array_equal(out_idx.cpu().numpy(), e_idx)
+    assert np.array_equal(pair.cpu().numpy(), e_pair)
+    # the output grid is directly usable for the next level (rank == row, no perm)
+    pair2 = ops.rulebook_subm(out_idx, out_grid, 3, 1).cpu().numpy()
+    assert np.array_equal(pair2, cpu.subm_rulebook(e_idx, e_shape, 3, 1))
+
+
+def test_conv_rulebook_scene_chain_bit_exact():
+    """The three strided levels + conv_out of the LiDAR backbone on a real-shaped scene."""
+    idx = scene_indices(1, 1, batch=1)
+    shape = [41, 1440, 1440]
+    g_idx, g_grid = cuda(idx), None
+    g_grid = ops.grid_build(g_idx, 1, shape)
+    e_idx, e_shape = idx, shape
+    for ks, st, pd in ((3, 2, 1), (3, 2, 1), (3, 2, (0, 1, 1)), ((3, 1, 1), (2, 1, 1), 0)):
+        g_idx, g_pair, g_grid = ops.rulebook_conv(g_idx, g_grid, ks, st, pd, 1)
+        e_idx, e_pair, e_shape = cpu.conv_rulebook(e_idx, e_shape, ks, st, pd, 1)
+        assert g_grid.spatial_shape == e_shape
+        assert np.array_equal(g_idx.cpu().numpy(), e_idx)
+        assert np.array_equal(g_pair.cpu().numpy(), e_pair)
+    assert e_shape == [2, 180, 180]
+
+
+# ----------------------------------------------------------------------------------------------
+# sparse conv forward
+# ----------------------------------------------------------------------------------------------
+CH_CASES = [(5, 16), (16, 16), (16, 32), (32, 32), (32, 64), (64, 64), (64, 128), (128, 128), (80, 80),
+            (96, 128), (192, 192), (3, 7), (20, 36)]
+
+
+@pytest.mark.parametrize('cin,cout', CH_CASES)
+def test_spconv_fwd_matches_oracle(cin, cout):
+    rng = np.random.default_rng(cin * 1000 + cout)
+    shape, batch, n = [9, 40, 40], 2, 3000
+    idx = random_indices(rng, batch, shape, n)
+    feat = rng.standard_normal((n, cin)).astype(np.float32)
+    w = (rng.standard_normal((cout, 3, 3, 3, cin)) / np.sqrt(27 * cin)).astype(np.float32)
+    pair = cpu.subm_rulebook(idx, shape, 3, 1)
+    expect = cpu.spconv_fwd(feat, w, pair)
+    packed = ops.pack_weight(cuda(w))
+    got = ops.spconv_fwd(cuda(feat), packed, cuda(pair)).cpu().numpy()
+    assert np.abs(got - expect).max() < FEAT_TOL
+    # fused epilogue: BN scale/shift + residual + ReLU
+    scale = rng.uniform(0.5, 1.5, cout).astype(np.float32)
+    shift = rng.standard_normal(cout).astype(np.float32)
+    res = rng.standard_normal((n, cout)).astype(np.float32)
+    got = ops.spconv_fwd(cuda(feat), packed, cuda(pair), cuda(scale), cuda(shift), cuda(res), True).cpu().numpy()
+    assert np.abs(got - np.maximum(expect * scale + shift + res, 0)).max() < FEAT_TOL
+
+
+def test_spconv_fwd_strided_and_large_tile_path():
+    """Enough output rows to take the tall-tile (RM=8) launch + a strided rulebook."""
+    rng = np.random.default_rng(9)
+    shape, batch, n = [21, 200, 200], 1, 90000
+    idx = random_indices(rng, batch, shape, n)
+    feat = rng.standard_normal((n, 16)).astype(np.float32)
+    w = (rng.standard_normal((32, 3, 3, 3, 16)) / np.sqrt(27 * 16)).astype(np.float32)
+    e_idx, e_pair, _ = cpu.conv_rulebook(idx, shape, 3, 2, 1, 1)
+    expect = cpu.spconv_fwd(feat, w, e_pair)
+    got = ops.spconv_fwd(cuda(feat), ops.pack_weight(cuda(w)), cuda(e_pair)).cpu().numpy()
+    assert np.abs(got - expect).max() < FEAT_TOL
+    pair = cpu.subm_rulebook(idx, shape, 3, 1)
+    w2 = (rng.standard_normal((16, 3, 3, 3, 16)) / np.sqrt(27 * 16)).astype(np.float32)
+    got = ops.spconv_fwd(cuda(feat), ops.pack_weight(cuda(w2)), cuda(pair)).cpu().numpy()
+    assert np.abs(got - cpu.spconv_fwd(feat, w2, pair)).max() < FEAT_TOL
+
+
+def test_to_dense_matches_oracle():
+    rng = np.random.default_rng(4)
+    shape, batch, n = [2, 180, 180], 2, 5000
+    idx = random_indices(rng, batch, shape, n)
+    feat = rng.standard_normal((n, 128)).astype(np.float32)
+    got = ops.to_dense(cuda(idx), cuda(feat), shape, batch).cpu().numpy()
+    assert np.array_equal(got, cpu.dense(idx, feat, shape, batch))
+
+
+# ----------------------------------------------------------------------------------------------
+# module level: SubMConv3d / SparseConv3d / SparseBasicBlock / SparseEncoder
+# ----------------------------------------------------------------------------------------------
+def randomize_bn(module, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    for mod in module.modules():
+        if isinstance(mod, torch.nn.BatchNorm1d):
+            mod.weight.data = torch.rand(mod.weight.shape, generator=g) + 0.5
+            mod.bias.data = torch.randn(mod.bias.shape, generator=g) * 0.1
+            mod.running_mean.data = torch.randn(mod.running_mean.shape, generator=g) * 0.1
+            mod.running_var.data = torch.rand(mod.running_var.shape, generator=g) + 0.5
+
+
+def test_config1_voxelize_plus_one_subm():
+    """BASELINE.json configs[0]: hard_voxelize + one SubMConv3d(5->16,k3) on 1 k points."""
+    pts = synthetic.random_points(1000, 5, seed=0)
+    layer = m.Voxelization(synthetic.VOXEL_SIZE, synthetic.POINT_CLOUD_RANGE, 10, (120000, 160000)).eval()
+    mean, coors, num = layer.forward_mean(cuda(pts), 5, batch_idx=0)
+    torch.manual_seed(0)
+    conv = m.spconv.SubMConv3d(5, 16, 3, padding=1, bias=False, indice_key='subm1').to(dev())
+    x = m.spconv.SparseConvTensor(mean, coors, [41, 1440, 1440], 1)
+    with torch.no_grad():
+        y = conv(x)
+    ev, ec, en = cpu.hard_voxelize(pts, synthetic.VOXEL_SIZE, synthetic.POINT_CLOUD_RANGE, 10, 160000)
+    eidx = np.concatenate([np.zeros((ec.shape[0], 1), np.int32), ec], 1)
+    emean = cpu.hard_simple_vfe(ev, en, 5)
+    expect = cpu.spconv_fwd(emean, conv.weight.detach().cpu().numpy(), cpu.subm_rulebook(eidx, [41, 1440, 1440], 3, 1))
+    assert np.array_equal(y.indices.cpu().numpy(), eidx)
+    assert np.abs(y.features.cpu().numpy() - expect).max() < FEAT_TOL
+    assert y.find_indice_pair('subm1') is not None
+
+
+def test_basic_block_fused_equals_unfused_and_oracle():
+    rng = np.random.default_rng(12)
+    shape, n, c = [11, 60, 60], 6000, 64
+    idx = random_indices(rng, 1, shape, n)
+    feat = rng.standard_normal((n, c)).astype(np.float32)
+    torch.manual_seed(1)
+    blk = m.SparseBasicBlock(c, c, norm_cfg=dict(type='BN1d', eps=1e-3, momentum=0.01),
+                             conv_cfg=dict(type='SubMConv3d')).to(dev())
+    randomize_bn(blk, 2)
+    blk.eval()
+    x = m.spconv.SparseConvTensor(cuda(feat), cuda(idx), shape, 1)
+    with torch.no_grad():
+        fused = blk(x).features.cpu().numpy()
+        # unfused: the literal reference sequence (sparse_block.py:103-126)
+        out = blk.conv1(x)
+        out = out.replace_feature(torch.relu(blk.norm1(out.features)))
+        out = blk.conv2(out)
+        out = out.replace_feature(torch.relu(blk.norm2(out.features) + x.features))
+        unfused = out.features.cpu().numpy()
+    sd = {k: v.cpu() for k, v in blk.state_dict().items()}
+    expect = omodel.basic_block({'b.' + k: v for k, v in sd.items()}, 'b',
+                                omodel.SpTensor(feat, idx, shape, 1), 1e-3).features
+    assert np.abs(fused - unfused).max() < 1e-5
+    assert np.abs(fused - expect).max() < FEAT_TOL
+
+
+@pytest.mark.parametrize('batch', [1, 2])
+def test_sparse_encoder_end_to_end(batch):
+    """configs[1] slice at single-sweep size: voxelize -> VFE -> SparseEncoder -> dense vs oracle."""
+    cfg = m.Config.fromfile(os.path.join(ROOT, 'configs', 'msmd_lc_hotpath.py')).hotpath
+    torch.manual_seed(0)
+    enc = registry.build_middle_encoder(cfg.pts_middle_encoder).to(dev())
+    randomize_bn(enc, 3)
+    enc.eval()
+    layer = m.Voxelization(**cfg.pts_voxel_layer).eval()
+    scenes = [synthetic.lidar_scene(20 + b, 1) for b in range(batch)]
+    feats, coors = [], []
+    for b, pts in enumerate(scenes):
+        mean, c4, _ = layer.forward_mean(cuda(pts), 5, batch_idx=b)
+        feats.append(mean)
+        coors.append(c4)
+    with torch.no_grad():
+        spatial, encode_features = enc(torch.cat(feats), torch.cat(coors), batch)
+    torch.cuda.synchronize()
+    # oracle
+    ev, en, ec = omodel.voxelize_batch(scenes, synthetic.VOXEL_SIZE, synthetic.POINT_CLOUD_RANGE, 10, 160000)
+    emean = cpu.hard_simple_vfe(ev, en, 5)
+    sd = {k: v.cpu() for k, v in enc.state_dict().items()}
+    e_spatial, e_feats, _ = omodel.sparse_encoder(sd, dict(cfg.pts_middle_encoder), emean, ec, batch)
+    assert spatial.shape == (batch, 256, 180, 180)
+    assert len(encode_features) == 5
+    for g, e in zip(encode_features, e_feats):
+        assert g.spatial_shape == e.spatial_shape
+        assert np.array_equal(g.indices.cpu().numpy(), e.indices)          # bit-exact indices
+        assert np.abs(g.features.cpu().numpy() - e.features).max() < FEAT_TOL
+    assert np.abs(spatial.cpu().numpy() - e_spatial).max() < FEAT_TOL

@@ -1,0 +1,125 @@
+"""CPU tests of the host-side mirror: registries, config loading, module/state-dict layout,
+and that the C-ABI library loads and exports every symbol include/*.h declares.  No compute
+call is made (there is no GPU here)."""
+import ctypes
+import glob
+import os
+import re
+
+import pytest
+import torch
+
+import msmdfusion_b200 as m
+from msmdfusion_b200 import _cabi, registry
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    names = set()
+    for h in glob.glob(os.path.join(ROOT, 'include', '*.h')):
+        names |= set(re.findall(r'\b(msmd_[a-z0-9_]+)\s*\(', open(h).read()))
+    return sorted(names)
+
+
+def test_cabi_exports_every_declared_symbol():
+    from msmdfusion_b200 import build
+    build.build()
+    lib = ctypes.CDLL(_cabi.LIB_PATH)
+    syms = declared_symbols()
+    assert len(syms) >= 14
+    for s in syms:
+        assert hasattr(lib, s), f'{s} declared in include/ but not exported'
+        assert s in _cabi.SIGNATURES, f'{s} has no ctypes signature in _cabi.py'
+    assert set(_cabi.SIGNATURES) <= set(syms)
+    L = _cabi.lib()
+    assert L.msmd_abi_version() == 1
+    assert L.msmd_scan_workspace() > 0 and L.msmd_hard_voxelize_workspace(1000) > 0
+
+
+def test_no_cpu_fallback():
+    """Ops must refuse CPU tensors instead of silently computing elsewhere."""
+    from msmdfusion_b200 import ops
+    with pytest.raises(RuntimeError):
+        ops.hard_voxelize(torch.zeros(10, 5), [1, 1, 1], [0, 0, 0, 4, 4, 4], 5, 100)
+    with pytest.raises(RuntimeError):
+        m.hard_voxelize(torch.zeros(10, 5), None, None, None, [1, 1, 1], [0, 0, 0, 4, 4, 4], 5, 100)
+
+
+def test_product_never_imports_oracle():
+    for f in glob.glob(os.path.join(ROOT, 'msmdfusion_b200', '*.py')):
+        src = open(f).read()
+        assert not re.search(r'^\s*(from|import)\s+oracle\b', src, re.M), f
+        assert 'oracle.' not in src.replace('oracle/', ''), f
+
+
+def test_registries_and_builders():
+    assert 'HardSimpleVFE' in registry.VOXEL_ENCODERS
+    assert 'SparseEncoder' in registry.MIDDLE_ENCODERS
+    assert registry.FUSION_LAYERS.name == 'fusion_layer'
+    assert 'SubMConv3d' in registry.CONV_LAYERS and 'SparseConv3d' in registry.CONV_LAYERS
+    conv = registry.build_conv_layer(dict(type='SubMConv3d', indice_key='k'), 4, 8, 3, padding=1, bias=False)
+    assert tuple(conv.weight.shape) == (8, 3, 3, 3, 4) and conv.bias is None and conv.subm
+    conv = registry.build_conv_layer(dict(type='SparseConv3d', indice_key='d'), 4, 8, (3, 1, 1),
+                                     stride=(2, 1, 1), padding=0, bias=False)
+    assert tuple(conv.weight.shape) == (8, 3, 1, 1, 4) and not conv.subm
+    name, bn = registry.build_norm_layer(dict(type='BN1d', eps=1e-3, momentum=0.01), 8)
+    assert isinstance(bn, torch.nn.BatchNorm1d) and bn.eps == 1e-3 and name == 'bn'
+    with pytest.raises(KeyError):
+        registry.build_middle_encoder(dict(type='NoSuchEncoder'))
+
+
+def test_hotpath_config_builds_encoder_with_reference_state_dict_layout():
+    cfg = m.Config.fromfile(os.path.join(ROOT, 'configs', 'msmd_lc_hotpath.py'))
+    enc = registry.build_middle_encoder(cfg.hotpath.pts_middle_encoder)
+    sd = enc.state_dict()
+    # key layout + KRSC weight shapes
+    assert tuple(sd['conv_input.0.weight'].shape) == (16, 3, 3, 3, 5)
+    assert tuple(sd['encoder_layers.encoder_layer1.0.conv1.weight'].shape) == (16, 3, 3, 3, 16)
+    assert tuple(sd['encoder_layers.encoder_layer1.2.0.weight'].shape) == (32, 3, 3, 3, 16)
+    assert tuple(sd['encoder_layers.encoder_layer3.2.0.weight'].shape) == (128, 3, 3, 3, 64)
+    assert tuple(sd['encoder_layers.encoder_layer4.1.conv2.weight'].shape) == (128, 3, 3, 3, 128)
+    assert tuple(sd['conv_out.0.weight'].shape) == (128, 3, 1, 1, 128)
+    assert 'encoder_layers.encoder_layer2.1.bn2.running_var' in sd
+    n_conv = sum(1 for k in sd if k.endswith('weight') and sd[k].dim() == 5)
+    assert n_conv == 21
+    assert enc.encoder_layers.encoder_layer3[2][0].padding == [0, 1, 1]
+    vfe = registry.build_voxel_encoder(cfg.hotpath.pts_voxel_encoder)
+    assert vfe.num_features == 5
+    vl = m.Voxelization(**cfg.hotpath.pts_voxel_layer)
+    assert vl.max_voxels == (120000, 160000) and vl.grid_size.tolist() == [1440, 1440, 40]
+
+
+@pytest.mark.skipif(not os.path.isdir('/root/reference/configs'), reason='reference tree not mounted')
+def test_reference_config_files_load_unchanged():
+    for name in ('MSMDFusion_nusc_voxel_LC.py', 'transfusion_nusc_voxel_L.py'):
+        cfg = m.Config.fromfile(os.path.join('/root/reference/configs', name))
+        enc = registry.build_middle_encoder(cfg.model.pts_middle_encoder)
+        assert enc.sparse_shape == [41, 1440, 1440]
+        registry.build_voxel_encoder(cfg.model.pts_voxel_encoder)
+        m.Voxelization(**cfg.model.pts_voxel_layer)
+
+
+def test_hard_simple_vfe_matches_reference_formula():
+    vfe = m.HardSimpleVFE(num_features=4)
+    feats = torch.rand(7, 10, 5)
+    num = torch.randint(1, 10, (7,), dtype=torch.int32)
+    out = vfe(feats, num, None)
+    assert out.shape == (7, 4)
+    assert torch.allclose(out, feats[:, :, :4].sum(1) / num.float().view(-1, 1))
+
+
+def test_sparse_tensor_surface():
+    sp = m.spconv
+    f = torch.rand(5, 3)
+    idx = torch.zeros(5, 4, dtype=torch.int32)
+    t = sp.SparseConvTensor(f, idx, [4, 4, 4], 1)
+    t2 = t.replace_feature(f * 2)
+    assert t2.indices is t.indices and t2.features is not t.features
+    t.indices = torch.zeros(5, 5, dtype=torch.int32)  # MSMDFusion.py:322-323 assigns 5 columns
+    assert t.indices.shape[1] == 5
+    assert t.find_indice_pair('nope') is None and t.find_indice_pair(None) is None
+    seq = sp.SparseSequential(torch.nn.ReLU())
+    assert len(seq) == 1 and isinstance(seq[0], torch.nn.ReLU)
+    with pytest.raises(ValueError):
+        sp._iset_of(t)

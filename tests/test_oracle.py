@@ -1,0 +1,198 @@
+"""CPU tests: pin the oracle against the reference's own known answers / golden vectors and
+against an independent dense conv3d; nothing here touches the CUDA library."""
+import glob
+import os
+import zlib
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from msmdfusion_b200 import synthetic
+from oracle import cpu
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+
+
+def test_voxel_generator_known_answer():
+    """tests/test_models/test_voxel_encoder/test_voxel_generator.py:6-21 of the reference."""
+    np.random.seed(0)
+    points = np.random.rand(1000, 4)
+    voxels, coors, num = cpu.hard_voxelize(points.astype(np.float32), [0.5, 0.5, 0.5],
+                                           [0, -40, -3, 70.4, 40, 1], 1000, 20000)
+    expected = np.array([[7, 81, 1], [6, 81, 0], [7, 80, 1], [6, 81, 1], [7, 81, 0], [6, 80, 1],
+                         [7, 80, 0], [6, 80, 0]])
+    assert np.all(coors == expected)
+    assert voxels.shape == (8, 1000, 4)
+    assert np.all(num == np.array([120, 121, 127, 134, 115, 127, 125, 131]))
+
+
+def golden_cases():
+    return sorted(glob.glob(os.path.join(GOLDEN, 'voxelize_*.npz')))
+
+
+def golden_points(name):
+    from importlib import util
+    spec = util.spec_from_file_location('make_golden', os.path.join(GOLDEN, 'make_golden.py'))
+    mod = util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    key = os.path.basename(name)[len('voxelize_'):-len('.npz')]
+    return mod.CASES[key][0]()
+
+
+@pytest.mark.parametrize('path', golden_cases(), ids=os.path.basename)
+def test_oracle_matches_reference_golden(path):
+    """Fixtures were produced by the reference's own CPU hard_voxelize (make_golden.py)."""
+    g = np.load(path)
+    pts = golden_points(path)
+    assert np.uint32(zlib.crc32(pts.tobytes())) == g['points_crc'], 'synthetic generator drifted'
+    v, c, n = cpu.hard_voxelize(pts, g['voxel_size'], g['coors_range'], int(g['max_points']),
+                                int(g['max_voxels']))
+    assert c.shape[0] == int(g['voxel_num'])
+    assert np.array_equal(c, g['coors'].astype(np.int32))
+    assert np.array_equal(n, g['num_points'].astype(np.int32))
+    assert np.uint32(zlib.crc32(np.ascontiguousarray(v).tobytes())) == g['voxels_crc']
+
+
+@pytest.mark.skipif(not os.path.isdir('/root/reference'), reason='reference tree not mounted')
+def test_oracle_matches_reference_op_live():
+    pts = synthetic.lidar_scene(seed=11, sweeps=1)[:8000]
+    a = cpu.hard_voxelize(pts, synthetic.VOXEL_SIZE, synthetic.POINT_CLOUD_RANGE, 10, 3000)
+    b = cpu.hard_voxelize_ref(pts, synthetic.VOXEL_SIZE, synthetic.POINT_CLOUD_RANGE, 10, 3000)
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
+
+
+def test_fps_known_answer():
+    """tests/test_models/test_common_modules/test_pointnet_ops.py:9-23 of the reference."""
+    xyz = np.array([[[-0.2748, 1.0020, -1.1674], [0.1015, 1.3952, -1.2681], [-0.8070, 2.4137, -0.5845],
+                     [-1.0001, 2.1982, -0.5859], [0.3841, 1.8983, -0.7431]],
+                    [[-1.0696, 3.0758, -0.1899], [-0.2559, 3.5521, -0.1402], [0.8164, 4.0081, -0.1839],
+                     [-1.1000, 3.0213, -0.8205], [-0.0518, 3.7251, -0.3950]]], np.float32)
+    idx = np.stack([cpu.furthest_point_sample(xyz[b], 3) for b in range(2)])
+    assert np.array_equal(idx, np.array([[0, 2, 4], [0, 2, 1]]))
+
+
+BQ_NEW = np.array([[[-0.0740, 1.3147, -1.3625], [-2.2769, 2.7817, -0.2334], [-0.4003, 2.4666, -0.5116],
+                    [-0.0740, 1.3147, -1.3625], [-0.0740, 1.3147, -1.3625]],
+                   [[-2.0289, 2.4952, -0.1708], [-2.0668, 6.0278, -0.4875], [0.4066, 1.4211, -0.2947],
+                    [-2.0289, 2.4952, -0.1708], [-2.0289, 2.4952, -0.1708]]], np.float32)
+BQ_XYZ = np.array([[[-0.0740, 1.3147, -1.3625], [0.5555, 1.0399, -1.3634], [-0.4003, 2.4666, -0.5116],
+                    [-0.5251, 2.4379, -0.8466], [-0.9691, 1.1418, -1.3733], [-0.2232, 0.9561, -1.3626],
+                    [-2.2769, 2.7817, -0.2334], [-0.2822, 1.3192, -1.3645], [0.1533, 1.5024, -1.0432],
+                    [0.4917, 1.1529, -1.3496]],
+                   [[-2.0289, 2.4952, -0.1708], [-0.7188, 0.9956, -0.5096], [-2.0668, 6.0278, -0.4875],
+                    [-1.9304, 3.3092, 0.6610], [0.0949, 1.4332, 0.3140], [-1.2879, 2.0008, -0.7791],
+                    [-0.7252, 0.9611, -0.6371], [0.4066, 1.4211, -0.2947], [0.3220, 1.4447, 0.3548],
+                    [-0.9744, 2.3856, -1.2000]]], np.float32)
+BQ_EXPECT_0 = np.array([[[0, 0, 0, 0, 0], [6, 6, 6, 6, 6], [2, 2, 2, 2, 2], [0, 0, 0, 0, 0], [0, 0, 0, 0, 0]],
+                        [[0, 0, 0, 0, 0], [2, 2, 2, 2, 2], [7, 7, 7, 7, 7], [0, 0, 0, 0, 0], [0, 0, 0, 0, 0]]])
+BQ_EXPECT_1 = np.array([[[0, 5, 7, 0, 0], [6, 6, 6, 6, 6], [2, 3, 2, 2, 2], [0, 5, 7, 0, 0], [0, 5, 7, 0, 0]],
+                        [[0, 0, 0, 0, 0], [2, 2, 2, 2, 2], [7, 7, 7, 7, 7], [0, 0, 0, 0, 0], [0, 0, 0, 0, 0]]])
+
+
+def test_ball_query_known_answer():
+    """test_pointnet_ops.py:26-74 of the reference (plain and dilated ball query)."""
+    for (rmin, rmax, exp) in ((0, 0.2, BQ_EXPECT_0), (0.2, 0.4, BQ_EXPECT_1)):
+        idx = np.stack([cpu.ball_query(rmin, rmax, 5, BQ_XYZ[b], BQ_NEW[b]) for b in range(2)])
+        assert np.array_equal(idx, exp)
+
+
+def random_sparse(rng, batch, shape, n, c):
+    D, H, W = shape
+    lin = rng.choice(batch * D * H * W, size=n, replace=False)
+    rng.shuffle(lin)
+    idx = np.stack([lin // (D * H * W), (lin // (H * W)) % D, (lin // W) % H, lin % W], 1).astype(np.int32)
+    feat = rng.standard_normal((n, c)).astype(np.float32)
+    return idx, feat
+
+
+def dense_conv_oracle(idx, feat, shape, batch, weight, stride, padding, dilation):
+    """Independent oracle: densify -> F.conv3d -> (B,Cout,oD,oH,oW)."""
+    x = torch.from_numpy(cpu.dense(idx, feat, shape, batch)).double()
+    w = torch.from_numpy(weight).double().permute(0, 4, 1, 2, 3).contiguous()  # KRSC -> (Co,Ci,kz,ky,kx)
+    return F.conv3d(x, w, stride=stride, padding=padding, dilation=dilation).numpy()
+
+
+@pytest.mark.parametrize('ksize,dilation', [(3, 1), ((3, 1, 1), 1), (3, 2), ((1, 3, 3), 1)])
+def test_subm_conv_vs_dense(ksize, dilation):
+    rng = np.random.default_rng(0)
+    shape, batch = [7, 12, 10], 2
+    idx, feat = random_sparse(rng, batch, shape, 300, 6)
+    ks = cpu._triple(ksize)
+    w = rng.standard_normal((9, *ks, 6)).astype(np.float32)
+    pair = cpu.subm_rulebook(idx, shape, ksize, dilation)
+    out = cpu.spconv_fwd(feat, w, pair)
+    dl = cpu._triple(dilation)
+    pad = [(k // 2) * d for k, d in zip(ks, dl)]
+    ref = dense_conv_oracle(idx, feat, shape, batch, w, 1, pad, dl)
+    got = ref[idx[:, 0], :, idx[:, 1], idx[:, 2], idx[:, 3]]
+    assert np.abs(out - got).max() < 1e-4
+
+
+@pytest.mark.parametrize('ksize,stride,padding', [(3, 2, 1), (3, 2, (0, 1, 1)), ((3, 1, 1), (2, 1, 1), 0),
+                                                  (2, 2, 0), (3, 1, 0), (3, (1, 2, 3), (1, 0, 2))])
+def test_strided_conv_vs_dense(ksize, stride, padding):
+    rng = np.random.default_rng(1)
+    shape, batch = [9, 14, 11], 2
+    idx, feat = random_sparse(rng, batch, shape, 400, 5)
+    ks = cpu._triple(ksize)
+    w = rng.standard_normal((7, *ks, 5)).astype(np.float32)
+    out_idx, pair, out_shape = cpu.conv_rulebook(idx, shape, ksize, stride, padding, 1)
+    out = cpu.spconv_fwd(feat, w, pair)
+    ref = dense_conv_oracle(idx, feat, shape, batch, w, cpu._triple(stride), cpu._triple(padding), 1)
+    assert list(ref.shape[2:]) == out_shape
+    # ascending linear order, unique
+    lin = ((out_idx[:, 0].astype(np.int64) * out_shape[0] + out_idx[:, 1]) * out_shape[1]
+           + out_idx[:, 2]) * out_shape[2] + out_idx[:, 3]
+    assert np.all(np.diff(lin) > 0)
+    got = ref[out_idx[:, 0], :, out_idx[:, 1], out_idx[:, 2], out_idx[:, 3]]
+    assert np.abs(out - got).max() < 1e-4
+    # every output position the dense conv can reach from an active input is in the set:
+    occ = torch.from_numpy(cpu.dense(idx, np.ones((idx.shape[0], 1), np.float32), shape, batch))
+    reach = F.conv3d(occ, torch.ones(1, 1, *ks), stride=cpu._triple(stride),
+                     padding=cpu._triple(padding)).numpy()[:, 0] > 0
+    assert reach.sum() == out_idx.shape[0]
+    assert reach[out_idx[:, 0], out_idx[:, 1], out_idx[:, 2], out_idx[:, 3]].all()
+
+
+def test_sparse_add_and_dense():
+    rng = np.random.default_rng(2)
+    shape = [5, 8, 9]
+    ia, fa = random_sparse(rng, 2, shape, 120, 4)
+    ib, fb = random_sparse(rng, 2, shape, 150, 4)
+    oi, of = cpu.sparse_add(ia, fa, ib, fb, shape)
+    assert np.allclose(cpu.dense(oi, of, shape, 2), cpu.dense(ia, fa, shape, 2) + cpu.dense(ib, fb, shape, 2))
+    lin = ((oi[:, 0].astype(np.int64) * shape[0] + oi[:, 1]) * shape[1] + oi[:, 2]) * shape[2] + oi[:, 3]
+    assert np.all(np.diff(lin) > 0)
+
+
+def test_float_key_collisions_reproduced():
+    """the float32 key z*1e6+y*1e3+x collapses neighbouring x for z >= 17."""
+    c = np.array([[17, 1000, 700], [17, 1000, 701], [3, 10, 7], [3, 10, 8]], np.int32)
+    k = cpu.float_key(c)
+    assert k[0] == k[1] or abs(float(k[1]) - float(k[0])) == 2.0  # rounded to even spacing
+    assert k[2] != k[3]
+    ref = (torch.from_numpy(c[:, 0]) * 1e6 + torch.from_numpy(c[:, 1]) * 1e3 + torch.from_numpy(c[:, 2])).numpy()
+    assert ref.dtype == np.float32 and np.array_equal(ref, k)
+
+
+def test_modality_split_consistency():
+    rng = np.random.default_rng(3)
+    shape = [41, 200, 200]
+    i3, _ = random_sparse(rng, 2, shape, 3000, 1)
+    i2, _ = random_sparse(rng, 2, shape, 2500, 1)
+    i2[:800] = i3[rng.choice(3000, 800, replace=False)]  # force overlaps
+    i3 = i3[np.argsort(i3[:, 0], kind='stable')]
+    i2 = i2[np.argsort(i2[:, 0], kind='stable')]
+    c3, c2, s3, s2 = cpu.voxel_modality_split(i3, i2, 2)
+    assert c3.shape == (3000, 5) and c2.shape == (2500, 5)
+    assert s3.shape == s2.shape and s3.shape[0] >= 800
+    # matched pairs carry equal float keys (sample 0 has offset 0)
+    n0 = int((i3[:, 0] == 0).sum())
+    m0 = int((i2[:, 0] == 0).sum())
+    k3, k2 = cpu.float_key(i3[:, 1:]), cpu.float_key(i2[:, 1:])
+    first = s3 < n0
+    assert np.array_equal(k3[s3[first & (s2 < m0)]], k2[s2[first & (s2 < m0)]])
+    assert c3[:, 1].sum() == s3.shape[0] and c2[:, 1].sum() == s2.shape[0]
