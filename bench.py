@@ -36,6 +36,7 @@ def parse():
     ap.add_argument('--profile', default='S', choices=['S', 'L'],
                     help='S: single 32-beam sweep (~30 k points); L: 10 sweeps (~285 k points)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--breakdown', default=None, help='write a per-op CUDA-event breakdown (json) here')
     return ap.parse_args()
 
 
@@ -205,8 +206,18 @@ def run_ours(args, rank, world, device):
         ops.PROFILE = None
         for r in recs:
             r['ms'] = r['start'].elapsed_time(r['end'])
-            r['pairs'] = int((r.pop('pair') >= 0).sum().item())
+            if 'pair' in r:
+                r['pairs'] = int((r.pop('pair') >= 0).sum().item())
         conv = [r for r in recs if r['op'] == 'spconv_fwd']
+        if args.breakdown:
+            by_op = {}
+            for r in recs:
+                by_op.setdefault(r['op'], [0, 0.0])
+                by_op[r['op']][0] += 1
+                by_op[r['op']][1] += r['ms']
+            layers = [{k: v for k, v in r.items() if k not in ('start', 'end')} for r in recs[:len(recs) // 3]]
+            json.dump({'per_op_calls_ms_over_3_steps': by_op, 'first_step_calls': layers},
+                      open(args.breakdown, 'w'), indent=1)
         b, f = conv_layer_bytes_flops(conv)
         conv_ms = sum(r['ms'] for r in conv)
         hbm, bf16, src = peaks()

@@ -281,10 +281,11 @@ def randomize_bn(module, seed=0):
     g = torch.Generator().manual_seed(seed)
     for mod in module.modules():
         if isinstance(mod, torch.nn.BatchNorm1d):
-            mod.weight.data = torch.rand(mod.weight.shape, generator=g) + 0.5
-            mod.bias.data = torch.randn(mod.bias.shape, generator=g) * 0.1
-            mod.running_mean.data = torch.randn(mod.running_mean.shape, generator=g) * 0.1
-            mod.running_var.data = torch.rand(mod.running_var.shape, generator=g) + 0.5
+            d = mod.weight.device
+            mod.weight.data = (torch.rand(mod.weight.shape, generator=g) + 0.5).to(d)
+            mod.bias.data = (torch.randn(mod.bias.shape, generator=g) * 0.1).to(d)
+            mod.running_mean.data = (torch.randn(mod.running_mean.shape, generator=g) * 0.1).to(d)
+            mod.running_var.data = (torch.rand(mod.running_var.shape, generator=g) + 0.5).to(d)
 
 
 def test_config1_voxelize_plus_one_subm():
