@@ -137,6 +137,82 @@ MSMD_API int msmd_spconv_fwd(const float* features, int n_in, const float* packe
 MSMD_API int msmd_to_dense(const int* indices, const float* features, int n, int c, int batch_size,
                   const int* spatial_shape, float* out, msmd_stream_t stream);
 
+/* ------------------------------------------------------------------------------------
+ * Furthest point sampling -- replaces furthest_point_sample(xyz (B,N,3) f32, m) -> (B,m) i32
+ *   mmdet3d/ops/furthest_point_sample/furthest_point_sample.py:8-37, CUDA kernel
+ *   src/furthest_point_sample_cuda.cu:25-140 (start index 0, arg-max tie-break reproduced).
+ *   One batch element per call: xyz (n,3), idx (m).
+ * ---------------------------------------------------------------------------------- */
+MSMD_API size_t msmd_fps_workspace(int n);
+MSMD_API int msmd_fps(const float* xyz, int n, int m, int* idx, void* workspace,
+                      size_t workspace_bytes, msmd_stream_t stream);
+
+/* Ball query -- replaces ball_query(min_radius, max_radius, nsample, xyz, center_xyz)
+ *   mmdet3d/ops/ball_query/ball_query.py:8-46, src/ball_query_cuda.cu:11-55.
+ *   xyz (n,3) candidates, centers (m,3); idx (m,nsample) is zero-filled inside. */
+MSMD_API int msmd_ball_query(const float* xyz, int n, const float* centers, int m,
+                             float min_radius, float max_radius, int nsample, int* idx,
+                             msmd_stream_t stream);
+
+/* Nearest key voxel per query voxel on integer (z,y,x) coordinates; rows are
+ * `*_stride` ints apart and point at the z column.  val = ||q-key||_2 (fp32), idx = first
+ * minimal key.  Replaces torch.norm(...).min(-1) of
+ * sparse_multimodal_encoder_painting.py:289-291 / :302-305 without the (Q,N,3) temporary. */
+MSMD_API int msmd_nn_search(const int* query, int query_stride, int nq, const int* key,
+                            int key_stride, int nk, float* val, int* idx, msmd_stream_t stream);
+
+/* query_NN_key_idx[group] = nn  (painting.py:311-321).  group (m,nsample) from ball query
+ * (NULL: every query is its own representative, the Q <= fps_num branch :288-293);
+ * out (nq) int64 = nn_idx + base or -1.  Duplicate targets: the last (representative,
+ * slot) pair in row-major order wins.  winner_scratch: nq ints. */
+MSMD_API int msmd_group_assign(const int* group, int m, int nsample, const float* val,
+                               const int* nn_idx, float dist_thresh, int nq, int base,
+                               int* winner_scratch, long long* out, msmd_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * voxel_modality_split for ONE sample -- replaces MSMDFusion.py:251-325 (+ type_assign
+ * :27-45): float32 key z*1e6+y*1e3+x, stable sort, one-to-one pairing of equal keys.
+ *   coord3 (n3,4) / coord2 (n2,4) i32 (b,z,y,x) rows of this sample
+ *   mix3 (n3) / mix2 (n2) i32: 1 = voxel exists in both modalities
+ *   syn3 / syn2: int64 row ids (+offset) of the paired voxels in sorted-key order; capacity
+ *   min(n3,n2); *num_mix (device) = number of pairs
+ * ---------------------------------------------------------------------------------- */
+MSMD_API size_t msmd_modality_split_workspace(int n3, int n2);
+MSMD_API int msmd_modality_split(const int* coord3, int n3, const int* coord2, int n2,
+                                 long long offset3, long long offset2, int* mix3, int* mix2,
+                                 long long* syn3, long long* syn2, int* num_mix, void* workspace,
+                                 size_t workspace_bytes, msmd_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * Fsp.sparse_add(a, b) -- call site sparse_multimodal_encoder_painting.py:455.
+ *   step 1 builds the union bit grid (bits/prefix sized by msmd_grid_num_words) and
+ *   *num_out; step 2 (needs num_out on the host) writes out_indices (ascending linear
+ *   order) and out_features = sum of coincident rows.  The grid is reusable as the index
+ *   structure of the output tensor.
+ * ---------------------------------------------------------------------------------- */
+MSMD_API int msmd_sparse_add_outputs(const int* idx_a, int na, const int* idx_b, int nb,
+                                     int batch_size, const int* spatial_shape, uint32_t* bits,
+                                     int* prefix, int* num_out, void* workspace,
+                                     size_t workspace_bytes, msmd_stream_t stream);
+MSMD_API int msmd_sparse_add_finish(const uint32_t* bits, const int* prefix, int n_out,
+                                    const int* idx_a, const float* feat_a, int na,
+                                    const int* idx_b, const float* feat_b, int nb, int c,
+                                    int batch_size, const int* spatial_shape, int* out_indices,
+                                    float* out_features, msmd_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * Virtual-point lift -- replaces the per-camera loop of get_foreground2D
+ * (MSMDFusion.py:189-230): out[p] = [ points[p] (point_dims) | feat[cam,:,v,u] * score ],
+ * score = ReLU(w . [feat, depth, lidar2img[cam] (16)] + b).  img_feat is addressed by
+ * element strides (any layout); pixels (M,3) = (u,v,depth) in network-input pixels.
+ * ---------------------------------------------------------------------------------- */
+MSMD_API int msmd_lift_gather(const float* img_feat, long long stride_cam, long long stride_c,
+                              long long stride_y, long long stride_x, int channels, int height,
+                              int width, const float* pixels, const int* cam_ids,
+                              const float* points, int point_dims, int num_points,
+                              const float* lidar2img, float downscale, const float* score_weight,
+                              float score_bias, float* out, msmd_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -12,5 +12,8 @@ from . import spconv  # noqa: F401
 from .sparse_block import SparseBasicBlock, make_sparse_convmodule  # noqa: F401
 from .sparse_encoder import SparseEncoder  # noqa: F401
 from .voxel import HardSimpleVFE, Voxelization, hard_voxelize, voxelization  # noqa: F401
+from . import functional  # noqa: F401
+from .fusion_encoder import SparseMultiModalEncoderPaint  # noqa: F401
+from .detector import MSMDFusionDetector, SPPModule, TransFusionDetector  # noqa: F401
 
 __version__ = '0.1.0'

@@ -38,6 +38,20 @@ SIGNATURES = {
     'msmd_spconv_pack_weight': (_i, [_vp, _i, _i, _i, _vp, _vp]),
     'msmd_spconv_fwd': (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _vp]),
     'msmd_to_dense': (_i, [_vp, _vp, _i, _i, _i, _c_int_p, _vp, _vp]),
+    'msmd_fps_workspace': (_sz, [_i]),
+    'msmd_fps': (_i, [_vp, _i, _i, _vp, _vp, _sz, _vp]),
+    'msmd_ball_query': (_i, [_vp, _i, _vp, _i, ctypes.c_float, ctypes.c_float, _i, _vp, _vp]),
+    'msmd_nn_search': (_i, [_vp, _i, _i, _vp, _i, _i, _vp, _vp, _vp]),
+    'msmd_group_assign': (_i, [_vp, _i, _i, _vp, _vp, ctypes.c_float, _i, _i, _vp, _vp, _vp]),
+    'msmd_modality_split_workspace': (_sz, [_i, _i]),
+    'msmd_modality_split': (_i, [_vp, _i, _vp, _i, ctypes.c_longlong, ctypes.c_longlong, _vp, _vp,
+                                 _vp, _vp, _vp, _vp, _sz, _vp]),
+    'msmd_sparse_add_outputs': (_i, [_vp, _i, _vp, _i, _i, _c_int_p, _vp, _vp, _vp, _vp, _sz, _vp]),
+    'msmd_sparse_add_finish': (_i, [_vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _c_int_p, _vp,
+                                    _vp, _vp]),
+    'msmd_lift_gather': (_i, [_vp, ctypes.c_longlong, ctypes.c_longlong, ctypes.c_longlong,
+                              ctypes.c_longlong, _i, _i, _i, _vp, _vp, _vp, _i, _i, _vp,
+                              ctypes.c_float, _vp, ctypes.c_float, _vp, _vp]),
 }
 
 _LIB = None

@@ -1,0 +1,340 @@
+// fusion.cu -- the index/gather ops either side of the Gated Modality-Aware convolution:
+//   * voxel_modality_split   (MSMDFusion.py:27-45, :251-325)
+//   * Fsp.sparse_add         (call site sparse_multimodal_encoder_painting.py:455)
+//   * get_foreground2D lift  (MSMDFusion.py:169-238): pixel-feature gather x score gate
+#include "sort.cuh"
+
+namespace msmd {
+
+// ------------------------------------------------------------------------------------
+// voxel_modality_split
+// The reference builds a FLOAT32 key z*1e6 + y*1e3 + x (int32 tensor * python float ->
+// float32; MSMDFusion.py:271-272), sorts both voxel sets by it, and pairs equal keys
+// one-to-one with a CPU two-pointer merge (type_assign).  Keys above 2^24 collide for
+// neighbouring x -- that rounding is part of the reference's behaviour and is reproduced
+// exactly (separate fp32 mul, mul, add, add; no FMA).  The keys are exact integers < 2^26, so
+// they sort as uint32; the sort is stable (ties keep row order).  For a run of `a` equal keys
+// in one set and `b` in the other the merge flags the first min(a,b) of each:
+//        flagged(i)  <=>  (i - lower_bound_own(key)) < count_other(key).
+// ------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t float_key(int z, int y, int x) {
+  const float a = __fmul_rn((float)z, 1e6f);
+  const float b = __fmul_rn((float)y, 1e3f);
+  const float k = __fadd_rn(__fadd_rn(a, b), (float)x);
+  return (uint32_t)k;
+}
+
+__global__ void __launch_bounds__(256)
+split_keys_kernel(const int* __restrict__ coord, int stride, int n, uint32_t* __restrict__ keys) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int* c = coord + (size_t)i * stride;  // (b, z, y, x)
+  keys[i] = float_key(c[1], c[2], c[3]);
+}
+
+__device__ __forceinline__ int lower_bound_u32(const uint32_t* a, int n, uint32_t v) {
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (a[mid] < v) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+__device__ __forceinline__ int upper_bound_u32(const uint32_t* a, int n, uint32_t v) {
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (a[mid] <= v) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+__global__ void __launch_bounds__(256)
+split_flag_kernel(const uint32_t* __restrict__ own, const int* __restrict__ own_rows, int n_own,
+                  const uint32_t* __restrict__ other, int n_other, int* __restrict__ flag_sorted,
+                  int* __restrict__ mix_rows) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_own) return;
+  const uint32_t key = own[i];
+  const int j = i - lower_bound_u32(own, n_own, key);
+  const int cnt = upper_bound_u32(other, n_other, key) - lower_bound_u32(other, n_other, key);
+  const int f = j < cnt;
+  flag_sorted[i] = f;
+  mix_rows[own_rows[i]] = f;
+}
+
+struct SplitCompact {
+  const int* rows;
+  long long offset;
+  long long* out;
+  __device__ void operator()(int i, int ex, int v) const {
+    if (v) out[ex] = (long long)rows[i] + offset;
+  }
+};
+
+struct SplitWs {
+  uint32_t *k3, *k2;
+  int *r3, *r2, *f3, *f2;
+  int* total2;
+  SortWs sort;
+  bool carve(Workspace& ws, int n3, int n2) {
+    k3 = ws.take<uint32_t>(n3 > 0 ? n3 : 1);
+    k2 = ws.take<uint32_t>(n2 > 0 ? n2 : 1);
+    r3 = ws.take<int>(n3 > 0 ? n3 : 1);
+    r2 = ws.take<int>(n2 > 0 ? n2 : 1);
+    f3 = ws.take<int>(n3 > 0 ? n3 : 1);
+    f2 = ws.take<int>(n2 > 0 ? n2 : 1);
+    total2 = ws.take<int>(1);
+    return sort.carve(ws, n3 > n2 ? n3 : n2);
+  }
+};
+
+// ------------------------------------------------------------------------------------
+// sparse_add: union of two sparse tensors, features of coincident voxels summed, output
+// rows ascending by linear index (spconv v2.1.21: torch.sparse coalesce).  The union is the
+// OR of both occupancy bitmaps; the popcount scan yields the sorted output rows directly,
+// and the same grid serves the strided convolution that follows.
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+grid_or_kernel(const int4* __restrict__ indices, int n, int batch, int D, int H, int W,
+               uint32_t* __restrict__ bits) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int4 c = indices[i];
+  if ((unsigned)c.x >= (unsigned)batch || (unsigned)c.y >= (unsigned)D ||
+      (unsigned)c.z >= (unsigned)H || (unsigned)c.w >= (unsigned)W)
+    return;
+  const int L = ((c.x * D + c.y) * H + c.z) * W + c.w;
+  atomicOr(&bits[L >> 5], 1u << (L & 31));
+}
+
+struct PopcWord2 {
+  const uint32_t* bits;
+  __device__ int operator()(int w) const { return __popc(bits[w]); }
+};
+struct StorePrefix2 {
+  int* prefix;
+  __device__ void operator()(int w, int ex, int) const { prefix[w] = ex; }
+};
+
+__global__ void __launch_bounds__(256)
+union_enumerate_kernel(const uint32_t* __restrict__ bits, const int* __restrict__ prefix,
+                       int num_words, int D, int H, int W, int4* __restrict__ out_indices) {
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= num_words) return;
+  uint32_t word = bits[w];
+  if (!word) return;
+  int r = prefix[w];
+  while (word) {
+    const int b = __ffs(word) - 1;
+    word &= word - 1;
+    int L = (w << 5) + b;
+    int4 c;
+    c.w = L % W; L /= W;
+    c.z = L % H; L /= H;
+    c.y = L % D; L /= D;
+    c.x = L;
+    out_indices[r++] = c;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+scatter_add_rows_kernel(const int4* __restrict__ indices, const float* __restrict__ feat, int n,
+                        int C, int batch, int D, int H, int W, const uint32_t* __restrict__ bits,
+                        const int* __restrict__ prefix, float* __restrict__ out) {
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (size_t)n * C) return;
+  const int i = (int)(t / C), ch = (int)(t % C);
+  const int4 c = indices[i];
+  if ((unsigned)c.x >= (unsigned)batch || (unsigned)c.y >= (unsigned)D ||
+      (unsigned)c.z >= (unsigned)H || (unsigned)c.w >= (unsigned)W)
+    return;
+  const int L = ((c.x * D + c.y) * H + c.z) * W + c.w;
+  const int w = L >> 5;
+  const unsigned b = (unsigned)L & 31u;
+  const uint32_t word = __ldg(bits + w);
+  const int r = __ldg(prefix + w) + __popc(word & ((1u << b) - 1u));
+  atomicAdd(out + (size_t)r * C + ch, feat[t]);
+}
+
+// ------------------------------------------------------------------------------------
+// Lift: per virtual point, gather the C-channel image feature at its pixel, gate it with
+// score = ReLU(Linear_{C+17 -> 1}([feat, depth, lidar2img(16)])) and emit
+// [point(P) | feat * score]  (MSMDFusion.py:202-230).  One warp per point; the feature map is
+// addressed through explicit strides so a channels-last map gives 196-byte coalesced reads.
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+lift_gather_kernel(const float* __restrict__ img, long long s_cam, long long s_c, long long s_y,
+                   long long s_x, int C, int H, int W, const float* __restrict__ pix,
+                   const int* __restrict__ cam, const float* __restrict__ pts, int P, int M,
+                   const float* __restrict__ lidar2img, float downscale,
+                   const float* __restrict__ score_w, float score_b, float* __restrict__ out) {
+  const int p = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (p >= M) return;
+  const float u = pix[3 * p + 0], v = pix[3 * p + 1], depth = pix[3 * p + 2];
+  // fg_pxl * downscale_factor in fp32, then .long() (truncation toward zero), :207-209
+  int cw = (int)truncf(__fmul_rn(u, downscale));
+  int chh = (int)truncf(__fmul_rn(v, downscale));
+  cw = min(max(cw, 0), W - 1);  // the reference would raise on out-of-map pixels
+  chh = min(max(chh, 0), H - 1);
+  const int cm = cam[p];
+  const float* base = img + (long long)cm * s_cam + (long long)chh * s_y + (long long)cw * s_x;
+  float f[4];
+  float acc = 0.f;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int c = lane + 32 * j;
+    f[j] = 0.f;
+    if (c < C) {
+      f[j] = __ldg(base + (long long)c * s_c);
+      acc = fmaf(f[j], __ldg(score_w + c), acc);
+    }
+  }
+  if (lane == 0) acc = fmaf(depth, __ldg(score_w + C), acc);
+  if (lane < 16) acc = fmaf(__ldg(lidar2img + cm * 16 + lane), __ldg(score_w + C + 1 + lane), acc);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  const float score = fmaxf(acc + score_b, 0.f);
+  float* o = out + (size_t)p * (P + C);
+  for (int c = lane; c < P; c += 32) o[c] = pts[(size_t)p * P + c];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int c = lane + 32 * j;
+    if (c < C) o[P + c] = f[j] * score;
+  }
+}
+
+}  // namespace msmd
+
+using namespace msmd;
+
+extern "C" MSMD_API size_t msmd_modality_split_workspace(int n3, int n2) {
+  Workspace ws((void*)256, ~(size_t)0 >> 1);
+  SplitWs s;
+  s.carve(ws, n3, n2);
+  return ws.used + 256;
+}
+
+extern "C" MSMD_API int msmd_modality_split(const int* coord3, int n3, const int* coord2, int n2,
+                                            long long offset3, long long offset2, int* mix3,
+                                            int* mix2, long long* syn3, long long* syn2,
+                                            int* num_mix, void* workspace, size_t workspace_bytes,
+                                            msmd_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  MSMD_REQUIRE(n3 >= 0 && n2 >= 0 && num_mix, "modality_split: bad arguments");
+  Workspace ws(workspace, workspace_bytes);
+  SplitWs s;
+  if (!s.carve(ws, n3, n2)) {
+    set_error("modality_split: workspace too small (%zu < %zu)", workspace_bytes,
+              msmd_modality_split_workspace(n3, n2));
+    return MSMD_ERR_WORKSPACE;
+  }
+  if (n3 == 0 || n2 == 0) {
+    if (n3) MSMD_CUDA_OK(cudaMemsetAsync(mix3, 0, (size_t)n3 * sizeof(int), stream));
+    if (n2) MSMD_CUDA_OK(cudaMemsetAsync(mix2, 0, (size_t)n2 * sizeof(int), stream));
+    MSMD_CUDA_OK(cudaMemsetAsync(num_mix, 0, sizeof(int), stream));
+    return MSMD_OK;
+  }
+  split_keys_kernel<<<ceil_div(n3, 256), 256, 0, stream>>>(coord3, 4, n3, s.k3);
+  MSMD_LAUNCH_OK();
+  split_keys_kernel<<<ceil_div(n2, 256), 256, 0, stream>>>(coord2, 4, n2, s.k2);
+  MSMD_LAUNCH_OK();
+  MSMD_CUDA_OK(radix_sort_pairs(s.k3, s.r3, n3, 26, true, s.sort, stream));
+  MSMD_CUDA_OK(radix_sort_pairs(s.k2, s.r2, n2, 26, true, s.sort, stream));
+  split_flag_kernel<<<ceil_div(n3, 256), 256, 0, stream>>>(s.k3, s.r3, n3, s.k2, n2, s.f3, mix3);
+  MSMD_LAUNCH_OK();
+  split_flag_kernel<<<ceil_div(n2, 256), 256, 0, stream>>>(s.k2, s.r2, n2, s.k3, n3, s.f2, mix2);
+  MSMD_LAUNCH_OK();
+  MSMD_CUDA_OK(cudaMemsetAsync(s.sort.counter, 0, sizeof(unsigned), stream));
+  ScanTemp<int> t3{s.sort.block_sums, s.sort.counter, num_mix};
+  MSMD_CUDA_OK((device_exclusive_scan<int>(LoadInt{s.f3}, SplitCompact{s.r3, offset3, syn3}, n3, t3,
+                                           stream)));
+  ScanTemp<int> t2{s.sort.block_sums, s.sort.counter, s.total2};
+  MSMD_CUDA_OK((device_exclusive_scan<int>(LoadInt{s.f2}, SplitCompact{s.r2, offset2, syn2}, n2, t2,
+                                           stream)));
+  return MSMD_OK;
+}
+
+extern "C" MSMD_API int msmd_sparse_add_outputs(const int* idx_a, int na, const int* idx_b, int nb,
+                                                int batch_size, const int* shape, uint32_t* bits,
+                                                int* prefix, int* num_out, void* workspace,
+                                                size_t workspace_bytes, msmd_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  MSMD_REQUIRE(batch_size > 0 && shape[0] > 0 && shape[1] > 0 && shape[2] > 0 && na >= 0 && nb >= 0,
+               "sparse_add: bad arguments");
+  MSMD_REQUIRE((long long)batch_size * shape[0] * shape[1] * shape[2] < 0x7fffffffLL,
+               "sparse_add: grid exceeds the int32 cell index");
+  const size_t words = msmd_grid_num_words(batch_size, shape);
+  MSMD_CUDA_OK(cudaMemsetAsync(bits, 0, words * sizeof(uint32_t), stream));
+  if (na) {
+    grid_or_kernel<<<ceil_div(na, 256), 256, 0, stream>>>((const int4*)idx_a, na, batch_size, shape[0],
+                                                          shape[1], shape[2], bits);
+    MSMD_LAUNCH_OK();
+  }
+  if (nb) {
+    grid_or_kernel<<<ceil_div(nb, 256), 256, 0, stream>>>((const int4*)idx_b, nb, batch_size, shape[0],
+                                                          shape[1], shape[2], bits);
+    MSMD_LAUNCH_OK();
+  }
+  Workspace ws(workspace, workspace_bytes);
+  int* block_sums = ws.take<int>(kScanMaxBlocks);
+  int* total = ws.take<int>(1);
+  unsigned* counter = ws.take<unsigned>(1);
+  if (!ws.ok()) {
+    set_error("sparse_add: workspace too small");
+    return MSMD_ERR_WORKSPACE;
+  }
+  (void)total;
+  MSMD_CUDA_OK(cudaMemsetAsync(counter, 0, sizeof(unsigned), stream));
+  ScanTemp<int> tmp{block_sums, counter, num_out};
+  MSMD_CUDA_OK((device_exclusive_scan<int>(PopcWord2{bits}, StorePrefix2{prefix}, (int)words, tmp,
+                                           stream)));
+  return MSMD_OK;
+}
+
+extern "C" MSMD_API int msmd_sparse_add_finish(const uint32_t* bits, const int* prefix, int n_out,
+                                               const int* idx_a, const float* feat_a, int na,
+                                               const int* idx_b, const float* feat_b, int nb, int c,
+                                               int batch_size, const int* shape, int* out_indices,
+                                               float* out_features, msmd_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (n_out == 0) return MSMD_OK;
+  MSMD_REQUIRE(c > 0 && out_indices && out_features, "sparse_add: bad arguments");
+  const size_t words = msmd_grid_num_words(batch_size, shape);
+  union_enumerate_kernel<<<ceil_div((long long)words, 256), 256, 0, stream>>>(
+      bits, prefix, (int)words, shape[0], shape[1], shape[2], (int4*)out_indices);
+  MSMD_LAUNCH_OK();
+  MSMD_CUDA_OK(cudaMemsetAsync(out_features, 0, (size_t)n_out * c * sizeof(float), stream));
+  if (na) {
+    scatter_add_rows_kernel<<<ceil_div((long long)na * c, 256), 256, 0, stream>>>(
+        (const int4*)idx_a, feat_a, na, c, batch_size, shape[0], shape[1], shape[2], bits, prefix,
+        out_features);
+    MSMD_LAUNCH_OK();
+  }
+  if (nb) {
+    scatter_add_rows_kernel<<<ceil_div((long long)nb * c, 256), 256, 0, stream>>>(
+        (const int4*)idx_b, feat_b, nb, c, batch_size, shape[0], shape[1], shape[2], bits, prefix,
+        out_features);
+    MSMD_LAUNCH_OK();
+  }
+  return MSMD_OK;
+}
+
+extern "C" MSMD_API int msmd_lift_gather(const float* img_feat, long long stride_cam,
+                                         long long stride_c, long long stride_y, long long stride_x,
+                                         int channels, int height, int width, const float* pixels,
+                                         const int* cam_ids, const float* points, int point_dims,
+                                         int num_points, const float* lidar2img, float downscale,
+                                         const float* score_weight, float score_bias, float* out,
+                                         msmd_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  MSMD_REQUIRE(channels > 0 && channels <= 128 && point_dims >= 0 && num_points >= 0,
+               "lift_gather: channels must be in [1,128]");
+  if (num_points == 0) return MSMD_OK;
+  lift_gather_kernel<<<ceil_div((long long)num_points * 32, 256), 256, 0, stream>>>(
+      img_feat, stride_cam, stride_c, stride_y, stride_x, channels, height, width, pixels, cam_ids,
+      points, point_dims, num_points, lidar2img, downscale, score_weight, score_bias, out);
+  MSMD_LAUNCH_OK();
+  return MSMD_OK;
+}

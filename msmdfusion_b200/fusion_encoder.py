@@ -1,0 +1,207 @@
+"""SparseMultiModalEncoderPaint -- the Gated Modality-Aware convolution encoder.
+
+Mirrors ``mmdet3d/models/middle_encoders/sparse_multimodal_encoder_painting.py:99-459``:
+same constructor kwargs, sub-module names (state-dict compatible, including the
+``grouped_sp_conv_blocks_2D`` / ``_mix`` blocks the reference builds but never calls) and the
+same ``forward`` signature / return value.
+
+B200-first differences that cannot change results:
+* ``fps_NN_fast`` never materialises the (1, fps_num, N3D, 3) distance tensor: FPS runs on a
+  thread-block cluster with the reference's arg-max tie-break, the nearest-3-D-voxel search and
+  the ball query are streaming kernels (csrc/points.cu);
+* the duplicate-index scatter of ``:321`` (winner undefined in the reference) is resolved
+  deterministically: the last (representative, slot) pair in row-major order wins;
+* ``pad_missing_batch_id`` counts batch ids on the device and reads the counts back once
+  instead of ``unique().cpu()`` per call.
+"""
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from . import functional as Fsp
+from . import ops, spconv
+from .registry import MIDDLE_ENCODERS
+from .sparse_block import SparseBasicBlock, make_sparse_convmodule
+
+
+def fps_nn_fast(query, key, fps_num, radius, max_cluster_samples, dist_thresh, base=0):
+    """``fps_NN_fast`` (:276-323) for ONE sample.
+
+    query (Q,4) / key (Nk,4) int32 (b,z,y,x) -> (Q,) int64: row (+base) of the nearest 3-D voxel
+    of each only-2D voxel (through its FPS representative when Q > fps_num), -1 = unassigned.
+    """
+    Q = query.shape[0]
+    q = query[:, 1:].contiguous()
+    k = key[:, 1:].contiguous()
+    if q.dtype != torch.int32:
+        q, k = q.int(), k.int()
+    if Q == 0:
+        return torch.empty((0,), dtype=torch.int64, device=query.device)
+    if Q <= fps_num:
+        val, idx = ops.nn_search(q, k)
+        return ops.group_assign(None, val, idx, dist_thresh, Q, base)
+    qf = q.float()
+    repr_idx = ops.furthest_point_sample_single(qf, fps_num)
+    repr_q = q.index_select(0, repr_idx.long())
+    val, idx = ops.nn_search(repr_q, k)
+    group = ops.ball_query_single(0, radius, max_cluster_samples, qf, repr_q.float())
+    return ops.group_assign(group, val, idx, dist_thresh, Q, base)
+
+
+@MIDDLE_ENCODERS.register_module()
+class SparseMultiModalEncoderPaint(nn.Module):
+
+    def __init__(self, in_channels_3D=(16, 32, 64, 128), in_channels_2D=(259, 259, 259, 259),
+                 out_channels=(32, 64, 128, 128), padding=(1, 1, 1, [0, 1, 1]),
+                 down_kernel_size=(3, 3, 3, [3, 1, 1]), down_stride=(2, 2, 2, [2, 1, 1]),
+                 order=('conv', 'norm', 'act'),
+                 norm_cfg=dict(type='BN1d', eps=1e-3, momentum=0.01), block_type='conv_module'):
+        super().__init__()
+        assert block_type in ['conv_module', 'basicblock']
+        self.in_channels_3D = in_channels_3D
+        self.in_channels_2D = in_channels_2D
+        self.out_channels = out_channels
+        self.padding = padding
+        self.down_kernel_size = down_kernel_size
+        self.down_stride = down_stride
+        self.order = order
+        self.fp16_enabled = False
+        self.make_grouped_sparse_conv_blocks(norm_cfg)
+        self.make_aggregation_block(norm_cfg)
+        self.make_downscale_block(norm_cfg)
+
+    # -- construction (:126-206) --------------------------------------------------------
+    def make_grouped_sparse_conv_blocks(self, norm_cfg, conv_cfg=dict(type='SubMConv3d')):
+        self.grouped_sp_conv_blocks_3D = spconv.SparseSequential()
+        self.grouped_sp_conv_blocks_2D = spconv.SparseSequential()    # built, never called (:142-150)
+        self.grouped_sp_conv_blocks_mix = spconv.SparseSequential()   # built, never called (:151-156)
+        gate_control, cross_gate_control = [], []
+        for i, c3 in enumerate(self.in_channels_3D):
+            stage_name = f'stage_{i + 1}'
+            self.grouped_sp_conv_blocks_3D.add_module(stage_name, make_sparse_convmodule(
+                c3, c3, 3, indice_key=f'subm3D_{i + 1}', norm_cfg=norm_cfg, padding=1,
+                conv_type='SubMConv3d'))
+            self.grouped_sp_conv_blocks_2D.add_module(stage_name, make_sparse_convmodule(
+                64, 64, 3, indice_key=f'block2d_0_{i + 1}', norm_cfg=norm_cfg, padding=1,
+                conv_type='SubMConv3d'))
+            self.grouped_sp_conv_blocks_mix.add_module(stage_name, SparseBasicBlock(
+                c3 + 64, c3 + 64, norm_cfg=norm_cfg, conv_cfg=conv_cfg))
+            gate_control.append(nn.Sequential(nn.Linear(c3, self.in_channels_2D[i]), nn.ReLU()))
+            cross_gate_control.append(nn.Sequential(nn.Linear(c3, self.in_channels_2D[i]), nn.ReLU()))
+        self.gate_control = nn.ModuleList(gate_control)
+        self.cross_gate_control = nn.ModuleList(cross_gate_control)
+
+    def make_aggregation_block(self, norm_cfg, conv_cfg=dict(type='SubMConv3d')):
+        self.aggregation_blocks = spconv.SparseSequential()
+        for i, c3 in enumerate(self.in_channels_3D):
+            self.aggregation_blocks.add_module(f'stage_{i + 1}', SparseBasicBlock(
+                c3 + 64, c3 + 64, norm_cfg=norm_cfg, conv_cfg=conv_cfg))
+
+    def make_downscale_block(self, norm_cfg):
+        self.downscale_blocks = spconv.SparseSequential()
+        for i, c3 in enumerate(self.in_channels_3D):
+            self.downscale_blocks.add_module(f'stage_{i + 1}', make_sparse_convmodule(
+                c3 + 64, self.out_channels[i] + 64, kernel_size=self.down_kernel_size[i],
+                indice_key=f'spconv_ds_{i + 1}', norm_cfg=norm_cfg, stride=self.down_stride[i],
+                padding=self.padding[i], conv_type='SparseConv3d'))
+
+    # -- helpers ------------------------------------------------------------------------
+    def pad_missing_batch_id(self, indices, features, B, template_indice, template_feature):
+        """:208-225 -- append an all-zero voxel (b,0,...,0) for every batch id with no row."""
+        counts = torch.bincount(indices[:, 0].long(), minlength=B)[:B].cpu() if indices.shape[0] \
+            else torch.zeros(B, dtype=torch.long)
+        for batch_id in range(B):
+            if int(counts[batch_id]) == 0:
+                padded_indices = torch.zeros_like(template_indice).unsqueeze(0)
+                padded_indices[0, 0] = batch_id
+                padded_features = torch.zeros_like(template_feature).unsqueeze(0)
+                indices = torch.cat([indices, padded_indices], dim=0)
+                features = torch.cat([features, padded_features], dim=0)
+        return indices, features
+
+    def fps_NN_fast(self, query, key, fps_num, radius, max_cluster_samples, dist_thresh):
+        return fps_nn_fast(query, key, fps_num, radius, max_cluster_samples, dist_thresh)
+
+    fps_NN = fps_NN_fast  # :226-274 is the pure-torch variant of the same function
+
+    # -- one stage of the GMA convolution (:325-430) --------------------------------------
+    def grouped_sparse_conv(self, voxel_3D, voxel_2D, syn_mix_3D, syn_mix_2D, stage_id, fps_num,
+                            radius, max_cluster_samples, dist_thresh):
+        ind3, ind2 = voxel_3D.indices, voxel_2D.indices
+        feat3, feat2 = voxel_3D.features, voxel_2D.features
+        c3 = self.in_channels_3D[stage_id]
+        B = voxel_3D.batch_size
+        only_3D_mask = ind3[:, 1] == 0
+        only_2D_mask = ind2[:, 1] == 0
+
+        voxel_only_2D_indices = ind2[only_2D_mask]
+        voxel_only_2D_features = feat2[only_2D_mask]
+        voxel_only_2D_indices, voxel_only_2D_features = self.pad_missing_batch_id(
+            voxel_only_2D_indices, voxel_only_2D_features, B, ind2[0], feat2[0])
+
+        # nearest 3-D voxel of every only-2D voxel, per sample (:352-369)
+        only2d_bzyx = voxel_only_2D_indices[:, [0, 2, 3, 4]].contiguous()
+        v3_bzyx = ind3[:, [0, 2, 3, 4]].contiguous()
+        nn_idx = torch.full((only2d_bzyx.shape[0],), -1, dtype=torch.int64, device=ind3.device)
+        if B == 1:
+            nn_idx = fps_nn_fast(only2d_bzyx, v3_bzyx, fps_num, radius, max_cluster_samples,
+                                 dist_thresh, base=0)
+        else:
+            base = 0
+            for batch_id in range(B):
+                m2 = only2d_bzyx[:, 0] == batch_id
+                m3 = v3_bzyx[:, 0] == batch_id
+                k3 = v3_bzyx[m3]
+                if k3.shape[0] == 0:
+                    continue  # the reference loops over the batch ids present in voxel_3D (:355)
+                nn_idx[m2] = fps_nn_fast(only2d_bzyx[m2], k3, fps_num, radius,
+                                         max_cluster_samples, dist_thresh, base=base)
+                base = k3.shape[0]  # previous sample's length only (:369; valid for B <= 2)
+
+        # cross gate: only-2D features scaled by the gate of their nearest 3-D voxel; unassigned
+        # voxels (-1) pick the last row = gate of a random dummy embedding (:371-377)
+        dummy_embedding = torch.rand(1, feat3.shape[1]).to(feat3.device)
+        cross_gating = self.cross_gate_control[stage_id](torch.cat([feat3, dummy_embedding], dim=0))
+        voxel_only_2D_features = cross_gating[nn_idx] * voxel_only_2D_features
+
+        voxel_only_3D = spconv.SparseConvTensor(feat3[only_3D_mask],
+                                                ind3[only_3D_mask][:, [0, 2, 3, 4]].contiguous(),
+                                                voxel_3D.spatial_shape, B)
+
+        # mixed voxels: [3-D feature | gated 2-D feature] at the 2-D voxel's coordinates (:391-408)
+        mixed_3D_feat = feat3[syn_mix_3D]
+        mixed_2D_feat = feat2[syn_mix_2D]
+        assert mixed_3D_feat.shape[0] == mixed_2D_feat.shape[0]
+        gating = self.gate_control[stage_id](mixed_3D_feat)
+        voxel_mixed_feat = torch.cat([mixed_3D_feat, gating * mixed_2D_feat], dim=-1)
+        voxel_mixed_indices = ind2[syn_mix_2D]
+        voxel_mixed_indices, voxel_mixed_feat = self.pad_missing_batch_id(
+            voxel_mixed_indices, voxel_mixed_feat, B, ind3[0], torch.cat([feat3[0], feat2[0]], dim=-1))
+
+        stage_name = f'stage_{stage_id + 1}'
+        voxel_only_3D = getattr(self.grouped_sp_conv_blocks_3D, stage_name)(voxel_only_3D)
+        only_2D_feat = F.pad(voxel_only_2D_features, (c3, 0), mode='constant', value=0)
+        only_3D_feat = F.pad(voxel_only_3D.features, (0, 64), mode='constant', value=0)
+        assert only_2D_feat.shape[-1] == only_3D_feat.shape[-1] == voxel_mixed_feat.shape[-1]
+
+        unified_voxel_feat = torch.cat([only_3D_feat, only_2D_feat, voxel_mixed_feat], dim=0)
+        unified_voxel_coors = torch.cat([voxel_only_3D.indices, only2d_bzyx,
+                                         voxel_mixed_indices[:, [0, 2, 3, 4]]], dim=0).contiguous()
+        unified_voxel = spconv.SparseConvTensor(unified_voxel_feat, unified_voxel_coors,
+                                                voxel_2D.spatial_shape, voxel_2D.batch_size)
+        return getattr(self.aggregation_blocks, stage_name)(unified_voxel)
+
+    def forward(self, voxel_3D_list, voxel_2D_list, syn_mix_3D_list, syn_mix_2D_list, fps_num_list,
+                radius_list, max_cluster_samples_list, dist_thresh_list):
+        """:433-459 -> list of the 4 down-scaled stage outputs."""
+        stage_outs = []
+        for stage_id in range(len(voxel_2D_list)):
+            stage_name = f'stage_{stage_id + 1}'
+            out = self.grouped_sparse_conv(
+                voxel_3D_list[stage_id], voxel_2D_list[stage_id], syn_mix_3D_list[stage_id],
+                syn_mix_2D_list[stage_id], stage_id, fps_num_list[stage_id], radius_list[stage_id],
+                max_cluster_samples_list[stage_id], dist_thresh_list[stage_id])
+            if stage_id > 0:
+                out = Fsp.sparse_add(out, stage_outs[stage_id - 1])
+            stage_outs.append(getattr(self.downscale_blocks, stage_name)(out))
+        return stage_outs

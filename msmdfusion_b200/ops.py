@@ -225,3 +225,137 @@ def to_dense(indices, features, spatial_shape, batch_size):
         check(lib().msmd_to_dense(ptr(indices), ptr(features), n, c, int(batch_size), ints([d, h, w]),
                                   ptr(out), stream(features.device)), 'msmd_to_dense')
     return out
+
+
+# --------------------------------------------------------------------------------------
+# FPS / ball query / nearest 3-D voxel (fps_NN_fast, painting.py:276-323)
+# --------------------------------------------------------------------------------------
+def furthest_point_sample_single(xyz, m):
+    """xyz (n,3) f32 -> (m,) i32; start index 0, reference tie-break."""
+    xyz = xyz.contiguous().float()
+    n = xyz.shape[0]
+    idx = torch.empty((m,), dtype=torch.int32, device=xyz.device)
+    ws = scratch.get(xyz.device, lib().msmd_fps_workspace(n))
+    with _Timed('fps', n=n, m=int(m)):
+        check(lib().msmd_fps(ptr(xyz), n, int(m), ptr(idx), ptr(ws), ws.numel(), stream(xyz.device)),
+              'msmd_fps')
+    return idx
+
+
+def ball_query_single(min_radius, max_radius, nsample, xyz, center_xyz):
+    """xyz (n,3), center_xyz (m,3) f32 -> (m,nsample) i32."""
+    xyz, center_xyz = xyz.contiguous().float(), center_xyz.contiguous().float()
+    n, mc = xyz.shape[0], center_xyz.shape[0]
+    idx = torch.empty((mc, nsample), dtype=torch.int32, device=xyz.device)
+    with _Timed('ball_query', n=n, m=mc, nsample=int(nsample)):
+        check(lib().msmd_ball_query(ptr(xyz), n, ptr(center_xyz), mc, float(min_radius),
+                                    float(max_radius), int(nsample), ptr(idx), stream(xyz.device)),
+              'msmd_ball_query')
+    return idx
+
+
+def nn_search(query_zyx, key_zyx):
+    """(nq,3)/(nk,3) int32 voxel coordinates -> (val f32 (nq), idx i32 (nq))."""
+    q, k = query_zyx.contiguous(), key_zyx.contiguous()
+    assert q.dtype == torch.int32 and k.dtype == torch.int32
+    nq, nk = q.shape[0], k.shape[0]
+    val = torch.empty((nq,), dtype=torch.float32, device=q.device)
+    idx = torch.empty((nq,), dtype=torch.int32, device=q.device)
+    with _Timed('nn_search', nq=nq, nk=nk):
+        check(lib().msmd_nn_search(ptr(q), q.shape[1], nq, ptr(k), k.shape[1], nk, ptr(val), ptr(idx),
+                                   stream(q.device)), 'msmd_nn_search')
+    return val, idx
+
+
+def group_assign(group, val, nn_idx, dist_thresh, nq, base=0):
+    """query_NN_key_idx (nq,) int64: nearest key (+base) of each query's representative or -1."""
+    dev = val.device
+    out = torch.empty((nq,), dtype=torch.int64, device=dev)
+    if group is None:
+        m = nsample = 0
+        winner = None
+    else:
+        group = group.contiguous()
+        m, nsample = group.shape
+        winner = torch.empty((max(nq, 1),), dtype=torch.int32, device=dev)
+    with _Timed('group_assign', nq=nq, m=m):
+        check(lib().msmd_group_assign(ptr(group), m, nsample, ptr(val), ptr(nn_idx), float(dist_thresh),
+                                      nq, int(base), ptr(winner), ptr(out), stream(dev)),
+              'msmd_group_assign')
+    return out
+
+
+# --------------------------------------------------------------------------------------
+# voxel_modality_split (one sample), sparse_add, lift gather
+# --------------------------------------------------------------------------------------
+def modality_split_single(coord3, coord2, offset3=0, offset2=0):
+    """coord3 (n3,4) / coord2 (n2,4) int32 rows of one sample ->
+    (mix3 (n3) i32, mix2 (n2) i32, syn3 (P) i64, syn2 (P) i64)."""
+    coord3, coord2 = _indices_ok(coord3), _indices_ok(coord2)
+    dev = coord3.device
+    n3, n2 = coord3.shape[0], coord2.shape[0]
+    mix3 = torch.empty((n3,), dtype=torch.int32, device=dev)
+    mix2 = torch.empty((n2,), dtype=torch.int32, device=dev)
+    cap = max(1, min(n3, n2))
+    syn3 = torch.empty((cap,), dtype=torch.int64, device=dev)
+    syn2 = torch.empty((cap,), dtype=torch.int64, device=dev)
+    count = torch.zeros((1,), dtype=torch.int32, device=dev)
+    ws = scratch.get(dev, lib().msmd_modality_split_workspace(n3, n2))
+    with _Timed('modality_split', n3=n3, n2=n2):
+        check(lib().msmd_modality_split(ptr(coord3), n3, ptr(coord2), n2, int(offset3), int(offset2),
+                                        ptr(mix3), ptr(mix2), ptr(syn3), ptr(syn2), ptr(count), ptr(ws),
+                                        ws.numel(), stream(dev)), 'msmd_modality_split')
+    p = int(count.item())
+    return mix3, mix2, syn3[:p], syn2[:p]
+
+
+def sparse_add(idx_a, feat_a, idx_b, feat_b, spatial_shape, batch_size):
+    """Returns (out_indices ascending, out_features, BitGrid of the union)."""
+    idx_a, idx_b = _indices_ok(idx_a), _indices_ok(idx_b)
+    feat_a, feat_b = feat_a.contiguous().float(), feat_b.contiguous().float()
+    assert feat_a.shape[1] == feat_b.shape[1]
+    dev = idx_a.device
+    shape = _triple(spatial_shape)
+    B = int(batch_size)
+    words = lib().msmd_grid_num_words(B, ints(shape))
+    bits = torch.empty((words,), dtype=torch.int32, device=dev)
+    prefix = torch.empty((words,), dtype=torch.int32, device=dev)
+    count = torch.zeros((1,), dtype=torch.int32, device=dev)
+    ws = scratch.get(dev, lib().msmd_scan_workspace())
+    na, nb, c = idx_a.shape[0], idx_b.shape[0], feat_a.shape[1]
+    with _Timed('sparse_add_outputs', na=na, nb=nb, words=int(words)):
+        check(lib().msmd_sparse_add_outputs(ptr(idx_a), na, ptr(idx_b), nb, B, ints(shape), ptr(bits),
+                                            ptr(prefix), ptr(count), ptr(ws), ws.numel(), stream(dev)),
+              'msmd_sparse_add_outputs')
+    n_out = int(count.item())
+    out_idx = torch.empty((n_out, 4), dtype=torch.int32, device=dev)
+    out_feat = torch.empty((n_out, c), dtype=torch.float32, device=dev)
+    with _Timed('sparse_add_finish', n_out=n_out, c=c):
+        check(lib().msmd_sparse_add_finish(ptr(bits), ptr(prefix), n_out, ptr(idx_a), ptr(feat_a), na,
+                                           ptr(idx_b), ptr(feat_b), nb, c, B, ints(shape), ptr(out_idx),
+                                           ptr(out_feat), stream(dev)), 'msmd_sparse_add_finish')
+    return out_idx, out_feat, BitGrid(bits, prefix, None, shape, B, count)
+
+
+def lift_gather(img_feat, pixels, cam_ids, points, lidar2img, downscale, score_weight, score_bias):
+    """img_feat (ncam,C,h,w) any strides; pixels (M,3) f32; cam_ids (M) i32; points (M,P) f32;
+    lidar2img (ncam,16) f32; score_weight (C+17) f32 -> (M, P+C) f32."""
+    assert img_feat.dim() == 4 and img_feat.dtype == torch.float32
+    ncam, C, h, w = img_feat.shape
+    pixels, points = pixels.contiguous().float(), points.contiguous().float()
+    cam_ids = cam_ids.contiguous().int()
+    lidar2img = lidar2img.contiguous().float()
+    score_weight = score_weight.detach().contiguous().float().view(-1)
+    assert score_weight.numel() == C + 17 and lidar2img.shape == (ncam, 16)
+    M, P = points.shape
+    out = torch.empty((M, P + C), dtype=torch.float32, device=points.device)
+    if not img_feat.is_cuda:
+        raise RuntimeError('lift_gather needs CUDA tensors (no CPU fallback)')
+    s = img_feat.stride()
+    with _Timed('lift_gather', m=M, c=C):
+        check(lib().msmd_lift_gather(_cabi.ctypes.c_void_p(img_feat.data_ptr()), s[0], s[1], s[2], s[3],
+                                     C, h, w, ptr(pixels), ptr(cam_ids), ptr(points), P, M,
+                                     ptr(lidar2img), float(downscale), ptr(score_weight),
+                                     float(score_bias), ptr(out), stream(points.device)),
+              'msmd_lift_gather')
+    return out

@@ -189,7 +189,19 @@ def is_spconv_module(module):
 
 
 def _bn_scale_shift(bn):
-    """Fold an eval-mode BatchNorm1d into y = x*scale + shift (fp32)."""
+    """Fold an eval-mode BatchNorm1d into y = x*scale + shift (fp32).  Cached on the module,
+    keyed by the versions of its parameters/buffers, so inference folds each BN once."""
+    key = tuple((t.data_ptr(), t._version) for t in
+                (bn.weight, bn.bias, bn.running_mean, bn.running_var) if t is not None)
+    cached = getattr(bn, '_msmd_fold', None)
+    if cached is not None and cached[0] == key:
+        return cached[1], cached[2]
+    scale, shift = _bn_scale_shift_compute(bn)
+    bn._msmd_fold = (key, scale, shift)
+    return scale, shift
+
+
+def _bn_scale_shift_compute(bn):
     inv = torch.rsqrt(bn.running_var.float() + bn.eps)
     w = bn.weight.detach().float() if bn.weight is not None else torch.ones_like(inv)
     b = bn.bias.detach().float() if bn.bias is not None else torch.zeros_like(inv)

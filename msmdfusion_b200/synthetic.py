@@ -61,3 +61,102 @@ def random_points(n, c, seed=0, pc_range=POINT_CLOUD_RANGE, margin=1.05):
     xyz = (mid + (rng.random((n, 3), dtype=np.float32) * 2 - 1) * half).astype(np.float32)
     extra = rng.random((n, max(c - 3, 0)), dtype=np.float32)
     return np.ascontiguousarray(np.concatenate([xyz, extra], 1)[:, :c])
+
+
+# --------------------------------------------------------------------------------------
+# cameras + virtual points (SURVEY.md section 8(d) config 3, Appendix B input schema)
+# --------------------------------------------------------------------------------------
+INPUT_SHAPE = (448, 800)          # network-input (H, W), configs/MSMDFusion_nusc_voxel_LC.py:17,55-57
+CAMERA_YAWS_DEG = (0.0, -55.0, 55.0, 180.0, 110.0, -110.0)  # front, front-right/left, back, back-left/right
+
+
+def camera_matrices(seed=0):
+    """Six synthetic ``lidar2img`` (4,4) float64 matrices for an 800x448 input image
+    (nuScenes intrinsics scaled by 0.5; camera x right, y down, z forward)."""
+    rng = np.random.default_rng(seed + 1000)
+    H, W = INPUT_SHAPE
+    f = 633.0
+    K = np.array([[f, 0, W / 2.0, 0], [0, f, H / 2.0, 0], [0, 0, 1, 0], [0, 0, 0, 1]], np.float64)
+    mats = []
+    for yaw_deg in CAMERA_YAWS_DEG:
+        yaw = np.deg2rad(yaw_deg + rng.normal(0, 0.5))
+        fwd = np.array([np.cos(yaw), np.sin(yaw), 0.0])
+        right = np.array([np.sin(yaw), -np.cos(yaw), 0.0])
+        down = np.array([0.0, 0.0, -1.0])
+        R = np.stack([right, down, fwd], 0)                  # lidar -> camera axes
+        t = -R @ (np.array([0.0, 0.0, 1.5]) + 0.8 * fwd)     # camera 1.5 m up, 0.8 m ahead
+        E = np.eye(4)
+        E[:3, :3], E[:3, 3] = R, t
+        mats.append(K @ E)
+    return mats
+
+
+def project(points_xyz, lidar2img):
+    """(N,3) lidar points -> (u, v, depth) in network-input pixels + in-image mask."""
+    H, W = INPUT_SHAPE
+    p = np.concatenate([points_xyz.astype(np.float64), np.ones((points_xyz.shape[0], 1))], 1) @ lidar2img.T
+    depth = p[:, 2]
+    with np.errstate(divide='ignore', invalid='ignore'):
+        u, v = p[:, 0] / depth, p[:, 1] / depth
+    ok = (depth > 0.5) & (u >= 0) & (u < W - 1e-3) & (v >= 0) & (v < H - 1e-3)
+    return np.stack([u, v, depth], 1), ok
+
+
+def camera_scene(seed=0, lidar_points=None, virtual_per_camera=10000, real_per_camera=2000,
+                 boxes_per_camera=4, empty_cameras=()):
+    """One sample's ``img_metas`` entry: ``lidar2img``, ``input_shape``, ``pad_shape`` and
+    ``foreground2D_info`` = {fg_pixels, fg_points, fg_real_pixels} per camera (Appendix B).
+
+    Virtual points are sampled inside random object boxes in each camera's frustum (15 dims =
+    xyz + 10 one-hot class + score + dt); real pixels are projected LiDAR returns.
+    """
+    rng = np.random.default_rng(seed + 2000)
+    mats = camera_matrices(seed)
+    fg_pixels, fg_points, fg_real = [], [], []
+    for cam, (mat, yaw_deg) in enumerate(zip(mats, CAMERA_YAWS_DEG)):
+        if cam in empty_cameras:
+            fg_pixels.append(np.zeros((0, 3), np.float32))
+            fg_points.append(np.zeros((0, 15), np.float32))
+            fg_real.append(np.zeros((0, 3), np.float32))
+            continue
+        yaw = np.deg2rad(yaw_deg)
+        pts = []
+        for _ in range(boxes_per_camera):
+            dist = rng.uniform(6.0, 45.0)
+            ang = yaw + np.deg2rad(rng.uniform(-25, 25))
+            centre = np.array([dist * np.cos(ang), dist * np.sin(ang), rng.uniform(-1.5, 0.0)])
+            size = np.array([rng.uniform(1.5, 5.0), rng.uniform(1.5, 2.5), rng.uniform(1.4, 2.5)])
+            n = 2 * virtual_per_camera // boxes_per_camera
+            local = (rng.random((n, 3)) - 0.5) * size
+            byaw = rng.uniform(0, np.pi)
+            c, s = np.cos(byaw), np.sin(byaw)
+            local[:, :2] = local[:, :2] @ np.array([[c, -s], [s, c]]).T
+            cls = rng.integers(0, 10)
+            onehot = np.zeros((n, 10), np.float32)
+            onehot[:, cls] = 1.0
+            score = np.full((n, 1), rng.uniform(0.3, 1.0), np.float32)
+            pts.append(np.concatenate([(local + centre).astype(np.float32), onehot, score,
+                                       np.zeros((n, 1), np.float32)], 1))
+        pts = np.concatenate(pts, 0)
+        pix, ok = project(pts[:, :3], mat)
+        inside = (np.abs(pts[:, 0]) < 53.9) & (np.abs(pts[:, 1]) < 53.9) & (pts[:, 2] > -4.9) & (pts[:, 2] < 2.9)
+        keep = np.nonzero(ok & inside)[0][:virtual_per_camera]
+        fg_pixels.append(np.ascontiguousarray(pix[keep], np.float32))
+        fg_points.append(np.ascontiguousarray(pts[keep], np.float32))
+        if lidar_points is not None and lidar_points.shape[0]:
+            rpix, rok = project(lidar_points[:, :3], mat)
+            ridx = np.nonzero(rok)[0]
+            if ridx.shape[0] > real_per_camera:
+                ridx = rng.choice(ridx, real_per_camera, replace=False)
+            fg_real.append(np.ascontiguousarray(rpix[ridx], np.float32))
+        else:
+            fg_real.append(np.zeros((0, 3), np.float32))
+    return dict(lidar2img=mats, input_shape=INPUT_SHAPE, pad_shape=(INPUT_SHAPE[0], INPUT_SHAPE[1], 3),
+                foreground2D_info=dict(fg_pixels=fg_pixels, fg_points=fg_points, fg_real_pixels=fg_real))
+
+
+def fpn_features(seed=0, batch=1, ncam=6, channels=256):
+    """Random stand-ins for the three FPN levels the lift reads (strides 4, 8, 16 of 448x800)."""
+    rng = np.random.default_rng(seed + 3000)
+    H, W = INPUT_SHAPE
+    return [rng.standard_normal((batch * ncam, channels, H // s, W // s), dtype=np.float32) for s in (4, 8, 16)]

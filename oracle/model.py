@@ -103,3 +103,133 @@ def voxelize_batch(points_list, voxel_size, coors_range, max_points, max_voxels)
         nums.append(n)
         coors.append(np.concatenate([np.full((c.shape[0], 1), i, np.int32), c], 1))
     return np.concatenate(voxels, 0), np.concatenate(nums, 0), np.concatenate(coors, 0)
+
+
+# --------------------------------------------------------------------------------------
+# Fusion side: get_foreground2D -> fetch_2D_voxels -> voxel_modality_split (cpu.py) ->
+# SparseMultiModalEncoderPaint
+# --------------------------------------------------------------------------------------
+def _linear_relu(sd, prefix, x):
+    w, b = _np(sd, prefix + '.weight').astype(np.float32), _np(sd, prefix + '.bias').astype(np.float32)
+    return np.maximum(x.astype(np.float32) @ w.T + b, 0).astype(np.float32)
+
+
+def depth_canvas(img_metas, H, W):
+    """mmdet3d/models/detectors/MSMDFusion.py:335-356: (B*6, 1, H, W) sparse depth map; duplicate
+    pixels -> the last real point in input order wins (sequential index_put_)."""
+    B = len(img_metas)
+    ncam = len(img_metas[0]['foreground2D_info']['fg_real_pixels'])
+    canvas = np.zeros((B, ncam, H, W), np.float32)
+    for i, meta in enumerate(img_metas):
+        for j in range(ncam):
+            r = np.asarray(meta['foreground2D_info']['fg_real_pixels'][j], np.float32)
+            coors = r[:, :2].astype(np.int64)  # .long(): truncation
+            for k in range(r.shape[0]):
+                canvas[i, j, coors[k, 1], coors[k, 0]] = r[k, 2]
+    return canvas.reshape(B * ncam, 1, H, W)
+
+
+def get_foreground2d(img_feats, img_metas, score_w, score_b):
+    """MSMDFusion.py:169-238.  img_feats (B*ncam, C, h, w) -> list (len B) of (M_b, 15+C)."""
+    B = len(img_metas)
+    BN, C, h, w = img_feats.shape
+    ncam = BN // B
+    input_w = img_metas[0]['input_shape'][-1]
+    out = []
+    for b, meta in enumerate(img_metas):
+        info = meta['foreground2D_info']
+        cams = []
+        for v in range(ncam):
+            pix = np.asarray(info['fg_pixels'][v], np.float32).reshape(-1, 3)
+            pts = np.asarray(info['fg_points'][v], np.float32).reshape(pix.shape[0], -1)
+            cams.append(cpu.lift_gather(img_feats[b * ncam + v], pix, pts, np.asarray(meta['lidar2img'][v]),
+                                        score_w, score_b, input_w))
+        out.append(np.concatenate(cams, 0))
+    return out
+
+
+def fetch_2d_voxels(img_feats, img_metas, score_w, score_b, spatial_shape, downscale_factor,
+                    base_voxel_size, coors_range, max_points, max_voxels):
+    """MSMDFusion.py:371-393 -> SpTensor((V,64) mean features with xyz / (13.5,13.5,2), (V,4))."""
+    B = len(img_metas)
+    fg = get_foreground2d(img_feats, img_metas, score_w, score_b)
+    for i in range(B):
+        if fg[i].shape[0] == 0:
+            fg[i] = np.zeros((100, fg[i].shape[1]), np.float32)
+    vs = [float(x) * downscale_factor for x in base_voxel_size]
+    voxels, nums, coors = voxelize_batch(fg, vs, coors_range, max_points, max_voxels)
+    feat = cpu.hard_simple_vfe(voxels, nums, voxels.shape[-1])
+    feat[:, :3] = feat[:, :3] / np.array([13.5, 13.5, 2.0], np.float32)[None, :]
+    return SpTensor(feat.astype(np.float32), coors, spatial_shape, B)
+
+
+def _pad_missing_batch_id(indices, features, B):
+    """sparse_multimodal_encoder_painting.py:208-225."""
+    present = set(np.unique(indices[:, 0]).tolist())
+    for b in range(B):
+        if b not in present:
+            pad_i = np.zeros((1, indices.shape[1]), indices.dtype)
+            pad_i[0, 0] = b
+            indices = np.concatenate([indices, pad_i], 0)
+            features = np.concatenate([features, np.zeros((1, features.shape[1]), features.dtype)], 0)
+    return indices, features
+
+
+def grouped_sparse_conv(sd, prefix, v3, v2, syn3, syn2, stage_id, c3, fps_num, radius, nsample, thresh,
+                        dummy_embedding, eps):
+    """sparse_multimodal_encoder_painting.py:325-430.  v3 / v2 carry (N,5) indices (b,mix,z,y,x)."""
+    B = v3.batch_size
+    ind3, ind2, f3, f2 = v3.indices, v2.indices, v3.features, v2.features
+    only3 = ind3[:, 1] == 0
+    only2 = ind2[:, 1] == 0
+    o2_idx, o2_feat = _pad_missing_batch_id(ind2[only2], f2[only2], B)
+    o2_bzyx = o2_idx[:, [0, 2, 3, 4]]
+    v3_bzyx = ind3[:, [0, 2, 3, 4]]
+    nn = np.full((o2_bzyx.shape[0],), -1, np.int64)
+    base = 0
+    for b in np.unique(v3_bzyx[:, 0]).tolist():        # :355-369 (B = #batch ids present in voxel_3D)
+        m2 = o2_bzyx[:, 0] == b
+        m3 = v3_bzyx[:, 0] == b
+        r = cpu.fps_nn_fast(o2_bzyx[m2], v3_bzyx[m3], fps_num, radius, nsample, thresh)
+        r[r != -1] += base
+        nn[m2] = r
+        base = int(m3.sum())
+    cross = _linear_relu(sd, f'{prefix}cross_gate_control.{stage_id}.0',
+                         np.concatenate([f3, dummy_embedding.reshape(1, -1).astype(np.float32)], 0))
+    o2_feat = cross[nn] * o2_feat                        # -1 -> last row = dummy embedding's gate
+    x3 = SpTensor(f3[only3], np.ascontiguousarray(ind3[only3][:, [0, 2, 3, 4]]), v3.spatial_shape, B)
+    m3f, m2f = f3[syn3], f2[syn2]
+    gate = _linear_relu(sd, f'{prefix}gate_control.{stage_id}.0', m3f)
+    mixed_feat = np.concatenate([m3f, gate * m2f], 1)
+    mixed_idx, mixed_feat = _pad_missing_batch_id(ind2[syn2], mixed_feat, B)
+    name = f'stage_{stage_id + 1}'
+    x3 = convmodule(sd, f'{prefix}grouped_sp_conv_blocks_3D.{name}', x3, 'SubMConv3d', 3, 1, 1, eps)
+    o2_feat = np.pad(o2_feat, ((0, 0), (c3, 0)))
+    o3_feat = np.pad(x3.features, ((0, 0), (0, 64)))
+    feat = np.concatenate([o3_feat, o2_feat, mixed_feat], 0).astype(np.float32)
+    coors = np.concatenate([x3.indices, o2_bzyx, mixed_idx[:, [0, 2, 3, 4]]], 0).astype(np.int32)
+    uni = SpTensor(feat, np.ascontiguousarray(coors), v2.spatial_shape, B)
+    return basic_block(sd, f'{prefix}aggregation_blocks.{name}', uni, eps)
+
+
+def multimodal_encoder(sd, cfg, v3_list, v2_list, syn3_list, syn2_list, fps_num_list, radius_list,
+                       nsample_list, thresh_list, dummy_embeddings, prefix=''):
+    """SparseMultiModalEncoderPaint.forward (:433-459).  dummy_embeddings[s] = the torch.rand(1,C3)
+    draw of stage s (the caller draws them from the same seeded CPU generator)."""
+    eps = cfg.get('norm_cfg', dict(eps=1e-3)).get('eps', 1e-3)
+    c3s = cfg.get('in_channels_3D', (16, 32, 64, 128))
+    pads = cfg.get('padding', (1, 1, 1, [0, 1, 1]))
+    ksz = cfg.get('down_kernel_size', (3, 3, 3, [3, 1, 1]))
+    strides = cfg.get('down_stride', (2, 2, 2, [2, 1, 1]))
+    outs = []
+    for s in range(len(v2_list)):
+        x = grouped_sparse_conv(sd, prefix, v3_list[s], v2_list[s], syn3_list[s], syn2_list[s], s, c3s[s],
+                                fps_num_list[s], radius_list[s], nsample_list[s], thresh_list[s],
+                                dummy_embeddings[s], eps)
+        if s > 0:
+            oi, of = cpu.sparse_add(x.indices, x.features, outs[s - 1].indices, outs[s - 1].features,
+                                    x.spatial_shape)
+            x = SpTensor(of, oi, x.spatial_shape, x.batch_size)
+        outs.append(convmodule(sd, f'{prefix}downscale_blocks.stage_{s + 1}', x, 'SparseConv3d', ksz[s],
+                               strides[s], pads[s], eps))
+    return outs

@@ -363,3 +363,258 @@ def test_sparse_encoder_end_to_end(batch):
         assert np.array_equal(g.indices.cpu().numpy(), e.indices)          # bit-exact indices
         assert np.abs(g.features.cpu().numpy() - e.features).max() < FEAT_TOL
     assert np.abs(spatial.cpu().numpy() - e_spatial).max() < FEAT_TOL
+
+
+# --------------------------------------------------------------------------------------
+# fusion-side ops: FPS, ball query, nearest 3-D voxel, modality split, sparse_add, lift
+# --------------------------------------------------------------------------------------
+def voxel_cloud(rng, n, shape, clusters=12, spread=9.0):
+    """Unique integer (z,y,x) voxel coordinates clustered like foreground objects."""
+    D, H, W = shape
+    centres = np.stack([rng.integers(0, D, clusters), rng.integers(0, H, clusters),
+                        rng.integers(0, W, clusters)], 1)
+    pts = centres[rng.integers(0, clusters, 4 * n)] + \
+        np.round(rng.normal(0, 1, (4 * n, 3)) * np.array([1.5, spread, spread])).astype(np.int64)
+    pts = pts[(pts[:, 0] >= 0) & (pts[:, 0] < D) & (pts[:, 1] >= 0) & (pts[:, 1] < H) &
+              (pts[:, 2] >= 0) & (pts[:, 2] < W)]
+    _, first = np.unique(pts, axis=0, return_index=True)
+    pts = pts[np.sort(first)][:n]
+    return pts.astype(np.int32)
+
+
+@pytest.mark.parametrize('n,m', [(5, 3), (37, 20), (1000, 64), (4097, 512), (20000, 2048), (70000, 256)])
+def test_fps_bit_exact_on_voxel_coordinates(n, m):
+    """Integer coordinates: ties everywhere, so this checks the arg-max tie-break
+    (furthest_point_sample_cuda.cu:17-23,:69-70) and not just distances."""
+    rng = np.random.default_rng(n)
+    xyz = voxel_cloud(rng, n, [41, 400, 400]).astype(np.float32)
+    n = xyz.shape[0]
+    m = min(m, n)
+    got = ops.furthest_point_sample_single(cuda(xyz), m).cpu().numpy()
+    assert np.array_equal(got, cpu.furthest_point_sample(xyz, m))
+
+
+def test_fps_reference_known_answer():
+    """tests/test_models/test_common_modules/test_pointnet_ops.py:9-23 of the reference."""
+    from test_oracle import BQ_XYZ  # noqa: F401  (same module-level fixtures)
+    xyz = np.array([[-0.2748, 1.0020, -1.1674], [0.1015, 1.3952, -1.2681], [-0.8070, 2.4137, -0.5845],
+                    [-1.0001, 2.1982, -0.5859], [0.3841, 1.8983, -0.7431]], np.float32)
+    assert ops.furthest_point_sample_single(cuda(xyz), 3).cpu().tolist() == [0, 2, 4]
+
+
+def test_ball_query_reference_known_answer():
+    from test_oracle import BQ_EXPECT_0, BQ_EXPECT_1, BQ_NEW, BQ_XYZ
+    for (rmin, rmax, exp) in ((0, 0.2, BQ_EXPECT_0), (0.2, 0.4, BQ_EXPECT_1)):
+        for b in range(2):
+            got = ops.ball_query_single(rmin, rmax, 5, cuda(BQ_XYZ[b]), cuda(BQ_NEW[b])).cpu().numpy()
+            assert np.array_equal(got, exp[b])
+
+
+@pytest.mark.parametrize('n,m,radius,nsample', [(3000, 256, 6, 200), (20000, 2048, 3, 100), (500, 64, 1, 25),
+                                               (10, 4, 2, 50)])
+def test_ball_query_bit_exact(n, m, radius, nsample):
+    rng = np.random.default_rng(n + m)
+    xyz = voxel_cloud(rng, n, [21, 300, 300]).astype(np.float32)
+    centers = xyz[rng.choice(xyz.shape[0], min(m, xyz.shape[0]), replace=False)].copy()
+    centers[::7] += 1000.0  # centres with no neighbour keep the zero-initialised row
+    got = ops.ball_query_single(0, radius, nsample, cuda(xyz), cuda(centers)).cpu().numpy()
+    assert np.array_equal(got, cpu.ball_query(0, radius, nsample, xyz, centers))
+
+
+@pytest.mark.parametrize('nq,nk', [(1, 1), (300, 5000), (2048, 60000)])
+def test_nn_search_bit_exact(nq, nk):
+    rng = np.random.default_rng(nq)
+    q = voxel_cloud(rng, nq, [41, 500, 500])
+    k = voxel_cloud(rng, nk, [41, 500, 500])
+    val, idx = ops.nn_search(cuda(q), cuda(k))
+    eval_, eidx = cpu.nn_search(q, k)
+    assert np.array_equal(idx.cpu().numpy(), eidx)
+    assert np.array_equal(val.cpu().numpy(), eval_)
+
+
+@pytest.mark.parametrize('Q,fps_num,radius,nsample,thresh', [(900, 2048, 6, 200, 13.3), (9000, 2048, 6, 200, 13.3),
+                                                           (6000, 512, 2, 50, 3.3), (3000, 256, 1, 25, 1.6)])
+def test_fps_nn_fast_matches_oracle(Q, fps_num, radius, nsample, thresh):
+    """sparse_multimodal_encoder_painting.py:276-323 composed from the C-ABI ops."""
+    from msmdfusion_b200 import fusion_encoder
+    rng = np.random.default_rng(Q)
+    shape = [41, 360, 360]
+    q = voxel_cloud(rng, Q, shape)
+    k = voxel_cloud(rng, 7000, shape)
+    q4 = np.concatenate([np.zeros((q.shape[0], 1), np.int32), q], 1)
+    k4 = np.concatenate([np.zeros((k.shape[0], 1), np.int32), k], 1)
+    got = fusion_encoder.fps_nn_fast(cuda(q4), cuda(k4), fps_num, radius, nsample, thresh).cpu().numpy()
+    exp = cpu.fps_nn_fast(q4, k4, fps_num, radius, nsample, thresh)
+    assert got.dtype == np.int64 and np.array_equal(got, exp)
+
+
+def test_modality_split_bit_exact():
+    rng = np.random.default_rng(5)
+    shape = [41, 1440, 1440]
+    i3 = voxel_cloud(rng, 20000, shape, clusters=40, spread=30)
+    i2 = voxel_cloud(rng, 30000, shape, clusters=40, spread=30)
+    take = rng.choice(i3.shape[0], 6000, replace=False)
+    i2[:6000] = i3[take]
+    i2 = i2[rng.permutation(i2.shape[0])]
+    # duplicates inside one set and float-key near-misses (z >= 17: neighbouring x collide)
+    i2[100:110] = i2[90:100]
+    for b in (0, 1):
+        c3 = np.concatenate([np.full((i3.shape[0], 1), b, np.int32), i3], 1)
+        c2 = np.concatenate([np.full((i2.shape[0], 1), b, np.int32), i2], 1)
+        mix3, mix2, syn3, syn2 = ops.modality_split_single(cuda(c3), cuda(c2), offset3=7, offset2=11)
+        z3, z2 = c3.copy(), c2.copy()
+        z3[:, 0] = 0
+        z2[:, 0] = 0  # the oracle selects rows by batch id; one sample per call here
+        e3, e2, es3, es2 = cpu.voxel_modality_split(z3, z2, 1)
+        assert np.array_equal(mix3.cpu().numpy(), e3[:, 1])
+        assert np.array_equal(mix2.cpu().numpy(), e2[:, 1])
+        assert np.array_equal(syn3.cpu().numpy(), es3 + 7)
+        assert np.array_equal(syn2.cpu().numpy(), es2 + 11)
+        assert syn3.shape[0] >= 6000
+
+
+def test_modality_split_empty_sets():
+    c3 = np.array([[0, 1, 2, 3]], np.int32)
+    empty = np.zeros((0, 4), np.int32)
+    mix3, mix2, syn3, syn2 = ops.modality_split_single(cuda(c3), cuda(empty))
+    assert mix3.cpu().tolist() == [0] and mix2.numel() == 0 and syn3.numel() == 0 and syn2.numel() == 0
+
+
+@pytest.mark.parametrize('shape,batch,na,nb,c', [([5, 8, 9], 2, 120, 150, 4), ([11, 360, 360], 1, 30000, 20000, 128),
+                                                 ([2, 180, 180], 2, 5000, 1, 192), ([3, 4, 5], 1, 0, 7, 3)])
+def test_sparse_add_matches_oracle(shape, batch, na, nb, c):
+    rng = np.random.default_rng(na + nb)
+    ia = random_indices(rng, batch, shape, na)
+    ib = random_indices(rng, batch, shape, nb)
+    if na and nb:
+        ib[: min(na, nb) // 2] = ia[: min(na, nb) // 2]
+    fa = rng.standard_normal((ia.shape[0], c)).astype(np.float32)
+    fb = rng.standard_normal((ib.shape[0], c)).astype(np.float32)
+    oi, of, grid = ops.sparse_add(cuda(ia), cuda(fa), cuda(ib), cuda(fb), shape, batch)
+    ei, ef = cpu.sparse_add(ia, fa, ib, fb, shape)
+    assert np.array_equal(oi.cpu().numpy(), ei)
+    assert np.array_equal(of.cpu().numpy(), ef)  # a + b of two fp32 values: exact in either order
+    assert int(grid.num_active.item()) == ei.shape[0]
+
+
+def test_lift_gather_matches_oracle():
+    rng = np.random.default_rng(9)
+    ncam, C, h, w = 6, 49, 112, 200
+    input_w = 800
+    img = rng.standard_normal((ncam, C, h, w)).astype(np.float32)
+    score_w = (rng.standard_normal(C + 17) * 0.1).astype(np.float32)
+    score_b = 0.05
+    outs, pix_all, pts_all, cam_all, l2i = [], [], [], [], []
+    for cam in range(ncam):
+        M = int(rng.integers(0, 3000))
+        pix = np.stack([rng.uniform(0, 799.99, M), rng.uniform(0, 447.99, M), rng.uniform(1, 60, M)], 1).astype(np.float32)
+        pts = rng.standard_normal((M, 15)).astype(np.float32)
+        mat = rng.standard_normal((4, 4))
+        outs.append(cpu.lift_gather(img[cam], pix, pts, mat, score_w, score_b, input_w))
+        pix_all.append(pix); pts_all.append(pts); cam_all.append(np.full((M,), cam, np.int32))
+        l2i.append(mat.reshape(16).astype(np.float32))
+    exp = np.concatenate(outs, 0)
+    for layout in ('nchw', 'nhwc'):
+        feat = cuda(img)
+        if layout == 'nhwc':
+            feat = feat.permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2)
+        got = ops.lift_gather(feat, cuda(np.concatenate(pix_all)), cuda(np.concatenate(cam_all)),
+                              cuda(np.concatenate(pts_all)), cuda(np.stack(l2i)), w / input_w,
+                              cuda(score_w), score_b).cpu().numpy()
+        assert np.array_equal(got[:, :15], exp[:, :15])
+        assert np.abs(got - exp).max() < FEAT_TOL
+
+
+# --------------------------------------------------------------------------------------
+# detector level: lift -> multi-scale virtual-point voxels -> modality split -> GMA encoder
+# --------------------------------------------------------------------------------------
+def build_msmd_detector(seed=0):
+    cfg = m.Config.fromfile(os.path.join(ROOT, 'configs', 'msmd_lc_hotpath.py')).hotpath
+    torch.manual_seed(seed)
+    det = m.MSMDFusionDetector(**{k: cfg[k] for k in (
+        'pts_voxel_layer', 'pts_voxel_encoder', 'pts_middle_encoder', 'multimodal_middle_encoder',
+        'spatial_shapes', 'downscale_factors', 'fps_num_list', 'radius_list', 'max_cluster_samples_list',
+        'dist_thresh_list')}).to(dev())
+    randomize_bn(det, seed + 1)
+    with torch.no_grad():  # make the ReLU score gate open for roughly half of the points
+        det.score_net[0].weight.mul_(0.2)
+        det.score_net[0].bias.fill_(0.05)
+    return det.eval(), cfg
+
+
+def test_depth_canvas_matches_oracle():
+    det, _ = build_msmd_detector()
+    pts = synthetic.lidar_scene(3, 1)
+    metas = [synthetic.camera_scene(3, pts, virtual_per_camera=10), synthetic.camera_scene(4, pts, virtual_per_camera=10)]
+    for meta in metas:  # force duplicate pixels: the last point in input order must win
+        r = meta['foreground2D_info']['fg_real_pixels'][0]
+        r[-50:, :2] = r[:50, :2]
+    H, W = synthetic.INPUT_SHAPE
+    captured = {}
+    orig = torch.nn.functional.interpolate
+
+    def spy(canvas, size, mode='nearest', **kw):
+        captured.setdefault('canvas', canvas.clone())
+        return orig(canvas, size, mode=mode, **kw)
+    feats = [cuda(f) for f in synthetic.fpn_features(0, batch=2)]
+    torch.nn.functional.interpolate = spy
+    try:
+        with torch.no_grad():
+            out = det.depth_aware_channel_compression(feats, metas)
+    finally:
+        torch.nn.functional.interpolate = orig
+    assert [tuple(o.shape) for o in out] == [(12, 49, 112, 200), (12, 49, 56, 100), (12, 49, 28, 50)]
+    assert np.array_equal(captured['canvas'].cpu().numpy(), omodel.depth_canvas(metas, H, W))
+
+
+@pytest.mark.parametrize('batch', [1, 2])
+def test_msmd_voxel_space_end_to_end(batch):
+    """configs[2] slice: LiDAR encoder + 4-scale virtual-point voxels + modality split + GMA encoder
+    + sparse_add + downscale + dense, CUDA path vs the CPU oracle on the same seeded scene."""
+    det, cfg = build_msmd_detector(1)
+    scenes = [synthetic.lidar_scene(30 + b, 1) for b in range(batch)]
+    metas = [synthetic.camera_scene(30 + b, scenes[b], virtual_per_camera=3000 if b == 0 else 300,
+                                    empty_cameras=(() if b == 0 else (2,))) for b in range(batch)]
+    fpn = [cuda(f) for f in synthetic.fpn_features(1, batch=batch)]
+    pts_t = [cuda(s) for s in scenes]
+    torch.manual_seed(77)
+    dummies = [torch.rand(1, c).numpy() for c in cfg.multimodal_middle_encoder['in_channels_3D']]
+    torch.manual_seed(77)
+    with torch.no_grad():
+        bev, stage_outs = det.extract_voxel_space(pts_t, fpn, metas)
+        comp = det.depth_aware_channel_compression(fpn, metas)
+    torch.cuda.synchronize()
+    assert bev.shape == (batch, 256 + 384, 180, 180)
+
+    # ---- oracle ----
+    sd = {k: v.cpu() for k, v in det.state_dict().items()}
+    ev, en, ec = omodel.voxelize_batch(scenes, synthetic.VOXEL_SIZE, synthetic.POINT_CLOUD_RANGE, 10, 160000)
+    emean = cpu.hard_simple_vfe(ev, en, 5)
+    e_spatial, e_feats, _ = omodel.sparse_encoder(sd, dict(cfg.pts_middle_encoder), emean, ec, batch,
+                                                  prefix='pts_middle_encoder.')
+    comp_np = [c.cpu().numpy() for c in comp]
+    img_list = [comp_np[0]] + comp_np
+    score_w = sd['score_net.0.weight'].numpy().reshape(-1)
+    score_b = float(sd['score_net.0.bias'].item())
+    v3l, v2l, s3l, s2l = [], [], [], []
+    for i in range(4):
+        v2 = omodel.fetch_2d_voxels(img_list[i], metas, score_w, score_b, cfg.spatial_shapes[i],
+                                    cfg.downscale_factors[i], synthetic.VOXEL_SIZE,
+                                    synthetic.POINT_CLOUD_RANGE, 10, 160000)
+        v3 = e_feats[i]
+        c3, c2, s3, s2 = cpu.voxel_modality_split(v3.indices, v2.indices, batch)
+        v3l.append(omodel.SpTensor(v3.features, c3, v3.spatial_shape, batch))
+        v2l.append(omodel.SpTensor(v2.features, c2, v2.spatial_shape, batch))
+        s3l.append(s3)
+        s2l.append(s2)
+    e_outs = omodel.multimodal_encoder(sd, dict(cfg.multimodal_middle_encoder), v3l, v2l, s3l, s2l,
+                                       cfg.fps_num_list, cfg.radius_list, cfg.max_cluster_samples_list,
+                                       cfg.dist_thresh_list, dummies, prefix='multimodal_middle_encoder.')
+    for g, e in zip(stage_outs, e_outs):
+        assert g.spatial_shape == e.spatial_shape
+        assert np.array_equal(g.indices.cpu().numpy(), e.indices)            # bit-exact indices
+        err = np.abs(g.features.cpu().numpy() - e.features).max()
+        assert err < FEAT_TOL, err
+    e_mm = cpu.dense(e_outs[-1].indices, e_outs[-1].features, e_outs[-1].spatial_shape, batch)
+    e_bev = np.concatenate([e_spatial, e_mm.reshape(batch, -1, 180, 180)], 1)
+    assert np.abs(bev.cpu().numpy() - e_bev).max() < FEAT_TOL
