@@ -132,6 +132,20 @@ MSMD_API int msmd_spconv_fwd(const float* features, int n_in, const float* packe
                     const float* scale, const float* shift, const float* residual, int relu,
                     float* out, msmd_stream_t stream);
 
+/* Tensor-core path of the same contraction (tcgen05.mma kind::tf32, accumulator in TMEM,
+ * fp32-level accuracy through the 3xTF32 split  A_hi*B_hi + A_lo*B_hi + A_hi*B_lo).
+ *   packed_tc: the weight re-packed once into the shared-memory image the tensor core reads
+ *   (msmd_spconv_tc_packed_floats() floats, 16-byte aligned).  Supported: cout <= 256,
+ *   kvol <= 32 (msmd_spconv_tc_supported); everything else uses msmd_spconv_fwd. */
+MSMD_API int msmd_spconv_tc_supported(int cout, int kvol, int cin);
+MSMD_API size_t msmd_spconv_tc_packed_floats(int cout, int kvol, int cin);
+MSMD_API int msmd_spconv_tc_pack_weight(const float* weight_krsc, int cout, int kvol, int cin,
+                                        float* packed_tc, msmd_stream_t stream);
+MSMD_API int msmd_spconv_fwd_tc(const float* features, int n_in, const float* packed_tc,
+                                const int* pair_fwd, int n_out, int cin, int cout, int kvol,
+                                const float* scale, const float* shift, const float* residual,
+                                int relu, float* out, msmd_stream_t stream);
+
 /* SparseConvTensor.dense(): (n,c) rows -> (batch, c, D, H, W), zero-filled inside.
  * spconv-1.x equivalent mmdet3d/ops/spconv/structure.py:54-66. */
 MSMD_API int msmd_to_dense(const int* indices, const float* features, int n, int c, int batch_size,

@@ -37,6 +37,10 @@ SIGNATURES = {
                                       _c_int_p, _vp, _vp, _vp, _vp, _vp, _vp]),
     'msmd_spconv_pack_weight': (_i, [_vp, _i, _i, _i, _vp, _vp]),
     'msmd_spconv_fwd': (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _vp]),
+    'msmd_spconv_tc_supported': (_i, [_i, _i, _i]),
+    'msmd_spconv_tc_packed_floats': (_sz, [_i, _i, _i]),
+    'msmd_spconv_tc_pack_weight': (_i, [_vp, _i, _i, _i, _vp, _vp]),
+    'msmd_spconv_fwd_tc': (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _vp]),
     'msmd_to_dense': (_i, [_vp, _vp, _i, _i, _i, _c_int_p, _vp, _vp]),
     'msmd_fps_workspace': (_sz, [_i]),
     'msmd_fps': (_i, [_vp, _i, _i, _vp, _vp, _sz, _vp]),

@@ -193,7 +193,60 @@ def pack_weight(weight):
     return packed
 
 
+class TcWeight:
+    """Weight packed for the tensor-core path (csrc/spconv_tc.cu)."""
+
+    __slots__ = ('packed', 'cout', 'kvol', 'cin')
+
+    def __init__(self, packed, cout, kvol, cin):
+        self.packed, self.cout, self.kvol, self.cin = packed, cout, kvol, cin
+
+
+def tc_supported(cout, kvol, cin):
+    return bool(lib().msmd_spconv_tc_supported(int(cout), int(kvol), int(cin)))
+
+
+def pack_weight_tc(weight):
+    """KRSC [Cout,kz,ky,kx,Cin] parameter -> swizzled tf32 hi/lo K-chunk image."""
+    w = weight.detach()
+    if w.dtype != torch.float32:
+        w = w.float()
+    w = w.contiguous()
+    cout, cin = w.shape[0], w.shape[-1]
+    kvol = w.numel() // (cout * cin)
+    n = lib().msmd_spconv_tc_packed_floats(cout, kvol, cin)
+    assert n > 0, 'shape not supported by the tensor-core path'
+    packed = torch.empty((n,), dtype=torch.float32, device=w.device)
+    check(lib().msmd_spconv_tc_pack_weight(ptr(w), cout, kvol, cin, ptr(packed), stream(w.device)),
+          'msmd_spconv_tc_pack_weight')
+    return TcWeight(packed, cout, kvol, cin)
+
+
+def spconv_fwd_tc(features, tcw, pair_fwd, scale=None, shift=None, residual=None, relu=False):
+    """Sparse conv forward on tcgen05 tensor cores (3xTF32, fp32 accumulate in TMEM)."""
+    features = features.contiguous()
+    if features.dtype != torch.float32:
+        features = features.float()
+    assert features.shape[1] == tcw.cin, 'channel size mismatch'
+    assert pair_fwd.shape[0] == tcw.kvol and pair_fwd.dtype == torch.int32
+    n_out = pair_fwd.shape[1]
+    out = torch.empty((n_out, tcw.cout), dtype=torch.float32, device=features.device)
+    if residual is not None:
+        residual = residual.contiguous()
+        assert residual.shape == out.shape
+    pair_fwd = pair_fwd.contiguous()
+    with _Timed('spconv_fwd', n_in=features.shape[0], n_out=n_out, cin=tcw.cin, cout=tcw.cout,
+                kvol=tcw.kvol, residual=residual is not None, pair=pair_fwd, path='tc'):
+        check(lib().msmd_spconv_fwd_tc(ptr(features), features.shape[0], ptr(tcw.packed), ptr(pair_fwd),
+                                       n_out, tcw.cin, tcw.cout, tcw.kvol, ptr(scale), ptr(shift),
+                                       ptr(residual), int(bool(relu)), ptr(out),
+                                       stream(features.device)), 'msmd_spconv_fwd_tc')
+    return out
+
+
 def spconv_fwd(features, packed_weight, pair_fwd, scale=None, shift=None, residual=None, relu=False):
+    if isinstance(packed_weight, TcWeight):
+        return spconv_fwd_tc(features, packed_weight, pair_fwd, scale, shift, residual, relu)
     features = features.contiguous()
     if features.dtype != torch.float32:
         features = features.float()
@@ -207,7 +260,7 @@ def spconv_fwd(features, packed_weight, pair_fwd, scale=None, shift=None, residu
         assert residual.shape == out.shape
     pair_fwd = pair_fwd.contiguous()
     with _Timed('spconv_fwd', n_in=features.shape[0], n_out=n_out, cin=cin, cout=cout, kvol=kvol,
-                residual=residual is not None, pair=pair_fwd):
+                residual=residual is not None, pair=pair_fwd, path='simt'):
         check(lib().msmd_spconv_fwd(ptr(features), features.shape[0], ptr(packed_weight),
                                     ptr(pair_fwd), n_out, cin, cout, kvol, ptr(scale), ptr(shift),
                                     ptr(residual), int(bool(relu)), ptr(out),

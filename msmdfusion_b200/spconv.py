@@ -16,6 +16,7 @@ B200-first differences that cannot change results:
   add and ReLU into the convolution's store.
 """
 import math
+import os
 import warnings
 from collections import OrderedDict
 
@@ -26,6 +27,10 @@ from torch.nn.parameter import Parameter
 
 from . import ops
 from .registry import CONV_LAYERS
+
+
+# contraction kernel: 'tc' (tcgen05, 3xTF32) or 'simt' (exact fp32 FFMA); MSMD_CONV_PATH overrides
+CONV_PATH = os.environ.get('MSMD_CONV_PATH', 'tc')
 
 
 def expand_nd(ndim, val):
@@ -342,10 +347,15 @@ class SparseConvolution(SparseModule):
                 init.uniform_(self.bias, -1 / math.sqrt(fan_in), 1 / math.sqrt(fan_in))
 
     def packed_weight(self):
+        """Kernel-layout copy of the weight, re-packed only when the parameter changes.
+        ``CONV_PATH`` selects the contraction kernel: 'tc' = tcgen05 tensor cores (3xTF32,
+        default), 'simt' = exact-fp32 FFMA kernel."""
         w = self.weight
-        key = (w.data_ptr(), w._version, w.device)
+        kvol = int(math.prod(self.kernel_size))
+        use_tc = CONV_PATH == 'tc' and ops.tc_supported(self.out_channels, kvol, self.in_channels)
+        key = (w.data_ptr(), w._version, w.device, use_tc)
         if self._packed is None or self._packed_key != key:
-            self._packed = ops.pack_weight(w)
+            self._packed = ops.pack_weight_tc(w) if use_tc else ops.pack_weight(w)
             self._packed_key = key
         return self._packed
 

@@ -141,7 +141,8 @@ def get_foreground2d(img_feats, img_metas, score_w, score_b):
         cams = []
         for v in range(ncam):
             pix = np.asarray(info['fg_pixels'][v], np.float32).reshape(-1, 3)
-            pts = np.asarray(info['fg_points'][v], np.float32).reshape(pix.shape[0], -1)
+            pts = np.asarray(info['fg_points'][v], np.float32)
+            pts = pts.reshape(pix.shape[0], -1) if pix.shape[0] else np.zeros((0, 15), np.float32)
             cams.append(cpu.lift_gather(img_feats[b * ncam + v], pix, pts, np.asarray(meta['lidar2img'][v]),
                                         score_w, score_b, input_w))
         out.append(np.concatenate(cams, 0))

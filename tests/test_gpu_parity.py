@@ -493,7 +493,8 @@ def test_sparse_add_matches_oracle(shape, batch, na, nb, c):
     oi, of, grid = ops.sparse_add(cuda(ia), cuda(fa), cuda(ib), cuda(fb), shape, batch)
     ei, ef = cpu.sparse_add(ia, fa, ib, fb, shape)
     assert np.array_equal(oi.cpu().numpy(), ei)
-    assert np.array_equal(of.cpu().numpy(), ef)  # a + b of two fp32 values: exact in either order
+    # a set may hold a coordinate twice; three-term sums depend on the (atomic) order -> 1-ulp slack
+    assert np.abs(of.cpu().numpy() - ef).max() < 1e-5
     assert int(grid.num_active.item()) == ei.shape[0]
 
 
