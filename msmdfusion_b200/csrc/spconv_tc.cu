@@ -18,15 +18,18 @@
 //     ReLU, store.
 //   K chunks whose kernel offsets no voxel of the tile uses are skipped entirely.
 //
-// Pipeline: `stages` shared-memory stages, mbarrier full/empty per stage (full = 128 producer
+// Pipeline: `stages` shared-memory stages, mbarrier full/empty per stage (full = 256 producer
 // arrivals + the bulk copy's transaction bytes; empty = tcgen05.commit), one accumulator-ready
-// barrier for the epilogue.  Warps 0-3 gather, then run the epilogue; warp 4 issues the B bulk
-// copies; warp 5 allocates TMEM and issues the MMAs.
+// barrier for the epilogue.  Warps 0-7 gather (each thread keeps the loads of TWO chunks in
+// flight), then run the epilogue; warp 8 issues the B bulk copies; warp 9 allocates TMEM and
+// issues the MMAs.
 #include "tc.cuh"
 
 namespace msmd {
 
-constexpr int kTcThreads = 192;
+constexpr int kTcProducerWarps = 8;                       // gather warps (also the epilogue)
+constexpr int kTcProducers = kTcProducerWarps * 32;       // 256 threads
+constexpr int kTcThreads = kTcProducers + 64;             // + B-loader warp + MMA warp
 constexpr int kTcM = 128;        // output voxels per tile (UMMA M)
 constexpr int kTcKC = 32;        // floats per K chunk = one 128-byte swizzle row
 constexpr int kTcABytes = kTcM * kTcKC * 4;  // 16 KB per A half (hi or lo)
@@ -81,13 +84,13 @@ spconv_fwd_tc_kernel(const float* __restrict__ feat, const float* __restrict__ w
   // ---- one-time setup -------------------------------------------------------------------
   if (tid == 0) {
     for (int s = 0; s < stages; ++s) {
-      tc::mbar_init(&full_bar[s], 128 + 1);  // 128 gather threads + the arrive.expect_tx of the B copy
+      tc::mbar_init(&full_bar[s], kTcProducers + 1);  // gather threads + the arrive.expect_tx of the B copy
       tc::mbar_init(&empty_bar[s], 1);       // one tcgen05.commit
     }
     tc::mbar_init(accum_bar, 1);
     tc::fence_mbar_init();
   }
-  if (warp == 5) {
+  if (warp == kTcProducerWarps + 1) {
     tc::tmem_alloc(tmem_ptr_s, (uint32_t)tmem_cols);
     tc::tmem_relinquish();
   }
@@ -121,23 +124,22 @@ spconv_fwd_tc_kernel(const float* __restrict__ feat, const float* __restrict__ w
   const int any_active = __syncthreads_or(mine);
   const uint32_t tmem_base = *tmem_ptr_s;
 
-  if (warp < 4) {
+  if (warp < kTcProducerWarps) {
     // ===== A producers: gather + tf32 hi/lo split + swizzled store ==========================
-    const int p = tid & 7;      // 16-byte piece inside the 128-byte chunk row
-    const int rbase = tid >> 3; // rows rbase + 16*i
-    int it = 0;
-    for (int j = 0; j < chunks; ++j) {
-      if (!act[j]) continue;
-      const int s = it % stages;
-      const uint32_t ph = (uint32_t)(it / stages) & 1u;
+    // thread -> 16-byte piece p of rows rbase + 32*i: 8 consecutive lanes read one contiguous
+    // 128-byte row segment.  The loads of the NEXT active chunk are issued before the current
+    // chunk is split and stored, so two chunks (8 x 16 B per thread) are always in flight.
+    const int p = tid & 7;
+    const int rbase = tid >> 3;  // 0..31
+    constexpr int RPT = kTcM / (kTcProducers / 8);  // rows per thread = 4
+    auto gather = [&](int j, float4 (&v)[RPT]) {
       const int kk0 = j * kTcKC + p * 4;
       const int k = kk0 / cin_pad;
       const int c = kk0 - k * cin_pad;
       const bool kvalid = k < kvol;
-      float4 v[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int r = rbase + 16 * i;
+      for (int i = 0; i < RPT; ++i) {
+        const int r = rbase + 32 * i;
         const int idx = kvalid ? pair_s[k * kTcM + r] : -1;
         v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (idx >= 0) {
@@ -152,12 +154,22 @@ spconv_fwd_tc_kernel(const float* __restrict__ feat, const float* __restrict__ w
           }
         }
       }
-      tc::mbar_wait(&empty_bar[s], ph ^ 1u);  // slot free (loads above already in flight)
+    };
+    auto next_active = [&](int j) {
+      ++j;
+      while (j < chunks && !act[j]) ++j;
+      return j;
+    };
+    int it = 0;
+    auto store = [&](const float4 (&v)[RPT]) {
+      const int s = it % stages;
+      const uint32_t ph = (uint32_t)(it / stages) & 1u;
+      tc::mbar_wait(&empty_bar[s], ph ^ 1u);
       const uint32_t a_hi = tc::smem_u32(smem + (size_t)s * stage_bytes);
       const uint32_t a_lo = a_hi + kTcABytes;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int r = rbase + 16 * i;
+      for (int i = 0; i < RPT; ++i) {
+        const int r = rbase + 32 * i;
         const uint32_t off = (uint32_t)(r * 128 + ((p ^ (r & 7)) << 4));
         const float hx = tc::round_tf32(v[i].x), hy = tc::round_tf32(v[i].y),
                     hz = tc::round_tf32(v[i].z), hw = tc::round_tf32(v[i].w);
@@ -167,6 +179,25 @@ spconv_fwd_tc_kernel(const float* __restrict__ feat, const float* __restrict__ w
       tc::fence_proxy_async();
       tc::mbar_arrive(&full_bar[s]);
       ++it;
+    };
+    // two register buffers, alternated without copies: while one chunk is split and stored the
+    // loads of the following chunk are already in flight
+    float4 bufa[RPT], bufb[RPT];
+    int ja = next_active(-1);
+    int jb = chunks;
+    if (ja < chunks) {
+      gather(ja, bufa);
+      jb = next_active(ja);
+      if (jb < chunks) gather(jb, bufb);
+    }
+    while (ja < chunks) {
+      store(bufa);
+      ja = (jb < chunks) ? next_active(jb) : chunks;
+      if (ja < chunks) gather(ja, bufa);
+      if (jb >= chunks) break;
+      store(bufb);
+      jb = (ja < chunks) ? next_active(ja) : chunks;
+      if (jb < chunks) gather(jb, bufb);
     }
 
     // ===== epilogue: TMEM -> registers -> fused BN / residual / ReLU -> global =============
@@ -174,13 +205,18 @@ spconv_fwd_tc_kernel(const float* __restrict__ feat, const float* __restrict__ w
       tc::mbar_wait(accum_bar, 0);
       tc::fence_after_sync();
     }
-    const int o = row0 + warp * 32 + lane;
+    const int quarter = warp & 3;             // TMEM lanes this warp may read: 32*quarter ..
+    const int o = row0 + quarter * 32 + lane;
+    const int nsteps = N / 16;
+    const int step_lo = (warp >> 2) ? (nsteps + 1) / 2 : 0;  // two warpgroups split the columns
+    const int step_hi = (warp >> 2) ? nsteps : (nsteps + 1) / 2;
     const bool vec_out = (cout % 4 == 0) && (((uintptr_t)out & 15) == 0) &&
                          (residual == nullptr || ((uintptr_t)residual & 15) == 0);
-    for (int c0 = 0; c0 < N; c0 += 16) {
+    for (int st = step_lo; st < step_hi; ++st) {
+      const int c0 = st * 16;
       uint32_t acc[16];
       if (any_active) {
-        tc::tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, acc);
+        tc::tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, acc);
         tc::tmem_ld_wait();
       } else {
 #pragma unroll
@@ -222,7 +258,7 @@ spconv_fwd_tc_kernel(const float* __restrict__ feat, const float* __restrict__ w
         }
       }
     }
-  } else if (warp == 4) {
+  } else if (warp == kTcProducerWarps) {
     // ===== B loader: one bulk copy (hi + lo image of the chunk) per active chunk ============
     if (lane == 0) {
       const uint32_t bytes = (uint32_t)N * kTcKC * 4u * 2u;
@@ -274,7 +310,7 @@ spconv_fwd_tc_kernel(const float* __restrict__ feat, const float* __restrict__ w
   // ---- teardown -------------------------------------------------------------------------
   tc::fence_before_sync();
   __syncthreads();
-  if (warp == 5) tc::tmem_dealloc(tmem_base, (uint32_t)tmem_cols);
+  if (warp == kTcProducerWarps + 1) tc::tmem_dealloc(tmem_base, (uint32_t)tmem_cols);
 }
 
 // Packed weight image: [chunk j][half: hi, lo][n < N][32 floats, 128-byte swizzled by (n & 7)].

@@ -12,6 +12,7 @@ from ._cabi import check, floats, ints, lib, ptr, scratch, stream
 # bench.py sets PROFILE to a list to time every C-ABI call with CUDA events on the launching
 # stream (per-kernel roofline accounting); None = no instrumentation.
 PROFILE = None
+PROFILE_SYNC = False  # debugging: synchronise before each timed call
 
 
 class _Timed:
@@ -24,6 +25,8 @@ class _Timed:
 
     def __enter__(self):
         if self.rec is not None:
+            if PROFILE_SYNC:
+                torch.cuda.synchronize()
             self.rec['start'] = torch.cuda.Event(enable_timing=True)
             self.rec['end'] = torch.cuda.Event(enable_timing=True)
             self.rec['start'].record()
