@@ -138,6 +138,9 @@ MSMD_API int msmd_spconv_fwd(const float* features, int n_in, const float* packe
  *   (msmd_spconv_tc_packed_floats() floats, 16-byte aligned).  Supported: cout <= 256,
  *   kvol <= 32 (msmd_spconv_tc_supported); everything else uses msmd_spconv_fwd. */
 MSMD_API int msmd_spconv_tc_supported(int cout, int kvol, int cin);
+/* kernel variant: 0 (default) = chosen by Cout, 3 = A operand staged in tensor memory,
+ * 2 = A operand in shared memory */
+MSMD_API int msmd_spconv_tc_set_variant(int variant);
 MSMD_API size_t msmd_spconv_tc_packed_floats(int cout, int kvol, int cin);
 MSMD_API int msmd_spconv_tc_pack_weight(const float* weight_krsc, int cout, int kvol, int cin,
                                         float* packed_tc, msmd_stream_t stream);
@@ -196,6 +199,14 @@ MSMD_API int msmd_modality_split(const int* coord3, int n3, const int* coord2, i
                                  long long offset3, long long offset2, int* mix3, int* mix2,
                                  long long* syn3, long long* syn2, int* num_mix, void* workspace,
                                  size_t workspace_bytes, msmd_stream_t stream);
+
+/* Rows i (ascending) with flags[i] == 0 -> out_rows (capacity n, int64), *count (device).
+ * Replaces the boolean-mask indexing `indices[:, 1] == 0` of
+ * sparse_multimodal_encoder_painting.py:338-343 (only-3D / only-2D voxel selection) without
+ * the host synchronisation of torch.nonzero: the caller already knows the count
+ * (n - number of mixed pairs).  workspace: msmd_scan_workspace() bytes. */
+MSMD_API int msmd_compact_unflagged(const int* flags, int n, long long* out_rows, int* count,
+                                    void* workspace, size_t workspace_bytes, msmd_stream_t stream);
 
 /* ------------------------------------------------------------------------------------
  * Fsp.sparse_add(a, b) -- call site sparse_multimodal_encoder_painting.py:455.

@@ -38,6 +38,7 @@ SIGNATURES = {
     'msmd_spconv_pack_weight': (_i, [_vp, _i, _i, _i, _vp, _vp]),
     'msmd_spconv_fwd': (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _vp]),
     'msmd_spconv_tc_supported': (_i, [_i, _i, _i]),
+    'msmd_spconv_tc_set_variant': (_i, [_i]),
     'msmd_spconv_tc_packed_floats': (_sz, [_i, _i, _i]),
     'msmd_spconv_tc_pack_weight': (_i, [_vp, _i, _i, _i, _vp, _vp]),
     'msmd_spconv_fwd_tc': (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _vp]),
@@ -50,6 +51,7 @@ SIGNATURES = {
     'msmd_modality_split_workspace': (_sz, [_i, _i]),
     'msmd_modality_split': (_i, [_vp, _i, _vp, _i, ctypes.c_longlong, ctypes.c_longlong, _vp, _vp,
                                  _vp, _vp, _vp, _vp, _sz, _vp]),
+    'msmd_compact_unflagged': (_i, [_vp, _i, _vp, _vp, _vp, _sz, _vp]),
     'msmd_sparse_add_outputs': (_i, [_vp, _i, _vp, _i, _i, _c_int_p, _vp, _vp, _vp, _vp, _sz, _vp]),
     'msmd_sparse_add_finish': (_i, [_vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _c_int_p, _vp,
                                     _vp, _vp]),
@@ -76,6 +78,9 @@ def lib():
             fn.argtypes = args
         if L.msmd_abi_version() != 1:
             raise RuntimeError('libmsmd_b200.so ABI version mismatch')
+        if os.environ.get('MSMD_TC_VARIANT'):  # A/B switch of the tensor-core conv kernel (2 | 3)
+            if L.msmd_spconv_tc_set_variant(int(os.environ['MSMD_TC_VARIANT'])) != 0:
+                raise RuntimeError('bad MSMD_TC_VARIANT')
         _LIB = L
     return _LIB
 

@@ -72,6 +72,17 @@ struct SplitCompact {
   }
 };
 
+struct LoadUnflagged {
+  const int* f;
+  __device__ int operator()(int i) const { return f[i] == 0; }
+};
+struct StoreRow {
+  long long* out;
+  __device__ void operator()(int i, int ex, int v) const {
+    if (v) out[ex] = (long long)i;
+  }
+};
+
 struct SplitWs {
   uint32_t *k3, *k2;
   int *r3, *r2, *f3, *f2;
@@ -253,6 +264,24 @@ extern "C" MSMD_API int msmd_modality_split(const int* coord3, int n3, const int
   ScanTemp<int> t2{s.sort.block_sums, s.sort.counter, s.total2};
   MSMD_CUDA_OK((device_exclusive_scan<int>(LoadInt{s.f2}, SplitCompact{s.r2, offset2, syn2}, n2, t2,
                                            stream)));
+  return MSMD_OK;
+}
+
+extern "C" MSMD_API int msmd_compact_unflagged(const int* flags, int n, long long* out_rows, int* count,
+                                               void* workspace, size_t workspace_bytes,
+                                               msmd_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  MSMD_REQUIRE(n >= 0 && count, "compact_unflagged: bad arguments");
+  Workspace ws(workspace, workspace_bytes);
+  int* block_sums = ws.take<int>(kScanMaxBlocks);
+  unsigned* counter = ws.take<unsigned>(1);
+  if (!ws.ok()) {
+    set_error("compact_unflagged: workspace too small");
+    return MSMD_ERR_WORKSPACE;
+  }
+  MSMD_CUDA_OK(cudaMemsetAsync(counter, 0, sizeof(unsigned), stream));
+  ScanTemp<int> tmp{block_sums, counter, count};
+  MSMD_CUDA_OK((device_exclusive_scan<int>(LoadUnflagged{flags}, StoreRow{out_rows}, n, tmp, stream)));
   return MSMD_OK;
 }
 

@@ -41,17 +41,52 @@ __device__ __forceinline__ unsigned fps_priority(int k, int block, int log2block
   return (rev << 22) | q;  // q < 2^22 is checked on the host
 }
 
+// A candidate travels between the CTAs of the cluster as two 16-byte vector stores, each carrying
+// the round number as a tag: {key.lo, key.hi, x, tag} {y, z, tag, 0}.  A reader polls its LOCAL
+// shared memory until both tags equal the round -- no cluster barrier on the serial chain.
+struct __align__(32) FpsCand {
+  uint4 h0, h1;
+};
+
+__device__ __forceinline__ uint32_t fps_map_cluster(uint32_t smem_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void fps_st_cluster_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c,
+                                                  uint32_t d) {
+  asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d)
+               : "memory");
+}
+__device__ __forceinline__ uint4 fps_ld_volatile_v4(const void* p) {
+  uint4 v;
+  asm volatile("ld.volatile.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "r"((uint32_t)__cvta_generic_to_shared(p))
+               : "memory");
+  return v;
+}
+// warp-wide max of a 64-bit key with two 32-bit redux instructions (high word first)
+__device__ __forceinline__ unsigned long long fps_warp_max(unsigned long long key) {
+  const unsigned hi = (unsigned)(key >> 32), lo = (unsigned)key;
+  const unsigned mhi = __reduce_max_sync(0xffffffffu, hi);
+  const unsigned mlo = __reduce_max_sync(0xffffffffu, hi == mhi ? lo : 0u);
+  return ((unsigned long long)mhi << 32) | mlo;
+}
+
 template <int PPT>
 __global__ void __cluster_dims__(kFpsCluster, 1, 1) __launch_bounds__(kFpsThreads, 1)
 fps_cluster_kernel(const float* __restrict__ xyz, int n, int m, int block, int log2block,
                    int* __restrict__ idx) {
   cg::cluster_group cluster = cg::this_cluster();
   const unsigned rank = cluster.block_rank();
-  __shared__ unsigned long long warp_best[kFpsThreads / 32];
-  __shared__ unsigned long long cta_best[2][kFpsCluster];  // double-buffered across rounds
+  extern __shared__ float xyz_s[];  // this CTA's points: slot j*kFpsThreads + tid -> (x,y,z)
+  __shared__ unsigned long long warp_best[2][kFpsThreads / 32];  // double-buffered across rounds
+  __shared__ FpsCand cand[2][kFpsCluster];                        // slot c is written by CTA c
 
   const int gtid = rank * kFpsThreads + threadIdx.x;
   const int gthreads = kFpsCluster * kFpsThreads;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float px[PPT], py[PPT], pz[PPT], temp[PPT];
   unsigned prio[PPT];
 #pragma unroll
@@ -64,12 +99,23 @@ fps_cluster_kernel(const float* __restrict__ xyz, int n, int m, int block, int l
       px[j] = py[j] = pz[j] = 0.f;
       prio[j] = 0xffffffffu;
     }
+    float* dst = xyz_s + 3 * (j * kFpsThreads + threadIdx.x);
+    dst[0] = px[j]; dst[1] = py[j]; dst[2] = pz[j];
     temp[j] = 1e10f;  // furthest_point_sample.py:28
   }
-  int old = 0;
+  if (threadIdx.x < 2 * kFpsCluster) {
+    FpsCand z;
+    z.h0 = make_uint4(0, 0, 0, 0);
+    z.h1 = make_uint4(0, 0, 0, 0);
+    (&cand[0][0])[threadIdx.x] = z;  // tag 0 never matches a round number (rounds start at 1)
+  }
+  // round 0 picks point 0 (furthest_point_sample_cuda.cu:46-47)
+  float x1 = __ldg(xyz + 0), y1 = __ldg(xyz + 1), z1 = __ldg(xyz + 2);
   if (gtid == 0) idx[0] = 0;
+  cluster.sync();  // every CTA's slots are initialised before anyone publishes into them
+  const uint32_t cand_base = (uint32_t)__cvta_generic_to_shared(&cand[0][0]);
   for (int r = 1; r < m; ++r) {
-    const float x1 = __ldg(xyz + 3 * old), y1 = __ldg(xyz + 3 * old + 1), z1 = __ldg(xyz + 3 * old + 2);
+    const int par = r & 1;
     unsigned long long best = 0ull;
 #pragma unroll
     for (int j = 0; j < PPT; ++j) {
@@ -84,30 +130,55 @@ fps_cluster_kernel(const float* __restrict__ xyz, int n, int m, int block, int l
         best = u64max(best, key);  // "none" is 0; point 0 (priority 0) always has a key > 0
       }
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) best = u64max(best, __shfl_xor_sync(0xffffffffu, best, o));
-    if ((threadIdx.x & 31) == 0) warp_best[threadIdx.x >> 5] = best;
-    __syncthreads();
-    if (threadIdx.x < 32) {
-      unsigned long long b = threadIdx.x < kFpsThreads / 32 ? warp_best[threadIdx.x] : 0ull;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) b = u64max(b, __shfl_xor_sync(0xffffffffu, b, o));
-      if (threadIdx.x < kFpsCluster) {
-        // publish this CTA's best into slot [rank] of every CTA of the cluster (DSMEM)
-        unsigned long long* remote = cluster.map_shared_rank(&cta_best[r & 1][0], threadIdx.x);
-        remote[rank] = b;
+    best = fps_warp_max(best);
+    if (lane == 0) warp_best[par][warp] = best;
+    __syncthreads();  // the only CTA-wide barrier of the round
+    if (warp == 0) {
+      unsigned long long b = lane < kFpsThreads / 32 ? warp_best[par][lane] : 0ull;
+      b = fps_warp_max(b);
+      if (lane < kFpsCluster) {
+        // this CTA's best: coordinates from the local shared-memory copy; publish {key, xyz, tag}
+        // into slot [rank] of CTA `lane` (distributed shared memory)
+        float cx = 0.f, cy = 0.f, cz = 0.f;
+        if (b != 0ull) {
+          const unsigned pr = ~(unsigned)(b & 0xffffffffull);
+          const unsigned rev = pr >> 22, q = pr & ((1u << 22) - 1u);
+          const unsigned t = log2block ? (__brev(rev) >> (32 - log2block)) : 0u;
+          const int k = (int)((q << log2block) | t);
+          const int slot = (k / gthreads) * kFpsThreads + (k % gthreads) - (int)rank * kFpsThreads;
+          cx = xyz_s[3 * slot + 0]; cy = xyz_s[3 * slot + 1]; cz = xyz_s[3 * slot + 2];
+        }
+        const uint32_t local = cand_base + (uint32_t)((par * kFpsCluster + rank) * sizeof(FpsCand));
+        const uint32_t remote = fps_map_cluster(local, (uint32_t)lane);
+        fps_st_cluster_v4(remote, (unsigned)b, (unsigned)(b >> 32), __float_as_uint(cx), (unsigned)r);
+        fps_st_cluster_v4(remote + 16, __float_as_uint(cy), __float_as_uint(cz), (unsigned)r, 0u);
       }
     }
-    cluster.sync();
-    unsigned long long g = cta_best[r & 1][0];
+    // every thread: wait for the 8 candidates of this round in LOCAL shared memory, take the max
+    unsigned long long g = 0ull;
+    long long t0 = 0;
 #pragma unroll
-    for (int c = 1; c < kFpsCluster; ++c) g = u64max(g, cta_best[r & 1][c]);
-    // decode the winner: low 32 bits = ~priority
-    const unsigned p = ~(unsigned)(g & 0xffffffffull);
-    const unsigned rev = p >> 22, q = p & ((1u << 22) - 1u);
-    const unsigned tid = log2block ? (__brev(rev) >> (32 - log2block)) : 0u;
-    old = (int)((q << log2block) | tid);
-    if (gtid == 0) idx[r] = old;
+    for (int c = 0; c < kFpsCluster; ++c) {
+      uint4 h0, h1;
+      for (;;) {
+        h0 = fps_ld_volatile_v4(&cand[par][c].h0);
+        h1 = fps_ld_volatile_v4(&cand[par][c].h1);
+        if (h0.w == (unsigned)r && h1.z == (unsigned)r) break;
+        if (t0 == 0) t0 = clock64();
+        else if (clock64() - t0 > 4000000000LL) __trap();  // protocol bug: fail, never hang
+      }
+      const unsigned long long kc = ((unsigned long long)h0.y << 32) | h0.x;
+      if (c == 0 || kc > g) {
+        g = kc;
+        x1 = __uint_as_float(h0.z); y1 = __uint_as_float(h1.x); z1 = __uint_as_float(h1.y);
+      }
+    }
+    if (gtid == 0) {
+      const unsigned p = ~(unsigned)(g & 0xffffffffull);
+      const unsigned rev = p >> 22, q = p & ((1u << 22) - 1u);
+      const unsigned t = log2block ? (__brev(rev) >> (32 - log2block)) : 0u;
+      idx[r] = (int)((q << log2block) | t);
+    }
   }
   cluster.sync();  // no CTA may exit while peers can still write into its shared memory
 }
@@ -296,7 +367,16 @@ extern "C" MSMD_API int msmd_fps(const float* xyz, int n, int m, int* idx, void*
   if (n <= cap * kFpsMaxPerThread) {
     const int ppt = ceil_div(n, cap);
 #define MSMD_FPS(P)                                                                             \
-  fps_cluster_kernel<P><<<kFpsCluster, kFpsThreads, 0, stream>>>(xyz, n, m, block, log2block, idx)
+  do {                                                                                          \
+    const size_t smem = (size_t)(P) * kFpsThreads * 3 * sizeof(float);                          \
+    static bool attr_done = false; /* dynamic + 640 B static must fit: raise the limit once */  \
+    if (!attr_done) {                                                                           \
+      MSMD_CUDA_OK(cudaFuncSetAttribute(fps_cluster_kernel<P>,                                  \
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      attr_done = true;                                                                         \
+    }                                                                                           \
+    fps_cluster_kernel<P><<<kFpsCluster, kFpsThreads, smem, stream>>>(xyz, n, m, block, log2block, idx); \
+  } while (0)
     if (ppt <= 1) MSMD_FPS(1);
     else if (ppt <= 2) MSMD_FPS(2);
     else if (ppt <= 4) MSMD_FPS(4);

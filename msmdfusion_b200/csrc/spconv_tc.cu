@@ -43,7 +43,7 @@ static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 static TcSmemLayout tc_layout(int N, int kvol, int chunks) {
   TcSmemLayout L;
   L.stage_bytes = 2 * kTcABytes + N * kTcKC * 4 * 2;
-  const int misc = round_up(kvol * kTcM * 4, 16) + round_up(chunks, 16) + 256;
+  const int misc = round_up(kvol * kTcM * 4, 16) + round_up(2 * chunks, 16) + 256 + 8 * N;
   // two CTAs per SM when two stages fit in half of the SM's shared memory, else one CTA
   // with as many stages as fit (max 4)
   const int half = 112 * 1024, full = 224 * 1024;
@@ -55,9 +55,104 @@ static TcSmemLayout tc_layout(int N, int kvol, int chunks) {
   if (L.stages > 4) L.stages = 4;
   L.pair_off = L.stages * L.stage_bytes;
   L.act_off = L.pair_off + round_up(kvol * kTcM * 4, 16);
-  L.bar_off = L.act_off + round_up(chunks, 16);
-  L.total = L.bar_off + 256 + 1024;  // + slack for the 1024-byte alignment of the base
+  L.bar_off = L.act_off + round_up(2 * chunks, 16);
+  L.total = L.bar_off + 256 + 8 * N + 1024;  // barriers | scale/shift | slack for the 1024-byte alignment
   return L;
+}
+
+// One lane polls the mbarrier, the warp follows through __syncwarp (31 fewer spinning lanes per
+// warp: the producers are instruction-issue bound, ncu profiles/r01d).
+__device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity, int lane) {
+  if (lane == 0) tc::mbar_wait(bar, parity);
+  __syncwarp();
+}
+
+// Compact list of the K chunks this tile uses (a chunk is skipped when none of its kernel
+// offsets has a pair in the tile).  Executed by warp 0; returns the count in *n_act_s.
+__device__ __forceinline__ void tc_build_active_list(const int* used_s, int chunks, int cin_pad, int kvol,
+                                                     int lane, unsigned short* alist, int* n_act_s) {
+  int cnt = 0;
+  for (int base = 0; base < chunks; base += 32) {
+    const int j = base + lane;
+    int a = 0;
+    if (j < chunks) {
+      const int k_lo = (j * kTcKC) / cin_pad;
+      int k_hi = (j * kTcKC + kTcKC - 1) / cin_pad;
+      if (k_hi > kvol - 1) k_hi = kvol - 1;
+      for (int k = k_lo; k <= k_hi; ++k) a |= used_s[k];
+    }
+    const unsigned b = __ballot_sync(0xffffffffu, a != 0);
+    if (a) alist[cnt + __popc(b & ((1u << lane) - 1u))] = (unsigned short)j;
+    cnt += __popc(b);
+  }
+  if (lane == 0) *n_act_s = cnt;
+}
+
+// Epilogue shared by the kernel variants: executed by the 8 producer warps once the accumulator
+// barrier fires.  Warp w may read TMEM lanes 32*(w&3)..+31 (= accumulator rows); the two
+// warpgroups split the N columns.  y = relu(acc*scale + shift + residual), 16-byte stores.
+__device__ __forceinline__ void tc_epilogue(int any_active, uint64_t* accum_bar, uint32_t tmem_base,
+                                            int warp, int lane, int row0, int n_out, int cout, int N,
+                                            const float* ss /* smem: scale[N] | shift[N] */,
+                                            const float* __restrict__ residual, int relu,
+                                            float* __restrict__ out) {
+    if (any_active) {
+      tc::mbar_wait(accum_bar, 0);
+      tc::fence_after_sync();
+    }
+    const int quarter = warp & 3;             // TMEM lanes this warp may read: 32*quarter ..
+    const int o = row0 + quarter * 32 + lane;
+    const int nsteps = N / 16;
+    const int step_lo = (warp >> 2) ? (nsteps + 1) / 2 : 0;  // two warpgroups split the columns
+    const int step_hi = (warp >> 2) ? nsteps : (nsteps + 1) / 2;
+    const bool vec_out = (cout % 4 == 0) && (((uintptr_t)out & 15) == 0) &&
+                         (residual == nullptr || ((uintptr_t)residual & 15) == 0);
+    for (int st = step_lo; st < step_hi; ++st) {
+      const int c0 = st * 16;
+      uint32_t acc[16];
+      if (any_active) {
+        tc::tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, acc);
+        tc::tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int e = 0; e < 16; ++e) acc[e] = 0u;
+      }
+      if (o < n_out) {
+        float* orow = out + (size_t)o * cout;
+        const float* rrow = residual ? residual + (size_t)o * cout : nullptr;
+#pragma unroll
+        for (int e = 0; e < 16; e += 4) {
+          const int co = c0 + e;
+          if (co >= cout) break;
+          float y[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            y[q] = __uint_as_float(acc[e + q]);
+            y[q] = fmaf(y[q], ss[co + q], ss[N + co + q]);  // (1, 0) when no BatchNorm is folded in
+          }
+          if (vec_out) {
+            if (rrow) {
+              const float4 rv = __ldg((const float4*)(rrow + co));
+              y[0] += rv.x; y[1] += rv.y; y[2] += rv.z; y[3] += rv.w;
+            }
+            if (relu) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) y[q] = fmaxf(y[q], 0.f);
+            }
+            *(float4*)(orow + co) = make_float4(y[0], y[1], y[2], y[3]);
+          } else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              if (co + q >= cout) break;
+              float t = y[q];
+              if (rrow) t += __ldg(rrow + co + q);
+              if (relu) t = fmaxf(t, 0.f);
+              orow[co + q] = t;
+            }
+          }
+        }
+      }
+    }
 }
 
 template <bool VEC>
@@ -71,12 +166,18 @@ spconv_fwd_tc_kernel(const float* __restrict__ feat, const float* __restrict__ w
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   int* pair_s = (int*)(smem + pair_off);
-  uint8_t* act = smem + act_off;
+  unsigned short* alist = (unsigned short*)(smem + act_off);
   uint64_t* full_bar = (uint64_t*)(smem + bar_off);
   uint64_t* empty_bar = full_bar + 4;
   uint64_t* accum_bar = full_bar + 8;
   uint32_t* tmem_ptr_s = (uint32_t*)(full_bar + 9);
+  int* n_act_s = (int*)(full_bar + 9) + 1;
   int* used_s = (int*)(full_bar + 10);  // [kvol <= 32]
+  float* ss = (float*)(smem + bar_off + 256);  // folded BatchNorm scale[N] | shift[N]
+  for (int c = threadIdx.x; c < N; c += kTcThreads) {
+    ss[c] = (scale && c < cout) ? __ldg(scale + c) : 1.f;
+    ss[N + c] = (shift && c < cout) ? __ldg(shift + c) : 0.f;
+  }
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int row0 = blockIdx.x * kTcM;
@@ -84,7 +185,7 @@ spconv_fwd_tc_kernel(const float* __restrict__ feat, const float* __restrict__ w
   // ---- one-time setup -------------------------------------------------------------------
   if (tid == 0) {
     for (int s = 0; s < stages; ++s) {
-      tc::mbar_init(&full_bar[s], kTcProducers + 1);  // gather threads + the arrive.expect_tx of the B copy
+      tc::mbar_init(&full_bar[s], kTcProducerWarps + 1);  // one arrive per gather warp + the B copy's expect_tx
       tc::mbar_init(&empty_bar[s], 1);       // one tcgen05.commit
     }
     tc::mbar_init(accum_bar, 1);
@@ -111,17 +212,10 @@ spconv_fwd_tc_kernel(const float* __restrict__ feat, const float* __restrict__ w
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
-  int mine = 0;
-  for (int j = tid; j < chunks; j += kTcThreads) {
-    const int k_lo = (j * kTcKC) / cin_pad;
-    int k_hi = (j * kTcKC + kTcKC - 1) / cin_pad;
-    if (k_hi > kvol - 1) k_hi = kvol - 1;
-    int a = 0;
-    for (int k = k_lo; k <= k_hi; ++k) a |= used_s[k];
-    act[j] = (uint8_t)a;
-    mine |= a;
-  }
-  const int any_active = __syncthreads_or(mine);
+  if (warp == 0) tc_build_active_list(used_s, chunks, cin_pad, kvol, lane, alist, n_act_s);
+  __syncthreads();
+  const int n_act = *n_act_s;
+  const int any_active = n_act > 0;
   const uint32_t tmem_base = *tmem_ptr_s;
 
   if (warp < kTcProducerWarps) {
@@ -155,16 +249,11 @@ spconv_fwd_tc_kernel(const float* __restrict__ feat, const float* __restrict__ w
         }
       }
     };
-    auto next_active = [&](int j) {
-      ++j;
-      while (j < chunks && !act[j]) ++j;
-      return j;
-    };
     int it = 0;
     auto store = [&](const float4 (&v)[RPT]) {
       const int s = it % stages;
       const uint32_t ph = (uint32_t)(it / stages) & 1u;
-      tc::mbar_wait(&empty_bar[s], ph ^ 1u);
+      mbar_wait_warp(&empty_bar[s], ph ^ 1u, lane);
       const uint32_t a_hi = tc::smem_u32(smem + (size_t)s * stage_bytes);
       const uint32_t a_lo = a_hi + kTcABytes;
 #pragma unroll
@@ -176,102 +265,38 @@ spconv_fwd_tc_kernel(const float* __restrict__ feat, const float* __restrict__ w
         tc::st_shared_v4(a_hi + off, hx, hy, hz, hw);
         tc::st_shared_v4(a_lo + off, v[i].x - hx, v[i].y - hy, v[i].z - hz, v[i].w - hw);
       }
-      tc::fence_proxy_async();
-      tc::mbar_arrive(&full_bar[s]);
+      tc::fence_proxy_async();  // every lane: its generic-proxy stores -> async proxy
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&full_bar[s]);  // one arrival per warp (256 -> 8 smem atomics)
       ++it;
     };
     // two register buffers, alternated without copies: while one chunk is split and stored the
     // loads of the following chunk are already in flight
     float4 bufa[RPT], bufb[RPT];
-    int ja = next_active(-1);
-    int jb = chunks;
-    if (ja < chunks) {
-      gather(ja, bufa);
-      jb = next_active(ja);
-      if (jb < chunks) gather(jb, bufb);
-    }
-    while (ja < chunks) {
+    if (n_act > 0) gather(alist[0], bufa);
+    if (n_act > 1) gather(alist[1], bufb);
+    for (int i = 0; i < n_act; i += 2) {
       store(bufa);
-      ja = (jb < chunks) ? next_active(jb) : chunks;
-      if (ja < chunks) gather(ja, bufa);
-      if (jb >= chunks) break;
+      if (i + 2 < n_act) gather(alist[i + 2], bufa);
+      if (i + 1 >= n_act) break;
       store(bufb);
-      jb = (ja < chunks) ? next_active(ja) : chunks;
-      if (jb < chunks) gather(jb, bufb);
+      if (i + 3 < n_act) gather(alist[i + 3], bufb);
     }
 
     // ===== epilogue: TMEM -> registers -> fused BN / residual / ReLU -> global =============
-    if (any_active) {
-      tc::mbar_wait(accum_bar, 0);
-      tc::fence_after_sync();
-    }
-    const int quarter = warp & 3;             // TMEM lanes this warp may read: 32*quarter ..
-    const int o = row0 + quarter * 32 + lane;
-    const int nsteps = N / 16;
-    const int step_lo = (warp >> 2) ? (nsteps + 1) / 2 : 0;  // two warpgroups split the columns
-    const int step_hi = (warp >> 2) ? nsteps : (nsteps + 1) / 2;
-    const bool vec_out = (cout % 4 == 0) && (((uintptr_t)out & 15) == 0) &&
-                         (residual == nullptr || ((uintptr_t)residual & 15) == 0);
-    for (int st = step_lo; st < step_hi; ++st) {
-      const int c0 = st * 16;
-      uint32_t acc[16];
-      if (any_active) {
-        tc::tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, acc);
-        tc::tmem_ld_wait();
-      } else {
-#pragma unroll
-        for (int e = 0; e < 16; ++e) acc[e] = 0u;
-      }
-      if (o < n_out) {
-        float* orow = out + (size_t)o * cout;
-        const float* rrow = residual ? residual + (size_t)o * cout : nullptr;
-#pragma unroll
-        for (int e = 0; e < 16; e += 4) {
-          const int co = c0 + e;
-          if (co >= cout) break;
-          float y[4];
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            y[q] = __uint_as_float(acc[e + q]);
-            if (scale && co + q < cout) y[q] = fmaf(y[q], __ldg(scale + co + q), __ldg(shift + co + q));
-          }
-          if (vec_out) {
-            if (rrow) {
-              const float4 rv = __ldg((const float4*)(rrow + co));
-              y[0] += rv.x; y[1] += rv.y; y[2] += rv.z; y[3] += rv.w;
-            }
-            if (relu) {
-#pragma unroll
-              for (int q = 0; q < 4; ++q) y[q] = fmaxf(y[q], 0.f);
-            }
-            *(float4*)(orow + co) = make_float4(y[0], y[1], y[2], y[3]);
-          } else {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              if (co + q >= cout) break;
-              float t = y[q];
-              if (rrow) t += __ldg(rrow + co + q);
-              if (relu) t = fmaxf(t, 0.f);
-              orow[co + q] = t;
-            }
-          }
-        }
-      }
-    }
+    tc_epilogue(any_active, accum_bar, tmem_base, warp, lane, row0, n_out, cout, N, ss, residual, relu, out);
   } else if (warp == kTcProducerWarps) {
     // ===== B loader: one bulk copy (hi + lo image of the chunk) per active chunk ============
     if (lane == 0) {
       const uint32_t bytes = (uint32_t)N * kTcKC * 4u * 2u;
-      int it = 0;
-      for (int j = 0; j < chunks; ++j) {
-        if (!act[j]) continue;
+      for (int it = 0; it < n_act; ++it) {
+        const int j = alist[it];
         const int s = it % stages;
         const uint32_t ph = (uint32_t)(it / stages) & 1u;
         tc::mbar_wait(&empty_bar[s], ph ^ 1u);
         tc::mbar_arrive_expect_tx(&full_bar[s], bytes);
         tc::bulk_g2s(smem + (size_t)s * stage_bytes + 2 * kTcABytes,
                      wpk + (size_t)j * N * kTcKC * 2, bytes, &full_bar[s]);
-        ++it;
       }
     }
   } else {
@@ -279,9 +304,7 @@ spconv_fwd_tc_kernel(const float* __restrict__ feat, const float* __restrict__ w
     if (lane == 0) {
       const uint32_t idesc = tc::idesc_f32acc(tc::kFmtTF32, kTcM, N);
       uint32_t accumulate = 0;
-      int it = 0;
-      for (int j = 0; j < chunks; ++j) {
-        if (!act[j]) continue;
+      for (int it = 0; it < n_act; ++it) {
         const int s = it % stages;
         const uint32_t ph = (uint32_t)(it / stages) & 1u;
         tc::mbar_wait(&full_bar[s], ph);
@@ -301,13 +324,247 @@ spconv_fwd_tc_kernel(const float* __restrict__ feat, const float* __restrict__ w
           accumulate = 1u;
         }
         tc::mma_commit(&empty_bar[s]);  // frees the stage once these MMAs have read it
-        ++it;
       }
-      if (it > 0) tc::mma_commit(accum_bar);  // accumulator complete -> epilogue
+      if (n_act > 0) tc::mma_commit(accum_bar);  // accumulator complete -> epilogue
     }
   }
 
   // ---- teardown -------------------------------------------------------------------------
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == kTcProducerWarps + 1) tc::tmem_dealloc(tmem_base, (uint32_t)tmem_cols);
+}
+
+// ------------------------------------------------------------------------------------------
+// Variant 3: the A operand lives in TENSOR MEMORY.
+//
+// Variant 2 above is shared-memory-bandwidth bound: per 32-float K chunk it writes A hi+lo
+// (32 KB) and the three MMAs of each k-step re-read A from shared memory (48 KB per chunk) on
+// top of B (32 KB written, 48 KB read) -- 160 KB per chunk vs 96 KB the SM can move in the 768
+// tensor cycles of the chunk (ncu: profiles/r01b_ncu_full_*).  Here the gathered fp32 tile makes ONE
+// pass through shared memory (16 KB written coalesced, 16 KB read row-per-thread), is split into
+// tf32 hi/lo in registers and stored with tcgen05.st into TMEM (row = lane, K along columns);
+// tcgen05.mma reads A from TMEM, so shared memory carries B only.  Shared memory per CTA drops to
+// ~110 KB for N = 128, i.e. two CTAs per SM (one CTA's epilogue overlaps the other's main loop).
+//
+//   smem : B ring (b_stages x N*256 B) | raw A (2 x 16 KB, 128-B swizzled) | pair table | flags | barriers
+//   TMEM : D [0, N) | A ring: a_stages x {hi 32 cols | lo 32 cols}
+//   barriers: b_full/b_empty (bulk copy <-> MMA), a_full/a_empty (tcgen05.st <-> MMA), accum
+// ------------------------------------------------------------------------------------------
+struct Tc3Layout {
+  int b_stage_bytes, b_stages, a_stages, raw_off, pair_off, act_off, bar_off, total, tmem_cols;
+};
+
+static Tc3Layout tc3_layout(int N, int kvol, int chunks) {
+  Tc3Layout L;
+  L.b_stage_bytes = N * kTcKC * 4 * 2;
+  const int misc = 2 * kTcABytes + round_up(kvol * kTcM * 4, 16) + round_up(2 * chunks, 16) + 512 + 8 * N;
+  const int half = 113 * 1024, full = 224 * 1024;
+  int budget = (2 * L.b_stage_bytes + misc + 1024 <= half) ? half : full;
+  L.b_stages = (budget - misc - 1024) / L.b_stage_bytes;
+  if (L.b_stages > 4) L.b_stages = 4;
+  L.a_stages = (N <= 64) ? 3 : 2;
+  L.tmem_cols = 32;
+  while (L.tmem_cols < N + 64 * L.a_stages) L.tmem_cols <<= 1;
+  L.raw_off = L.b_stages * L.b_stage_bytes;
+  L.pair_off = L.raw_off + 2 * kTcABytes;
+  L.act_off = L.pair_off + round_up(kvol * kTcM * 4, 16);
+  L.bar_off = L.act_off + round_up(2 * chunks, 16);
+  L.total = L.bar_off + 512 + 8 * N + 1024;
+  return L;
+}
+
+template <bool VEC>
+__global__ void __launch_bounds__(kTcThreads)
+spconv_fwd_tc3_kernel(const float* __restrict__ feat, const float* __restrict__ wpk,
+                      const int* __restrict__ pair, int n_out, int cin, int cin_pad, int cout, int N,
+                      int kvol, int chunks, int b_stages, int b_stage_bytes, int a_stages, int raw_off,
+                      int pair_off, int act_off, int bar_off, int tmem_cols,
+                      const float* __restrict__ scale, const float* __restrict__ shift,
+                      const float* __restrict__ residual, int relu, float* __restrict__ out) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  int* pair_s = (int*)(smem + pair_off);
+  unsigned short* alist = (unsigned short*)(smem + act_off);
+  uint64_t* b_full = (uint64_t*)(smem + bar_off);
+  uint64_t* b_empty = b_full + 4;
+  uint64_t* a_full = b_full + 8;
+  uint64_t* a_empty = b_full + 12;
+  uint64_t* accum_bar = b_full + 16;
+  uint32_t* tmem_ptr_s = (uint32_t*)(b_full + 17);
+  int* n_act_s = (int*)(b_full + 17) + 1;
+  int* used_s = (int*)(b_full + 18);  // [kvol <= 32]
+  float* ss = (float*)(smem + bar_off + 512);  // folded BatchNorm scale[N] | shift[N]
+  for (int c = threadIdx.x; c < N; c += kTcThreads) {
+    ss[c] = (scale && c < cout) ? __ldg(scale + c) : 1.f;
+    ss[N + c] = (shift && c < cout) ? __ldg(shift + c) : 0.f;
+  }
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int row0 = blockIdx.x * kTcM;
+
+  if (tid == 0) {
+    for (int s = 0; s < 4; ++s) {
+      tc::mbar_init(&b_full[s], 1);              // the arrive.expect_tx of the bulk copy
+      tc::mbar_init(&b_empty[s], 1);             // tcgen05.commit
+      tc::mbar_init(&a_full[s], kTcProducerWarps);  // one arrive per converter warp after its tcgen05.st
+      tc::mbar_init(&a_empty[s], 1);             // tcgen05.commit
+    }
+    tc::mbar_init(accum_bar, 1);
+    tc::fence_mbar_init();
+  }
+  if (warp == kTcProducerWarps + 1) {
+    tc::tmem_alloc(tmem_ptr_s, (uint32_t)tmem_cols);
+    tc::tmem_relinquish();
+  }
+  for (int k = warp; k < kvol; k += kTcThreads / 32) {
+    bool any = false;
+#pragma unroll
+    for (int q = 0; q < kTcM / 32; ++q) {
+      const int r = lane + 32 * q;
+      const int o = row0 + r;
+      const int p = (o < n_out) ? __ldg(pair + (size_t)k * n_out + o) : -1;
+      pair_s[k * kTcM + r] = p;
+      any |= p >= 0;
+    }
+    const unsigned b = __ballot_sync(0xffffffffu, any);
+    if (lane == 0) used_s[k] = b != 0;
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  if (warp == 0) tc_build_active_list(used_s, chunks, cin_pad, kvol, lane, alist, n_act_s);
+  __syncthreads();
+  const int n_act = *n_act_s;
+  const int any_active = n_act > 0;
+  const uint32_t tmem_base = *tmem_ptr_s;
+  const uint32_t tmem_a0 = tmem_base + (uint32_t)N;  // A ring starts right after the accumulator
+
+  if (warp < kTcProducerWarps) {
+    // ===== gather (coalesced) -> raw smem -> row-per-thread read -> split -> tcgen05.st =====
+    const int p = tid & 7;
+    const int rbase = tid >> 3;  // 0..31
+    constexpr int RPT = kTcM / (kTcProducers / 8);  // 4 rows per thread in the gather mapping
+    auto gather = [&](int j, float4 (&v)[RPT]) {
+      const int kk0 = j * kTcKC + p * 4;
+      const int k = kk0 / cin_pad;
+      const int c = kk0 - k * cin_pad;
+      const bool kvalid = k < kvol;
+#pragma unroll
+      for (int i = 0; i < RPT; ++i) {
+        const int r = rbase + 32 * i;
+        const int idx = kvalid ? pair_s[k * kTcM + r] : -1;
+        v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (idx >= 0) {
+          const float* src = feat + (size_t)idx * cin + c;
+          if (VEC) {
+            v[i] = __ldg((const float4*)src);
+          } else {
+            if (c + 0 < cin) v[i].x = __ldg(src + 0);
+            if (c + 1 < cin) v[i].y = __ldg(src + 1);
+            if (c + 2 < cin) v[i].z = __ldg(src + 2);
+            if (c + 3 < cin) v[i].w = __ldg(src + 3);
+          }
+        }
+      }
+    };
+    // converter mapping: this thread owns accumulator row `crow` (the TMEM lane it may write)
+    // and 16 of the chunk's 32 K columns
+    const int crow = (warp & 3) * 32 + lane;
+    const int chalf = warp >> 2;  // K columns [16*chalf, +16)
+    const uint32_t raw0 = tc::smem_u32(smem + raw_off);
+    int it = 0;
+    auto convert = [&](const float4 (&v)[RPT]) {
+      const uint32_t raw = raw0 + (uint32_t)(it & 1) * kTcABytes;
+      // 1. coalesced-layout registers -> swizzled raw tile (one pass, conflict-free)
+#pragma unroll
+      for (int i = 0; i < RPT; ++i) {
+        const int r = rbase + 32 * i;
+        tc::st_shared_v4(raw + (uint32_t)(r * 128 + ((p ^ (r & 7)) << 4)), v[i].x, v[i].y, v[i].z, v[i].w);
+      }
+      tc::named_bar_sync(1, kTcProducers);
+      // 2. my row, my 16 K columns (4 pieces), back out of the raw tile
+      uint32_t hi[16], lo[16];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int piece = chalf * 4 + q;
+        const float4 x = tc::ld_shared_v4(raw + (uint32_t)(crow * 128 + ((piece ^ (crow & 7)) << 4)));
+        const float hx = tc::round_tf32(x.x), hy = tc::round_tf32(x.y), hz = tc::round_tf32(x.z),
+                    hw = tc::round_tf32(x.w);
+        hi[4 * q + 0] = __float_as_uint(hx); hi[4 * q + 1] = __float_as_uint(hy);
+        hi[4 * q + 2] = __float_as_uint(hz); hi[4 * q + 3] = __float_as_uint(hw);
+        lo[4 * q + 0] = __float_as_uint(x.x - hx); lo[4 * q + 1] = __float_as_uint(x.y - hy);
+        lo[4 * q + 2] = __float_as_uint(x.z - hz); lo[4 * q + 3] = __float_as_uint(x.w - hw);
+      }
+      // 3. TMEM A stage free?  store hi | lo, make it visible to the MMA issuer
+      const int sa = it % a_stages;
+      const uint32_t ph = (uint32_t)(it / a_stages) & 1u;
+      mbar_wait_warp(&a_empty[sa], ph ^ 1u, lane);
+      tc::fence_after_sync();
+      const uint32_t ta = tmem_a0 + (uint32_t)(sa * 64) + ((uint32_t)((warp & 3) * 32) << 16);
+      tc::tmem_st16(ta + (uint32_t)(16 * chalf), hi);
+      tc::tmem_st16(ta + 32u + (uint32_t)(16 * chalf), lo);
+      tc::tmem_st_wait();  // warp-wide: all 32 lanes' stores have landed
+      tc::fence_before_sync();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&a_full[sa]);
+      ++it;
+    };
+    float4 bufa[RPT], bufb[RPT];
+    if (n_act > 0) gather(alist[0], bufa);
+    if (n_act > 1) gather(alist[1], bufb);
+    for (int i = 0; i < n_act; i += 2) {
+      convert(bufa);
+      if (i + 2 < n_act) gather(alist[i + 2], bufa);
+      if (i + 1 >= n_act) break;
+      convert(bufb);
+      if (i + 3 < n_act) gather(alist[i + 3], bufb);
+    }
+
+    tc_epilogue(any_active, accum_bar, tmem_base, warp, lane, row0, n_out, cout, N, ss, residual, relu, out);
+  } else if (warp == kTcProducerWarps) {
+    // ===== B loader ============================================================================
+    if (lane == 0) {
+      const uint32_t bytes = (uint32_t)b_stage_bytes;
+      for (int it = 0; it < n_act; ++it) {
+        const int j = alist[it];
+        const int s = it % b_stages;
+        const uint32_t ph = (uint32_t)(it / b_stages) & 1u;
+        tc::mbar_wait(&b_empty[s], ph ^ 1u);
+        tc::mbar_arrive_expect_tx(&b_full[s], bytes);
+        tc::bulk_g2s(smem + (size_t)s * b_stage_bytes, wpk + (size_t)j * N * kTcKC * 2, bytes, &b_full[s]);
+      }
+    }
+  } else {
+    // ===== MMA issuer: A from TMEM, B from shared memory =======================================
+    if (lane == 0) {
+      const uint32_t idesc = tc::idesc_f32acc(tc::kFmtTF32, kTcM, N);
+      uint32_t accumulate = 0;
+      for (int it = 0; it < n_act; ++it) {
+        const int sb = it % b_stages, sa = it % a_stages;
+        tc::mbar_wait(&b_full[sb], (uint32_t)(it / b_stages) & 1u);
+        tc::mbar_wait(&a_full[sa], (uint32_t)(it / a_stages) & 1u);
+        tc::fence_after_sync();
+        const uint32_t b_hi = tc::smem_u32(smem + (size_t)sb * b_stage_bytes);
+        const uint32_t b_lo = b_hi + (uint32_t)N * kTcKC * 4u;
+        const uint32_t a_hi = tmem_a0 + (uint32_t)(sa * 64);
+        const uint32_t a_lo = a_hi + 32u;
+#pragma unroll
+        for (int ks = 0; ks < kTcKC / 8; ++ks) {
+          const uint64_t dbh = tc::desc_k_sw128(b_hi + (uint32_t)ks * 32u);
+          const uint64_t dbl = tc::desc_k_sw128(b_lo + (uint32_t)ks * 32u);
+          tc::mma_tf32_ts(tmem_base, a_lo + (uint32_t)ks * 8u, dbh, idesc, accumulate);
+          tc::mma_tf32_ts(tmem_base, a_hi + (uint32_t)ks * 8u, dbl, idesc, 1u);
+          tc::mma_tf32_ts(tmem_base, a_hi + (uint32_t)ks * 8u, dbh, idesc, 1u);
+          accumulate = 1u;
+        }
+        tc::mma_commit(&b_empty[sb]);
+        tc::mma_commit(&a_empty[sa]);
+      }
+      if (n_act > 0) tc::mma_commit(accum_bar);
+    }
+  }
+
   tc::fence_before_sync();
   __syncthreads();
   if (warp == kTcProducerWarps + 1) tc::tmem_dealloc(tmem_base, (uint32_t)tmem_cols);
@@ -354,6 +611,14 @@ static bool tc_geom(int cout, int kvol, int cin, TcGeom& g) {
 
 using namespace msmd;
 
+static int g_tc_variant = 0;  // 0: auto (by N); 2: A through shared memory; 3: A through tensor memory
+
+extern "C" MSMD_API int msmd_spconv_tc_set_variant(int variant) {
+  MSMD_REQUIRE(variant == 0 || variant == 2 || variant == 3, "spconv_tc_set_variant: variant must be 0, 2 or 3");
+  g_tc_variant = variant;
+  return MSMD_OK;
+}
+
 extern "C" MSMD_API int msmd_spconv_tc_supported(int cout, int kvol, int cin) {
   TcGeom g;
   return tc_geom(cout, kvol, cin, g) ? 1 : 0;
@@ -392,11 +657,28 @@ extern "C" MSMD_API int msmd_spconv_fwd_tc(const float* features, int n_in, cons
   if (n_out == 0) return MSMD_OK;
   MSMD_REQUIRE(features && packed_tc && pair_fwd && out, "spconv_fwd_tc: null pointer");
   MSMD_REQUIRE(((uintptr_t)packed_tc & 15) == 0, "spconv_fwd_tc: packed weights must be 16-byte aligned");
-  const TcSmemLayout L = tc_layout(g.N, kvol, g.chunks);
-  MSMD_REQUIRE(L.stages >= 2, "spconv_fwd_tc: tile does not fit in shared memory");
   const bool vec = (cin % 4 == 0) && (((uintptr_t)features & 15) == 0);
   const int tiles = ceil_div(n_out, kTcM);
-  static bool attr_set[2] = {false, false};
+  static bool attr_set[4] = {false, false, false, false};
+  // variant 3 (A in tensor memory) wins once the tile is shared-memory-bandwidth bound (N >= 96);
+  // below that the per-chunk latency chain of variant 2 is shorter (measured, profiles/README.md)
+  if (g_tc_variant == 3 || (g_tc_variant == 0 && g.N >= 96)) {
+    const Tc3Layout L = tc3_layout(g.N, kvol, g.chunks);
+    MSMD_REQUIRE(L.b_stages >= 1 && L.tmem_cols <= 512, "spconv_fwd_tc: tile does not fit on the SM");
+    auto kern = vec ? spconv_fwd_tc3_kernel<true> : spconv_fwd_tc3_kernel<false>;
+    if (!attr_set[2 + vec]) {
+      MSMD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      attr_set[2 + vec] = true;
+    }
+    kern<<<tiles, kTcThreads, L.total, stream>>>(features, packed_tc, pair_fwd, n_out, cin, g.cin_pad, cout,
+                                                 g.N, kvol, g.chunks, L.b_stages, L.b_stage_bytes,
+                                                 L.a_stages, L.raw_off, L.pair_off, L.act_off, L.bar_off,
+                                                 L.tmem_cols, scale, shift, residual, relu, out);
+    MSMD_LAUNCH_OK();
+    return MSMD_OK;
+  }
+  const TcSmemLayout L = tc_layout(g.N, kvol, g.chunks);
+  MSMD_REQUIRE(L.stages >= 2, "spconv_fwd_tc: tile does not fit in shared memory");
   auto kern = vec ? spconv_fwd_tc_kernel<true> : spconv_fwd_tc_kernel<false>;
   if (!attr_set[vec]) {
     MSMD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));

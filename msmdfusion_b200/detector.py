@@ -278,8 +278,8 @@ class MSMDFusionDetector(nn.Module, _VoxelPathMixin):
             order = torch.arange(lin.shape[0], device=device)
             winner = torch.full_like(canvas, -1, dtype=torch.long).scatter_reduce_(
                 0, lin, order, reduce='amax', include_self=True)
-            hit = winner >= 0
-            canvas[hit] = pk.real_pixels[winner[hit], 2]
+            depth = pk.real_pixels[:, 2].contiguous()
+            canvas = torch.where(winner >= 0, depth[winner.clamp_min(0)], canvas)  # no host sync
         canvas = canvas.view(ncanvas, 1, H, W)
         out = []
         for i in range(3):
@@ -327,6 +327,9 @@ class MSMDFusionDetector(nn.Module, _VoxelPathMixin):
         m3, m2 = cat(mix3), cat(mix2)
         voxel_3D.indices = torch.cat([coord_3D[:, :1], m3[:, None], coord_3D[:, 1:]], dim=1)
         voxel_2D.indices = torch.cat([coord_2D[:, :1], m2[:, None], coord_2D[:, 1:]], dim=1)
+        # kept for SparseMultiModalEncoderPaint's sync-free group selection (one sample per GPU)
+        voxel_3D._mix, voxel_3D._bzyx = m3, coord_3D
+        voxel_2D._mix, voxel_2D._bzyx = m2, coord_2D
         return voxel_3D, voxel_2D, cat(syn3), cat(syn2)
 
     # -- :400-418 ---------------------------------------------------------------------------

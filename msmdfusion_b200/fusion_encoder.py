@@ -127,6 +127,10 @@ class SparseMultiModalEncoderPaint(nn.Module):
     # -- one stage of the GMA convolution (:325-430) --------------------------------------
     def grouped_sparse_conv(self, voxel_3D, voxel_2D, syn_mix_3D, syn_mix_2D, stage_id, fps_num,
                             radius, max_cluster_samples, dist_thresh):
+        if voxel_3D.batch_size == 1 and getattr(voxel_3D, '_mix', None) is not None and \
+                getattr(voxel_2D, '_mix', None) is not None:
+            return self._grouped_sparse_conv_b1(voxel_3D, voxel_2D, syn_mix_3D, syn_mix_2D, stage_id,
+                                                fps_num, radius, max_cluster_samples, dist_thresh)
         ind3, ind2 = voxel_3D.indices, voxel_2D.indices
         feat3, feat2 = voxel_3D.features, voxel_2D.features
         c3 = self.in_channels_3D[stage_id]
@@ -189,6 +193,58 @@ class SparseMultiModalEncoderPaint(nn.Module):
                                          voxel_mixed_indices[:, [0, 2, 3, 4]]], dim=0).contiguous()
         unified_voxel = spconv.SparseConvTensor(unified_voxel_feat, unified_voxel_coors,
                                                 voxel_2D.spatial_shape, voxel_2D.batch_size)
+        return getattr(self.aggregation_blocks, stage_name)(unified_voxel)
+
+    def _grouped_sparse_conv_b1(self, voxel_3D, voxel_2D, syn_mix_3D, syn_mix_2D, stage_id, fps_num,
+                                radius, max_cluster_samples, dist_thresh):
+        """Same result as ``grouped_sparse_conv`` for one sample per GPU (the BASELINE sharding),
+        without host synchronisations: the voxel_modality_split of this package leaves the mix
+        flags and the 4-column coordinates on the tensors, the group sizes follow from the number
+        of mixed pairs P (only-3D = N3 - P, only-2D = N2 - P), and the row lists come from a
+        device scan (``ops.compact_unflagged``) instead of boolean-mask indexing."""
+        feat3, feat2 = voxel_3D.features, voxel_2D.features
+        bz3, bz2 = voxel_3D._bzyx, voxel_2D._bzyx
+        c3 = self.in_channels_3D[stage_id]
+        dev = feat3.device
+        P = syn_mix_3D.shape[0]
+        n3, n2 = bz3.shape[0], bz2.shape[0]
+        only3_rows = ops.compact_unflagged(voxel_3D._mix, n3 - P)
+        if n2 - P > 0:
+            only2_rows = ops.compact_unflagged(voxel_2D._mix, n2 - P)
+            only2_bzyx = bz2.index_select(0, only2_rows)
+            only2_feat = feat2.index_select(0, only2_rows)
+        else:  # pad_missing_batch_id (:208-225): one all-zero voxel for the missing batch id 0
+            only2_bzyx = torch.zeros((1, 4), dtype=bz2.dtype, device=dev)
+            only2_feat = torch.zeros((1, feat2.shape[1]), dtype=feat2.dtype, device=dev)
+        nn_idx = fps_nn_fast(only2_bzyx, bz3, fps_num, radius, max_cluster_samples, dist_thresh, base=0)
+
+        dummy_embedding = torch.rand(1, feat3.shape[1]).to(dev)
+        cross_gating = self.cross_gate_control[stage_id](torch.cat([feat3, dummy_embedding], dim=0))
+        only2_feat = cross_gating[nn_idx] * only2_feat
+
+        voxel_only_3D = spconv.SparseConvTensor(feat3.index_select(0, only3_rows),
+                                                bz3.index_select(0, only3_rows),
+                                                voxel_3D.spatial_shape, 1)
+        if P > 0:
+            mixed_3D_feat = feat3.index_select(0, syn_mix_3D)
+            gating = self.gate_control[stage_id](mixed_3D_feat)
+            mixed_feat = torch.cat([mixed_3D_feat, gating * feat2.index_select(0, syn_mix_2D)], dim=-1)
+            mixed_bzyx = bz2.index_select(0, syn_mix_2D)
+        else:
+            mixed_feat = torch.zeros((1, c3 + feat2.shape[1]), dtype=feat3.dtype, device=dev)
+            mixed_bzyx = torch.zeros((1, 4), dtype=bz2.dtype, device=dev)
+
+        stage_name = f'stage_{stage_id + 1}'
+        voxel_only_3D = getattr(self.grouped_sp_conv_blocks_3D, stage_name)(voxel_only_3D)
+        n_o3, n_o2, n_mx = voxel_only_3D.features.shape[0], only2_feat.shape[0], mixed_feat.shape[0]
+        cu = c3 + 64
+        # zero-padded concatenation (:414-425) written straight into the unified buffer
+        unified_feat = torch.zeros((n_o3 + n_o2 + n_mx, cu), dtype=feat3.dtype, device=dev)
+        unified_feat[:n_o3, :c3] = voxel_only_3D.features
+        unified_feat[n_o3:n_o3 + n_o2, c3:] = only2_feat
+        unified_feat[n_o3 + n_o2:] = mixed_feat
+        unified_coors = torch.cat([voxel_only_3D.indices, only2_bzyx, mixed_bzyx], dim=0)
+        unified_voxel = spconv.SparseConvTensor(unified_feat, unified_coors, voxel_2D.spatial_shape, 1)
         return getattr(self.aggregation_blocks, stage_name)(unified_voxel)
 
     def forward(self, voxel_3D_list, voxel_2D_list, syn_mix_3D_list, syn_mix_2D_list, fps_num_list,

@@ -205,6 +205,11 @@ class TcWeight:
         self.packed, self.cout, self.kvol, self.cin = packed, cout, kvol, cin
 
 
+def set_tc_variant(variant):
+    """0 (default): chosen by Cout; 3: A operand staged in tensor memory; 2: A operand in shared memory."""
+    check(lib().msmd_spconv_tc_set_variant(int(variant)), 'msmd_spconv_tc_set_variant')
+
+
 def tc_supported(cout, kvol, cin):
     return bool(lib().msmd_spconv_tc_supported(int(cout), int(kvol), int(cin)))
 
@@ -363,6 +368,20 @@ def modality_split_single(coord3, coord2, offset3=0, offset2=0):
                                         ws.numel(), stream(dev)), 'msmd_modality_split')
     p = int(count.item())
     return mix3, mix2, syn3[:p], syn2[:p]
+
+
+def compact_unflagged(flags, count):
+    """Rows with flags == 0, ascending, as int64 (count known on the host -> no synchronisation)."""
+    flags = flags.contiguous()
+    assert flags.dtype == torch.int32
+    n = flags.shape[0]
+    out = torch.empty((max(n, 1),), dtype=torch.int64, device=flags.device)
+    cnt = torch.empty((1,), dtype=torch.int32, device=flags.device)
+    ws = scratch.get(flags.device, lib().msmd_scan_workspace())
+    with _Timed('compact_unflagged', n=n):
+        check(lib().msmd_compact_unflagged(ptr(flags), n, ptr(out), ptr(cnt), ptr(ws), ws.numel(),
+                                           stream(flags.device)), 'msmd_compact_unflagged')
+    return out[:int(count)]
 
 
 def sparse_add(idx_a, feat_a, idx_b, feat_b, spatial_shape, batch_size):

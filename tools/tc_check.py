@@ -67,13 +67,18 @@ def main():
         (32, 32, 100, 1, 27, 0.5, False),
     ]
     ok = True
-    for i, s in enumerate(shapes):
-        try:
-            ok &= run(*s[:6], seed=i, epilogue=s[6])
-        except Exception as e:  # noqa: BLE001
-            print('EXC ', s, repr(e))
-            ok = False
-            break
+    variants = [int(v) for v in os.environ.get('TC_VARIANTS', '3,2').split(',')]
+    for variant in variants:
+        ops.set_tc_variant(variant)
+        print('--- variant', variant)
+        for i, s in enumerate(shapes):
+            try:
+                ok &= run(*s[:6], seed=i, epilogue=s[6])
+            except Exception as e:  # noqa: BLE001
+                print('EXC ', s, repr(e))
+                ok = False
+                break
+    ops.set_tc_variant(0)
     print('ALL OK' if ok else 'MISMATCH')
     return 0 if ok else 1
 
