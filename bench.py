@@ -219,7 +219,8 @@ def run_ours(args, rank, world, device):
         e.record()
     sync_all()
     launches = _cabi.lib().msmd_launch_count() - launches0
-    step_ms = sorted(s.elapsed_time(e) for s, e in ev)
+    step_raw = [s.elapsed_time(e) for s, e in ev]
+    step_ms = sorted(step_raw)
     dev_ms = sum(step_ms)
 
     # ---- end to end: pinned host points -> H2D -> hot path -> D2H of a result checksum ----
@@ -280,7 +281,16 @@ def run_ours(args, rank, world, device):
         tf32_peak = bf16 / 2.0  # tcgen05 kind::tf32 issues at half the bf16 rate
         hbm_time = b / (hbm * 1e9)
         tensor_time = (3.0 * f) / (tf32_peak * 1e12) if tc else 0.0  # 3 MMAs per product (3xTF32)
-        common = {'traffic': None, 'peak_source': src,
+        traffic, traffic_src = None, None
+        tp = os.path.join(ROOT, 'profiles', 'r01d_ncu_full_spconv_tc_v4_profileS.json')
+        if tc and args.workload == 'L' and args.profile == 'S' and os.path.exists(tp):
+            t = json.load(open(tp))  # one committed `ncu --set full` capture of these 21 launches
+            scale = {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}
+            traffic = t['sum_dram_read'] * scale[t['unit_bytes']] + t['sum_dram_write'] * 1e3
+            traffic_src = ('dram__bytes_read.sum + dram__bytes_write.sum summed over the 21 conv launches of '
+                           'one scene, profiles/r01d_ncu_full_spconv_tc_v4_profileS.json (writes stay in the '
+                           '126 MB L2 at this size)')
+        common = {'traffic': traffic, 'traffic_source': traffic_src, 'peak_source': src,
                   'kernel': ('spconv_fwd_tc_kernel (tcgen05 kind::tf32, 3xTF32)' if tc else
                              'spconv_fwd_simt_kernel') + ' (%d launches/scene, summed)' % (len(conv) // 3),
                   'kernel_ms_per_step': round(conv_ms / 3, 4),
@@ -299,7 +309,7 @@ def run_ours(args, rank, world, device):
     n_vox = int(feats[0].indices.shape[0])
     return dict(dev_ms=dev_ms, e2e_ms=e2e_ms, launches=int(launches), clocks=clk, roofline=roof,
                 step_ms=dict(min=round(step_ms[0], 4), median=round(step_ms[len(step_ms) // 2], 4),
-                             max=round(step_ms[-1], 4)),
+                             max=round(step_ms[-1], 4), all=[round(x, 3) for x in step_raw[:32]]),
                 points=int(pts_np.shape[0]), voxels=n_vox, checksum=checksum,
                 h2d=int(pts_np.nbytes) + int(h2d_extra[0]), d2h=4)
 

@@ -121,7 +121,9 @@ class _Scratch:
         self.buf = {}
 
     def get(self, device, nbytes, slot='ws'):
-        key = (torch.device(device).index, slot)
+        # one buffer per (device, stream): reuse is stream-ordered, and concurrent streams (the
+        # overlapped NN-assignment chains of the GMA encoder) never share scratch memory
+        key = (torch.device(device).index, slot, torch.cuda.current_stream(device).cuda_stream)
         b = self.buf.get(key)
         if b is None or b.numel() < nbytes:
             b = torch.empty(max(int(nbytes), 1 << 16), dtype=torch.uint8, device=device)

@@ -154,25 +154,30 @@ fps_cluster_kernel(const float* __restrict__ xyz, int n, int m, int block, int l
         fps_st_cluster_v4(remote + 16, __float_as_uint(cy), __float_as_uint(cz), (unsigned)r, 0u);
       }
     }
-    // every thread: wait for the 8 candidates of this round in LOCAL shared memory, take the max
-    unsigned long long g = 0ull;
-    long long t0 = 0;
-#pragma unroll
-    for (int c = 0; c < kFpsCluster; ++c) {
+    // lanes 0..7 of every warp each wait for one candidate of this round in LOCAL shared memory;
+    // the warp then takes the max with two redux instructions and shuffles the winner's xyz
+    unsigned long long kc = 0ull;
+    float cx = 0.f, cy = 0.f, cz = 0.f;
+    if (lane < kFpsCluster) {
       uint4 h0, h1;
+      long long t0 = 0;
       for (;;) {
-        h0 = fps_ld_volatile_v4(&cand[par][c].h0);
-        h1 = fps_ld_volatile_v4(&cand[par][c].h1);
+        h0 = fps_ld_volatile_v4(&cand[par][lane].h0);
+        h1 = fps_ld_volatile_v4(&cand[par][lane].h1);
         if (h0.w == (unsigned)r && h1.z == (unsigned)r) break;
         if (t0 == 0) t0 = clock64();
         else if (clock64() - t0 > 4000000000LL) __trap();  // protocol bug: fail, never hang
       }
-      const unsigned long long kc = ((unsigned long long)h0.y << 32) | h0.x;
-      if (c == 0 || kc > g) {
-        g = kc;
-        x1 = __uint_as_float(h0.z); y1 = __uint_as_float(h1.x); z1 = __uint_as_float(h1.y);
-      }
+      kc = ((unsigned long long)h0.y << 32) | h0.x;
+      cx = __uint_as_float(h0.z); cy = __uint_as_float(h1.x); cz = __uint_as_float(h1.y);
     }
+    __syncwarp();
+    const unsigned long long g = fps_warp_max(kc);
+    const unsigned winners = __ballot_sync(0xffffffffu, lane < kFpsCluster && kc == g);
+    const int src = __ffs(winners) - 1;
+    x1 = __shfl_sync(0xffffffffu, cx, src);
+    y1 = __shfl_sync(0xffffffffu, cy, src);
+    z1 = __shfl_sync(0xffffffffu, cz, src);
     if (gtid == 0) {
       const unsigned p = ~(unsigned)(g & 0xffffffffull);
       const unsigned rev = p >> 22, q = p & ((1u << 22) - 1u);
@@ -181,6 +186,67 @@ fps_cluster_kernel(const float* __restrict__ xyz, int n, int m, int block, int l
     }
   }
   cluster.sync();  // no CTA may exit while peers can still write into its shared memory
+}
+
+// Small point sets (n <= 8192): ONE CTA of 1024 threads, points in registers, a shared-memory copy
+// of the coordinates for the winner's lookup.  One __syncthreads per round; every warp reduces the
+// 32 per-warp candidates redundantly, so no broadcast step and no inter-SM traffic on the chain.
+constexpr int kFpsSingleThreads = 1024;
+constexpr int kFpsSingleMaxPerThread = 8;
+
+template <int PPT>
+__global__ void __launch_bounds__(kFpsSingleThreads, 1)
+fps_single_kernel(const float* __restrict__ xyz, int n, int m, int block, int log2block,
+                  int* __restrict__ idx) {
+  extern __shared__ float xyz_s[];  // (n, 3)
+  __shared__ unsigned long long warp_best[2][kFpsSingleThreads / 32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nthreads = blockDim.x, nwarps = blockDim.x >> 5;
+  float px[PPT], py[PPT], pz[PPT], temp[PPT];
+  unsigned prio[PPT];
+#pragma unroll
+  for (int j = 0; j < PPT; ++j) {
+    const int k = tid + j * nthreads;
+    if (k < n) {
+      px[j] = xyz[3 * k + 0]; py[j] = xyz[3 * k + 1]; pz[j] = xyz[3 * k + 2];
+      xyz_s[3 * k + 0] = px[j]; xyz_s[3 * k + 1] = py[j]; xyz_s[3 * k + 2] = pz[j];
+      prio[j] = fps_priority(k, block, log2block);
+    } else {
+      px[j] = py[j] = pz[j] = 0.f;
+      prio[j] = 0xffffffffu;
+    }
+    temp[j] = 1e10f;
+  }
+  if (tid == 0) idx[0] = 0;
+  __syncthreads();
+  float x1 = xyz_s[0], y1 = xyz_s[1], z1 = xyz_s[2];
+  for (int r = 1; r < m; ++r) {
+    const int par = r & 1;
+    unsigned long long best = 0ull;
+#pragma unroll
+    for (int j = 0; j < PPT; ++j) {
+      const int k = tid + j * nthreads;
+      if (k < n) {
+        const float d = (px[j] - x1) * (px[j] - x1) + (py[j] - y1) * (py[j] - y1) +
+                        (pz[j] - z1) * (pz[j] - z1);
+        const float d2 = fminf(d, temp[j]);
+        temp[j] = d2;
+        const unsigned long long key =
+            ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned long long)(~prio[j]);
+        best = u64max(best, key);
+      }
+    }
+    best = fps_warp_max(best);
+    if (lane == 0) warp_best[par][warp] = best;
+    __syncthreads();
+    const unsigned long long g = fps_warp_max(lane < nwarps ? warp_best[par][lane] : 0ull);
+    const unsigned p = ~(unsigned)(g & 0xffffffffull);
+    const unsigned rev = p >> 22, q = p & ((1u << 22) - 1u);
+    const unsigned t = log2block ? (__brev(rev) >> (32 - log2block)) : 0u;
+    const int old = (int)((q << log2block) | t);
+    x1 = xyz_s[3 * old + 0]; y1 = xyz_s[3 * old + 1]; z1 = xyz_s[3 * old + 2];
+    if (tid == 0) idx[r] = old;
+  }
 }
 
 // Fallback for point sets that do not fit the register-resident cluster kernel: one CTA,
@@ -364,7 +430,22 @@ extern "C" MSMD_API int msmd_fps(const float* xyz, int n, int m, int* idx, void*
   const int block = fps_block_size(n, &log2block);
   MSMD_REQUIRE((n >> log2block) < (1 << 22), "fps: too many points");
   const long long cap = (long long)kFpsCluster * kFpsThreads;
-  if (n <= cap * kFpsMaxPerThread) {
+  if (n <= kFpsSingleThreads * kFpsSingleMaxPerThread) {
+    // the round is instruction-issue bound (every warp repeats the block-level reduction), so
+    // use as few warps as keep <= 8 points per thread
+    int threads = ceil_div(ceil_div(n, kFpsSingleMaxPerThread), 32) * 32;
+    if (threads < 128) threads = 128;
+    if (threads > kFpsSingleThreads) threads = kFpsSingleThreads;
+    const size_t smem = (size_t)n * 3 * sizeof(float);
+    static bool attr_done = false;
+    if (!attr_done) {
+      MSMD_CUDA_OK(cudaFuncSetAttribute(fps_single_kernel<kFpsSingleMaxPerThread>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+      attr_done = true;
+    }
+    fps_single_kernel<kFpsSingleMaxPerThread><<<1, threads, smem, stream>>>(xyz, n, m, block, log2block, idx);
+    MSMD_LAUNCH_OK();
+  } else if (n <= cap * kFpsMaxPerThread) {
     const int ppt = ceil_div(n, cap);
 #define MSMD_FPS(P)                                                                             \
   do {                                                                                          \

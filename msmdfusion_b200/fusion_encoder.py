@@ -66,6 +66,8 @@ class SparseMultiModalEncoderPaint(nn.Module):
         self.down_stride = down_stride
         self.order = order
         self.fp16_enabled = False
+        self.overlap_assign = True   # run the stages' NN-assignment chains on side streams
+        self._side_streams = None
         self.make_grouped_sparse_conv_blocks(norm_cfg)
         self.make_aggregation_block(norm_cfg)
         self.make_downscale_block(norm_cfg)
@@ -195,8 +197,24 @@ class SparseMultiModalEncoderPaint(nn.Module):
                                                 voxel_2D.spatial_shape, voxel_2D.batch_size)
         return getattr(self.aggregation_blocks, stage_name)(unified_voxel)
 
+    def _assign_b1(self, voxel_3D, voxel_2D, P, fps_num, radius, max_cluster_samples, dist_thresh):
+        """Index-only part of a stage (one sample per GPU): only-3D / only-2D row lists and the
+        nearest-3-D-voxel assignment of the only-2D voxels.  Depends on coordinates only, so
+        ``forward`` runs the four stages' chains concurrently on side streams."""
+        bz3, bz2 = voxel_3D._bzyx, voxel_2D._bzyx
+        n3, n2 = bz3.shape[0], bz2.shape[0]
+        only3_rows = ops.compact_unflagged(voxel_3D._mix, n3 - P)
+        if n2 - P > 0:
+            only2_rows = ops.compact_unflagged(voxel_2D._mix, n2 - P)
+            only2_bzyx = bz2.index_select(0, only2_rows)
+        else:  # pad_missing_batch_id (:208-225): one all-zero voxel for the missing batch id 0
+            only2_rows = None
+            only2_bzyx = torch.zeros((1, 4), dtype=bz2.dtype, device=bz2.device)
+        nn_idx = fps_nn_fast(only2_bzyx, bz3, fps_num, radius, max_cluster_samples, dist_thresh, base=0)
+        return dict(only3_rows=only3_rows, only2_rows=only2_rows, only2_bzyx=only2_bzyx, nn_idx=nn_idx)
+
     def _grouped_sparse_conv_b1(self, voxel_3D, voxel_2D, syn_mix_3D, syn_mix_2D, stage_id, fps_num,
-                                radius, max_cluster_samples, dist_thresh):
+                                radius, max_cluster_samples, dist_thresh, assign=None):
         """Same result as ``grouped_sparse_conv`` for one sample per GPU (the BASELINE sharding),
         without host synchronisations: the voxel_modality_split of this package leaves the mix
         flags and the 4-column coordinates on the tensors, the group sizes follow from the number
@@ -207,16 +225,14 @@ class SparseMultiModalEncoderPaint(nn.Module):
         c3 = self.in_channels_3D[stage_id]
         dev = feat3.device
         P = syn_mix_3D.shape[0]
-        n3, n2 = bz3.shape[0], bz2.shape[0]
-        only3_rows = ops.compact_unflagged(voxel_3D._mix, n3 - P)
-        if n2 - P > 0:
-            only2_rows = ops.compact_unflagged(voxel_2D._mix, n2 - P)
-            only2_bzyx = bz2.index_select(0, only2_rows)
-            only2_feat = feat2.index_select(0, only2_rows)
-        else:  # pad_missing_batch_id (:208-225): one all-zero voxel for the missing batch id 0
-            only2_bzyx = torch.zeros((1, 4), dtype=bz2.dtype, device=dev)
+        if assign is None:
+            assign = self._assign_b1(voxel_3D, voxel_2D, P, fps_num, radius, max_cluster_samples,
+                                     dist_thresh)
+        only3_rows, only2_bzyx, nn_idx = assign['only3_rows'], assign['only2_bzyx'], assign['nn_idx']
+        if assign['only2_rows'] is not None:
+            only2_feat = feat2.index_select(0, assign['only2_rows'])
+        else:
             only2_feat = torch.zeros((1, feat2.shape[1]), dtype=feat2.dtype, device=dev)
-        nn_idx = fps_nn_fast(only2_bzyx, bz3, fps_num, radius, max_cluster_samples, dist_thresh, base=0)
 
         dummy_embedding = torch.rand(1, feat3.shape[1]).to(dev)
         cross_gating = self.cross_gate_control[stage_id](torch.cat([feat3, dummy_embedding], dim=0))
@@ -247,16 +263,60 @@ class SparseMultiModalEncoderPaint(nn.Module):
         unified_voxel = spconv.SparseConvTensor(unified_feat, unified_coors, voxel_2D.spatial_shape, 1)
         return getattr(self.aggregation_blocks, stage_name)(unified_voxel)
 
+    def _assign_all_overlapped(self, voxel_3D_list, voxel_2D_list, syn_mix_3D_list, fps_num_list,
+                               radius_list, max_cluster_samples_list, dist_thresh_list):
+        """Launch the index-only chains (FPS is ~2000 serial rounds on 8 SMs) of all stages on side
+        streams: they depend on coordinates only, so they overlap each other and the convolutions
+        of earlier stages.  Returns per-stage (assign dict, completion event) or None."""
+        n = len(voxel_2D_list)
+        ok = all(v3.batch_size == 1 and getattr(v3, '_mix', None) is not None and
+                 getattr(v2, '_mix', None) is not None and v3.features.is_cuda
+                 for v3, v2 in zip(voxel_3D_list, voxel_2D_list))
+        if not ok or not self.overlap_assign:
+            return None
+        dev = voxel_3D_list[0].features.device
+        if self._side_streams is None or self._side_streams[0].device != dev:
+            self._side_streams = [torch.cuda.Stream(device=dev) for _ in range(n)]
+        main = torch.cuda.current_stream(dev)
+        ready = torch.cuda.Event()
+        ready.record(main)
+        out = []
+        for s in range(n):
+            side = self._side_streams[s]
+            side.wait_event(ready)
+            with torch.cuda.stream(side):
+                a = self._assign_b1(voxel_3D_list[s], voxel_2D_list[s], syn_mix_3D_list[s].shape[0],
+                                    fps_num_list[s], radius_list[s], max_cluster_samples_list[s],
+                                    dist_thresh_list[s])
+                done = torch.cuda.Event()
+                done.record(side)
+            # The chain's outputs are consumed on the main stream.  No record_stream is needed: a
+            # side stream only ever starts work after waiting for `ready`, recorded on the main
+            # stream at the top of a forward, so blocks of its pool are never reused before every
+            # earlier main-stream reader has finished.
+            out.append((a, done))
+        return out
+
     def forward(self, voxel_3D_list, voxel_2D_list, syn_mix_3D_list, syn_mix_2D_list, fps_num_list,
                 radius_list, max_cluster_samples_list, dist_thresh_list):
         """:433-459 -> list of the 4 down-scaled stage outputs."""
         stage_outs = []
+        pre = self._assign_all_overlapped(voxel_3D_list, voxel_2D_list, syn_mix_3D_list, fps_num_list,
+                                          radius_list, max_cluster_samples_list, dist_thresh_list)
         for stage_id in range(len(voxel_2D_list)):
             stage_name = f'stage_{stage_id + 1}'
-            out = self.grouped_sparse_conv(
-                voxel_3D_list[stage_id], voxel_2D_list[stage_id], syn_mix_3D_list[stage_id],
-                syn_mix_2D_list[stage_id], stage_id, fps_num_list[stage_id], radius_list[stage_id],
-                max_cluster_samples_list[stage_id], dist_thresh_list[stage_id])
+            if pre is not None:
+                assign, done = pre[stage_id]
+                torch.cuda.current_stream(voxel_3D_list[stage_id].features.device).wait_event(done)
+                out = self._grouped_sparse_conv_b1(
+                    voxel_3D_list[stage_id], voxel_2D_list[stage_id], syn_mix_3D_list[stage_id],
+                    syn_mix_2D_list[stage_id], stage_id, fps_num_list[stage_id], radius_list[stage_id],
+                    max_cluster_samples_list[stage_id], dist_thresh_list[stage_id], assign=assign)
+            else:
+                out = self.grouped_sparse_conv(
+                    voxel_3D_list[stage_id], voxel_2D_list[stage_id], syn_mix_3D_list[stage_id],
+                    syn_mix_2D_list[stage_id], stage_id, fps_num_list[stage_id], radius_list[stage_id],
+                    max_cluster_samples_list[stage_id], dist_thresh_list[stage_id])
             if stage_id > 0:
                 out = Fsp.sparse_add(out, stage_outs[stage_id - 1])
             stage_outs.append(getattr(self.downscale_blocks, stage_name)(out))

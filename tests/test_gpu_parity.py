@@ -635,3 +635,42 @@ def test_msmd_voxel_space_end_to_end(batch):
     e_mm = cpu.dense(e_outs[-1].indices, e_outs[-1].features, e_outs[-1].spatial_shape, batch)
     e_bev = np.concatenate([e_spatial, e_mm.reshape(batch, -1, 180, 180)], 1)
     assert feat_err(bev.cpu().numpy(), e_bev) < FEAT_TOL
+
+
+# --------------------------------------------------------------------------------------
+# tensor-core sparse conv variants + sync-free compaction
+# --------------------------------------------------------------------------------------
+@pytest.mark.parametrize('variant', [2, 3])
+@pytest.mark.parametrize('cin,cout,kvol', [(16, 16, 27), (5, 16, 27), (64, 64, 27), (128, 128, 27), (80, 96, 27),
+                                           (128, 128, 3), (192, 192, 27)])
+def test_spconv_tc_variants_match_oracle(variant, cin, cout, kvol):
+    """Both tensor-core kernels (A operand through shared memory / through tensor memory) against
+    the CPU oracle on a random rulebook, with the fused BN/residual/ReLU epilogue."""
+    rng = np.random.default_rng(cin * 1000 + cout + kvol)
+    n_in, n_out = 5000, 3333
+    feat = rng.standard_normal((n_in, cin)).astype(np.float32)
+    w = (rng.standard_normal((cout, kvol, 1, 1, cin)) / np.sqrt(cin * kvol * 0.3)).astype(np.float32)
+    pair = rng.integers(0, n_in, (kvol, n_out)).astype(np.int32)
+    pair[rng.random((kvol, n_out)) > 0.3] = -1
+    if kvol > 2:
+        pair[1] = -1  # a kernel offset no voxel uses: its K chunks are skipped
+    scale = (rng.random(cout) + 0.5).astype(np.float32)
+    shift = (rng.standard_normal(cout) * 0.1).astype(np.float32)
+    res = rng.standard_normal((n_out, cout)).astype(np.float32)
+    expect = np.maximum(cpu.spconv_fwd(feat, w.reshape(cout, kvol, cin), pair) * scale + shift + res, 0)
+    ops.set_tc_variant(variant)
+    try:
+        got = ops.spconv_fwd_tc(cuda(feat), ops.pack_weight_tc(cuda(w)), cuda(pair), cuda(scale), cuda(shift),
+                                cuda(res), True).cpu().numpy()
+    finally:
+        ops.set_tc_variant(0)
+    assert feat_err(got, expect) < FEAT_TOL
+
+
+def test_compact_unflagged_matches_numpy():
+    rng = np.random.default_rng(4)
+    for n in (1, 31, 1000, 70001):
+        flags = (rng.random(n) < 0.4).astype(np.int32)
+        want = np.nonzero(flags == 0)[0]
+        got = ops.compact_unflagged(cuda(flags), want.shape[0]).cpu().numpy()
+        assert got.dtype == np.int64 and np.array_equal(got, want)
