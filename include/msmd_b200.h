@@ -149,6 +149,45 @@ MSMD_API int msmd_spconv_fwd_tc(const float* features, int n_in, const float* pa
                                 const float* scale, const float* shift, const float* residual,
                                 int relu, float* out, msmd_stream_t stream);
 
+/* ------------------------------------------------------------------------------------
+ * Native executor for a chain of sparse convolutions -- the host loop of
+ * SparseEncoder.forward (mmdet3d/models/middle_encoders/sparse_encoder.py:96-133) and of the
+ * SparseSequential / SparseBasicBlock modules it is built from (mmdet3d/ops/sparse_block.py:
+ * 103-126,161-190): ONE call runs every rulebook build and convolution of the plan.
+ *   layers[i] reads activation `input` (0 = the network input, j+1 = output of layer j) and
+ *   writes activation i+1;  y = relu?(conv(x) * scale + shift + acts[residual]).
+ *   All intermediates (grids, rulebooks, features, indices) are carved from `arena`; on return
+ *   acts[0..n_layers] describe every activation (device pointers into the arena, host counts).
+ *   The only synchronisations are the N_out read-backs of the strided convolutions.
+ *   MSMD_ERR_WORKSPACE: arena too small (msmd_last_error() says how far it got).
+ * ---------------------------------------------------------------------------------- */
+typedef struct msmd_conv_layer {
+  int subm;                 /* 1 = SubMConv3d, 0 = SparseConv3d */
+  int ksize[3], stride[3], padding[3], dilation[3];
+  int cin, cout;
+  const float* weight;      /* device: msmd_spconv_tc_pack_weight image if weight_tc, else msmd_spconv_pack_weight */
+  int weight_tc;
+  const float* scale;       /* device (cout) or NULL: folded BatchNorm1d(eval) */
+  const float* shift;
+  int relu;
+  int input;                /* activation index read by this layer */
+  int residual;             /* activation index added before the ReLU, or -1 */
+} msmd_conv_layer;
+
+typedef struct msmd_sparse_desc {
+  float* features;          /* device (n, channels) */
+  int* indices;             /* device (n, 4) (b,z,y,x) */
+  int n, channels;
+  int spatial_shape[3];
+} msmd_sparse_desc;
+
+MSMD_API int msmd_sparse_net_forward(const msmd_conv_layer* layers, int n_layers,
+                                     const float* features, const int* indices, int n, int channels,
+                                     int batch_size, const int* spatial_shape /* host [3] */,
+                                     void* arena, size_t arena_bytes,
+                                     msmd_sparse_desc* acts /* host [n_layers + 1] */,
+                                     msmd_stream_t stream);
+
 /* SparseConvTensor.dense(): (n,c) rows -> (batch, c, D, H, W), zero-filled inside.
  * spconv-1.x equivalent mmdet3d/ops/spconv/structure.py:54-66. */
 MSMD_API int msmd_to_dense(const int* indices, const float* features, int n, int c, int batch_size,

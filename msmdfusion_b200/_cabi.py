@@ -18,6 +18,21 @@ _vp = ctypes.c_void_p
 _i = ctypes.c_int
 _sz = ctypes.c_size_t
 
+class ConvLayer(ctypes.Structure):
+    """msmd_conv_layer (include/msmd_b200.h)."""
+    _fields_ = [('subm', ctypes.c_int), ('ksize', ctypes.c_int * 3), ('stride', ctypes.c_int * 3),
+                ('padding', ctypes.c_int * 3), ('dilation', ctypes.c_int * 3), ('cin', ctypes.c_int),
+                ('cout', ctypes.c_int), ('weight', ctypes.c_void_p), ('weight_tc', ctypes.c_int),
+                ('scale', ctypes.c_void_p), ('shift', ctypes.c_void_p), ('relu', ctypes.c_int),
+                ('input', ctypes.c_int), ('residual', ctypes.c_int)]
+
+
+class SparseDesc(ctypes.Structure):
+    """msmd_sparse_desc (include/msmd_b200.h)."""
+    _fields_ = [('features', ctypes.c_void_p), ('indices', ctypes.c_void_p), ('n', ctypes.c_int),
+                ('channels', ctypes.c_int), ('spatial_shape', ctypes.c_int * 3)]
+
+
 # name -> (restype, argtypes).  Device pointers travel as void*; host arrays as int*/float*.
 SIGNATURES = {
     'msmd_last_error': (ctypes.c_char_p, []),
@@ -42,6 +57,7 @@ SIGNATURES = {
     'msmd_spconv_tc_packed_floats': (_sz, [_i, _i, _i]),
     'msmd_spconv_tc_pack_weight': (_i, [_vp, _i, _i, _i, _vp, _vp]),
     'msmd_spconv_fwd_tc': (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _vp]),
+    'msmd_sparse_net_forward': (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _c_int_p, _vp, _sz, _vp, _vp]),
     'msmd_to_dense': (_i, [_vp, _vp, _i, _i, _i, _c_int_p, _vp, _vp]),
     'msmd_fps_workspace': (_sz, [_i]),
     'msmd_fps': (_i, [_vp, _i, _i, _vp, _vp, _sz, _vp]),
@@ -106,12 +122,24 @@ def stream(device=None):
     return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
+_INTS, _FLOATS = {}, {}
+
+
 def ints(vals):
-    return (ctypes.c_int * len(vals))(*[int(v) for v in vals])
+    """Host int array for a geometry tuple (cached: the same few tuples recur every call)."""
+    key = tuple(int(v) for v in vals)
+    a = _INTS.get(key)
+    if a is None:
+        a = _INTS[key] = (ctypes.c_int * len(key))(*key)
+    return a
 
 
 def floats(vals):
-    return (ctypes.c_float * len(vals))(*[float(v) for v in vals])
+    key = tuple(float(v) for v in vals)
+    a = _FLOATS.get(key)
+    if a is None:
+        a = _FLOATS[key] = (ctypes.c_float * len(key))(*key)
+    return a
 
 
 class _Scratch:

@@ -1,0 +1,182 @@
+// executor.cu -- native executor for a chain of sparse convolutions (the host-side loop of
+// SparseEncoder.forward, mmdet3d/models/middle_encoders/sparse_encoder.py:96-133, and of the
+// spconv SparseSequential / SparseBasicBlock modules it is made of).
+//
+// The Python modules of this package launch one C-ABI call per rulebook / convolution, i.e.
+// ~55 ctypes calls + allocations + 4 blocking size read-backs per LiDAR scene: ~1.2 ms of host
+// time against ~1.9 ms of GPU time.  This executor runs the same sequence from C++ with ONE call:
+// the layer list ("plan") is built once from the module tree, all intermediates are bump-allocated
+// from a caller-provided arena (the library still never allocates), and only the N_out of the
+// strided convolutions is read back (the output tensors cannot be sized without it).
+// Results are bit-identical to the module path -- the same kernels run on the same operands.
+#include <map>
+#include <vector>
+
+#include "common.cuh"
+
+namespace msmd {
+
+struct IndexSetX {
+  int* indices = nullptr;
+  int n = 0;
+  int shape[3] = {0, 0, 0};
+  uint32_t* bits = nullptr;
+  int* prefix = nullptr;
+  int* perm = nullptr;
+  bool has_grid = false;
+  bool ordered = false;  // rows already in ascending linear order (output of a strided conv)
+  std::map<std::vector<int>, int*> subm;  // (ksize, dilation) -> pair_fwd
+};
+
+struct Arena {
+  char* base;
+  size_t size, used;
+  template <typename T>
+  T* take(size_t count) {
+    const size_t off = align_up(used, 256);
+    const size_t end = off + sizeof(T) * (count ? count : 1);
+    used = end;
+    if (end > size) return nullptr;
+    return (T*)(base + off);
+  }
+};
+
+}  // namespace msmd
+
+using namespace msmd;
+
+#define MSMD_TRY(expr)        \
+  do {                        \
+    int _r = (expr);          \
+    if (_r != MSMD_OK) return _r; \
+  } while (0)
+
+#define MSMD_ARENA(ptr, T, count)                                                              \
+  T* ptr = arena.take<T>(count);                                                               \
+  if (!ptr) {                                                                                  \
+    set_error("sparse_net_forward: arena too small (%zu bytes needed so far, %zu given)",      \
+              arena.used, arena.size);                                                         \
+    return MSMD_ERR_WORKSPACE;                                                                 \
+  }
+
+static int ensure_grid(IndexSetX& s, int batch, Arena& arena, void* scan_ws, size_t scan_ws_bytes,
+                       cudaStream_t stream) {
+  if (s.has_grid) return MSMD_OK;
+  const size_t words = msmd_grid_num_words(batch, s.shape);
+  MSMD_ARENA(bits, uint32_t, words);
+  MSMD_ARENA(prefix, int, words);
+  int* perm = nullptr;
+  if (!s.ordered) {
+    MSMD_ARENA(p, int, (size_t)s.n);
+    perm = p;
+  }
+  MSMD_ARENA(count, int, 1);
+  MSMD_TRY(msmd_grid_build(s.indices, s.n, batch, s.shape, bits, prefix, perm, count, scan_ws,
+                           scan_ws_bytes, (msmd_stream_t)stream));
+  s.bits = bits; s.prefix = prefix; s.perm = perm; s.has_grid = true;
+  return MSMD_OK;
+}
+
+extern "C" MSMD_API int msmd_sparse_net_forward(const msmd_conv_layer* layers, int n_layers,
+                                                const float* features, const int* indices, int n,
+                                                int channels, int batch_size, const int* spatial_shape,
+                                                void* arena_ptr, size_t arena_bytes,
+                                                msmd_sparse_desc* acts, msmd_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  MSMD_REQUIRE(layers && n_layers > 0 && acts && arena_ptr, "sparse_net_forward: null argument");
+  MSMD_REQUIRE(n >= 0 && channels > 0 && batch_size > 0, "sparse_net_forward: bad input sizes");
+  Arena arena{(char*)arena_ptr, arena_bytes, 0};
+  const size_t scan_ws_bytes = msmd_scan_workspace();
+  MSMD_ARENA(scan_ws, char, scan_ws_bytes);
+
+  std::vector<IndexSetX> isets;
+  isets.reserve(n_layers + 1);
+  std::vector<int> act_iset(n_layers + 1, -1);
+  {
+    IndexSetX s0;
+    s0.indices = (int*)indices; s0.n = n;
+    for (int d = 0; d < 3; ++d) s0.shape[d] = spatial_shape[d];
+    isets.push_back(s0);
+    act_iset[0] = 0;
+    acts[0].features = (float*)features; acts[0].indices = (int*)indices; acts[0].n = n;
+    acts[0].channels = channels;
+    for (int d = 0; d < 3; ++d) acts[0].spatial_shape[d] = spatial_shape[d];
+  }
+
+  for (int li = 0; li < n_layers; ++li) {
+    const msmd_conv_layer& L = layers[li];
+    MSMD_REQUIRE(L.input >= 0 && L.input <= li, "sparse_net_forward: layer %d reads activation %d", li, L.input);
+    MSMD_REQUIRE(L.residual < 0 || L.residual <= li, "sparse_net_forward: layer %d bad residual", li);
+    const msmd_sparse_desc in = acts[L.input];
+    MSMD_REQUIRE(in.channels == L.cin, "sparse_net_forward: layer %d expects %d channels, got %d", li, L.cin,
+                 in.channels);
+    const int kvol = L.ksize[0] * L.ksize[1] * L.ksize[2];
+    const int in_id = act_iset[L.input];
+    MSMD_TRY(ensure_grid(isets[in_id], batch_size, arena, scan_ws, scan_ws_bytes, stream));
+
+    int out_id, n_out;
+    const int* pair = nullptr;
+    if (L.subm) {
+      IndexSetX& s = isets[in_id];
+      std::vector<int> key(L.ksize, L.ksize + 3);
+      key.insert(key.end(), L.dilation, L.dilation + 3);
+      auto it = s.subm.find(key);
+      if (it == s.subm.end()) {
+        MSMD_ARENA(p, int, (size_t)kvol * (size_t)s.n);
+        MSMD_TRY(msmd_rulebook_subm(s.indices, s.n, batch_size, s.shape, L.ksize, L.dilation, s.bits,
+                                    s.prefix, s.perm, p, (msmd_stream_t)stream));
+        s.subm[key] = p;
+        pair = p;
+      } else {
+        pair = it->second;
+      }
+      out_id = in_id;
+      n_out = s.n;
+    } else {
+      const IndexSetX s = isets[in_id];  // copy: isets may reallocate below
+      IndexSetX o;
+      MSMD_TRY(msmd_conv_out_shape(s.shape, L.ksize, L.stride, L.padding, L.dilation, o.shape));
+      const size_t words = msmd_grid_num_words(batch_size, o.shape);
+      MSMD_ARENA(obits, uint32_t, words);
+      MSMD_ARENA(oprefix, int, words);
+      MSMD_ARENA(count, int, 1);
+      MSMD_TRY(msmd_rulebook_conv_outputs(s.indices, s.n, batch_size, s.shape, L.ksize, L.stride,
+                                          L.padding, L.dilation, obits, oprefix, count, scan_ws,
+                                          scan_ws_bytes, (msmd_stream_t)stream));
+      // the one unavoidable read-back: N_out sizes the output rows and the pair table
+      int h_count = 0;
+      MSMD_CUDA_OK(cudaMemcpyAsync(&h_count, count, sizeof(int), cudaMemcpyDeviceToHost, stream));
+      MSMD_CUDA_OK(cudaStreamSynchronize(stream));
+      n_out = h_count;
+      MSMD_ARENA(oidx, int, (size_t)4 * (size_t)n_out);
+      MSMD_ARENA(p, int, (size_t)kvol * (size_t)n_out);
+      MSMD_TRY(msmd_rulebook_conv_pairs(obits, oprefix, n_out, batch_size, s.shape, L.ksize, L.stride,
+                                        L.padding, L.dilation, s.bits, s.prefix, s.perm, oidx, p,
+                                        (msmd_stream_t)stream));
+      o.indices = oidx; o.n = n_out; o.bits = obits; o.prefix = oprefix; o.perm = nullptr;
+      o.has_grid = true; o.ordered = true;
+      isets.push_back(o);
+      out_id = (int)isets.size() - 1;
+      pair = p;
+    }
+
+    MSMD_ARENA(out, float, (size_t)n_out * (size_t)L.cout);
+    const float* residual = nullptr;
+    if (L.residual >= 0) {
+      MSMD_REQUIRE(acts[L.residual].n == n_out && acts[L.residual].channels == L.cout,
+                   "sparse_net_forward: layer %d residual shape mismatch", li);
+      residual = acts[L.residual].features;
+    }
+    if (L.weight_tc)
+      MSMD_TRY(msmd_spconv_fwd_tc(in.features, in.n, L.weight, pair, n_out, L.cin, L.cout, kvol, L.scale,
+                                  L.shift, residual, L.relu, out, (msmd_stream_t)stream));
+    else
+      MSMD_TRY(msmd_spconv_fwd(in.features, in.n, L.weight, pair, n_out, L.cin, L.cout, kvol, L.scale,
+                               L.shift, residual, L.relu, out, (msmd_stream_t)stream));
+    msmd_sparse_desc& A = acts[li + 1];
+    A.features = out; A.indices = isets[out_id].indices; A.n = n_out; A.channels = L.cout;
+    for (int d = 0; d < 3; ++d) A.spatial_shape[d] = isets[out_id].shape[d];
+    act_iset[li + 1] = out_id;
+  }
+  return MSMD_OK;
+}

@@ -139,7 +139,7 @@ def rulebook_subm(indices, grid, ksize, dilation=1):
 
 
 def conv_out_shape(spatial_shape, ksize, stride, padding, dilation):
-    out = ints([0, 0, 0])
+    out = (_cabi.ctypes.c_int * 3)()  # output buffer: never the cached constant arrays of ints()
     check(lib().msmd_conv_out_shape(ints(_triple(spatial_shape)), ints(_triple(ksize)),
                                     ints(_triple(stride)), ints(_triple(padding)),
                                     ints(_triple(dilation)), out), 'msmd_conv_out_shape')

@@ -2,7 +2,9 @@
 (same constructor kwargs, sub-module names and return value)."""
 from torch import nn
 
-from . import spconv
+import torch
+
+from . import executor, ops, spconv
 from .registry import MIDDLE_ENCODERS
 from .sparse_block import SparseBasicBlock, make_sparse_convmodule
 
@@ -46,9 +48,45 @@ class SparseEncoder(nn.Module):
                                                norm_cfg=norm_cfg, padding=0,
                                                indice_key='spconv_down2', conv_type='SparseConv3d')
 
+    # ``use_executor``: run the whole chain through the native executor (csrc/executor.cu) -- one
+    # C-ABI call instead of ~55 -- whenever the module tree is in the fused-inference form
+    # (CUDA, no grad, eval-mode BatchNorm).  The module-by-module path below is the general one.
+    use_executor = True
+
+    def _plan_for(self):
+        mods = [self.conv_input, self.encoder_layers, self.conv_out]
+        key = executor.plan_key(mods)
+        cached = getattr(self, '_plan', None)
+        if cached is not None and cached[0] == key:
+            return cached[1], cached[2]
+        plan = executor.SparseNetPlan()
+        cur = plan.add(self.conv_input, 0)
+        marks = [cur]
+        for encoder_layer in self.encoder_layers:
+            cur = plan.add(encoder_layer, cur)
+            marks.append(cur)
+        marks.append(plan.add(self.conv_out, cur))
+        plan.finalize()
+        self._plan = (key, plan, marks)
+        return plan, marks
+
     def forward(self, voxel_features, coors, batch_size):
         """sparse_encoder.py:96-133 -> (spatial_features (B, C*D, H, W), encode_features)."""
         coors = coors.int()
+        if self.use_executor and voxel_features.is_cuda and not torch.is_grad_enabled():
+            try:
+                plan, marks = self._plan_for()
+            except executor.Unsupported:
+                plan = None
+            if plan is not None:
+                B = int(batch_size)
+                acts = plan.run(voxel_features, coors, self.sparse_shape, B)
+                encode_features = [spconv.SparseConvTensor(acts[i][0], acts[i][1], acts[i][2], B)
+                                   for i in marks[:-1]]
+                f, idx, shape = acts[marks[-1]]
+                spatial_features = ops.to_dense(idx, f, shape, B)
+                N, C, D, H, W = spatial_features.shape
+                return spatial_features.view(N, C * D, H, W), encode_features
         x = spconv.SparseConvTensor(voxel_features, coors, self.sparse_shape, batch_size)
         x = self.conv_input(x)
         encode_features = [x]

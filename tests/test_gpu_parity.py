@@ -674,3 +674,32 @@ def test_compact_unflagged_matches_numpy():
         want = np.nonzero(flags == 0)[0]
         got = ops.compact_unflagged(cuda(flags), want.shape[0]).cpu().numpy()
         assert got.dtype == np.int64 and np.array_equal(got, want)
+
+
+def test_native_executor_equals_module_path():
+    """csrc/executor.cu runs the same kernels on the same operands as the module-by-module path:
+    indices and features must be IDENTICAL, for one and two samples."""
+    cfg = m.Config.fromfile(os.path.join(ROOT, 'configs', 'msmd_lc_hotpath.py')).hotpath
+    torch.manual_seed(0)
+    enc = registry.build_middle_encoder(cfg.pts_middle_encoder).to(dev())
+    randomize_bn(enc, 5)
+    enc.eval()
+    layer = m.Voxelization(**cfg.pts_voxel_layer).eval()
+    for batch in (1, 2):
+        feats, coors = [], []
+        for b in range(batch):
+            mean, c4, _ = layer.forward_mean(cuda(synthetic.lidar_scene(40 + b, 1)), 5, batch_idx=b)
+            feats.append(mean)
+            coors.append(c4)
+        f, c = torch.cat(feats), torch.cat(coors)
+        with torch.no_grad():
+            enc.use_executor = True
+            sp1, ef1 = enc(f, c, batch)
+            enc.use_executor = False
+            sp2, ef2 = enc(f, c, batch)
+        assert getattr(enc, '_plan', None) is not None, 'the executor path did not run'
+        assert torch.equal(sp1, sp2)
+        for a, b in zip(ef1, ef2):
+            assert a.spatial_shape == b.spatial_shape
+            assert torch.equal(a.indices, b.indices) and torch.equal(a.features, b.features)
+    del enc.use_executor
