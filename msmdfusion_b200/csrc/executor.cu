@@ -9,12 +9,23 @@
 // from a caller-provided arena (the library still never allocates), and only the N_out of the
 // strided convolutions is read back (the output tensors cannot be sized without it).
 // Results are bit-identical to the module path -- the same kernels run on the same operands.
+//
+// Two streams: rulebooks depend on coordinates only, so the geometry chain (bit grids, rulebooks,
+// the N_out read-backs) runs on a library-owned auxiliary stream while the feature convolutions
+// run on the caller's stream, joined by events.  The host blocks only on the geometry stream --
+// a few tiny kernels -- while the convolutions of the previous resolution level keep the GPU busy,
+// so the read-backs no longer drain the pipeline.  (One process per GPU, single host thread.)
 #include <map>
 #include <vector>
 
 #include "common.cuh"
 
 namespace msmd {
+
+struct RulebookX {
+  int* pair = nullptr;
+  cudaEvent_t ready = nullptr;  // recorded on the geometry stream after the rulebook kernels
+};
 
 struct IndexSetX {
   int* indices = nullptr;
@@ -25,7 +36,7 @@ struct IndexSetX {
   int* perm = nullptr;
   bool has_grid = false;
   bool ordered = false;  // rows already in ascending linear order (output of a strided conv)
-  std::map<std::vector<int>, int*> subm;  // (ksize, dilation) -> pair_fwd
+  std::map<std::vector<int>, RulebookX> subm;  // (ksize, dilation) -> pair_fwd
 };
 
 struct Arena {
@@ -40,6 +51,35 @@ struct Arena {
     return (T*)(base + off);
   }
 };
+
+// library-owned auxiliary stream + event pool (per device, created on first use)
+struct AuxStreams {
+  cudaStream_t geom = nullptr;
+  std::vector<cudaEvent_t> events;
+  size_t next = 0;
+};
+static AuxStreams g_aux[16];
+
+static int aux_for_current_device(AuxStreams** out) {
+  int dev = 0;
+  MSMD_CUDA_OK(cudaGetDevice(&dev));
+  MSMD_REQUIRE(dev >= 0 && dev < 16, "sparse_net_forward: device ordinal %d unsupported", dev);
+  AuxStreams& a = g_aux[dev];
+  if (!a.geom) MSMD_CUDA_OK(cudaStreamCreateWithFlags(&a.geom, cudaStreamNonBlocking));
+  a.next = 0;
+  *out = &a;
+  return MSMD_OK;
+}
+
+static int next_event(AuxStreams& a, cudaEvent_t* ev) {
+  if (a.next == a.events.size()) {
+    cudaEvent_t e;
+    MSMD_CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    a.events.push_back(e);
+  }
+  *ev = a.events[a.next++];
+  return MSMD_OK;
+}
 
 }  // namespace msmd
 
@@ -89,6 +129,16 @@ extern "C" MSMD_API int msmd_sparse_net_forward(const msmd_conv_layer* layers, i
   const size_t scan_ws_bytes = msmd_scan_workspace();
   MSMD_ARENA(scan_ws, char, scan_ws_bytes);
 
+  AuxStreams* aux = nullptr;
+  MSMD_TRY(aux_for_current_device(&aux));
+  cudaStream_t geom = aux->geom;
+  {  // the geometry stream starts after everything already queued on the caller's stream
+    cudaEvent_t ev_in;
+    MSMD_TRY(next_event(*aux, &ev_in));
+    MSMD_CUDA_OK(cudaEventRecord(ev_in, stream));
+    MSMD_CUDA_OK(cudaStreamWaitEvent(geom, ev_in, 0));
+  }
+
   std::vector<IndexSetX> isets;
   isets.reserve(n_layers + 1);
   std::vector<int> act_iset(n_layers + 1, -1);
@@ -103,80 +153,98 @@ extern "C" MSMD_API int msmd_sparse_net_forward(const msmd_conv_layer* layers, i
     for (int d = 0; d < 3; ++d) acts[0].spatial_shape[d] = spatial_shape[d];
   }
 
-  for (int li = 0; li < n_layers; ++li) {
-    const msmd_conv_layer& L = layers[li];
-    MSMD_REQUIRE(L.input >= 0 && L.input <= li, "sparse_net_forward: layer %d reads activation %d", li, L.input);
-    MSMD_REQUIRE(L.residual < 0 || L.residual <= li, "sparse_net_forward: layer %d bad residual", li);
-    const msmd_sparse_desc in = acts[L.input];
-    MSMD_REQUIRE(in.channels == L.cin, "sparse_net_forward: layer %d expects %d channels, got %d", li, L.cin,
-                 in.channels);
-    const int kvol = L.ksize[0] * L.ksize[1] * L.ksize[2];
-    const int in_id = act_iset[L.input];
-    MSMD_TRY(ensure_grid(isets[in_id], batch_size, arena, scan_ws, scan_ws_bytes, stream));
+  int rc = MSMD_OK;
+  for (int li = 0; li < n_layers && rc == MSMD_OK; ++li) {
+    rc = [&]() -> int {
+      const msmd_conv_layer& L = layers[li];
+      MSMD_REQUIRE(L.input >= 0 && L.input <= li, "sparse_net_forward: layer %d reads activation %d", li,
+                   L.input);
+      MSMD_REQUIRE(L.residual < 0 || L.residual <= li, "sparse_net_forward: layer %d bad residual", li);
+      const msmd_sparse_desc in = acts[L.input];
+      MSMD_REQUIRE(in.channels == L.cin, "sparse_net_forward: layer %d expects %d channels, got %d", li,
+                   L.cin, in.channels);
+      const int kvol = L.ksize[0] * L.ksize[1] * L.ksize[2];
+      const int in_id = act_iset[L.input];
+      MSMD_TRY(ensure_grid(isets[in_id], batch_size, arena, scan_ws, scan_ws_bytes, geom));
 
-    int out_id, n_out;
-    const int* pair = nullptr;
-    if (L.subm) {
-      IndexSetX& s = isets[in_id];
-      std::vector<int> key(L.ksize, L.ksize + 3);
-      key.insert(key.end(), L.dilation, L.dilation + 3);
-      auto it = s.subm.find(key);
-      if (it == s.subm.end()) {
-        MSMD_ARENA(p, int, (size_t)kvol * (size_t)s.n);
-        MSMD_TRY(msmd_rulebook_subm(s.indices, s.n, batch_size, s.shape, L.ksize, L.dilation, s.bits,
-                                    s.prefix, s.perm, p, (msmd_stream_t)stream));
-        s.subm[key] = p;
-        pair = p;
+      int out_id, n_out;
+      RulebookX rb;
+      if (L.subm) {
+        IndexSetX& s = isets[in_id];
+        std::vector<int> key(L.ksize, L.ksize + 3);
+        key.insert(key.end(), L.dilation, L.dilation + 3);
+        auto it = s.subm.find(key);
+        if (it == s.subm.end()) {
+          MSMD_ARENA(p, int, (size_t)kvol * (size_t)s.n);
+          MSMD_TRY(msmd_rulebook_subm(s.indices, s.n, batch_size, s.shape, L.ksize, L.dilation, s.bits,
+                                      s.prefix, s.perm, p, (msmd_stream_t)geom));
+          rb.pair = p;
+          MSMD_TRY(next_event(*aux, &rb.ready));
+          MSMD_CUDA_OK(cudaEventRecord(rb.ready, geom));
+          s.subm[key] = rb;
+        } else {
+          rb = it->second;
+        }
+        out_id = in_id;
+        n_out = s.n;
       } else {
-        pair = it->second;
+        const IndexSetX s = isets[in_id];  // copy: isets may reallocate below
+        IndexSetX o;
+        MSMD_TRY(msmd_conv_out_shape(s.shape, L.ksize, L.stride, L.padding, L.dilation, o.shape));
+        const size_t words = msmd_grid_num_words(batch_size, o.shape);
+        MSMD_ARENA(obits, uint32_t, words);
+        MSMD_ARENA(oprefix, int, words);
+        MSMD_ARENA(count, int, 1);
+        MSMD_TRY(msmd_rulebook_conv_outputs(s.indices, s.n, batch_size, s.shape, L.ksize, L.stride,
+                                            L.padding, L.dilation, obits, oprefix, count, scan_ws,
+                                            scan_ws_bytes, (msmd_stream_t)geom));
+        // the one unavoidable read-back: N_out sizes the output rows and the pair table.  Only the
+        // geometry stream is drained; the convolutions queued on the caller's stream keep running.
+        int h_count = 0;
+        MSMD_CUDA_OK(cudaMemcpyAsync(&h_count, count, sizeof(int), cudaMemcpyDeviceToHost, geom));
+        MSMD_CUDA_OK(cudaStreamSynchronize(geom));
+        n_out = h_count;
+        MSMD_ARENA(oidx, int, (size_t)4 * (size_t)n_out);
+        MSMD_ARENA(p, int, (size_t)kvol * (size_t)n_out);
+        MSMD_TRY(msmd_rulebook_conv_pairs(obits, oprefix, n_out, batch_size, s.shape, L.ksize, L.stride,
+                                          L.padding, L.dilation, s.bits, s.prefix, s.perm, oidx, p,
+                                          (msmd_stream_t)geom));
+        rb.pair = p;
+        MSMD_TRY(next_event(*aux, &rb.ready));
+        MSMD_CUDA_OK(cudaEventRecord(rb.ready, geom));
+        o.indices = oidx; o.n = n_out; o.bits = obits; o.prefix = oprefix; o.perm = nullptr;
+        o.has_grid = true; o.ordered = true;
+        isets.push_back(o);
+        out_id = (int)isets.size() - 1;
       }
-      out_id = in_id;
-      n_out = s.n;
-    } else {
-      const IndexSetX s = isets[in_id];  // copy: isets may reallocate below
-      IndexSetX o;
-      MSMD_TRY(msmd_conv_out_shape(s.shape, L.ksize, L.stride, L.padding, L.dilation, o.shape));
-      const size_t words = msmd_grid_num_words(batch_size, o.shape);
-      MSMD_ARENA(obits, uint32_t, words);
-      MSMD_ARENA(oprefix, int, words);
-      MSMD_ARENA(count, int, 1);
-      MSMD_TRY(msmd_rulebook_conv_outputs(s.indices, s.n, batch_size, s.shape, L.ksize, L.stride,
-                                          L.padding, L.dilation, obits, oprefix, count, scan_ws,
-                                          scan_ws_bytes, (msmd_stream_t)stream));
-      // the one unavoidable read-back: N_out sizes the output rows and the pair table
-      int h_count = 0;
-      MSMD_CUDA_OK(cudaMemcpyAsync(&h_count, count, sizeof(int), cudaMemcpyDeviceToHost, stream));
-      MSMD_CUDA_OK(cudaStreamSynchronize(stream));
-      n_out = h_count;
-      MSMD_ARENA(oidx, int, (size_t)4 * (size_t)n_out);
-      MSMD_ARENA(p, int, (size_t)kvol * (size_t)n_out);
-      MSMD_TRY(msmd_rulebook_conv_pairs(obits, oprefix, n_out, batch_size, s.shape, L.ksize, L.stride,
-                                        L.padding, L.dilation, s.bits, s.prefix, s.perm, oidx, p,
-                                        (msmd_stream_t)stream));
-      o.indices = oidx; o.n = n_out; o.bits = obits; o.prefix = oprefix; o.perm = nullptr;
-      o.has_grid = true; o.ordered = true;
-      isets.push_back(o);
-      out_id = (int)isets.size() - 1;
-      pair = p;
-    }
 
-    MSMD_ARENA(out, float, (size_t)n_out * (size_t)L.cout);
-    const float* residual = nullptr;
-    if (L.residual >= 0) {
-      MSMD_REQUIRE(acts[L.residual].n == n_out && acts[L.residual].channels == L.cout,
-                   "sparse_net_forward: layer %d residual shape mismatch", li);
-      residual = acts[L.residual].features;
-    }
-    if (L.weight_tc)
-      MSMD_TRY(msmd_spconv_fwd_tc(in.features, in.n, L.weight, pair, n_out, L.cin, L.cout, kvol, L.scale,
-                                  L.shift, residual, L.relu, out, (msmd_stream_t)stream));
-    else
-      MSMD_TRY(msmd_spconv_fwd(in.features, in.n, L.weight, pair, n_out, L.cin, L.cout, kvol, L.scale,
-                               L.shift, residual, L.relu, out, (msmd_stream_t)stream));
-    msmd_sparse_desc& A = acts[li + 1];
-    A.features = out; A.indices = isets[out_id].indices; A.n = n_out; A.channels = L.cout;
-    for (int d = 0; d < 3; ++d) A.spatial_shape[d] = isets[out_id].shape[d];
-    act_iset[li + 1] = out_id;
+      MSMD_ARENA(out, float, (size_t)n_out * (size_t)L.cout);
+      const float* residual = nullptr;
+      if (L.residual >= 0) {
+        MSMD_REQUIRE(acts[L.residual].n == n_out && acts[L.residual].channels == L.cout,
+                     "sparse_net_forward: layer %d residual shape mismatch", li);
+        residual = acts[L.residual].features;
+      }
+      MSMD_CUDA_OK(cudaStreamWaitEvent(stream, rb.ready, 0));  // rulebook (and its indices) ready
+      if (L.weight_tc)
+        MSMD_TRY(msmd_spconv_fwd_tc(in.features, in.n, L.weight, rb.pair, n_out, L.cin, L.cout, kvol,
+                                    L.scale, L.shift, residual, L.relu, out, (msmd_stream_t)stream));
+      else
+        MSMD_TRY(msmd_spconv_fwd(in.features, in.n, L.weight, rb.pair, n_out, L.cin, L.cout, kvol, L.scale,
+                                 L.shift, residual, L.relu, out, (msmd_stream_t)stream));
+      msmd_sparse_desc& A = acts[li + 1];
+      A.features = out; A.indices = isets[out_id].indices; A.n = n_out; A.channels = L.cout;
+      for (int d = 0; d < 3; ++d) A.spatial_shape[d] = isets[out_id].shape[d];
+      act_iset[li + 1] = out_id;
+      return MSMD_OK;
+    }();
   }
-  return MSMD_OK;
+  // join: whatever the geometry stream still has queued (or an early error exit left behind) is
+  // ordered before anything the caller enqueues next on its stream
+  cudaEvent_t ev_out;
+  if (next_event(*aux, &ev_out) == MSMD_OK) {
+    cudaEventRecord(ev_out, geom);
+    cudaStreamWaitEvent(stream, ev_out, 0);
+  }
+  return rc;
 }
