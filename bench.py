@@ -199,7 +199,9 @@ def run_ours(args, rank, world, device):
             torch.cuda.synchronize(device)
 
     for _ in range(max(args.warmup, 3)):
-        step(pts_dev)
+        # results are kept across iterations exactly as in the timed loops, so the caching
+        # allocator reaches its steady state (two live result arenas) during warm-up
+        spatial, feats = step(pts_dev)
     sync_all()
     # serving-loop hygiene: move everything allocated so far out of the cyclic GC's reach so a
     # generation-2 collection cannot stall a timed step (the model graph is static from here on)
