@@ -118,8 +118,23 @@ def ptr(t):
     return ctypes.c_void_p(t.data_ptr())
 
 
+def _dev_index(device):
+    if device is None:
+        return torch.cuda.current_device()
+    if isinstance(device, int):
+        return device
+    idx = torch.device(device).index
+    return torch.cuda.current_device() if idx is None else idx
+
+
+def raw_stream(device=None):
+    """cudaStream_t of torch's current stream as an int (the private raw getter is ~10x cheaper than
+    building a torch.cuda.Stream object; it is called once per C-ABI call)."""
+    return torch._C._cuda_getCurrentRawStream(_dev_index(device))
+
+
 def stream(device=None):
-    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+    return ctypes.c_void_p(raw_stream(device))
 
 
 _INTS, _FLOATS = {}, {}
@@ -151,7 +166,7 @@ class _Scratch:
     def get(self, device, nbytes, slot='ws'):
         # one buffer per (device, stream): reuse is stream-ordered, and concurrent streams (the
         # overlapped NN-assignment chains of the GMA encoder) never share scratch memory
-        key = (torch.device(device).index, slot, torch.cuda.current_stream(device).cuda_stream)
+        key = (_dev_index(device), slot, raw_stream(device))
         b = self.buf.get(key)
         if b is None or b.numel() < nbytes:
             b = torch.empty(max(int(nbytes), 1 << 16), dtype=torch.uint8, device=device)

@@ -250,6 +250,22 @@ class MSMDFusionDetector(nn.Module, _VoxelPathMixin):
         self._packed = (img_metas, val)
         return val
 
+    def _score_bias(self):
+        """score_net bias as a host float, read back once per parameter version (not per call)."""
+        b = self.score_net[0].bias
+        if b is None:
+            return 0.0
+        key = (b.data_ptr(), b._version)
+        if getattr(self, '_bias_cache', (None, 0.0))[0] != key:
+            self._bias_cache = (key, float(b.detach().item()))
+        return self._bias_cache[1]
+
+    def _xyz_normalizer(self, device):
+        t = getattr(self, '_xyz_norm', None)
+        if t is None or t.device != device:
+            t = self._xyz_norm = torch.tensor([13.5, 13.5, 2.0], device=device)  # :388
+        return t
+
     # -- :169-238 ---------------------------------------------------------------------------
     def get_foreground2D(self, img_feats, img_metas):
         """Per sample: (M_b, 15 + C) = [virtual point | gated C-channel pixel feature]."""
@@ -259,8 +275,7 @@ class MSMDFusionDetector(nn.Module, _VoxelPathMixin):
         pk = self.packed_foreground(img_metas, img_feats.device)
         lin = self.score_net[0]
         out = ops.lift_gather(img_feats.float(), pk.pixels, pk.cam, pk.points, pk.lidar2img,
-                              downscale_factor, lin.weight, float(lin.bias.detach().item())
-                              if lin.bias is not None else 0.0)
+                              downscale_factor, lin.weight, self._score_bias())
         return list(torch.split(out, pk.counts, dim=0)) if B > 1 else [out]
 
     # -- :335-369 ---------------------------------------------------------------------------
@@ -298,7 +313,7 @@ class MSMDFusionDetector(nn.Module, _VoxelPathMixin):
         feat_dim = batch_fg[0].shape[-1]
         self.pts_voxel_encoder.num_features = feat_dim  # never restored in the reference (:386)
         fg_voxel_features, fg_coors, _ = self.voxelize_mean(batch_fg, feat_dim, downscale_factor)
-        xyz_normalizer = torch.tensor([13.5, 13.5, 2.0], device=fg_voxel_features.device)
+        xyz_normalizer = self._xyz_normalizer(fg_voxel_features.device)
         fg_voxel_features[:, :3] = fg_voxel_features[:, :3] / xyz_normalizer[None, :]
         return spconv.SparseConvTensor(fg_voxel_features, fg_coors, voxel_size, B)
 

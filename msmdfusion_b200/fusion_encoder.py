@@ -121,6 +121,20 @@ class SparseMultiModalEncoderPaint(nn.Module):
                 features = torch.cat([features, padded_features], dim=0)
         return indices, features
 
+    def _dummy_embedding(self, stage_id, channels, device):
+        """``torch.rand(1, C3).to(device)`` (:372): same draw from the CPU generator, but staged in
+        a pinned per-stage buffer and copied asynchronously (a pageable copy blocks the host until
+        the stream drains -- four extra synchronisations per scene)."""
+        val = torch.rand(1, channels)
+        if device.type != 'cuda':
+            return val.to(device)
+        bufs = self.__dict__.setdefault('_dummy_pinned', {})
+        buf = bufs.get((stage_id, channels))
+        if buf is None:
+            buf = bufs[(stage_id, channels)] = torch.empty((1, channels)).pin_memory()
+        buf.copy_(val)
+        return buf.to(device, non_blocking=True)
+
     def fps_NN_fast(self, query, key, fps_num, radius, max_cluster_samples, dist_thresh):
         return fps_nn_fast(query, key, fps_num, radius, max_cluster_samples, dist_thresh)
 
@@ -166,7 +180,7 @@ class SparseMultiModalEncoderPaint(nn.Module):
 
         # cross gate: only-2D features scaled by the gate of their nearest 3-D voxel; unassigned
         # voxels (-1) pick the last row = gate of a random dummy embedding (:371-377)
-        dummy_embedding = torch.rand(1, feat3.shape[1]).to(feat3.device)
+        dummy_embedding = self._dummy_embedding(stage_id, feat3.shape[1], feat3.device)
         cross_gating = self.cross_gate_control[stage_id](torch.cat([feat3, dummy_embedding], dim=0))
         voxel_only_2D_features = cross_gating[nn_idx] * voxel_only_2D_features
 
@@ -234,7 +248,7 @@ class SparseMultiModalEncoderPaint(nn.Module):
         else:
             only2_feat = torch.zeros((1, feat2.shape[1]), dtype=feat2.dtype, device=dev)
 
-        dummy_embedding = torch.rand(1, feat3.shape[1]).to(dev)
+        dummy_embedding = self._dummy_embedding(stage_id, feat3.shape[1], dev)
         cross_gating = self.cross_gate_control[stage_id](torch.cat([feat3, dummy_embedding], dim=0))
         only2_feat = cross_gating[nn_idx] * only2_feat
 
