@@ -361,6 +361,10 @@ def cpu_pass(profile, seed=0):
 
 def main():
     args = parse()
+    # torchrun exports OMP_NUM_THREADS=1; the CPU arms (reference / cpu_baseline) are specified to use
+    # all the host threads they can, so undo that before the oracle's OpenMP runtime is loaded
+    if os.environ.get('OMP_NUM_THREADS', '') in ('', '1'):
+        os.environ['OMP_NUM_THREADS'] = str(os.cpu_count() or 1)
     rank = int(os.environ.get('RANK', 0))
     local_rank = int(os.environ.get('LOCAL_RANK', 0))
     world = int(os.environ.get('WORLD_SIZE', 1))

@@ -148,6 +148,16 @@ MSMD_API int msmd_spconv_fwd_tc(const float* features, int n_in, const float* pa
                                 const int* pair_fwd, int n_out, int cin, int cout, int kvol,
                                 const float* scale, const float* shift, const float* residual,
                                 int relu, float* out, msmd_stream_t stream);
+/* Same, with scratch for split-K pairs: when the tile count leaves SMs idle (<= 74 tiles) or is
+ * just over one wave (149..222 tiles), two CTAs share an output tile, each takes half of the K
+ * chunks, and the first to finish hands its partial sums to the second through `workspace`
+ * (deterministic: a + b).  msmd_spconv_tc_workspace() returns the bytes needed, 0 = no split. */
+MSMD_API size_t msmd_spconv_tc_workspace(int n_out, int cout);
+MSMD_API int msmd_spconv_fwd_tc_ws(const float* features, int n_in, const float* packed_tc,
+                                   const int* pair_fwd, int n_out, int cin, int cout, int kvol,
+                                   const float* scale, const float* shift, const float* residual,
+                                   int relu, float* out, void* workspace, size_t workspace_bytes,
+                                   msmd_stream_t stream);
 
 /* ------------------------------------------------------------------------------------
  * Native executor for a chain of sparse convolutions -- the host loop of

@@ -226,9 +226,17 @@ extern "C" MSMD_API int msmd_sparse_net_forward(const msmd_conv_layer* layers, i
         residual = acts[L.residual].features;
       }
       MSMD_CUDA_OK(cudaStreamWaitEvent(stream, rb.ready, 0));  // rulebook (and its indices) ready
-      if (L.weight_tc)
-        MSMD_TRY(msmd_spconv_fwd_tc(in.features, in.n, L.weight, rb.pair, n_out, L.cin, L.cout, kvol,
-                                    L.scale, L.shift, residual, L.relu, out, (msmd_stream_t)stream));
+      if (L.weight_tc) {
+        const size_t ws_bytes = msmd_spconv_tc_workspace(n_out, L.cout);  // split-K hand-off buffer
+        char* ws = nullptr;
+        if (ws_bytes) {
+          MSMD_ARENA(w, char, ws_bytes);
+          ws = w;
+        }
+        MSMD_TRY(msmd_spconv_fwd_tc_ws(in.features, in.n, L.weight, rb.pair, n_out, L.cin, L.cout, kvol,
+                                       L.scale, L.shift, residual, L.relu, out, ws, ws_bytes,
+                                       (msmd_stream_t)stream));
+      }
       else
         MSMD_TRY(msmd_spconv_fwd(in.features, in.n, L.weight, rb.pair, n_out, L.cin, L.cout, kvol, L.scale,
                                  L.shift, residual, L.relu, out, (msmd_stream_t)stream));

@@ -95,7 +95,8 @@ __device__ __forceinline__ void tc_epilogue(int any_active, uint64_t* accum_bar,
                                             int warp, int lane, int row0, int n_out, int cout, int N,
                                             const float* ss /* smem: scale[N] | shift[N] */,
                                             const float* __restrict__ residual, int relu,
-                                            float* __restrict__ out) {
+                                            float* __restrict__ out, float* write_partial = nullptr,
+                                            const float* add_partial = nullptr) {
     if (any_active) {
       tc::mbar_wait(accum_bar, 0);
       tc::fence_after_sync();
@@ -116,6 +117,26 @@ __device__ __forceinline__ void tc_epilogue(int any_active, uint64_t* accum_bar,
       } else {
 #pragma unroll
         for (int e = 0; e < 16; ++e) acc[e] = 0u;
+      }
+      const int prow = quarter * 32 + lane;  // row inside the tile (split-K hand-off buffer [128][N])
+      if (write_partial) {  // first finisher of a split-K pair: raw partial sums, no epilogue
+        float4* dst = (float4*)(write_partial + (size_t)prow * N + c0);
+#pragma unroll
+        for (int e = 0; e < 16; e += 4)
+          __stcg(dst + (e >> 2), make_float4(__uint_as_float(acc[e]), __uint_as_float(acc[e + 1]),
+                                             __uint_as_float(acc[e + 2]), __uint_as_float(acc[e + 3])));
+        continue;
+      }
+      if (add_partial) {  // second finisher: add the partner's partial sums (L2, never L1)
+        const float4* src = (const float4*)(add_partial + (size_t)prow * N + c0);
+#pragma unroll
+        for (int e = 0; e < 16; e += 4) {
+          const float4 pv = __ldcg(src + (e >> 2));
+          acc[e] = __float_as_uint(__uint_as_float(acc[e]) + pv.x);
+          acc[e + 1] = __float_as_uint(__uint_as_float(acc[e + 1]) + pv.y);
+          acc[e + 2] = __float_as_uint(__uint_as_float(acc[e + 2]) + pv.z);
+          acc[e + 3] = __float_as_uint(__uint_as_float(acc[e + 3]) + pv.w);
+        }
       }
       if (o < n_out) {
         float* orow = out + (size_t)o * cout;
@@ -381,11 +402,12 @@ spconv_fwd_tc3_kernel(const float* __restrict__ feat, const float* __restrict__ 
                       int kvol, int chunks, int b_stages, int b_stage_bytes, int a_stages, int raw_off,
                       int pair_off, int act_off, int bar_off, int tmem_cols,
                       const float* __restrict__ scale, const float* __restrict__ shift,
-                      const float* __restrict__ residual, int relu, float* __restrict__ out) {
+                      const float* __restrict__ residual, int relu, float* __restrict__ out, int split,
+                      float* __restrict__ part_ws, int* __restrict__ part_flag) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   int* pair_s = (int*)(smem + pair_off);
-  unsigned short* alist = (unsigned short*)(smem + act_off);
+  const unsigned short* alist = (unsigned short*)(smem + act_off);
   uint64_t* b_full = (uint64_t*)(smem + bar_off);
   uint64_t* b_empty = b_full + 4;
   uint64_t* a_full = b_full + 8;
@@ -401,7 +423,10 @@ spconv_fwd_tc3_kernel(const float* __restrict__ feat, const float* __restrict__ 
   }
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int row0 = blockIdx.x * kTcM;
+  // split-K pairs (tail balance): CTA 2t and 2t+1 share output tile t and take half of its
+  // active K chunks each; the first to finish hands its partial sums to the second through L2
+  const int tile = (int)blockIdx.x / split, half = (int)blockIdx.x % split;
+  const int row0 = tile * kTcM;
 
   if (tid == 0) {
     for (int s = 0; s < 4; ++s) {
@@ -433,9 +458,14 @@ spconv_fwd_tc3_kernel(const float* __restrict__ feat, const float* __restrict__ 
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
-  if (warp == 0) tc_build_active_list(used_s, chunks, cin_pad, kvol, lane, alist, n_act_s);
+  if (warp == 0)
+    tc_build_active_list(used_s, chunks, cin_pad, kvol, lane, (unsigned short*)alist, n_act_s);
   __syncthreads();
-  const int n_act = *n_act_s;
+  int n_act = *n_act_s;
+  if (split == 2) {
+    const int mid = n_act / 2;
+    if (half) { alist += mid; n_act -= mid; } else { n_act = mid; }
+  }
   const int any_active = n_act > 0;
   const uint32_t tmem_base = *tmem_ptr_s;
   const uint32_t tmem_a0 = tmem_base + (uint32_t)N;  // A ring starts right after the accumulator
@@ -521,7 +551,35 @@ spconv_fwd_tc3_kernel(const float* __restrict__ feat, const float* __restrict__ 
       if (i + 3 < n_act) gather(alist[i + 3], bufb);
     }
 
-    tc_epilogue(any_active, accum_bar, tmem_base, warp, lane, row0, n_out, cout, N, ss, residual, relu, out);
+    if (split == 1) {
+      tc_epilogue(any_active, accum_bar, tmem_base, warp, lane, row0, n_out, cout, N, ss, residual, relu, out);
+    } else {
+      int* ticket_s = n_act_s;  // the active-chunk count is no longer needed: reuse its smem word
+      float* part = part_ws + (size_t)tile * kTcM * N;
+      tc::named_bar_sync(2, kTcProducers);  // every thread has read *n_act_s
+      if (tid == 0) *ticket_s = atomicAdd(&part_flag[2 * tile], 1);
+      tc::named_bar_sync(2, kTcProducers);
+      if (*ticket_s == 0) {
+        tc_epilogue(any_active, accum_bar, tmem_base, warp, lane, row0, n_out, cout, N, ss, residual, relu,
+                    out, part, nullptr);
+        __threadfence();
+        tc::named_bar_sync(2, kTcProducers);
+        if (tid == 0) atomicExch(&part_flag[2 * tile + 1], 1);  // partial sums are in L2
+      } else {
+        if (tid == 0) {
+          const long long t0 = clock64();
+          while (atomicAdd(&part_flag[2 * tile + 1], 0) == 0) {
+            if (clock64() - t0 > 4000000000LL) __trap();  // the partner is already in its epilogue
+          }
+        }
+        tc::named_bar_sync(2, kTcProducers);
+        __threadfence();
+        tc_epilogue(any_active, accum_bar, tmem_base, warp, lane, row0, n_out, cout, N, ss, residual, relu,
+                    out, nullptr, part);
+        tc::named_bar_sync(2, kTcProducers);
+        if (tid == 0) { part_flag[2 * tile] = 0; part_flag[2 * tile + 1] = 0; }  // ready for the next launch
+      }
+    }
   } else if (warp == kTcProducerWarps) {
     // ===== B loader ============================================================================
     if (lane == 0) {
@@ -644,10 +702,34 @@ extern "C" MSMD_API int msmd_spconv_tc_pack_weight(const float* weight_krsc, int
   return MSMD_OK;
 }
 
+// Split-K pairs pay off when the tile count leaves most SMs idle or one tile short of a wave:
+// makespan in tile-times is ceil(t/148) unsplit and ceil(2t/148)/2 split.
+static bool tc_use_split(int tiles, int N) {
+  if (N < 96) return false;  // variant 3 only
+  return tiles <= kNumSMs / 2 || (tiles > kNumSMs && tiles <= kNumSMs + kNumSMs / 2);
+}
+
+extern "C" MSMD_API size_t msmd_spconv_tc_workspace(int n_out, int cout) {
+  const int N = round_up(cout > 0 ? cout : 1, 16);
+  const int tiles = ceil_div(n_out > 0 ? n_out : 1, kTcM);
+  if (g_tc_variant == 2 || !tc_use_split(tiles, N)) return 0;
+  return (size_t)tiles * kTcM * N * sizeof(float) + (size_t)tiles * 2 * sizeof(int) + 512;
+}
+
 extern "C" MSMD_API int msmd_spconv_fwd_tc(const float* features, int n_in, const float* packed_tc,
                                            const int* pair_fwd, int n_out, int cin, int cout, int kvol,
                                            const float* scale, const float* shift,
                                            const float* residual, int relu, float* out,
+                                           msmd_stream_t stream_) {
+  return msmd_spconv_fwd_tc_ws(features, n_in, packed_tc, pair_fwd, n_out, cin, cout, kvol, scale, shift,
+                               residual, relu, out, nullptr, 0, stream_);
+}
+
+extern "C" MSMD_API int msmd_spconv_fwd_tc_ws(const float* features, int n_in, const float* packed_tc,
+                                           const int* pair_fwd, int n_out, int cin, int cout, int kvol,
+                                           const float* scale, const float* shift,
+                                           const float* residual, int relu, float* out,
+                                           void* workspace, size_t workspace_bytes,
                                            msmd_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   TcGeom g;
@@ -670,10 +752,20 @@ extern "C" MSMD_API int msmd_spconv_fwd_tc(const float* features, int n_in, cons
       MSMD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
       attr_set[2 + vec] = true;
     }
-    kern<<<tiles, kTcThreads, L.total, stream>>>(features, packed_tc, pair_fwd, n_out, cin, g.cin_pad, cout,
-                                                 g.N, kvol, g.chunks, L.b_stages, L.b_stage_bytes,
-                                                 L.a_stages, L.raw_off, L.pair_off, L.act_off, L.bar_off,
-                                                 L.tmem_cols, scale, shift, residual, relu, out);
+    int split = 1;
+    float* part_ws = nullptr;
+    int* part_flag = nullptr;
+    const size_t need = msmd_spconv_tc_workspace(n_out, cout);
+    if (workspace && need > 0 && workspace_bytes >= need) {
+      split = 2;
+      part_flag = (int*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+      part_ws = (float*)(part_flag + (size_t)2 * tiles + (64 - (2 * tiles) % 64) % 64);
+      MSMD_CUDA_OK(cudaMemsetAsync(part_flag, 0, (size_t)2 * tiles * sizeof(int), stream));
+    }
+    kern<<<tiles * split, kTcThreads, L.total, stream>>>(
+        features, packed_tc, pair_fwd, n_out, cin, g.cin_pad, cout, g.N, kvol, g.chunks, L.b_stages,
+        L.b_stage_bytes, L.a_stages, L.raw_off, L.pair_off, L.act_off, L.bar_off, L.tmem_cols, scale, shift,
+        residual, relu, out, split, part_ws, part_flag);
     MSMD_LAUNCH_OK();
     return MSMD_OK;
   }

@@ -245,10 +245,13 @@ def spconv_fwd_tc(features, tcw, pair_fwd, scale=None, shift=None, residual=None
     pair_fwd = pair_fwd.contiguous()
     with _Timed('spconv_fwd', n_in=features.shape[0], n_out=n_out, cin=tcw.cin, cout=tcw.cout,
                 kvol=tcw.kvol, residual=residual is not None, pair=pair_fwd, path='tc'):
-        check(lib().msmd_spconv_fwd_tc(ptr(features), features.shape[0], ptr(tcw.packed), ptr(pair_fwd),
-                                       n_out, tcw.cin, tcw.cout, tcw.kvol, ptr(scale), ptr(shift),
-                                       ptr(residual), int(bool(relu)), ptr(out),
-                                       stream(features.device)), 'msmd_spconv_fwd_tc')
+        need = lib().msmd_spconv_tc_workspace(n_out, tcw.cout)  # > 0: split-K pairs (tail balance)
+        ws = scratch.get(features.device, need, slot='tc_ws') if need else None
+        check(lib().msmd_spconv_fwd_tc_ws(ptr(features), features.shape[0], ptr(tcw.packed), ptr(pair_fwd),
+                                          n_out, tcw.cin, tcw.cout, tcw.kvol, ptr(scale), ptr(shift),
+                                          ptr(residual), int(bool(relu)), ptr(out), ptr(ws),
+                                          ws.numel() if ws is not None else 0,
+                                          stream(features.device)), 'msmd_spconv_fwd_tc_ws')
     return out
 
 

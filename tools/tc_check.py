@@ -65,6 +65,9 @@ def main():
         (16, 32, 20000, 6000, 27, 0.2, True),
         (20, 24, 3000, 777, 27, 0.3, True),     # cout not a multiple of 16, odd sizes
         (32, 32, 100, 1, 27, 0.5, False),
+        (128, 128, 30000, 21509, 27, 0.5, True),  # 169 tiles: split-K pairs
+        (192, 192, 9000, 6000, 27, 0.5, True),    # 47 tiles: split-K pairs
+        (128, 128, 9000, 130, 3, 0.7, True),      # 2 tiles, 12 chunks
     ]
     ok = True
     variants = [int(v) for v in os.environ.get('TC_VARIANTS', '3,2').split(',')]
