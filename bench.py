@@ -293,13 +293,13 @@ def run_ours(args, rank, world, device):
         hbm_time = b / (hbm * 1e9)
         tensor_time = (3.0 * f) / (tf32_peak * 1e12) if tc else 0.0  # 3 MMAs per product (3xTF32)
         traffic, traffic_src = None, None
-        tp = os.path.join(ROOT, 'profiles', 'r01d_ncu_full_spconv_tc_v4_profileS.json')
+        tp = os.path.join(ROOT, 'profiles', 'r01e_ncu_full_spconv_tc_profileS.json')
         if tc and args.workload == 'L' and args.profile == 'S' and os.path.exists(tp):
             t = json.load(open(tp))  # one committed `ncu --set full` capture of these 21 launches
             scale = {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}
-            traffic = t['sum_dram_read'] * scale[t['unit_bytes']] + t['sum_dram_write'] * 1e3
+            traffic = (t['sum_dram_read'] + t['sum_dram_write']) * scale[t['unit_bytes']]
             traffic_src = ('dram__bytes_read.sum + dram__bytes_write.sum summed over the 21 conv launches of '
-                           'one scene, profiles/r01d_ncu_full_spconv_tc_v4_profileS.json (writes stay in the '
+                           'one scene, profiles/r01e_ncu_full_spconv_tc_profileS.json (writes stay in the '
                            '126 MB L2 at this size)')
         common = {'traffic': traffic, 'traffic_source': traffic_src, 'peak_source': src,
                   'kernel': ('spconv_fwd_tc_kernel (tcgen05 kind::tf32, 3xTF32)' if tc else
