@@ -14,10 +14,13 @@ Parity pinning ("Oracle"):
   known-answer test.
 * FPS / ball query -- pinned against the inline vectors of
   ``tests/test_models/test_common_modules/test_pointnet_ops.py``.
-* sparse conv / sparse_add / modality split / GMA-conv -- the arithmetic lives in the
-  un-vendored spconv v2.1.21; no reference test pins results there ("parity unpinned" by
-  the reference).  The restatement is pinned against an independent dense
-  ``torch.nn.functional.conv3d`` oracle instead.
+* sparse conv arithmetic + rulebook geometry -- pinned against the reference's VENDORED spconv-1.x
+  (``mmdet3d/ops/spconv``), compiled unmodified by ``oracle/ref_spconv.py`` and run on the CPU
+  (live test + committed fixtures ``tests/golden/spconv1x_*.npz``), and independently against a
+  dense ``torch.nn.functional.conv3d`` oracle.
+* spconv-2.x-only conventions (ascending-linear-index row order of strided-conv outputs, ``sparse_add``
+  as a coalesced COO sum) / modality split / GMA-conv glue -- the un-vendored spconv v2.1.21 is not
+  available and no reference test pins results there: "parity unpinned" by the reference for these.
 """
 import ctypes
 import os

@@ -705,3 +705,29 @@ def test_native_executor_equals_module_path():
             assert a.spatial_shape == b.spatial_shape
             assert torch.equal(a.indices, b.indices) and torch.equal(a.features, b.features)
     del enc.use_executor
+
+
+@pytest.mark.parametrize('path', sorted(glob.glob(os.path.join(GOLDEN, 'spconv1x_*.npz'))), ids=os.path.basename)
+def test_cuda_conv_matches_reference_spconv1x_golden(path):
+    """The CUDA path (SubMConv3d / SparseConv3d modules -> C ABI) against fixtures produced by the
+    reference's own vendored spconv-1.x CPU ops (tests/golden/make_golden_spconv.py): output index
+    set bit-exact in spconv-2.x row order (ascending linear index), features within 1e-4."""
+    g = np.load(path)
+    idx = g['indices'].astype(np.int32)
+    shape = [int(s) for s in g['spatial_shape']]
+    ks, st, pd = [int(x) for x in g['ksize']], [int(x) for x in g['stride']], [int(x) for x in g['padding']]
+    w = g['weight_krsc']
+    cout, cin = w.shape[0], w.shape[-1]
+    cls = m.spconv.SubMConv3d if int(g['subm']) else m.spconv.SparseConv3d
+    for path_name in ('tc', 'simt'):
+        m.spconv.CONV_PATH = path_name
+        try:
+            conv = cls(cin, cout, ks, stride=st, padding=pd, bias=False).to(dev())
+            with torch.no_grad():
+                conv.weight.copy_(cuda(w))
+                y = conv(m.spconv.SparseConvTensor(cuda(g['features']), cuda(idx), shape, int(g['batch_size'])))
+        finally:
+            m.spconv.CONV_PATH = 'tc'
+        assert y.spatial_shape == [int(s) for s in g['out_shape']]
+        assert np.array_equal(y.indices.cpu().numpy(), g['out_indices'].astype(np.int32))
+        assert feat_err(y.features.cpu().numpy(), g['out_features']) < FEAT_TOL

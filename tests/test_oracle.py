@@ -245,3 +245,54 @@ def test_fusion_oracle_runs_end_to_end_small():
         assert np.all(np.diff(lin) > 0) and np.isfinite(o.features).all()
     canvas = omodel.depth_canvas(metas, H, W)
     assert canvas.shape == (6, 1, H, W) and (canvas > 0).sum() > 0
+
+
+# --------------------------------------------------------------------------------------
+# sparse conv / rulebook restatement pinned against the reference's VENDORED spconv-1.x
+# --------------------------------------------------------------------------------------
+def spconv1x_goldens():
+    return sorted(glob.glob(os.path.join(GOLDEN, 'spconv1x_*.npz')))
+
+
+def oracle_conv_on_golden(g):
+    idx = g['indices'].astype(np.int32)
+    shape = [int(s) for s in g['spatial_shape']]
+    ks, st, pd = [int(x) for x in g['ksize']], [int(x) for x in g['stride']], [int(x) for x in g['padding']]
+    if int(g['subm']):
+        pair, oi, oshape = cpu.subm_rulebook(idx, shape, ks, 1), idx, shape
+    else:
+        oi, pair, oshape = cpu.conv_rulebook(idx, shape, ks, st, pd, 1)
+    return oi, cpu.spconv_fwd(g['features'], g['weight_krsc'], pair), list(oshape)
+
+
+@pytest.mark.parametrize('path', spconv1x_goldens(), ids=os.path.basename)
+def test_oracle_conv_matches_reference_spconv1x_golden(path):
+    """Fixtures produced by the reference's own spconv-1.x CPU ops (tests/golden/make_golden_spconv.py):
+    output index set (ascending linear order) bit-exact, features to fp32 rounding."""
+    g = np.load(path)
+    oi, of, oshape = oracle_conv_on_golden(g)
+    assert oshape == [int(s) for s in g['out_shape']]
+    assert np.array_equal(oi, g['out_indices'].astype(np.int32))
+    assert np.abs(of - g['out_features']).max() < 1e-5
+
+
+@pytest.mark.skipif(not os.path.isdir('/root/reference/mmdet3d/ops/spconv/src'), reason='reference tree not mounted')
+def test_oracle_conv_matches_reference_spconv1x_live():
+    from oracle import ref_spconv
+    if ref_spconv.module() is None:
+        pytest.skip('reference spconv-1.x could not be built here')
+    rng = np.random.default_rng(21)
+    for (shape, batch, n, cin, cout, ks, st, pd, subm) in (
+            ([7, 18, 18], 2, 700, 8, 8, 3, 1, 1, True), ([7, 18, 18], 2, 700, 8, 16, 3, 2, 1, False),
+            ([9, 12, 12], 1, 400, 4, 4, [3, 1, 1], [2, 1, 1], 0, False)):
+        idx, feat = random_sparse(rng, batch, shape, n, cin)
+        k3 = ks if isinstance(ks, list) else [ks] * 3
+        w = rng.standard_normal((cout, *k3, cin)).astype(np.float32) * 0.2
+        oi, of, oshape = ref_spconv.conv(idx, feat, w, shape, batch, ks, st, pd, 1, subm)
+        if subm:
+            ei, pair = idx, cpu.subm_rulebook(idx, shape, ks, 1)
+        else:
+            ei, pair, es = cpu.conv_rulebook(idx, shape, ks, st, pd, 1)
+            assert list(es) == list(oshape)
+        assert np.array_equal(oi, ei)
+        assert np.abs(of - cpu.spconv_fwd(feat, w, pair)).max() < 1e-5
