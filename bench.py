@@ -31,7 +31,7 @@ UNIT = 'scenes/s'
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--steps', type=int, default=100)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--profile', default='S', choices=['S', 'L'],
@@ -82,7 +82,7 @@ class Clocks:
         try:
             self.proc = subprocess.Popen(
                 ['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q, '--format=csv,noheader,nounits',
-                 '-lms', '100'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 '-lms', '20'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except OSError:
@@ -92,7 +92,12 @@ class Clocks:
         for ln in self.proc.stdout:
             self.lines.append(ln.strip())
 
-    def stop(self):
+    def mark(self):
+        """Index of the next sample: brackets the timed region so that only samples taken DURING
+        it are summarised."""
+        return len(self.lines)
+
+    def stop(self, first=0, last=None):
         if self.proc is None:
             return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
         self.proc.terminate()
@@ -102,7 +107,8 @@ class Clocks:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        for ln in self.lines:
+        window = self.lines[first:last] if len(self.lines[first:last]) >= 2 else self.lines
+        for ln in window:
             f = [x.strip() for x in ln.split(',')]
             if len(f) < 6:
                 continue
@@ -198,6 +204,8 @@ def run_ours(args, rank, world, device):
             dist.barrier()
             torch.cuda.synchronize(device)
 
+    clocks = Clocks(torch.cuda.current_device())
+    clocks.start()  # nvidia-smi needs ~100 ms to produce its first sample: start it before warm-up
     for _ in range(max(args.warmup, 3)):
         # results are kept across iterations exactly as in the timed loops, so the caching
         # allocator reaches its steady state (two live result arenas) during warm-up
@@ -209,8 +217,7 @@ def run_ours(args, rank, world, device):
     gc.freeze()
 
     # ---- device-resident timing: K steps, L2 flushed between steps, CUDA events per step ----
-    clocks = Clocks(torch.cuda.current_device())
-    clocks.start()
+    mark0 = clocks.mark()
     launches0 = _cabi.lib().msmd_launch_count()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     sync_all()
@@ -240,7 +247,7 @@ def run_ours(args, rank, world, device):
         checksum = float(spatial.sum().item())  # device -> host read of the step result
         e.record()
     sync_all()
-    clk = clocks.stop()
+    clk = clocks.stop(mark0, clocks.mark())
     e2e_raw = [s.elapsed_time(e) for s, e in ev2]
     e2e_ms = sum(e2e_raw)
 
@@ -292,12 +299,13 @@ def run_ours(args, rank, world, device):
         tf32_peak = bf16 / 2.0  # tcgen05 kind::tf32 issues at half the bf16 rate
         hbm_time = b / (hbm * 1e9)
         tensor_time = (3.0 * f) / (tf32_peak * 1e12) if tc else 0.0  # 3 MMAs per product (3xTF32)
-        traffic, traffic_src = None, None
+        traffic, traffic_src, ncu_tensor_pct = None, None, None
         tp = os.path.join(ROOT, 'profiles', 'r01e_ncu_full_spconv_tc_profileS.json')
         if tc and args.workload == 'L' and args.profile == 'S' and os.path.exists(tp):
             t = json.load(open(tp))  # one committed `ncu --set full` capture of these 21 launches
             scale = {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}
             traffic = (t['sum_dram_read'] + t['sum_dram_write']) * scale[t['unit_bytes']]
+            ncu_tensor_pct = round(sum(l['tensor_active_pct'] * l['us'] for l in t['launches']) / t['sum_time'], 2)
             traffic_src = ('dram__bytes_read.sum + dram__bytes_write.sum summed over the 21 conv launches of '
                            'one scene, profiles/r01e_ncu_full_spconv_tc_profileS.json (writes stay in the '
                            '126 MB L2 at this size)')
@@ -309,6 +317,7 @@ def run_ours(args, rank, world, device):
                   'hbm': {'achieved_gbs': round(gbs, 2), 'peak_gbs': hbm, 'frac': round(gbs / hbm, 4)},
                   'tensor': {'achieved_tflops': round(tfl, 3), 'peak_tf32_tflops': round(tf32_peak, 1),
                              'frac': round(tfl / tf32_peak, 4), 'mma_per_product': 3 if tc else 0,
+                             'ncu_tensor_pipe_active_pct_time_weighted': ncu_tensor_pct,
                              'note': 'algorithmic flops 2*P*Cin*Cout; the fp32-parity mode issues 3 tf32 '
                                      'MMAs per product, so the attainable ceiling is peak/3'}}
         if tc and tensor_time > hbm_time:
