@@ -19,7 +19,7 @@ import torch.nn.functional as F
 from torch import nn
 
 from . import functional as Fsp
-from . import ops, spconv
+from . import executor, ops, spconv
 from .registry import MIDDLE_ENCODERS
 from .sparse_block import SparseBasicBlock, make_sparse_convmodule
 
@@ -135,6 +135,31 @@ class SparseMultiModalEncoderPaint(nn.Module):
         buf.copy_(val)
         return buf.to(device, non_blocking=True)
 
+    # one native-executor call per conv chain (csrc/executor.cu) instead of one C-ABI call per rulebook
+    # and convolution; falls back to the module when the chain is not in fused-inference form
+    use_executor = True
+
+    def _run_chain(self, key, module, x):
+        if not (self.use_executor and x.features.is_cuda and not torch.is_grad_enabled()
+                and x.indices.shape[0] > 0):
+            return module(x)
+        plans = self.__dict__.setdefault('_plans', {})
+        k = executor.plan_key([module])
+        ent = plans.get(key)
+        if ent is None or ent[0] != k:
+            try:
+                plan = executor.SparseNetPlan()
+                plan.add(module, 0)
+                plan.finalize()
+            except executor.Unsupported:
+                plan = None
+            plans[key] = ent = (k, plan)
+        if ent[1] is None:
+            return module(x)
+        idx = x.indices if x.indices.dtype == torch.int32 else x.indices.int()
+        f, oidx, shape = ent[1].run(x.features, idx, x.spatial_shape, x.batch_size)[-1]
+        return spconv.SparseConvTensor(f, oidx, shape, x.batch_size)
+
     def fps_NN_fast(self, query, key, fps_num, radius, max_cluster_samples, dist_thresh):
         return fps_nn_fast(query, key, fps_num, radius, max_cluster_samples, dist_thresh)
 
@@ -199,7 +224,8 @@ class SparseMultiModalEncoderPaint(nn.Module):
             voxel_mixed_indices, voxel_mixed_feat, B, ind3[0], torch.cat([feat3[0], feat2[0]], dim=-1))
 
         stage_name = f'stage_{stage_id + 1}'
-        voxel_only_3D = getattr(self.grouped_sp_conv_blocks_3D, stage_name)(voxel_only_3D)
+        voxel_only_3D = self._run_chain(('only3d', stage_id), getattr(self.grouped_sp_conv_blocks_3D, stage_name),
+                                        voxel_only_3D)
         only_2D_feat = F.pad(voxel_only_2D_features, (c3, 0), mode='constant', value=0)
         only_3D_feat = F.pad(voxel_only_3D.features, (0, 64), mode='constant', value=0)
         assert only_2D_feat.shape[-1] == only_3D_feat.shape[-1] == voxel_mixed_feat.shape[-1]
@@ -209,7 +235,7 @@ class SparseMultiModalEncoderPaint(nn.Module):
                                          voxel_mixed_indices[:, [0, 2, 3, 4]]], dim=0).contiguous()
         unified_voxel = spconv.SparseConvTensor(unified_voxel_feat, unified_voxel_coors,
                                                 voxel_2D.spatial_shape, voxel_2D.batch_size)
-        return getattr(self.aggregation_blocks, stage_name)(unified_voxel)
+        return self._run_chain(('agg', stage_id), getattr(self.aggregation_blocks, stage_name), unified_voxel)
 
     def _assign_b1(self, voxel_3D, voxel_2D, P, fps_num, radius, max_cluster_samples, dist_thresh):
         """Index-only part of a stage (one sample per GPU): only-3D / only-2D row lists and the
@@ -265,7 +291,8 @@ class SparseMultiModalEncoderPaint(nn.Module):
             mixed_bzyx = torch.zeros((1, 4), dtype=bz2.dtype, device=dev)
 
         stage_name = f'stage_{stage_id + 1}'
-        voxel_only_3D = getattr(self.grouped_sp_conv_blocks_3D, stage_name)(voxel_only_3D)
+        voxel_only_3D = self._run_chain(('only3d', stage_id), getattr(self.grouped_sp_conv_blocks_3D, stage_name),
+                                        voxel_only_3D)
         n_o3, n_o2, n_mx = voxel_only_3D.features.shape[0], only2_feat.shape[0], mixed_feat.shape[0]
         cu = c3 + 64
         # zero-padded concatenation (:414-425) written straight into the unified buffer
@@ -275,7 +302,7 @@ class SparseMultiModalEncoderPaint(nn.Module):
         unified_feat[n_o3 + n_o2:] = mixed_feat
         unified_coors = torch.cat([voxel_only_3D.indices, only2_bzyx, mixed_bzyx], dim=0)
         unified_voxel = spconv.SparseConvTensor(unified_feat, unified_coors, voxel_2D.spatial_shape, 1)
-        return getattr(self.aggregation_blocks, stage_name)(unified_voxel)
+        return self._run_chain(('agg', stage_id), getattr(self.aggregation_blocks, stage_name), unified_voxel)
 
     def _assign_all_overlapped(self, voxel_3D_list, voxel_2D_list, syn_mix_3D_list, fps_num_list,
                                radius_list, max_cluster_samples_list, dist_thresh_list):
@@ -333,5 +360,5 @@ class SparseMultiModalEncoderPaint(nn.Module):
                     max_cluster_samples_list[stage_id], dist_thresh_list[stage_id])
             if stage_id > 0:
                 out = Fsp.sparse_add(out, stage_outs[stage_id - 1])
-            stage_outs.append(getattr(self.downscale_blocks, stage_name)(out))
+            stage_outs.append(self._run_chain(('down', stage_id), getattr(self.downscale_blocks, stage_name), out))
         return stage_outs
