@@ -79,6 +79,8 @@ class Clocks:
         self.lines = []
 
     def start(self):
+        if os.environ.get('MSMD_BENCH_NOSMI'):  # diagnostic switch
+            return
         try:
             self.proc = subprocess.Popen(
                 ['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q, '--format=csv,noheader,nounits',
@@ -178,8 +180,10 @@ def run_ours(args, rank, world, device):
         pts_dev = pts_host.to(device)
         h2d_extra = [0]
 
+        metas_resident = [meta]  # same list object every step -> the packed upload stays on the device
+
         def step(points, fresh_upload=False):
-            metas = [dict(meta)] if fresh_upload else [meta]  # a new dict -> packed upload repeated
+            metas = [dict(meta)] if fresh_upload else metas_resident  # new dict -> pack + upload again
             with torch.no_grad():
                 bev, stage_outs = det.extract_voxel_space([points], fpn, metas)
             if fresh_upload:
@@ -215,9 +219,12 @@ def run_ours(args, rank, world, device):
     # generation-2 collection cannot stall a timed step (the model graph is static from here on)
     gc.collect()
     gc.freeze()
+    if os.environ.get('MSMD_BENCH_NOGC'):  # diagnostic switch
+        gc.disable()
 
     # ---- device-resident timing: K steps, L2 flushed between steps, CUDA events per step ----
     mark0 = clocks.mark()
+    ms0 = torch.cuda.memory_stats(device)
     launches0 = _cabi.lib().msmd_launch_count()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     sync_all()
@@ -228,6 +235,10 @@ def run_ours(args, rank, world, device):
         e.record()
     sync_all()
     launches = _cabi.lib().msmd_launch_count() - launches0
+    ms1 = torch.cuda.memory_stats(device)
+    alloc_diag = {k: int(ms1.get(k, 0) - ms0.get(k, 0)) for k in
+                  ('num_device_alloc', 'num_device_free', 'num_alloc_retries', 'num_sync_all_streams')}
+    alloc_diag['reserved_gb'] = round(ms1.get('reserved_bytes.all.current', 0) / 1e9, 2)
     step_raw = [s.elapsed_time(e) for s, e in ev]
     step_ms = sorted(step_raw)
     dev_ms = sum(step_ms)
@@ -333,6 +344,7 @@ def run_ours(args, rank, world, device):
     return dict(dev_ms=dev_ms, e2e_ms=e2e_ms, launches=int(launches), clocks=clk, roofline=roof,
                 e2e_step_ms=dict(min=round(min(e2e_raw), 4), median=round(sorted(e2e_raw)[len(e2e_raw) // 2], 4),
                                  max=round(max(e2e_raw), 4)),
+                alloc=alloc_diag,
                 step_ms=dict(min=round(step_ms[0], 4), median=round(step_ms[len(step_ms) // 2], 4),
                              max=round(step_ms[-1], 4), all=[round(x, 3) for x in step_raw[:32]]),
                 points=int(pts_np.shape[0]), voxels=n_vox, checksum=checksum,
@@ -440,6 +452,7 @@ def main():
                          '(Voxelization.forward_mean/SparseEncoder or MSMDFusionDetector.extract_voxel_space) '
                          '-> checksum of the BEV tensor read back')},
         'gpu_launches': res['launches'],
+        'allocator_during_timed_steps': res['alloc'],
         'clocks': res['clocks'],
         'roofline': res['roofline'],
         'cpu_baseline': cpu_base,

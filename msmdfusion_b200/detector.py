@@ -65,7 +65,7 @@ class PackedForeground:
     concatenation (``MSMDFusion.py:189-226``) produces.
     """
 
-    def __init__(self, img_metas, device, ncam=None):
+    def __init__(self, img_metas, device, ncam=None, staging=None):
         B = len(img_metas)
         pix, pts, cam, l2i, rpix, rcam, counts = [], [], [], [], [], [], []
         for b, meta in enumerate(img_metas):
@@ -89,26 +89,39 @@ class PackedForeground:
             self.ncam = n
         self.batch_size = B
         self.counts = counts
-        up = lambda arrs, width, dt: self._upload(arrs, width, dt, device)  # noqa: E731
+        # persistent pinned staging buffers (grow-only, owned by the detector): cudaHostAlloc per
+        # call costs milliseconds and synchronises the device
+        self._staging = staging if staging is not None else {}
+        ev = self._staging.get('event')
+        if ev is not None:
+            ev.synchronize()  # the previous upload has left the staging buffers
         pdim = pts[0].shape[1] if pts else 15
-        self.pixels = up(pix, 3, np.float32)
-        self.points = up(pts, pdim, np.float32)
-        self.cam = up(cam, None, np.int32)
-        self.lidar2img = up(l2i, None, np.float32).view(-1, 16)
-        self.real_pixels = up(rpix, 3, np.float32)
-        self.real_cam = up(rcam, None, np.int32)
+        self.pixels = self._upload('pixels', pix, 3, np.float32, device)
+        self.points = self._upload('points', pts, pdim, np.float32, device)
+        self.cam = self._upload('cam', cam, None, np.int32, device)
+        self.lidar2img = self._upload('lidar2img', l2i, None, np.float32, device).view(-1, 16)
+        self.real_pixels = self._upload('real_pixels', rpix, 3, np.float32, device)
+        self.real_cam = self._upload('real_cam', rcam, None, np.int32, device)
+        if torch.device(device).type == 'cuda':
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(device))
+            self._staging['event'] = ev
         self.h2d_bytes = sum(int(t.numel()) * t.element_size() for t in
                              (self.pixels, self.points, self.cam, self.lidar2img, self.real_pixels,
                               self.real_cam))
 
-    @staticmethod
-    def _upload(arrs, width, dtype, device):
+    def _upload(self, name, arrs, width, dtype, device):
         shape = (0,) if width is None else (0, width)
         a = np.concatenate(arrs, 0) if arrs else np.zeros(shape, dtype)
-        t = torch.from_numpy(np.ascontiguousarray(a))
-        if t.numel() and torch.device(device).type == 'cuda':
-            t = t.pin_memory()
-        return t.to(device, non_blocking=True)
+        src = torch.from_numpy(np.ascontiguousarray(a))
+        if src.numel() == 0 or torch.device(device).type != 'cuda':
+            return src.to(device)
+        buf = self._staging.get(name)
+        if buf is None or buf.numel() < src.numel() or buf.dtype != src.dtype:
+            buf = self._staging[name] = torch.empty((int(src.numel() * 1.25) + 16,), dtype=src.dtype).pin_memory()
+        stage = buf[:src.numel()].view(src.shape)
+        stage.copy_(src)
+        return stage.to(device, non_blocking=True)
 
 
 def _maybe_build(cfg, builder):
@@ -246,7 +259,9 @@ class MSMDFusionDetector(nn.Module, _VoxelPathMixin):
         key, val = self._packed
         if key is img_metas and val is not None and val.pixels.device == torch.device(device):
             return val
-        val = PackedForeground(img_metas, device)
+        if not hasattr(self, '_staging'):
+            self._staging = {}
+        val = PackedForeground(img_metas, device, staging=self._staging)
         self._packed = (img_metas, val)
         return val
 
