@@ -343,7 +343,7 @@ def run_ours(args, rank, world, device):
     n_vox = int(feats[0].indices.shape[0])
     return dict(dev_ms=dev_ms, e2e_ms=e2e_ms, launches=int(launches), clocks=clk, roofline=roof,
                 e2e_step_ms=dict(min=round(min(e2e_raw), 4), median=round(sorted(e2e_raw)[len(e2e_raw) // 2], 4),
-                                 max=round(max(e2e_raw), 4)),
+                                 max=round(max(e2e_raw), 4), all=[round(x, 2) for x in e2e_raw[:32]]),
                 alloc=alloc_diag,
                 step_ms=dict(min=round(step_ms[0], 4), median=round(step_ms[len(step_ms) // 2], 4),
                              max=round(step_ms[-1], 4), all=[round(x, 3) for x in step_raw[:32]]),
