@@ -96,7 +96,7 @@ __device__ __forceinline__ void tc_epilogue(int any_active, uint64_t* accum_bar,
                                             const float* ss /* smem: scale[N] | shift[N] */,
                                             const float* __restrict__ residual, int relu,
                                             float* __restrict__ out, float* write_partial = nullptr,
-                                            const float* add_partial = nullptr) {
+                                            const float* add_partial = nullptr, int cat_cols = 0) {
     if (any_active) {
       tc::mbar_wait(accum_bar, 0);
       tc::fence_after_sync();
@@ -113,6 +113,14 @@ __device__ __forceinline__ void tc_epilogue(int any_active, uint64_t* accum_bar,
       uint32_t acc[16];
       if (any_active) {
         tc::tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, acc);
+        if (cat_cols) {  // concatenated-B mode: columns [N, 2N) hold the A_hi * B_lo term
+          uint32_t acc2[16];
+          tc::tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(cat_cols + c0), acc2);
+          tc::tmem_ld_wait();
+#pragma unroll
+          for (int e = 0; e < 16; ++e)
+            acc[e] = __float_as_uint(__uint_as_float(acc[e]) + __uint_as_float(acc2[e]));
+        }
         tc::tmem_ld_wait();
       } else {
 #pragma unroll
@@ -183,7 +191,7 @@ spconv_fwd_tc_kernel(const float* __restrict__ feat, const float* __restrict__ w
                      int kvol, int chunks, int stages, int stage_bytes, int pair_off, int act_off,
                      int bar_off, int tmem_cols, const float* __restrict__ scale,
                      const float* __restrict__ shift, const float* __restrict__ residual, int relu,
-                     float* __restrict__ out) {
+                     float* __restrict__ out, int cat) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   int* pair_s = (int*)(smem + pair_off);
@@ -305,7 +313,8 @@ spconv_fwd_tc_kernel(const float* __restrict__ feat, const float* __restrict__ w
     }
 
     // ===== epilogue: TMEM -> registers -> fused BN / residual / ReLU -> global =============
-    tc_epilogue(any_active, accum_bar, tmem_base, warp, lane, row0, n_out, cout, N, ss, residual, relu, out);
+    tc_epilogue(any_active, accum_bar, tmem_base, warp, lane, row0, n_out, cout, N, ss, residual, relu, out,
+                nullptr, nullptr, cat ? N : 0);
   } else if (warp == kTcProducerWarps) {
     // ===== B loader: one bulk copy (hi + lo image of the chunk) per active chunk ============
     if (lane == 0) {
@@ -324,6 +333,7 @@ spconv_fwd_tc_kernel(const float* __restrict__ feat, const float* __restrict__ w
     // ===== MMA issuer ========================================================================
     if (lane == 0) {
       const uint32_t idesc = tc::idesc_f32acc(tc::kFmtTF32, kTcM, N);
+      const uint32_t idesc2 = tc::idesc_f32acc(tc::kFmtTF32, kTcM, 2 * N);
       uint32_t accumulate = 0;
       for (int it = 0; it < n_act; ++it) {
         const int s = it % stages;
@@ -339,9 +349,18 @@ spconv_fwd_tc_kernel(const float* __restrict__ feat, const float* __restrict__ w
           const uint32_t koff = (uint32_t)ks * 32u;  // 8 tf32 = 32 bytes along K
           const uint64_t dah = tc::desc_k_sw128(a_hi + koff), dal = tc::desc_k_sw128(a_lo + koff);
           const uint64_t dbh = tc::desc_k_sw128(b_hi + koff), dbl = tc::desc_k_sw128(b_lo + koff);
-          tc::mma_tf32(tmem_base, dal, dbh, idesc, accumulate);  // small terms first
-          tc::mma_tf32(tmem_base, dah, dbl, idesc, 1u);
-          tc::mma_tf32(tmem_base, dah, dbh, idesc, 1u);
+          if (cat) {
+            // B_hi and B_lo are adjacent in the stage, i.e. ONE K-major operand of 2N rows:
+            //   D[:, 0:2N] += A_hi * [B_hi; B_lo]      D[:, 0:N] += A_lo * B_hi
+            // two MMAs per k-step instead of three, A_hi is read from shared memory once; the
+            // epilogue adds the two column halves.
+            tc::mma_tf32(tmem_base, dah, dbh, idesc2, accumulate);
+            tc::mma_tf32(tmem_base, dal, dbh, idesc, 1u);
+          } else {
+            tc::mma_tf32(tmem_base, dal, dbh, idesc, accumulate);  // small terms first
+            tc::mma_tf32(tmem_base, dah, dbl, idesc, 1u);
+            tc::mma_tf32(tmem_base, dah, dbh, idesc, 1u);
+          }
           accumulate = 1u;
         }
         tc::mma_commit(&empty_bar[s]);  // frees the stage once these MMAs have read it
@@ -776,10 +795,17 @@ extern "C" MSMD_API int msmd_spconv_fwd_tc_ws(const float* features, int n_in, c
     MSMD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set[vec] = true;
   }
+  // concatenated-B mode needs 2N accumulator columns; two co-resident CTAs must fit in 512
+  const int cat = (2 * g.N <= 256) ? 1 : 0;
+  int tmem_cols = g.tmem_cols;
+  if (cat) {
+    tmem_cols = 32;
+    while (tmem_cols < 2 * g.N) tmem_cols <<= 1;
+  }
   kern<<<tiles, kTcThreads, L.total, stream>>>(features, packed_tc, pair_fwd, n_out, cin, g.cin_pad, cout,
                                                g.N, kvol, g.chunks, L.stages, L.stage_bytes, L.pair_off,
-                                               L.act_off, L.bar_off, g.tmem_cols, scale, shift, residual,
-                                               relu, out);
+                                               L.act_off, L.bar_off, tmem_cols, scale, shift, residual,
+                                               relu, out, cat);
   MSMD_LAUNCH_OK();
   return MSMD_OK;
 }

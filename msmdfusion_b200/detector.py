@@ -373,6 +373,11 @@ class MSMDFusionDetector(nn.Module, _VoxelPathMixin):
                                             downscale_factors[i], batch_size)
             v3, v2, s3, s2 = self.voxel_modality_split(encode_features[i], voxel_2D, batch_size)
             v3l.append(v3); v2l.append(v2); s3l.append(s3); s2l.append(s2)
+            enc = getattr(self, 'multimodal_middle_encoder', None)
+            if enc is not None and hasattr(enc, 'prelaunch_assign') and self.fps_num_list is not None:
+                # coordinates of this scale are final: start its FPS / NN-assignment chain now
+                enc.prelaunch_assign(i, v3, v2, s3.shape[0], self.fps_num_list[i], self.radius_list[i],
+                                     self.max_cluster_samples_list[i], self.dist_thresh_list[i])
         return v3l, v2l, s3l, s2l
 
     # -- :421-452 ---------------------------------------------------------------------------

@@ -304,38 +304,58 @@ class SparseMultiModalEncoderPaint(nn.Module):
         unified_voxel = spconv.SparseConvTensor(unified_feat, unified_coors, voxel_2D.spatial_shape, 1)
         return self._run_chain(('agg', stage_id), getattr(self.aggregation_blocks, stage_name), unified_voxel)
 
-    def _assign_all_overlapped(self, voxel_3D_list, voxel_2D_list, syn_mix_3D_list, fps_num_list,
-                               radius_list, max_cluster_samples_list, dist_thresh_list):
-        """Launch the index-only chains (FPS is ~2000 serial rounds on 8 SMs) of all stages on side
-        streams: they depend on coordinates only, so they overlap each other and the convolutions
-        of earlier stages.  Returns per-stage (assign dict, completion event) or None."""
-        n = len(voxel_2D_list)
-        ok = all(v3.batch_size == 1 and getattr(v3, '_mix', None) is not None and
-                 getattr(v2, '_mix', None) is not None and v3.features.is_cuda
-                 for v3, v2 in zip(voxel_3D_list, voxel_2D_list))
-        if not ok or not self.overlap_assign:
-            return None
-        dev = voxel_3D_list[0].features.device
-        if self._side_streams is None or self._side_streams[0].device != dev:
-            self._side_streams = [torch.cuda.Stream(device=dev) for _ in range(n)]
+    def _side_stream(self, stage_id, dev, n=4):
+        if self._side_streams is None or self._side_streams[0].device != dev or \
+                len(self._side_streams) < max(n, stage_id + 1):
+            self._side_streams = [torch.cuda.Stream(device=dev) for _ in range(max(n, stage_id + 1))]
+        return self._side_streams[stage_id]
+
+    def prelaunch_assign(self, stage_id, voxel_3D, voxel_2D, num_mix, fps_num, radius,
+                         max_cluster_samples, dist_thresh):
+        """Start stage ``stage_id``'s index-only chain (FPS ~2000 serial rounds on 8 SMs -> nearest
+        3-D voxel -> ball query -> assignment) on a side stream NOW.  It depends on coordinates
+        only, so the detector calls this right after each scale's voxel_modality_split and the
+        chain overlaps the remaining scales' lift / voxelize / split and the earlier stages'
+        convolutions.  Returns False when the sync-free single-sample path does not apply."""
+        ok = (self.overlap_assign and voxel_3D.batch_size == 1 and voxel_3D.features.is_cuda and
+              getattr(voxel_3D, '_mix', None) is not None and getattr(voxel_2D, '_mix', None) is not None)
+        if not ok:
+            return False
+        dev = voxel_3D.features.device
+        side = self._side_stream(stage_id, dev)
         main = torch.cuda.current_stream(dev)
         ready = torch.cuda.Event()
         ready.record(main)
+        # No record_stream is needed for the chain's outputs: a side stream only ever starts work
+        # after waiting for an event recorded on the main stream, so blocks of its pool are never
+        # reused before every earlier main-stream reader has finished.
+        side.wait_event(ready)
+        with torch.cuda.stream(side):
+            a = self._assign_b1(voxel_3D, voxel_2D, int(num_mix), fps_num, radius, max_cluster_samples,
+                                dist_thresh)
+            done = torch.cuda.Event()
+            done.record(side)
+        self.__dict__.setdefault('_pre', {})[stage_id] = (a, done, voxel_3D, voxel_2D)
+        return True
+
+    def _assign_all_overlapped(self, voxel_3D_list, voxel_2D_list, syn_mix_3D_list, fps_num_list,
+                               radius_list, max_cluster_samples_list, dist_thresh_list):
+        """Per-stage (assign dict, completion event) of the index-only chains, launching on side
+        streams whatever the detector has not pre-launched already; None = use the generic path."""
+        n = len(voxel_2D_list)
+        pre = self.__dict__.pop('_pre', {})
         out = []
         for s in range(n):
-            side = self._side_streams[s]
-            side.wait_event(ready)
-            with torch.cuda.stream(side):
-                a = self._assign_b1(voxel_3D_list[s], voxel_2D_list[s], syn_mix_3D_list[s].shape[0],
-                                    fps_num_list[s], radius_list[s], max_cluster_samples_list[s],
-                                    dist_thresh_list[s])
-                done = torch.cuda.Event()
-                done.record(side)
-            # The chain's outputs are consumed on the main stream.  No record_stream is needed: a
-            # side stream only ever starts work after waiting for `ready`, recorded on the main
-            # stream at the top of a forward, so blocks of its pool are never reused before every
-            # earlier main-stream reader has finished.
-            out.append((a, done))
+            ent = pre.get(s)
+            if ent is None or ent[2] is not voxel_3D_list[s] or ent[3] is not voxel_2D_list[s]:
+                if not self.prelaunch_assign(s, voxel_3D_list[s], voxel_2D_list[s],
+                                             syn_mix_3D_list[s].shape[0], fps_num_list[s], radius_list[s],
+                                             max_cluster_samples_list[s], dist_thresh_list[s]):
+                    self.__dict__.pop('_pre', None)
+                    return None
+                ent = self.__dict__['_pre'].pop(s)
+            out.append((ent[0], ent[1]))
+        self.__dict__.pop('_pre', None)
         return out
 
     def forward(self, voxel_3D_list, voxel_2D_list, syn_mix_3D_list, syn_mix_2D_list, fps_num_list,
