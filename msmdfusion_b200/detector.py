@@ -111,16 +111,20 @@ class PackedForeground:
                               self.real_cam))
 
     def _upload(self, name, arrs, width, dtype, device):
-        shape = (0,) if width is None else (0, width)
-        a = np.concatenate(arrs, 0) if arrs else np.zeros(shape, dtype)
-        src = torch.from_numpy(np.ascontiguousarray(a))
-        if src.numel() == 0 or torch.device(device).type != 'cuda':
-            return src.to(device)
+        """Concatenate ``arrs`` DIRECTLY into a persistent pinned staging buffer (no temporary host
+        array, no per-call cudaHostAlloc) and start the asynchronous upload."""
+        rows = sum(a.shape[0] for a in arrs)
+        shape = (rows,) if width is None else (rows, width)
+        numel = rows * (1 if width is None else width)
+        if numel == 0 or torch.device(device).type != 'cuda':
+            a = np.concatenate(arrs, 0) if arrs else np.zeros(shape, dtype)
+            return torch.from_numpy(np.ascontiguousarray(a.astype(dtype, copy=False))).to(device)
+        tdtype = torch.float32 if dtype == np.float32 else torch.int32
         buf = self._staging.get(name)
-        if buf is None or buf.numel() < src.numel() or buf.dtype != src.dtype:
-            buf = self._staging[name] = torch.empty((int(src.numel() * 1.25) + 16,), dtype=src.dtype).pin_memory()
-        stage = buf[:src.numel()].view(src.shape)
-        stage.copy_(src)
+        if buf is None or buf.numel() < numel or buf.dtype != tdtype:
+            buf = self._staging[name] = torch.empty((int(numel * 1.25) + 16,), dtype=tdtype).pin_memory()
+        stage = buf[:numel].view(shape)
+        np.concatenate([np.asarray(a, dtype).reshape((-1,) + shape[1:]) for a in arrs], 0, out=stage.numpy())
         return stage.to(device, non_blocking=True)
 
 
