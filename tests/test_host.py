@@ -6,6 +6,7 @@ import glob
 import os
 import re
 
+import numpy as np
 import pytest
 import torch
 
@@ -123,3 +124,58 @@ def test_sparse_tensor_surface():
     assert len(seq) == 1 and isinstance(seq[0], torch.nn.ReLU)
     with pytest.raises(ValueError):
         sp._iset_of(t)
+
+
+def test_executor_plan_matches_reference_layer_table(monkeypatch):
+    """The native-executor plan derived from the module tree is the 21-layer table of
+    SURVEY Appendix A (mmdet3d/models/middle_encoders/sparse_encoder.py:60-209): SubM/strided
+    kinds, channel widths, geometry, the residual links of SparseBasicBlock and the activations
+    exported as encode_features."""
+    import torch
+    import msmdfusion_b200 as m
+    from msmdfusion_b200 import executor, registry
+    from msmdfusion_b200 import spconv as sp
+    cfg = m.Config.fromfile(os.path.join(ROOT, 'configs', 'msmd_lc_hotpath.py')).hotpath
+    enc = registry.build_middle_encoder(cfg.pts_middle_encoder).eval()
+    # kernel-layout packing needs the CUDA library; the plan STRUCTURE does not
+    monkeypatch.setattr(sp.SparseConvolution, 'packed_weight', lambda self: self.weight.detach().reshape(-1))
+    plan = executor.SparseNetPlan()
+    cur = plan.add(enc.conv_input, 0)
+    marks = [cur]
+    for layer in enc.encoder_layers:
+        cur = plan.add(layer, cur)
+        marks.append(cur)
+    marks.append(plan.add(enc.conv_out, cur))
+    L = plan.layers
+    assert len(L) == 21 and marks == [1, 6, 11, 16, 20, 21]
+    assert [(x['cin'], x['cout']) for x in L] == (
+        [(5, 16)] + [(16, 16)] * 4 + [(16, 32)] + [(32, 32)] * 4 + [(32, 64)] + [(64, 64)] * 4 +
+        [(64, 128)] + [(128, 128)] * 4 + [(128, 128)])
+    assert [x['subm'] for x in L] == [1] * 5 + [0] + [1] * 4 + [0] + [1] * 4 + [0] + [1] * 4 + [0]
+    assert L[5]['stride'] == [2, 2, 2] and L[5]['padding'] == [1, 1, 1]
+    assert L[15]['padding'] == [0, 1, 1]                      # encoder_paddings ((0,0,[0,1,1]))
+    assert L[20]['ksize'] == [3, 1, 1] and L[20]['stride'] == [2, 1, 1] and L[20]['padding'] == [0, 0, 0]
+    # SparseBasicBlock: conv2 adds the block input before the ReLU
+    assert [x['residual'] for x in L[1:5]] == [-1, 1, -1, 3]
+    assert all(x['relu'] == 1 for x in L) and all(x['scale'] is not None for x in L)
+    enc.train()
+    with pytest.raises(executor.Unsupported):
+        executor.SparseNetPlan().add(enc.conv_input, 0)     # training-mode BN is not foldable
+
+
+def test_packed_foreground_layout_cpu():
+    """One packed upload per batch: order = samples, cameras, points (MSMDFusion.py:189-226)."""
+    from msmdfusion_b200 import synthetic
+    from msmdfusion_b200.detector import PackedForeground
+    pts = synthetic.lidar_scene(0, 1)[:5000]
+    metas = [synthetic.camera_scene(0, pts, virtual_per_camera=50, real_per_camera=20, empty_cameras=(2,)),
+             synthetic.camera_scene(1, pts, virtual_per_camera=30, real_per_camera=10)]
+    pk = PackedForeground(metas, 'cpu')
+    assert pk.counts == [250, 180] and pk.ncam == 6
+    assert pk.pixels.shape == (430, 3) and pk.points.shape == (430, 15) and pk.lidar2img.shape == (12, 16)
+    cam = pk.cam.numpy()
+    assert (np.diff(cam) >= 0).all() and set(cam[:250].tolist()) == {0, 1, 3, 4, 5}   # camera 2 is empty
+    assert cam[250] == 6
+    first = metas[1]['foreground2D_info']['fg_points'][0]
+    assert np.array_equal(pk.points[250:280].numpy(), first)
+    assert np.allclose(pk.lidar2img[7].numpy(), np.asarray(metas[1]['lidar2img'][1], np.float32).reshape(16))
