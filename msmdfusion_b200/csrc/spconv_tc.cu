@@ -18,11 +18,17 @@
 //     ReLU, store.
 //   K chunks whose kernel offsets no voxel of the tile uses are skipped entirely.
 //
-// Pipeline: `stages` shared-memory stages, mbarrier full/empty per stage (full = 256 producer
-// arrivals + the bulk copy's transaction bytes; empty = tcgen05.commit), one accumulator-ready
+// Pipeline: `stages` shared-memory stages, mbarrier full/empty per stage (full = one arrival per
+// gather warp + the bulk copy's transaction bytes; empty = tcgen05.commit), one accumulator-ready
 // barrier for the epilogue.  Warps 0-7 gather (each thread keeps the loads of TWO chunks in
 // flight), then run the epilogue; warp 8 issues the B bulk copies; warp 9 allocates TMEM and
 // issues the MMAs.
+//
+// Variants (chosen by N, see the dispatch at the bottom):
+//   variant 2 (this kernel)      A hi/lo staged in shared memory; for 2N <= 256 the B_hi|B_lo halves
+//                                are used as ONE 2N-row operand (2 MMAs per k-step instead of 3)
+//   variant 3 (spconv_fwd_tc3)   A hi/lo staged in TENSOR MEMORY (tcgen05.st), B only in shared
+//                                memory, optional split-K CTA pairs for tail balance
 #include "tc.cuh"
 
 namespace msmd {
@@ -61,7 +67,7 @@ static TcSmemLayout tc_layout(int N, int kvol, int chunks) {
 }
 
 // One lane polls the mbarrier, the warp follows through __syncwarp (31 fewer spinning lanes per
-// warp: the producers are instruction-issue bound, ncu profiles/r01d).
+// warp: the producers are instruction-issue bound, profiles/r01e_ncu_full_spconv_tc_profileS.json).
 __device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity, int lane) {
   if (lane == 0) tc::mbar_wait(bar, parity);
   __syncwarp();
