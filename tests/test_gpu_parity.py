@@ -731,3 +731,111 @@ def test_cuda_conv_matches_reference_spconv1x_golden(path):
         assert y.spatial_shape == [int(s) for s in g['out_shape']]
         assert np.array_equal(y.indices.cpu().numpy(), g['out_indices'].astype(np.int32))
         assert feat_err(y.features.cpu().numpy(), g['out_features']) < FEAT_TOL
+
+
+# --------------------------------------------------------------------------------------
+# BASELINE.json full sizes (profile L: 10 sweeps, ~285 k points, ~114 k voxels): the oracle is too
+# slow there, so the CUDA path is checked through size-independent properties of the domain
+# --------------------------------------------------------------------------------------
+def full_size_scene():
+    cfg = m.Config.fromfile(os.path.join(ROOT, 'configs', 'msmd_lc_hotpath.py')).hotpath
+    layer = m.Voxelization(**cfg.pts_voxel_layer).eval()
+    pts = synthetic.lidar_scene(123, 10)
+    mean, coors, num = layer.forward_mean(cuda(pts), 5, batch_idx=0)
+    return cfg, pts, mean, coors, num
+
+
+def lin_index(idx, shape):
+    i = idx.long()
+    return ((i[:, 0] * shape[0] + i[:, 1]) * shape[1] + i[:, 2]) * shape[2] + i[:, 3]
+
+
+def test_full_size_rulebook_and_conv_properties():
+    cfg, pts, mean, coors, num = full_size_scene()
+    n = coors.shape[0]
+    assert n > 100000 and int(num.sum()) <= pts.shape[0] and int(num.max()) <= 10
+    shape = [41, 1440, 1440]
+    assert torch.unique(lin_index(coors, shape)).numel() == n            # voxels are unique cells
+    torch.manual_seed(0)
+    subm = m.spconv.SubMConv3d(16, 64, 3, padding=1, bias=False, indice_key='s').to(dev())
+    down = m.spconv.SparseConv3d(64, 64, 3, stride=2, padding=1, bias=False, indice_key='d').to(dev())
+    g = torch.Generator(device='cpu').manual_seed(1)
+    x1 = torch.randn(n, 16, generator=g).to(dev())
+    x2 = torch.randn(n, 16, generator=g).to(dev())
+
+    def net(f):
+        with torch.no_grad():
+            t = subm(m.spconv.SparseConvTensor(f, coors, shape, 1))
+            return t, down(t)
+    a1, b1 = net(x1)
+    a2, b2 = net(x2)
+    a3, b3 = net(2.5 * x1 - 0.75 * x2)
+    # SubM keeps the index set; its centre offset maps every voxel to itself
+    assert torch.equal(a1.indices, coors)
+    pair = a1.find_indice_pair('s').pair_fwd
+    assert torch.equal(pair[13], torch.arange(n, device=dev(), dtype=torch.int32))
+    assert int((pair >= 0).sum()) == int(((pair >= 0) & (pair < n)).sum())
+    # strided outputs: spconv-2.x order = strictly ascending linear index; every output has an input
+    oshape = b1.spatial_shape
+    assert oshape == [21, 720, 720]
+    lin = lin_index(b1.indices, oshape)
+    assert bool((lin[1:] > lin[:-1]).all())
+    dpair = b1.find_indice_pair('d').pair_fwd
+    assert bool(((dpair >= 0).sum(0) >= 1).all()) and int(dpair.max()) < n
+    # every input voxel reaches exactly the outputs the geometry allows: sum of pairs == sum over
+    # inputs of the number of (kernel offset, output) combinations that hit it -> count both ways
+    assert int((dpair >= 0).sum()) == int(torch.bincount(dpair[dpair >= 0].long(), minlength=n).sum())
+    # linearity of the whole chain (tensor-core 3xTF32 path), relative to the output scale
+    for lhs, y1, y2 in ((a3, a1, a2), (b3, b1, b2)):
+        ref = 2.5 * y1.features - 0.75 * y2.features
+        assert feat_err(lhs.features.cpu().numpy(), ref.cpu().numpy()) < FEAT_TOL
+    # determinism (split-K pairs, overlapped streams): a second run is bit-identical
+    a1b, b1b = net(x1)
+    assert torch.equal(a1.features, a1b.features) and torch.equal(b1.features, b1b.features)
+
+
+def test_full_size_sparse_add_and_dense_properties():
+    cfg, pts, mean, coors, num = full_size_scene()
+    n = coors.shape[0]
+    shape = [41, 1440, 1440]
+    g = torch.Generator(device='cpu').manual_seed(2)
+    fa = torch.randn(n, 32, generator=g).to(dev())
+    half = coors[: n // 2]
+    fb = torch.randn(half.shape[0], 32, generator=g).to(dev())
+    a = m.spconv.SparseConvTensor(fa, coors, shape, 1)
+    b = m.spconv.SparseConvTensor(fb, half, shape, 1)
+    ab, ba, aa = m.functional.sparse_add(a, b), m.functional.sparse_add(b, a), m.functional.sparse_add(a, a)
+    lin = lin_index(ab.indices, shape)
+    assert ab.indices.shape[0] == n and bool((lin[1:] > lin[:-1]).all())       # coalesced + sorted
+    assert torch.equal(ab.indices, ba.indices) and torch.equal(ab.features, ba.features)  # commutative
+    # a + a == 2a on the same index set; checksum of features is preserved by a + b
+    order = torch.argsort(lin_index(coors, shape))
+    assert torch.equal(aa.indices, coors[order]) and torch.equal(aa.features, 2 * fa[order])
+    assert abs(float(ab.features.double().sum()) - float(fa.double().sum() + fb.double().sum())) < 1e-3
+    # dense(): every active cell carries its row, everything else is zero
+    f8 = ab.features[:, :8].contiguous()   # 8 channels: the dense tensor is 2.7 GB, not 11 GB
+    d = m.spconv.SparseConvTensor(f8, ab.indices, shape, 1).dense()
+    assert d.shape == (1, 8, 41, 1440, 1440)
+    i = ab.indices.long()
+    assert torch.equal(d[0, :, i[:, 1], i[:, 2], i[:, 3]].t(), f8)
+    assert int((d != 0).sum()) == int((f8 != 0).sum())
+
+
+def test_full_size_encoder_determinism_and_executor_equivalence():
+    cfg, pts, mean, coors, num = full_size_scene()
+    torch.manual_seed(0)
+    enc = registry.build_middle_encoder(cfg.pts_middle_encoder).to(dev())
+    randomize_bn(enc, 9)
+    enc.eval()
+    with torch.no_grad():
+        s1, f1 = enc(mean, coors, 1)
+        s2, f2 = enc(mean, coors, 1)
+        enc.use_executor = False
+        s3, f3 = enc(mean, coors, 1)
+    del enc.use_executor
+    assert torch.equal(s1, s2) and torch.equal(s1, s3)
+    for x, y in zip(f1, f3):
+        assert torch.equal(x.indices, y.indices) and torch.equal(x.features, y.features)
+    assert s1.shape == (1, 256, 180, 180) and bool(torch.isfinite(s1).all())
+    assert [t.spatial_shape for t in f1] == [[41, 1440, 1440], [21, 720, 720], [11, 360, 360], [5, 180, 180],
+                                             [5, 180, 180]]
