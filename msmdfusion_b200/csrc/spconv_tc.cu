@@ -46,14 +46,14 @@ struct TcSmemLayout {
 
 static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
-static TcSmemLayout tc_layout(int N, int kvol, int chunks) {
+static TcSmemLayout tc_layout(int N, int kvol, int chunks, int tiles) {
   TcSmemLayout L;
   L.stage_bytes = 2 * kTcABytes + N * kTcKC * 4 * 2;
   const int misc = round_up(kvol * kTcM * 4, 16) + round_up(2 * chunks, 16) + 256 + 8 * N;
-  // two CTAs per SM when two stages fit in half of the SM's shared memory, else one CTA
-  // with as many stages as fit (max 4)
+  // two CTAs per SM when two stages fit in half of the SM's shared memory AND there are enough
+  // tiles to need the second slot; otherwise one CTA with a deeper pipeline (max 4 stages)
   const int half = 112 * 1024, full = 224 * 1024;
-  if (2 * L.stage_bytes + misc + 1024 <= half) {
+  if (2 * L.stage_bytes + misc + 1024 <= half && tiles > kNumSMs) {
     L.stages = (half - misc - 1024) / L.stage_bytes;
   } else {
     L.stages = (full - misc - 1024) / L.stage_bytes;
@@ -794,7 +794,7 @@ extern "C" MSMD_API int msmd_spconv_fwd_tc_ws(const float* features, int n_in, c
     MSMD_LAUNCH_OK();
     return MSMD_OK;
   }
-  const TcSmemLayout L = tc_layout(g.N, kvol, g.chunks);
+  const TcSmemLayout L = tc_layout(g.N, kvol, g.chunks, tiles);
   MSMD_REQUIRE(L.stages >= 2, "spconv_fwd_tc: tile does not fit in shared memory");
   auto kern = vec ? spconv_fwd_tc_kernel<true> : spconv_fwd_tc_kernel<false>;
   if (!attr_set[vec]) {
