@@ -39,6 +39,7 @@ constexpr int kTcThreads = kTcProducers + 64;             // + B-loader warp + M
 constexpr int kTcM = 128;        // output voxels per tile (UMMA M)
 constexpr int kTcKC = 32;        // floats per K chunk = one 128-byte swizzle row
 constexpr int kTcABytes = kTcM * kTcKC * 4;  // 16 KB per A half (hi or lo)
+constexpr int kTcDepth = 3;      // variant 2: K chunks whose gather loads are in flight per thread
 
 struct TcSmemLayout {
   int stage_bytes, stages, pair_off, act_off, bar_off, total;
@@ -305,17 +306,20 @@ spconv_fwd_tc_kernel(const float* __restrict__ feat, const float* __restrict__ w
       if (lane == 0) tc::mbar_arrive(&full_bar[s]);  // one arrival per warp (256 -> 8 smem atomics)
       ++it;
     };
-    // two register buffers, alternated without copies: while one chunk is split and stored the
-    // loads of the following chunk are already in flight
-    float4 bufa[RPT], bufb[RPT];
-    if (n_act > 0) gather(alist[0], bufa);
-    if (n_act > 1) gather(alist[1], bufb);
-    for (int i = 0; i < n_act; i += 2) {
-      store(bufa);
-      if (i + 2 < n_act) gather(alist[i + 2], bufa);
-      if (i + 1 >= n_act) break;
-      store(bufb);
-      if (i + 3 < n_act) gather(alist[i + 3], bufb);
+    // kTcDepth register buffers rotated without copies: while one chunk is split and stored, the
+    // loads of the next kTcDepth-1 chunks are in flight (the gather is L2-latency bound)
+    float4 buf[kTcDepth][RPT];
+#pragma unroll
+    for (int d = 0; d < kTcDepth; ++d)
+      if (d < n_act) gather(alist[d], buf[d]);
+    for (int i = 0; i < n_act; i += kTcDepth) {
+#pragma unroll
+      for (int d = 0; d < kTcDepth; ++d) {
+        if (i + d < n_act) {
+          store(buf[d]);
+          if (i + d + kTcDepth < n_act) gather(alist[i + d + kTcDepth], buf[d]);
+        }
+      }
     }
 
     // ===== epilogue: TMEM -> registers -> fused BN / residual / ReLU -> global =============
