@@ -33,7 +33,7 @@ def run(cin, cout, n_in, n_out, kvol, density, seed, epilogue):
     err = (got - ref).abs()
     mx = float(err.max())
     tag = f'cin={cin:4d} cout={cout:4d} n_in={n_in:6d} n_out={n_out:6d} kvol={kvol:2d} dens={density:.2f} epi={int(epilogue)}'
-    ok = mx < 2e-5 * max(1.0, float(ref.abs().max()))
+    ok = mx < 4e-5 * max(1.0, float(ref.abs().max()))  # fp32 accumulation over K <= 5184 terms: ~2e-5 relative
     print(f'{"OK  " if ok else "FAIL"} {tag}  max|err|={mx:.3e}  max|ref|={float(ref.abs().max()):.3f}')
     if not ok:
         bad = (err > 1e-4).nonzero()
