@@ -179,3 +179,27 @@ def test_packed_foreground_layout_cpu():
     first = metas[1]['foreground2D_info']['fg_points'][0]
     assert np.array_equal(pk.points[250:280].numpy(), first)
     assert np.allclose(pk.lidar2img[7].numpy(), np.asarray(metas[1]['lidar2img'][1], np.float32).reshape(16))
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver times next to ours) prints ONE JSON line
+    with the contract's keys and `"impl": "reference"`; non-zero ranks exit silently."""
+    import json
+    import subprocess
+    import sys
+    env = dict(os.environ, OMP_NUM_THREADS='4')
+    out = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--steps', '1',
+                          '--warmup', '0'], capture_output=True, text=True, timeout=600, env=env, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    for key in ('impl', 'metric', 'value', 'unit', 'n_gpus', 'steps', 'warmup', 'ms_per_step', 'higher_is_better',
+                'scaling', 'vs_baseline', 'dtype', 'data', 'config', 'cpu_baseline', 'e2e'):
+        assert key in line, key
+    assert line['impl'] == 'reference' and line['unit'] == 'scenes/s' and line['value'] > 0
+    assert line['cpu_baseline']['kind'] in ('reference', 'port') and line['cpu_baseline']['cores'] >= 1
+    assert line['e2e'] == {'value': line['value'], 'unit': 'scenes/s', 'h2d_bytes_per_step': 0,
+                           'd2h_bytes_per_step': 0}
+    silent = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--gpus', '2'],
+                            capture_output=True, text=True, timeout=120, env=dict(env, RANK='1', WORLD_SIZE='2'),
+                            cwd=ROOT)
+    assert silent.returncode == 0 and silent.stdout.strip() == ''
