@@ -23,7 +23,6 @@ Parity pinning ("Oracle"):
   available and no reference test pins results there: "parity unpinned" by the reference for these.
 """
 import ctypes
-import os
 
 import numpy as np
 

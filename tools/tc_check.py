@@ -3,7 +3,6 @@ kernel on random rulebooks.  Prints an error summary per shape; exits non-zero o
 import sys
 import os
 
-import numpy as np
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
