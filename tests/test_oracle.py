@@ -296,3 +296,51 @@ def test_oracle_conv_matches_reference_spconv1x_live():
             assert list(es) == list(oshape)
         assert np.array_equal(oi, ei)
         assert np.abs(of - cpu.spconv_fwd(feat, w, pair)).max() < 1e-5
+
+
+# --------------------------------------------------------------------------------------
+# voxel_modality_split: the reference's own numba merge, executed from where it lies
+# --------------------------------------------------------------------------------------
+REF_DETECTOR = '/root/reference/mmdet3d/models/detectors/MSMDFusion.py'
+
+
+def reference_type_assign():
+    """Compile the reference's `type_assign` (MSMDFusion.py:26-45) from its own source text at test
+    time -- the module itself cannot be imported here (mmcv / mmdet / spconv are absent)."""
+    import numba  # noqa: F401
+    lines = open(REF_DETECTOR).read().splitlines()
+    start = next(i for i, ln in enumerate(lines) if ln.startswith('def type_assign'))
+    end = next(i for i in range(start + 1, len(lines)) if lines[i].startswith('class ') or lines[i].startswith('def '))
+    ns = {}
+    exec('from numba import jit\nimport numpy as np\n@jit(nopython=True)\n' + '\n'.join(lines[start:end]), ns)
+    return ns['type_assign']
+
+
+@pytest.mark.skipif(not os.path.exists(REF_DETECTOR), reason='reference tree not mounted')
+def test_modality_split_matches_reference_type_assign_live():
+    """oracle.cpu.type_assign / voxel_modality_split against the reference's numba merge and the
+    reference's key / sort expressions (MSMDFusion.py:271-275) evaluated with torch on the CPU."""
+    ref_assign = reference_type_assign()
+    rng = np.random.default_rng(31)
+    shape = [41, 300, 300]
+    i3, _ = random_sparse(rng, 1, shape, 4000, 1)
+    i2, _ = random_sparse(rng, 1, shape, 3000, 1)
+    i2[:900] = i3[rng.choice(4000, 900, replace=False)]
+    i2[900:930, 3] += 1      # x-neighbours: collide under the float32 key for z >= 17
+    c3, c2 = torch.from_numpy(i3[:, 1:]), torch.from_numpy(i2[:, 1:])
+    k3 = c3[:, 0] * 1e6 + c3[:, 1] * 1e3 + c3[:, 2]          # :271 (int32 tensor * python float)
+    k2 = c2[:, 0] * 1e6 + c2[:, 1] * 1e3 + c2[:, 2]
+    assert np.array_equal(k3.numpy(), cpu.float_key(i3[:, 1:])) and k3.dtype == torch.float32
+    v3, ind3 = torch.sort(k3, dim=-1, stable=True)           # :274 (stable: one legal outcome)
+    v2, ind2 = torch.sort(k2, dim=-1, stable=True)
+    t3, t2 = ref_assign(v3.numpy(), v2.numpy(), np.zeros_like(v3.numpy()), np.zeros_like(v2.numpy()))
+    o3, o2 = cpu.type_assign(v3.numpy(), v2.numpy())
+    assert np.array_equal(t3, o3) and np.array_equal(t2, o2) and t3.sum() >= 900
+    # full restatement: mix flags and the matched row ids in sorted-key order
+    e3, e2, s3, s2 = cpu.voxel_modality_split(i3, i2, 1)
+    mix3 = np.zeros(i3.shape[0], np.int32)
+    mix3[ind3.numpy()] = t3.astype(np.int32)
+    mix2 = np.zeros(i2.shape[0], np.int32)
+    mix2[ind2.numpy()] = t2.astype(np.int32)
+    assert np.array_equal(e3[:, 1], mix3) and np.array_equal(e2[:, 1], mix2)
+    assert np.array_equal(s3, ind3.numpy()[np.nonzero(t3)[0]]) and np.array_equal(s2, ind2.numpy()[np.nonzero(t2)[0]])
