@@ -464,6 +464,18 @@ def test_fps_nn_fast_matches_oracle(Q, fps_num, radius, nsample, thresh):
     assert got.dtype == np.int64 and np.array_equal(got, exp)
 
 
+@pytest.mark.parametrize('name', ['assign_scale0', 'assign_scale1', 'assign_scale2', 'assign_scale3', 'assign_direct'])
+def test_fps_nn_fast_matches_reference_golden(name):
+    """CUDA path against committed outputs of the reference's OWN `fps_NN_fast` method body
+    (sparse_multimodal_encoder_painting.py:276-323; fixtures by tests/golden/make_golden_assign.py)."""
+    from msmdfusion_b200 import fusion_encoder
+    g = np.load(os.path.join(GOLDEN, name + '.npz'))
+    fps_num, radius, nsample, thresh = g['params']
+    got = fusion_encoder.fps_nn_fast(cuda(g['query']), cuda(g['key']), int(fps_num), float(radius), int(nsample),
+                                     float(thresh)).cpu().numpy()
+    assert got.dtype == np.int64 and np.array_equal(got, g['assign'])
+
+
 def test_modality_split_bit_exact():
     rng = np.random.default_rng(5)
     shape = [41, 1440, 1440]
@@ -487,6 +499,16 @@ def test_modality_split_bit_exact():
         assert np.array_equal(syn3.cpu().numpy(), es3 + 7)
         assert np.array_equal(syn2.cpu().numpy(), es2 + 11)
         assert syn3.shape[0] >= 6000
+
+
+@pytest.mark.parametrize('name', ['split_dense_overlap', 'split_lidar_grid', 'split_disjoint'])
+def test_modality_split_matches_reference_golden(name):
+    """CUDA path against committed outputs of the reference's OWN numba merge + float-key / sort
+    expressions (MSMDFusion.py:26-45,271-300; fixtures by tests/golden/make_golden_split.py)."""
+    g = np.load(os.path.join(GOLDEN, name + '.npz'))
+    mix3, mix2, syn3, syn2 = ops.modality_split_single(cuda(g['indices3']), cuda(g['indices2']))
+    assert np.array_equal(mix3.cpu().numpy(), g['mix3']) and np.array_equal(mix2.cpu().numpy(), g['mix2'])
+    assert np.array_equal(syn3.cpu().numpy(), g['syn3']) and np.array_equal(syn2.cpu().numpy(), g['syn2'])
 
 
 def test_modality_split_empty_sets():
@@ -582,6 +604,47 @@ def test_depth_canvas_matches_oracle():
         torch.nn.functional.interpolate = orig
     assert [tuple(o.shape) for o in out] == [(12, 49, 112, 200), (12, 49, 56, 100), (12, 49, 28, 50)]
     assert np.array_equal(captured['canvas'].cpu().numpy(), omodel.depth_canvas(metas, H, W))
+
+
+def test_lift_matches_reference_golden():
+    """CUDA lift (msmd_lift_gather through MSMDFusionDetector.get_foreground2D) and the depth canvas
+    against committed outputs of the reference's OWN methods (MSMDFusion.py:169-238, 335-356; fixtures by
+    tests/golden/make_golden_lift.py, inputs rebuilt from the seeded synthetic scene)."""
+    import importlib.util
+    import zlib
+    spec = importlib.util.spec_from_file_location('make_golden_lift', os.path.join(GOLDEN, 'make_golden_lift.py'))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    metas, feat, score_w, score_b = mod.lift_inputs()
+    g = np.load(os.path.join(GOLDEN, 'lift_reference.npz'))
+    assert mod.inputs_crc(metas, feat, score_w, score_b) == int(g['inputs_crc'][0]), 'synthetic generator drifted'
+    det, _ = build_msmd_detector()
+    with torch.no_grad():
+        det.score_net[0].weight.copy_(cuda(score_w).view(1, -1))
+        det.score_net[0].bias.fill_(float(score_b))
+        fg = det.get_foreground2D(cuda(feat), metas)
+    for b, a in enumerate(fg):
+        a = a.cpu().numpy()
+        assert a.shape[0] == int(g['count%d' % b][0])
+        assert zlib.crc32(np.ascontiguousarray(a[:, :15]).tobytes()) == int(g['points_crc%d' % b][0])
+        assert feat_err(a[::mod.ROW_STEP], g['rows%d' % b]) < FEAT_TOL
+    captured = {}
+    orig = torch.nn.functional.interpolate
+
+    def spy(canvas, size, mode='nearest', **kw):
+        captured.setdefault('canvas', canvas.clone())
+        return orig(canvas, size, mode=mode, **kw)
+    feats = [cuda(f) for f in synthetic.fpn_features(0, batch=2)]
+    torch.nn.functional.interpolate = spy
+    try:
+        with torch.no_grad():
+            det.depth_aware_channel_compression(feats, metas)
+    finally:
+        torch.nn.functional.interpolate = orig
+    canvas = captured['canvas'].cpu().numpy().reshape(-1)
+    nz = np.nonzero(canvas)[0]
+    assert canvas.shape[0] == int(g['canvas_size'][0])
+    assert np.array_equal(nz, g['canvas_index']) and np.array_equal(canvas[nz], g['canvas_value'])
 
 
 @pytest.mark.parametrize('batch', [1, 2])

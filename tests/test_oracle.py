@@ -301,46 +301,304 @@ def test_oracle_conv_matches_reference_spconv1x_live():
 # --------------------------------------------------------------------------------------
 # voxel_modality_split: the reference's own numba merge, executed from where it lies
 # --------------------------------------------------------------------------------------
-REF_DETECTOR = '/root/reference/mmdet3d/models/detectors/MSMDFusion.py'
+def split_case(seed, shape, n3, n2, shared):
+    rng = np.random.default_rng(seed)
+    i3, _ = random_sparse(rng, 1, shape, n3, 1)
+    i2, _ = random_sparse(rng, 1, shape, n2, 1)
+    i2[:shared] = i3[rng.choice(i3.shape[0], shared, replace=False)]
+    i2[shared:shared + 30, 3] += 1      # x-neighbours: collide under the float32 key for z >= 17
+    return i3, i2[rng.permutation(i2.shape[0])]
 
 
-def reference_type_assign():
-    """Compile the reference's `type_assign` (MSMDFusion.py:26-45) from its own source text at test
-    time -- the module itself cannot be imported here (mmcv / mmdet / spconv are absent)."""
-    import numba  # noqa: F401
-    lines = open(REF_DETECTOR).read().splitlines()
-    start = next(i for i, ln in enumerate(lines) if ln.startswith('def type_assign'))
-    end = next(i for i in range(start + 1, len(lines)) if lines[i].startswith('class ') or lines[i].startswith('def '))
-    ns = {}
-    exec('from numba import jit\nimport numpy as np\n@jit(nopython=True)\n' + '\n'.join(lines[start:end]), ns)
-    return ns['type_assign']
-
-
-@pytest.mark.skipif(not os.path.exists(REF_DETECTOR), reason='reference tree not mounted')
+@pytest.mark.skipif(not __import__('oracle.ref_split', fromlist=['x']).available(), reason='reference tree not mounted')
 def test_modality_split_matches_reference_type_assign_live():
     """oracle.cpu.type_assign / voxel_modality_split against the reference's numba merge and the
     reference's key / sort expressions (MSMDFusion.py:271-275) evaluated with torch on the CPU."""
-    ref_assign = reference_type_assign()
-    rng = np.random.default_rng(31)
-    shape = [41, 300, 300]
-    i3, _ = random_sparse(rng, 1, shape, 4000, 1)
-    i2, _ = random_sparse(rng, 1, shape, 3000, 1)
-    i2[:900] = i3[rng.choice(4000, 900, replace=False)]
-    i2[900:930, 3] += 1      # x-neighbours: collide under the float32 key for z >= 17
-    c3, c2 = torch.from_numpy(i3[:, 1:]), torch.from_numpy(i2[:, 1:])
-    k3 = c3[:, 0] * 1e6 + c3[:, 1] * 1e3 + c3[:, 2]          # :271 (int32 tensor * python float)
-    k2 = c2[:, 0] * 1e6 + c2[:, 1] * 1e3 + c2[:, 2]
-    assert np.array_equal(k3.numpy(), cpu.float_key(i3[:, 1:])) and k3.dtype == torch.float32
-    v3, ind3 = torch.sort(k3, dim=-1, stable=True)           # :274 (stable: one legal outcome)
-    v2, ind2 = torch.sort(k2, dim=-1, stable=True)
-    t3, t2 = ref_assign(v3.numpy(), v2.numpy(), np.zeros_like(v3.numpy()), np.zeros_like(v2.numpy()))
-    o3, o2 = cpu.type_assign(v3.numpy(), v2.numpy())
-    assert np.array_equal(t3, o3) and np.array_equal(t2, o2) and t3.sum() >= 900
-    # full restatement: mix flags and the matched row ids in sorted-key order
-    e3, e2, s3, s2 = cpu.voxel_modality_split(i3, i2, 1)
-    mix3 = np.zeros(i3.shape[0], np.int32)
-    mix3[ind3.numpy()] = t3.astype(np.int32)
-    mix2 = np.zeros(i2.shape[0], np.int32)
-    mix2[ind2.numpy()] = t2.astype(np.int32)
-    assert np.array_equal(e3[:, 1], mix3) and np.array_equal(e2[:, 1], mix2)
-    assert np.array_equal(s3, ind3.numpy()[np.nonzero(t3)[0]]) and np.array_equal(s2, ind2.numpy()[np.nonzero(t2)[0]])
+    from oracle import ref_split
+    i3, i2 = split_case(31, [41, 300, 300], 4000, 3000, 900)
+    k3, k2 = np.sort(cpu.float_key(i3[:, 1:])), np.sort(cpu.float_key(i2[:, 1:]))
+    o3, o2 = cpu.type_assign(k3, k2)
+    r3, r2 = ref_split.type_assign()(k3, k2, np.zeros_like(k3), np.zeros_like(k2))
+    assert np.array_equal(r3, o3) and np.array_equal(r2, o2) and r3.sum() >= 900
+    # the float key itself: int32 tensor * python float, as MSMDFusion.py:271 writes it
+    c3 = torch.from_numpy(i3[:, 1:])
+    t3 = c3[:, 0] * 1e6 + c3[:, 1] * 1e3 + c3[:, 2]
+    assert t3.dtype == torch.float32 and np.array_equal(t3.numpy(), cpu.float_key(i3[:, 1:]))
+
+
+@pytest.mark.skipif(not __import__('oracle.ref_split', fromlist=['x']).available(), reason='reference tree not mounted')
+@pytest.mark.parametrize('batch', [1, 2])
+def test_modality_split_matches_reference_method_live(batch):
+    """oracle.cpu.voxel_modality_split against MSMDFusionDetector.voxel_modality_split itself
+    (MSMDFusion.py:251-325, whole method run in place): the (b, mix, z, y, x) index tensors and the
+    batch-offset synchronisation indices, including duplicate rows and float32-key collisions."""
+    from oracle import ref_split
+    parts3, parts2 = [], []
+    for b in range(batch):
+        i3, i2 = split_case(40 + b, [41, 300, 300], 4000 - 500 * b, 3000 + 300 * b, 900)
+        i2[50:60] = i2[40:50]
+        i3[:, 0] = b
+        i2[:, 0] = b
+        parts3.append(i3)
+        parts2.append(i2)
+    i3, i2 = np.concatenate(parts3), np.concatenate(parts2)
+    r3, r2, rs3, rs2 = ref_split.voxel_modality_split(i3, i2, batch)
+    e3, e2, es3, es2 = cpu.voxel_modality_split(i3, i2, batch)
+    assert r3.dtype == np.int32 and r3.shape == (i3.shape[0], 5)
+    assert np.array_equal(r3, e3) and np.array_equal(r2, e2)
+    assert rs3.dtype == np.int64 and np.array_equal(rs3, es3) and np.array_equal(rs2, es2)
+    assert rs3.shape[0] >= 900 * batch
+
+
+@pytest.mark.parametrize('name', ['split_dense_overlap', 'split_lidar_grid', 'split_disjoint'])
+def test_modality_split_matches_reference_golden(name):
+    """Committed outputs of the reference's own merge (tests/golden/make_golden_split.py)."""
+    g = np.load(os.path.join(GOLDEN, name + '.npz'))
+    e3, e2, s3, s2 = cpu.voxel_modality_split(g['indices3'], g['indices2'], 1)
+    assert np.array_equal(e3[:, 1], g['mix3']) and np.array_equal(e2[:, 1], g['mix2'])
+    assert np.array_equal(s3, g['syn3']) and np.array_equal(s2, g['syn2'])
+
+
+# --------------------------------------------------------------------------------------
+# fps_NN_fast: the reference's own method body, executed from where it lies
+# --------------------------------------------------------------------------------------
+ASSIGN_CASES = ['assign_scale0', 'assign_scale1', 'assign_scale2', 'assign_scale3', 'assign_direct']
+
+
+@pytest.mark.skipif(not __import__('oracle.ref_assign', fromlist=['x']).available(), reason='reference tree not mounted')
+@pytest.mark.parametrize('Q,K,fps_num,radius,nsample,thresh', [(300, 500, 512, 2., 8, 3.), (3000, 2000, 512, 3., 16, 4.),
+                                                              (5000, 3000, 1024, 2., 8, 1.5), (2500, 40, 256, 6., 32, 8.)])
+def test_fps_nn_fast_matches_reference_method_live(Q, K, fps_num, radius, nsample, thresh):
+    """oracle.cpu.fps_nn_fast against `SparseMultiModalEncoderPaint.fps_NN_fast` itself
+    (sparse_multimodal_encoder_painting.py:276-323): distance matrix, first-minimum tie-break, threshold
+    and the duplicate-index scatter are the reference's code run by torch (oracle/ref_assign.py)."""
+    from oracle import ref_assign
+    rng = np.random.default_rng(Q + K)
+    both, _ = random_sparse(rng, 1, [11, 60, 60], Q + K, 1)
+    q, k = both[:Q], both[Q:]
+    got = cpu.fps_nn_fast(q, k, fps_num, radius, nsample, thresh)
+    exp = ref_assign.fps_nn_fast(q, k, fps_num, radius, nsample, thresh)
+    assert exp.dtype == np.int64 and np.array_equal(got, exp) and (exp >= 0).any()
+
+
+@pytest.mark.parametrize('name', ASSIGN_CASES)
+def test_fps_nn_fast_matches_reference_golden(name):
+    """Committed outputs of the reference's own method (tests/golden/make_golden_assign.py) at the four
+    scales' parameters of configs/MSMDFusion_nusc_voxel_LC.py:146-149."""
+    g = np.load(os.path.join(GOLDEN, name + '.npz'))
+    fps_num, radius, nsample, thresh = g['params']
+    got = cpu.fps_nn_fast(g['query'], g['key'], int(fps_num), float(radius), int(nsample), float(thresh))
+    assert np.array_equal(got, g['assign'])
+
+
+# --------------------------------------------------------------------------------------
+# 2D -> 3D lift: the reference's own get_foreground2D / depth canvas, executed from where they lie
+# --------------------------------------------------------------------------------------
+def load_lift_golden():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location('make_golden_lift', os.path.join(GOLDEN, 'make_golden_lift.py'))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    metas, feat, score_w, score_b = mod.lift_inputs()
+    g = np.load(os.path.join(GOLDEN, 'lift_reference.npz'))
+    assert mod.inputs_crc(metas, feat, score_w, score_b) == int(g['inputs_crc'][0]), 'synthetic generator drifted'
+    return mod, g, metas, feat, score_w, score_b
+
+
+@pytest.mark.skipif(not __import__('oracle.ref_lift', fromlist=['x']).available(), reason='reference tree not mounted')
+def test_lift_matches_reference_methods_live():
+    """oracle.model.get_foreground2d / depth_canvas against MSMDFusionDetector.get_foreground2D and
+    .depth_aware_channel_compression (MSMDFusion.py:169-238, 335-369) run by torch (oracle/ref_lift.py)."""
+    from oracle import model as omodel, ref_lift
+    mod, _, metas, feat, score_w, score_b = load_lift_golden()
+    # gate == 1 (w = 0, b = 1): pixel truncation, the (h, w) gather, camera / sample order, the empty
+    # camera and the concatenation are compared bit for bit
+    zero_w = np.zeros_like(score_w)
+    for a, b in zip(ref_lift.get_foreground2d(feat, metas, zero_w, np.float32(1)),
+                    omodel.get_foreground2d(feat, metas, zero_w, np.float32(1))):
+        assert a.shape == b.shape and np.array_equal(a, b)
+    # learned gate: the 66-term dot product is summed in a different order (torch addmm vs numpy)
+    for a, b in zip(ref_lift.get_foreground2d(feat, metas, score_w, score_b),
+                    omodel.get_foreground2d(feat, metas, score_w, score_b)):
+        assert np.array_equal(a[:, :15], b[:, :15])
+        assert np.abs(a - b).max() <= 2e-6 * max(1.0, np.abs(a).max())
+        assert np.array_equal((a[:, 15:] != 0).any(1), (b[:, 15:] != 0).any(1))
+    H, W = synthetic.INPUT_SHAPE
+    shapes = [(H // s, W // s) for s in (4, 8, 16)]
+    canvas = torch.from_numpy(omodel.depth_canvas(metas, H, W))
+    for (h, w), ref in zip(shapes, ref_lift.depth_maps(shapes, metas)):
+        assert np.array_equal(ref, F.interpolate(canvas, (h, w), mode='bilinear').numpy())
+
+
+def test_lift_matches_reference_golden():
+    from oracle import model as omodel
+    mod, g, metas, feat, score_w, score_b = load_lift_golden()
+    for b, a in enumerate(omodel.get_foreground2d(feat, metas, score_w, score_b)):
+        assert a.shape[0] == int(g['count%d' % b][0])
+        assert zlib.crc32(np.ascontiguousarray(a[:, :15]).tobytes()) == int(g['points_crc%d' % b][0])
+        ref = g['rows%d' % b]
+        assert np.abs(a[::mod.ROW_STEP] - ref).max() <= 2e-6 * max(1.0, np.abs(ref).max())
+    H, W = synthetic.INPUT_SHAPE
+    canvas = omodel.depth_canvas(metas, H, W).reshape(-1)
+    assert canvas.shape[0] == int(g['canvas_size'][0])
+    nz = np.nonzero(canvas)[0]
+    assert np.array_equal(nz, g['canvas_index']) and np.array_equal(canvas[nz], g['canvas_value'])
+
+
+# --------------------------------------------------------------------------------------
+# GMA encoder glue: the reference's own grouped_sparse_conv / forward, executed from where they lie
+# --------------------------------------------------------------------------------------
+@pytest.mark.skipif(not __import__('oracle.ref_encoder', fromlist=['x']).available(), reason='reference tree not mounted')
+def test_multimodal_encoder_matches_reference_glue_live():
+    """oracle.model.multimodal_encoder against SparseMultiModalEncoderPaint.forward /
+    .grouped_sparse_conv / .pad_missing_batch_id / .fps_NN_fast themselves
+    (sparse_multimodal_encoder_painting.py:208-225, 276-459), run by torch around the oracle's conv
+    restatement (oracle/ref_encoder.py).  Batch of 2 with an empty camera: the per-sample assignment
+    loop, its `base` offset, the dummy-embedding row and the batch padding are all on the path."""
+    import msmdfusion_b200 as m
+    from oracle import model as omodel, ref_encoder
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cfg = m.Config.fromfile(os.path.join(root, 'configs', 'msmd_lc_hotpath.py')).hotpath
+    torch.manual_seed(0)
+    det = m.MSMDFusionDetector(**{k: cfg[k] for k in (
+        'pts_voxel_layer', 'pts_voxel_encoder', 'pts_middle_encoder', 'multimodal_middle_encoder',
+        'spatial_shapes', 'downscale_factors', 'fps_num_list', 'radius_list', 'max_cluster_samples_list',
+        'dist_thresh_list')}).eval()
+    gen = torch.Generator().manual_seed(9)
+    for mod in det.modules():   # non-trivial eval-mode statistics
+        if isinstance(mod, torch.nn.BatchNorm1d):
+            mod.running_mean.copy_(torch.randn(mod.num_features, generator=gen) * 0.1)
+            mod.running_var.copy_(torch.rand(mod.num_features, generator=gen) + 0.5)
+    sd = det.state_dict()
+    B = 2
+    scenes = [synthetic.lidar_scene(5 + b, 1)[:4000] for b in range(B)]
+    metas = [synthetic.camera_scene(5 + b, scenes[b], virtual_per_camera=2500 if b == 0 else 150, real_per_camera=50,
+                                    empty_cameras=(() if b == 0 else (1,))) for b in range(B)]
+    ev, en, ec = omodel.voxelize_batch(scenes, synthetic.VOXEL_SIZE, synthetic.POINT_CLOUD_RANGE, 10, 160000)
+    _, e_feats, _ = omodel.sparse_encoder(sd, dict(cfg.pts_middle_encoder), cpu.hard_simple_vfe(ev, en, 5), ec, B,
+                                          prefix='pts_middle_encoder.')
+    rng = np.random.default_rng(0)
+    H, W = synthetic.INPUT_SHAPE
+    comp = [np.abs(rng.standard_normal((6 * B, 49, H // s, W // s))).astype(np.float32) for s in (4, 8, 16)]
+    img_list = [comp[0]] + comp
+    v3l, v2l, s3l, s2l = [], [], [], []
+    for i in range(4):
+        v2 = omodel.fetch_2d_voxels(img_list[i], metas, np.full((66,), 0.01, np.float32), 0.0, cfg.spatial_shapes[i],
+                                    cfg.downscale_factors[i], synthetic.VOXEL_SIZE, synthetic.POINT_CLOUD_RANGE,
+                                    10, 160000)
+        c3, c2, s3, s2 = cpu.voxel_modality_split(e_feats[i].indices, v2.indices, B)
+        v3l.append(omodel.SpTensor(e_feats[i].features, c3, e_feats[i].spatial_shape, B))
+        v2l.append(omodel.SpTensor(v2.features, c2, v2.spatial_shape, B))
+        s3l.append(s3)
+        s2l.append(s2)
+    assert sum(s.shape[0] for s in s3l) > 100
+    fps = [256] * 4     # smaller than most only-2D sets: the FPS + ball-query branch runs at every scale
+    args = (v3l, v2l, s3l, s2l, fps, cfg.radius_list, cfg.max_cluster_samples_list, cfg.dist_thresh_list)
+    torch.manual_seed(77)
+    dummies = [torch.rand(1, c).numpy() for c in cfg.multimodal_middle_encoder['in_channels_3D']]
+    mine = omodel.multimodal_encoder(sd, dict(cfg.multimodal_middle_encoder), *args, dummies,
+                                     prefix='multimodal_middle_encoder.')
+    ref = ref_encoder.forward(sd, dict(cfg.multimodal_middle_encoder), *args, 77, prefix='multimodal_middle_encoder.')
+    for a, b in zip(ref, mine):
+        assert a.spatial_shape == b.spatial_shape and np.array_equal(a.indices, b.indices)
+        # the two gate MLPs run through torch addmm there and numpy matmul here
+        assert np.abs(a.features - b.features).max() <= 2e-6 * max(1.0, np.abs(a.features).max())
+
+
+# --------------------------------------------------------------------------------------
+# LiDAR SparseEncoder: the reference's own class, executed from where it lies
+# --------------------------------------------------------------------------------------
+ENCODER_CFGS = {
+    # configs/MSMDFusion_nusc_voxel_LC.py / transfusion_nusc_voxel_L.py pts_middle_encoder
+    'basicblock': dict(type='SparseEncoder', in_channels=5, sparse_shape=[41, 1440, 1440], output_channels=128,
+                       order=('conv', 'norm', 'act'),
+                       encoder_channels=((16, 16, 32), (32, 32, 64), (64, 64, 128), (128, 128)),
+                       encoder_paddings=((0, 0, 1), (0, 0, 1), (0, 0, [0, 1, 1]), (0, 0)), block_type='basicblock'),
+    # the class defaults (SECOND-style conv_module stack)
+    'conv_module': dict(type='SparseEncoder', in_channels=4, sparse_shape=[41, 400, 352]),
+}
+
+
+def assert_same_layer_table(net, table):
+    """`table`: [(qualified name, spec)] recorded by the reference's own constructor (oracle/ref_stubs.py);
+    `net`: this package's module -- same names, same conv type / channels / kernel / stride / padding."""
+    from msmdfusion_b200 import spconv as sp
+    from msmdfusion_b200.sparse_block import SparseBasicBlock
+    ours = dict(net.named_modules())
+    triple = lambda v: [v] * 3 if isinstance(v, int) else list(v)  # noqa: E731
+    for name, spec in table:
+        mod = ours[name]
+        if spec['kind'] == 'basicblock':
+            assert isinstance(mod, SparseBasicBlock)
+            assert mod.conv1.in_channels == spec['cin'] and mod.conv2.out_channels == spec['cout']
+            assert isinstance(mod.conv1, sp.SubMConv3d) and isinstance(mod.conv2, sp.SubMConv3d)
+            continue
+        conv, bn, act = list(mod.children())
+        assert type(conv).__name__ == spec['conv_type'] and isinstance(bn, torch.nn.BatchNorm1d)
+        assert isinstance(act, torch.nn.ReLU) and bn.eps == spec['eps']
+        assert (conv.in_channels, conv.out_channels) == (spec['cin'], spec['cout'])
+        assert list(conv.kernel_size) == triple(spec['ksize']) and list(conv.stride) == triple(spec['stride'])
+        assert list(conv.padding) == triple(spec['padding']) and conv.indice_key == spec['indice_key']
+    assert {n for n, mod in ours.items() if isinstance(mod, SparseBasicBlock) or
+            (isinstance(mod, sp.SparseSequential) and any(isinstance(c, sp.SparseConvolution) for c in mod.children()))
+            } == {n for n, _ in table}
+
+
+@pytest.mark.skipif(not __import__('oracle.ref_lidar_encoder', fromlist=['x']).available(), reason='reference tree not mounted')
+@pytest.mark.parametrize('kind', list(ENCODER_CFGS))
+def test_sparse_encoder_layer_table_matches_reference_class_live(kind):
+    """The layer table the reference's own SparseEncoder constructor lays out (sparse_encoder.py:31-209,
+    run in place by oracle/ref_lidar_encoder.py) against this package's module tree: same qualified
+    names, same conv type / channels / kernel / stride / padding at every position."""
+    import msmdfusion_b200 as m
+    from oracle import ref_lidar_encoder
+    cfg = ENCODER_CFGS[kind]
+    ours = m.SparseEncoder(**{k: v for k, v in cfg.items() if k != 'type'})
+    table = ref_lidar_encoder.layer_table(cfg)
+    assert len(table) == (13 if kind == 'basicblock' else 12)
+    assert_same_layer_table(ours, table)
+
+
+@pytest.mark.skipif(not __import__('oracle.ref_lidar_encoder', fromlist=['x']).available(), reason='reference tree not mounted')
+@pytest.mark.parametrize('kind', list(ENCODER_CFGS))
+def test_sparse_encoder_forward_matches_reference_class_live(kind):
+    """oracle.model.sparse_encoder against the reference's SparseEncoder.forward (sparse_encoder.py:96-133)
+    run in place around the oracle's conv restatement: same encode_features in the same order, same dense
+    (N, C*D, H, W) view."""
+    import msmdfusion_b200 as m
+    from oracle import model as omodel, ref_lidar_encoder
+    cfg = dict(ENCODER_CFGS[kind])
+    cfg['sparse_shape'] = [41, 96, 96]
+    torch.manual_seed(3)
+    net = m.SparseEncoder(**{k: v for k, v in cfg.items() if k != 'type'}).eval()
+    sd = net.state_dict()
+    rng = np.random.default_rng(8)
+    idx, feat = random_sparse(rng, 2, cfg['sparse_shape'], 3000, cfg['in_channels'])
+    e_spatial, e_feats, _ = omodel.sparse_encoder(sd, cfg, feat, idx, 2)
+    r_spatial, r_feats = ref_lidar_encoder.forward(sd, cfg, feat, idx, 2)
+    assert r_spatial.shape == e_spatial.shape and np.array_equal(r_spatial, e_spatial)
+    assert len(r_feats) == len(e_feats) == 5
+    for a, b in zip(r_feats, e_feats):
+        assert a.spatial_shape == b.spatial_shape and np.array_equal(a.indices, b.indices)
+        assert np.array_equal(a.features, b.features)
+
+
+@pytest.mark.skipif(not __import__('oracle.ref_encoder', fromlist=['x']).available(), reason='reference tree not mounted')
+def test_multimodal_encoder_layout_matches_reference_class_live():
+    """Module layout of the reference's own SparseMultiModalEncoderPaint constructor
+    (sparse_multimodal_encoder_painting.py:99-205, run in place) against this package's class: the 20
+    sparse-conv blocks by qualified name and the gate MLPs' state-dict keys and shapes."""
+    import msmdfusion_b200 as m
+    from oracle import ref_encoder
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cfg = dict(m.Config.fromfile(os.path.join(root, 'configs', 'msmd_lc_hotpath.py')).hotpath.multimodal_middle_encoder)
+    ref = ref_encoder.build(cfg)
+    ours = m.SparseMultiModalEncoderPaint(**{k: v for k, v in cfg.items() if k != 'type'})
+    table = ref_encoder.ref_stubs.layer_table(ref)
+    assert len(table) == 20
+    assert_same_layer_table(ours, table)
+    gates = {k: tuple(v.shape) for k, v in ref.state_dict().items()}
+    assert len(gates) == 16 and all(k.startswith(('gate_control.', 'cross_gate_control.')) for k in gates)
+    mine = {k: tuple(v.shape) for k, v in ours.state_dict().items()}
+    assert all(mine[k] == shape for k, shape in gates.items())
+    assert {k for k in mine if 'gate_control' in k} == set(gates)
