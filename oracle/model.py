@@ -234,3 +234,63 @@ def multimodal_encoder(sd, cfg, v3_list, v2_list, syn3_list, syn2_list, fps_num_
         outs.append(convmodule(sd, f'{prefix}downscale_blocks.stage_{s + 1}', x, 'SparseConv3d', ksz[s],
                                strides[s], pads[s], eps))
     return outs
+
+
+# --------------------------------------------------------------------------------------
+# Detector level: MSMDFusionDetector.extract_pts_feat up to the tensor bev_fusion consumes
+# --------------------------------------------------------------------------------------
+def depth_aware_channel_compression(sd, feat_list, img_metas, prefix=''):
+    """MSMDFusion.py:335-369.  The dense image-plane part (bilinear resample, Conv2d + BatchNorm2d(eval)
+    + ReLU of `conv1x1_blocks`, :108-125) is not a kernel of this project: it is evaluated with plain
+    torch fp32 ops on the CPU.  feat_list: three (B*6, 256, h, w) arrays -> three (B*6, 49, h, w)."""
+    import torch
+    import torch.nn.functional as F
+    H, W = img_metas[0]['pad_shape'][:2]
+    canvas = torch.from_numpy(depth_canvas(img_metas, H, W))
+    out = []
+    for i, feat in enumerate(feat_list):
+        feat = torch.from_numpy(np.ascontiguousarray(feat, np.float32))
+        depth = F.interpolate(canvas, feat.shape[-2:], mode='bilinear')
+        w = torch.from_numpy(_np(sd, f'{prefix}conv1x1_blocks.{i}.0.weight').astype(np.float32))
+        bn = [torch.from_numpy(_np(sd, f'{prefix}conv1x1_blocks.{i}.1.{k}').astype(np.float32))
+              for k in ('running_mean', 'running_var', 'weight', 'bias')]
+        y = F.conv2d(torch.cat([feat, depth], 1), w, padding=w.shape[-1] // 2)
+        out.append(torch.relu(F.batch_norm(y, bn[0], bn[1], bn[2], bn[3], False, 0.0, 1e-3)).numpy())
+    return out
+
+
+def extract_voxel_space(sd, cfg, scenes, fpn_feats, img_metas, dummy_embeddings, compressed=None):
+    """MSMDFusion.py:421-445 with extract_multiscale_voxel_feat (:400-419) inlined: voxelize ->
+    HardSimpleVFE -> SparseEncoder -> (depth-aware compression -> 4x fetch_2D_voxels -> modality split) ->
+    SparseMultiModalEncoderPaint -> dense -> cat.  `cfg`: the hot-path config (configs/msmd_lc_hotpath.py).
+    `compressed`: the three compressed image features if the caller already has them.
+    -> (bev (B, 256+384, 180, 180), [SpTensor] stage_outs, compressed)."""
+    B = len(scenes)
+    vl = cfg['pts_voxel_layer']
+    max_voxels = vl['max_voxels'][1] if isinstance(vl['max_voxels'], (tuple, list)) else vl['max_voxels']
+    ev, en, ec = voxelize_batch(scenes, vl['voxel_size'], vl['point_cloud_range'], vl['max_num_points'], max_voxels)
+    mean = cpu.hard_simple_vfe(ev, en, cfg['pts_voxel_encoder']['num_features'])
+    spatial, feats, _ = sparse_encoder(sd, dict(cfg['pts_middle_encoder']), mean, ec, B, prefix='pts_middle_encoder.')
+    if compressed is None:
+        compressed = depth_aware_channel_compression(sd, fpn_feats, img_metas)
+    img_list = [compressed[0]] + list(compressed)                        # :404-405
+    score_w = _np(sd, 'score_net.0.weight').reshape(-1)
+    score_b = float(_np(sd, 'score_net.0.bias').reshape(-1)[0])
+    v3l, v2l, s3l, s2l = [], [], [], []
+    for i in range(4):
+        v2 = fetch_2d_voxels(img_list[i], img_metas, score_w, score_b, cfg['spatial_shapes'][i],
+                             cfg['downscale_factors'][i], vl['voxel_size'], vl['point_cloud_range'],
+                             vl['max_num_points'], max_voxels)
+        v3 = feats[i]
+        c3, c2, s3, s2 = cpu.voxel_modality_split(v3.indices, v2.indices, B)
+        v3l.append(SpTensor(v3.features, c3, v3.spatial_shape, B))
+        v2l.append(SpTensor(v2.features, c2, v2.spatial_shape, B))
+        s3l.append(s3)
+        s2l.append(s2)
+    outs = multimodal_encoder(sd, dict(cfg['multimodal_middle_encoder']), v3l, v2l, s3l, s2l, cfg['fps_num_list'],
+                              cfg['radius_list'], cfg['max_cluster_samples_list'], cfg['dist_thresh_list'],
+                              dummy_embeddings, prefix='multimodal_middle_encoder.')
+    last = outs[-1]
+    mm = cpu.dense(last.indices, last.features, last.spatial_shape, B)
+    bev = np.concatenate([spatial, mm.reshape(B, -1, mm.shape[-2], mm.shape[-1])], 1)
+    return bev, outs, compressed

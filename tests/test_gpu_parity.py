@@ -14,6 +14,9 @@ from msmdfusion_b200 import ops, registry, synthetic
 from oracle import cpu
 from oracle import model as omodel
 
+import _fixtures
+from _fixtures import randomize_bn
+
 pytestmark = pytest.mark.gpu
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
@@ -293,17 +296,6 @@ def test_to_dense_matches_oracle():
 # ----------------------------------------------------------------------------------------------
 # module level: SubMConv3d / SparseConv3d / SparseBasicBlock / SparseEncoder
 # ----------------------------------------------------------------------------------------------
-def randomize_bn(module, seed=0):
-    g = torch.Generator().manual_seed(seed)
-    for mod in module.modules():
-        if isinstance(mod, torch.nn.BatchNorm1d):
-            d = mod.weight.device
-            mod.weight.data = (torch.rand(mod.weight.shape, generator=g) + 0.5).to(d)
-            mod.bias.data = (torch.randn(mod.bias.shape, generator=g) * 0.1).to(d)
-            mod.running_mean.data = (torch.randn(mod.running_mean.shape, generator=g) * 0.1).to(d)
-            mod.running_var.data = (torch.rand(mod.running_var.shape, generator=g) + 0.5).to(d)
-
-
 def test_config1_voxelize_plus_one_subm():
     """BASELINE.json configs[0]: hard_voxelize + one SubMConv3d(5->16,k3) on 1 k points."""
     pts = synthetic.random_points(1000, 5, seed=0)
@@ -568,17 +560,7 @@ def test_lift_gather_matches_oracle():
 # detector level: lift -> multi-scale virtual-point voxels -> modality split -> GMA encoder
 # --------------------------------------------------------------------------------------
 def build_msmd_detector(seed=0):
-    cfg = m.Config.fromfile(os.path.join(ROOT, 'configs', 'msmd_lc_hotpath.py')).hotpath
-    torch.manual_seed(seed)
-    det = m.MSMDFusionDetector(**{k: cfg[k] for k in (
-        'pts_voxel_layer', 'pts_voxel_encoder', 'pts_middle_encoder', 'multimodal_middle_encoder',
-        'spatial_shapes', 'downscale_factors', 'fps_num_list', 'radius_list', 'max_cluster_samples_list',
-        'dist_thresh_list')}).to(dev())
-    randomize_bn(det, seed + 1)
-    with torch.no_grad():  # make the ReLU score gate open for roughly half of the points
-        det.score_net[0].weight.mul_(0.2)
-        det.score_net[0].bias.fill_(0.05)
-    return det.eval(), cfg
+    return _fixtures.build_msmd_detector(seed, dev())
 
 
 def test_depth_canvas_matches_oracle():
@@ -652,10 +634,8 @@ def test_msmd_voxel_space_end_to_end(batch):
     """configs[2] slice: LiDAR encoder + 4-scale virtual-point voxels + modality split + GMA encoder
     + sparse_add + downscale + dense, CUDA path vs the CPU oracle on the same seeded scene."""
     det, cfg = build_msmd_detector(1)
-    scenes = [synthetic.lidar_scene(30 + b, 1) for b in range(batch)]
-    metas = [synthetic.camera_scene(30 + b, scenes[b], virtual_per_camera=3000 if b == 0 else 300,
-                                    empty_cameras=(() if b == 0 else (2,))) for b in range(batch)]
-    fpn = [cuda(f) for f in synthetic.fpn_features(1, batch=batch)]
+    scenes, metas, fpn_np = _fixtures.lc_scene(batch)
+    fpn = [cuda(f) for f in fpn_np]
     pts_t = [cuda(s) for s in scenes]
     torch.manual_seed(77)
     dummies = [torch.rand(1, c).numpy() for c in cfg.multimodal_middle_encoder['in_channels_3D']]
@@ -666,38 +646,53 @@ def test_msmd_voxel_space_end_to_end(batch):
     torch.cuda.synchronize()
     assert bev.shape == (batch, 256 + 384, 180, 180)
 
-    # ---- oracle ----
+    # ---- oracle (the dense image-plane convolutions are taken from the torch / cuDNN run above) ----
     sd = {k: v.cpu() for k, v in det.state_dict().items()}
-    ev, en, ec = omodel.voxelize_batch(scenes, synthetic.VOXEL_SIZE, synthetic.POINT_CLOUD_RANGE, 10, 160000)
-    emean = cpu.hard_simple_vfe(ev, en, 5)
-    e_spatial, e_feats, _ = omodel.sparse_encoder(sd, dict(cfg.pts_middle_encoder), emean, ec, batch,
-                                                  prefix='pts_middle_encoder.')
-    comp_np = [c.cpu().numpy() for c in comp]
-    img_list = [comp_np[0]] + comp_np
-    score_w = sd['score_net.0.weight'].numpy().reshape(-1)
-    score_b = float(sd['score_net.0.bias'].item())
-    v3l, v2l, s3l, s2l = [], [], [], []
-    for i in range(4):
-        v2 = omodel.fetch_2d_voxels(img_list[i], metas, score_w, score_b, cfg.spatial_shapes[i],
-                                    cfg.downscale_factors[i], synthetic.VOXEL_SIZE,
-                                    synthetic.POINT_CLOUD_RANGE, 10, 160000)
-        v3 = e_feats[i]
-        c3, c2, s3, s2 = cpu.voxel_modality_split(v3.indices, v2.indices, batch)
-        v3l.append(omodel.SpTensor(v3.features, c3, v3.spatial_shape, batch))
-        v2l.append(omodel.SpTensor(v2.features, c2, v2.spatial_shape, batch))
-        s3l.append(s3)
-        s2l.append(s2)
-    e_outs = omodel.multimodal_encoder(sd, dict(cfg.multimodal_middle_encoder), v3l, v2l, s3l, s2l,
-                                       cfg.fps_num_list, cfg.radius_list, cfg.max_cluster_samples_list,
-                                       cfg.dist_thresh_list, dummies, prefix='multimodal_middle_encoder.')
+    e_bev, e_outs, _ = omodel.extract_voxel_space(sd, cfg, scenes, None, metas, dummies,
+                                                  compressed=[c.cpu().numpy() for c in comp])
     for g, e in zip(stage_outs, e_outs):
         assert g.spatial_shape == e.spatial_shape
         assert np.array_equal(g.indices.cpu().numpy(), e.indices)            # bit-exact indices
         err = feat_err(g.features.cpu().numpy(), e.features)
         assert err < FEAT_TOL, err
-    e_mm = cpu.dense(e_outs[-1].indices, e_outs[-1].features, e_outs[-1].spatial_shape, batch)
-    e_bev = np.concatenate([e_spatial, e_mm.reshape(batch, -1, 180, 180)], 1)
     assert feat_err(bev.cpu().numpy(), e_bev) < FEAT_TOL
+
+
+def test_msmd_voxel_space_matches_reference_golden():
+    """The CUDA voxel-space path (batch 2) against the committed output of the REFERENCE's own
+    `extract_pts_feat` (MSMDFusion.py:421-445, every method and class it reaches run in place with the
+    reference's C++ voxelizer; fixture by tests/golden/make_golden_detector.py): per stage the voxel
+    count, the index tensor (CRC, i.e. bit-exact) and sampled feature rows; 40 000 sampled positions of
+    the (2, 640, 180, 180) BEV tensor and its non-zero count.  The three dense image-plane blocks
+    (`conv1x1_blocks`, library convolutions, not kernels of this project) run without cuDNN here: its
+    TF32 / Winograd algorithms differ from the fp32 reference run by ~2e-3, torch's native fp32 path does not."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location('make_golden_detector', os.path.join(GOLDEN, 'make_golden_detector.py'))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    g = np.load(os.path.join(GOLDEN, 'detector_reference.npz'))
+    det, cfg = build_msmd_detector(mod.DET_SEED)
+    assert _fixtures.state_dict_crc(det.state_dict()) == int(g['weights_crc'][0]), 'random-init weights drifted'
+    scenes, metas, fpn_np = _fixtures.lc_scene(mod.BATCH)
+    assert mod.inputs_crc(scenes, metas, fpn_np) == int(g['inputs_crc'][0]), 'synthetic generator drifted'
+    with torch.backends.cudnn.flags(enabled=False):   # native fp32 im2col + SGEMM convolution
+        torch.manual_seed(mod.DUMMY_SEED)
+        with torch.no_grad():
+            bev, stage_outs = det.extract_voxel_space([cuda(s) for s in scenes], [cuda(f) for f in fpn_np], metas)
+        torch.cuda.synchronize()
+    bev = bev.cpu().numpy()
+    assert list(bev.shape) == g['bev_shape'].tolist()
+    for i, o in enumerate(stage_outs):
+        idx, feat = o.indices.cpu().numpy(), o.features.cpu().numpy()
+        assert o.spatial_shape == g['shape%d' % i].tolist() and idx.shape[0] == int(g['count%d' % i][0])
+        assert zlib.crc32(np.ascontiguousarray(idx, np.int32).tobytes()) == int(g['indices_crc%d' % i][0])
+        err = feat_err(feat[::mod.ROW_STEP], g['rows%d' % i])
+        assert err < FEAT_TOL, (i, err)
+    flat = bev.reshape(-1)
+    sample = flat[mod.bev_positions(flat.shape[0])]
+    assert np.abs(sample - g['bev_values']).max() / max(1.0, float(g['bev_absmax'][0])) < FEAT_TOL
+    # a ReLU input within rounding of zero may land on either side: the count is compared to 1e-4
+    assert abs(np.count_nonzero(flat) - int(g['bev_nonzero'][0])) <= 1e-4 * int(g['bev_nonzero'][0])
 
 
 # --------------------------------------------------------------------------------------

@@ -602,3 +602,91 @@ def test_multimodal_encoder_layout_matches_reference_class_live():
     mine = {k: tuple(v.shape) for k, v in ours.state_dict().items()}
     assert all(mine[k] == shape for k, shape in gates.items())
     assert {k for k in mine if 'gate_control' in k} == set(gates)
+
+
+# --------------------------------------------------------------------------------------
+# Detector level: the reference's own extract_pts_feat, executed from where it lies
+# --------------------------------------------------------------------------------------
+def load_detector_golden():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location('make_golden_detector', os.path.join(GOLDEN, 'make_golden_detector.py'))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod, np.load(os.path.join(GOLDEN, 'detector_reference.npz'))
+
+
+@pytest.mark.skipif(not __import__('oracle.ref_detector', fromlist=['x']).available(), reason='reference tree not mounted')
+def test_extract_voxel_space_matches_reference_detector_live():
+    """oracle.model.extract_voxel_space against MSMDFusionDetector.extract_pts_feat itself
+    (MSMDFusion.py:421-445 and every method / class it reaches, run in place by oracle/ref_detector.py
+    with the reference's own C++ voxelizer): the four stage outputs' indices bit for bit, their features
+    and the (B, 640, 180, 180) tensor handed to bev_fusion within fp32 summation-order noise."""
+    import _fixtures
+    from oracle import model as omodel, ref_detector
+    det, cfg = _fixtures.build_msmd_detector(1)
+    sd = det.state_dict()
+    scenes, metas, fpn = _fixtures.lc_scene(1, points=20000, virtual=(1500, 300))
+    r_bev, r_outs = ref_detector.extract_voxel_space(sd, cfg, scenes, fpn, metas, 77)
+    torch.manual_seed(77)
+    dummies = [torch.rand(1, c).numpy() for c in cfg.multimodal_middle_encoder['in_channels_3D']]
+    e_bev, e_outs, _ = omodel.extract_voxel_space(sd, cfg, scenes, fpn, metas, dummies)
+    assert r_bev.shape == e_bev.shape == (1, 640, 180, 180)
+    for a, b in zip(r_outs, e_outs):
+        assert a.spatial_shape == b.spatial_shape and np.array_equal(a.indices, b.indices)
+        assert np.abs(a.features - b.features).max() <= 1e-5 * max(1.0, np.abs(a.features).max())
+    assert np.abs(r_bev - e_bev).max() <= 1e-5 * max(1.0, np.abs(r_bev).max())
+    assert np.count_nonzero(r_bev) == np.count_nonzero(e_bev) > 100000
+
+
+def check_against_detector_golden(mod, g, bev, outs, tol):
+    """bev: (B,640,180,180) array; outs: [(indices (N,4) int32, features (N,C))] per stage."""
+    assert list(bev.shape) == g['bev_shape'].tolist()
+    for i, (idx, feat) in enumerate(outs):
+        assert idx.shape[0] == int(g['count%d' % i][0])
+        assert zlib.crc32(np.ascontiguousarray(idx, np.int32).tobytes()) == int(g['indices_crc%d' % i][0])
+        ref = g['rows%d' % i]
+        assert np.abs(feat[::mod.ROW_STEP] - ref).max() <= tol * max(1.0, np.abs(ref).max())
+    flat = bev.reshape(-1)
+    ref = g['bev_values']
+    assert np.abs(flat[mod.bev_positions(flat.shape[0])] - ref).max() <= tol * max(1.0, float(g['bev_absmax'][0]))
+    assert np.count_nonzero(flat) == int(g['bev_nonzero'][0])
+
+
+def test_extract_voxel_space_matches_reference_golden():
+    """The oracle chain against the committed output of the reference's own extract_pts_feat on the
+    batch-2 scene (tests/golden/make_golden_detector.py) -- the same fixture the CUDA path is checked
+    against on the GPU box."""
+    import _fixtures
+    from oracle import model as omodel
+    mod, g = load_detector_golden()
+    det, cfg = _fixtures.build_msmd_detector(mod.DET_SEED)
+    sd = det.state_dict()
+    assert _fixtures.state_dict_crc(sd) == int(g['weights_crc'][0]), 'random-init weights drifted'
+    scenes, metas, fpn = _fixtures.lc_scene(mod.BATCH)
+    assert mod.inputs_crc(scenes, metas, fpn) == int(g['inputs_crc'][0]), 'synthetic generator drifted'
+    torch.manual_seed(mod.DUMMY_SEED)
+    dummies = [torch.rand(1, c).numpy() for c in cfg.multimodal_middle_encoder['in_channels_3D']]
+    bev, outs, _ = omodel.extract_voxel_space(sd, cfg, scenes, fpn, metas, dummies)
+    check_against_detector_golden(mod, g, bev, [(o.indices, o.features) for o in outs], 1e-5)
+
+
+@pytest.mark.skipif(not __import__('oracle.ref_detector', fromlist=['x']).available(), reason='reference tree not mounted')
+def test_spp_module_matches_reference_class_live():
+    """bev_fusion: this package's SPPModule against the reference's own class (MSMDFusion.py:47-90, run in
+    place): identical state-dict names and shapes, identical output on the same weights (dense torch ops
+    on both sides -- no kernel of this project; it closes the path behind the voxel-space tensor)."""
+    from msmdfusion_b200.detector import SPPModule
+    from oracle import ref_detector
+    torch.manual_seed(4)
+    ours = SPPModule().eval()
+    ref = ref_detector.spp_module()().eval()
+    assert [(k, tuple(v.shape)) for k, v in ours.state_dict().items()] == \
+        [(k, tuple(v.shape)) for k, v in ref.state_dict().items()]
+    for mod in ours.modules():
+        if isinstance(mod, torch.nn.BatchNorm2d):
+            mod.running_mean.normal_(0, 0.1)
+            mod.running_var.uniform_(0.5, 1.5)
+    ref.load_state_dict(ours.state_dict())
+    x = torch.randn(1, 640, 40, 40)
+    with torch.no_grad():
+        assert torch.equal(ours(x), ref(x))
