@@ -18,9 +18,13 @@ Parity pinning ("Oracle"):
   (``mmdet3d/ops/spconv``), compiled unmodified by ``oracle/ref_spconv.py`` and run on the CPU
   (live test + committed fixtures ``tests/golden/spconv1x_*.npz``), and independently against a
   dense ``torch.nn.functional.conv3d`` oracle.
+* modality split, ``fps_NN_fast``, the 2D->3D lift, both encoder classes and the whole
+  ``extract_pts_feat`` chain -- pinned against the reference's OWN Python code, compiled from its source
+  text in place and run on the CPU (``oracle/ref_inplace.py`` and the ``oracle/ref_*.py`` runners; live
+  tests + committed fixtures ``tests/golden/{split,assign,lift,detector}_*.npz``).
 * spconv-2.x-only conventions (ascending-linear-index row order of strided-conv outputs, ``sparse_add``
-  as a coalesced COO sum) / modality split / GMA-conv glue -- the un-vendored spconv v2.1.21 is not
-  available and no reference test pins results there: "parity unpinned" by the reference for these.
+  as a coalesced COO sum) -- the un-vendored spconv v2.1.21 is not available and no reference test pins
+  results there: "parity unpinned" by the reference for these two conventions.
 """
 import ctypes
 
