@@ -309,20 +309,31 @@ ball_query_kernel(const float* __restrict__ xyz, int n, const float* __restrict_
   int* row = idx + (size_t)c * nsample;
   int cnt = 0;
   int first = -1;
-  for (int base = 0; base < n && cnt < nsample; base += 32) {
-    const int k = base + lane;
-    bool hit = false;
-    if (k < n) {
-      const float x = xyz[3 * k], y = xyz[3 * k + 1], z = xyz[3 * k + 2];
-      const float d2 = (nx - x) * (nx - x) + (ny - y) * (ny - y) + (nz - z) * (nz - z);
-      hit = (d2 == 0.f) || (d2 >= min_r2 && d2 < max_r2);
+  // kBqUnroll groups of 32 candidates are loaded before the first ballot, so that many L2 round trips
+  // overlap (the scan is latency bound: one dependent ballot per step).  The groups are then appended
+  // in order; a group that starts after the row is full writes nothing (pos >= nsample).
+  constexpr int kBqUnroll = 4;
+  for (int base = 0; base < n && cnt < nsample; base += 32 * kBqUnroll) {
+    bool hit[kBqUnroll];
+#pragma unroll
+    for (int u = 0; u < kBqUnroll; ++u) {
+      const int k = base + 32 * u + lane;
+      hit[u] = false;
+      if (k < n) {
+        const float x = xyz[3 * k], y = xyz[3 * k + 1], z = xyz[3 * k + 2];
+        const float d2 = (nx - x) * (nx - x) + (ny - y) * (ny - y) + (nz - z) * (nz - z);
+        hit[u] = (d2 == 0.f) || (d2 >= min_r2 && d2 < max_r2);
+      }
     }
-    const unsigned bal = __ballot_sync(0xffffffffu, hit);
-    if (bal) {
-      if (first < 0) first = base + __ffs(bal) - 1;
-      const int pos = cnt + __popc(bal & ((1u << lane) - 1u));
-      if (hit && pos < nsample) row[pos] = k;
-      cnt += __popc(bal);
+#pragma unroll
+    for (int u = 0; u < kBqUnroll; ++u) {
+      const unsigned bal = __ballot_sync(0xffffffffu, hit[u]);
+      if (bal) {
+        if (first < 0) first = base + 32 * u + __ffs(bal) - 1;
+        const int pos = cnt + __popc(bal & ((1u << lane) - 1u));
+        if (hit[u] && pos < nsample) row[pos] = base + 32 * u + lane;
+        cnt += __popc(bal);
+      }
     }
   }
   if (first >= 0) {
