@@ -32,7 +32,7 @@ def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=100)
-    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=30)  # a fresh box needs ~25 steps to reach steady clocks (profiles/r01f_bench_S.json)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--profile', default='S', choices=['S', 'L'],
                     help='S: single 32-beam sweep (~30 k points); L: 10 sweeps (~285 k points)')
