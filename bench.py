@@ -26,6 +26,7 @@ sys.path.insert(0, ROOT)
 
 METRIC = 'nuScenes-shape scenes/sec forward (voxel hot path: hard_voxelize+VFE+SparseEncoder+dense; --workload LC adds lift+split+GMA encoder)'
 UNIT = 'scenes/s'
+SETTLE_MS = 200.0  # untimed pipeline run before the warm-up steps (see run_ours)
 
 
 def parse():
@@ -210,9 +211,22 @@ def run_ours(args, rank, world, device):
 
     clocks = Clocks(torch.cuda.current_device())
     clocks.start()  # nvidia-smi needs ~100 ms to produce its first sample: start it before warm-up
+    # settle: a freshly acquired box runs its first ~50 ms of work below steady speed with the SM clock
+    # already reading max (profiles/r01f_bench_S.json), so the pipeline is driven for SETTLE_MS of wall
+    # time before the W warm-up steps the caller asked for; untimed, reported in config.settle_ms
+    t_settle = None
+    settle_steps = 0
+    while t_settle is None or (time.perf_counter() - t_settle) * 1e3 < SETTLE_MS:
+        flush.zero_()
+        spatial, feats = step(pts_dev)
+        torch.cuda.synchronize(device)
+        settle_steps += 1
+        if t_settle is None:  # the very first step carries lazy initialisation: the clock starts after it
+            t_settle = time.perf_counter()
     for _ in range(max(args.warmup, 3)):
         # results are kept across iterations exactly as in the timed loops, so the caching
         # allocator reaches its steady state (two live result arenas) during warm-up
+        flush.zero_()
         spatial, feats = step(pts_dev)
     sync_all()
     # serving-loop hygiene: move everything allocated so far out of the cyclic GC's reach so a
@@ -341,7 +355,7 @@ def run_ours(args, rank, world, device):
             roof = dict(bound='hbm', achieved=round(gbs, 2), peak=hbm, unit='GB/s', frac=round(gbs / hbm, 4),
                         **common)
     n_vox = int(feats[0].indices.shape[0])
-    return dict(dev_ms=dev_ms, e2e_ms=e2e_ms, launches=int(launches), clocks=clk, roofline=roof,
+    return dict(dev_ms=dev_ms, e2e_ms=e2e_ms, launches=int(launches), clocks=clk, roofline=roof, settle_steps=settle_steps,
                 e2e_step_ms=dict(min=round(min(e2e_raw), 4), median=round(sorted(e2e_raw)[len(e2e_raw) // 2], 4),
                                  max=round(max(e2e_raw), 4), all=[round(x, 2) for x in e2e_raw[:32]]),
                 alloc=alloc_diag,
@@ -445,6 +459,7 @@ def main():
         'config': {'workload': workload_name(args.profile, args.workload), 'arithmetic': 'fp32 in/out; contraction = 3xTF32 tensor-core split with fp32 accumulate (<=1e-4 vs fp32 oracle)', 'points_per_scene': res['points'],
                    'voxels_per_scene': res['voxels'], 'scenes_per_gpu_per_step': 1, 'parallelism': 'dp%d' % world,
                    'l2': 'flushed between steps (256 MiB memset, outside the per-step events)',
+                   'settle': '%d untimed steps (the first + %.0f ms of wall time) before the %d warm-up steps' % (res['settle_steps'], SETTLE_MS, max(args.warmup, 3)),
                    'weights': 'random init (spconv default), BN eval'},
         'e2e': {'value': world * K / (res['e2e_ms'] * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': res['h2d'],
                 'd2h_bytes_per_step': res['d2h'], 'step_ms': res['e2e_step_ms'],
