@@ -72,6 +72,20 @@ class PackedForeground:
             info = meta['foreground2D_info']
             n = len(info['fg_pixels']) if ncam is None else ncam
             total = 0
+            scene = info.get('packed') if isinstance(info, dict) else None
+            if scene is not None and scene.ncam == n:
+                # produced by msmdfusion_b200.loading: already camera-major packed arrays (the per-camera
+                # lists are views of them) -- one block per array instead of one per camera
+                pix.append(scene.pixels)
+                pts.append(_as_numpy(scene.points))
+                cam.append(scene.cam_ids() + np.int32(b * n))
+                rpix.append(scene.real_pixels)
+                rcam.append(np.repeat(np.arange(n, dtype=np.int32), np.diff(scene.real_offsets)) + np.int32(b * n))
+                for v in range(n):
+                    l2i.append(np.asarray(meta['lidar2img'][v], np.float64).reshape(16).astype(np.float32))
+                counts.append(int(scene.offsets[-1]))
+                self.ncam = n
+                continue
             for v in range(n):
                 p = _as_numpy(info['fg_pixels'][v]).reshape(-1, 3)
                 q = _as_numpy(info['fg_points'][v])

@@ -5,6 +5,8 @@ the reference pipeline produces (``configs/MSMDFusion_nusc_voxel_LC.py:24-57``,
 ``mmdet3d/datasets/pipelines/my_loading_multi_proj.py``): a 32-beam LiDAR scan in the
 ``[-54,54]^2 x [-5,3]`` range, optionally 10 jittered sweeps, six cameras of virtual points.
 """
+import os
+
 import numpy as np
 
 POINT_CLOUD_RANGE = [-54.0, -54.0, -5.0, 54.0, 54.0, 3.0]
@@ -160,3 +162,66 @@ def fpn_features(seed=0, batch=1, ncam=6, channels=256):
     rng = np.random.default_rng(seed + 3000)
     H, W = INPUT_SHAPE
     return [rng.standard_normal((batch * ncam, channels, H // s, W // s), dtype=np.float32) for s in (4, 8, 16)]
+
+
+# --------------------------------------------------------------------------------------------
+# Virtual-point WIRE FORMAT: the per-sweep `.pkl.npy` files the reference's
+# LoadForeground2D / LoadForeground2DFromMultiSweeps read
+# (mmdet3d/datasets/pipelines/my_loading_multi_proj.py:17-35,126-131,307-311)
+# --------------------------------------------------------------------------------------------
+FOREGROUND_DIR = 'FOREGROUND_MIXED_6NN_WITH_DEPTH'
+
+
+def foreground_wire_dict(rng, virtual_per_camera=2000, real_per_camera=300, ncam=6, empty_cameras=(),
+                         outside_fraction=0.05):
+    """One sweep's saved dict: four keys, each a list of `ncam` float32 arrays.  `*_pixel_indices`:
+    (n, 14) = u, v in ORIGINAL image pixels (1600x900), depth, 10 one-hot class dims + score;
+    `*_points`: (n, 3) xyz in that sweep's LiDAR frame.  A fraction of the points lies outside the
+    point-cloud range so that the range filter has work to do."""
+    out = {k: [] for k in ('virtual_pixel_indices', 'real_pixel_indices', 'virtual_points', 'real_points')}
+    for cam in range(ncam):
+        for kind, n in (('virtual', virtual_per_camera), ('real', real_per_camera)):
+            n = 0 if cam in empty_cameras else int(n * rng.uniform(0.6, 1.0))
+            u = rng.uniform(0, 1599, n) if kind == 'real' else np.floor(rng.uniform(0, 1600, n))
+            v = rng.uniform(0, 899, n) if kind == 'real' else np.floor(rng.uniform(0, 900, n))
+            depth = rng.uniform(1.0, 60.0, n)
+            onehot = np.zeros((n, 10))
+            if n:
+                onehot[np.arange(n), rng.integers(0, 10, n)] = 1.0
+            score = rng.uniform(0.3, 1.0, (n, 1))
+            out[kind + '_pixel_indices'].append(
+                np.concatenate([u[:, None], v[:, None], depth[:, None], onehot, score], 1).astype(np.float32))
+            xyz = rng.uniform([-50, -50, -4.5], [50, 50, 2.5], (n, 3))
+            far = rng.random(n) < outside_fraction
+            xyz[far] *= 1.3
+            out[kind + '_points'].append(xyz.astype(np.float32))
+    return out
+
+
+def write_foreground_wire(root, seed=0, sweeps=10, missing_sweeps=(), **kw):
+    """Writes `<root>/samples/<FOREGROUND_DIR>/*.pkl.npy` for one sample and its sweeps the way the
+    reference expects to find them next to `<root>/samples/LIDAR_TOP/<file>` (path logic of :126-128) and
+    returns the `results` dict the pipeline stages receive (keys of nuscenes_dataset.py:get_data_info that
+    these stages read): pts_filename, timestamp [s], sweeps[{data_path, timestamp [us], sensor2lidar_*}]."""
+    rng = np.random.default_rng(seed + 7000)
+    fg_dir = os.path.join(root, 'samples', FOREGROUND_DIR)
+    os.makedirs(fg_dir, exist_ok=True)
+
+    def save(name, d):
+        np.save(os.path.join(fg_dir, name + '.pkl.npy'), d, allow_pickle=True)
+    sample_name = 'n015-sample-%04d.pcd.bin' % seed
+    save(sample_name, foreground_wire_dict(rng, **kw))
+    ts_us = 1533151603547590 + 500000 * seed
+    results = dict(pts_filename=os.path.join(root, 'samples', 'LIDAR_TOP', sample_name), timestamp=ts_us / 1e6,
+                   sweeps=[])
+    for s in range(sweeps):
+        name = 'n015-sweep-%04d-%02d.pcd.bin' % (seed, s)
+        if s not in missing_sweeps:   # the reference skips sweeps whose file does not exist (:311,324)
+            save(name, foreground_wire_dict(rng, **kw))
+        ang = rng.normal(0, 0.02)
+        c, sn = np.cos(ang), np.sin(ang)
+        results['sweeps'].append(dict(
+            data_path=os.path.join(root, 'samples', 'LIDAR_TOP', name), timestamp=ts_us - 50000 * (s + 1),
+            sensor2lidar_rotation=np.array([[c, -sn, 0.0], [sn, c, 0.0], [0.0, 0.0, 1.0]]),
+            sensor2lidar_translation=rng.normal(0, 0.5, 3) * np.array([1.0, 1.0, 0.05])))
+    return results
