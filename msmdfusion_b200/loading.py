@@ -48,6 +48,19 @@ class CameraPoints:
         return self.tensor.shape[0]
 
 
+class ForegroundInfo(dict):
+    """``results['foreground2D_info']``: the reference's keys (per-camera views) + ``'packed'``.  Pickles as
+    the packed scene alone (DataLoader workers hand samples over by pickle): the views are rebuilt on the
+    other side instead of being serialised a second time as copies."""
+
+    def __reduce__(self):
+        return (_info_from_scene, (self['packed'],))
+
+
+def _info_from_scene(scene):
+    return scene.reference_dict()
+
+
 class ForegroundScene:
     """Packed, camera-major foreground info of one sample (see the module docstring)."""
 
@@ -64,11 +77,16 @@ class ForegroundScene:
         """The reference's ``foreground2D_info`` dict: per-camera views, no copies."""
         o, r = self.offsets, self.real_offsets
         cams = range(self.ncam)
-        return {'fg_pixels': [self.pixels[o[c]:o[c + 1]] for c in cams],
-                'fg_points': [CameraPoints(self.points[o[c]:o[c + 1]]) for c in cams],
-                'fg_real_pixels': [self.real_pixels[r[c]:r[c + 1]] for c in cams],
-                'fg_real_points': [self.real_points[r[c]:r[c + 1]] for c in cams],
-                'packed': self}
+        return ForegroundInfo({'fg_pixels': [self.pixels[o[c]:o[c + 1]] for c in cams],
+                               'fg_points': [CameraPoints(self.points[o[c]:o[c + 1]]) for c in cams],
+                               'fg_real_pixels': [self.real_pixels[r[c]:r[c + 1]] for c in cams],
+                               'fg_real_points': [self.real_points[r[c]:r[c + 1]] for c in cams],
+                               'packed': self})
+
+    def __getstate__(self):
+        state = dict(self.__dict__)
+        state.pop('key_frame', None)     # the raw key-frame dict is only needed between the two load stages
+        return state
 
 
 def scene_of(results):

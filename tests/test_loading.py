@@ -162,6 +162,22 @@ def test_packed_scene_is_what_the_detector_uploads(wire):
     assert torch.equal(pk2.real_cam[:r], pk.real_cam) and pk2.counts == [m, m]
 
 
+def test_foreground_info_pickles_as_one_packed_scene(wire):
+    """DataLoader workers pickle samples: the dict travels as the packed arrays only and comes back with
+    its per-camera views rebuilt on them."""
+    import pickle
+    info = loading.run_pipeline(ours_test_pipeline(), pipeline_meta(wire(seed=4, sweeps=2, virtual_per_camera=400,
+                                                                         real_per_camera=60)))['foreground2D_info']
+    blob = pickle.dumps(info, protocol=pickle.HIGHEST_PROTOCOL)
+    scene = info['packed']
+    payload = scene.pixels.nbytes + scene.points.numel() * 4 + scene.real_pixels.nbytes + scene.real_points.nbytes
+    assert len(blob) < 1.05 * payload + 4096            # not twice: the views are not serialised
+    back = pickle.loads(blob)
+    assert isinstance(back, loading.ForegroundInfo) and scene_crc(back) == scene_crc(info)
+    assert all(np.shares_memory(v, back['packed'].pixels) for v in back['fg_pixels'] if v.size)
+    assert not hasattr(back['packed'], 'key_frame')
+
+
 def test_registry_and_errors(wire):
     for name in ('LoadForeground2D', 'LoadForeground2DFromMultiSweeps', 'GlobalRotTransFilterForeground2D',
                  'ImgScaleCropFlipForeground2D', 'ShuffleForeground2D'):
