@@ -7,6 +7,9 @@ Mirror of the reference's foreground-2D pipeline stages
 same constructor kwargs, same keys read from / written to the ``results`` dict, results identical bit
 for bit (``tests/test_loading.py`` runs the reference's own classes in place beside these).
 
+This is dataset-side host code by definition -- the reference's stages are numpy on DataLoader
+workers -- not a CPU fallback of any kernel: nothing here has a CUDA counterpart that it stands in for.
+
 What is different is the memory plan.  The reference keeps six Python lists of per-camera arrays and
 grows them by ``np.concatenate`` once per sweep and camera (every merge copies everything merged so
 far, in float64), then wraps each camera in a ``LiDARPoints``.  Here one sample is ONE set of packed,
