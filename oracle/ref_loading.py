@@ -9,7 +9,7 @@ in place (oracle/ref_inplace.py); `get_points_type('LIDAR')` is bound to the ref
 `LiDARPoints` / `BasePoints` classes (mmdet3d/core/points/{lidar_points,base_points}.py), compiled the
 same way.  Nothing is copied into this repository.
 
-Used by tests/test_loading.py and tools/bench_loader.py.  Needs /root/reference.
+Used by tests/test_loading.py and tests/tools/bench_loader.py.  Needs /root/reference.
 """
 import os
 from abc import abstractmethod

@@ -4,7 +4,7 @@ config-3 size (about 60 k virtual points per sample after the merge) -- the refe
 in place (oracle/ref_loading.py) beside msmdfusion_b200.loading, same files (page cache warm), one host
 thread, median of `--reps` runs.  CPU only; needs /root/reference for the reference leg.
 
-    python tools/bench_loader.py [--reps 20] [--virtual 900] [--real 180]
+    python tests/tools/bench_loader.py [--reps 20] [--virtual 900] [--real 180]
 """
 import argparse
 import copy
@@ -17,7 +17,7 @@ import time
 import numpy as np
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 
 from msmdfusion_b200 import loading, synthetic  # noqa: E402
