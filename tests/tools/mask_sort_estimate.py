@@ -6,7 +6,8 @@ nearly every tile touches nearly all 27 offsets although a row uses 12-50 % of t
 output rows by their 27-bit neighbour mask before tiling (`mask_argsort_fwd_splits`, call site
 bug_fix/conv.py:382-415).  This script measures what that ordering would buy on the bench scenes: average
 active offsets per tile, current order vs rows sorted by mask, for the four SubM resolution levels of the
-LiDAR encoder.  Output committed as profiles/r01g_mask_sort_estimate.txt.
+LiDAR encoder, for a sort by the full mask (spconv's choice) and by a 15-bit structural digest
+(two 8-bit radix passes).  Output committed as profiles/r01g_mask_sort_estimate.txt.
 
     python tests/tools/mask_sort_estimate.py
 """
@@ -29,6 +30,19 @@ def tiles_active(used, order):
     return float(u.sum(0).mean()), int(u.sum())
 
 
+def digest_key(mask):
+    """15-bit sort key that groups rows by neighbourhood STRUCTURE instead of by the numeric value of
+    the mask (offset k = (dz+1)*9 + (dy+1)*3 + (dx+1)): for the plane below and the plane above, one bit
+    per dy row ("any neighbour in that row"), then the nine bits of the voxel's own z plane.  LiDAR
+    surfaces are mostly thin sheets: most rows have no neighbour above / below at all."""
+    lower, centre, upper = mask & 0x1FF, (mask >> 9) & 0x1FF, (mask >> 18) & 0x1FF
+    key = centre.copy()
+    for plane, base in ((upper, 9), (lower, 12)):
+        for row in range(3):
+            key |= (((plane >> (3 * row)) & 7) != 0).astype(np.int64) << (base + row)
+    return key
+
+
 def main():
     for prof, sweeps in (('S', 1), ('L', 10)):
         pts = synthetic.lidar_scene(seed=0, sweeps=sweeps)
@@ -40,9 +54,11 @@ def main():
             mask = (used.astype(np.int64) * (1 << np.arange(27))[:, None]).sum(0)
             base = tiles_active(used, np.arange(idx.shape[0]))
             srt = tiles_active(used, np.argsort(mask, kind='stable'))
+            dig = tiles_active(used, np.argsort(digest_key(mask), kind='stable'))
             print('profile %s level %d: N %6d, pair density %.3f, active offsets per 128-row tile: %.1f now -> %.1f '
-                  'mask-sorted (tile-offset products %d -> %d, x%.2f)'
-                  % (prof, level, idx.shape[0], used.mean(), base[0], srt[0], base[1], srt[1], base[1] / srt[1]))
+                  'sorted by the 27-bit mask (x%.2f) -> %.1f sorted by the 15-bit digest (x%.2f)'
+                  % (prof, level, idx.shape[0], used.mean(), base[0], srt[0], base[1] / srt[1], dig[0],
+                     base[1] / dig[1]))
             if level < 3:
                 idx, _, shape = cpu.conv_rulebook(idx, shape, 3, 2, 1 if level < 2 else (0, 1, 1), 1)
 
