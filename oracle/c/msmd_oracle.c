@@ -298,6 +298,74 @@ int orc_spconv_fwd(const float *feat, const float *weight, const int *pair_fwd, 
   return 0;
 }
 
+/*
+ * Sparse conv backward (config 5, the train step).  The reference path calls spconv-2.x
+ * implicit_gemm backward through pair_bwd (bug_fix/conv.py:442-447); the arithmetic is the one
+ * the vendored spconv-1.x spells out (spconv_ops.h:364-457): per kernel offset k, with the
+ * offset's pairs (i -> o):   dW_k = X_k^T dY_k      dX_k = dY_k W_k^T   (scatter-added into dX).
+ *   grad_in[i,ci]  = sum_{k, o: pair_fwd[k,o]=i} sum_co grad_out[o,co] * W[co,k,ci]
+ *   grad_w[co,k,ci] = sum_{o: pair_fwd[k,o]>=0}  grad_out[o,co] * x[pair_fwd[k,o],ci]
+ * grad_w is KRSC like the parameter; it is accumulated in double (a checker should carry less
+ * rounding than the thing it checks), grad_in in fp32 like the forward.
+ */
+int orc_spconv_bwd(const float *feat, const float *weight, const int *pair_fwd,
+                   const float *grad_out, int n_in, int n_out, int cin, int cout, int K,
+                   float *grad_in, float *grad_w) {
+  if (grad_in) {
+    for (size_t t = 0; t < (size_t)n_in * cin; ++t) grad_in[t] = 0.f;
+    for (int o = 0; o < n_out; ++o) {
+      const float *dy = grad_out + (size_t)o * cout;
+      for (int k = 0; k < K; ++k) {
+        int p = pair_fwd[(size_t)k * n_out + o];
+        if (p < 0) continue;
+        float *dx = grad_in + (size_t)p * cin;
+        for (int co = 0; co < cout; ++co) {
+          float g = dy[co];
+          const float *wr = weight + ((size_t)co * K + k) * cin;
+          for (int ci = 0; ci < cin; ++ci) dx[ci] += g * wr[ci];
+        }
+      }
+    }
+  }
+  if (grad_w) {
+    int fail = 0;
+#pragma omp parallel for schedule(dynamic)
+    for (int k = 0; k < K; ++k) {
+      double *acc = (double *)calloc((size_t)cout * cin, sizeof(double));
+      if (!acc) { fail = 1; continue; }
+      for (int o = 0; o < n_out; ++o) {
+        int p = pair_fwd[(size_t)k * n_out + o];
+        if (p < 0) continue;
+        const float *x = feat + (size_t)p * cin;
+        const float *dy = grad_out + (size_t)o * cout;
+        for (int co = 0; co < cout; ++co) {
+          double g = dy[co];
+          double *ar = acc + (size_t)co * cin;
+          for (int ci = 0; ci < cin; ++ci) ar[ci] += g * (double)x[ci];
+        }
+      }
+      for (int co = 0; co < cout; ++co)
+        for (int ci = 0; ci < cin; ++ci)
+          grad_w[((size_t)co * K + k) * cin + ci] = (float)acc[(size_t)co * cin + ci];
+      free(acc);
+    }
+    if (fail) return -1;
+  }
+  return 0;
+}
+
+/* pair_bwd (K, n_in): pair_bwd[k,i] = o with pair_fwd[k,o] = i, else -1 (at most one such o per
+ * (k,i): o = (i + pad - k*dil) / stride).  What spconv-2.x returns next to pair_fwd
+ * (bug_fix/conv.py:382-415). */
+void orc_pair_transpose(const int *pair_fwd, int K, int n_out, int n_in, int *pair_bwd) {
+  for (size_t t = 0; t < (size_t)K * n_in; ++t) pair_bwd[t] = -1;
+  for (int k = 0; k < K; ++k)
+    for (int o = 0; o < n_out; ++o) {
+      int p = pair_fwd[(size_t)k * n_out + o];
+      if (p >= 0 && p < n_in) pair_bwd[(size_t)k * n_in + p] = o;
+    }
+}
+
 /* ------------------------------------------------------------------------- */
 /* furthest point sampling                                                     */
 /* mmdet3d/ops/furthest_point_sample/src/furthest_point_sample_cuda.cu:11-140  */

@@ -55,6 +55,11 @@ def lib():
         L.orc_spconv_fwd.restype = ctypes.c_int
         L.orc_spconv_fwd.argtypes = [f32p, f32p, i32p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                      ctypes.c_int, f32p]
+        L.orc_spconv_bwd.restype = ctypes.c_int
+        L.orc_spconv_bwd.argtypes = [f32p, f32p, i32p, f32p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                     ctypes.c_int, ctypes.c_int, f32p, f32p]
+        L.orc_pair_transpose.restype = None
+        L.orc_pair_transpose.argtypes = [i32p, ctypes.c_int, ctypes.c_int, ctypes.c_int, i32p]
         L.orc_fps_block.restype = ctypes.c_int
         L.orc_fps_block.argtypes = [ctypes.c_int]
         L.orc_fps.restype = ctypes.c_int
@@ -195,6 +200,42 @@ def spconv_fwd(features, weight, pair_fwd):
     r = lib().orc_spconv_fwd(_fp(features), _fp(weight), _ip(pair_fwd), n_out, cin, cout, K, _fp(out))
     assert r == 0
     return out
+
+
+def spconv_bwd(features, weight, pair_fwd, grad_out, need_input_grad=True, need_weight_grad=True):
+    """Backward of ``spconv_fwd`` (config 5; arithmetic as the vendored spconv-1.x
+    ``indiceConvBackward``, mmdet3d/ops/spconv/include/spconv/spconv_ops.h:364-457).
+    Returns (grad_features (N_in,Cin) | None, grad_weight KRSC | None)."""
+    features, weight, pair_fwd, grad_out = _f32(features), _f32(weight), _i32(pair_fwd), _f32(grad_out)
+    cout, cin = weight.shape[0], weight.shape[-1]
+    K, n_out = pair_fwd.shape
+    assert grad_out.shape == (n_out, cout) and features.shape[1] == cin
+    gi = np.empty(features.shape, np.float32) if need_input_grad else None
+    gw = np.zeros(weight.shape, np.float32) if need_weight_grad else None
+    r = lib().orc_spconv_bwd(_fp(features), _fp(weight), _ip(pair_fwd), _fp(grad_out), features.shape[0],
+                             n_out, cin, cout, K, _fp(gi) if gi is not None else None,
+                             _fp(gw) if gw is not None else None)
+    assert r == 0
+    return gi, gw
+
+
+def pair_transpose(pair_fwd, n_in):
+    """pair_bwd (K,N_in): the output row that reads input row i through offset k, or -1."""
+    pair_fwd = _i32(pair_fwd)
+    K, n_out = pair_fwd.shape
+    out = np.empty((K, n_in), np.int32)
+    lib().orc_pair_transpose(_ip(pair_fwd), K, n_out, int(n_in), _ip(out))
+    return out
+
+
+def batchnorm_train(x, weight, bias, eps):
+    """torch.nn.BatchNorm1d in training mode over active-voxel rows: biased batch variance for the
+    normalisation (SURVEY 8c hazard 6).  Returns (y, batch_mean, biased batch_var)."""
+    x64 = x.astype(np.float64)
+    mean = x64.mean(0)
+    var = x64.var(0)
+    y = (x64 - mean) / np.sqrt(var + eps) * weight.astype(np.float64) + bias.astype(np.float64)
+    return y.astype(np.float32), mean.astype(np.float32), var.astype(np.float32)
 
 
 def batchnorm_eval(x, weight, bias, mean, var, eps):

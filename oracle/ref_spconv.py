@@ -96,3 +96,34 @@ def conv(indices, features, weight_krsc, spatial_shape, batch_size, ksize, strid
         order = np.argsort(lin, kind='stable')
         oi, of = oi[order], of[order]
     return oi, of, out_shape
+
+
+def conv_backward(indices, features, weight_krsc, grad_out_sorted, spatial_shape, batch_size, ksize, stride=1,
+                  padding=0, dilation=1, subm=False):
+    """The reference's ``indice_conv_backward_fp32`` (spconv_ops.h:364-457) on the CPU.
+    ``grad_out_sorted`` is given in the row order ``conv`` returns (ascending linear index for strided
+    convs, input order for SubM).  Returns (grad_features (N_in,Cin), grad_weight KRSC)."""
+    m = module()
+    assert m is not None, 'reference spconv-1.x is not built (needs /root/reference)'
+    ks, st, pd, dl = _triple(ksize), _triple(stride), _triple(padding), _triple(dilation)
+    shape = [int(s) for s in spatial_shape]
+    if subm:
+        out_shape = shape
+    else:
+        out_shape = [(shape[i] + 2 * pd[i] - dl[i] * (ks[i] - 1) - 1) // st[i] + 1 for i in range(3)]
+    idx = torch.from_numpy(np.ascontiguousarray(indices, np.int32))
+    feat = torch.from_numpy(np.ascontiguousarray(features, np.float32))
+    w = torch.from_numpy(np.ascontiguousarray(weight_krsc, np.float32))
+    filters = w.permute(1, 2, 3, 4, 0).contiguous()  # [kz,ky,kx,Cin,Cout]
+    outids, pairs, pair_num = m.get_indice_pairs_3d(idx, int(batch_size), out_shape, shape, ks, st, pd, dl,
+                                                    [0, 0, 0], int(subm), 0)
+    g = np.ascontiguousarray(grad_out_sorted, np.float32)
+    if not subm:  # un-sort: the reference's own output rows are in first-touch order
+        oi = outids.numpy().astype(np.int64)
+        lin = ((oi[:, 0] * out_shape[0] + oi[:, 1]) * out_shape[1] + oi[:, 2]) * out_shape[2] + oi[:, 3]
+        order = np.argsort(lin, kind='stable')
+        native = np.empty_like(g)
+        native[order] = g
+        g = native
+    gin, gfil = m.indice_conv_backward_fp32(feat, filters, torch.from_numpy(g), pairs, pair_num, 0, int(subm))
+    return gin.numpy().astype(np.float32), gfil.permute(4, 0, 1, 2, 3).contiguous().numpy().astype(np.float32)

@@ -690,3 +690,133 @@ def test_spp_module_matches_reference_class_live():
     x = torch.randn(1, 640, 40, 40)
     with torch.no_grad():
         assert torch.equal(ours(x), ref(x))
+
+
+# --------------------------------------------------------------------------------------
+# sparse conv BACKWARD (config 5): the oracle restatement pinned against the reference's vendored
+# spconv-1.x backward (live + committed fixtures) and against autograd through a dense conv3d
+# --------------------------------------------------------------------------------------
+def spconv1x_bwd_goldens():
+    return sorted(glob.glob(os.path.join(GOLDEN, 'spconv1xbwd_*.npz')))
+
+
+def load_bwd_golden(path):
+    """(forward fixture, backward fixture, pair_fwd, n_in) of one spconv1xbwd_<name>.npz."""
+    name = os.path.basename(path)[len('spconv1xbwd_'):-len('.npz')]
+    g = np.load(os.path.join(GOLDEN, f'spconv1x_{name}.npz'))
+    b = np.load(path)
+    idx = g['indices'].astype(np.int32)
+    shape = [int(s) for s in g['spatial_shape']]
+    ks, st, pd = [int(x) for x in g['ksize']], [int(x) for x in g['stride']], [int(x) for x in g['padding']]
+    if int(g['subm']):
+        pair = cpu.subm_rulebook(idx, shape, ks, 1)
+    else:
+        _, pair, _ = cpu.conv_rulebook(idx, shape, ks, st, pd, 1)
+    return g, b, pair, idx.shape[0]
+
+
+def rel_err(got, ref):
+    return float(np.abs(got - ref).max() / max(1.0, np.abs(ref).max()))
+
+
+@pytest.mark.parametrize('path', spconv1x_bwd_goldens(), ids=os.path.basename)
+def test_oracle_conv_backward_matches_reference_spconv1x_golden(path):
+    """Fixtures produced by the reference's own ``indice_conv_backward_fp32``
+    (tests/golden/make_golden_spconv_bwd.py)."""
+    g, b, pair, n_in = load_bwd_golden(path)
+    gi, gw = cpu.spconv_bwd(g['features'], g['weight_krsc'], pair, b['grad_out'].astype(np.float32))
+    assert rel_err(gi, b['grad_features']) < 5e-6
+    assert rel_err(gw, b['grad_weight']) < 5e-6
+
+
+@pytest.mark.skipif(not os.path.isdir('/root/reference/mmdet3d/ops/spconv/src'), reason='reference tree not mounted')
+def test_oracle_conv_backward_matches_reference_spconv1x_live():
+    from oracle import ref_spconv
+    if ref_spconv.module() is None:
+        pytest.skip('reference spconv-1.x could not be built here')
+    rng = np.random.default_rng(22)
+    for (shape, batch, n, cin, cout, ks, st, pd, subm) in (
+            ([7, 18, 18], 2, 700, 8, 12, 3, 1, 1, True), ([7, 18, 18], 2, 700, 8, 16, 3, 2, 1, False),
+            ([9, 12, 12], 1, 400, 4, 6, [3, 1, 1], [2, 1, 1], 0, False)):
+        idx, feat = random_sparse(rng, batch, shape, n, cin)
+        k3 = ks if isinstance(ks, list) else [ks] * 3
+        w = rng.standard_normal((cout, *k3, cin)).astype(np.float32) * 0.2
+        if subm:
+            pair = cpu.subm_rulebook(idx, shape, ks, 1)
+        else:
+            _, pair, _ = cpu.conv_rulebook(idx, shape, ks, st, pd, 1)
+        go = rng.standard_normal((pair.shape[1], cout)).astype(np.float32)
+        ri, rw = ref_spconv.conv_backward(idx, feat, w, go, shape, batch, ks, st, pd, 1, subm)
+        gi, gw = cpu.spconv_bwd(feat, w, pair, go)
+        assert rel_err(gi, ri) < 5e-6 and rel_err(gw, rw) < 5e-6
+
+
+@pytest.mark.parametrize('subm,ksize,stride,padding', [(True, 3, 1, 1), (False, 3, 2, 1),
+                                                       (False, (3, 1, 1), (2, 1, 1), 0), (False, 3, 2, (0, 1, 1))])
+def test_conv_backward_vs_dense_autograd(subm, ksize, stride, padding):
+    """Independent pin: d/dx, d/dW of a dense conv3d (float64 autograd) sampled at the active rows."""
+    rng = np.random.default_rng(3)
+    shape, batch, cin, cout = [7, 12, 10], 2, 5, 6
+    idx, feat = random_sparse(rng, batch, shape, 300, cin)
+    ks = cpu._triple(ksize)
+    w = rng.standard_normal((cout, *ks, cin)).astype(np.float32)
+    if subm:
+        pair, out_idx = cpu.subm_rulebook(idx, shape, ksize, 1), idx
+    else:
+        out_idx, pair, _ = cpu.conv_rulebook(idx, shape, ksize, stride, padding, 1)
+    go = rng.standard_normal((out_idx.shape[0], cout)).astype(np.float32)
+    gi, gw = cpu.spconv_bwd(feat, w, pair, go)
+
+    ft = torch.from_numpy(feat).double().requires_grad_(True)
+    li = torch.from_numpy(idx.astype(np.int64))
+    x = torch.zeros(batch, *shape, cin, dtype=torch.float64)          # channels last, then permute
+    x = x.index_put((li[:, 0], li[:, 1], li[:, 2], li[:, 3]), ft).permute(0, 4, 1, 2, 3)
+    wt = torch.from_numpy(w).double().requires_grad_(True)
+    y = F.conv3d(x, wt.permute(0, 4, 1, 2, 3), stride=cpu._triple(stride), padding=cpu._triple(padding))
+    lo = torch.from_numpy(out_idx.astype(np.int64))
+    rows = y[lo[:, 0], :, lo[:, 1], lo[:, 2], lo[:, 3]]
+    (rows * torch.from_numpy(go).double()).sum().backward()
+    assert rel_err(gi, ft.grad.numpy()) < 1e-5
+    assert rel_err(gw, wt.grad.numpy()) < 1e-5
+
+
+def test_pair_transpose_and_dgrad_as_forward():
+    """dgrad = the FORWARD contraction over pair_bwd with the weight transposed (Cin <-> Cout): the
+    identity the CUDA path relies on to reuse its forward kernels for msmd_spconv_bwd_data.  For SubM
+    pair_bwd is pair_fwd with the kernel offsets reversed (o reads i through k  <=>  i reads o through
+    K-1-k)."""
+    rng = np.random.default_rng(5)
+    shape, batch, cin, cout = [7, 14, 12], 2, 6, 9
+    idx, feat = random_sparse(rng, batch, shape, 500, cin)
+    for subm in (True, False):
+        ks = [3, 3, 3]
+        w = rng.standard_normal((cout, *ks, cin)).astype(np.float32)
+        if subm:
+            pair = cpu.subm_rulebook(idx, shape, 3, 1)
+        else:
+            _, pair, _ = cpu.conv_rulebook(idx, shape, 3, 2, 1, 1)
+        pb = cpu.pair_transpose(pair, idx.shape[0])
+        K, n_out = pair.shape
+        for k in range(K):  # definition
+            o = np.nonzero(pair[k] >= 0)[0]
+            assert np.array_equal(pb[k, pair[k, o]], o)
+            assert (pb[k] >= 0).sum() == o.shape[0]
+        if subm:
+            assert np.array_equal(pb, pair[::-1])
+        go = rng.standard_normal((n_out, cout)).astype(np.float32)
+        gi, _ = cpu.spconv_bwd(feat, w, pair, go, need_weight_grad=False)
+        wt = np.ascontiguousarray(np.transpose(w, (4, 1, 2, 3, 0)))  # [Cin,kz,ky,kx,Cout]
+        assert rel_err(cpu.spconv_fwd(go, wt, pb), gi) < 1e-5
+
+
+def test_batchnorm_train_matches_torch():
+    rng = np.random.default_rng(6)
+    x = rng.standard_normal((257, 12)).astype(np.float32) * 3 + 1
+    bn = torch.nn.BatchNorm1d(12, eps=1e-3, momentum=0.01).train()
+    with torch.no_grad():
+        bn.weight.uniform_(0.5, 1.5)
+        bn.bias.normal_()
+    y = bn(torch.from_numpy(x)).detach().numpy()
+    got, mean, var = cpu.batchnorm_train(x, bn.weight.detach().numpy(), bn.bias.detach().numpy(), 1e-3)
+    assert np.abs(got - y).max() < 1e-5
+    assert np.abs(mean * 0.01 - bn.running_mean.numpy()).max() < 1e-6
