@@ -160,6 +160,47 @@ MSMD_API int msmd_spconv_fwd_tc_ws(const float* features, int n_in, const float*
                                    msmd_stream_t stream);
 
 /* ------------------------------------------------------------------------------------
+ * Sparse convolution BACKWARD (config 5, the train step) -- replaces the backward of
+ * Fsp.implicit_gemm (call site bug_fix/conv.py:442-447; spconv-2.x differentiates through
+ * pair_bwd / mask_argsort_bwd_splits, bug_fix/conv.py:382-415).  Arithmetic as the vendored
+ * spconv-1.x indiceConvBackward (mmdet3d/ops/spconv/include/spconv/spconv_ops.h:364-457).
+ *
+ *   msmd_rulebook_transpose     pair_bwd (kvol, n_in): pair_bwd[k,i] = o with pair_fwd[k,o] = i,
+ *                               else -1 (what get_indice_pairs_implicit_gemm returns as pair_bwd).
+ *                               SubM layers do not need it: pair_bwd[k] == pair_fwd[kvol-1-k].
+ *   msmd_spconv_transpose_weight  W[co,k,ci] -> Wt[ci,k',co], k' = flip_k ? kvol-1-k : k (a KRSC
+ *                               weight with the channel roles swapped; feed it to
+ *                               msmd_spconv_pack_weight / msmd_spconv_tc_pack_weight).
+ *   msmd_spconv_bwd_data        grad_in (n_in,cin) = forward contraction of grad_out over pair_bwd
+ *                               with the packed transposed weight (weight_tc: 1 = tensor-core image,
+ *                               workspace as msmd_spconv_fwd_tc_ws with (n_in, cin); 0 = SIMT layout).
+ *   msmd_spconv_bwd_weight      grad_weight KRSC [cout,kvol,cin] = sum over pairs of
+ *                               grad_out[o,co] * features[i,ci]; deterministic (partial tiles in
+ *                               `workspace`, msmd_spconv_bwd_weight_workspace() bytes, summed in a
+ *                               fixed order).  Exact fp32 (FFMA).
+ * ---------------------------------------------------------------------------------- */
+MSMD_API int msmd_rulebook_transpose(const int* pair_fwd, int kvol, int n_out, int n_in,
+                                     int* pair_bwd, msmd_stream_t stream);
+MSMD_API int msmd_spconv_transpose_weight(const float* weight_krsc, int cout, int kvol, int cin,
+                                          int flip_k, float* weight_t, msmd_stream_t stream);
+MSMD_API int msmd_spconv_bwd_data(const float* grad_out, int n_out, const float* packed_wt,
+                                  int weight_tc, const int* pair_bwd, int n_in, int cin, int cout,
+                                  int kvol, float* grad_in, void* workspace, size_t workspace_bytes,
+                                  msmd_stream_t stream);
+MSMD_API size_t msmd_spconv_bwd_weight_workspace(int n_out, int cin, int cout, int kvol);
+MSMD_API int msmd_spconv_bwd_weight(const float* features, int n_in, const float* grad_out,
+                                    const int* pair_fwd, int n_out, int cin, int cout, int kvol,
+                                    float* grad_weight_krsc, void* workspace, size_t workspace_bytes,
+                                    msmd_stream_t stream);
+/* Backward of msmd_to_dense: rows (n,c) gathered out of a (batch, c, D, H, W) gradient. */
+MSMD_API int msmd_from_dense(const int* indices, const float* dense, int n, int c, int batch_size,
+                             const int* spatial_shape, float* out, msmd_stream_t stream);
+/* Row of each voxel in a bit grid's ascending order (-1 = absent): the gather map that the backward
+ * of Fsp.sparse_add needs (grad_a = grad_out[rows_a], grad_b = grad_out[rows_b]). */
+MSMD_API int msmd_grid_rows(const int* indices, int n, int batch_size, const int* spatial_shape,
+                            const uint32_t* bits, const int* prefix, int* rows, msmd_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
  * Native executor for a chain of sparse convolutions -- the host loop of
  * SparseEncoder.forward (mmdet3d/models/middle_encoders/sparse_encoder.py:96-133) and of the
  * SparseSequential / SparseBasicBlock modules it is built from (mmdet3d/ops/sparse_block.py:

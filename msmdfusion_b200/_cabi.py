@@ -59,6 +59,13 @@ SIGNATURES = {
     'msmd_spconv_fwd_tc': (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _vp]),
     'msmd_spconv_tc_workspace': (_sz, [_i, _i]),
     'msmd_spconv_fwd_tc_ws': (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _sz, _vp]),
+    'msmd_rulebook_transpose': (_i, [_vp, _i, _i, _i, _vp, _vp]),
+    'msmd_spconv_transpose_weight': (_i, [_vp, _i, _i, _i, _i, _vp, _vp]),
+    'msmd_spconv_bwd_data': (_i, [_vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _sz, _vp]),
+    'msmd_spconv_bwd_weight_workspace': (_sz, [_i, _i, _i, _i]),
+    'msmd_spconv_bwd_weight': (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _sz, _vp]),
+    'msmd_from_dense': (_i, [_vp, _vp, _i, _i, _i, _c_int_p, _vp, _vp]),
+    'msmd_grid_rows': (_i, [_vp, _i, _i, _c_int_p, _vp, _vp, _vp, _vp]),
     'msmd_sparse_net_forward': (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _c_int_p, _vp, _sz, _vp, _vp]),
     'msmd_to_dense': (_i, [_vp, _vp, _i, _i, _i, _c_int_p, _vp, _vp]),
     'msmd_fps_workspace': (_sz, [_i]),

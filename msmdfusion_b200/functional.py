@@ -2,6 +2,7 @@
 ``mmdet3d/models/middle_encoders/sparse_multimodal_encoder_painting.py:12``)."""
 import torch
 
+from . import autograd as _ag
 from . import ops
 from . import spconv as _sp
 
@@ -20,9 +21,15 @@ def sparse_add(a, b):
     assert a.features.shape[1] == b.features.shape[1], 'sparse_add: channel sizes differ'
     ia = a.indices if a.indices.dtype == torch.int32 else a.indices.int()
     ib = b.indices if b.indices.dtype == torch.int32 else b.indices.int()
-    out_idx, out_feat, grid = ops.sparse_add(ia, a.features, ib, b.features, a.spatial_shape,
-                                             a.batch_size)
+    if torch.is_grad_enabled() and (a.features.requires_grad or b.features.requires_grad):
+        holder = {}   # train step: Fsp.sparse_add is differentiable w.r.t. both feature tensors
+        out_feat = _ag.SparseAddFunction.apply(a.features, b.features, ia.contiguous(), ib.contiguous(),
+                                               a.spatial_shape, a.batch_size, holder)
+        out_idx, grid = holder['out_idx'], holder['grid']
+    else:
+        out_idx, out_feat, grid = ops.sparse_add(ia, a.features, ib, b.features, a.spatial_shape,
+                                                 a.batch_size)
     out = _sp.SparseConvTensor(out_feat, out_idx, a.spatial_shape, a.batch_size,
                                benchmark=a.benchmark)
-    _sp._attach_iset(out, _sp.IndexSet(out_idx, a.spatial_shape, a.batch_size, grid=grid))
+    _sp._attach_iset(out, _sp.IndexSet(out_idx, a.spatial_shape, a.batch_size, grid=grid, unique=True))
     return out

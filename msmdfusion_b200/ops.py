@@ -292,6 +292,112 @@ def to_dense(indices, features, spatial_shape, batch_size):
 
 
 # --------------------------------------------------------------------------------------
+# sparse conv backward (config 5: the train step), dense() / sparse_add backward helpers
+# reference: Fsp.implicit_gemm backward through pair_bwd (bug_fix/conv.py:382-415,442-447);
+# arithmetic of mmdet3d/ops/spconv/include/spconv/spconv_ops.h:364-457
+# --------------------------------------------------------------------------------------
+def rulebook_transpose(pair_fwd, n_in):
+    """pair_fwd (K,N_out) -> pair_bwd (K,N_in): the output row reading input row i through offset k."""
+    pair_fwd = pair_fwd.contiguous()
+    assert pair_fwd.dtype == torch.int32 and pair_fwd.dim() == 2
+    kvol, n_out = pair_fwd.shape
+    pair_bwd = torch.empty((kvol, int(n_in)), dtype=torch.int32, device=pair_fwd.device)
+    with _Timed('rulebook_transpose', n_in=int(n_in), n_out=n_out, kvol=kvol):
+        check(lib().msmd_rulebook_transpose(ptr(pair_fwd), kvol, n_out, int(n_in), ptr(pair_bwd),
+                                            stream(pair_fwd.device)), 'msmd_rulebook_transpose')
+    return pair_bwd
+
+
+def transpose_weight(weight, flip_k=False):
+    """KRSC [Cout,kz,ky,kx,Cin] -> [Cin,kz,ky,kx,Cout] (kernel offsets reversed when ``flip_k``):
+    the weight whose FORWARD contraction over pair_bwd is the data gradient."""
+    w = weight.detach()
+    if w.dtype != torch.float32:
+        w = w.float()
+    w = w.contiguous()
+    cout, cin = w.shape[0], w.shape[-1]
+    kvol = w.numel() // (cout * cin)
+    wt = torch.empty((cin, *w.shape[1:-1], cout), dtype=torch.float32, device=w.device)
+    check(lib().msmd_spconv_transpose_weight(ptr(w), cout, kvol, cin, int(bool(flip_k)), ptr(wt),
+                                             stream(w.device)), 'msmd_spconv_transpose_weight')
+    return wt
+
+
+def spconv_bwd_data(grad_out, packed_wt, pair_bwd):
+    """grad_in (N_in,Cin): forward contraction of grad_out (N_out,Cout) over pair_bwd (K,N_in) with the
+    packed TRANSPOSED weight (``pack_weight`` / ``pack_weight_tc`` of ``transpose_weight``)."""
+    grad_out = grad_out.contiguous()
+    if grad_out.dtype != torch.float32:
+        grad_out = grad_out.float()
+    pair_bwd = pair_bwd.contiguous()
+    n_in = pair_bwd.shape[1]
+    if isinstance(packed_wt, TcWeight):
+        cin, cout, kvol, tc, wbuf = packed_wt.cout, packed_wt.cin, packed_wt.kvol, 1, packed_wt.packed
+    else:
+        kvol, cout, cin = packed_wt.shape
+        tc, wbuf = 0, packed_wt
+    assert grad_out.shape[1] == cout and pair_bwd.shape[0] == kvol and pair_bwd.dtype == torch.int32
+    grad_in = torch.empty((n_in, cin), dtype=torch.float32, device=grad_out.device)
+    with _Timed('spconv_bwd_data', n_in=n_in, n_out=grad_out.shape[0], cin=cin, cout=cout, kvol=kvol,
+                pair=pair_bwd, path='tc' if tc else 'simt'):
+        need = lib().msmd_spconv_tc_workspace(n_in, cin) if tc else 0
+        ws = scratch.get(grad_out.device, need, slot='tc_ws') if need else None
+        check(lib().msmd_spconv_bwd_data(ptr(grad_out), grad_out.shape[0], ptr(wbuf), tc, ptr(pair_bwd),
+                                         n_in, cin, cout, kvol, ptr(grad_in), ptr(ws),
+                                         ws.numel() if ws is not None else 0, stream(grad_out.device)),
+              'msmd_spconv_bwd_data')
+    return grad_in
+
+
+def spconv_bwd_weight(features, grad_out, pair_fwd, weight_shape):
+    """grad_weight in the parameter's KRSC shape; deterministic, exact fp32."""
+    features, grad_out, pair_fwd = features.contiguous(), grad_out.contiguous(), pair_fwd.contiguous()
+    if features.dtype != torch.float32:
+        features = features.float()
+    if grad_out.dtype != torch.float32:
+        grad_out = grad_out.float()
+    cout, cin = int(weight_shape[0]), int(weight_shape[-1])
+    kvol, n_out = pair_fwd.shape
+    assert features.shape[1] == cin and grad_out.shape == (n_out, cout) and pair_fwd.dtype == torch.int32
+    grad_w = torch.empty(tuple(weight_shape), dtype=torch.float32, device=features.device)
+    assert grad_w.numel() == cout * kvol * cin
+    need = lib().msmd_spconv_bwd_weight_workspace(n_out, cin, cout, kvol)
+    ws = scratch.get(features.device, need, slot='wgrad_ws')
+    with _Timed('spconv_bwd_weight', n_in=features.shape[0], n_out=n_out, cin=cin, cout=cout, kvol=kvol,
+                pair=pair_fwd):
+        check(lib().msmd_spconv_bwd_weight(ptr(features), features.shape[0], ptr(grad_out), ptr(pair_fwd),
+                                           n_out, cin, cout, kvol, ptr(grad_w), ptr(ws), ws.numel(),
+                                           stream(features.device)), 'msmd_spconv_bwd_weight')
+    return grad_w
+
+
+def from_dense(indices, dense, spatial_shape, batch_size):
+    """Backward of ``to_dense``: (B,C,D,H,W) -> the active rows (n,C)."""
+    indices = _indices_ok(indices)
+    dense = dense.contiguous().float()
+    n, c = indices.shape[0], dense.shape[1]
+    d, h, w = _triple(spatial_shape)
+    assert tuple(dense.shape) == (int(batch_size), c, d, h, w)
+    out = torch.empty((n, c), dtype=torch.float32, device=dense.device)
+    with _Timed('from_dense', n=n, c=c):
+        check(lib().msmd_from_dense(ptr(indices), ptr(dense), n, c, int(batch_size), ints([d, h, w]),
+                                    ptr(out), stream(dense.device)), 'msmd_from_dense')
+    return out
+
+
+def grid_rows(indices, grid):
+    """Row of each voxel in ``grid``'s ascending order (int64, -1 = absent)."""
+    indices = _indices_ok(indices)
+    n = indices.shape[0]
+    rows = torch.empty((n,), dtype=torch.int32, device=indices.device)
+    with _Timed('grid_rows', n=n):
+        check(lib().msmd_grid_rows(ptr(indices), n, grid.batch_size, ints(grid.spatial_shape),
+                                   ptr(grid.bits), ptr(grid.prefix), ptr(rows), stream(indices.device)),
+              'msmd_grid_rows')
+    return rows.long()
+
+
+# --------------------------------------------------------------------------------------
 # FPS / ball query / nearest 3-D voxel (fps_NN_fast, painting.py:276-323)
 # --------------------------------------------------------------------------------------
 def furthest_point_sample_single(xyz, m):

@@ -17,7 +17,6 @@ B200-first differences that cannot change results:
 """
 import math
 import os
-import warnings
 from collections import OrderedDict
 
 import torch
@@ -25,6 +24,7 @@ from torch import nn
 from torch.nn import init
 from torch.nn.parameter import Parameter
 
+from . import autograd as _ag
 from . import ops
 from .registry import CONV_LAYERS
 
@@ -59,12 +59,15 @@ class IndiceData:
 class IndexSet:
     """One set of active voxels: (N,4) int32 indices + its bit grid + cached SubM rulebooks."""
 
-    def __init__(self, indices, spatial_shape, batch_size, grid=None):
+    def __init__(self, indices, spatial_shape, batch_size, grid=None, unique=False):
         self.indices = indices
         self.spatial_shape = list(spatial_shape)
         self.batch_size = int(batch_size)
         self._grid = grid
         self._subm = {}
+        # True when the rows are known to be distinct voxels (enumerated from a bit grid: strided-conv
+        # outputs, sparse_add); user-assigned index lists may repeat a coordinate
+        self.unique = bool(unique)
 
     @property
     def grid(self):
@@ -80,6 +83,16 @@ class IndexSet:
             pair = ops.rulebook_subm(self.indices, self.grid, ksize, dilation)
             self._subm[key] = pair
         return pair
+
+    def rulebook_record(self, pair, subm, ksize, dilation, path):
+        """The dict ``autograd.SparseConvFunction`` differentiates through.  One record per rulebook
+        tensor, so that the transposed table of a strided conv is built once however many layers or
+        backward passes use it."""
+        recs = self.__dict__.setdefault('_records', {})
+        rec = recs.get(id(pair))
+        if rec is None or rec['pair_fwd'] is not pair:
+            rec = recs[id(pair)] = dict(pair_fwd=pair, subm=bool(subm), path=path, unique=self.unique)
+        return rec
 
 
 class SparseConvTensor:
@@ -148,7 +161,11 @@ class SparseConvTensor:
 
     def dense(self, channels_first=True):
         idx = self._indices if self._indices.dtype == torch.int32 else self._indices.int()
-        out = ops.to_dense(idx, self._features, self.spatial_shape, self.batch_size)
+        if torch.is_grad_enabled() and self._features.requires_grad:
+            out = _ag.ToDenseFunction.apply(self._features, idx.contiguous(), self.spatial_shape,
+                                            self.batch_size)
+        else:
+            out = ops.to_dense(idx, self._features, self.spatial_shape, self.batch_size)
         if not channels_first:
             return out.permute(0, 2, 3, 4, 1).contiguous()
         return out
@@ -367,8 +384,9 @@ class SparseConvolution(SparseModule):
         assert isinstance(input, SparseConvTensor)
         assert input.features.shape[1] == self.in_channels, 'channel size mismatch'
         features = input.features
-        if torch.is_grad_enabled() and (features.requires_grad or self.weight.requires_grad):
-            _warn_no_backward()
+        # train step (config 5): differentiate through the convolution; the epilogue terms become
+        # plain torch ops so that autograd sees them
+        with_grad = torch.is_grad_enabled() and (features.requires_grad or self.weight.requires_grad)
         if self.conv1x1:
             out = torch.mm(features, self.weight.view(self.out_channels, self.in_channels).T)
             if self.bias is not None:
@@ -408,13 +426,23 @@ class SparseConvolution(SparseModule):
             out_indices, pair, out_grid = ops.rulebook_conv(
                 iset.indices, iset.grid, self.kernel_size, self.stride, self.padding, self.dilation)
             out_shape = out_grid.spatial_shape
-            out_iset = IndexSet(out_indices, out_shape, input.batch_size, grid=out_grid)
+            out_iset = IndexSet(out_indices, out_shape, input.batch_size, grid=out_grid, unique=True)
             if self.indice_key is not None:
                 indice_dict[self.indice_key] = IndiceData(
                     out_indices, iset.indices, pair, False, input.spatial_shape, out_shape,
                     self.kernel_size, self.stride, self.padding, self.dilation)
-        out_features = ops.spconv_fwd(features, self.packed_weight(), pair, scale, shift, residual,
-                                      relu)
+        if with_grad:
+            rb = iset.rulebook_record(pair, self.subm, self.kernel_size, self.dilation, CONV_PATH)
+            out_features = _ag.SparseConvFunction.apply(features, self.weight, self.packed_weight(), rb)
+            if scale is not None:
+                out_features = out_features * scale + shift
+            if residual is not None:
+                out_features = out_features + residual
+            if relu:
+                out_features = torch.relu(out_features)
+        else:
+            out_features = ops.spconv_fwd(features, self.packed_weight(), pair, scale, shift, residual,
+                                          relu)
         out = SparseConvTensor(out_features, out_iset.indices, out_shape, input.batch_size,
                                indice_dict=indice_dict, benchmark=input.benchmark)
         out.benchmark_record = input.benchmark_record
@@ -436,16 +464,6 @@ class SparseConvolution(SparseModule):
         if inp.indices.shape[0] != datas.indices.shape[0]:
             raise ValueError(f'subm with same indice_key must have same num of indices, expect '
                              f'{datas.indices.shape[0]}, input {inp.indices.shape[0]}')
-
-
-_WARNED = [False]
-
-
-def _warn_no_backward():
-    if not _WARNED[0]:
-        _WARNED[0] = True
-        warnings.warn('msmdfusion_b200 sparse convolution: backward is not implemented yet; '
-                      'outputs are detached (run under torch.no_grad() for inference).')
 
 
 @CONV_LAYERS.register_module()
