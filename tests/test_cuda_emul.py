@@ -1,0 +1,283 @@
+"""CPU tests that RUN the SIMT CUDA kernels of the train step on a host emulation of the CUDA execution
+model (tests/tools/cuda_emul: one std::thread per CUDA thread, std::barrier for __syncthreads, warp
+shuffles through an exchange buffer; the .cu sources are compiled as they are, launches rewritten by a
+script).  Purpose: the backward kernels were written in a session without GPU time, so their indexing,
+barrier placement and host-side launch logic are checked here against the oracle; the emulator itself
+is calibrated on the forward SIMT kernel, which is verified on the B200 by the ``-m gpu`` tests.
+Tensor-core / TMA / cluster kernels cannot be emulated and are not covered."""
+import ctypes
+import importlib.util
+import os
+
+import numpy as np
+import pytest
+
+from oracle import cpu
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+def emu():
+    global _LIB
+    if _LIB is None:
+        spec = importlib.util.spec_from_file_location('emul_build', os.path.join(HERE, 'tools', 'cuda_emul', 'build.py'))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        _LIB = ctypes.CDLL(mod.build())
+        _LIB.emu_last_error.restype = ctypes.c_char_p
+        _LIB.emu_msmd_spconv_bwd_weight_workspace.restype = ctypes.c_size_t
+    return _LIB
+
+
+def P(a):
+    return a.ctypes.data_as(ctypes.c_void_p) if a is not None else None
+
+
+def ok(status):
+    assert status == 0, emu().emu_last_error()
+
+
+def random_sparse(seed, batch, shape, n, c):
+    rng = np.random.default_rng(seed)
+    D, H, W = shape
+    lin = rng.choice(batch * D * H * W, size=n, replace=False)
+    idx = np.stack([lin // (D * H * W), (lin // (H * W)) % D, (lin // W) % H, lin % W], 1).astype(np.int32)
+    return idx, rng.standard_normal((n, c)).astype(np.float32)
+
+
+def rel(a, b):
+    return float(np.abs(a - b).max() / max(1.0, np.abs(b).max()))
+
+
+def emu_pack(w):
+    cout, cin = w.shape[0], w.shape[-1]
+    kvol = w.size // (cout * cin)
+    packed = np.empty((kvol, cin, cout), np.float32)
+    ok(emu().emu_msmd_spconv_pack_weight(P(w), cout, kvol, cin, P(packed), None))
+    return packed
+
+
+def emu_fwd(feat, w, pair, scale=None, shift=None, residual=None, relu=0):
+    cout, cin = w.shape[0], w.shape[-1]
+    kvol, n_out = pair.shape
+    out = np.full((n_out, cout), np.nan, np.float32)
+    ok(emu().msmd_spconv_fwd(P(feat), feat.shape[0], P(emu_pack(w)), P(pair), n_out, cin, cout, kvol, P(scale),
+                             P(shift), P(residual), relu, P(out), None))
+    return out
+
+
+@pytest.mark.parametrize('cin,cout', [(5, 16), (16, 32), (8, 72)])
+def test_emulator_calibration_forward_simt_kernel(cin, cout):
+    """The GPU-verified forward kernel, run on the emulator, reproduces the oracle (incl. the fused
+    scale / shift / residual / ReLU epilogue) -- i.e. the emulator executes this code base faithfully."""
+    shape, batch = [7, 14, 14], 2
+    idx, feat = random_sparse(0, batch, shape, 500, cin)
+    rng = np.random.default_rng(1)
+    w = (rng.standard_normal((cout, 3, 3, 3, cin)) * 0.2).astype(np.float32)
+    pair = cpu.subm_rulebook(idx, shape, 3, 1)
+    ref = cpu.spconv_fwd(feat, w, pair)
+    assert rel(emu_fwd(feat, w, pair), ref) < 1e-5
+    scale = rng.uniform(0.5, 1.5, cout).astype(np.float32)
+    shift = rng.standard_normal(cout).astype(np.float32)
+    res = rng.standard_normal(ref.shape).astype(np.float32)
+    got = emu_fwd(feat, w, pair, scale, shift, res, 1)
+    assert rel(got, np.maximum(ref * scale + shift + res, 0)) < 1e-5
+
+
+@pytest.mark.parametrize('cin,cout,ksize,subm,n', [(8, 12, 3, True, 700), (5, 6, 3, True, 300),
+                                                    (16, 16, 3, False, 900), (68, 72, (3, 1, 1), True, 600),
+                                                    (4, 4, 3, True, 40)])
+def test_wgrad_kernel_on_emulator(cin, cout, ksize, subm, n):
+    """msmd_spconv_bwd_weight (row-slice partial tiles + fixed-order reduction): vector and scalar
+    staging paths, multi-tile channels, several row slices, a single short chunk."""
+    shape, batch = [7, 16, 16], 2
+    idx, feat = random_sparse(3, batch, shape, n, cin)
+    rng = np.random.default_rng(4)
+    ks = cpu._triple(ksize)
+    if subm:
+        pair = cpu.subm_rulebook(idx, shape, ks, 1)
+    else:
+        _, pair, _ = cpu.conv_rulebook(idx, shape, ks, 2, 1, 1)
+    kvol, n_out = pair.shape
+    go = rng.standard_normal((n_out, cout)).astype(np.float32)
+    _, ref = cpu.spconv_bwd(feat, np.zeros((cout, *ks, cin), np.float32), pair, go, need_input_grad=False)
+    need = emu().emu_msmd_spconv_bwd_weight_workspace(n_out, cin, cout, kvol)
+    assert need > 0 and need % (kvol * cin * cout * 4) == 0
+    ws = np.full(need // 4, np.nan, np.float32)
+    gw = np.full((cout, *ks, cin), np.nan, np.float32)
+    ok(emu().emu_msmd_spconv_bwd_weight(P(feat), feat.shape[0], P(go), P(pair), n_out, cin, cout, kvol, P(gw),
+                                        P(ws), ctypes.c_size_t(need), None))
+    assert np.isfinite(ws).all(), 'every partial tile must be written (the reduction reads all of them)'
+    assert rel(gw, ref) < 1e-5
+    # too small a workspace is an error, not an overrun
+    assert emu().emu_msmd_spconv_bwd_weight(P(feat), feat.shape[0], P(go), P(pair), n_out, cin, cout, kvol, P(gw),
+                                            P(ws), ctypes.c_size_t(need - 4), None) == -3
+
+
+def test_wgrad_empty_inputs_on_emulator():
+    gw = np.full((4, 27, 3), np.nan, np.float32)
+    ok(emu().emu_msmd_spconv_bwd_weight(None, 0, None, None, 0, 3, 4, 27, P(gw), None, ctypes.c_size_t(0), None))
+    assert (gw == 0).all()
+
+
+@pytest.mark.parametrize('subm', [True, False])
+def test_dgrad_path_on_emulator(subm):
+    """msmd_rulebook_transpose + msmd_spconv_transpose_weight + msmd_spconv_bwd_data (SIMT layout) ==
+    the oracle's data gradient; for SubM the mirrored-offset form needs no second table."""
+    shape, batch, cin, cout = [7, 14, 14], 2, 8, 12
+    idx, feat = random_sparse(5, batch, shape, 500, cin)
+    rng = np.random.default_rng(6)
+    w = (rng.standard_normal((cout, 3, 3, 3, cin)) * 0.2).astype(np.float32)
+    if subm:
+        pair = cpu.subm_rulebook(idx, shape, 3, 1)
+    else:
+        _, pair, _ = cpu.conv_rulebook(idx, shape, 3, 2, 1, 1)
+    kvol, n_out = pair.shape
+    n_in = idx.shape[0]
+    go = rng.standard_normal((n_out, cout)).astype(np.float32)
+    ref, _ = cpu.spconv_bwd(feat, w, pair, go, need_weight_grad=False)
+
+    wt = np.full((cin, 3, 3, 3, cout), np.nan, np.float32)
+    ok(emu().emu_msmd_spconv_transpose_weight(P(w), cout, kvol, cin, int(subm), P(wt), None))
+    w3 = w.reshape(cout, kvol, cin)
+    expect = (w3[:, ::-1] if subm else w3).transpose(2, 1, 0)
+    assert np.array_equal(wt.reshape(cin, kvol, cout), expect)
+    if subm:
+        pair_bwd = pair
+    else:
+        pair_bwd = np.full((kvol, n_in), 7, np.int32)
+        ok(emu().emu_msmd_rulebook_transpose(P(pair), kvol, n_out, n_in, P(pair_bwd), None))
+        assert np.array_equal(pair_bwd, cpu.pair_transpose(pair, n_in))
+    packed = emu_pack(wt)                       # "cout" = cin, "cin" = cout
+    gi = np.full((n_in, cin), np.nan, np.float32)
+    ok(emu().emu_msmd_spconv_bwd_data(P(go), n_out, P(packed), 0, P(pair_bwd), n_in, cin, cout, kvol, P(gi), None,
+                                      ctypes.c_size_t(0), None))
+    assert rel(gi, ref) < 1e-5
+
+
+def test_from_dense_and_grid_rows_on_emulator():
+    shape, batch, c = [5, 9, 11], 2, 7
+    idx, feat = random_sparse(7, batch, shape, 300, c)
+    dense = cpu.dense(idx, feat, shape, batch)
+    out = np.full((idx.shape[0], c), np.nan, np.float32)
+    sh = (ctypes.c_int * 3)(*shape)
+    ok(emu().emu_msmd_from_dense(P(idx), P(dense), idx.shape[0], c, batch, sh, P(out), None))
+    assert np.array_equal(out, feat)
+    # bit grid of a superset (as sparse_add builds it): rank = row in ascending linear order
+    extra, _ = random_sparse(8, batch, shape, 200, 1)
+    D, H, W = shape
+    lin = lambda a: ((a[:, 0].astype(np.int64) * D + a[:, 1]) * H + a[:, 2]) * W + a[:, 3]  # noqa: E731
+    union = np.unique(np.concatenate([lin(idx), lin(extra)]))
+    cells = batch * D * H * W
+    words = (cells + 31) // 32
+    bits = np.zeros(words, np.uint32)
+    np.bitwise_or.at(bits, union >> 5, (np.uint32(1) << (union & 31).astype(np.uint32)))
+    pop = np.array([bin(int(b)).count('1') for b in bits], np.int32)
+    prefix = (np.cumsum(pop) - pop).astype(np.int32)
+    probe = np.concatenate([idx, np.array([[0, 0, 0, 0], [batch, 0, 0, 0], [1, D - 1, H - 1, W - 1]], np.int32)])
+    rows = np.full(probe.shape[0], -7, np.int32)
+    ok(emu().emu_msmd_grid_rows(P(probe), probe.shape[0], batch, sh, P(bits), P(prefix), P(rows), None))
+    pl = lin(probe)
+    pos = np.searchsorted(union, pl)
+    expect = np.where((probe[:, 0] < batch) & (pos < union.size) & (union[np.minimum(pos, union.size - 1)] == pl), pos, -1)
+    assert np.array_equal(rows, expect.astype(np.int32))
+
+
+# --------------------------------------------------------------------------------------
+# the REAL tensor-level wrappers (msmdfusion_b200/ops.py, with the ctypes signatures of _cabi.py)
+# driving the emulated kernels: wrapper argument order / types + kernels, end to end on the CPU
+# --------------------------------------------------------------------------------------
+class _EmuLib:
+    """Looks like ``_cabi.lib()``: msmd_X resolves to the emulated entry with _cabi's own argtypes."""
+
+    def __init__(self, cabi):
+        self._cabi, self._cache = cabi, {}
+
+    def __getattr__(self, name):
+        fn = self._cache.get(name)
+        if fn is None:
+            L = emu()
+            fn = getattr(L, name) if name == 'msmd_spconv_fwd' else getattr(L, 'emu_' + name)
+            fn.restype, fn.argtypes = self._cabi.SIGNATURES[name]
+            self._cache[name] = fn
+        return fn
+
+
+@pytest.fixture()
+def ops_on_emulator(monkeypatch):
+    import torch
+    from msmdfusion_b200 import _cabi, ops
+    shim = _EmuLib(_cabi)
+
+    def ptr(t):
+        if t is None:
+            return None
+        assert t.is_contiguous()
+        return ctypes.c_void_p(t.data_ptr())
+
+    class Scratch:
+        def get(self, device, nbytes, slot='ws'):
+            return torch.empty(max(int(nbytes), 16), dtype=torch.uint8)
+    for mod in (_cabi, ops):
+        monkeypatch.setattr(mod, 'lib', lambda: shim)
+        monkeypatch.setattr(mod, 'ptr', ptr)
+        monkeypatch.setattr(mod, 'stream', lambda device=None: None)
+        monkeypatch.setattr(mod, 'scratch', Scratch())
+    monkeypatch.setattr(ops, 'tc_supported', lambda *a: False)
+    return ops
+
+
+def test_ops_wrappers_drive_emulated_kernels(ops_on_emulator):
+    import torch
+    ops = ops_on_emulator
+    shape, batch, cin, cout = [7, 14, 14], 2, 8, 12
+    idx, feat = random_sparse(9, batch, shape, 400, cin)
+    rng = np.random.default_rng(10)
+    w = (rng.standard_normal((cout, 3, 3, 3, cin)) * 0.2).astype(np.float32)
+    oi, pair, oshape = cpu.conv_rulebook(idx, shape, 3, 2, 1, 1)
+    go = rng.standard_normal((oi.shape[0], cout)).astype(np.float32)
+    t = torch.from_numpy
+    out = ops.spconv_fwd(t(feat), ops.pack_weight(t(w)), t(pair))
+    assert rel(out.numpy(), cpu.spconv_fwd(feat, w, pair)) < 1e-5
+    ri, rw = cpu.spconv_bwd(feat, w, pair, go)
+    pair_bwd = ops.rulebook_transpose(t(pair), idx.shape[0])
+    gi = ops.spconv_bwd_data(t(go), ops.pack_weight(ops.transpose_weight(t(w))), pair_bwd)
+    assert rel(gi.numpy(), ri) < 1e-5
+    gw = ops.spconv_bwd_weight(t(feat), t(go), t(pair), w.shape)
+    assert tuple(gw.shape) == w.shape and rel(gw.numpy(), rw) < 1e-5
+    d = ops.to_dense(t(oi), out, oshape, batch)
+    assert np.array_equal(d.numpy(), cpu.dense(oi, out.numpy(), oshape, batch))
+    assert np.array_equal(ops.from_dense(t(oi), d, oshape, batch).numpy(), out.numpy())
+
+
+def test_conv_autograd_function_on_emulated_kernels(ops_on_emulator, monkeypatch):
+    """SubMConv3d / SparseConv3d modules -> autograd.SparseConvFunction -> real wrappers -> emulated
+    kernels, against the oracle's gradients (rulebooks come from the oracle: the bit-grid kernels use a
+    decoupled look-back scan that a block-sequential emulator cannot run)."""
+    import torch
+    import _cpu_ops
+    from msmdfusion_b200 import spconv
+    ops = ops_on_emulator
+    for name in ('grid_build', 'rulebook_subm', 'rulebook_conv'):
+        monkeypatch.setattr(ops, name, _cpu_ops.STANDINS[name])
+    shape, batch, cin, cout = [7, 12, 12], 1, 4, 8
+    idx, feat = random_sparse(11, batch, shape, 250, cin)
+    idx = np.concatenate([idx, idx[:9]])                 # duplicate coordinates in the SubM case
+    feat = np.concatenate([feat, feat[:9] * 2])
+    for cls, kw in ((spconv.SubMConv3d, dict(padding=1)), (spconv.SparseConv3d, dict(stride=2, padding=1))):
+        torch.manual_seed(0)
+        conv = cls(cin, cout, 3, bias=False, **kw)
+        f = torch.from_numpy(feat).clone().requires_grad_(True)
+        out = conv(spconv.SparseConvTensor(f, torch.from_numpy(idx), shape, batch))
+        g = torch.randn(out.features.shape, generator=torch.Generator().manual_seed(1))
+        (out.features * g).sum().backward()
+        w = conv.weight.detach().numpy()
+        if conv.subm:
+            pair = cpu.subm_rulebook(idx, shape, 3, 1)
+        else:
+            _, pair, _ = cpu.conv_rulebook(idx, shape, 3, 2, 1, 1)
+        ri, rw = cpu.spconv_bwd(feat, w, pair, g.numpy())
+        assert rel(out.features.detach().numpy(), cpu.spconv_fwd(feat, w, pair)) < 1e-5
+        assert rel(f.grad.numpy(), ri) < 1e-5
+        assert rel(conv.weight.grad.numpy(), rw) < 1e-5

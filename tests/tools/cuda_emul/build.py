@@ -1,0 +1,116 @@
+"""TEST INFRASTRUCTURE: builds a host-emulated copy of selected SIMT translation units of
+msmdfusion_b200/csrc (see cuda_emul.h).  The CUDA sources are used as they are: the script takes the
+device helpers of common.cuh and the whole body of the .cu file, rewrites the ``kernel<<<grid, block,
+smem, stream>>>(args)`` launches into ``emu::launch(grid, block, [&]{ kernel(args); })`` and compiles the
+result with g++ -std=c++20.  Entry points keep their C-ABI names with an ``emu_`` prefix."""
+import os
+import re
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(HERE)))
+CSRC = os.path.join(ROOT, 'msmdfusion_b200', 'csrc')
+OUT = os.path.join(HERE, '_build')
+
+
+def _device_helpers():
+    """common.cuh from the '// device helpers' banner to the end of namespace msmd."""
+    text = open(os.path.join(CSRC, 'common.cuh')).read()
+    start = text.index('// device helpers')
+    start = text.index('\n', text.index('// ----', start)) + 1
+    end = text.rindex('}  // namespace msmd')
+    return 'namespace msmd {\n' + text[start:end] + '}  // namespace msmd\n'
+
+
+def _rewrite_launches(src):
+    out, pos = [], 0
+    for m in re.finditer(r'([A-Za-z_]\w*(?:<[^<>;(){}]*>)?)\s*<<<', src):
+        if m.start() < pos:
+            continue
+        cfg_end = src.index('>>>', m.end())
+        cfg = src[m.end():cfg_end]
+        # split the launch configuration at top-level commas
+        parts, depth, cur = [], 0, ''
+        for ch in cfg:
+            if ch in '(<[':
+                depth += 1
+            elif ch in ')>]':
+                depth -= 1
+            if ch == ',' and depth == 0:
+                parts.append(cur)
+                cur = ''
+            else:
+                cur += ch
+        parts.append(cur)
+        p = src.index('(', cfg_end)
+        depth, q = 0, p
+        while True:
+            if src[q] == '(':
+                depth += 1
+            elif src[q] == ')':
+                depth -= 1
+                if depth == 0:
+                    break
+            q += 1
+        args = src[p + 1:q]
+        out.append(src[pos:m.start()])
+        out.append(f'::emu::launch(dim3({parts[0].strip()}), dim3({parts[1].strip()}), [&]() {{ '
+                   f'{m.group(1)}({args}); }})')
+        pos = q + 1
+    out.append(src[pos:])
+    return ''.join(out)
+
+
+def translate(cu_name):
+    src = open(os.path.join(CSRC, cu_name)).read()
+    src = src.replace('#include "common.cuh"', '')
+    src = src.replace('#include "scan.cuh"', '')
+    src = _rewrite_launches(src)
+    src = re.sub(r'extern "C" MSMD_API (\w[\w ]*?[ *])msmd_(\w+)\(', r'extern "C" \1emu_msmd_\2(', src)
+    # calls between entry points of the same unit keep working; calls into OTHER units are stubbed
+    return src
+
+
+PRELUDE = '''#include "cuda_emul.h"
+namespace emu {
+thread_local dim3 t_threadIdx, t_blockIdx;
+dim3 g_blockDim, g_gridDim;
+std::barrier<>* g_block_barrier = nullptr;
+std::vector<WarpBox> g_warps;
+char g_error[512];
+std::atomic<int> g_or{0};
+}
+extern "C" const char* emu_last_error() { return ::emu::g_error; }
+'''
+
+# entry points of other translation units that spconv_bwd.cu calls (the forward kernels: tensor-core
+# code cannot be emulated; dgrad-through-forward is covered by the oracle-level identity test instead)
+STUBS_BWD = '''
+extern "C" int msmd_spconv_fwd_tc_ws(const float*, int, const float*, const int*, int, int, int, int, const float*,
+                                     const float*, const float*, int, float*, void*, size_t, msmd_stream_t) { return -100; }
+extern "C" int msmd_spconv_fwd(const float*, int, const float*, const int*, int, int, int, int, const float*,
+                               const float*, const float*, int, float*, msmd_stream_t);
+'''
+
+
+def build(verbose=False):
+    os.makedirs(OUT, exist_ok=True)
+    lib = os.path.join(OUT, 'libmsmd_emul.so')
+    deps = [os.path.join(CSRC, f) for f in ('common.cuh', 'spconv_bwd.cu', 'spconv.cu')] + \
+        [os.path.join(HERE, 'cuda_emul.h'), os.path.abspath(__file__)]
+    if os.path.exists(lib) and all(os.path.getmtime(lib) > os.path.getmtime(d) for d in deps):
+        return lib
+    fwd = translate('spconv.cu').replace('emu_msmd_spconv_fwd(', 'msmd_spconv_fwd(')  # linked by bwd_data
+    text = PRELUDE + _device_helpers() + STUBS_BWD + fwd + translate('spconv_bwd.cu')
+    cpp = os.path.join(OUT, 'emul_unit.cpp')
+    with open(cpp, 'w') as f:
+        f.write(text)
+    cmd = ['g++', '-std=c++20', '-O1', '-g', '-shared', '-fPIC', '-pthread', '-I', HERE, cpp, '-o', lib]
+    if verbose:
+        print(' '.join(cmd))
+    subprocess.check_call(cmd)
+    return lib
+
+
+if __name__ == '__main__':
+    print(build(verbose=True))

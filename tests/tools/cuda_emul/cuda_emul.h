@@ -1,0 +1,171 @@
+// cuda_emul.h -- TEST INFRASTRUCTURE: a minimal CPU emulation of the CUDA execution model, enough to
+// run this repository's SIMT kernels (no tensor-core / TMA / cluster code) functionally on the host
+// when no GPU is available.  One std::thread per CUDA thread, thread blocks run one after another,
+// __syncthreads() is a std::barrier, warp shuffles go through a per-warp exchange buffer.  It checks
+// indexing, barrier placement and arithmetic order -- not performance, not memory-model races.
+// Used only by tests/test_cuda_emul.py (via tests/tools/cuda_emul/build.py); never by the product.
+#pragma once
+#include <algorithm>
+#include <atomic>
+#include <barrier>
+#include <cmath>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <thread>
+#include <vector>
+
+#define __global__
+#define __device__
+#define __host__
+#define __forceinline__ inline
+#define __restrict__
+#define __launch_bounds__(...)
+#define __shared__ static
+#define __align__(x) __attribute__((aligned(x)))
+#define MSMD_API
+
+struct dim3 {
+  unsigned x, y, z;
+  dim3(unsigned x_ = 1, unsigned y_ = 1, unsigned z_ = 1) : x(x_), y(y_), z(z_) {}
+};
+struct alignas(16) float4 { float x, y, z, w; };
+struct alignas(8) float2 { float x, y; };
+struct alignas(16) int4 { int x, y, z, w; };
+static inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
+
+typedef void* cudaStream_t;
+typedef void* msmd_stream_t;
+typedef int cudaError_t;
+static const cudaError_t cudaSuccess = 0;
+static inline cudaError_t cudaGetLastError() { return 0; }
+static inline const char* cudaGetErrorString(cudaError_t) { return "emulated"; }
+static inline cudaError_t cudaMemsetAsync(void* p, int v, size_t n, cudaStream_t) {
+  memset(p, v, n);
+  return 0;
+}
+
+enum { MSMD_OK = 0, MSMD_ERR_INVALID = -1, MSMD_ERR_CUDA = -2, MSMD_ERR_WORKSPACE = -3 };
+
+namespace emu {
+extern thread_local dim3 t_threadIdx, t_blockIdx;
+extern dim3 g_blockDim, g_gridDim;
+extern std::barrier<>* g_block_barrier;
+struct WarpBox {
+  std::unique_ptr<std::barrier<>> bar;
+  long long slot[32];
+};
+extern std::vector<WarpBox> g_warps;
+extern char g_error[512];
+extern std::atomic<int> g_or;
+
+template <typename F>
+void launch(dim3 grid, dim3 block, F body) {
+  const unsigned nthreads = block.x * block.y * block.z;
+  g_blockDim = block;
+  g_gridDim = grid;
+  for (unsigned bz = 0; bz < grid.z; ++bz)
+    for (unsigned by = 0; by < grid.y; ++by)
+      for (unsigned bx = 0; bx < grid.x; ++bx) {
+        std::barrier<> bar(nthreads);
+        g_block_barrier = &bar;
+        g_warps.clear();
+        g_warps.resize((nthreads + 31) / 32);
+        for (unsigned w = 0; w < g_warps.size(); ++w) {
+          const unsigned lanes = std::min(32u, nthreads - w * 32);
+          g_warps[w].bar.reset(new std::barrier<>(lanes));
+        }
+        std::vector<std::thread> ts;
+        ts.reserve(nthreads);
+        for (unsigned t = 0; t < nthreads; ++t)
+          ts.emplace_back([=]() {
+            t_threadIdx = dim3(t % block.x, (t / block.x) % block.y, t / (block.x * block.y));
+            t_blockIdx = dim3(bx, by, bz);
+            body();
+            g_block_barrier->arrive_and_drop();            // exited threads leave the barriers
+            g_warps[t / 32].bar->arrive_and_drop();
+          });
+        for (auto& th : ts) th.join();
+      }
+}
+}  // namespace emu
+
+#define threadIdx (::emu::t_threadIdx)
+#define blockIdx (::emu::t_blockIdx)
+#define blockDim (::emu::g_blockDim)
+#define gridDim (::emu::g_gridDim)
+
+static inline void __syncthreads() { ::emu::g_block_barrier->arrive_and_wait(); }
+
+static inline int __syncthreads_or(int pred) {
+  if (pred) ::emu::g_or.store(1);
+  ::emu::g_block_barrier->arrive_and_wait();
+  const int r = ::emu::g_or.load();
+  ::emu::g_block_barrier->arrive_and_wait();
+  if (threadIdx.x == 0 && threadIdx.y == 0 && threadIdx.z == 0) ::emu::g_or.store(0);
+  ::emu::g_block_barrier->arrive_and_wait();
+  return r;
+}
+using std::max;
+using std::min;
+
+template <typename T>
+static inline T emu_warp_exchange(T v, int src_lane_of_me, bool take) {
+  static_assert(sizeof(T) <= sizeof(long long), "shuffle payload");
+  const unsigned lin = threadIdx.x + threadIdx.y * blockDim.x + threadIdx.z * blockDim.x * blockDim.y;
+  auto& box = ::emu::g_warps[lin / 32];
+  const int lane = lin & 31;
+  long long raw = 0;
+  memcpy(&raw, &v, sizeof(T));
+  box.slot[lane] = raw;
+  box.bar->arrive_and_wait();
+  T out = v;
+  if (take) memcpy(&out, &box.slot[src_lane_of_me], sizeof(T));
+  box.bar->arrive_and_wait();
+  return out;
+}
+template <typename T>
+static inline T __shfl_up_sync(unsigned, T v, int d) {
+  const int lane = (threadIdx.x + threadIdx.y * blockDim.x) & 31;
+  return emu_warp_exchange(v, lane - d, lane - d >= 0);
+}
+template <typename T>
+static inline T __shfl_xor_sync(unsigned, T v, int d) {
+  const int lane = (threadIdx.x + threadIdx.y * blockDim.x) & 31;
+  return emu_warp_exchange(v, lane ^ d, true);
+}
+template <typename T>
+static inline T __ldg(const T* p) { return *p; }
+static inline int __popc(unsigned v) { return __builtin_popcount(v); }
+static inline int __ffs(unsigned v) { return __builtin_ffs((int)v); }
+
+// what csrc/common.cuh provides on the host side
+namespace msmd {
+static inline void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(::emu::g_error, sizeof(::emu::g_error), fmt, ap);
+  va_end(ap);
+}
+static inline void count_launch(int) {}
+static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+constexpr int kNumSMs = 148;
+}  // namespace msmd
+
+#define MSMD_CUDA_OK(expr)                         \
+  do {                                             \
+    if ((expr) != cudaSuccess) return MSMD_ERR_CUDA; \
+  } while (0)
+#define MSMD_REQUIRE(cond, ...)          \
+  do {                                   \
+    if (!(cond)) {                       \
+      ::msmd::set_error(__VA_ARGS__);    \
+      return MSMD_ERR_INVALID;           \
+    }                                    \
+  } while (0)
+#define MSMD_LAUNCH_OK() \
+  do {                   \
+  } while (0)
