@@ -37,9 +37,11 @@ def parse():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--profile', default='S', choices=['S', 'L'],
                     help='S: single 32-beam sweep (~30 k points); L: 10 sweeps (~285 k points)')
-    ap.add_argument('--workload', default='L', choices=['L', 'LC'],
+    ap.add_argument('--workload', default='L', choices=['L', 'LC', 'train'],
                     help='L: transfusion_nusc_voxel_L LiDAR hot path (BASELINE configs[1], the default); '
-                         'LC: MSMDFusion_nusc_voxel_LC voxel-space fusion path (configs[2])')
+                         'LC: MSMDFusion_nusc_voxel_LC voxel-space fusion path (configs[2]); '
+                         'train: LC train step (configs[4]): forward in train mode, backward through the GMA '
+                         'encoder, one NCCL gradient all-reduce, clip, AdamW')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--breakdown', default=None, help='write a per-op CUDA-event breakdown (json) here')
     return ap.parse_args()
@@ -55,6 +57,11 @@ def peaks():
 
 def workload_name(profile, workload='L'):
     scene = '30k-pt single-sweep' if profile == 'S' else '285k-pt 10-sweep'
+    if workload == 'train':
+        return ('MSMDFusion_nusc_voxel_LC TRAIN step on the voxel-space path (frozen LiDAR encoder, lift x4 scales, '
+                'GMA encoder forward + backward, quadratic loss on the BEV tensor in place of TransFusionHead.loss, '
+                'flat-buffer gradient all-reduce, clip 10, AdamW), synthetic %s scene + 60k virtual points, one '
+                'scene per GPU' % scene)
     if workload == 'LC':
         return ('MSMDFusion_nusc_voxel_LC voxel-space fusion path (LiDAR encoder + 6-camera virtual-point '
                 'lift x4 scales + modality split + GMA encoder + dense), synthetic %s scene + 60k virtual '
@@ -175,7 +182,24 @@ def run_ours(args, rank, world, device):
     import torch.distributed as dist
     from msmdfusion_b200 import _cabi, ops, synthetic
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)  # > 126 MB L2
-    if args.workload == 'LC':
+    trainer = None
+    if args.workload == 'train':
+        from msmdfusion_b200 import train as _train
+        cfg, det, pts_np, meta, fpn = build_lc_pipeline(device, rank, args.profile)
+        pts_host = torch.from_numpy(pts_np).pin_memory()
+        pts_dev = pts_host.to(device)
+        h2d_extra = [0]
+        metas_resident = [meta]
+        target = torch.randn((1, 640, 180, 180), generator=torch.Generator().manual_seed(1 + rank)).to(device)
+        trainer = _train.VoxelSpaceTrainStep(det, lambda bev: ((bev - target) ** 2).mean())
+
+        def step(points, fresh_upload=False):
+            metas = [dict(meta)] if fresh_upload else metas_resident
+            loss = trainer([points], fpn, metas)
+            if fresh_upload:
+                h2d_extra[0] = det.packed_foreground(metas, device).h2d_bytes
+            return loss, trainer.last_stage_outs
+    elif args.workload == 'LC':
         cfg, det, pts_np, meta, fpn = build_lc_pipeline(device, rank, args.profile)
         pts_host = torch.from_numpy(pts_np).pin_memory()
         pts_dev = pts_host.to(device)
@@ -307,7 +331,9 @@ def run_ours(args, rank, world, device):
             r['ms'] = r['start'].elapsed_time(r['end'])
             if 'pair' in r:
                 r['pairs'] = int((r.pop('pair') >= 0).sum().item())
-        conv = [r for r in recs if r['op'] == 'spconv_fwd']
+        conv = [r for r in recs if r['op'] in ('spconv_fwd', 'spconv_bwd_data', 'spconv_bwd_weight')]
+        for r in conv:
+            r.setdefault('residual', False)
         if args.breakdown:
             by_op = {}
             for r in recs:
@@ -321,7 +347,7 @@ def run_ours(args, rank, world, device):
         conv_ms = sum(r['ms'] for r in conv)
         hbm, bf16, src = peaks()
         paths = sorted({r.get('path', 'simt') for r in conv})
-        tc = paths == ['tc']
+        tc = paths == ['tc'] or (args.workload == 'train' and 'tc' in paths)
         gbs = b / (conv_ms * 1e-3) / 1e9 if conv_ms else 0.0
         tfl = f / (conv_ms * 1e-3) / 1e12 if conv_ms else 0.0
         tf32_peak = bf16 / 2.0  # tcgen05 kind::tf32 issues at half the bf16 rate
@@ -338,7 +364,9 @@ def run_ours(args, rank, world, device):
                            'one scene, profiles/r01e_ncu_full_spconv_tc_profileS.json (writes stay in the '
                            '126 MB L2 at this size)')
         common = {'traffic': traffic, 'traffic_source': traffic_src, 'peak_source': src,
-                  'kernel': ('spconv_fwd_tc_kernel (tcgen05 kind::tf32, 3xTF32)' if tc else
+                  'kernel': ('sparse conv forward + data gradient (tcgen05 kind::tf32, 3xTF32) + weight gradient '
+                             '(spconv_wgrad_simt_kernel, FFMA)' if args.workload == 'train' else
+                             'spconv_fwd_tc_kernel (tcgen05 kind::tf32, 3xTF32)' if tc else
                              'spconv_fwd_simt_kernel') + ' (%d launches/scene, summed)' % (len(conv) // 3),
                   'kernel_ms_per_step': round(conv_ms / 3, 4),
                   'algorithmic_bytes_per_step': b / 3, 'algorithmic_flops_per_step': f / 3,
@@ -460,7 +488,8 @@ def main():
                    'voxels_per_scene': res['voxels'], 'scenes_per_gpu_per_step': 1, 'parallelism': 'dp%d' % world,
                    'l2': 'flushed between steps (256 MiB memset, outside the per-step events)',
                    'settle': '%d untimed steps (the first + %.0f ms of wall time) before the %d warm-up steps' % (res['settle_steps'], SETTLE_MS, max(args.warmup, 3)),
-                   'weights': 'random init (spconv default), BN eval'},
+                   'weights': ('random init (spconv default); LiDAR encoder frozen (BN eval), GMA encoder BN in '
+                               'training mode' if args.workload == 'train' else 'random init (spconv default), BN eval')},
         'e2e': {'value': world * K / (res['e2e_ms'] * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': res['h2d'],
                 'd2h_bytes_per_step': res['d2h'], 'step_ms': res['e2e_step_ms'],
                 'note': ('pinned host points (+ packed virtual points for LC) -> H2D -> public modules '

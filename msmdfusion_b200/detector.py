@@ -17,6 +17,8 @@ B200-first differences that cannot change results:
 * ``voxel_modality_split`` runs on the device (stable radix sort + binary-search merge) instead
   of GPU sort -> CPU numba merge -> GPU.
 """
+import contextlib
+
 import numpy as np
 import torch
 import torch.nn.functional as F
@@ -405,7 +407,11 @@ class MSMDFusionDetector(nn.Module, _VoxelPathMixin):
         batch_size = len(pts)
         nf = min(self.pts_voxel_encoder.num_features, pts[0].shape[1])  # [:64] of 5 dims after :386
         voxel_features, coors, _ = self.voxelize_mean(pts, nf)
-        x, encode_features = self.pts_middle_encoder(voxel_features, coors, batch_size)
+        # a frozen LiDAR encoder (tools/train.py:185-211) has no grad-requiring input either (voxelize is
+        # no_grad, :462-464), so autograd would skip it anyway: run it on the inference path
+        frozen = torch.is_grad_enabled() and not any(p.requires_grad for p in self.pts_middle_encoder.parameters())
+        with (torch.no_grad() if frozen else contextlib.nullcontext()):
+            x, encode_features = self.pts_middle_encoder(voxel_features, coors, batch_size)
         v3l, v2l, s3l, s2l = self.extract_multiscale_voxel_feat(
             img_feats, encode_features, img_metas, self.spatial_shapes, self.downscale_factors, batch_size)
         stage_outs = self.multimodal_middle_encoder(

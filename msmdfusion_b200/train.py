@@ -1,0 +1,106 @@
+"""Train step of the voxel-space path (BASELINE.json configs[4]: MSMDFusion_nusc_voxel_LC train step,
+one scene per GPU, NCCL gradient all-reduce).
+
+Mirrors the reference's step as far as the hot path goes: ``tools/train.py:185-211`` freezes
+the LiDAR components (parameters and BatchNorm statistics), ``MMDistributedDataParallel(
+find_unused_parameters=True)`` all-reduces the gradients of the parameters that took part in the step
+(``configs/MSMDFusion_nusc_voxel_LC.py:309``), the optimiser is AdamW with gradient clipping at 10
+(``:282-286``).  ``TransFusionHead.loss`` is outside the hot path; the step takes the
+loss as a callable on the tensor the head consumes.
+
+B200-first: the gradients of all participating parameters are VIEWS of one flat fp32 buffer, so the
+exchange step is ONE NCCL all-reduce over NVLink (no bucketing, no copies: ~10 M parameters = 38 MB, far
+below the size where splitting would buy overlap), the clip is one norm over that buffer and the update
+is the fused multi-tensor AdamW.  Parameters that receive no gradient in the first step (the blocks the
+reference builds but never calls, ``score_net``, ``conv1x1_blocks``: the virtual-point features are
+constants, ``MSMDFusion.py:462-464``) are left out of the buffer and of the optimiser, which is what
+``find_unused_parameters`` amounts to.
+"""
+import torch
+import torch.distributed as dist
+
+
+def freeze_lidar_components(detector):
+    """tools/train.py:185-211: LiDAR voxel encoder / middle encoder frozen, their BN in eval mode."""
+    for name in ('pts_voxel_encoder', 'pts_middle_encoder'):
+        mod = getattr(detector, name, None)
+        if mod is None:
+            continue
+        for p in mod.parameters():
+            p.requires_grad_(False)
+        mod.eval()
+    return detector
+
+
+class FlatGradients:
+    """One flat fp32 buffer holding the gradients of ``params`` (each ``p.grad`` is a view of it)."""
+
+    def __init__(self, params):
+        self.params = [p for p in params]
+        assert self.params, 'no parameters take part in the step'
+        dev = self.params[0].device
+        total = sum(p.numel() for p in self.params)
+        self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
+        off = 0
+        for p in self.params:
+            assert p.dtype == torch.float32 and p.device == dev
+            n = p.numel()
+            p.grad = self.flat[off:off + n].view_as(p)   # autograd accumulates in place into the view
+            off += n
+
+    def zero(self):
+        self.flat.zero_()
+
+    def all_reduce_mean(self):
+        """The exchange step: average over ranks with ONE collective (no-op for a single rank)."""
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
+            self.flat.div_(dist.get_world_size())
+
+    def clip_(self, max_norm):
+        """``clip_grad_norm_`` (mmcv ``grad_clip=dict(max_norm=10, norm_type=2)``) on the flat buffer,
+        without a host synchronisation."""
+        norm = torch.linalg.vector_norm(self.flat)
+        self.flat.mul_(torch.clamp(max_norm / (norm + 1e-6), max=1.0))
+        return norm
+
+
+class VoxelSpaceTrainStep:
+    """forward (train mode) -> loss -> backward -> gradient all-reduce -> clip -> AdamW."""
+
+    def __init__(self, detector, loss_fn, lr=1e-4, weight_decay=0.01, grad_clip=10.0):
+        detector.train()                       # batch-statistics BatchNorm, max_voxels[0] (voxelize.py:103-114)
+        self.det = freeze_lidar_components(detector)
+        self.loss_fn = loss_fn
+        self.last_stage_outs = None
+        self.lr, self.weight_decay, self.grad_clip = lr, weight_decay, grad_clip
+        self.grads = None
+        self.opt = None
+
+    def _probe(self, loss):
+        """First step: see which parameters the step reaches, then lay out the flat buffer."""
+        loss.backward()
+        used = [p for p in self.det.parameters() if p.requires_grad and p.grad is not None]
+        first = [p.grad.detach().clone() for p in used]
+        self.grads = FlatGradients(used)
+        for p, g in zip(used, first):
+            p.grad.copy_(g)
+        self.opt = torch.optim.AdamW(used, lr=self.lr, weight_decay=self.weight_decay,
+                                     fused=used[0].is_cuda)
+
+    def forward_loss(self, points, img_feats, img_metas):
+        bev, self.last_stage_outs = self.det.extract_voxel_space(points, img_feats, img_metas)
+        return self.loss_fn(bev)
+
+    def __call__(self, points, img_feats, img_metas):
+        if self.grads is not None:
+            self.grads.zero()
+        loss = self.forward_loss(points, img_feats, img_metas)
+        if self.grads is None:
+            self._probe(loss)
+        else:
+            loss.backward()
+        self.grads.all_reduce_mean()
+        self.grads.clip_(self.grad_clip)
+        self.opt.step()
+        return loss.detach()

@@ -317,3 +317,95 @@ def test_subm_gradient_with_duplicate_coordinates(cpu_ops):
     (y * g.double()).sum().backward()
     assert rel(f.grad, fr.grad) < 1e-5 and rel(conv.weight.grad, wr.grad) < 1e-5
     assert (fr.grad[pair[13] != torch.arange(idx.shape[0])] == 0).all()
+
+
+def test_gma_encoder_single_sample_path_gradients(cpu_ops, monkeypatch):
+    """The sync-free one-sample-per-GPU path (``_grouped_sparse_conv_b1``: device-scan row lists, the
+    zero-padded concatenation written by slice assignment) gives the same output and the same parameter
+    gradients as the generic path in training mode."""
+    from msmdfusion_b200 import fusion_encoder as fe
+    from msmdfusion_b200 import ops
+    from oracle import cpu
+
+    def fps_nn_fast(query, key, fps_num, radius, nsample, thresh, base=0):
+        out = cpu.fps_nn_fast(query.numpy(), key.numpy(), fps_num, radius, nsample, thresh)
+        return torch.from_numpy(np.where(out >= 0, out + base, out))
+    monkeypatch.setattr(fe, 'fps_nn_fast', fps_nn_fast)
+    monkeypatch.setattr(ops, 'compact_unflagged',
+                        lambda flags, count: torch.nonzero(flags == 0).flatten()[:int(count)])
+    torch.manual_seed(12)
+    enc = fe.SparseMultiModalEncoderPaint(in_channels_3D=(4, 8, 8, 8), in_channels_2D=(64,) * 4,
+                                          out_channels=(8, 8, 8, 8), padding=(1, 1, [0, 1, 1], 0)).train()
+    inputs = _encoder_inputs(31, 1)
+    results = []
+    for single in (False, True):
+        v3l, v2l, s3l, s2l = inputs
+        v3 = [spconv.SparseConvTensor(f.clone(), i.clone(), s, 1) for i, f, s in v3l]
+        v2 = [spconv.SparseConvTensor(f.clone(), i.clone(), s, 1) for i, f, s in v2l]
+        if single:  # what MSMDFusionDetector.voxel_modality_split leaves on the tensors
+            for t in v3 + v2:
+                t._mix = t.indices[:, 1].contiguous().int()
+                t._bzyx = t.indices[:, [0, 2, 3, 4]].contiguous()
+        torch.manual_seed(5)
+        outs = enc(v3, v2, s3l, s2l, [6, 6, 6, 6], [6, 3, 2, 1], [20, 10, 5, 3], [13.3, 6.6, 3.3, 1.6])
+        d = outs[-1].dense()
+        g = torch.randn(d.shape, generator=torch.Generator().manual_seed(9))
+        enc.zero_grad(set_to_none=True)
+        (d * g).sum().backward()
+        results.append((d.detach(), {k: v.grad.clone() for k, v in enc.named_parameters() if v.grad is not None}))
+    (d0, g0), (d1, g1) = results
+    assert rel(d1, d0) < 1e-5 and g0.keys() == g1.keys()
+    for k in g0:
+        assert rel(g1[k], g0[k]) < 1e-4, k
+
+
+def test_voxel_space_train_step_on_a_stand_in_detector():
+    """VoxelSpaceTrainStep: LiDAR components frozen (eval-mode BN), parameters the step never reaches
+    stay out of the flat gradient buffer and of the optimiser (find_unused_parameters semantics),
+    gradients are views of one buffer, and three steps equal clip_grad_norm_ + torch AdamW by hand."""
+    from msmdfusion_b200 import train
+
+    class Det(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.pts_voxel_encoder = torch.nn.Identity()
+            self.pts_middle_encoder = torch.nn.Sequential(torch.nn.Linear(6, 8), torch.nn.BatchNorm1d(8))
+            self.multimodal_middle_encoder = torch.nn.Sequential(torch.nn.Linear(8, 8), torch.nn.BatchNorm1d(8),
+                                                                 torch.nn.ReLU(), torch.nn.Linear(8, 4))
+            self.score_net = torch.nn.Linear(3, 1)          # reached only through a detached input
+
+        def extract_voxel_space(self, points, img_feats, img_metas):
+            with torch.no_grad():
+                x = self.pts_middle_encoder(points[0])
+                gate = self.score_net(img_feats)
+            return self.multimodal_middle_encoder(x * gate), ['stage_outs']
+
+    def make():
+        torch.manual_seed(0)
+        return Det()
+    det, ref = make(), make()
+    pts = torch.randn(32, 6, generator=torch.Generator().manual_seed(1))
+    img = torch.randn(32, 3, generator=torch.Generator().manual_seed(2))
+    step = train.VoxelSpaceTrainStep(det, lambda bev: bev.pow(2).mean() * 50, lr=1e-2, weight_decay=0.01, grad_clip=1.0)
+    assert not det.pts_middle_encoder.training and det.multimodal_middle_encoder.training
+    assert not any(p.requires_grad for p in det.pts_middle_encoder.parameters())
+
+    ref.train()
+    train.freeze_lidar_components(ref)
+    used = list(ref.multimodal_middle_encoder.parameters())
+    opt = torch.optim.AdamW(used, lr=1e-2, weight_decay=0.01)
+    for it in range(3):
+        loss = step([pts], img, None)
+        opt.zero_grad(set_to_none=True)
+        rl = ref.extract_voxel_space([pts], img, None)[0].pow(2).mean() * 50
+        rl.backward()
+        torch.nn.utils.clip_grad_norm_(used, 1.0)
+        opt.step()
+        assert abs(float(loss) - float(rl.detach())) < 1e-5 * max(1.0, abs(float(rl.detach()))), it
+    assert step.last_stage_outs == ['stage_outs']
+    assert len(step.grads.params) == len(used) and det.score_net.weight.grad is None
+    lo, hi = step.grads.flat.data_ptr(), step.grads.flat.data_ptr() + step.grads.flat.numel() * 4
+    assert all(lo <= p.grad.data_ptr() < hi for p in step.grads.params)
+    for a, b in zip(det.multimodal_middle_encoder.parameters(), used):
+        assert torch.allclose(a, b, atol=1e-6)
+    assert torch.equal(det.pts_middle_encoder[0].weight, ref.pts_middle_encoder[0].weight)
