@@ -160,6 +160,33 @@ MSMD_API int msmd_spconv_fwd_tc_ws(const float* features, int n_in, const float*
                                    msmd_stream_t stream);
 
 /* ------------------------------------------------------------------------------------
+ * Mask-sorted tiles -- the role of mask_argsort_fwd_splits among the outputs of
+ * ops.get_indice_pairs_implicit_gemm (bug_fix/conv.py:382-415): output rows are grouped by the
+ * structure of their neighbour mask before the implicit GEMM tiles them, so that a 128-row tile
+ * touches few kernel offsets and the convolution can skip the rest.
+ *   msmd_rulebook_mask_sort   (kvol = 27 only) row_perm (n): tile slot -> output row, stable order by
+ *                             a 15-bit digest of the 27-bit mask; pair_sorted (kvol, n) =
+ *                             pair_fwd[:, row_perm].  Once per rulebook (a SubM rulebook serves 4-5
+ *                             layers).  workspace: msmd_rulebook_mask_sort_workspace(n) bytes.
+ *   msmd_spconv_fwd_tc_sorted msmd_spconv_fwd_tc_ws on the permuted table: slot s of a tile computes
+ *                             output row row_perm[s] (residual read / result written there), so `out`
+ *                             is in the ORIGINAL row order.  Per-row accumulation order is unchanged.
+ * Opt-in (msmd_spconv_set_mask_sort / MSMD_MASK_SORT=1): not yet measured on hardware.
+ * ---------------------------------------------------------------------------------- */
+MSMD_API size_t msmd_rulebook_mask_sort_workspace(int n);
+MSMD_API int msmd_rulebook_mask_sort(const int* pair_fwd, int kvol, int n, int* row_perm,
+                                     int* pair_sorted, void* workspace, size_t workspace_bytes,
+                                     msmd_stream_t stream);
+MSMD_API int msmd_spconv_fwd_tc_sorted(const float* features, int n_in, const float* packed_tc,
+                                       const int* pair_sorted, const int* row_perm, int n_out, int cin,
+                                       int cout, int kvol, const float* scale, const float* shift,
+                                       const float* residual, int relu, float* out, void* workspace,
+                                       size_t workspace_bytes, msmd_stream_t stream);
+/* 1: the native executor (msmd_sparse_net_forward) mask-sorts every 3x3x3 SubM rulebook it builds and
+ * runs the tensor-core layers that use it through msmd_spconv_fwd_tc_sorted.  Default 0. */
+MSMD_API int msmd_spconv_set_mask_sort(int enable);
+
+/* ------------------------------------------------------------------------------------
  * Sparse convolution BACKWARD (config 5, the train step) -- replaces the backward of
  * Fsp.implicit_gemm (call site bug_fix/conv.py:442-447; spconv-2.x differentiates through
  * pair_bwd / mask_argsort_bwd_splits, bug_fix/conv.py:382-415).  Arithmetic as the vendored

@@ -59,6 +59,11 @@ SIGNATURES = {
     'msmd_spconv_fwd_tc': (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _vp]),
     'msmd_spconv_tc_workspace': (_sz, [_i, _i]),
     'msmd_spconv_fwd_tc_ws': (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _sz, _vp]),
+    'msmd_rulebook_mask_sort_workspace': (_sz, [_i]),
+    'msmd_rulebook_mask_sort': (_i, [_vp, _i, _i, _vp, _vp, _vp, _sz, _vp]),
+    'msmd_spconv_fwd_tc_sorted': (_i, [_vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _vp,
+                                       _sz, _vp]),
+    'msmd_spconv_set_mask_sort': (_i, [_i]),
     'msmd_rulebook_transpose': (_i, [_vp, _i, _i, _i, _vp, _vp]),
     'msmd_spconv_transpose_weight': (_i, [_vp, _i, _i, _i, _i, _vp, _vp]),
     'msmd_spconv_bwd_data': (_i, [_vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _sz, _vp]),
@@ -103,6 +108,8 @@ def lib():
             fn.argtypes = args
         if L.msmd_abi_version() != 1:
             raise RuntimeError('libmsmd_b200.so ABI version mismatch')
+        if os.environ.get('MSMD_MASK_SORT', '0') not in ('', '0'):  # opt-in: mask-sorted tiles (executor path)
+            L.msmd_spconv_set_mask_sort(1)
         if os.environ.get('MSMD_TC_VARIANT'):  # A/B switch of the tensor-core conv kernel (2 | 3)
             if L.msmd_spconv_tc_set_variant(int(os.environ['MSMD_TC_VARIANT'])) != 0:
                 raise RuntimeError('bad MSMD_TC_VARIANT')

@@ -24,8 +24,12 @@ namespace msmd {
 
 struct RulebookX {
   int* pair = nullptr;
+  int* pair_sorted = nullptr;   // mask-sorted copy of the table + its slot -> row map (opt-in)
+  int* row_perm = nullptr;
   cudaEvent_t ready = nullptr;  // recorded on the geometry stream after the rulebook kernels
 };
+
+static int g_mask_sort = 0;  // msmd_spconv_set_mask_sort
 
 struct IndexSetX {
   int* indices = nullptr;
@@ -117,6 +121,11 @@ static int ensure_grid(IndexSetX& s, int batch, Arena& arena, void* scan_ws, siz
   return MSMD_OK;
 }
 
+extern "C" MSMD_API int msmd_spconv_set_mask_sort(int enable) {
+  g_mask_sort = enable ? 1 : 0;
+  return MSMD_OK;
+}
+
 extern "C" MSMD_API int msmd_sparse_net_forward(const msmd_conv_layer* layers, int n_layers,
                                                 const float* features, const int* indices, int n,
                                                 int channels, int batch_size, const int* spatial_shape,
@@ -179,6 +188,17 @@ extern "C" MSMD_API int msmd_sparse_net_forward(const msmd_conv_layer* layers, i
           MSMD_TRY(msmd_rulebook_subm(s.indices, s.n, batch_size, s.shape, L.ksize, L.dilation, s.bits,
                                       s.prefix, s.perm, p, (msmd_stream_t)geom));
           rb.pair = p;
+          if (g_mask_sort && kvol == 27 && s.n > 0) {
+            // group the rows by neighbour-mask structure once; every SubM layer on this index set
+            // (4-5 of them) then tiles the permuted table
+            const size_t sort_bytes = msmd_rulebook_mask_sort_workspace(s.n);
+            MSMD_ARENA(rp, int, (size_t)s.n);
+            MSMD_ARENA(ps, int, (size_t)kvol * (size_t)s.n);
+            MSMD_ARENA(sort_ws, char, sort_bytes);
+            MSMD_TRY(msmd_rulebook_mask_sort(p, kvol, s.n, rp, ps, sort_ws, sort_bytes, (msmd_stream_t)geom));
+            rb.row_perm = rp;
+            rb.pair_sorted = ps;
+          }
           MSMD_TRY(next_event(*aux, &rb.ready));
           MSMD_CUDA_OK(cudaEventRecord(rb.ready, geom));
           s.subm[key] = rb;
@@ -233,9 +253,14 @@ extern "C" MSMD_API int msmd_sparse_net_forward(const msmd_conv_layer* layers, i
           MSMD_ARENA(w, char, ws_bytes);
           ws = w;
         }
-        MSMD_TRY(msmd_spconv_fwd_tc_ws(in.features, in.n, L.weight, rb.pair, n_out, L.cin, L.cout, kvol,
-                                       L.scale, L.shift, residual, L.relu, out, ws, ws_bytes,
-                                       (msmd_stream_t)stream));
+        if (rb.pair_sorted)
+          MSMD_TRY(msmd_spconv_fwd_tc_sorted(in.features, in.n, L.weight, rb.pair_sorted, rb.row_perm, n_out,
+                                             L.cin, L.cout, kvol, L.scale, L.shift, residual, L.relu, out, ws,
+                                             ws_bytes, (msmd_stream_t)stream));
+        else
+          MSMD_TRY(msmd_spconv_fwd_tc_ws(in.features, in.n, L.weight, rb.pair, n_out, L.cin, L.cout, kvol,
+                                         L.scale, L.shift, residual, L.relu, out, ws, ws_bytes,
+                                         (msmd_stream_t)stream));
       }
       else
         MSMD_TRY(msmd_spconv_fwd(in.features, in.n, L.weight, rb.pair, n_out, L.cin, L.cout, kvol, L.scale,

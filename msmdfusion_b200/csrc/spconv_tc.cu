@@ -103,13 +103,17 @@ __device__ __forceinline__ void tc_epilogue(int any_active, uint64_t* accum_bar,
                                             const float* ss /* smem: scale[N] | shift[N] */,
                                             const float* __restrict__ residual, int relu,
                                             float* __restrict__ out, float* write_partial = nullptr,
-                                            const float* add_partial = nullptr, int cat_cols = 0) {
+                                            const float* add_partial = nullptr, int cat_cols = 0,
+                                            const int* __restrict__ row_perm = nullptr) {
     if (any_active) {
       tc::mbar_wait(accum_bar, 0);
       tc::fence_after_sync();
     }
     const int quarter = warp & 3;             // TMEM lanes this warp may read: 32*quarter ..
-    const int o = row0 + quarter * 32 + lane;
+    int o = row0 + quarter * 32 + lane;
+    // mask-sorted tiles: the pair table was permuted so that rows with similar neighbour masks share a
+    // tile; tile slot o holds output row row_perm[o] (the residual is read, the result written there)
+    if (row_perm) o = (o < n_out) ? __ldg(row_perm + o) : n_out;
     const int nsteps = N / 16;
     const int step_lo = (warp >> 2) ? (nsteps + 1) / 2 : 0;  // two warpgroups split the columns
     const int step_hi = (warp >> 2) ? nsteps : (nsteps + 1) / 2;
@@ -198,7 +202,7 @@ spconv_fwd_tc_kernel(const float* __restrict__ feat, const float* __restrict__ w
                      int kvol, int chunks, int stages, int stage_bytes, int pair_off, int act_off,
                      int bar_off, int tmem_cols, const float* __restrict__ scale,
                      const float* __restrict__ shift, const float* __restrict__ residual, int relu,
-                     float* __restrict__ out, int cat) {
+                     float* __restrict__ out, int cat, const int* __restrict__ row_perm) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   int* pair_s = (int*)(smem + pair_off);
@@ -324,7 +328,7 @@ spconv_fwd_tc_kernel(const float* __restrict__ feat, const float* __restrict__ w
 
     // ===== epilogue: TMEM -> registers -> fused BN / residual / ReLU -> global =============
     tc_epilogue(any_active, accum_bar, tmem_base, warp, lane, row0, n_out, cout, N, ss, residual, relu, out,
-                nullptr, nullptr, cat ? N : 0);
+                nullptr, nullptr, cat ? N : 0, row_perm);
   } else if (warp == kTcProducerWarps) {
     // ===== B loader: one bulk copy (hi + lo image of the chunk) per active chunk ============
     if (lane == 0) {
@@ -432,7 +436,8 @@ spconv_fwd_tc3_kernel(const float* __restrict__ feat, const float* __restrict__ 
                       int pair_off, int act_off, int bar_off, int tmem_cols,
                       const float* __restrict__ scale, const float* __restrict__ shift,
                       const float* __restrict__ residual, int relu, float* __restrict__ out, int split,
-                      float* __restrict__ part_ws, int* __restrict__ part_flag) {
+                      float* __restrict__ part_ws, int* __restrict__ part_flag,
+                      const int* __restrict__ row_perm) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   int* pair_s = (int*)(smem + pair_off);
@@ -581,7 +586,8 @@ spconv_fwd_tc3_kernel(const float* __restrict__ feat, const float* __restrict__ 
     }
 
     if (split == 1) {
-      tc_epilogue(any_active, accum_bar, tmem_base, warp, lane, row0, n_out, cout, N, ss, residual, relu, out);
+      tc_epilogue(any_active, accum_bar, tmem_base, warp, lane, row0, n_out, cout, N, ss, residual, relu, out,
+                  nullptr, nullptr, 0, row_perm);
     } else {
       int* ticket_s = n_act_s;  // the active-chunk count is no longer needed: reuse its smem word
       float* part = part_ws + (size_t)tile * kTcM * N;
@@ -604,7 +610,7 @@ spconv_fwd_tc3_kernel(const float* __restrict__ feat, const float* __restrict__ 
         tc::named_bar_sync(2, kTcProducers);
         __threadfence();
         tc_epilogue(any_active, accum_bar, tmem_base, warp, lane, row0, n_out, cout, N, ss, residual, relu,
-                    out, nullptr, part);
+                    out, nullptr, part, 0, row_perm);
         tc::named_bar_sync(2, kTcProducers);
         if (tid == 0) { part_flag[2 * tile] = 0; part_flag[2 * tile + 1] = 0; }  // ready for the next launch
       }
@@ -754,12 +760,36 @@ extern "C" MSMD_API int msmd_spconv_fwd_tc(const float* features, int n_in, cons
                                residual, relu, out, nullptr, 0, stream_);
 }
 
+static int tc_forward_impl(const float* features, int n_in, const float* packed_tc, const int* pair_fwd,
+                           const int* row_perm, int n_out, int cin, int cout, int kvol, const float* scale,
+                           const float* shift, const float* residual, int relu, float* out, void* workspace,
+                           size_t workspace_bytes, msmd_stream_t stream_);
+
 extern "C" MSMD_API int msmd_spconv_fwd_tc_ws(const float* features, int n_in, const float* packed_tc,
                                            const int* pair_fwd, int n_out, int cin, int cout, int kvol,
                                            const float* scale, const float* shift,
                                            const float* residual, int relu, float* out,
                                            void* workspace, size_t workspace_bytes,
                                            msmd_stream_t stream_) {
+  return tc_forward_impl(features, n_in, packed_tc, pair_fwd, nullptr, n_out, cin, cout, kvol, scale, shift,
+                         residual, relu, out, workspace, workspace_bytes, stream_);
+}
+
+extern "C" MSMD_API int msmd_spconv_fwd_tc_sorted(const float* features, int n_in, const float* packed_tc,
+                                                  const int* pair_sorted, const int* row_perm, int n_out,
+                                                  int cin, int cout, int kvol, const float* scale,
+                                                  const float* shift, const float* residual, int relu,
+                                                  float* out, void* workspace, size_t workspace_bytes,
+                                                  msmd_stream_t stream_) {
+  MSMD_REQUIRE(row_perm || n_out == 0, "spconv_fwd_tc_sorted: null row_perm");
+  return tc_forward_impl(features, n_in, packed_tc, pair_sorted, row_perm, n_out, cin, cout, kvol, scale,
+                         shift, residual, relu, out, workspace, workspace_bytes, stream_);
+}
+
+static int tc_forward_impl(const float* features, int n_in, const float* packed_tc, const int* pair_fwd,
+                           const int* row_perm, int n_out, int cin, int cout, int kvol, const float* scale,
+                           const float* shift, const float* residual, int relu, float* out, void* workspace,
+                           size_t workspace_bytes, msmd_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   TcGeom g;
   MSMD_REQUIRE(tc_geom(cout, kvol, cin, g), "spconv_fwd_tc: unsupported shape (cout<=256, kvol<=32)");
@@ -794,7 +824,7 @@ extern "C" MSMD_API int msmd_spconv_fwd_tc_ws(const float* features, int n_in, c
     kern<<<tiles * split, kTcThreads, L.total, stream>>>(
         features, packed_tc, pair_fwd, n_out, cin, g.cin_pad, cout, g.N, kvol, g.chunks, L.b_stages,
         L.b_stage_bytes, L.a_stages, L.raw_off, L.pair_off, L.act_off, L.bar_off, L.tmem_cols, scale, shift,
-        residual, relu, out, split, part_ws, part_flag);
+        residual, relu, out, split, part_ws, part_flag, row_perm);
     MSMD_LAUNCH_OK();
     return MSMD_OK;
   }
@@ -815,7 +845,7 @@ extern "C" MSMD_API int msmd_spconv_fwd_tc_ws(const float* features, int n_in, c
   kern<<<tiles, kTcThreads, L.total, stream>>>(features, packed_tc, pair_fwd, n_out, cin, g.cin_pad, cout,
                                                g.N, kvol, g.chunks, L.stages, L.stage_bytes, L.pair_off,
                                                L.act_off, L.bar_off, tmem_cols, scale, shift, residual,
-                                               relu, out, cat);
+                                               relu, out, cat, row_perm);
   MSMD_LAUNCH_OK();
   return MSMD_OK;
 }

@@ -205,6 +205,11 @@ class TcWeight:
         self.packed, self.cout, self.kvol, self.cin = packed, cout, kvol, cin
 
 
+def set_mask_sort(enable):
+    """Opt-in: the native executor mask-sorts its 3x3x3 SubM rulebooks (``msmd_spconv_set_mask_sort``)."""
+    check(lib().msmd_spconv_set_mask_sort(int(bool(enable))), 'msmd_spconv_set_mask_sort')
+
+
 def set_tc_variant(variant):
     """0 (default): chosen by Cout; 3: A operand staged in tensor memory; 2: A operand in shared memory."""
     check(lib().msmd_spconv_tc_set_variant(int(variant)), 'msmd_spconv_tc_set_variant')
@@ -230,8 +235,27 @@ def pack_weight_tc(weight):
     return TcWeight(packed, cout, kvol, cin)
 
 
-def spconv_fwd_tc(features, tcw, pair_fwd, scale=None, shift=None, residual=None, relu=False):
-    """Sparse conv forward on tcgen05 tensor cores (3xTF32, fp32 accumulate in TMEM)."""
+def rulebook_mask_sort(pair_fwd):
+    """Mask-sorted tiles (spconv-2.x ``mask_argsort_fwd_splits``): (row_perm (n) i32, pair_sorted (27,n))
+    with pair_sorted = pair_fwd[:, row_perm], rows grouped by a 15-bit digest of their neighbour mask."""
+    pair_fwd = pair_fwd.contiguous()
+    kvol, n = pair_fwd.shape
+    assert kvol == 27 and pair_fwd.dtype == torch.int32
+    dev = pair_fwd.device
+    row_perm = torch.empty((max(n, 1),), dtype=torch.int32, device=dev)[:n]
+    pair_sorted = torch.empty_like(pair_fwd)
+    need = lib().msmd_rulebook_mask_sort_workspace(n)
+    ws = scratch.get(dev, need, slot='mask_sort')
+    with _Timed('rulebook_mask_sort', n=n, kvol=kvol):
+        check(lib().msmd_rulebook_mask_sort(ptr(pair_fwd), kvol, n, ptr(row_perm), ptr(pair_sorted), ptr(ws),
+                                            ws.numel(), stream(dev)), 'msmd_rulebook_mask_sort')
+    return row_perm, pair_sorted
+
+
+def spconv_fwd_tc(features, tcw, pair_fwd, scale=None, shift=None, residual=None, relu=False, row_perm=None):
+    """Sparse conv forward on tcgen05 tensor cores (3xTF32, fp32 accumulate in TMEM).  With
+    ``row_perm`` the table is a mask-sorted one (``rulebook_mask_sort``); the output keeps the original
+    row order."""
     features = features.contiguous()
     if features.dtype != torch.float32:
         features = features.float()
@@ -247,6 +271,15 @@ def spconv_fwd_tc(features, tcw, pair_fwd, scale=None, shift=None, residual=None
                 kvol=tcw.kvol, residual=residual is not None, pair=pair_fwd, path='tc'):
         need = lib().msmd_spconv_tc_workspace(n_out, tcw.cout)  # > 0: split-K pairs (tail balance)
         ws = scratch.get(features.device, need, slot='tc_ws') if need else None
+        if row_perm is not None:
+            assert row_perm.dtype == torch.int32 and row_perm.shape[0] == n_out
+            check(lib().msmd_spconv_fwd_tc_sorted(ptr(features), features.shape[0], ptr(tcw.packed),
+                                                  ptr(pair_fwd), ptr(row_perm.contiguous()), n_out, tcw.cin,
+                                                  tcw.cout, tcw.kvol, ptr(scale), ptr(shift), ptr(residual),
+                                                  int(bool(relu)), ptr(out), ptr(ws),
+                                                  ws.numel() if ws is not None else 0,
+                                                  stream(features.device)), 'msmd_spconv_fwd_tc_sorted')
+            return out
         check(lib().msmd_spconv_fwd_tc_ws(ptr(features), features.shape[0], ptr(tcw.packed), ptr(pair_fwd),
                                           n_out, tcw.cin, tcw.cout, tcw.kvol, ptr(scale), ptr(shift),
                                           ptr(residual), int(bool(relu)), ptr(out), ptr(ws),

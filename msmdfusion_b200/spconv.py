@@ -31,6 +31,9 @@ from .registry import CONV_LAYERS
 
 # contraction kernel: 'tc' (tcgen05, 3xTF32) or 'simt' (exact fp32 FFMA); MSMD_CONV_PATH overrides
 CONV_PATH = os.environ.get('MSMD_CONV_PATH', 'tc')
+# opt-in: mask-sorted tiles for the 3x3x3 SubM layers of the tensor-core path (spconv-2.x
+# mask_argsort_fwd_splits); MSMD_MASK_SORT=1 also switches it on inside the native executor
+MASK_SORT = os.environ.get('MSMD_MASK_SORT', '0') not in ('', '0')
 
 
 def expand_nd(ndim, val):
@@ -83,6 +86,14 @@ class IndexSet:
             pair = ops.rulebook_subm(self.indices, self.grid, ksize, dilation)
             self._subm[key] = pair
         return pair
+
+    def subm_pairs_sorted(self, ksize, dilation):
+        """(row_perm, pair_sorted) of the SubM rulebook (``ops.rulebook_mask_sort``), built once."""
+        key = ('sorted', tuple(ksize), tuple(dilation))
+        ent = self._subm.get(key)
+        if ent is None:
+            ent = self._subm[key] = ops.rulebook_mask_sort(self.subm_pairs(ksize, dilation))
+        return ent
 
     def rulebook_record(self, pair, subm, ksize, dilation, path):
         """The dict ``autograd.SparseConvFunction`` differentiates through.  One record per rulebook
@@ -441,8 +452,14 @@ class SparseConvolution(SparseModule):
             if relu:
                 out_features = torch.relu(out_features)
         else:
-            out_features = ops.spconv_fwd(features, self.packed_weight(), pair, scale, shift, residual,
-                                          relu)
+            packed = self.packed_weight()
+            if MASK_SORT and self.subm and pair.shape[0] == 27 and isinstance(packed, ops.TcWeight) \
+                    and pair.shape[1] > 0:
+                row_perm, pair_sorted = iset.subm_pairs_sorted(self.kernel_size, self.dilation)
+                out_features = ops.spconv_fwd_tc(features, packed, pair_sorted, scale, shift, residual, relu,
+                                                 row_perm=row_perm)
+            else:
+                out_features = ops.spconv_fwd(features, packed, pair, scale, shift, residual, relu)
         out = SparseConvTensor(out_features, out_iset.indices, out_shape, input.batch_size,
                                indice_dict=indice_dict, benchmark=input.benchmark)
         out.benchmark_record = input.benchmark_record

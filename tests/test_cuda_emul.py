@@ -281,3 +281,74 @@ def test_conv_autograd_function_on_emulated_kernels(ops_on_emulator, monkeypatch
         assert rel(out.features.detach().numpy(), cpu.spconv_fwd(feat, w, pair)) < 1e-5
         assert rel(f.grad.numpy(), ri) < 1e-5
         assert rel(conv.weight.grad.numpy(), rw) < 1e-5
+
+
+# --------------------------------------------------------------------------------------
+# mask-sorted tiles: digest + stable radix sort + table permutation (csrc/fusion.cu, sort.cuh, scan.cuh)
+# --------------------------------------------------------------------------------------
+def digest_key(mask):
+    """The 15-bit structural digest (tests/tools/mask_sort_estimate.py): own z plane (9 bits), then one
+    'any neighbour in this ky row' bit per row of the plane above, then of the plane below."""
+    lower, centre, upper = mask & 0x1FF, (mask >> 9) & 0x1FF, (mask >> 18) & 0x1FF
+    key = centre.copy()
+    for plane, base in ((upper, 9), (lower, 12)):
+        for row in range(3):
+            key |= (((plane >> (3 * row)) & 7) != 0).astype(np.int64) << (base + row)
+    return key
+
+
+def test_emulator_calibration_modality_split_sort_and_scan():
+    """The GPU-verified voxel_modality_split (stable radix sort + device scan + merge) on the emulator
+    reproduces the oracle bit for bit: sort.cuh / scan.cuh execute faithfully."""
+    rng = np.random.default_rng(0)
+    shape = [41, 60, 60]
+    def coords(n):
+        lin = rng.choice(int(np.prod(shape)), size=n, replace=False)
+        return np.stack([np.zeros(n, np.int64), lin // 3600, (lin // 60) % 60, lin % 60], 1).astype(np.int32)
+    c3, c2 = coords(2500), coords(3100)
+    c2[:800] = c3[rng.choice(2500, 800, replace=False)]
+    m3 = np.full(2500, -1, np.int32)
+    m2 = np.full(3100, -1, np.int32)
+    s3 = np.full(2500, -1, np.int64)
+    s2 = np.full(2500, -1, np.int64)
+    cnt = np.zeros(1, np.int32)
+    L = emu()
+    L.emu_msmd_modality_split_workspace.restype = ctypes.c_size_t
+    need = L.emu_msmd_modality_split_workspace(2500, 3100)
+    ws = np.zeros(need, np.uint8)
+    ok(L.emu_msmd_modality_split(P(c3), 2500, P(c2), 3100, ctypes.c_longlong(0), ctypes.c_longlong(0), P(m3), P(m2),
+                                 P(s3), P(s2), P(cnt), P(ws), ctypes.c_size_t(need), None))
+    e3, e2, es3, es2 = cpu.voxel_modality_split(c3, c2, 1)
+    assert np.array_equal(m3, e3[:, 1]) and np.array_equal(m2, e2[:, 1])
+    p = int(cnt[0])
+    assert p == es3.shape[0] and np.array_equal(s3[:p], es3) and np.array_equal(s2[:p], es2)
+
+
+@pytest.mark.parametrize('n', [700, 5000])
+def test_mask_sort_on_emulator(n):
+    from msmdfusion_b200 import synthetic
+    pts = synthetic.lidar_scene(seed=4, sweeps=1)[:n * 2]
+    _, c, _ = cpu.hard_voxelize(pts, synthetic.VOXEL_SIZE, synthetic.POINT_CLOUD_RANGE, 10, 160000)
+    idx = np.concatenate([np.zeros((c.shape[0], 1), np.int32), c], 1)[:n]
+    n = idx.shape[0]
+    pair = cpu.subm_rulebook(idx, [41, 1440, 1440], 3, 1)
+    L = emu()
+    L.emu_msmd_rulebook_mask_sort_workspace.restype = ctypes.c_size_t
+    need = L.emu_msmd_rulebook_mask_sort_workspace(n)
+    ws = np.zeros(need, np.uint8)
+    perm = np.full(n, -1, np.int32)
+    pair_sorted = np.full_like(pair, -9)
+    ok(L.emu_msmd_rulebook_mask_sort(P(pair), 27, n, P(perm), P(pair_sorted), P(ws), ctypes.c_size_t(need), None))
+    used = pair >= 0
+    mask = (used.astype(np.int64) * (1 << np.arange(27))[:, None]).sum(0)
+    expect = np.argsort(digest_key(mask), kind='stable')
+    assert np.array_equal(perm, expect.astype(np.int32))
+    assert np.array_equal(pair_sorted, pair[:, perm])
+    # what the sort is for: fewer (tile, kernel offset) products than the index-set order
+    def products(order):
+        nt = (n + 127) // 128
+        u = np.concatenate([used[:, order], np.zeros((27, nt * 128 - n), bool)], 1).reshape(27, nt, 128).any(2)
+        return int(u.sum())
+    assert products(perm) < products(np.arange(n))
+    assert L.emu_msmd_rulebook_mask_sort(P(pair), 27, n, P(perm), P(pair_sorted), P(ws), ctypes.c_size_t(64), None) == -3
+    assert L.emu_msmd_rulebook_mask_sort(P(pair), 9, n, P(perm), P(pair_sorted), P(ws), ctypes.c_size_t(need), None) == -1

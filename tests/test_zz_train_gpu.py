@@ -234,3 +234,63 @@ def test_lc_train_step_runs_and_learns():
     assert not any('grouped_sp_conv_blocks_2D' in k or 'grouped_sp_conv_blocks_mix' in k for k in moved)
     assert len([k for k in moved if k.endswith('conv1.weight') or k.endswith('conv2.weight') or
                 k.endswith('.0.weight') and ('downscale' in k or 'blocks_3D' in k)]) == 16
+
+
+# --------------------------------------------------------------------------------------
+# mask-sorted tiles (opt-in, MSMD_MASK_SORT=1): same results as the index-set order
+# --------------------------------------------------------------------------------------
+@pytest.mark.parametrize('cin,cout', [(16, 16), (64, 64), (128, 128), (5, 16)])
+def test_mask_sorted_conv_equals_unsorted(cin, cout):
+    """msmd_rulebook_mask_sort + msmd_spconv_fwd_tc_sorted against msmd_spconv_fwd_tc_ws on a LiDAR voxel
+    set, fused epilogue included.  A row's accumulation order does not depend on its tile, so layers
+    without split-K agree bit for bit; split-K layers regroup two partial sums (<= 1e-5)."""
+    pts = synthetic.lidar_scene(seed=2, sweeps=1)
+    _, c, _ = cpu.hard_voxelize(pts, synthetic.VOXEL_SIZE, synthetic.POINT_CLOUD_RANGE, 10, 160000)
+    idx = cuda(np.concatenate([np.zeros((c.shape[0], 1), np.int32), c], 1))
+    n = idx.shape[0]
+    shape = [41, 1440, 1440]
+    grid = ops.grid_build(idx, 1, shape)
+    pair = ops.rulebook_subm(idx, grid, [3, 3, 3], 1)
+    row_perm, pair_sorted = ops.rulebook_mask_sort(pair)
+    pn, rp = pair.cpu().numpy(), row_perm.cpu().numpy()
+    assert np.array_equal(np.sort(rp), np.arange(n)) and np.array_equal(pair_sorted.cpu().numpy(), pn[:, rp])
+    gen = torch.Generator().manual_seed(cin)
+    feat = torch.randn(n, cin, generator=gen).to(dev())
+    w = (torch.randn(cout, 3, 3, 3, cin, generator=gen) / (cin * 27 * 0.2) ** 0.5).to(dev())
+    tcw = ops.pack_weight_tc(w)
+    scale = (torch.rand(cout, generator=gen) + 0.5).to(dev())
+    shift = torch.randn(cout, generator=gen).to(dev())
+    res = torch.randn(n, cout, generator=gen).to(dev())
+    for args in ((None, None, None, False), (scale, shift, res, True)):
+        a = ops.spconv_fwd_tc(feat, tcw, pair, *args)
+        b = ops.spconv_fwd_tc(feat, tcw, pair_sorted, *args, row_perm=row_perm)
+        torch.cuda.synchronize()
+        if ops.lib().msmd_spconv_tc_workspace(n, cout) == 0:
+            assert torch.equal(a, b)
+        else:
+            assert err(b, a) < 1e-5
+
+
+def test_executor_with_mask_sort_equals_default():
+    """The native executor with msmd_spconv_set_mask_sort(1): SparseEncoder outputs against the default
+    order (bit-identical except through split-K layers: <= 1e-5 of the tensor's scale)."""
+    from msmdfusion_b200 import registry
+    cfg = m.Config.fromfile(os.path.join(ROOT, 'configs', 'msmd_lc_hotpath.py')).hotpath
+    torch.manual_seed(0)
+    enc = registry.build_middle_encoder(cfg.pts_middle_encoder).to(dev()).eval()
+    layer = m.Voxelization(**cfg.pts_voxel_layer).eval()
+    outs = []
+    try:
+        for flag in (False, True):
+            ops.set_mask_sort(flag)
+            with torch.no_grad():
+                mean, coors, _ = layer.forward_mean(cuda(synthetic.lidar_scene(seed=5, sweeps=1)), 5, batch_idx=0)
+                spatial, feats = enc(mean, coors, 1)
+            torch.cuda.synchronize()
+            outs.append((spatial.clone(), [(f.indices.clone(), f.features.clone()) for f in feats]))
+    finally:
+        ops.set_mask_sort(False)
+    (s0, f0), (s1, f1) = outs
+    assert err(s1, s0) < 1e-5
+    for (i0, x0), (i1, x1) in zip(f0, f1):
+        assert torch.equal(i0, i1) and err(x1, x0) < 1e-5

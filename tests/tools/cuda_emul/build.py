@@ -19,7 +19,9 @@ def _device_helpers():
     start = text.index('// device helpers')
     start = text.index('\n', text.index('// ----', start)) + 1
     end = text.rindex('}  // namespace msmd')
-    return 'namespace msmd {\n' + text[start:end] + '}  // namespace msmd\n'
+    ws0 = text.index('// Bump allocator')
+    ws1 = text.index('// ----', ws0)
+    return 'namespace msmd {\n' + text[ws0:ws1] + text[start:end] + '}  // namespace msmd\n'
 
 
 def _rewrite_launches(src):
@@ -61,12 +63,29 @@ def _rewrite_launches(src):
     return ''.join(out)
 
 
+_INLINED = set()
+
+
+def _inline_headers(src):
+    """#include "x.cuh" -> the header's text, once per unit (common.cuh is provided by cuda_emul.h +
+    _device_helpers)."""
+    def sub(m):
+        name = m.group(1)
+        if name == 'common.cuh' or name in _INLINED:
+            return ''
+        _INLINED.add(name)
+        text = open(os.path.join(CSRC, name)).read().replace('#pragma once', '')
+        return _inline_headers(text)
+    return re.sub(r'#include "(\w+\.cuh)"', sub, src)
+
+
 def translate(cu_name):
-    src = open(os.path.join(CSRC, cu_name)).read()
-    src = src.replace('#include "common.cuh"', '')
-    src = src.replace('#include "scan.cuh"', '')
+    src = _inline_headers(open(os.path.join(CSRC, cu_name)).read())
     src = _rewrite_launches(src)
+    defined = re.findall(r'extern "C" MSMD_API \w[\w ]*?[ *]msmd_(\w+)\(', src)
     src = re.sub(r'extern "C" MSMD_API (\w[\w ]*?[ *])msmd_(\w+)\(', r'extern "C" \1emu_msmd_\2(', src)
+    for name in defined:  # calls between entry points of this unit follow the renaming
+        src = re.sub(r'(?<![\w])msmd_%s\(' % name, 'emu_msmd_%s(' % name, src)
     # calls between entry points of the same unit keep working; calls into OTHER units are stubbed
     return src
 
@@ -90,22 +109,27 @@ extern "C" int msmd_spconv_fwd_tc_ws(const float*, int, const float*, const int*
                                      const float*, const float*, int, float*, void*, size_t, msmd_stream_t) { return -100; }
 extern "C" int msmd_spconv_fwd(const float*, int, const float*, const int*, int, int, int, int, const float*,
                                const float*, const float*, int, float*, msmd_stream_t);
+extern "C" size_t msmd_grid_num_words(int batch_size, const int* s) {   // as csrc/rulebook.cu
+  return (size_t)(((long long)batch_size * s[0] * s[1] * s[2] + 31) / 32);
+}
 '''
 
 
 def build(verbose=False):
     os.makedirs(OUT, exist_ok=True)
     lib = os.path.join(OUT, 'libmsmd_emul.so')
-    deps = [os.path.join(CSRC, f) for f in ('common.cuh', 'spconv_bwd.cu', 'spconv.cu')] + \
+    deps = [os.path.join(CSRC, f) for f in ('common.cuh', 'spconv_bwd.cu', 'spconv.cu', 'fusion.cu', 'sort.cuh',
+                                            'scan.cuh')] + \
         [os.path.join(HERE, 'cuda_emul.h'), os.path.abspath(__file__)]
     if os.path.exists(lib) and all(os.path.getmtime(lib) > os.path.getmtime(d) for d in deps):
         return lib
     fwd = translate('spconv.cu').replace('emu_msmd_spconv_fwd(', 'msmd_spconv_fwd(')  # linked by bwd_data
-    text = PRELUDE + _device_helpers() + STUBS_BWD + fwd + translate('spconv_bwd.cu')
+    _INLINED.clear()
+    text = PRELUDE + _device_helpers() + STUBS_BWD + fwd + translate('spconv_bwd.cu') + translate('fusion.cu')
     cpp = os.path.join(OUT, 'emul_unit.cpp')
     with open(cpp, 'w') as f:
         f.write(text)
-    cmd = ['g++', '-std=c++20', '-O1', '-g', '-shared', '-fPIC', '-pthread', '-I', HERE, cpp, '-o', lib]
+    cmd = ['g++', '-std=c++20', '-O1', '-g', '-ffp-contract=off', '-shared', '-fPIC', '-pthread', '-I', HERE, cpp, '-o', lib]
     if verbose:
         print(' '.join(cmd))
     subprocess.check_call(cmd)

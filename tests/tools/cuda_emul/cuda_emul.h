@@ -137,6 +137,57 @@ static inline T __shfl_xor_sync(unsigned, T v, int d) {
   return emu_warp_exchange(v, lane ^ d, true);
 }
 template <typename T>
+static inline unsigned __match_any_sync(unsigned, T v) {
+  static_assert(sizeof(T) <= sizeof(long long), "match payload");
+  const unsigned lin = threadIdx.x + threadIdx.y * blockDim.x + threadIdx.z * blockDim.x * blockDim.y;
+  auto& box = ::emu::g_warps[lin / 32];
+  long long raw = 0;
+  memcpy(&raw, &v, sizeof(T));
+  box.slot[lin & 31] = raw;
+  box.bar->arrive_and_wait();
+  unsigned m = 0;
+  for (int l = 0; l < 32; ++l) m |= (box.slot[l] == raw ? 1u : 0u) << l;
+  box.bar->arrive_and_wait();
+  return m;
+}
+static inline unsigned __ballot_sync(unsigned, int pred) {
+  unsigned m = __match_any_sync(0xffffffffu, pred ? 1 : 0);
+  return pred ? m : ~m;
+}
+template <typename T>
+static inline T atomicAdd(T* p, T v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+static inline float atomicAdd(float* p, float v) {
+  float old = *p, want;
+  do { want = old + v; } while (!__atomic_compare_exchange(p, &old, &want, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST));
+  return old;
+}
+template <typename T>
+static inline T atomicOr(T* p, T v) { return __atomic_fetch_or(p, v, __ATOMIC_SEQ_CST); }
+template <typename T>
+static inline T atomicExch(T* p, T v) { return __atomic_exchange_n(p, v, __ATOMIC_SEQ_CST); }
+template <typename T>
+static inline T atomicMax(T* p, T v) {
+  T old = __atomic_load_n(p, __ATOMIC_SEQ_CST);
+  while (old < v && !__atomic_compare_exchange_n(p, &old, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {}
+  return old;
+}
+template <typename T>
+static inline T atomicMin(T* p, T v) {
+  T old = __atomic_load_n(p, __ATOMIC_SEQ_CST);
+  while (old > v && !__atomic_compare_exchange_n(p, &old, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {}
+  return old;
+}
+static inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+static inline void __syncwarp(unsigned = 0xffffffffu) {
+  const unsigned lin = threadIdx.x + threadIdx.y * blockDim.x + threadIdx.z * blockDim.x * blockDim.y;
+  ::emu::g_warps[lin / 32].bar->arrive_and_wait();
+}
+static inline float __fmul_rn(float a, float b) { volatile float r = a * b; return r; }
+static inline float __fadd_rn(float a, float b) { volatile float r = a + b; return r; }
+static inline float __uint_as_float(unsigned u) { float f; memcpy(&f, &u, 4); return f; }
+static inline unsigned __float_as_uint(float f) { unsigned u; memcpy(&u, &f, 4); return u; }
+static inline int __float2int_rz(float f) { return (int)f; }
+template <typename T>
 static inline T __ldg(const T* p) { return *p; }
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
 static inline int __ffs(unsigned v) { return __builtin_ffs((int)v); }
