@@ -1,0 +1,33 @@
+#!/bin/bash
+# First GPU call of round 2 (everything written at the end of round 1 without GPU time), in priority order.
+#   /usr/local/graft/bin/gpurun --timeout 1500 -- 'bash tools/gpu_round2.sh'
+# Outputs land in gpurun_out/r02a_*; each step has its own timeout so that one hang cannot eat the call.
+set -u
+mkdir -p gpurun_out
+O=gpurun_out
+# 1. the forward-path suite first (must stay green), then the new backward / mask-sort tests on their own
+timeout 900 python -m pytest tests -m gpu -x -q --deselect tests/test_zz_train_gpu.py > $O/r02a_pytest_forward.log 2>&1
+echo "forward suite exit $?" | tee -a $O/r02a_summary.txt
+timeout 600 python -m pytest tests/test_zz_train_gpu.py -q > $O/r02a_pytest_train_masksort.log 2>&1
+echo "train + mask-sort suite exit $?" | tee -a $O/r02a_summary.txt
+tail -n 30 $O/r02a_pytest_train_masksort.log
+# 2. bench lines: default, mask-sorted, LC, LC mask-sorted, train step
+timeout 300 python bench.py --steps 100 --warmup 30 > $O/r02a_bench_S.json 2>$O/r02a_bench_S.err
+MSMD_MASK_SORT=1 timeout 300 python bench.py --steps 100 --warmup 30 --no-cpu-baseline > $O/r02a_bench_S_masksort.json 2>$O/r02a_bench_S_masksort.err
+MSMD_MASK_SORT=1 timeout 300 python bench.py --profile L --steps 50 --warmup 10 --no-cpu-baseline > $O/r02a_bench_L_masksort.json 2>&1
+timeout 300 python bench.py --profile L --steps 50 --warmup 10 --no-cpu-baseline > $O/r02a_bench_L.json 2>&1
+timeout 300 python bench.py --workload LC --steps 30 --warmup 10 --no-cpu-baseline > $O/r02a_bench_LC.json 2>&1
+MSMD_MASK_SORT=1 timeout 300 python bench.py --workload LC --steps 30 --warmup 10 --no-cpu-baseline > $O/r02a_bench_LC_masksort.json 2>&1
+timeout 300 python bench.py --workload train --steps 20 --warmup 5 --no-cpu-baseline --breakdown $O/r02a_breakdown_train.json > $O/r02a_bench_train.json 2>$O/r02a_bench_train.err
+for f in S S_masksort L L_masksort LC LC_masksort train; do
+  echo "== $f"; tail -c 600 $O/r02a_bench_$f.json | python -c "import sys,json
+try:
+    d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print(d.get('value'), d.get('ms_per_step'), (d.get('e2e') or {}).get('value'))
+except Exception as e: print('unparsed', e)"
+done | tee -a $O/r02a_summary.txt
+# 3. ncu: launch list of the train step, full capture of the wgrad kernel
+timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -s 600 -c 500 --csv --log-file $O/r02a_launches_train.csv \
+  python bench.py --workload train --steps 2 --warmup 3 --no-cpu-baseline > /dev/null 2>&1
+timeout 400 ncu --set full --clock-control none --import-source on -k regex:spconv_wgrad -s 16 -c 16 -o $O/r02a_prof_wgrad \
+  python bench.py --workload train --steps 1 --warmup 3 --no-cpu-baseline > /dev/null 2>&1
+ls -la $O | tail -n 20
