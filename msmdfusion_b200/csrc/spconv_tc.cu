@@ -677,9 +677,7 @@ tc_pack_weight_kernel(const float* __restrict__ w, int cout, int kvol, int cin, 
   const int k = K / cin_pad, c = K - k * cin_pad;
   float val = 0.f;
   if (k < kvol && c < cin && n < cout) val = w[((size_t)n * kvol + k) * cin + c];
-  uint32_t hb;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(val));
-  const float hi = __uint_as_float(hb);
+  const float hi = tc::round_tf32(val);
   const float lo = val - hi;
   const size_t blk = (size_t)N * kTcKC;
   const size_t off = (size_t)n * kTcKC + (size_t)((((kk >> 2) ^ (n & 7)) << 2) + (kk & 3));

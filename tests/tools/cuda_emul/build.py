@@ -56,7 +56,8 @@ def _rewrite_launches(src):
             q += 1
         args = src[p + 1:q]
         out.append(src[pos:m.start()])
-        out.append(f'::emu::launch(dim3({parts[0].strip()}), dim3({parts[1].strip()}), [&]() {{ '
+        smem = parts[2].strip() if len(parts) > 2 else '0'
+        out.append(f'::emu::launch(dim3({parts[0].strip()}), dim3({parts[1].strip()}), (size_t)({smem}), [&]() {{ '
                    f'{m.group(1)}({args}); }})')
         pos = q + 1
     out.append(src[pos:])
@@ -98,6 +99,9 @@ std::barrier<>* g_block_barrier = nullptr;
 std::vector<WarpBox> g_warps;
 char g_error[512];
 std::atomic<int> g_or{0};
+uint8_t* g_dyn_smem = nullptr;
+void (*g_block_begin)(uint32_t) = nullptr;
+void (*g_block_end)() = nullptr;
 }
 extern "C" const char* emu_last_error() { return ::emu::g_error; }
 '''
@@ -136,5 +140,57 @@ def build(verbose=False):
     return lib
 
 
+TC_PRELUDE = '''#include "tc_emul.h"
+namespace emu {
+uint8_t* g_smem_window = nullptr;
+uint32_t g_dyn_bytes = 0;
+std::mutex g_tc_mu;
+std::condition_variable g_tc_cv;
+std::map<uint32_t, MBar> g_mbar;
+uint32_t g_tmem[128][512];
+uint32_t g_tmem_next = 0, g_tmem_live = 0;
+NamedBar g_named[16];
+std::atomic<long long> g_mma_count{0};
+static void tc_begin(uint32_t bytes) { tc_block_reset(bytes); g_dyn_smem = g_smem_window + kDynBase; }
+static void tc_end() { tc_block_check(); }
+static struct TcHooks { TcHooks() { g_block_begin = tc_begin; g_block_end = tc_end; } } g_tc_hooks;
+}
+extern "C" long long emu_tc_mma_count() { return ::emu::g_mma_count.load(); }
+'''
+
+
+def build_tc(verbose=False):
+    """Host-emulated copy of csrc/spconv_tc.cu (tcgen05 / TMEM / bulk-copy kernels) over tc_emul.h."""
+    os.makedirs(OUT, exist_ok=True)
+    lib = os.path.join(OUT, 'libmsmd_tc_emul.so')
+    deps = [os.path.join(CSRC, f) for f in ('common.cuh', 'spconv_tc.cu')] + \
+        [os.path.join(HERE, 'cuda_emul.h'), os.path.join(HERE, 'tc_emul.h'), os.path.abspath(__file__)]
+    if os.path.exists(lib) and all(os.path.getmtime(lib) > os.path.getmtime(d) for d in deps):
+        return lib
+    _INLINED.clear()
+    _INLINED.add('tc.cuh')   # replaced by tc_emul.h
+    unit = translate('spconv_tc.cu')
+    _INLINED.clear()
+    # dynamic shared memory: the window tc_emul.h hands out (deliberately 16-byte aligned only)
+    unit, n = re.subn(r'extern __shared__ uint8_t (\w+)\[\];', r'uint8_t* \1 = ::emu::g_dyn_smem;', unit)
+    assert n >= 1
+    fwd_decl = '''
+extern "C" int emu_msmd_spconv_fwd_tc_ws(const float*, int, const float*, const int*, int, int, int, int, const float*,
+                                         const float*, const float*, int, float*, void*, size_t, msmd_stream_t);
+extern "C" size_t emu_msmd_spconv_tc_workspace(int, int);
+'''   # declared by include/msmd_b200.h in the real build
+    text = PRELUDE + TC_PRELUDE + _device_helpers() + fwd_decl + unit
+    cpp = os.path.join(OUT, 'emul_tc_unit.cpp')
+    with open(cpp, 'w') as f:
+        f.write(text)
+    cmd = ['g++', '-std=c++20', '-O2', '-g', '-ffp-contract=off', '-Wno-unknown-pragmas', '-shared', '-fPIC',
+           '-pthread', '-I', HERE, cpp, '-o', lib]
+    if verbose:
+        print(' '.join(cmd))
+    subprocess.check_call(cmd)
+    return lib
+
+
 if __name__ == '__main__':
+    print(build_tc(verbose=True))
     print(build(verbose=True))

@@ -1,5 +1,5 @@
 // cuda_emul.h -- TEST INFRASTRUCTURE: a minimal CPU emulation of the CUDA execution model, enough to
-// run this repository's SIMT kernels (no tensor-core / TMA / cluster code) functionally on the host
+// run this repository's SIMT kernels (tensor-core / bulk-copy code: see tc_emul.h; no cluster code) functionally on the host
 // when no GPU is available.  One std::thread per CUDA thread, thread blocks run one after another,
 // __syncthreads() is a std::barrier, warp shuffles go through a per-warp exchange buffer.  It checks
 // indexing, barrier placement and arithmetic order -- not performance, not memory-model races.
@@ -60,9 +60,13 @@ struct WarpBox {
 extern std::vector<WarpBox> g_warps;
 extern char g_error[512];
 extern std::atomic<int> g_or;
+// dynamic shared memory + per-CTA hooks (set by tc_emul.h's translation unit; null for the SIMT units)
+extern uint8_t* g_dyn_smem;
+extern void (*g_block_begin)(uint32_t dyn_smem_bytes);
+extern void (*g_block_end)();
 
 template <typename F>
-void launch(dim3 grid, dim3 block, F body) {
+void launch(dim3 grid, dim3 block, size_t dyn_smem_bytes, F body) {
   const unsigned nthreads = block.x * block.y * block.z;
   g_blockDim = block;
   g_gridDim = grid;
@@ -71,6 +75,7 @@ void launch(dim3 grid, dim3 block, F body) {
       for (unsigned bx = 0; bx < grid.x; ++bx) {
         std::barrier<> bar(nthreads);
         g_block_barrier = &bar;
+        if (g_block_begin) g_block_begin((uint32_t)dyn_smem_bytes);
         g_warps.clear();
         g_warps.resize((nthreads + 31) / 32);
         for (unsigned w = 0; w < g_warps.size(); ++w) {
@@ -88,8 +93,11 @@ void launch(dim3 grid, dim3 block, F body) {
             g_warps[t / 32].bar->arrive_and_drop();
           });
         for (auto& th : ts) th.join();
+        if (g_block_end) g_block_end();
       }
 }
+template <typename F>
+void launch(dim3 grid, dim3 block, F body) { launch(grid, block, 0, body); }
 }  // namespace emu
 
 #define threadIdx (::emu::t_threadIdx)
