@@ -42,6 +42,10 @@ def parse():
                          'LC: MSMDFusion_nusc_voxel_LC voxel-space fusion path (configs[2]); '
                          'train: LC train step (configs[4]): forward in train mode, backward through the GMA '
                          'encoder, one NCCL gradient all-reduce, clip, AdamW')
+    ap.add_argument('--precision', default=None, choices=['tf32x3', 'bf16x3', 'bf16'],
+                    help='operand precision of the tensor-core sparse convolutions (default: MSMD_CONV_PRECISION or '
+                         'tf32x3 = the fp32-parity mode).  bf16x3: bf16 hi/lo split, ~5e-6 per layer.  bf16: operands '
+                         'rounded to bf16 (the train-step arithmetic of BASELINE configs[4]; not a parity mode)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--breakdown', default=None, help='write a per-op CUDA-event breakdown (json) here')
     return ap.parse_args()
@@ -53,6 +57,15 @@ def peaks():
         d = json.load(open(p))
         return float(d['hbm_gbs']), float(d.get('bf16_tflops', 1590.0)), 'measured'
     return 6650.0, 1590.0, 'fallback'
+
+
+ARITHMETIC = {
+    'tf32x3': 'fp32 in/out; contraction = 3xTF32 tensor-core split with fp32 accumulate (<=1e-4 vs fp32 oracle)',
+    'bf16x3': 'fp32 in/out; contraction = bf16 hi/lo split (3 kind::f16 MMAs per product) with fp32 accumulate '
+              '(~5e-6 per layer vs fp32; opt-in)',
+    'bf16': 'fp32 storage; contraction operands rounded to bf16 (1 kind::f16 MMA per product), fp32 accumulate -- '
+            'NOT a parity mode (2e-3 per layer): the train-step arithmetic of BASELINE configs[4]',
+}
 
 
 def workload_name(profile, workload='L'):
@@ -181,6 +194,10 @@ def conv_layer_bytes_flops(records):
 def run_ours(args, rank, world, device):
     import torch.distributed as dist
     from msmdfusion_b200 import _cabi, ops, synthetic
+    from msmdfusion_b200 import spconv as _spconv
+    if args.precision:
+        _spconv.CONV_PRECISION = args.precision
+    args.precision = _spconv.CONV_PRECISION
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)  # > 126 MB L2
     trainer = None
     if args.workload == 'train':
@@ -350,9 +367,11 @@ def run_ours(args, rank, world, device):
         tc = paths == ['tc'] or (args.workload == 'train' and 'tc' in paths)
         gbs = b / (conv_ms * 1e-3) / 1e9 if conv_ms else 0.0
         tfl = f / (conv_ms * 1e-3) / 1e12 if conv_ms else 0.0
-        tf32_peak = bf16 / 2.0  # tcgen05 kind::tf32 issues at half the bf16 rate
+        # tcgen05 kind::tf32 issues at half the bf16 rate; the 16-bit modes run kind::f16 at the bf16 rate
+        tf32_peak = bf16 / 2.0 if args.precision == 'tf32x3' else bf16
+        mma_per_product = 1 if args.precision == 'bf16' else 3
         hbm_time = b / (hbm * 1e9)
-        tensor_time = (3.0 * f) / (tf32_peak * 1e12) if tc else 0.0  # 3 MMAs per product (3xTF32)
+        tensor_time = (mma_per_product * f) / (tf32_peak * 1e12) if tc else 0.0
         traffic, traffic_src, ncu_tensor_pct = None, None, None
         tp = os.path.join(ROOT, 'profiles', 'r01e_ncu_full_spconv_tc_profileS.json')
         if tc and args.workload == 'L' and args.profile == 'S' and os.path.exists(tp):
@@ -366,13 +385,15 @@ def run_ours(args, rank, world, device):
         common = {'traffic': traffic, 'traffic_source': traffic_src, 'peak_source': src,
                   'kernel': ('sparse conv forward + data gradient (tcgen05 kind::tf32, 3xTF32) + weight gradient '
                              '(spconv_wgrad_simt_kernel, FFMA)' if args.workload == 'train' else
-                             'spconv_fwd_tc_kernel (tcgen05 kind::tf32, 3xTF32)' if tc else
+                             'spconv_fwd_tc_kernel (tcgen05 kind::tf32, 3xTF32)' if tc and args.precision == 'tf32x3' else
+                             'spconv_fwd_tc16_kernel (tcgen05 kind::f16 on bf16 operands, %s)' % args.precision if tc else
                              'spconv_fwd_simt_kernel') + ' (%d launches/scene, summed)' % (len(conv) // 3),
                   'kernel_ms_per_step': round(conv_ms / 3, 4),
                   'algorithmic_bytes_per_step': b / 3, 'algorithmic_flops_per_step': f / 3,
                   'hbm': {'achieved_gbs': round(gbs, 2), 'peak_gbs': hbm, 'frac': round(gbs / hbm, 4)},
                   'tensor': {'achieved_tflops': round(tfl, 3), 'peak_tf32_tflops': round(tf32_peak, 1),
-                             'frac': round(tfl / tf32_peak, 4), 'mma_per_product': 3 if tc else 0,
+                             'frac': round(tfl / tf32_peak, 4), 'mma_per_product': mma_per_product if tc else 0,
+                             'operand_precision': args.precision,
                              'ncu_tensor_pipe_active_pct_time_weighted': ncu_tensor_pct,
                              'note': 'algorithmic flops 2*P*Cin*Cout; the fp32-parity mode issues 3 tf32 '
                                      'MMAs per product, so the attainable ceiling is peak/3'}}
@@ -483,8 +504,8 @@ def main():
     line = {
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': K, 'warmup': max(args.warmup, 3),
         'ms_per_step': res['dev_ms'] / K, 'step_ms': res['step_ms'], 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-        'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': workload_name(args.profile, args.workload), 'arithmetic': 'fp32 in/out; contraction = 3xTF32 tensor-core split with fp32 accumulate (<=1e-4 vs fp32 oracle)', 'points_per_scene': res['points'],
+        'dtype': 'bf16' if args.precision == 'bf16' else 'f32', 'data': 'synthetic',
+        'config': {'workload': workload_name(args.profile, args.workload), 'arithmetic': ARITHMETIC[args.precision], 'points_per_scene': res['points'],
                    'voxels_per_scene': res['voxels'], 'scenes_per_gpu_per_step': 1, 'parallelism': 'dp%d' % world,
                    'l2': 'flushed between steps (256 MiB memset, outside the per-step events)',
                    'settle': '%d untimed steps (the first + %.0f ms of wall time) before the %d warm-up steps' % (res['settle_steps'], SETTLE_MS, max(args.warmup, 3)),

@@ -187,6 +187,29 @@ MSMD_API int msmd_spconv_fwd_tc_sorted(const float* features, int n_in, const fl
 MSMD_API int msmd_spconv_set_mask_sort(int enable);
 
 /* ------------------------------------------------------------------------------------
+ * 16-bit operand modes of the tensor-core sparse convolution (csrc/spconv_tc16.cu) -- same contract as
+ * msmd_spconv_fwd_tc (features / out fp32 in HBM, fp32 accumulate, fused epilogue), the contraction on
+ * tcgen05.mma.kind::f16 with bf16 operands, 64 K elements per pipeline step:
+ *   x3 = 0  "bf16":    operands rounded to bf16, one MMA per product.  The arithmetic BASELINE configs[4]
+ *                      names for the train step ("bf16 sparse-conv kernels"; spconv-2.x runs fp16/bf16
+ *                      features through the same Fsp.implicit_gemm call, bug_fix/conv.py:442-447).  Outside the
+ *                      1e-4 inference parity bound.
+ *   x3 = 1  "bf16x3":  operands split hi + lo in bf16, three MMAs per product (lo*lo dropped): ~5e-6
+ *                      relative per layer, inside the parity bound, half the tensor-pipe time of 3xTF32.
+ * `packed_tc16`: msmd_spconv_tc16_pack_weight image (msmd_spconv_tc16_packed_bytes bytes) of the KRSC weight
+ * for the SAME x3.  `row_perm` NULL, or the slot -> row map of a mask-sorted table (msmd_rulebook_mask_sort).
+ * Opt-in (MSMD_CONV_PRECISION / MSMD_TRAIN_PRECISION, msmd_conv_layer.weight_tc 2 / 3): checked on the host
+ * model of tcgen05 only, not yet run on hardware.
+ * ---------------------------------------------------------------------------------- */
+MSMD_API size_t msmd_spconv_tc16_packed_bytes(int cout, int kvol, int cin, int x3);
+MSMD_API int msmd_spconv_tc16_pack_weight(const float* weight_krsc, int cout, int kvol, int cin, int x3,
+                                          void* packed_tc16, msmd_stream_t stream);
+MSMD_API int msmd_spconv_fwd_tc16(const float* features, int n_in, const void* packed_tc16,
+                                  const int* pair_fwd, const int* row_perm, int n_out, int cin, int cout,
+                                  int kvol, int x3, const float* scale, const float* shift,
+                                  const float* residual, int relu, float* out, msmd_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
  * Sparse convolution BACKWARD (config 5, the train step) -- replaces the backward of
  * Fsp.implicit_gemm (call site bug_fix/conv.py:442-447; spconv-2.x differentiates through
  * pair_bwd / mask_argsort_bwd_splits, bug_fix/conv.py:382-415).  Arithmetic as the vendored
@@ -243,8 +266,9 @@ typedef struct msmd_conv_layer {
   int subm;                 /* 1 = SubMConv3d, 0 = SparseConv3d */
   int ksize[3], stride[3], padding[3], dilation[3];
   int cin, cout;
-  const float* weight;      /* device: msmd_spconv_tc_pack_weight image if weight_tc, else msmd_spconv_pack_weight */
-  int weight_tc;
+  const float* weight;      /* device: packed image selected by weight_tc */
+  int weight_tc;            /* 0: msmd_spconv_pack_weight (fp32 FFMA kernel); 1: msmd_spconv_tc_pack_weight (3xTF32);
+                             * 2: msmd_spconv_tc16_pack_weight x3=1 (bf16x3); 3: msmd_spconv_tc16_pack_weight x3=0 (bf16) */
   const float* scale;       /* device (cout) or NULL: folded BatchNorm1d(eval) */
   const float* shift;
   int relu;

@@ -59,6 +59,9 @@ SIGNATURES = {
     'msmd_spconv_fwd_tc': (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _vp]),
     'msmd_spconv_tc_workspace': (_sz, [_i, _i]),
     'msmd_spconv_fwd_tc_ws': (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _sz, _vp]),
+    'msmd_spconv_tc16_packed_bytes': (_sz, [_i, _i, _i, _i]),
+    'msmd_spconv_tc16_pack_weight': (_i, [_vp, _i, _i, _i, _i, _vp, _vp]),
+    'msmd_spconv_fwd_tc16': (_i, [_vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _vp]),
     'msmd_rulebook_mask_sort_workspace': (_sz, [_i]),
     'msmd_rulebook_mask_sort': (_i, [_vp, _i, _i, _vp, _vp, _vp, _sz, _vp]),
     'msmd_spconv_fwd_tc_sorted': (_i, [_vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _vp,

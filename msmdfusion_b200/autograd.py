@@ -26,6 +26,7 @@ class SparseConvFunction(torch.autograd.Function):
         out = ops.spconv_fwd(features, packed, rb['pair_fwd'])
         ctx.save_for_backward(features, weight)
         ctx.rb = rb
+        ctx.tc_mode = packed.mode if isinstance(packed, ops.TcWeight) else 0   # dgrad runs in the forward's precision
         return out
 
     @staticmethod
@@ -37,8 +38,11 @@ class SparseConvFunction(torch.autograd.Function):
         cout, cin = weight.shape[0], weight.shape[-1]
         kvol = int(math.prod(weight.shape[1:-1]))
         if ctx.needs_input_grad[0]:
-            use_tc = rb.get('path', 'tc') == 'tc' and ops.tc_supported(cin, kvol, cout)
-            pack = ops.pack_weight_tc if use_tc else ops.pack_weight
+            use_tc = ctx.tc_mode != 0 and rb.get('path', 'tc') == 'tc' and ops.tc_supported(cin, kvol, cout)
+            mode = ctx.tc_mode
+
+            def pack(w):
+                return ops.pack_weight_tc(w, mode) if use_tc else ops.pack_weight(w)
             if rb['subm']:
                 # o reads i through offset k  <=>  i reads o through offset K-1-k: pair_fwd itself is
                 # the transposed rulebook once the weight's offsets are reversed

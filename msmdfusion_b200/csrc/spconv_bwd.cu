@@ -251,6 +251,9 @@ extern "C" MSMD_API int msmd_spconv_bwd_data(const float* grad_out, int n_out, c
                                              int cout, int kvol, float* grad_in, void* workspace,
                                              size_t workspace_bytes, msmd_stream_t stream) {
   // forward contraction with the channel roles swapped: "cin" = cout, "cout" = cin
+  if (weight_tc == 2 || weight_tc == 3)  // bf16x3 / bf16 image (csrc/spconv_tc16.cu)
+    return msmd_spconv_fwd_tc16(grad_out, n_out, packed_wt, pair_bwd, nullptr, n_in, cout, cin, kvol,
+                                weight_tc == 2, nullptr, nullptr, nullptr, 0, grad_in, stream);
   if (weight_tc)
     return msmd_spconv_fwd_tc_ws(grad_out, n_out, packed_wt, pair_bwd, n_in, cout, cin, kvol, nullptr,
                                  nullptr, nullptr, 0, grad_in, workspace, workspace_bytes, stream);

@@ -1,0 +1,346 @@
+// spconv_tc16.cu -- sparse convolution forward on tcgen05 with 16-bit (bf16) operands.
+//
+// Same implicit GEMM as spconv_tc.cu (D[128 output voxels, Cout] = A[gathered rows, K] * B[Cout, K]^T,
+// K = (kernel offset, input channel), fp32 accumulator in tensor memory, fused BN / residual / ReLU
+// epilogue), with tcgen05.mma.kind::f16 on bf16 operands -- twice the tensor rate of kind::tf32 and twice
+// the K elements per 128-byte shared-memory row, so a K chunk is 64 elements and a tile runs HALF the
+// pipeline steps of the tf32 kernel.  Two modes (msmd_conv_layer.weight_tc / the `x3` argument):
+//
+//   bf16      one MMA per product.  Operands rounded to bf16 (2^-9 relative): the train-step arithmetic
+//             of BASELINE configs[4] ("bf16 sparse-conv kernels", fp32 accumulate, fp32 master weights);
+//             NOT within the 1e-4 inference parity bound.
+//   bf16 x3   x = hi + lo with hi = bf16(x), lo = bf16(x - hi) (16 significand bits kept);
+//             D += A_lo*B_hi + A_hi*B_lo + A_hi*B_hi, the lo*lo term (2^-18) dropped: ~5e-6 relative per
+//             layer (tests/test_oracle.py::test_bf16x3_accuracy_model), i.e. inside the parity bound at
+//             half the tensor-pipe time of 3xTF32.  Opt-in until measured on hardware.
+//
+// Features stay fp32 in HBM: the gather warps load float4 pieces exactly like the tf32 kernel (32 K
+// elements per step, kT16Depth steps in flight per thread), convert to bf16 in registers and fill one
+// half of the 128-byte row per step, so the register budget is the tf32 kernel's.  The operand layout in
+// shared memory is the K-major SWIZZLE_128B canonical layout the tf32 kernel uses (same descriptors; only
+// the instruction descriptor's operand format and K = 16 per MMA differ).
+//
+// Status: written without GPU time.  Checked on the host model of tcgen05 (tests/tools/cuda_emul/tc_emul.h,
+// calibrated on the GPU-verified tf32 kernels): tests/test_cuda_emul.py::test_tc16_*.  GPU tests:
+// tests/test_zz_train_gpu.py::test_tc16_*.
+#include "tc_common.cuh"
+
+namespace msmd {
+
+constexpr int kT16KC = 64;                 // bf16 K elements per chunk = one 128-byte swizzle row
+constexpr int kT16Step = 32;               // K elements per gather step (one float4 per thread and row)
+constexpr int kT16ABytes = kTcM * 128;     // 16 KB per A image (hi or lo)
+constexpr int kT16Depth = 3;               // gather steps whose loads are in flight per thread
+
+struct T16Layout {
+  int stage_bytes, stages, pair_off, act_off, bar_off, total;
+};
+
+static T16Layout t16_layout(int N, int kvol, int chunks, int tiles, int images) {
+  T16Layout L;
+  L.stage_bytes = images * (kT16ABytes + N * 128);  // A hi [| A lo] | B hi [| B lo], all 1024-B aligned
+  const int misc = round_up(kvol * kTcM * 4, 16) + round_up(2 * chunks, 16) + 256 + 8 * N;
+  const int half = 112 * 1024, full = 224 * 1024;
+  if (2 * L.stage_bytes + misc + 1024 <= half && tiles > kNumSMs)
+    L.stages = (half - misc - 1024) / L.stage_bytes;   // two CTAs per SM
+  else
+    L.stages = (full - misc - 1024) / L.stage_bytes;
+  if (L.stages > 4) L.stages = 4;
+  L.pair_off = L.stages * L.stage_bytes;
+  L.act_off = L.pair_off + round_up(kvol * kTcM * 4, 16);
+  L.bar_off = L.act_off + round_up(2 * chunks, 16);
+  L.total = L.bar_off + 256 + 8 * N + 1024;
+  return L;
+}
+
+template <bool VEC, bool X3>
+__global__ void __launch_bounds__(kTcThreads)
+spconv_fwd_tc16_kernel(const float* __restrict__ feat, const uint16_t* __restrict__ wpk,
+                       const int* __restrict__ pair, int n_out, int cin, int cin_pad, int cout, int N,
+                       int kvol, int chunks, int stages, int stage_bytes, int pair_off, int act_off,
+                       int bar_off, int tmem_cols, const float* __restrict__ scale,
+                       const float* __restrict__ shift, const float* __restrict__ residual, int relu,
+                       float* __restrict__ out, int cat, const int* __restrict__ row_perm) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  int* pair_s = (int*)(smem + pair_off);
+  unsigned short* alist = (unsigned short*)(smem + act_off);
+  uint64_t* full_bar = (uint64_t*)(smem + bar_off);
+  uint64_t* empty_bar = full_bar + 4;
+  uint64_t* accum_bar = full_bar + 8;
+  uint32_t* tmem_ptr_s = (uint32_t*)(full_bar + 9);
+  int* n_act_s = (int*)(full_bar + 9) + 1;
+  int* used_s = (int*)(full_bar + 10);  // [kvol <= 32]
+  float* ss = (float*)(smem + bar_off + 256);  // folded BatchNorm scale[N] | shift[N]
+  for (int c = threadIdx.x; c < N; c += kTcThreads) {
+    ss[c] = (scale && c < cout) ? __ldg(scale + c) : 1.f;
+    ss[N + c] = (shift && c < cout) ? __ldg(shift + c) : 0.f;
+  }
+  constexpr int kImages = X3 ? 2 : 1;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int row0 = blockIdx.x * kTcM;
+
+  if (tid == 0) {
+    for (int s = 0; s < stages; ++s) {
+      tc::mbar_init(&full_bar[s], kTcProducerWarps + 1);  // one arrive per gather warp + the B copy's expect_tx
+      tc::mbar_init(&empty_bar[s], 1);                    // one tcgen05.commit
+    }
+    tc::mbar_init(accum_bar, 1);
+    tc::fence_mbar_init();
+  }
+  if (warp == kTcProducerWarps + 1) {
+    tc::tmem_alloc(tmem_ptr_s, (uint32_t)tmem_cols);
+    tc::tmem_relinquish();
+  }
+  for (int k = warp; k < kvol; k += kTcThreads / 32) {
+    bool any = false;
+#pragma unroll
+    for (int q = 0; q < kTcM / 32; ++q) {
+      const int r = lane + 32 * q;
+      const int o = row0 + r;
+      const int p = (o < n_out) ? __ldg(pair + (size_t)k * n_out + o) : -1;
+      pair_s[k * kTcM + r] = p;
+      any |= p >= 0;
+    }
+    const unsigned b = __ballot_sync(0xffffffffu, any);
+    if (lane == 0) used_s[k] = b != 0;
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  if (warp == 0) tc_build_active_list(used_s, chunks, cin_pad, kvol, lane, alist, n_act_s, kT16KC);
+  __syncthreads();
+  const int n_act = *n_act_s;
+  const int any_active = n_act > 0;
+  const uint32_t tmem_base = *tmem_ptr_s;
+
+  if (warp < kTcProducerWarps) {
+    // ===== A producers: gather (fp32) -> bf16 [hi | lo] -> swizzled store ======================
+    // A chunk is filled in two gather steps of 32 K elements; in a step thread (p, rbase) owns
+    // the float4 piece p of rows rbase + 32*i, i.e. 8 bytes of the bf16 row: the lower (p even)
+    // or upper (p odd) half of the 16-byte swizzle unit  4*h + p/2  of the row.
+    const int p = tid & 7;
+    const int rbase = tid >> 3;  // 0..31
+    constexpr int RPT = kTcM / (kTcProducers / 8);  // rows per thread = 4
+    auto gather = [&](int t, float4 (&v)[RPT]) {   // t = gather step: chunk alist[t / 2], half t % 2
+      const int kk0 = ((int)alist[t >> 1] * 2 + (t & 1)) * kT16Step + p * 4;
+      const int k = kk0 / cin_pad;
+      const int c = kk0 - k * cin_pad;
+      const bool kvalid = k < kvol;
+#pragma unroll
+      for (int i = 0; i < RPT; ++i) {
+        const int r = rbase + 32 * i;
+        const int idx = kvalid ? pair_s[k * kTcM + r] : -1;
+        v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (idx >= 0) {
+          const float* src = feat + (size_t)idx * cin + c;
+          if (VEC) {
+            v[i] = __ldg((const float4*)src);
+          } else {
+            if (c + 0 < cin) v[i].x = __ldg(src + 0);
+            if (c + 1 < cin) v[i].y = __ldg(src + 1);
+            if (c + 2 < cin) v[i].z = __ldg(src + 2);
+            if (c + 3 < cin) v[i].w = __ldg(src + 3);
+          }
+        }
+      }
+    };
+    auto store = [&](int t, const float4 (&v)[RPT]) {
+      const int it = t >> 1, h = t & 1;
+      const int s = it % stages;
+      if (h == 0) mbar_wait_warp(&empty_bar[s], ((uint32_t)(it / stages) & 1u) ^ 1u, lane);
+      const uint32_t a_hi = tc::smem_u32(smem + (size_t)s * stage_bytes);
+      const uint32_t a_lo = a_hi + kT16ABytes;
+      const int unit = 4 * h + (p >> 1);
+#pragma unroll
+      for (int i = 0; i < RPT; ++i) {
+        const int r = rbase + 32 * i;
+        const uint32_t off = (uint32_t)(r * 128 + ((unit ^ (r & 7)) << 4) + ((p & 1) << 3));
+        const uint32_t h01 = tc::pack_bf16x2(v[i].x, v[i].y), h23 = tc::pack_bf16x2(v[i].z, v[i].w);
+        tc::st_shared_v2_b32(a_hi + off, h01, h23);
+        if (X3) {
+          const float lx = v[i].x - __uint_as_float(h01 << 16), ly = v[i].y - __uint_as_float(h01 & 0xFFFF0000u);
+          const float lz = v[i].z - __uint_as_float(h23 << 16), lw = v[i].w - __uint_as_float(h23 & 0xFFFF0000u);
+          tc::st_shared_v2_b32(a_lo + off, tc::pack_bf16x2(lx, ly), tc::pack_bf16x2(lz, lw));
+        }
+      }
+      if (h == 1) {  // the chunk is complete
+        tc::fence_proxy_async();  // every lane: its generic-proxy stores -> async proxy
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(&full_bar[s]);
+      }
+    };
+    const int n_steps = 2 * n_act;
+    float4 buf[kT16Depth][RPT];
+#pragma unroll
+    for (int d = 0; d < kT16Depth; ++d)
+      if (d < n_steps) gather(d, buf[d]);
+    for (int i = 0; i < n_steps; i += kT16Depth) {
+#pragma unroll
+      for (int d = 0; d < kT16Depth; ++d) {
+        if (i + d < n_steps) {
+          store(i + d, buf[d]);
+          if (i + d + kT16Depth < n_steps) gather(i + d + kT16Depth, buf[d]);
+        }
+      }
+    }
+
+    tc_epilogue(any_active, accum_bar, tmem_base, warp, lane, row0, n_out, cout, N, ss, residual, relu, out,
+                nullptr, nullptr, (X3 && cat) ? N : 0, row_perm);
+  } else if (warp == kTcProducerWarps) {
+    // ===== B loader: one bulk copy (hi [+ lo] image of the chunk) per active chunk ==============
+    if (lane == 0) {
+      const uint32_t bytes = (uint32_t)(kImages * N * 128);
+      for (int it = 0; it < n_act; ++it) {
+        const int j = alist[it];
+        const int s = it % stages;
+        const uint32_t ph = (uint32_t)(it / stages) & 1u;
+        tc::mbar_wait(&empty_bar[s], ph ^ 1u);
+        tc::mbar_arrive_expect_tx(&full_bar[s], bytes);
+        tc::bulk_g2s(smem + (size_t)s * stage_bytes + kImages * kT16ABytes,
+                     (const uint8_t*)wpk + (size_t)j * bytes, bytes, &full_bar[s]);
+      }
+    }
+  } else {
+    // ===== MMA issuer ===========================================================================
+    if (lane == 0) {
+      const uint32_t idesc = tc::idesc_f32acc(tc::kFmtBF16, kTcM, N);
+      const uint32_t idesc2 = tc::idesc_f32acc(tc::kFmtBF16, kTcM, 2 * N);
+      uint32_t accumulate = 0;
+      for (int it = 0; it < n_act; ++it) {
+        const int s = it % stages;
+        const uint32_t ph = (uint32_t)(it / stages) & 1u;
+        tc::mbar_wait(&full_bar[s], ph);
+        tc::fence_after_sync();
+        const uint32_t a_hi = tc::smem_u32(smem + (size_t)s * stage_bytes);
+        const uint32_t a_lo = a_hi + kT16ABytes;
+        const uint32_t b_hi = a_hi + kImages * kT16ABytes;
+        const uint32_t b_lo = b_hi + (uint32_t)N * 128u;
+#pragma unroll
+        for (int ks = 0; ks < kT16KC / 16; ++ks) {
+          const uint32_t koff = (uint32_t)ks * 32u;  // 16 bf16 = 32 bytes along K
+          const uint64_t dah = tc::desc_k_sw128(a_hi + koff), dbh = tc::desc_k_sw128(b_hi + koff);
+          if (!X3) {
+            tc::mma_f16(tmem_base, dah, dbh, idesc, accumulate);
+          } else {
+            const uint64_t dal = tc::desc_k_sw128(a_lo + koff), dbl = tc::desc_k_sw128(b_lo + koff);
+            if (cat) {
+              // B_hi and B_lo are adjacent in the stage = ONE K-major operand of 2N rows:
+              //   D[:, 0:2N] += A_hi * [B_hi; B_lo]      D[:, 0:N] += A_lo * B_hi
+              tc::mma_f16(tmem_base, dah, dbh, idesc2, accumulate);
+              tc::mma_f16(tmem_base, dal, dbh, idesc, 1u);
+            } else {
+              tc::mma_f16(tmem_base, dal, dbh, idesc, accumulate);  // small terms first
+              tc::mma_f16(tmem_base, dah, dbl, idesc, 1u);
+              tc::mma_f16(tmem_base, dah, dbh, idesc, 1u);
+            }
+          }
+          accumulate = 1u;
+        }
+        tc::mma_commit(&empty_bar[s]);  // frees the stage once these MMAs have read it
+      }
+      if (n_act > 0) tc::mma_commit(accum_bar);  // accumulator complete -> epilogue
+    }
+  }
+
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == kTcProducerWarps + 1) tc::tmem_dealloc(tmem_base, (uint32_t)tmem_cols);
+}
+
+// Packed weight image: [chunk j][image: hi (, lo)][n < N][64 bf16, 16-byte units swizzled by (n & 7)].
+__global__ void __launch_bounds__(256)
+tc16_pack_weight_kernel(const float* __restrict__ w, int cout, int kvol, int cin, int cin_pad, int N,
+                        int chunks, int images, uint16_t* __restrict__ packed) {
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t total = (size_t)chunks * N * kT16KC;
+  if (t >= total) return;
+  const int kk = (int)(t % kT16KC);
+  const int n = (int)((t / kT16KC) % N);
+  const int j = (int)(t / ((size_t)kT16KC * N));
+  const int K = j * kT16KC + kk;
+  const int k = K / cin_pad, c = K - k * cin_pad;
+  float val = 0.f;
+  if (k < kvol && c < cin && n < cout) val = w[((size_t)n * kvol + k) * cin + c];
+  const uint32_t hi = tc::pack_bf16x2(val, 0.f) & 0xFFFFu;
+  const size_t blk = (size_t)N * kT16KC;
+  const size_t off = (size_t)n * kT16KC + (size_t)((((kk >> 3) ^ (n & 7)) << 3) + (kk & 7));
+  packed[((size_t)j * images + 0) * blk + off] = (uint16_t)hi;
+  if (images == 2) {
+    const float lo = val - __uint_as_float(hi << 16);
+    packed[((size_t)j * images + 1) * blk + off] = (uint16_t)(tc::pack_bf16x2(lo, 0.f) & 0xFFFFu);
+  }
+}
+
+struct T16Geom {
+  int cin_pad, N, chunks;
+};
+static bool t16_geom(int cout, int kvol, int cin, T16Geom& g) {
+  if (cout < 1 || cout > 256 || kvol < 1 || kvol > 32 || cin < 1) return false;
+  g.cin_pad = round_up(cin, 4);
+  g.N = round_up(cout, 16);
+  g.chunks = ((long long)kvol * g.cin_pad + kT16KC - 1) / kT16KC;
+  return true;
+}
+
+}  // namespace msmd
+
+using namespace msmd;
+
+extern "C" MSMD_API size_t msmd_spconv_tc16_packed_bytes(int cout, int kvol, int cin, int x3) {
+  T16Geom g;
+  if (!t16_geom(cout, kvol, cin, g)) return 0;
+  return (size_t)g.chunks * (x3 ? 2 : 1) * g.N * kT16KC * sizeof(uint16_t);
+}
+
+extern "C" MSMD_API int msmd_spconv_tc16_pack_weight(const float* weight_krsc, int cout, int kvol, int cin,
+                                                     int x3, void* packed, msmd_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  T16Geom g;
+  MSMD_REQUIRE(t16_geom(cout, kvol, cin, g), "spconv_tc16: unsupported shape (cout<=256, kvol<=32)");
+  MSMD_REQUIRE(weight_krsc && packed, "spconv_tc16_pack_weight: null pointer");
+  MSMD_REQUIRE(((uintptr_t)packed & 15) == 0, "spconv_tc16_pack_weight: packed must be 16-byte aligned");
+  const size_t total = (size_t)g.chunks * g.N * kT16KC;
+  tc16_pack_weight_kernel<<<ceil_div((long long)total, 256), 256, 0, stream>>>(
+      weight_krsc, cout, kvol, cin, g.cin_pad, g.N, g.chunks, x3 ? 2 : 1, (uint16_t*)packed);
+  MSMD_LAUNCH_OK();
+  return MSMD_OK;
+}
+
+extern "C" MSMD_API int msmd_spconv_fwd_tc16(const float* features, int n_in, const void* packed_tc16,
+                                             const int* pair_fwd, const int* row_perm, int n_out, int cin,
+                                             int cout, int kvol, int x3, const float* scale,
+                                             const float* shift, const float* residual, int relu, float* out,
+                                             msmd_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  T16Geom g;
+  MSMD_REQUIRE(t16_geom(cout, kvol, cin, g), "spconv_fwd_tc16: unsupported shape (cout<=256, kvol<=32)");
+  MSMD_REQUIRE(n_in >= 0 && n_out >= 0, "spconv_fwd_tc16: bad sizes");
+  MSMD_REQUIRE((scale == nullptr) == (shift == nullptr), "spconv_fwd_tc16: scale/shift must come together");
+  if (n_out == 0) return MSMD_OK;
+  MSMD_REQUIRE(features && packed_tc16 && pair_fwd && out, "spconv_fwd_tc16: null pointer");
+  MSMD_REQUIRE(((uintptr_t)packed_tc16 & 15) == 0, "spconv_fwd_tc16: packed weights must be 16-byte aligned");
+  const bool vec = (cin % 4 == 0) && (((uintptr_t)features & 15) == 0);
+  const int tiles = ceil_div(n_out, kTcM);
+  const int images = x3 ? 2 : 1;
+  const T16Layout L = t16_layout(g.N, kvol, g.chunks, tiles, images);
+  MSMD_REQUIRE(L.stages >= 2, "spconv_fwd_tc16: tile does not fit in shared memory");
+  auto kern = x3 ? (vec ? spconv_fwd_tc16_kernel<true, true> : spconv_fwd_tc16_kernel<false, true>)
+                 : (vec ? spconv_fwd_tc16_kernel<true, false> : spconv_fwd_tc16_kernel<false, false>);
+  static bool attr_set[4] = {false, false, false, false};
+  if (!attr_set[2 * (x3 ? 1 : 0) + vec]) {
+    MSMD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set[2 * (x3 ? 1 : 0) + vec] = true;
+  }
+  // concatenated-B mode (x3 only) needs 2N accumulator columns; two co-resident CTAs must fit in 512
+  const int cat = (x3 && 2 * g.N <= 256) ? 1 : 0;
+  int tmem_cols = 32;
+  while (tmem_cols < (cat ? 2 * g.N : g.N)) tmem_cols <<= 1;
+  kern<<<tiles, kTcThreads, L.total, stream>>>(features, (const uint16_t*)packed_tc16, pair_fwd, n_out, cin,
+                                               g.cin_pad, cout, g.N, kvol, g.chunks, L.stages, L.stage_bytes,
+                                               L.pair_off, L.act_off, L.bar_off, tmem_cols, scale, shift,
+                                               residual, relu, out, cat, row_perm);
+  MSMD_LAUNCH_OK();
+  return MSMD_OK;
+}

@@ -51,7 +51,7 @@ class SparseNetPlan:
         self.keep += [wt, scale, shift]
         self.layers.append(dict(subm=int(conv.subm), ksize=conv.kernel_size, stride=conv.stride,
                                 padding=conv.padding, dilation=conv.dilation, cin=conv.in_channels,
-                                cout=conv.out_channels, weight=wt, weight_tc=int(tcw), scale=scale,
+                                cout=conv.out_channels, weight=wt, weight_tc=(w.mode if tcw else 0), scale=scale,
                                 shift=shift, relu=int(relu), input=cur, residual=residual))
         return len(self.layers)  # activation index of this layer's output
 
@@ -141,7 +141,7 @@ class SparseNetPlan:
 
 def plan_key(modules):
     """Changes whenever a parameter / buffer the plan baked in is replaced or modified in place."""
-    key = [spconv.CONV_PATH]
+    key = [spconv.CONV_PATH, spconv.CONV_PRECISION]
     for m in modules:
         for t in list(m.parameters()) + list(m.buffers()):
             key.append((t.data_ptr(), t._version))

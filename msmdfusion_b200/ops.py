@@ -197,12 +197,17 @@ def pack_weight(weight):
 
 
 class TcWeight:
-    """Weight packed for the tensor-core path (csrc/spconv_tc.cu)."""
+    """Weight packed for the tensor-core path.  ``mode`` = the value of ``msmd_conv_layer.weight_tc``:
+    1 = tf32 hi/lo image (csrc/spconv_tc.cu, 3xTF32), 2 = bf16 hi/lo image (csrc/spconv_tc16.cu, bf16x3),
+    3 = bf16 image (one MMA per product: the train-step arithmetic of BASELINE configs[4])."""
 
-    __slots__ = ('packed', 'cout', 'kvol', 'cin')
+    __slots__ = ('packed', 'cout', 'kvol', 'cin', 'mode')
 
-    def __init__(self, packed, cout, kvol, cin):
-        self.packed, self.cout, self.kvol, self.cin = packed, cout, kvol, cin
+    def __init__(self, packed, cout, kvol, cin, mode=1):
+        self.packed, self.cout, self.kvol, self.cin, self.mode = packed, cout, kvol, cin, int(mode)
+
+
+TC_MODES = {'tf32x3': 1, 'bf16x3': 2, 'bf16': 3}
 
 
 def set_mask_sort(enable):
@@ -219,20 +224,31 @@ def tc_supported(cout, kvol, cin):
     return bool(lib().msmd_spconv_tc_supported(int(cout), int(kvol), int(cin)))
 
 
-def pack_weight_tc(weight):
-    """KRSC [Cout,kz,ky,kx,Cin] parameter -> swizzled tf32 hi/lo K-chunk image."""
+def pack_weight_tc(weight, mode=1):
+    """KRSC [Cout,kz,ky,kx,Cin] parameter -> swizzled K-chunk image of the tensor-core kernels: tf32 hi/lo
+    (mode 1), bf16 hi/lo (mode 2) or bf16 (mode 3)."""
     w = weight.detach()
     if w.dtype != torch.float32:
         w = w.float()
     w = w.contiguous()
     cout, cin = w.shape[0], w.shape[-1]
     kvol = w.numel() // (cout * cin)
-    n = lib().msmd_spconv_tc_packed_floats(cout, kvol, cin)
-    assert n > 0, 'shape not supported by the tensor-core path'
-    packed = torch.empty((n,), dtype=torch.float32, device=w.device)
-    check(lib().msmd_spconv_tc_pack_weight(ptr(w), cout, kvol, cin, ptr(packed), stream(w.device)),
-          'msmd_spconv_tc_pack_weight')
-    return TcWeight(packed, cout, kvol, cin)
+    mode = int(mode)
+    assert mode in (1, 2, 3)
+    if mode == 1:
+        n = lib().msmd_spconv_tc_packed_floats(cout, kvol, cin)
+        assert n > 0, 'shape not supported by the tensor-core path'
+        packed = torch.empty((n,), dtype=torch.float32, device=w.device)
+        check(lib().msmd_spconv_tc_pack_weight(ptr(w), cout, kvol, cin, ptr(packed), stream(w.device)),
+              'msmd_spconv_tc_pack_weight')
+    else:
+        x3 = int(mode == 2)
+        n = lib().msmd_spconv_tc16_packed_bytes(cout, kvol, cin, x3)
+        assert n > 0, 'shape not supported by the tensor-core path'
+        packed = torch.empty((n // 2,), dtype=torch.int16, device=w.device)   # raw bf16 bit patterns
+        check(lib().msmd_spconv_tc16_pack_weight(ptr(w), cout, kvol, cin, x3, ptr(packed), stream(w.device)),
+              'msmd_spconv_tc16_pack_weight')
+    return TcWeight(packed, cout, kvol, cin, mode)
 
 
 def rulebook_mask_sort(pair_fwd):
@@ -253,7 +269,8 @@ def rulebook_mask_sort(pair_fwd):
 
 
 def spconv_fwd_tc(features, tcw, pair_fwd, scale=None, shift=None, residual=None, relu=False, row_perm=None):
-    """Sparse conv forward on tcgen05 tensor cores (3xTF32, fp32 accumulate in TMEM).  With
+    """Sparse conv forward on tcgen05 tensor cores (3xTF32 / bf16x3 / bf16 by ``tcw.mode``, fp32
+    accumulate in TMEM).  With
     ``row_perm`` the table is a mask-sorted one (``rulebook_mask_sort``); the output keeps the original
     row order."""
     features = features.contiguous()
@@ -268,11 +285,20 @@ def spconv_fwd_tc(features, tcw, pair_fwd, scale=None, shift=None, residual=None
         assert residual.shape == out.shape
     pair_fwd = pair_fwd.contiguous()
     with _Timed('spconv_fwd', n_in=features.shape[0], n_out=n_out, cin=tcw.cin, cout=tcw.cout,
-                kvol=tcw.kvol, residual=residual is not None, pair=pair_fwd, path='tc'):
+                kvol=tcw.kvol, residual=residual is not None, pair=pair_fwd, path='tc', tc_mode=tcw.mode):
+        if row_perm is not None:
+            assert row_perm.dtype == torch.int32 and row_perm.shape[0] == n_out
+            row_perm = row_perm.contiguous()
+        if tcw.mode != 1:   # 16-bit operand kernels (bf16x3 / bf16)
+            check(lib().msmd_spconv_fwd_tc16(ptr(features), features.shape[0], ptr(tcw.packed), ptr(pair_fwd),
+                                             ptr(row_perm), n_out, tcw.cin, tcw.cout, tcw.kvol,
+                                             int(tcw.mode == 2), ptr(scale), ptr(shift), ptr(residual),
+                                             int(bool(relu)), ptr(out), stream(features.device)),
+                  'msmd_spconv_fwd_tc16')
+            return out
         need = lib().msmd_spconv_tc_workspace(n_out, tcw.cout)  # > 0: split-K pairs (tail balance)
         ws = scratch.get(features.device, need, slot='tc_ws') if need else None
         if row_perm is not None:
-            assert row_perm.dtype == torch.int32 and row_perm.shape[0] == n_out
             check(lib().msmd_spconv_fwd_tc_sorted(ptr(features), features.shape[0], ptr(tcw.packed),
                                                   ptr(pair_fwd), ptr(row_perm.contiguous()), n_out, tcw.cin,
                                                   tcw.cout, tcw.kvol, ptr(scale), ptr(shift), ptr(residual),
@@ -365,7 +391,7 @@ def spconv_bwd_data(grad_out, packed_wt, pair_bwd):
     pair_bwd = pair_bwd.contiguous()
     n_in = pair_bwd.shape[1]
     if isinstance(packed_wt, TcWeight):
-        cin, cout, kvol, tc, wbuf = packed_wt.cout, packed_wt.cin, packed_wt.kvol, 1, packed_wt.packed
+        cin, cout, kvol, tc, wbuf = packed_wt.cout, packed_wt.cin, packed_wt.kvol, packed_wt.mode, packed_wt.packed
     else:
         kvol, cout, cin = packed_wt.shape
         tc, wbuf = 0, packed_wt
@@ -373,7 +399,7 @@ def spconv_bwd_data(grad_out, packed_wt, pair_bwd):
     grad_in = torch.empty((n_in, cin), dtype=torch.float32, device=grad_out.device)
     with _Timed('spconv_bwd_data', n_in=n_in, n_out=grad_out.shape[0], cin=cin, cout=cout, kvol=kvol,
                 pair=pair_bwd, path='tc' if tc else 'simt'):
-        need = lib().msmd_spconv_tc_workspace(n_in, cin) if tc else 0
+        need = lib().msmd_spconv_tc_workspace(n_in, cin) if tc == 1 else 0
         ws = scratch.get(grad_out.device, need, slot='tc_ws') if need else None
         check(lib().msmd_spconv_bwd_data(ptr(grad_out), grad_out.shape[0], ptr(wbuf), tc, ptr(pair_bwd),
                                          n_in, cin, cout, kvol, ptr(grad_in), ptr(ws),

@@ -31,6 +31,11 @@ from .registry import CONV_LAYERS
 
 # contraction kernel: 'tc' (tcgen05, 3xTF32) or 'simt' (exact fp32 FFMA); MSMD_CONV_PATH overrides
 CONV_PATH = os.environ.get('MSMD_CONV_PATH', 'tc')
+# operand precision of the tensor-core path: 'tf32x3' (default: 3xTF32, ~1e-6 of fp32), 'bf16x3' (bf16 hi/lo
+# split, ~5e-6 per layer, half the tensor-pipe time; opt-in until measured) or 'bf16' (operands rounded to
+# bf16: the train-step arithmetic BASELINE configs[4] names -- outside the inference parity bound).
+# MSMD_CONV_PRECISION overrides; train.VoxelSpaceTrainStep(precision=...) sets it for a train step.
+CONV_PRECISION = os.environ.get('MSMD_CONV_PRECISION', 'tf32x3')
 # opt-in: mask-sorted tiles for the 3x3x3 SubM layers of the tensor-core path (spconv-2.x
 # mask_argsort_fwd_splits); MSMD_MASK_SORT=1 also switches it on inside the native executor
 MASK_SORT = os.environ.get('MSMD_MASK_SORT', '0') not in ('', '0')
@@ -381,9 +386,10 @@ class SparseConvolution(SparseModule):
         w = self.weight
         kvol = int(math.prod(self.kernel_size))
         use_tc = CONV_PATH == 'tc' and ops.tc_supported(self.out_channels, kvol, self.in_channels)
-        key = (w.data_ptr(), w._version, w.device, use_tc)
+        mode = ops.TC_MODES[CONV_PRECISION] if use_tc else 0
+        key = (w.data_ptr(), w._version, w.device, mode)
         if self._packed is None or self._packed_key != key:
-            self._packed = ops.pack_weight_tc(w) if use_tc else ops.pack_weight(w)
+            self._packed = ops.pack_weight_tc(w, mode) if use_tc else ops.pack_weight(w)
             self._packed_key = key
         return self._packed
 

@@ -68,7 +68,11 @@ class FlatGradients:
 class VoxelSpaceTrainStep:
     """forward (train mode) -> loss -> backward -> gradient all-reduce -> clip -> AdamW."""
 
-    def __init__(self, detector, loss_fn, lr=1e-4, weight_decay=0.01, grad_clip=10.0):
+    def __init__(self, detector, loss_fn, lr=1e-4, weight_decay=0.01, grad_clip=10.0, precision=None):
+        # precision: operand precision of the sparse convolutions during the step ('tf32x3' | 'bf16x3' | 'bf16',
+        # spconv.CONV_PRECISION); None keeps the process-wide setting.  'bf16' is what BASELINE configs[4] names:
+        # bf16 operands on the tensor cores, fp32 accumulation, fp32 master weights and optimiser state.
+        self.precision = precision
         detector.train()                       # batch-statistics BatchNorm, max_voxels[0] (voxelize.py:103-114)
         self.det = freeze_lidar_components(detector)
         self.loss_fn = loss_fn
@@ -93,13 +97,20 @@ class VoxelSpaceTrainStep:
         return self.loss_fn(bev)
 
     def __call__(self, points, img_feats, img_metas):
+        from . import spconv
         if self.grads is not None:
             self.grads.zero()
-        loss = self.forward_loss(points, img_feats, img_metas)
-        if self.grads is None:
-            self._probe(loss)
-        else:
-            loss.backward()
+        saved = spconv.CONV_PRECISION
+        if self.precision:
+            spconv.CONV_PRECISION = self.precision
+        try:
+            loss = self.forward_loss(points, img_feats, img_metas)
+            if self.grads is None:
+                self._probe(loss)
+            else:
+                loss.backward()
+        finally:
+            spconv.CONV_PRECISION = saved
         self.grads.all_reduce_mean()
         self.grads.clip_(self.grad_clip)
         self.opt.step()

@@ -47,6 +47,7 @@ def tc_emu():
         _TC.emu_last_error.restype = ctypes.c_char_p
         _TC.emu_msmd_spconv_tc_packed_floats.restype = ctypes.c_size_t
         _TC.emu_msmd_spconv_tc_workspace.restype = ctypes.c_size_t
+        _TC.emu_msmd_spconv_tc16_packed_bytes.restype = ctypes.c_size_t
     return _TC
 
 
@@ -492,3 +493,81 @@ def test_mask_sorted_tc_path_on_emulator(cin, cout, variant, split):
     # per-row accumulation order is the kernel-offset order in both cases; only chunk skipping differs
     assert rel(got, plain) < 5e-6
     assert (c1 - c0) < (c2 - c1)   # fewer MMAs issued: the reason for the sort
+
+
+# --------------------------------------------------------------------------------------
+# 16-bit operand kernels (csrc/spconv_tc16.cu: bf16 / bf16x3) -- not yet run on hardware
+# --------------------------------------------------------------------------------------
+def bf16_round(x):
+    u = np.ascontiguousarray(x, np.float32).view(np.uint32).astype(np.uint64)
+    u = (u + 0x7FFF + ((u >> 16) & 1)) & 0xFFFF0000
+    return u.astype(np.uint32).view(np.float32).reshape(np.shape(x))
+
+
+def tc16_fwd(feat, w, pair, x3, scale=None, shift=None, residual=None, relu=0, row_perm=None):
+    L = tc_emu()
+    cout, cin = w.shape[0], w.shape[-1]
+    kvol, n_out = pair.shape
+    packed = np.full(L.emu_msmd_spconv_tc16_packed_bytes(cout, kvol, cin, x3) // 2, 0x7FC0, np.uint16)  # NaN fill
+    assert L.emu_msmd_spconv_tc16_pack_weight(P(w), cout, kvol, cin, x3, P(packed), None) == 0, L.emu_last_error()
+    out = np.full((n_out, cout), np.nan, np.float32)
+    st = L.emu_msmd_spconv_fwd_tc16(P(feat), feat.shape[0], P(packed), P(pair), P(row_perm), n_out, cin, cout, kvol,
+                                    x3, P(scale), P(shift), P(residual), relu, P(out), None)
+    assert st == 0, L.emu_last_error()
+    return out
+
+
+@pytest.mark.parametrize('x3', [0, 1])
+@pytest.mark.parametrize('cin,cout,n', [(16, 16, 300),    # four kernel offsets per 64-element chunk, vector gather
+                                        (5, 16, 200),     # scalar gather, eight offsets per chunk
+                                        (20, 144, 150),   # piece straddling cin (cin % 8 == 4), padded N, 3-MMA x3 mode
+                                        (64, 128, 140)])  # one offset per chunk, concatenated-B x3 mode at 2N = 256
+def test_tc16_kernels_on_emulator(x3, cin, cout, n):
+    """bf16: equals the convolution of the bf16-ROUNDED operands (fp32 accumulate) -- the rounding is the
+    only difference from the fp32 path.  bf16x3: within 2e-5 of the fp32 oracle (hi/lo split, lo*lo
+    dropped).  Fused epilogue on both."""
+    shape = [5, 12, 12]
+    idx, feat = random_sparse(0, 1, shape, n, cin)
+    rng = np.random.default_rng(1)
+    w = (rng.standard_normal((cout, 3, 3, 3, cin)) * 0.2).astype(np.float32)
+    pair = cpu.subm_rulebook(idx, shape, 3, 1)
+    if x3:
+        ref, tol = cpu.spconv_fwd(feat, w, pair), 2e-5
+    else:
+        ref, tol = cpu.spconv_fwd(bf16_round(feat), bf16_round(w), pair), 2e-6
+    assert rel(tc16_fwd(feat, w, pair, x3), ref) < tol
+    scale = rng.uniform(0.5, 1.5, cout).astype(np.float32)
+    shift = rng.standard_normal(cout).astype(np.float32)
+    res = rng.standard_normal(ref.shape).astype(np.float32)
+    got = tc16_fwd(feat, w, pair, x3, scale, shift, res, 1)
+    assert rel(got, np.maximum(ref * scale + shift + res, 0)) < tol
+    if not x3:   # and it IS a different arithmetic from fp32: the parity bound does not hold
+        assert rel(tc16_fwd(feat, w, pair, 0), cpu.spconv_fwd(feat, w, pair)) > 1e-4
+
+
+def test_tc16_strided_rulebook_mask_sorted_and_empty_tiles_on_emulator():
+    shape = [7, 14, 14]
+    idx, feat = random_sparse(5, 1, shape, 400, 16)
+    rng = np.random.default_rng(6)
+    w = (rng.standard_normal((32, 3, 3, 3, 16)) * 0.2).astype(np.float32)
+    _, pair, _ = cpu.conv_rulebook(idx, shape, (3, 3, 3), 2, 1, 1)
+    assert rel(tc16_fwd(feat, w, pair, 1), cpu.spconv_fwd(feat, w, pair)) < 2e-5
+    # mask-sorted SubM table through the slot -> row map
+    pair = cpu.subm_rulebook(idx, shape, 3, 1)
+    n = pair.shape[1]
+    L = emu()
+    L.emu_msmd_rulebook_mask_sort_workspace.restype = ctypes.c_size_t
+    need = L.emu_msmd_rulebook_mask_sort_workspace(n)
+    ws, perm, pair_sorted = np.zeros(need, np.uint8), np.full(n, -1, np.int32), np.full_like(pair, -9)
+    ok(L.emu_msmd_rulebook_mask_sort(P(pair), 27, n, P(perm), P(pair_sorted), P(ws), ctypes.c_size_t(need), None))
+    res = rng.standard_normal((n, 32)).astype(np.float32)
+    one = np.ones(32, np.float32)
+    for x3 in (0, 1):
+        plain = tc16_fwd(feat, w, pair, x3, one, 0 * one, res, 1)
+        assert np.array_equal(tc16_fwd(feat, w, pair_sorted, x3, one, 0 * one, res, 1, row_perm=perm), plain)
+    # a tile without any pair: rows = shift
+    empty = np.full((27, 140), -1, np.int32)
+    empty[13, 130] = 7
+    shift = rng.standard_normal(32).astype(np.float32)
+    got = tc16_fwd(feat, w, empty, 0, one, shift)
+    assert rel(got, cpu.spconv_fwd(bf16_round(feat), bf16_round(w), empty) + shift) < 2e-6

@@ -294,3 +294,89 @@ def test_executor_with_mask_sort_equals_default():
     assert err(s1, s0) < 1e-5
     for (i0, x0), (i1, x1) in zip(f0, f1):
         assert torch.equal(i0, i1) and err(x1, x0) < 1e-5
+
+
+# --------------------------------------------------------------------------------------
+# 16-bit operand kernels (csrc/spconv_tc16.cu; opt-in: MSMD_CONV_PRECISION / --precision)
+# --------------------------------------------------------------------------------------
+def bf16_round(x):
+    return x.to(torch.bfloat16).to(torch.float32)
+
+
+@pytest.mark.parametrize('mode', ['bf16', 'bf16x3'])
+@pytest.mark.parametrize('cin,cout,subm', [(16, 16, True), (5, 16, True), (64, 64, True), (128, 128, True),
+                                            (80, 96, False), (192, 192, True)])
+def test_tc16_conv_matches_oracle(mode, cin, cout, subm):
+    """msmd_spconv_fwd_tc16 against the CPU oracle.  bf16: the oracle convolves the bf16-rounded operands
+    (the kernel's only deviation from fp32; fp32 accumulation order differs -> 1e-5).  bf16x3: the plain
+    fp32 oracle at 2e-5.  Fused epilogue included."""
+    shape, batch = [9, 24, 24], 2
+    idx, feat = random_sparse(cin + cout, batch, shape, 1500, cin)
+    rng = np.random.default_rng(1)
+    w = (rng.standard_normal((cout, 3, 3, 3, cin)) / np.sqrt(cin * 27 * 0.2)).astype(np.float32)
+    if subm:
+        pair = cpu.subm_rulebook(idx, shape, 3, 1)
+    else:
+        _, pair, _ = cpu.conv_rulebook(idx, shape, 3, 2, 1, 1)
+    tcw = ops.pack_weight_tc(cuda(w), ops.TC_MODES[mode])
+    assert tcw.mode == ops.TC_MODES[mode]
+    if mode == 'bf16':
+        ref = cpu.spconv_fwd(bf16_round(torch.from_numpy(feat)).numpy(), bf16_round(torch.from_numpy(w)).numpy(), pair)
+        tol = 1e-5
+    else:
+        ref, tol = cpu.spconv_fwd(feat, w, pair), 2e-5
+    got = ops.spconv_fwd_tc(cuda(feat), tcw, cuda(pair))
+    assert err(got, ref) < tol
+    scale = rng.uniform(0.5, 1.5, cout).astype(np.float32)
+    shift = rng.standard_normal(cout).astype(np.float32)
+    res = rng.standard_normal(ref.shape).astype(np.float32)
+    got = ops.spconv_fwd_tc(cuda(feat), tcw, cuda(pair), cuda(scale), cuda(shift), cuda(res), True)
+    assert err(got, np.maximum(ref * scale + shift + res, 0)) < tol
+
+
+def test_tc16_bf16x3_sparse_encoder_within_parity_bound():
+    """The whole LiDAR SparseEncoder (21 layers, native executor) in the bf16x3 mode against the default
+    3xTF32 mode: inside the path's 1e-4 bound (CPU model: tests/test_oracle.py::test_bf16x3_accuracy_model)."""
+    from msmdfusion_b200 import registry
+    cfg = m.Config.fromfile(os.path.join(ROOT, 'configs', 'msmd_lc_hotpath.py')).hotpath
+    torch.manual_seed(0)
+    enc = registry.build_middle_encoder(cfg.pts_middle_encoder).to(dev()).eval()
+    layer = m.Voxelization(**cfg.pts_voxel_layer).eval()
+    outs = {}
+    try:
+        for prec in ('tf32x3', 'bf16x3'):
+            m.spconv.CONV_PRECISION = prec
+            with torch.no_grad():
+                mean, coors, _ = layer.forward_mean(cuda(synthetic.lidar_scene(seed=5, sweeps=1)), 5, batch_idx=0)
+                spatial, feats = enc(mean, coors, 1)
+            torch.cuda.synchronize()
+            outs[prec] = (spatial.clone(), [f.features.clone() for f in feats])
+    finally:
+        m.spconv.CONV_PRECISION = 'tf32x3'
+    assert err(outs['bf16x3'][0], outs['tf32x3'][0]) < TOL
+    for a, b in zip(outs['bf16x3'][1], outs['tf32x3'][1]):
+        assert err(a, b) < TOL
+
+
+def test_tc16_bf16_backward_matches_rounded_operand_autograd():
+    """Train-step arithmetic (precision 'bf16'): forward and data gradient run the bf16 kernel, the weight
+    gradient stays exact fp32.  Reference: float64 autograd of the same convolution on bf16-rounded
+    operands for the output / data gradient (1e-5 .. 3e-3: the data gradient also rounds grad_out)."""
+    shape, batch, cin, cout = [9, 24, 24], 1, 64, 80
+    idx, feat = random_sparse(3, batch, shape, 1200, cin)
+    conv = m.spconv.SubMConv3d(cin, cout, 3, padding=1, bias=False, indice_key='k').to(dev())
+    x = m.spconv.SparseConvTensor(cuda(feat).requires_grad_(True), cuda(idx), shape, batch)
+    pair = cpu.subm_rulebook(idx, shape, 3, 1)
+    go = np.random.default_rng(4).standard_normal((idx.shape[0], cout)).astype(np.float32)
+    try:
+        m.spconv.CONV_PRECISION = 'bf16'
+        y = conv(x)
+        y.features.backward(cuda(go))
+    finally:
+        m.spconv.CONV_PRECISION = 'tf32x3'
+    w = conv.weight.detach().cpu().numpy()
+    ref_y = cpu.spconv_fwd(bf16_round(torch.from_numpy(feat)).numpy(), bf16_round(torch.from_numpy(w)).numpy(), pair)
+    assert err(y.features, ref_y) < 1e-5
+    gi, gw = cpu.spconv_bwd(feat, w, pair, go)
+    assert err(x.features.grad, gi) < 1e-2     # bf16 operands (grad_out and W^T rounded): 2^-9 per operand
+    assert err(conv.weight.grad, gw) < TOL     # exact-fp32 wgrad on the fp32 features

@@ -111,6 +111,8 @@ extern "C" const char* emu_last_error() { return ::emu::g_error; }
 STUBS_BWD = '''
 extern "C" int msmd_spconv_fwd_tc_ws(const float*, int, const float*, const int*, int, int, int, int, const float*,
                                      const float*, const float*, int, float*, void*, size_t, msmd_stream_t) { return -100; }
+extern "C" int msmd_spconv_fwd_tc16(const float*, int, const void*, const int*, const int*, int, int, int, int, int,
+                                    const float*, const float*, const float*, int, float*, msmd_stream_t) { return -100; }
 extern "C" int msmd_spconv_fwd(const float*, int, const float*, const int*, int, int, int, int, const float*,
                                const float*, const float*, int, float*, msmd_stream_t);
 extern "C" size_t msmd_grid_num_words(int batch_size, const int* s) {   // as csrc/rulebook.cu
@@ -163,17 +165,17 @@ def build_tc(verbose=False):
     """Host-emulated copy of csrc/spconv_tc.cu (tcgen05 / TMEM / bulk-copy kernels) over tc_emul.h."""
     os.makedirs(OUT, exist_ok=True)
     lib = os.path.join(OUT, 'libmsmd_tc_emul.so')
-    deps = [os.path.join(CSRC, f) for f in ('common.cuh', 'spconv_tc.cu')] + \
+    deps = [os.path.join(CSRC, f) for f in ('common.cuh', 'tc_common.cuh', 'spconv_tc.cu', 'spconv_tc16.cu')] + \
         [os.path.join(HERE, 'cuda_emul.h'), os.path.join(HERE, 'tc_emul.h'), os.path.abspath(__file__)]
     if os.path.exists(lib) and all(os.path.getmtime(lib) > os.path.getmtime(d) for d in deps):
         return lib
     _INLINED.clear()
     _INLINED.add('tc.cuh')   # replaced by tc_emul.h
-    unit = translate('spconv_tc.cu')
+    unit = translate('spconv_tc.cu') + translate('spconv_tc16.cu')   # tc_common.cuh is inlined once
     _INLINED.clear()
     # dynamic shared memory: the window tc_emul.h hands out (deliberately 16-byte aligned only)
     unit, n = re.subn(r'extern __shared__ uint8_t (\w+)\[\];', r'uint8_t* \1 = ::emu::g_dyn_smem;', unit)
-    assert n >= 1
+    assert n >= 3
     fwd_decl = '''
 extern "C" int emu_msmd_spconv_fwd_tc_ws(const float*, int, const float*, const int*, int, int, int, int, const float*,
                                          const float*, const float*, int, float*, void*, size_t, msmd_stream_t);

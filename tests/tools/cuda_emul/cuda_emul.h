@@ -67,34 +67,46 @@ extern void (*g_block_end)();
 
 template <typename F>
 void launch(dim3 grid, dim3 block, size_t dyn_smem_bytes, F body) {
+  // The CTA's threads are created ONCE per launch and walk the grid together (thread blocks run one after
+  // another): two launch-level barriers per CTA instead of nthreads thread creations.
   const unsigned nthreads = block.x * block.y * block.z;
+  const unsigned nblocks = grid.x * grid.y * grid.z;
+  if (nthreads == 0 || nblocks == 0) return;
   g_blockDim = block;
   g_gridDim = grid;
-  for (unsigned bz = 0; bz < grid.z; ++bz)
-    for (unsigned by = 0; by < grid.y; ++by)
-      for (unsigned bx = 0; bx < grid.x; ++bx) {
-        std::barrier<> bar(nthreads);
-        g_block_barrier = &bar;
-        if (g_block_begin) g_block_begin((uint32_t)dyn_smem_bytes);
-        g_warps.clear();
-        g_warps.resize((nthreads + 31) / 32);
-        for (unsigned w = 0; w < g_warps.size(); ++w) {
-          const unsigned lanes = std::min(32u, nthreads - w * 32);
-          g_warps[w].bar.reset(new std::barrier<>(lanes));
+  std::barrier<> cta_done(nthreads), cta_ready(nthreads);
+  std::unique_ptr<std::barrier<>> bar;
+  auto begin_cta = [&]() {
+    bar.reset(new std::barrier<>(nthreads));
+    g_block_barrier = bar.get();
+    if (g_block_begin) g_block_begin((uint32_t)dyn_smem_bytes);
+    g_warps.clear();
+    g_warps.resize((nthreads + 31) / 32);
+    for (unsigned w = 0; w < g_warps.size(); ++w) {
+      const unsigned lanes = std::min(32u, nthreads - w * 32);
+      g_warps[w].bar.reset(new std::barrier<>(lanes));
+    }
+  };
+  begin_cta();
+  std::vector<std::thread> ts;
+  ts.reserve(nthreads);
+  for (unsigned t = 0; t < nthreads; ++t)
+    ts.emplace_back([&, t]() {
+      t_threadIdx = dim3(t % block.x, (t / block.x) % block.y, t / (block.x * block.y));
+      for (unsigned b = 0; b < nblocks; ++b) {
+        t_blockIdx = dim3(b % grid.x, (b / grid.x) % grid.y, b / (grid.x * grid.y));
+        body();
+        g_block_barrier->arrive_and_drop();            // exited threads leave the CTA's barriers
+        g_warps[t / 32].bar->arrive_and_drop();
+        cta_done.arrive_and_wait();
+        if (t == 0) {                                  // everyone else is parked between the two barriers
+          if (g_block_end) g_block_end();
+          if (b + 1 < nblocks) begin_cta();
         }
-        std::vector<std::thread> ts;
-        ts.reserve(nthreads);
-        for (unsigned t = 0; t < nthreads; ++t)
-          ts.emplace_back([=]() {
-            t_threadIdx = dim3(t % block.x, (t / block.x) % block.y, t / (block.x * block.y));
-            t_blockIdx = dim3(bx, by, bz);
-            body();
-            g_block_barrier->arrive_and_drop();            // exited threads leave the barriers
-            g_warps[t / 32].bar->arrive_and_drop();
-          });
-        for (auto& th : ts) th.join();
-        if (g_block_end) g_block_end();
+        cta_ready.arrive_and_wait();
       }
+    });
+  for (auto& th : ts) th.join();
 }
 template <typename F>
 void launch(dim3 grid, dim3 block, F body) { launch(grid, block, 0, body); }

@@ -384,6 +384,11 @@ static inline void st_shared_v4(uint32_t addr, float a, float b, float c, float 
   const float v[4] = {a, b, c, d};
   memcpy(::emu::smem_ptr(addr, 16), v, 16);
 }
+static inline void st_shared_v2_b32(uint32_t addr, uint32_t a, uint32_t b) {
+  if (addr & 7) ::emu::tc_fail("st.shared.v2 at %u is not 8-byte aligned", addr);
+  const uint32_t v[2] = {a, b};
+  memcpy(::emu::smem_ptr(addr, 8), v, 8);
+}
 static inline void st_shared_v4_b32(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   if (addr & 15) ::emu::tc_fail("st.shared.v4 at %u is not 16-byte aligned", addr);
   const uint32_t v[4] = {a, b, c, d};
