@@ -11,6 +11,8 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, '_C', 'libmsmd_b200.so')
+if os.environ.get('MSMD_LIB'):   # debug builds of the same ABI (tools/tc_trace.py: the -DMSMD_TC_TRACE build)
+    LIB_PATH = os.environ['MSMD_LIB']
 
 _c_int_p = ctypes.POINTER(ctypes.c_int)
 _c_float_p = ctypes.POINTER(ctypes.c_float)

@@ -36,6 +36,23 @@ def needs_build():
     return any(os.path.getmtime(f) > t for f in _deps())
 
 
+TRACE_LIB = os.path.join(OUT_DIR, 'libmsmd_b200_trace.so')
+
+
+def build_trace(verbose=False):
+    """Debug build with the per-role timeline of the tensor-core kernels compiled in (csrc/tc_trace.cuh,
+    -DMSMD_TC_TRACE); used only by tools/tc_trace.py through MSMD_LIB.  The product library never carries it."""
+    global LIB, OUT_DIR
+    saved = (LIB, OUT_DIR)
+    try:
+        LIB, OUT_DIR = TRACE_LIB, os.path.join(saved[1], 'trace')
+        os.makedirs(OUT_DIR, exist_ok=True)
+        return build(force=not os.path.exists(TRACE_LIB) or needs_build(), verbose=verbose,
+                     extra_flags=['-DMSMD_TC_TRACE'])
+    finally:
+        LIB, OUT_DIR = saved
+
+
 def build(force=False, verbose=False, extra_flags=()):
     if not force and not needs_build():
         return LIB
@@ -66,5 +83,8 @@ def build(force=False, verbose=False, extra_flags=()):
 
 
 if __name__ == '__main__':
+    if '--trace' in sys.argv:
+        print(build_trace(verbose=True))
+        sys.exit(0)
     print(build(force='--force' in sys.argv, verbose=True,
                 extra_flags=['-Xptxas', '-v'] if '--ptxas' in sys.argv else ()))

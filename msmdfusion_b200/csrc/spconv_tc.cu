@@ -30,6 +30,7 @@
 //   variant 3 (spconv_fwd_tc3)   A hi/lo staged in TENSOR MEMORY (tcgen05.st), B only in shared
 //                                memory, optional split-K CTA pairs for tail balance
 #include "tc_common.cuh"
+#include "tc_trace.cuh"
 
 namespace msmd {
 
@@ -83,6 +84,8 @@ spconv_fwd_tc_kernel(const float* __restrict__ feat, const float* __restrict__ w
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int row0 = blockIdx.x * kTcM;
+  TC_TRACE_INIT();
+  TC_TRACE_ENTRY();
 
   // ---- one-time setup -------------------------------------------------------------------
   if (tid == 0) {
@@ -119,6 +122,7 @@ spconv_fwd_tc_kernel(const float* __restrict__ feat, const float* __restrict__ w
   const int n_act = *n_act_s;
   const int any_active = n_act > 0;
   const uint32_t tmem_base = *tmem_ptr_s;
+  if (tid == 0) { TC_TRACE_HEAD(1, clock64()); TC_TRACE_HEAD(7, n_act); }
 
   if (warp < kTcProducerWarps) {
     // ===== A producers: gather + tf32 hi/lo split + swizzled store ==========================
@@ -152,10 +156,14 @@ spconv_fwd_tc_kernel(const float* __restrict__ feat, const float* __restrict__ w
       }
     };
     int it = 0;
+    const int tr_role = warp == 0 ? 0 : (warp == kTcProducerWarps - 1 ? 1 : -1);  // traced gather warps
+    (void)tr_role;
     auto store = [&](const float4 (&v)[RPT]) {
       const int s = it % stages;
       const uint32_t ph = (uint32_t)(it / stages) & 1u;
+      if (lane == 0) TC_TRACE(tr_role, it, 0);
       mbar_wait_warp(&empty_bar[s], ph ^ 1u, lane);
+      if (lane == 0) TC_TRACE(tr_role, it, 1);
       const uint32_t a_hi = tc::smem_u32(smem + (size_t)s * stage_bytes);
       const uint32_t a_lo = a_hi + kTcABytes;
 #pragma unroll
@@ -170,6 +178,7 @@ spconv_fwd_tc_kernel(const float* __restrict__ feat, const float* __restrict__ w
       tc::fence_proxy_async();  // every lane: its generic-proxy stores -> async proxy
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(&full_bar[s]);  // one arrival per warp (256 -> 8 smem atomics)
+      if (lane == 0) TC_TRACE(tr_role, it, 2);
       ++it;
     };
     // kTcDepth register buffers rotated without copies: while one chunk is split and stored, the
@@ -189,8 +198,10 @@ spconv_fwd_tc_kernel(const float* __restrict__ feat, const float* __restrict__ w
     }
 
     // ===== epilogue: TMEM -> registers -> fused BN / residual / ReLU -> global =============
+    if (tid == 0) TC_TRACE_HEAD(2, clock64());
     tc_epilogue(any_active, accum_bar, tmem_base, warp, lane, row0, n_out, cout, N, ss, residual, relu, out,
                 nullptr, nullptr, cat ? N : 0, row_perm);
+    if (tid == 0) TC_TRACE_HEAD(4, clock64());
   } else if (warp == kTcProducerWarps) {
     // ===== B loader: one bulk copy (hi + lo image of the chunk) per active chunk ============
     if (lane == 0) {
@@ -199,7 +210,9 @@ spconv_fwd_tc_kernel(const float* __restrict__ feat, const float* __restrict__ w
         const int j = alist[it];
         const int s = it % stages;
         const uint32_t ph = (uint32_t)(it / stages) & 1u;
+        TC_TRACE(2, it, 0);
         tc::mbar_wait(&empty_bar[s], ph ^ 1u);
+        TC_TRACE(2, it, 1);
         tc::mbar_arrive_expect_tx(&full_bar[s], bytes);
         tc::bulk_g2s(smem + (size_t)s * stage_bytes + 2 * kTcABytes,
                      wpk + (size_t)j * N * kTcKC * 2, bytes, &full_bar[s]);
@@ -214,7 +227,9 @@ spconv_fwd_tc_kernel(const float* __restrict__ feat, const float* __restrict__ w
       for (int it = 0; it < n_act; ++it) {
         const int s = it % stages;
         const uint32_t ph = (uint32_t)(it / stages) & 1u;
+        TC_TRACE(3, it, 0);
         tc::mbar_wait(&full_bar[s], ph);
+        TC_TRACE(3, it, 1);
         tc::fence_after_sync();
         const uint32_t a_hi = tc::smem_u32(smem + (size_t)s * stage_bytes);
         const uint32_t a_lo = a_hi + kTcABytes;
@@ -240,6 +255,7 @@ spconv_fwd_tc_kernel(const float* __restrict__ feat, const float* __restrict__ w
           accumulate = 1u;
         }
         tc::mma_commit(&empty_bar[s]);  // frees the stage once these MMAs have read it
+        TC_TRACE(3, it, 2);
       }
       if (n_act > 0) tc::mma_commit(accum_bar);  // accumulator complete -> epilogue
     }
@@ -248,6 +264,7 @@ spconv_fwd_tc_kernel(const float* __restrict__ feat, const float* __restrict__ w
   // ---- teardown -------------------------------------------------------------------------
   tc::fence_before_sync();
   __syncthreads();
+  TC_TRACE_EXIT();
   if (warp == kTcProducerWarps + 1) tc::tmem_dealloc(tmem_base, (uint32_t)tmem_cols);
 }
 
@@ -323,6 +340,8 @@ spconv_fwd_tc3_kernel(const float* __restrict__ feat, const float* __restrict__ 
   // active K chunks each; the first to finish hands its partial sums to the second through L2
   const int tile = (int)blockIdx.x / split, half = (int)blockIdx.x % split;
   const int row0 = tile * kTcM;
+  TC_TRACE_INIT();
+  TC_TRACE_ENTRY();
 
   if (tid == 0) {
     for (int s = 0; s < 4; ++s) {
@@ -365,6 +384,7 @@ spconv_fwd_tc3_kernel(const float* __restrict__ feat, const float* __restrict__ 
   const int any_active = n_act > 0;
   const uint32_t tmem_base = *tmem_ptr_s;
   const uint32_t tmem_a0 = tmem_base + (uint32_t)N;  // A ring starts right after the accumulator
+  if (tid == 0) { TC_TRACE_HEAD(1, clock64()); TC_TRACE_HEAD(7, n_act); }
 
   if (warp < kTcProducerWarps) {
     // ===== gather (coalesced) -> raw smem -> row-per-thread read -> split -> tcgen05.st =====
@@ -400,6 +420,8 @@ spconv_fwd_tc3_kernel(const float* __restrict__ feat, const float* __restrict__ 
     const int chalf = warp >> 2;  // K columns [16*chalf, +16)
     const uint32_t raw0 = tc::smem_u32(smem + raw_off);
     int it = 0;
+    const int tr_role = warp == 0 ? 0 : (warp == kTcProducerWarps - 1 ? 1 : -1);  // traced gather warps
+    (void)tr_role;
     auto convert = [&](const float4 (&v)[RPT]) {
       const uint32_t raw = raw0 + (uint32_t)(it & 1) * kTcABytes;
       // 1. coalesced-layout registers -> swizzled raw tile (one pass, conflict-free)
@@ -425,7 +447,9 @@ spconv_fwd_tc3_kernel(const float* __restrict__ feat, const float* __restrict__ 
       // 3. TMEM A stage free?  store hi | lo, make it visible to the MMA issuer
       const int sa = it % a_stages;
       const uint32_t ph = (uint32_t)(it / a_stages) & 1u;
+      if (lane == 0) TC_TRACE(tr_role, it, 0);
       mbar_wait_warp(&a_empty[sa], ph ^ 1u, lane);
+      if (lane == 0) TC_TRACE(tr_role, it, 1);
       tc::fence_after_sync();
       const uint32_t ta = tmem_a0 + (uint32_t)(sa * 64) + ((uint32_t)((warp & 3) * 32) << 16);
       tc::tmem_st16(ta + (uint32_t)(16 * chalf), hi);
@@ -434,6 +458,7 @@ spconv_fwd_tc3_kernel(const float* __restrict__ feat, const float* __restrict__ 
       tc::fence_before_sync();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(&a_full[sa]);
+      if (lane == 0) TC_TRACE(tr_role, it, 2);
       ++it;
     };
     float4 bufa[RPT], bufb[RPT];
@@ -447,9 +472,11 @@ spconv_fwd_tc3_kernel(const float* __restrict__ feat, const float* __restrict__ 
       if (i + 3 < n_act) gather(alist[i + 3], bufb);
     }
 
+    if (tid == 0) TC_TRACE_HEAD(2, clock64());
     if (split == 1) {
       tc_epilogue(any_active, accum_bar, tmem_base, warp, lane, row0, n_out, cout, N, ss, residual, relu, out,
                   nullptr, nullptr, 0, row_perm);
+      if (tid == 0) TC_TRACE_HEAD(4, clock64());
     } else {
       int* ticket_s = n_act_s;  // the active-chunk count is no longer needed: reuse its smem word
       float* part = part_ws + (size_t)tile * kTcM * N;
@@ -485,7 +512,9 @@ spconv_fwd_tc3_kernel(const float* __restrict__ feat, const float* __restrict__ 
         const int j = alist[it];
         const int s = it % b_stages;
         const uint32_t ph = (uint32_t)(it / b_stages) & 1u;
+        TC_TRACE(2, it, 0);
         tc::mbar_wait(&b_empty[s], ph ^ 1u);
+        TC_TRACE(2, it, 1);
         tc::mbar_arrive_expect_tx(&b_full[s], bytes);
         tc::bulk_g2s(smem + (size_t)s * b_stage_bytes, wpk + (size_t)j * N * kTcKC * 2, bytes, &b_full[s]);
       }
@@ -497,8 +526,11 @@ spconv_fwd_tc3_kernel(const float* __restrict__ feat, const float* __restrict__ 
       uint32_t accumulate = 0;
       for (int it = 0; it < n_act; ++it) {
         const int sb = it % b_stages, sa = it % a_stages;
+        TC_TRACE(3, it, 0);
         tc::mbar_wait(&b_full[sb], (uint32_t)(it / b_stages) & 1u);
+        TC_TRACE(3, it, 3);   // weights in; now the A operand
         tc::mbar_wait(&a_full[sa], (uint32_t)(it / a_stages) & 1u);
+        TC_TRACE(3, it, 1);
         tc::fence_after_sync();
         const uint32_t b_hi = tc::smem_u32(smem + (size_t)sb * b_stage_bytes);
         const uint32_t b_lo = b_hi + (uint32_t)N * kTcKC * 4u;
@@ -515,6 +547,7 @@ spconv_fwd_tc3_kernel(const float* __restrict__ feat, const float* __restrict__ 
         }
         tc::mma_commit(&b_empty[sb]);
         tc::mma_commit(&a_empty[sa]);
+        TC_TRACE(3, it, 2);
       }
       if (n_act > 0) tc::mma_commit(accum_bar);
     }
@@ -522,6 +555,7 @@ spconv_fwd_tc3_kernel(const float* __restrict__ feat, const float* __restrict__ 
 
   tc::fence_before_sync();
   __syncthreads();
+  TC_TRACE_EXIT();
   if (warp == kTcProducerWarps + 1) tc::tmem_dealloc(tmem_base, (uint32_t)tmem_cols);
 }
 
@@ -563,6 +597,11 @@ static bool tc_geom(int cout, int kvol, int cin, TcGeom& g) {
 }  // namespace msmd
 
 using namespace msmd;
+
+#ifdef MSMD_TC_TRACE
+extern "C" MSMD_API int msmd_tc_trace_set(unsigned long long* buf) { return tc_trace_set_impl(buf); }
+extern "C" MSMD_API int msmd_tc_trace_record_words(void) { return kTrRecord; }
+#endif
 
 static int g_tc_variant = 0;  // 0: auto (by N); 2: A through shared memory; 3: A through tensor memory
 

@@ -24,6 +24,7 @@
 // calibrated on the GPU-verified tf32 kernels): tests/test_cuda_emul.py::test_tc16_*.  GPU tests:
 // tests/test_zz_train_gpu.py::test_tc16_*.
 #include "tc_common.cuh"
+#include "tc_trace.cuh"
 
 namespace msmd {
 
@@ -80,6 +81,8 @@ spconv_fwd_tc16_kernel(const float* __restrict__ feat, const uint16_t* __restric
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int row0 = blockIdx.x * kTcM;
+  TC_TRACE_INIT();
+  TC_TRACE_ENTRY();
 
   if (tid == 0) {
     for (int s = 0; s < stages; ++s) {
@@ -114,6 +117,7 @@ spconv_fwd_tc16_kernel(const float* __restrict__ feat, const uint16_t* __restric
   const int n_act = *n_act_s;
   const int any_active = n_act > 0;
   const uint32_t tmem_base = *tmem_ptr_s;
+  if (tid == 0) { TC_TRACE_HEAD(1, clock64()); TC_TRACE_HEAD(7, n_act); }
 
   if (warp < kTcProducerWarps) {
     // ===== A producers: gather (fp32) -> bf16 [hi | lo] -> swizzled store ======================
@@ -146,10 +150,16 @@ spconv_fwd_tc16_kernel(const float* __restrict__ feat, const uint16_t* __restric
         }
       }
     };
+    const int tr_role = warp == 0 ? 0 : (warp == kTcProducerWarps - 1 ? 1 : -1);  // traced gather warps
+    (void)tr_role;
     auto store = [&](int t, const float4 (&v)[RPT]) {
       const int it = t >> 1, h = t & 1;
       const int s = it % stages;
-      if (h == 0) mbar_wait_warp(&empty_bar[s], ((uint32_t)(it / stages) & 1u) ^ 1u, lane);
+      if (h == 0) {
+        if (lane == 0) TC_TRACE(tr_role, it, 0);
+        mbar_wait_warp(&empty_bar[s], ((uint32_t)(it / stages) & 1u) ^ 1u, lane);
+        if (lane == 0) TC_TRACE(tr_role, it, 1);
+      }
       const uint32_t a_hi = tc::smem_u32(smem + (size_t)s * stage_bytes);
       const uint32_t a_lo = a_hi + kT16ABytes;
       const int unit = 4 * h + (p >> 1);
@@ -169,6 +179,7 @@ spconv_fwd_tc16_kernel(const float* __restrict__ feat, const uint16_t* __restric
         tc::fence_proxy_async();  // every lane: its generic-proxy stores -> async proxy
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(&full_bar[s]);
+        if (lane == 0) TC_TRACE(tr_role, it, 2);
       }
     };
     const int n_steps = 2 * n_act;
@@ -186,8 +197,10 @@ spconv_fwd_tc16_kernel(const float* __restrict__ feat, const uint16_t* __restric
       }
     }
 
+    if (tid == 0) TC_TRACE_HEAD(2, clock64());
     tc_epilogue(any_active, accum_bar, tmem_base, warp, lane, row0, n_out, cout, N, ss, residual, relu, out,
                 nullptr, nullptr, (X3 && cat) ? N : 0, row_perm);
+    if (tid == 0) TC_TRACE_HEAD(4, clock64());
   } else if (warp == kTcProducerWarps) {
     // ===== B loader: one bulk copy (hi [+ lo] image of the chunk) per active chunk ==============
     if (lane == 0) {
@@ -196,7 +209,9 @@ spconv_fwd_tc16_kernel(const float* __restrict__ feat, const uint16_t* __restric
         const int j = alist[it];
         const int s = it % stages;
         const uint32_t ph = (uint32_t)(it / stages) & 1u;
+        TC_TRACE(2, it, 0);
         tc::mbar_wait(&empty_bar[s], ph ^ 1u);
+        TC_TRACE(2, it, 1);
         tc::mbar_arrive_expect_tx(&full_bar[s], bytes);
         tc::bulk_g2s(smem + (size_t)s * stage_bytes + kImages * kT16ABytes,
                      (const uint8_t*)wpk + (size_t)j * bytes, bytes, &full_bar[s]);
@@ -211,7 +226,9 @@ spconv_fwd_tc16_kernel(const float* __restrict__ feat, const uint16_t* __restric
       for (int it = 0; it < n_act; ++it) {
         const int s = it % stages;
         const uint32_t ph = (uint32_t)(it / stages) & 1u;
+        TC_TRACE(3, it, 0);
         tc::mbar_wait(&full_bar[s], ph);
+        TC_TRACE(3, it, 1);
         tc::fence_after_sync();
         const uint32_t a_hi = tc::smem_u32(smem + (size_t)s * stage_bytes);
         const uint32_t a_lo = a_hi + kT16ABytes;
@@ -239,6 +256,7 @@ spconv_fwd_tc16_kernel(const float* __restrict__ feat, const uint16_t* __restric
           accumulate = 1u;
         }
         tc::mma_commit(&empty_bar[s]);  // frees the stage once these MMAs have read it
+        TC_TRACE(3, it, 2);
       }
       if (n_act > 0) tc::mma_commit(accum_bar);  // accumulator complete -> epilogue
     }
@@ -246,6 +264,7 @@ spconv_fwd_tc16_kernel(const float* __restrict__ feat, const uint16_t* __restric
 
   tc::fence_before_sync();
   __syncthreads();
+  TC_TRACE_EXIT();
   if (warp == kTcProducerWarps + 1) tc::tmem_dealloc(tmem_base, (uint32_t)tmem_cols);
 }
 
@@ -287,6 +306,10 @@ static bool t16_geom(int cout, int kvol, int cin, T16Geom& g) {
 }  // namespace msmd
 
 using namespace msmd;
+
+#ifdef MSMD_TC_TRACE
+extern "C" MSMD_API int msmd_tc16_trace_set(unsigned long long* buf) { return tc_trace_set_impl(buf); }
+#endif
 
 extern "C" MSMD_API size_t msmd_spconv_tc16_packed_bytes(int cout, int kvol, int cin, int x3) {
   T16Geom g;

@@ -204,3 +204,31 @@ def test_bench_reference_arm_prints_the_contract_line():
                             capture_output=True, text=True, timeout=120, env=dict(env, RANK='1', WORLD_SIZE='2'),
                             cwd=ROOT)
     assert silent.returncode == 0 and silent.stdout.strip() == ''
+
+
+def test_tc_trace_summary_on_fabricated_record():
+    """tools/tc_trace.py (GPU debug tool): the record layout of csrc/tc_trace.cuh and the per-chunk
+    period / wait-share arithmetic, on a fabricated timeline (2000 cycles per chunk at 2000 MHz)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location('tc_trace', os.path.join(ROOT, 'tools', 'tc_trace.py'))
+    T = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(T)
+    src = open(os.path.join(ROOT, 'msmdfusion_b200', 'csrc', 'tc_trace.cuh')).read()
+    assert 'kTrCtas = %d, kTrRoles = %d, kTrIts = %d, kTrPhases = %d, kTrHead = %d' % (
+        T.CTAS, T.ROLES, T.ITS, T.PHASES, T.HEAD) in src
+    words = T.HEAD + T.ROLES * T.ITS * T.PHASES
+    rec = np.zeros((T.CTAS, words), np.uint64)
+    r = rec[3]
+    r[0], r[1], r[2], r[4], r[5], r[6], r[7], r[8], r[9], r[10] = 1000, 3000, 23000, 25000, 26000, 5, 10, 42, 10**6, 10**6 + 14000
+    ev = r[T.HEAD:].reshape(T.ROLES, T.ITS, T.PHASES)
+    for it in range(10):
+        t0 = 3000 + 2000 * it
+        ev[0, it] = [t0, t0 + 200, t0 + 900, 0]
+        ev[1, it] = [t0, t0 + 300, t0 + 950, 0]
+        ev[2, it] = [t0, t0 + 100, 0, 0]
+        ev[3, it] = [t0 + 500, t0 + 1500, t0 + 1800, 0]
+    (d,) = T.summarize(rec, 2000.0)
+    assert d['cta'] == 42 and d['n_act'] == 10 and abs(d['period_us'] - 1.0) < 1e-9
+    assert abs(d['mma_wait'] - 0.5) < 1e-9 and abs(d['prod0_wait'] - 0.1) < 1e-9 and abs(d['prod0_fill'] - 0.35) < 1e-9
+    assert abs(d['b_lead_us'] - 0.2) < 1e-9 and abs(d['setup_us'] - 1.0) < 1e-9 and abs(d['wall_us'] - 14.0) < 1e-9
+    assert 'mma_wait_weights' not in d

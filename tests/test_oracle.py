@@ -820,3 +820,55 @@ def test_batchnorm_train_matches_torch():
     got, mean, var = cpu.batchnorm_train(x, bn.weight.detach().numpy(), bn.bias.detach().numpy(), 1e-3)
     assert np.abs(got - y).max() < 1e-5
     assert np.abs(mean * 0.01 - bn.running_mean.numpy()).max() < 1e-6
+
+
+# --------------------------------------------------------------------------------------
+# arithmetic model of the opt-in bf16x3 mode (csrc/spconv_tc16.cu): is it inside the parity bound
+# over the WHOLE 21-layer LiDAR encoder?  (the kernel itself: tests/test_cuda_emul.py::test_tc16_*)
+# --------------------------------------------------------------------------------------
+def _bf16_round(x):
+    u = np.ascontiguousarray(x, np.float32).view(np.uint32).astype(np.uint64)
+    u = (u + 0x7FFF + ((u >> 16) & 1)) & 0xFFFF0000
+    return u.astype(np.uint32).view(np.float32).reshape(np.shape(x))
+
+
+def test_bf16x3_accuracy_model(monkeypatch):
+    """SparseEncoder (random spconv-default weights, BN statistics randomised) with every convolution
+    computed as A_hi*B_hi + A_lo*B_hi + A_hi*B_lo on bf16 hi/lo parts, against the fp32 oracle: each of the
+    five returned tensors and the BEV tensor within 1e-4 of its scale (north_star's bound), with margin.
+    The single-MMA bf16 mode is NOT (that is why it is only the train-step arithmetic)."""
+    from msmdfusion_b200 import synthetic
+    from oracle import model as omodel
+    import msmdfusion_b200 as m
+    from _fixtures import hotpath_cfg, randomize_bn
+    cfg = hotpath_cfg()
+    torch.manual_seed(0)
+    enc = m.registry.build_middle_encoder(cfg.pts_middle_encoder)
+    randomize_bn(enc, 1)
+    sd = enc.eval().state_dict()
+    scene = synthetic.lidar_scene(5, 1)[:6000]
+    ev, en, ec = omodel.voxelize_batch([scene], synthetic.VOXEL_SIZE, synthetic.POINT_CLOUD_RANGE, 10, 160000)
+    emean = cpu.hard_simple_vfe(ev, en, 5)
+    ref_sp, ref_feats, _ = omodel.sparse_encoder(sd, dict(cfg.pts_middle_encoder), emean, ec, 1)
+    exact = cpu.spconv_fwd
+
+    def x3(features, weight, pair):
+        fh, wh = _bf16_round(features), _bf16_round(weight)
+        fl, wl = _bf16_round(features - fh), _bf16_round(weight - wh)
+        return exact(fl, wh, pair) + exact(fh, wl, pair) + exact(fh, wh, pair)
+
+    def x1(features, weight, pair):
+        return exact(_bf16_round(features), _bf16_round(weight), pair)
+
+    def run(fn):
+        monkeypatch.setattr(cpu, 'spconv_fwd', fn)
+        try:
+            sp, feats, _ = omodel.sparse_encoder(sd, dict(cfg.pts_middle_encoder), emean, ec, 1)
+        finally:
+            monkeypatch.setattr(cpu, 'spconv_fwd', exact)
+        errs = [rel_err(a.features, b.features) for a, b in zip(feats, ref_feats)] + [rel_err(sp, ref_sp)]
+        return max(errs)
+
+    e3, e1 = run(x3), run(x1)
+    assert e3 < 3e-5, e3
+    assert e1 > 1e-4, e1
