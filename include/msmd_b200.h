@@ -242,6 +242,19 @@ MSMD_API int msmd_spconv_bwd_weight(const float* features, int n_in, const float
                                     const int* pair_fwd, int n_out, int cin, int cout, int kvol,
                                     float* grad_weight_krsc, void* workspace, size_t workspace_bytes,
                                     msmd_stream_t stream);
+/* Tensor-core weight gradient (csrc/spconv_wgrad_tc.cu): same contract and workspace layout as
+ * msmd_spconv_bwd_weight, the contraction over an offset's pairs on tcgen05 (3xTF32, fp32 accumulate in
+ * tensor memory, deterministic slice reduction) instead of exact-fp32 FFMA.  Needs cin, cout multiples of 4,
+ * cin <= 256 and 16-byte aligned features / grad_out.  msmd_spconv_set_wgrad_tc(1) (MSMD_WGRAD_TC=1) routes
+ * msmd_spconv_bwd_weight / msmd_spconv_bwd_weight_workspace here whenever the shape is supported.  Opt-in:
+ * checked on the host model of tcgen05 only, not yet run on hardware. */
+MSMD_API int msmd_spconv_bwd_weight_tc_supported(int cin, int cout, int kvol);
+MSMD_API size_t msmd_spconv_bwd_weight_tc_workspace(int n_out, int cin, int cout, int kvol);
+MSMD_API int msmd_spconv_bwd_weight_tc(const float* features, int n_in, const float* grad_out,
+                                       const int* pair_fwd, int n_out, int cin, int cout, int kvol,
+                                       float* grad_weight_krsc, void* workspace, size_t workspace_bytes,
+                                       msmd_stream_t stream);
+MSMD_API int msmd_spconv_set_wgrad_tc(int enable);
 /* Backward of msmd_to_dense: rows (n,c) gathered out of a (batch, c, D, H, W) gradient. */
 MSMD_API int msmd_from_dense(const int* indices, const float* dense, int n, int c, int batch_size,
                              const int* spatial_shape, float* out, msmd_stream_t stream);

@@ -74,6 +74,10 @@ SIGNATURES = {
     'msmd_spconv_bwd_data': (_i, [_vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _sz, _vp]),
     'msmd_spconv_bwd_weight_workspace': (_sz, [_i, _i, _i, _i]),
     'msmd_spconv_bwd_weight': (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _sz, _vp]),
+    'msmd_spconv_bwd_weight_tc_supported': (_i, [_i, _i, _i]),
+    'msmd_spconv_bwd_weight_tc_workspace': (_sz, [_i, _i, _i, _i]),
+    'msmd_spconv_bwd_weight_tc': (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _sz, _vp]),
+    'msmd_spconv_set_wgrad_tc': (_i, [_i]),
     'msmd_from_dense': (_i, [_vp, _vp, _i, _i, _i, _c_int_p, _vp, _vp]),
     'msmd_grid_rows': (_i, [_vp, _i, _i, _c_int_p, _vp, _vp, _vp, _vp]),
     'msmd_sparse_net_forward': (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _c_int_p, _vp, _sz, _vp, _vp]),
@@ -115,6 +119,8 @@ def lib():
             raise RuntimeError('libmsmd_b200.so ABI version mismatch')
         if os.environ.get('MSMD_MASK_SORT', '0') not in ('', '0'):  # opt-in: mask-sorted tiles (executor path)
             L.msmd_spconv_set_mask_sort(1)
+        if os.environ.get('MSMD_WGRAD_TC', '0') not in ('', '0'):  # opt-in: tensor-core weight gradient
+            L.msmd_spconv_set_wgrad_tc(1)
         if os.environ.get('MSMD_TC_VARIANT'):  # A/B switch of the tensor-core conv kernel (2 | 3)
             if L.msmd_spconv_tc_set_variant(int(os.environ['MSMD_TC_VARIANT'])) != 0:
                 raise RuntimeError('bad MSMD_TC_VARIANT')

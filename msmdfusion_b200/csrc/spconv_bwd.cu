@@ -261,8 +261,17 @@ extern "C" MSMD_API int msmd_spconv_bwd_data(const float* grad_out, int n_out, c
                          nullptr, 0, grad_in, stream);
 }
 
+static int g_wgrad_tc = 0;  // msmd_spconv_set_wgrad_tc: route msmd_spconv_bwd_weight to the tensor-core kernel
+
+extern "C" MSMD_API int msmd_spconv_set_wgrad_tc(int enable) {
+  g_wgrad_tc = enable ? 1 : 0;
+  return MSMD_OK;
+}
+
 extern "C" MSMD_API size_t msmd_spconv_bwd_weight_workspace(int n_out, int cin, int cout, int kvol) {
   if (n_out <= 0 || cin <= 0 || cout <= 0 || kvol <= 0) return 0;
+  if (g_wgrad_tc && msmd_spconv_bwd_weight_tc_supported(cin, cout, kvol))
+    return msmd_spconv_bwd_weight_tc_workspace(n_out, cin, cout, kvol);
   return (size_t)wgrad_splits(n_out, cin, cout, kvol) * kvol * cin * cout * sizeof(float);
 }
 
@@ -279,6 +288,10 @@ extern "C" MSMD_API int msmd_spconv_bwd_weight(const float* features, int n_in, 
     return MSMD_OK;
   }
   MSMD_REQUIRE(features && grad_out && pair_fwd, "spconv_bwd_weight: null pointer");
+  if (g_wgrad_tc && msmd_spconv_bwd_weight_tc_supported(cin, cout, kvol) &&
+      (((uintptr_t)features | (uintptr_t)grad_out) & 15) == 0)
+    return msmd_spconv_bwd_weight_tc(features, n_in, grad_out, pair_fwd, n_out, cin, cout, kvol,
+                                     grad_weight_krsc, workspace, workspace_bytes, stream_);
   const int splits = wgrad_splits(n_out, cin, cout, kvol);
   if (workspace == nullptr || workspace_bytes < (size_t)splits * total * sizeof(float)) {
     set_error("spconv_bwd_weight: workspace too small (%zu < %zu bytes)", workspace_bytes,

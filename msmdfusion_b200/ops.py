@@ -215,6 +215,12 @@ def set_mask_sort(enable):
     check(lib().msmd_spconv_set_mask_sort(int(bool(enable))), 'msmd_spconv_set_mask_sort')
 
 
+def set_wgrad_tc(enable):
+    """Opt-in: ``spconv_bwd_weight`` runs the tensor-core kernel (csrc/spconv_wgrad_tc.cu, 3xTF32) for the
+    shapes it supports instead of the exact-fp32 FFMA kernel (``msmd_spconv_set_wgrad_tc``)."""
+    check(lib().msmd_spconv_set_wgrad_tc(int(bool(enable))), 'msmd_spconv_set_wgrad_tc')
+
+
 def set_tc_variant(variant):
     """0 (default): chosen by Cout; 3: A operand staged in tensor memory; 2: A operand in shared memory."""
     check(lib().msmd_spconv_tc_set_variant(int(variant)), 'msmd_spconv_tc_set_variant')

@@ -48,6 +48,7 @@ def tc_emu():
         _TC.emu_msmd_spconv_tc_packed_floats.restype = ctypes.c_size_t
         _TC.emu_msmd_spconv_tc_workspace.restype = ctypes.c_size_t
         _TC.emu_msmd_spconv_tc16_packed_bytes.restype = ctypes.c_size_t
+        _TC.emu_msmd_spconv_bwd_weight_tc_workspace.restype = ctypes.c_size_t
     return _TC
 
 
@@ -571,3 +572,61 @@ def test_tc16_strided_rulebook_mask_sorted_and_empty_tiles_on_emulator():
     shift = rng.standard_normal(32).astype(np.float32)
     got = tc16_fwd(feat, w, empty, 0, one, shift)
     assert rel(got, cpu.spconv_fwd(bf16_round(feat), bf16_round(w), empty) + shift) < 2e-6
+
+
+# --------------------------------------------------------------------------------------
+# tensor-core weight gradient (csrc/spconv_wgrad_tc.cu) -- not yet run on hardware
+# --------------------------------------------------------------------------------------
+@pytest.mark.parametrize('cin,cout,ksize,subm,n', [(16, 16, 3, True, 700),      # one co tile, N = 16
+                                                    (8, 12, 3, True, 300),       # padded N (8 -> 16), cout % 16 != 0
+                                                    (68, 72, (3, 1, 1), True, 600),   # N = 80, three offsets
+                                                    (32, 160, 3, False, 2500),   # strided rulebook, two co tiles
+                                                    (192, 64, 3, True, 1500)])   # widest ci on the path, two row slices
+def test_wgrad_tc_kernel_on_emulator(cin, cout, ksize, subm, n):
+    """msmd_spconv_bwd_weight_tc on the tcgen05 host model against the oracle's float64-accumulated
+    gradient: compaction, raw-tile transposition into TMEM (A) / swizzled shared memory (B), 3xTF32
+    accumulation across chunks and scans, partial tiles + fixed-order slice reduction."""
+    L = tc_emu()
+    shape, batch = [7, 16, 16], 2
+    idx, feat = random_sparse(3, batch, shape, n, cin)
+    rng = np.random.default_rng(4)
+    ks = cpu._triple(ksize)
+    if subm:
+        pair = cpu.subm_rulebook(idx, shape, ks, 1)
+    else:
+        _, pair, _ = cpu.conv_rulebook(idx, shape, ks, 2, 1, 1)
+    kvol, n_out = pair.shape
+    go = rng.standard_normal((n_out, cout)).astype(np.float32)
+    _, ref = cpu.spconv_bwd(feat, np.zeros((cout, *ks, cin), np.float32), pair, go, need_input_grad=False)
+    assert L.emu_msmd_spconv_bwd_weight_tc_supported(cin, cout, kvol) == 1
+    need = L.emu_msmd_spconv_bwd_weight_tc_workspace(n_out, cin, cout, kvol)
+    assert need > 0 and need % (kvol * cin * cout * 4) == 0
+    ws = np.full(need // 4, np.nan, np.float32)
+    gw = np.full((cout, *ks, cin), np.nan, np.float32)
+    st = L.emu_msmd_spconv_bwd_weight_tc(P(feat), feat.shape[0], P(go), P(pair), n_out, cin, cout, kvol, P(gw),
+                                         P(ws), ctypes.c_size_t(need), None)
+    assert st == 0, L.emu_last_error()
+    assert rel(gw, ref) < 5e-6
+    assert L.emu_msmd_spconv_bwd_weight_tc(P(feat), feat.shape[0], P(go), P(pair), n_out, cin, cout, kvol, P(gw),
+                                           P(ws), ctypes.c_size_t(need - 4), None) == -3   # MSMD_ERR_WORKSPACE
+
+
+def test_wgrad_tc_edge_cases_on_emulator():
+    L = tc_emu()
+    gw = np.full((4, 27, 8), np.nan, np.float32)
+    assert L.emu_msmd_spconv_bwd_weight_tc(None, 0, None, None, 0, 8, 4, 27, P(gw), None, ctypes.c_size_t(0), None) == 0
+    assert np.all(gw == 0)
+    assert L.emu_msmd_spconv_bwd_weight_tc_supported(5, 16, 27) == 0      # the SIMT kernel keeps these
+    assert L.emu_msmd_spconv_bwd_weight_tc_supported(260, 16, 27) == 0
+    # an offset without any pair: its gradient slab is exactly zero
+    idx, feat = random_sparse(9, 1, [5, 9, 9], 60, 8)
+    pair = cpu.subm_rulebook(idx, [5, 9, 9], 3, 1)
+    pair[3, :] = -1
+    go = np.random.default_rng(0).standard_normal((60, 8)).astype(np.float32)
+    need = L.emu_msmd_spconv_bwd_weight_tc_workspace(60, 8, 8, 27)
+    ws = np.full(need // 4, np.nan, np.float32)
+    gw = np.full((8, 3, 3, 3, 8), np.nan, np.float32)
+    assert L.emu_msmd_spconv_bwd_weight_tc(P(feat), 60, P(go), P(pair), 60, 8, 8, 27, P(gw), P(ws),
+                                           ctypes.c_size_t(need), None) == 0, L.emu_last_error()
+    _, ref = cpu.spconv_bwd(feat, np.zeros_like(gw), pair, go, need_input_grad=False)
+    assert rel(gw, ref) < 5e-6 and np.all(gw.reshape(8, 27, 8)[:, 3] == 0)

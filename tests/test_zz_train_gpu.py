@@ -380,3 +380,34 @@ def test_tc16_bf16_backward_matches_rounded_operand_autograd():
     gi, gw = cpu.spconv_bwd(feat, w, pair, go)
     assert err(x.features.grad, gi) < 1e-2     # bf16 operands (grad_out and W^T rounded): 2^-9 per operand
     assert err(conv.weight.grad, gw) < TOL     # exact-fp32 wgrad on the fp32 features
+
+
+# --------------------------------------------------------------------------------------
+# tensor-core weight gradient (csrc/spconv_wgrad_tc.cu; opt-in: MSMD_WGRAD_TC=1 / ops.set_wgrad_tc)
+# --------------------------------------------------------------------------------------
+@pytest.mark.parametrize('cin,cout,subm', [(16, 16, True), (80, 80, True), (96, 128, False), (192, 192, True),
+                                            (64, 32, False)])
+def test_wgrad_tc_matches_simt_and_oracle(cin, cout, subm):
+    """msmd_spconv_bwd_weight with the tensor-core kernel switched on: against the oracle (float64
+    accumulation) and the exact-fp32 SIMT kernel at 1e-4 of the tensor's scale (3xTF32); bitwise repeatable."""
+    shape, batch = [9, 24, 24], 2
+    idx, feat = random_sparse(cin + cout, batch, shape, 3000, cin)
+    rng = np.random.default_rng(1)
+    if subm:
+        pair = cpu.subm_rulebook(idx, shape, 3, 1)
+    else:
+        _, pair, _ = cpu.conv_rulebook(idx, shape, 3, 2, 1, 1)
+    go = rng.standard_normal((pair.shape[1], cout)).astype(np.float32)
+    wshape = (cout, 3, 3, 3, cin)
+    _, ref = cpu.spconv_bwd(feat, np.zeros(wshape, np.float32), pair, go, need_input_grad=False)
+    simt = ops.spconv_bwd_weight(cuda(feat), cuda(go), cuda(pair), wshape)
+    try:
+        ops.set_wgrad_tc(True)
+        assert ops.lib().msmd_spconv_bwd_weight_tc_supported(cin, cout, 27) == 1
+        a = ops.spconv_bwd_weight(cuda(feat), cuda(go), cuda(pair), wshape)
+        b = ops.spconv_bwd_weight(cuda(feat), cuda(go), cuda(pair), wshape)
+        torch.cuda.synchronize()
+    finally:
+        ops.set_wgrad_tc(False)
+    assert err(a, ref) < TOL and err(a, simt) < TOL
+    assert torch.equal(a, b)

@@ -113,6 +113,10 @@ extern "C" int msmd_spconv_fwd_tc_ws(const float*, int, const float*, const int*
                                      const float*, const float*, int, float*, void*, size_t, msmd_stream_t) { return -100; }
 extern "C" int msmd_spconv_fwd_tc16(const float*, int, const void*, const int*, const int*, int, int, int, int, int,
                                     const float*, const float*, const float*, int, float*, msmd_stream_t) { return -100; }
+extern "C" int msmd_spconv_bwd_weight_tc_supported(int, int, int) { return 0; }
+extern "C" size_t msmd_spconv_bwd_weight_tc_workspace(int, int, int, int) { return 0; }
+extern "C" int msmd_spconv_bwd_weight_tc(const float*, int, const float*, const int*, int, int, int, int, float*, void*,
+                                         size_t, msmd_stream_t) { return -100; }
 extern "C" int msmd_spconv_fwd(const float*, int, const float*, const int*, int, int, int, int, const float*,
                                const float*, const float*, int, float*, msmd_stream_t);
 extern "C" size_t msmd_grid_num_words(int batch_size, const int* s) {   // as csrc/rulebook.cu
@@ -165,21 +169,22 @@ def build_tc(verbose=False):
     """Host-emulated copy of csrc/spconv_tc.cu (tcgen05 / TMEM / bulk-copy kernels) over tc_emul.h."""
     os.makedirs(OUT, exist_ok=True)
     lib = os.path.join(OUT, 'libmsmd_tc_emul.so')
-    deps = [os.path.join(CSRC, f) for f in ('common.cuh', 'tc_common.cuh', 'spconv_tc.cu', 'spconv_tc16.cu')] + \
+    deps = [os.path.join(CSRC, f) for f in ('common.cuh', 'tc_common.cuh', 'tc_trace.cuh', 'spconv_tc.cu', 'spconv_tc16.cu', 'spconv_wgrad_tc.cu')] + \
         [os.path.join(HERE, 'cuda_emul.h'), os.path.join(HERE, 'tc_emul.h'), os.path.abspath(__file__)]
     if os.path.exists(lib) and all(os.path.getmtime(lib) > os.path.getmtime(d) for d in deps):
         return lib
     _INLINED.clear()
     _INLINED.add('tc.cuh')   # replaced by tc_emul.h
-    unit = translate('spconv_tc.cu') + translate('spconv_tc16.cu')   # tc_common.cuh is inlined once
+    unit = translate('spconv_tc.cu') + translate('spconv_tc16.cu') + translate('spconv_wgrad_tc.cu')   # tc_common.cuh is inlined once
     _INLINED.clear()
     # dynamic shared memory: the window tc_emul.h hands out (deliberately 16-byte aligned only)
     unit, n = re.subn(r'extern __shared__ uint8_t (\w+)\[\];', r'uint8_t* \1 = ::emu::g_dyn_smem;', unit)
-    assert n >= 3
+    assert n >= 4
     fwd_decl = '''
 extern "C" int emu_msmd_spconv_fwd_tc_ws(const float*, int, const float*, const int*, int, int, int, int, const float*,
                                          const float*, const float*, int, float*, void*, size_t, msmd_stream_t);
 extern "C" size_t emu_msmd_spconv_tc_workspace(int, int);
+extern "C" int emu_msmd_spconv_bwd_weight_tc_supported(int, int, int);
 '''   # declared by include/msmd_b200.h in the real build
     text = PRELUDE + TC_PRELUDE + _device_helpers() + fwd_decl + unit
     cpp = os.path.join(OUT, 'emul_tc_unit.cpp')
