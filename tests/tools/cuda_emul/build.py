@@ -157,11 +157,15 @@ uint32_t g_tmem[128][512];
 uint32_t g_tmem_next = 0, g_tmem_live = 0;
 NamedBar g_named[16];
 std::atomic<long long> g_mma_count{0};
+std::deque<AsyncOp> g_mma_queue;
+std::vector<AsyncOp> g_copy_queue;
+int g_async_late = 1;
 static void tc_begin(uint32_t bytes) { tc_block_reset(bytes); g_dyn_smem = g_smem_window + kDynBase; }
 static void tc_end() { tc_block_check(); }
 static struct TcHooks { TcHooks() { g_block_begin = tc_begin; g_block_end = tc_end; } } g_tc_hooks;
 }
 extern "C" long long emu_tc_mma_count() { return ::emu::g_mma_count.load(); }
+extern "C" void emu_tc_set_async_late(int v) { ::emu::g_async_late = v; }
 '''
 
 

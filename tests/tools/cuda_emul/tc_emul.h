@@ -4,10 +4,10 @@
 // are.  It replaces tc.cuh textually (build.py) and keeps its names and signatures.
 //
 // What it models                               what it does NOT model
-//   shared-memory window with real 32-bit        asynchrony of the tensor core / copy engine (an MMA or
-//   shared addresses, 1024-byte alignment        bulk copy completes at issue), proxy fences, memory-
-//   rules, SWIZZLE_128B K-major operand reads    model races, timing, bank conflicts, TMEM allocation
-//   (address-bit XOR), descriptor / idesc        contention between CTAs
+//   shared-memory window with real 32-bit        proxy fences, memory-model races between ordinary
+//   shared addresses, 1024-byte alignment        threads, timing, bank conflicts, TMEM allocation
+//   rules, SWIZZLE_128B K-major operand reads    contention between CTAs.  Asynchrony of the tensor core /
+//   (address-bit XOR), descriptor / idesc        copy engine IS modelled, adversarially: see AsyncOp below
 //   field decoding with validity checks,
 //   mbarrier phases + transaction bytes,
 //   TMEM as 128 lanes x 512 columns with the
@@ -22,6 +22,8 @@
 #include <chrono>
 #include <condition_variable>
 #include <cstdlib>
+#include <deque>
+#include <functional>
 #include <map>
 #include <mutex>
 
@@ -50,6 +52,21 @@ struct NamedBar {
 };
 extern NamedBar g_named[16];
 extern std::atomic<long long> g_mma_count;
+// Asynchronous units, scheduled ADVERSARIALLY: a tcgen05.mma / bulk copy is queued at issue and executes as
+// LATE as the program allows -- when some thread first polls the mbarrier its completion is tied to (the
+// commit's barrier / the copy's complete_tx barrier), or at CTA exit.  Operands are therefore read, and
+// results written, at the last legal moment: a kernel that overwrites a stage before waiting on its
+// "empty" barrier, or reads a stage / accumulator before waiting on its "full" barrier, computes garbage.
+// (g_async_late = 0 restores completion at issue.)
+struct AsyncOp {
+  std::function<void()> run;   // empty for a commit marker
+  uint32_t bar = 0;            // commit marker / bulk copy: shared address of the mbarrier
+  uint32_t tx = 0;             // bulk copy: bytes to complete
+  int kind = 0;                // 0 = MMA, 1 = commit marker, 2 = bulk copy
+};
+extern std::deque<AsyncOp> g_mma_queue;        // in issue order (one issuing thread per CTA)
+extern std::vector<AsyncOp> g_copy_queue;      // bulk copies complete independently of each other
+extern int g_async_late;
 
 [[noreturn]] static inline void tc_fail(const char* fmt, ...) {
   va_list ap;
@@ -80,8 +97,16 @@ static inline void tc_block_reset(uint32_t dyn_bytes) {
   g_tmem_next = 0;
   g_tmem_live = 0;
   for (auto& b : g_named) b = NamedBar();
+  g_mma_queue.clear();
+  g_copy_queue.clear();
 }
 static inline void tc_block_check() {
+  // whatever is still queued completes now (nobody looked at its barrier any more); the arrivals
+  // they would perform cannot matter after the CTA's exit
+  for (auto& op : g_mma_queue) if (op.kind == 0) op.run();
+  for (auto& op : g_copy_queue) op.run();
+  g_mma_queue.clear();
+  g_copy_queue.clear();
   if (g_tmem_live != 0) tc_fail("CTA exited with %u TMEM columns still allocated", g_tmem_live);
   for (uint32_t a = 0; a < kSmemWindow; ++a) {
     if (a >= kDynBase && a < kDynBase + g_dyn_bytes) { a = kDynBase + g_dyn_bytes - 1; continue; }
@@ -155,14 +180,45 @@ static inline void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
   --b.pending;
   bar_check(b);
 }
+// g_tc_mu held.  Somebody is about to look at the barrier at shared address `a`: everything whose
+// completion that barrier tracks completes now (MMAs in issue order up to the last commit on it).
+static inline void async_flush_for(uint32_t a) {
+  int last = -1;
+  for (int i = 0; i < (int)::emu::g_mma_queue.size(); ++i)
+    if (::emu::g_mma_queue[i].kind == 1 && ::emu::g_mma_queue[i].bar == a) last = i;
+  for (int i = 0; i <= last; ++i) {
+    ::emu::AsyncOp op = std::move(::emu::g_mma_queue.front());
+    ::emu::g_mma_queue.pop_front();
+    if (op.kind == 0) { op.run(); continue; }
+    auto& b = ::emu::g_mbar[op.bar];
+    if (b.pending <= 0) ::emu::tc_fail("mbarrier at %u: more arrivals than its count %u", op.bar, b.expected);
+    --b.pending;
+    bar_check(b);
+  }
+  for (size_t i = 0; i < ::emu::g_copy_queue.size();) {
+    if (::emu::g_copy_queue[i].bar != a) { ++i; continue; }
+    ::emu::AsyncOp op = std::move(::emu::g_copy_queue[i]);
+    ::emu::g_copy_queue.erase(::emu::g_copy_queue.begin() + (long)i);
+    op.run();
+    auto& b = ::emu::g_mbar[op.bar];
+    b.tx -= op.tx;
+    bar_check(b);
+  }
+}
 static inline bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   std::lock_guard<std::mutex> g(::emu::g_tc_mu);
-  return (bar_at(bar).phase & 1u) != (parity & 1u);
+  auto& b = bar_at(bar);
+  async_flush_for(smem_u32(bar));
+  return (b.phase & 1u) != (parity & 1u);
 }
 static inline void mbar_wait(uint64_t* bar, uint32_t parity) {
   std::unique_lock<std::mutex> g(::emu::g_tc_mu);
   auto& b = bar_at(bar);
-  if (!::emu::g_tc_cv.wait_for(g, std::chrono::seconds(30), [&] { return (b.phase & 1u) != (parity & 1u); }))
+  const uint32_t a = smem_u32(bar);
+  if (!::emu::g_tc_cv.wait_for(g, std::chrono::seconds(30), [&] {
+        async_flush_for(a);
+        return (b.phase & 1u) != (parity & 1u);
+      }))
     ::emu::tc_fail("deadlock: thread %d waited 30 s on the mbarrier at %u (parity %u, pending %d, tx %lld)",
                    ::emu::emu_lin_tid(), smem_u32(bar), parity, b.pending, b.tx);
 }
@@ -172,11 +228,22 @@ static inline void bulk_g2s(void* dst_smem, const void* src, uint32_t bytes, uin
   const uint32_t d = smem_u32(dst_smem);
   if ((d & 15) || ((uintptr_t)src & 15) || (bytes & 15))
     ::emu::tc_fail("cp.async.bulk: dst %u / src %p / size %u must be 16-byte aligned", d, src, bytes);
-  memcpy(::emu::smem_ptr(d, bytes), src, bytes);
+  uint8_t* dst = ::emu::smem_ptr(d, bytes);
   std::lock_guard<std::mutex> g(::emu::g_tc_mu);
   auto& b = bar_at(bar);
-  b.tx -= bytes;
-  bar_check(b);
+  if (!::emu::g_async_late) {
+    memcpy(dst, src, bytes);
+    b.tx -= bytes;
+    bar_check(b);
+    return;
+  }
+  ::emu::AsyncOp op;
+  op.kind = 2;
+  op.bar = smem_u32(bar);
+  op.tx = bytes;
+  op.run = [dst, src, bytes] { memcpy(dst, src, bytes); };
+  ::emu::g_copy_queue.push_back(std::move(op));
+  ::emu::g_tc_cv.notify_all();   // a waiter re-evaluates (and thereby completes the copy)
 }
 
 // ---- TMEM -----------------------------------------------------------------------------
@@ -313,15 +380,29 @@ static inline float smem_h16(uint64_t desc, int r, int k, uint32_t fmt) {
   return bf16_operand(h, fmt);
 }
 
+static inline void mma_issue(std::function<void()> fn) {
+  if (!::emu::g_async_late) { fn(); return; }
+  std::lock_guard<std::mutex> g(::emu::g_tc_mu);
+  ::emu::AsyncOp op;
+  op.kind = 0;
+  op.run = std::move(fn);
+  ::emu::g_mma_queue.push_back(std::move(op));
+}
 static inline void mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   const IDesc I = decode_idesc(idesc, kFmtTF32, kFmtTF32);
-  mma_core(d_tmem, I.N, 8, accumulate, [&](int m, int k) { return smem_tf32(adesc, m, k); },
-           [&](int n, int k) { return smem_tf32(bdesc, n, k); });
+  check_d(d_tmem, I.N);
+  mma_issue([=] {
+    mma_core(d_tmem, I.N, 8, accumulate, [&](int m, int k) { return smem_tf32(adesc, m, k); },
+             [&](int n, int k) { return smem_tf32(bdesc, n, k); });
+  });
 }
 static inline void mma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   const IDesc I = decode_idesc(idesc, kFmtF16, kFmtBF16);
-  mma_core(d_tmem, I.N, 16, accumulate, [&](int m, int k) { return smem_h16(adesc, m, k, I.afmt); },
-           [&](int n, int k) { return smem_h16(bdesc, n, k, I.bfmt); });
+  check_d(d_tmem, I.N);
+  mma_issue([=] {
+    mma_core(d_tmem, I.N, 16, accumulate, [&](int m, int k) { return smem_h16(adesc, m, k, I.afmt); },
+             [&](int n, int k) { return smem_h16(bdesc, n, k, I.bfmt); });
+  });
 }
 static inline void check_a_tmem(uint32_t a_tmem, int cols) {
   if ((a_tmem >> 16) != 0) ::emu::tc_fail("tcgen05.mma: TMEM A address 0x%x has a lane offset", a_tmem);
@@ -333,8 +414,11 @@ static inline void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc,
   const IDesc I = decode_idesc(idesc, kFmtTF32, kFmtTF32);
   check_a_tmem(a_tmem, 8);
   const uint32_t ac = a_tmem & 0xFFFF;
-  mma_core(d_tmem, I.N, 8, accumulate, [&](int m, int k) { return tf32_operand(::emu::g_tmem[m][ac + k]); },
-           [&](int n, int k) { return smem_tf32(bdesc, n, k); });
+  check_d(d_tmem, I.N);
+  mma_issue([=] {
+    mma_core(d_tmem, I.N, 8, accumulate, [&](int m, int k) { return tf32_operand(::emu::g_tmem[m][ac + k]); },
+             [&](int n, int k) { return smem_tf32(bdesc, n, k); });
+  });
 }
 // A in tensor memory, 16-bit operands: two K elements per 32-bit column (low half = even k)
 static inline void mma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc,
@@ -342,15 +426,27 @@ static inline void mma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, 
   const IDesc I = decode_idesc(idesc, kFmtF16, kFmtBF16);
   check_a_tmem(a_tmem, 8);
   const uint32_t ac = a_tmem & 0xFFFF;
-  mma_core(d_tmem, I.N, 16, accumulate,
-           [&](int m, int k) {
-             const uint32_t w = ::emu::g_tmem[m][ac + (k >> 1)];
-             return bf16_operand((uint16_t)((k & 1) ? (w >> 16) : (w & 0xFFFF)), I.afmt);
-           },
-           [&](int n, int k) { return smem_h16(bdesc, n, k, I.bfmt); });
+  check_d(d_tmem, I.N);
+  mma_issue([=] {
+    mma_core(d_tmem, I.N, 16, accumulate,
+             [&](int m, int k) {
+               const uint32_t w = ::emu::g_tmem[m][ac + (k >> 1)];
+               return bf16_operand((uint16_t)((k & 1) ? (w >> 16) : (w & 0xFFFF)), I.afmt);
+             },
+             [&](int n, int k) { return smem_h16(bdesc, n, k, I.bfmt); });
+  });
 }
-// every MMA of the emulation completes at issue, so the commit is an immediate arrival
-static inline void mma_commit(uint64_t* bar) { mbar_arrive(bar); }
+// the commit's arrival happens once every MMA issued before it has executed (see AsyncOp)
+static inline void mma_commit(uint64_t* bar) {
+  if (!::emu::g_async_late) { mbar_arrive(bar); return; }
+  std::lock_guard<std::mutex> g(::emu::g_tc_mu);
+  bar_at(bar);
+  ::emu::AsyncOp op;
+  op.kind = 1;
+  op.bar = smem_u32(bar);
+  ::emu::g_mma_queue.push_back(std::move(op));
+  ::emu::g_tc_cv.notify_all();   // a waiter re-evaluates (and thereby runs the queue up to here)
+}
 
 static inline void tmem_lane_rule(uint32_t taddr, const char* what) {
   const int tid = ::emu::emu_lin_tid();
