@@ -1,6 +1,6 @@
 #!/bin/bash
 # First GPU call of round 2 (everything written at the end of round 1 without GPU time), in priority order.
-#   /usr/local/graft/bin/gpurun --timeout 1500 -- 'bash tools/gpu_round2.sh'
+#   /usr/local/graft/bin/gpurun --timeout 2400 -- 'bash tools/gpu_round2.sh'
 # Outputs land in gpurun_out/r02a_*; each step has its own timeout so that one hang cannot eat the call.
 set -u
 mkdir -p gpurun_out
@@ -11,7 +11,19 @@ echo "forward suite exit $?" | tee -a $O/r02a_summary.txt
 timeout 600 python -m pytest tests/test_zz_train_gpu.py -q > $O/r02a_pytest_train_masksort.log 2>&1
 echo "train + mask-sort suite exit $?" | tee -a $O/r02a_summary.txt
 tail -n 30 $O/r02a_pytest_train_masksort.log
-# 2. bench lines: default, mask-sorted, LC, LC mask-sorted, train step
+# 1b. where does the per-chunk time go?  per-role timeline of the tensor-core kernels (csrc/tc_trace.cuh)
+timeout 300 python tools/tc_trace.py --json $O/r02a_tc_trace_S.json > $O/r02a_tc_trace_S.txt 2>&1
+timeout 300 python tools/tc_trace.py --precision bf16x3 --json $O/r02a_tc_trace_S_bf16x3.json > $O/r02a_tc_trace_S_bf16x3.txt 2>&1
+timeout 300 python tools/tc_trace.py --mask-sort --json $O/r02a_tc_trace_S_masksort.json > $O/r02a_tc_trace_S_masksort.txt 2>&1
+timeout 300 python tools/tc_trace.py --sweeps 10 --json $O/r02a_tc_trace_L.json > $O/r02a_tc_trace_L.txt 2>&1
+head -n 30 $O/r02a_tc_trace_S.txt
+# 2. bench lines: default, mask-sorted, 16-bit operand modes, LC, LC mask-sorted, train step (fp32 / bf16 / tc wgrad)
+timeout 300 python bench.py --steps 100 --warmup 30 --precision bf16x3 --no-cpu-baseline > $O/r02a_bench_S_bf16x3.json 2>$O/r02a_bench_S_bf16x3.err
+MSMD_MASK_SORT=1 timeout 300 python bench.py --steps 100 --warmup 30 --precision bf16x3 --no-cpu-baseline > $O/r02a_bench_S_bf16x3_masksort.json 2>&1
+timeout 300 python bench.py --profile L --steps 50 --warmup 10 --precision bf16x3 --no-cpu-baseline > $O/r02a_bench_L_bf16x3.json 2>&1
+timeout 300 python bench.py --workload LC --steps 30 --warmup 10 --precision bf16x3 --no-cpu-baseline > $O/r02a_bench_LC_bf16x3.json 2>&1
+MSMD_WGRAD_TC=1 timeout 300 python bench.py --workload train --steps 20 --warmup 5 --no-cpu-baseline --breakdown $O/r02a_breakdown_train_wgradtc.json > $O/r02a_bench_train_wgradtc.json 2>&1
+MSMD_WGRAD_TC=1 timeout 300 python bench.py --workload train --precision bf16 --steps 20 --warmup 5 --no-cpu-baseline > $O/r02a_bench_train_bf16_wgradtc.json 2>&1
 timeout 300 python bench.py --steps 100 --warmup 30 > $O/r02a_bench_S.json 2>$O/r02a_bench_S.err
 MSMD_MASK_SORT=1 timeout 300 python bench.py --steps 100 --warmup 30 --no-cpu-baseline > $O/r02a_bench_S_masksort.json 2>$O/r02a_bench_S_masksort.err
 MSMD_MASK_SORT=1 timeout 300 python bench.py --profile L --steps 50 --warmup 10 --no-cpu-baseline > $O/r02a_bench_L_masksort.json 2>&1
@@ -19,7 +31,7 @@ timeout 300 python bench.py --profile L --steps 50 --warmup 10 --no-cpu-baseline
 timeout 300 python bench.py --workload LC --steps 30 --warmup 10 --no-cpu-baseline > $O/r02a_bench_LC.json 2>&1
 MSMD_MASK_SORT=1 timeout 300 python bench.py --workload LC --steps 30 --warmup 10 --no-cpu-baseline > $O/r02a_bench_LC_masksort.json 2>&1
 timeout 300 python bench.py --workload train --steps 20 --warmup 5 --no-cpu-baseline --breakdown $O/r02a_breakdown_train.json > $O/r02a_bench_train.json 2>$O/r02a_bench_train.err
-for f in S S_masksort L L_masksort LC LC_masksort train; do
+for f in S S_masksort S_bf16x3 S_bf16x3_masksort L L_masksort L_bf16x3 LC LC_masksort LC_bf16x3 train train_wgradtc train_bf16_wgradtc; do
   echo "== $f"; tail -c 600 $O/r02a_bench_$f.json | python -c "import sys,json
 try:
     d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print(d.get('value'), d.get('ms_per_step'), (d.get('e2e') or {}).get('value'))
