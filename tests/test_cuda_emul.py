@@ -216,14 +216,41 @@ class _EmuLib:
     def __init__(self, cabi):
         self._cabi, self._cache = cabi, {}
 
+    TC_UNIT = ('msmd_spconv_tc_', 'msmd_spconv_fwd_tc', 'msmd_spconv_tc16_', 'msmd_spconv_bwd_weight_tc')
+
     def __getattr__(self, name):
         fn = self._cache.get(name)
         if fn is None:
-            L = emu()
+            if name == 'msmd_spconv_bwd_data':
+                return self._bwd_data
+            if name == 'msmd_spconv_set_wgrad_tc':
+                return self._set_wgrad_tc
+            if name in ('msmd_spconv_bwd_weight', 'msmd_spconv_bwd_weight_workspace') and self._wgrad_tc:
+                name = name.replace('bwd_weight', 'bwd_weight_tc')   # what csrc/spconv_bwd.cu does when switched on
+            L = tc_emu() if name.startswith(self.TC_UNIT) else emu()
             fn = getattr(L, name) if name == 'msmd_spconv_fwd' else getattr(L, 'emu_' + name)
             fn.restype, fn.argtypes = self._cabi.SIGNATURES[name]
-            self._cache[name] = fn
+            if not self._wgrad_tc:
+                self._cache[name] = fn
         return fn
+
+    _wgrad_tc = False
+
+    def _set_wgrad_tc(self, enable):
+        self._wgrad_tc = bool(enable)
+        self._cache.clear()
+        return 0
+
+    def _bwd_data(self, go, n_out, wt, weight_tc, pair_bwd, n_in, cin, cout, kvol, gi, ws, ws_bytes, stream):
+        """csrc/spconv_bwd.cu:msmd_spconv_bwd_data restated (three-way dispatch onto the forward entry points;
+        the SIMT emulation unit cannot link the tensor-core one)."""
+        if weight_tc in (2, 3):
+            return self.msmd_spconv_fwd_tc16(go, n_out, wt, pair_bwd, None, n_in, cout, cin, kvol, int(weight_tc == 2),
+                                             None, None, None, 0, gi, stream)
+        if weight_tc:
+            return self.msmd_spconv_fwd_tc_ws(go, n_out, wt, pair_bwd, n_in, cout, cin, kvol, None, None, None, 0, gi,
+                                              ws, ws_bytes, stream)
+        return self.msmd_spconv_fwd(go, n_out, wt, pair_bwd, n_in, cout, cin, kvol, None, None, None, 0, gi, stream)
 
 
 @pytest.fixture()
@@ -630,3 +657,85 @@ def test_wgrad_tc_edge_cases_on_emulator():
                                            ctypes.c_size_t(need), None) == 0, L.emu_last_error()
     _, ref = cpu.spconv_bwd(feat, np.zeros_like(gw), pair, go, need_input_grad=False)
     assert rel(gw, ref) < 5e-6 and np.all(gw.reshape(8, 27, 8)[:, 3] == 0)
+
+
+# --------------------------------------------------------------------------------------
+# the real wrappers / modules / autograd over the EMULATED tensor-core kernels: the Python glue of the
+# paths that have not run on hardware (precision modes, mask-sorted tables, tc dgrad, tc wgrad)
+# --------------------------------------------------------------------------------------
+@pytest.fixture()
+def tc_ops_on_emulator(ops_on_emulator, monkeypatch):
+    import _cpu_ops
+    ops = ops_on_emulator
+    monkeypatch.setattr(ops, 'tc_supported', lambda cout, kvol, cin: cout <= 256 and kvol <= 32)
+    for name in ('grid_build', 'rulebook_subm', 'rulebook_conv'):
+        monkeypatch.setattr(ops, name, _cpu_ops.STANDINS[name])
+    yield ops
+    ops.set_wgrad_tc(False)
+
+
+def test_tc_wrappers_drive_emulated_kernels(tc_ops_on_emulator):
+    import torch
+    ops = tc_ops_on_emulator
+    shape, cin, cout = [7, 14, 14], 16, 24
+    idx, feat = random_sparse(9, 1, shape, 300, cin)
+    rng = np.random.default_rng(10)
+    w = (rng.standard_normal((cout, 3, 3, 3, cin)) * 0.2).astype(np.float32)
+    pair = cpu.subm_rulebook(idx, shape, 3, 1)
+    ref = cpu.spconv_fwd(feat, w, pair)
+    t = torch.from_numpy
+    row_perm, pair_sorted = ops.rulebook_mask_sort(t(pair))
+    for mode, tol in (('tf32x3', 5e-6), ('bf16x3', 2e-5), ('bf16', 1e-2)):
+        tcw = ops.pack_weight_tc(t(w), ops.TC_MODES[mode])
+        assert tcw.mode == ops.TC_MODES[mode] and (tcw.packed.dtype == torch.int16) == (mode != 'tf32x3')
+        out = ops.spconv_fwd(t(feat), tcw, t(pair))
+        assert rel(out.numpy(), ref) < tol
+        srt = ops.spconv_fwd_tc(t(feat), tcw, pair_sorted, row_perm=row_perm)
+        assert rel(srt.numpy(), out.numpy()) < 5e-6
+        # data gradient through the same precision: forward contraction with the mirrored weight
+        go = rng.standard_normal(ref.shape).astype(np.float32)
+        gi = ops.spconv_bwd_data(t(go), ops.pack_weight_tc(ops.transpose_weight(t(w), flip_k=True), tcw.mode), t(pair))
+        ri, _ = cpu.spconv_bwd(feat, w, pair, go, need_weight_grad=False)
+        assert rel(gi.numpy(), ri) < tol
+    # weight gradient: SIMT by default, tensor-core kernel when switched on, same wrapper
+    _, rw = cpu.spconv_bwd(feat, w, pair, go, need_input_grad=False)
+    simt = ops.spconv_bwd_weight(t(feat), t(go), t(pair), w.shape)
+    ops.set_wgrad_tc(True)
+    tcg = ops.spconv_bwd_weight(t(feat), t(go), t(pair), w.shape)
+    ops.set_wgrad_tc(False)
+    assert rel(simt.numpy(), rw) < 1e-5 and rel(tcg.numpy(), rw) < 5e-6 and not np.array_equal(simt.numpy(), tcg.numpy())
+
+
+@pytest.mark.parametrize('precision', ['bf16x3', 'bf16'])
+def test_modules_and_autograd_in_16bit_modes_on_emulated_kernels(tc_ops_on_emulator, monkeypatch, precision):
+    """SubMConv3d / SparseConv3d with spconv.CONV_PRECISION set: inference path (fused epilogue, packed-weight
+    cache keyed on the mode) and the autograd path (forward + dgrad in the forward's precision, fp32 wgrad)."""
+    import torch
+    from msmdfusion_b200 import spconv
+    monkeypatch.setattr(spconv, 'CONV_PRECISION', precision)
+    tol = 2e-5 if precision == 'bf16x3' else 1e-2
+    shape, cin, cout = [7, 12, 12], 8, 16
+    idx, feat = random_sparse(11, 1, shape, 250, cin)
+    for cls, kw in ((spconv.SubMConv3d, dict(padding=1)), (spconv.SparseConv3d, dict(stride=2, padding=1))):
+        torch.manual_seed(0)
+        conv = cls(cin, cout, 3, bias=False, **kw)
+        w = conv.weight.detach().numpy()
+        if conv.subm:
+            pair = cpu.subm_rulebook(idx, shape, 3, 1)
+        else:
+            _, pair, _ = cpu.conv_rulebook(idx, shape, 3, 2, 1, 1)
+        ref = cpu.spconv_fwd(feat, w, pair)
+        with torch.no_grad():
+            out = conv(spconv.SparseConvTensor(torch.from_numpy(feat), torch.from_numpy(idx), shape, 1))
+        assert conv.packed_weight().mode == tc_ops_on_emulator.TC_MODES[precision]
+        assert rel(out.features.numpy(), ref) < tol
+        monkeypatch.setattr(spconv, 'CONV_PRECISION', 'tf32x3')      # the cache follows the setting
+        assert conv.packed_weight().mode == 1
+        monkeypatch.setattr(spconv, 'CONV_PRECISION', precision)
+        f = torch.from_numpy(feat).clone().requires_grad_(True)
+        out = conv(spconv.SparseConvTensor(f, torch.from_numpy(idx), shape, 1))
+        g = torch.randn(out.features.shape, generator=torch.Generator().manual_seed(1))
+        (out.features * g).sum().backward()
+        ri, rw = cpu.spconv_bwd(feat, w, pair, g.numpy())
+        assert rel(out.features.detach().numpy(), ref) < tol
+        assert rel(f.grad.numpy(), ri) < tol and rel(conv.weight.grad.numpy(), rw) < 1e-5
