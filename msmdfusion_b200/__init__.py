@@ -15,6 +15,7 @@ from .voxel import HardSimpleVFE, Voxelization, hard_voxelize, voxelization  # n
 from . import functional  # noqa: F401
 from .fusion_encoder import SparseMultiModalEncoderPaint  # noqa: F401
 from .detector import MSMDFusionDetector, SPPModule, TransFusionDetector  # noqa: F401
+from .bev_tail import SECOND, SECONDFPN  # noqa: F401  (BEV tail behind the path; SURVEY §8(f) rank 1, cuDNN convs)
 from . import loading  # noqa: F401  (virtual-point wire format -> packed scene)
 from .loading import PIPELINES  # noqa: F401
 

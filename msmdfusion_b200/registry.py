@@ -95,6 +95,11 @@ NORM_LAYERS.register_module('BN2d', module=nn.BatchNorm2d)
 NORM_LAYERS.register_module('BN3d', module=nn.BatchNorm3d)
 NORM_LAYERS.register_module('LN', module=nn.LayerNorm)
 
+UPSAMPLE_LAYERS = Registry('upsample layer')
+UPSAMPLE_LAYERS.register_module('nearest', module=nn.Upsample)
+UPSAMPLE_LAYERS.register_module('bilinear', module=nn.Upsample)
+UPSAMPLE_LAYERS.register_module('deconv', module=nn.ConvTranspose2d)
+
 _NORM_ABBR = {'BN': 'bn', 'BN1d': 'bn', 'BN2d': 'bn', 'BN3d': 'bn', 'LN': 'ln'}
 
 
@@ -121,6 +126,18 @@ def build_norm_layer(cfg, num_features, postfix=''):
     for p in layer.parameters():
         p.requires_grad = requires_grad
     return _NORM_ABBR.get(layer_type, 'norm') + str(postfix), layer
+
+
+def build_upsample_layer(cfg, *args, **kwargs):
+    """mmcv.cnn.build_upsample_layer: 'deconv' -> ConvTranspose2d, 'nearest' / 'bilinear' -> Upsample(mode=type)."""
+    cfg_ = dict(cfg)
+    layer_type = cfg_.pop('type')
+    cls = UPSAMPLE_LAYERS.get(layer_type)
+    if cls is None:
+        raise KeyError(f'Unrecognized upsample type {layer_type}')
+    if cls is nn.Upsample:
+        cfg_['mode'] = layer_type
+    return cls(*args, **kwargs, **cfg_)
 
 
 def build_voxel_encoder(cfg):

@@ -872,3 +872,100 @@ def test_bf16x3_accuracy_model(monkeypatch):
     e3, e1 = run(x3), run(x1)
     assert e3 < 3e-5, e3
     assert e1 > 1e-4, e1
+
+
+# --------------------------------------------------------------------------------------
+# BEV tail: SECOND + SECONDFPN against the reference's own classes run in place
+# --------------------------------------------------------------------------------------
+def _reference_bev_tail():
+    """The reference's SECOND / SECONDFPN classes compiled from their source where it lies; mmcv's layer
+    builders are absent, so the three builder names resolve to this package's registry mirrors (plain
+    torch.nn layers on both sides -- what is compared is the reference's wiring of them)."""
+    import numpy
+    from torch import nn
+    from msmdfusion_b200 import registry
+    from oracle.ref_inplace import load_def
+    ns = {'nn': nn, 'torch': torch, 'np': numpy, 'build_conv_layer': registry.build_conv_layer,
+          'build_norm_layer': registry.build_norm_layer, 'build_upsample_layer': registry.build_upsample_layer,
+          'auto_fp16': lambda *a, **k: (lambda f: f)}
+    second = load_def('mmdet3d/models/backbones/second.py', 'SECOND', ns, keyword='class')
+    fpn = load_def('mmdet3d/models/necks/second_fpn.py', 'SECONDFPN', ns, keyword='class')
+    return second, fpn
+
+
+def _randomize_bn2d(module, seed):
+    g = torch.Generator().manual_seed(seed)
+    for mod in module.modules():
+        if isinstance(mod, torch.nn.BatchNorm2d):
+            mod.weight.data = torch.rand(mod.weight.shape, generator=g) + 0.5
+            mod.bias.data = torch.randn(mod.bias.shape, generator=g) * 0.1
+            mod.running_mean.data = torch.randn(mod.running_mean.shape, generator=g) * 0.1
+            mod.running_var.data = torch.rand(mod.running_var.shape, generator=g) + 0.5
+
+
+@pytest.mark.skipif(not __import__('oracle.ref_detector', fromlist=['x']).available(), reason='reference tree not mounted')
+def test_second_and_secondfpn_match_reference_classes_live():
+    """Same constructor kwargs as configs/MSMDFusion_nusc_voxel_LC.py:191-206 (narrower channels to keep it
+    quick): identical state-dict names and shapes, bit-identical output on the same weights in the layer-by-layer
+    mode (eval and train), and the BN-folded channels-last inference path within 1e-5 of it."""
+    import msmdfusion_b200 as m
+    ref_second, ref_fpn = _reference_bev_tail()
+    bb = dict(in_channels=32, out_channels=[16, 32], layer_nums=[5, 5], layer_strides=[1, 2],
+              norm_cfg=dict(type='BN', eps=0.001, momentum=0.01), conv_cfg=dict(type='Conv2d', bias=False))
+    nk = dict(in_channels=[16, 32], out_channels=[32, 32], upsample_strides=[1, 2],
+              norm_cfg=dict(type='BN', eps=0.001, momentum=0.01), upsample_cfg=dict(type='deconv', bias=False),
+              use_conv_for_no_stride=True)
+    torch.manual_seed(3)
+    ours_b = m.registry.build_backbone(dict(type='SECOND', **bb))
+    ours_n = m.registry.build_neck(dict(type='SECONDFPN', **nk))
+    _randomize_bn2d(ours_b, 1)
+    _randomize_bn2d(ours_n, 2)
+    rb, rn = ref_second(**bb), ref_fpn(**nk)
+    for ours, ref in ((ours_b, rb), (ours_n, rn)):
+        assert [(k, tuple(v.shape)) for k, v in ours.state_dict().items()] == \
+            [(k, tuple(v.shape)) for k, v in ref.state_dict().items()]
+        ref.load_state_dict(ours.state_dict())
+    x = torch.randn(2, 32, 24, 24)
+    for mode in ('eval', 'train'):
+        for mod in (ours_b, ours_n, rb, rn):
+            getattr(mod, mode)()
+        a = ours_n(ours_b(x.clone()))     # grad enabled: layer-by-layer path in both modes
+        b = rn(rb(x.clone()))
+        assert len(a) == 1 and a[0].shape == (2, 64, 24, 24) and torch.equal(a[0], b[0])
+    for mod in (ours_b, ours_n, rb, rn):
+        mod.eval()
+    with torch.no_grad():
+        fused = ours_n(ours_b(x.clone()))[0]
+        assert ours_b._folded is not None and ours_n._folded is not None      # the folded path ran
+        plain = rn(rb(x.clone()))[0]
+    assert rel_err(fused.numpy(), plain.numpy()) < 1e-5
+    # the cache follows in-place parameter updates
+    with torch.no_grad():
+        ours_b.blocks[0][0].weight.mul_(1.5)
+        rb.load_state_dict(ours_b.state_dict())
+        assert rel_err(ours_n(ours_b(x.clone()))[0].numpy(), rn(rb(x.clone()))[0].numpy()) < 1e-5
+    # the other level types: deconv with stride 1 (use_conv_for_no_stride=False) and a down-sampling level (stride 0.5)
+    nk2 = dict(in_channels=[16, 32], out_channels=[8, 8], upsample_strides=[0.5, 1],
+               norm_cfg=dict(type='BN', eps=0.001, momentum=0.01), upsample_cfg=dict(type='deconv', bias=False))
+    torch.manual_seed(5)
+    o2, r2 = m.SECONDFPN(**nk2).eval(), ref_fpn(**nk2).eval()
+    r2.load_state_dict(o2.state_dict())
+    xs = (torch.randn(1, 16, 24, 24), torch.randn(1, 32, 12, 12))
+    with torch.no_grad():
+        assert rel_err(o2(xs)[0].numpy(), r2(xs)[0].numpy()) < 1e-5
+
+
+def test_detector_builds_the_bev_tail_from_the_unchanged_config_entries():
+    """pts_backbone / pts_neck of the config resolve through the registries and run behind extract_pts_feat's
+    BEV tensor: (B, 256, 180, 180) -> SECOND -> SECONDFPN -> (B, 512, 180, 180) (configs/...LC.py:191-206)."""
+    import msmdfusion_b200 as m
+    bb = m.registry.build_backbone(dict(type='SECOND', in_channels=256, out_channels=[128, 256], layer_nums=[5, 5],
+                                        layer_strides=[1, 2], norm_cfg=dict(type='BN', eps=0.001, momentum=0.01),
+                                        conv_cfg=dict(type='Conv2d', bias=False))).eval()
+    nk = m.registry.build_neck(dict(type='SECONDFPN', in_channels=[128, 256], out_channels=[256, 256],
+                                    upsample_strides=[1, 2], norm_cfg=dict(type='BN', eps=0.001, momentum=0.01),
+                                    upsample_cfg=dict(type='deconv', bias=False), use_conv_for_no_stride=True)).eval()
+    assert sum(p.numel() for p in bb.parameters()) + sum(p.numel() for p in nk.parameters()) == 4_576_768   # SURVEY 8e: "SECOND+FPN ~4.6 M"
+    with torch.no_grad():
+        out = nk(bb(torch.randn(1, 256, 36, 36)))
+    assert out[0].shape == (1, 512, 36, 36)
