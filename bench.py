@@ -46,6 +46,10 @@ def parse():
                     help='operand precision of the tensor-core sparse convolutions (default: MSMD_CONV_PRECISION or '
                          'tf32x3 = the fp32-parity mode).  bf16x3: bf16 hi/lo split, ~5e-6 per layer.  bf16: operands '
                          'rounded to bf16 (the train-step arithmetic of BASELINE configs[4]; not a parity mode)')
+    ap.add_argument('--scenes-per-step', type=int, default=1,
+                    help='workload L only: scenes batched into one step on each GPU (default 1 = the workload '
+                         'BASELINE configs[1] names; the reference config trains with samples_per_gpu=2).  Reported in '
+                         'config.scenes_per_gpu_per_step; value counts scenes, not steps')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--breakdown', default=None, help='write a per-op CUDA-event breakdown (json) here')
     return ap.parse_args()
@@ -233,15 +237,24 @@ def run_ours(args, rank, world, device):
             return bev, stage_outs
     else:
         cfg, layer, enc = build_pipeline(device)
-        pts_np = synthetic.lidar_scene(seed=rank, sweeps=1 if args.profile == 'S' else 10)
+        B = max(1, args.scenes_per_step)
+        sweeps = 1 if args.profile == 'S' else 10
+        scenes = [synthetic.lidar_scene(seed=rank * B + b, sweeps=sweeps) for b in range(B)]
+        pts_np = np.concatenate(scenes) if B > 1 else scenes[0]
+        bounds = np.cumsum([0] + [len(sc) for sc in scenes])
         pts_host = torch.from_numpy(pts_np).pin_memory()
         pts_dev = pts_host.to(device)
         h2d_extra = [0]
 
         def step(points, fresh_upload=False):
             with torch.no_grad():
-                mean, coors, _ = layer.forward_mean(points, 5, batch_idx=0)
-                spatial, feats = enc(mean, coors, 1)
+                if B == 1:
+                    mean, coors, _ = layer.forward_mean(points, 5, batch_idx=0)
+                else:   # per-sample voxelisation, batch index in front (mvx_two_stage.py voxelize)
+                    parts = [layer.forward_mean(points[bounds[b]:bounds[b + 1]], 5, batch_idx=b) for b in range(B)]
+                    mean = torch.cat([q[0] for q in parts])
+                    coors = torch.cat([q[1] for q in parts])
+                spatial, feats = enc(mean, coors, B)
             return spatial, feats
 
     def sync_all():
@@ -500,18 +513,19 @@ def main():
     if rank != 0:
         return 0
     K = args.steps
-    value = world * K / (res['dev_ms'] * 1e-3)
+    SPS = max(1, args.scenes_per_step) if args.workload == 'L' else 1
+    value = world * K * SPS / (res['dev_ms'] * 1e-3)
     line = {
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': K, 'warmup': max(args.warmup, 3),
         'ms_per_step': res['dev_ms'] / K, 'step_ms': res['step_ms'], 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': 'bf16' if args.precision == 'bf16' else 'f32', 'data': 'synthetic',
-        'config': {'workload': workload_name(args.profile, args.workload), 'arithmetic': ARITHMETIC[args.precision], 'points_per_scene': res['points'],
-                   'voxels_per_scene': res['voxels'], 'scenes_per_gpu_per_step': 1, 'parallelism': 'dp%d' % world,
+        'config': {'workload': workload_name(args.profile, args.workload), 'arithmetic': ARITHMETIC[args.precision], 'points_per_scene': res['points'] // SPS,
+                   'voxels_per_scene': res['voxels'] // SPS, 'scenes_per_gpu_per_step': SPS, 'parallelism': 'dp%d' % world,
                    'l2': 'flushed between steps (256 MiB memset, outside the per-step events)',
                    'settle': '%d untimed steps (the first + %.0f ms of wall time) before the %d warm-up steps' % (res['settle_steps'], SETTLE_MS, max(args.warmup, 3)),
                    'weights': ('random init (spconv default); LiDAR encoder frozen (BN eval), GMA encoder BN in '
                                'training mode' if args.workload == 'train' else 'random init (spconv default), BN eval')},
-        'e2e': {'value': world * K / (res['e2e_ms'] * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': res['h2d'],
+        'e2e': {'value': world * K * SPS / (res['e2e_ms'] * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': res['h2d'],
                 'd2h_bytes_per_step': res['d2h'], 'step_ms': res['e2e_step_ms'],
                 'note': ('pinned host points (+ packed virtual points for LC) -> H2D -> public modules '
                          '(Voxelization.forward_mean/SparseEncoder or MSMDFusionDetector.extract_voxel_space) '
