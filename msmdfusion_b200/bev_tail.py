@@ -15,7 +15,7 @@ this project here and no claim on it.  What is B200-first is the inference data 
 the first layer to the concatenation, the ReLU runs in place on the conv output, and ``dtype='bf16'``
 (``MSMD_BEV_DTYPE=bf16``) runs the stack under bf16 with fp32 folded weights cast once.  In training mode, or with
 ``fused=False``, the modules run layer by layer exactly like the reference (bit-identical on the same torch build:
-tests/test_oracle.py::test_second_and_secondfpn_match_reference_classes_live).
+the CPU test test_second_and_secondfpn_match_reference_classes_live).
 """
 import os
 

@@ -53,6 +53,23 @@ def build_trace(verbose=False):
         LIB, OUT_DIR = saved
 
 
+PDL_LIB = os.path.join(OUT_DIR, 'libmsmd_b200_pdl.so')
+
+
+def build_pdl(verbose=False):
+    """Debug build with programmatic dependent launch of the tensor-core conv kernels (-DMSMD_TC_PDL: tc_launch in
+    csrc/tc_common.cuh, griddepcontrol in the kernels); A/B it against the product library through MSMD_LIB."""
+    global LIB, OUT_DIR
+    saved = (LIB, OUT_DIR)
+    try:
+        LIB, OUT_DIR = PDL_LIB, os.path.join(saved[1], 'pdl')
+        os.makedirs(OUT_DIR, exist_ok=True)
+        return build(force=not os.path.exists(PDL_LIB) or needs_build(), verbose=verbose,
+                     extra_flags=['-DMSMD_TC_PDL'])
+    finally:
+        LIB, OUT_DIR = saved
+
+
 def build(force=False, verbose=False, extra_flags=()):
     if not force and not needs_build():
         return LIB
@@ -83,6 +100,9 @@ def build(force=False, verbose=False, extra_flags=()):
 
 
 if __name__ == '__main__':
+    if '--pdl' in sys.argv:
+        print(build_pdl(verbose=True))
+        sys.exit(0)
     if '--trace' in sys.argv:
         print(build_trace(verbose=True))
         sys.exit(0)

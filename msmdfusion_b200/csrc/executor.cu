@@ -27,6 +27,7 @@ struct RulebookX {
   int* pair_sorted = nullptr;   // mask-sorted copy of the table + its slot -> row map (opt-in)
   int* row_perm = nullptr;
   cudaEvent_t ready = nullptr;  // recorded on the geometry stream after the rulebook kernels
+  int seq = -1;                 // position of `ready` among the events recorded on the geometry stream
 };
 
 static int g_mask_sort = 0;  // msmd_spconv_set_mask_sort
@@ -163,6 +164,7 @@ extern "C" MSMD_API int msmd_sparse_net_forward(const msmd_conv_layer* layers, i
   }
 
   int rc = MSMD_OK;
+  int ready_seq = 0, waited_seq = 0;  // events recorded on the geometry stream / the latest one `stream` waited for
   for (int li = 0; li < n_layers && rc == MSMD_OK; ++li) {
     rc = [&]() -> int {
       const msmd_conv_layer& L = layers[li];
@@ -201,6 +203,7 @@ extern "C" MSMD_API int msmd_sparse_net_forward(const msmd_conv_layer* layers, i
           }
           MSMD_TRY(next_event(*aux, &rb.ready));
           MSMD_CUDA_OK(cudaEventRecord(rb.ready, geom));
+          rb.seq = ++ready_seq;
           s.subm[key] = rb;
         } else {
           rb = it->second;
@@ -232,6 +235,7 @@ extern "C" MSMD_API int msmd_sparse_net_forward(const msmd_conv_layer* layers, i
         rb.pair = p;
         MSMD_TRY(next_event(*aux, &rb.ready));
         MSMD_CUDA_OK(cudaEventRecord(rb.ready, geom));
+        rb.seq = ++ready_seq;
         o.indices = oidx; o.n = n_out; o.bits = obits; o.prefix = oprefix; o.perm = nullptr;
         o.has_grid = true; o.ordered = true;
         isets.push_back(o);
@@ -245,7 +249,12 @@ extern "C" MSMD_API int msmd_sparse_net_forward(const msmd_conv_layer* layers, i
                      "sparse_net_forward: layer %d residual shape mismatch", li);
         residual = acts[L.residual].features;
       }
-      MSMD_CUDA_OK(cudaStreamWaitEvent(stream, rb.ready, 0));  // rulebook (and its indices) ready
+      // rulebook (and its indices) ready.  The geometry stream is in-order, so having waited for a later
+      // event covers every earlier one: the 4-5 layers that share a rulebook wait once, not once each
+      if (rb.seq > waited_seq) {
+        MSMD_CUDA_OK(cudaStreamWaitEvent(stream, rb.ready, 0));
+        waited_seq = rb.seq;
+      }
       if (L.weight_tc == 2 || L.weight_tc == 3) {  // 16-bit operand kernels: bf16x3 / bf16
         MSMD_TRY(msmd_spconv_fwd_tc16(in.features, in.n, L.weight, rb.pair_sorted ? rb.pair_sorted : rb.pair,
                                       rb.pair_sorted ? rb.row_perm : nullptr, n_out, L.cin, L.cout, kvol,

@@ -86,6 +86,7 @@ spconv_fwd_tc_kernel(const float* __restrict__ feat, const float* __restrict__ w
   const int row0 = blockIdx.x * kTcM;
   TC_TRACE_INIT();
   TC_TRACE_ENTRY();
+  tc::pdl_launch_dependents();  // (PDL build) the next layer's prologue may overlap this kernel
 
   // ---- one-time setup -------------------------------------------------------------------
   if (tid == 0) {
@@ -123,6 +124,9 @@ spconv_fwd_tc_kernel(const float* __restrict__ feat, const float* __restrict__ w
   const int any_active = n_act > 0;
   const uint32_t tmem_base = *tmem_ptr_s;
   if (tid == 0) { TC_TRACE_HEAD(1, clock64()); TC_TRACE_HEAD(7, n_act); }
+  // (PDL build) everything above touched only this layer's constants and its rulebook; features, residual,
+  // output and split-K scratch belong to the stream's data flow: wait for the previous kernel here
+  tc::pdl_wait();
 
   if (warp < kTcProducerWarps) {
     // ===== A producers: gather + tf32 hi/lo split + swizzled store ==========================
@@ -342,6 +346,7 @@ spconv_fwd_tc3_kernel(const float* __restrict__ feat, const float* __restrict__ 
   const int row0 = tile * kTcM;
   TC_TRACE_INIT();
   TC_TRACE_ENTRY();
+  tc::pdl_launch_dependents();  // (PDL build) the next layer's prologue may overlap this kernel
 
   if (tid == 0) {
     for (int s = 0; s < 4; ++s) {
@@ -385,6 +390,9 @@ spconv_fwd_tc3_kernel(const float* __restrict__ feat, const float* __restrict__ 
   const uint32_t tmem_base = *tmem_ptr_s;
   const uint32_t tmem_a0 = tmem_base + (uint32_t)N;  // A ring starts right after the accumulator
   if (tid == 0) { TC_TRACE_HEAD(1, clock64()); TC_TRACE_HEAD(7, n_act); }
+  // (PDL build) everything above touched only this layer's constants and its rulebook; features, residual,
+  // output and split-K scratch belong to the stream's data flow: wait for the previous kernel here
+  tc::pdl_wait();
 
   if (warp < kTcProducerWarps) {
     // ===== gather (coalesced) -> raw smem -> row-per-thread read -> split -> tcgen05.st =====
@@ -720,7 +728,7 @@ static int tc_forward_impl(const float* features, int n_in, const float* packed_
       part_ws = (float*)(part_flag + (size_t)2 * tiles + (64 - (2 * tiles) % 64) % 64);
       MSMD_CUDA_OK(cudaMemsetAsync(part_flag, 0, (size_t)2 * tiles * sizeof(int), stream));
     }
-    kern<<<tiles * split, kTcThreads, L.total, stream>>>(
+    tc_launch(kern, tiles * split, kTcThreads, L.total, stream, 
         features, packed_tc, pair_fwd, n_out, cin, g.cin_pad, cout, g.N, kvol, g.chunks, L.b_stages,
         L.b_stage_bytes, L.a_stages, L.raw_off, L.pair_off, L.act_off, L.bar_off, L.tmem_cols, scale, shift,
         residual, relu, out, split, part_ws, part_flag, row_perm);
@@ -741,7 +749,7 @@ static int tc_forward_impl(const float* features, int n_in, const float* packed_
     tmem_cols = 32;
     while (tmem_cols < 2 * g.N) tmem_cols <<= 1;
   }
-  kern<<<tiles, kTcThreads, L.total, stream>>>(features, packed_tc, pair_fwd, n_out, cin, g.cin_pad, cout,
+  tc_launch(kern, tiles, kTcThreads, L.total, stream, features, packed_tc, pair_fwd, n_out, cin, g.cin_pad, cout,
                                                g.N, kvol, g.chunks, L.stages, L.stage_bytes, L.pair_off,
                                                L.act_off, L.bar_off, tmem_cols, scale, shift, residual,
                                                relu, out, cat, row_perm);

@@ -83,6 +83,7 @@ spconv_fwd_tc16_kernel(const float* __restrict__ feat, const uint16_t* __restric
   const int row0 = blockIdx.x * kTcM;
   TC_TRACE_INIT();
   TC_TRACE_ENTRY();
+  tc::pdl_launch_dependents();  // (PDL build) the next layer's prologue may overlap this kernel
 
   if (tid == 0) {
     for (int s = 0; s < stages; ++s) {
@@ -118,6 +119,9 @@ spconv_fwd_tc16_kernel(const float* __restrict__ feat, const uint16_t* __restric
   const int any_active = n_act > 0;
   const uint32_t tmem_base = *tmem_ptr_s;
   if (tid == 0) { TC_TRACE_HEAD(1, clock64()); TC_TRACE_HEAD(7, n_act); }
+  // (PDL build) everything above touched only this layer's constants and its rulebook; features, residual,
+  // output and split-K scratch belong to the stream's data flow: wait for the previous kernel here
+  tc::pdl_wait();
 
   if (warp < kTcProducerWarps) {
     // ===== A producers: gather (fp32) -> bf16 [hi | lo] -> swizzled store ======================
@@ -360,7 +364,7 @@ extern "C" MSMD_API int msmd_spconv_fwd_tc16(const float* features, int n_in, co
   const int cat = (x3 && 2 * g.N <= 256) ? 1 : 0;
   int tmem_cols = 32;
   while (tmem_cols < (cat ? 2 * g.N : g.N)) tmem_cols <<= 1;
-  kern<<<tiles, kTcThreads, L.total, stream>>>(features, (const uint16_t*)packed_tc16, pair_fwd, n_out, cin,
+  tc_launch(kern, tiles, kTcThreads, L.total, stream, features, (const uint16_t*)packed_tc16, pair_fwd, n_out, cin,
                                                g.cin_pad, cout, g.N, kvol, g.chunks, L.stages, L.stage_bytes,
                                                L.pair_off, L.act_off, L.bar_off, tmem_cols, scale, shift,
                                                residual, relu, out, cat, row_perm);

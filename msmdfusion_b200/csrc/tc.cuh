@@ -158,6 +158,21 @@ __device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, ui
       : "memory");
 }
 
+// Programmatic dependent launch (opt-in debug build, -DMSMD_TC_PDL; see tc_launch in tc_common.cuh): a kernel
+// launched with programmatic stream serialization may start while its predecessor in the stream is still
+// running; everything that reads the predecessor's results must come after pdl_wait().  Without the
+// launch attribute both instructions are no-ops; without the macro they are not even emitted.
+__device__ __forceinline__ void pdl_launch_dependents() {
+#ifdef MSMD_TC_PDL
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
+__device__ __forceinline__ void pdl_wait() {
+#ifdef MSMD_TC_PDL
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
+}
+
 __device__ __forceinline__ float4 ld_shared_v4(uint32_t addr) {
   float4 v;
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));

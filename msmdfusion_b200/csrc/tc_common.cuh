@@ -15,6 +15,29 @@ constexpr int kTcDepth = 3;      // variant 2: K chunks whose gather loads are i
 
 static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
+// Launch of a tensor-core conv kernel.  Product build: an ordinary triple-chevron launch.  -DMSMD_TC_PDL (debug build
+// `python -m msmdfusion_b200.build --pdl`): programmatic stream serialization, so that consecutive layers of a
+// chain overlap the next kernel's prologue (barrier init, TMEM allocation, pair-table load, active-chunk list)
+// with this kernel's tail; the kernels order their data reads with tc::pdl_wait().
+template <typename Kern, typename... Args>
+static inline void tc_launch(Kern kern, int grid, int block, int smem, cudaStream_t stream, Args... args) {
+#ifdef MSMD_TC_PDL
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3((unsigned)block);
+  cfg.dynamicSmemBytes = (size_t)smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, kern, args...);
+#else
+  kern<<<grid, block, smem, stream>>>(args...);
+#endif
+}
+
 // One lane polls the mbarrier, the warp follows through __syncwarp (31 fewer spinning lanes per
 // warp: the producers are instruction-issue bound, profiles/r01e_ncu_full_spconv_tc_profileS.json).
 __device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity, int lane) {

@@ -469,6 +469,9 @@ static inline void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
 }
 static inline void tmem_st_wait() {}
 
+static inline void pdl_launch_dependents() {}
+static inline void pdl_wait() {}
+
 static inline float4 ld_shared_v4(uint32_t addr) {
   if (addr & 15) ::emu::tc_fail("ld.shared.v4 at %u is not 16-byte aligned", addr);
   float4 v;
