@@ -141,6 +141,10 @@ MSMD_API int msmd_spconv_tc_supported(int cout, int kvol, int cin);
 /* kernel variant: 0 (default) = chosen by Cout, 3 = A operand staged in tensor memory,
  * 2 = A operand in shared memory */
 MSMD_API int msmd_spconv_tc_set_variant(int variant);
+/* A/B switches of the host-side launch heuristics (defaults 0 = the measured rules): key 0 occupancy
+ * (1 = one CTA per SM with the deepest pipeline, 2 = two CTAs per SM whenever they fit), key 1 pipeline-stage
+ * cap (2..4), key 2 split-K pairs (1 = never, 2 = whenever supported).  MSMD_TC_TUNE="occ=1,stages=3,split=1". */
+MSMD_API int msmd_spconv_tc_set_tuning(int key, int value);
 MSMD_API size_t msmd_spconv_tc_packed_floats(int cout, int kvol, int cin);
 MSMD_API int msmd_spconv_tc_pack_weight(const float* weight_krsc, int cout, int kvol, int cin,
                                         float* packed_tc, msmd_stream_t stream);

@@ -56,6 +56,7 @@ SIGNATURES = {
     'msmd_spconv_fwd': (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _vp]),
     'msmd_spconv_tc_supported': (_i, [_i, _i, _i]),
     'msmd_spconv_tc_set_variant': (_i, [_i]),
+    'msmd_spconv_tc_set_tuning': (_i, [_i, _i]),
     'msmd_spconv_tc_packed_floats': (_sz, [_i, _i, _i]),
     'msmd_spconv_tc_pack_weight': (_i, [_vp, _i, _i, _i, _vp, _vp]),
     'msmd_spconv_fwd_tc': (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _vp]),
@@ -121,6 +122,11 @@ def lib():
             L.msmd_spconv_set_mask_sort(1)
         if os.environ.get('MSMD_WGRAD_TC', '0') not in ('', '0'):  # opt-in: tensor-core weight gradient
             L.msmd_spconv_set_wgrad_tc(1)
+        if os.environ.get('MSMD_TC_TUNE'):  # e.g. "occ=1,stages=3,split=1": launch-heuristic A/B switches
+            for item in os.environ['MSMD_TC_TUNE'].split(','):
+                name, _, val = item.partition('=')
+                if L.msmd_spconv_tc_set_tuning({'occ': 0, 'stages': 1, 'split': 2}[name.strip()], int(val)) != 0:
+                    raise RuntimeError('bad MSMD_TC_TUNE')
         if os.environ.get('MSMD_TC_VARIANT'):  # A/B switch of the tensor-core conv kernel (2 | 3)
             if L.msmd_spconv_tc_set_variant(int(os.environ['MSMD_TC_VARIANT'])) != 0:
                 raise RuntimeError('bad MSMD_TC_VARIANT')

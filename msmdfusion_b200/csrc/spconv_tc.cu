@@ -44,13 +44,9 @@ static TcSmemLayout tc_layout(int N, int kvol, int chunks, int tiles) {
   const int misc = round_up(kvol * kTcM * 4, 16) + round_up(2 * chunks, 16) + 256 + 8 * N;
   // two CTAs per SM when two stages fit in half of the SM's shared memory AND there are enough
   // tiles to need the second slot; otherwise one CTA with a deeper pipeline (max 4 stages)
-  const int half = 112 * 1024, full = 224 * 1024;
-  if (2 * L.stage_bytes + misc + 1024 <= half && tiles > kNumSMs) {
-    L.stages = (half - misc - 1024) / L.stage_bytes;
-  } else {
-    L.stages = (full - misc - 1024) / L.stage_bytes;
-  }
-  if (L.stages > 4) L.stages = 4;
+  const int budget = tc_smem_budget(2 * L.stage_bytes + misc + 1024 <= 112 * 1024, tiles);
+  L.stages = (budget - misc - 1024) / L.stage_bytes;
+  if (L.stages > tc_stage_cap()) L.stages = tc_stage_cap();
   L.pair_off = L.stages * L.stage_bytes;
   L.act_off = L.pair_off + round_up(kvol * kTcM * 4, 16);
   L.bar_off = L.act_off + round_up(2 * chunks, 16);
@@ -298,8 +294,9 @@ static Tc3Layout tc3_layout(int N, int kvol, int chunks) {
   const int misc = 2 * kTcABytes + round_up(kvol * kTcM * 4, 16) + round_up(2 * chunks, 16) + 512 + 8 * N;
   const int half = 113 * 1024, full = 224 * 1024;
   int budget = (2 * L.b_stage_bytes + misc + 1024 <= half) ? half : full;
+  if (g_tc_tune[0] == 1) budget = full;   // A/B switch: one CTA per SM
   L.b_stages = (budget - misc - 1024) / L.b_stage_bytes;
-  if (L.b_stages > 4) L.b_stages = 4;
+  if (L.b_stages > tc_stage_cap()) L.b_stages = tc_stage_cap();
   L.a_stages = (N <= 64) ? 3 : 2;
   L.tmem_cols = 32;
   while (L.tmem_cols < N + 64 * L.a_stages) L.tmem_cols <<= 1;
@@ -611,6 +608,14 @@ extern "C" MSMD_API int msmd_tc_trace_set(unsigned long long* buf) { return tc_t
 extern "C" MSMD_API int msmd_tc_trace_record_words(void) { return kTrRecord; }
 #endif
 
+int msmd::g_tc_tune[4] = {0, 0, 0, 0};
+
+extern "C" MSMD_API int msmd_spconv_tc_set_tuning(int key, int value) {
+  MSMD_REQUIRE(key >= 0 && key < 4, "spconv_tc_set_tuning: key must be 0 (occupancy), 1 (stage cap) or 2 (split-K)");
+  g_tc_tune[key] = value;
+  return MSMD_OK;
+}
+
 static int g_tc_variant = 0;  // 0: auto (by N); 2: A through shared memory; 3: A through tensor memory
 
 extern "C" MSMD_API int msmd_spconv_tc_set_variant(int variant) {
@@ -647,7 +652,8 @@ extern "C" MSMD_API int msmd_spconv_tc_pack_weight(const float* weight_krsc, int
 // Split-K pairs pay off when the tile count leaves most SMs idle or one tile short of a wave:
 // makespan in tile-times is ceil(t/148) unsplit and ceil(2t/148)/2 split.
 static bool tc_use_split(int tiles, int N) {
-  if (N < 96) return false;  // variant 3 only
+  if (N < 96 || g_tc_tune[2] == 1) return false;  // variant 3 only
+  if (g_tc_tune[2] == 2) return true;
   return tiles <= kNumSMs / 2 || (tiles > kNumSMs && tiles <= kNumSMs + kNumSMs / 2);
 }
 

@@ -41,12 +41,9 @@ static T16Layout t16_layout(int N, int kvol, int chunks, int tiles, int images) 
   T16Layout L;
   L.stage_bytes = images * (kT16ABytes + N * 128);  // A hi [| A lo] | B hi [| B lo], all 1024-B aligned
   const int misc = round_up(kvol * kTcM * 4, 16) + round_up(2 * chunks, 16) + 256 + 8 * N;
-  const int half = 112 * 1024, full = 224 * 1024;
-  if (2 * L.stage_bytes + misc + 1024 <= half && tiles > kNumSMs)
-    L.stages = (half - misc - 1024) / L.stage_bytes;   // two CTAs per SM
-  else
-    L.stages = (full - misc - 1024) / L.stage_bytes;
-  if (L.stages > 4) L.stages = 4;
+  const int budget = tc_smem_budget(2 * L.stage_bytes + misc + 1024 <= 112 * 1024, tiles);  // half: two CTAs per SM
+  L.stages = (budget - misc - 1024) / L.stage_bytes;
+  if (L.stages > tc_stage_cap()) L.stages = tc_stage_cap();
   L.pair_off = L.stages * L.stage_bytes;
   L.act_off = L.pair_off + round_up(kvol * kTcM * 4, 16);
   L.bar_off = L.act_off + round_up(2 * chunks, 16);

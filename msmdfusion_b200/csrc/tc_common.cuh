@@ -15,6 +15,20 @@ constexpr int kTcDepth = 3;      // variant 2: K chunks whose gather loads are i
 
 static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
+// Host-side tuning switches for A/B runs (msmd_spconv_tc_set_tuning; defaults = the measured heuristics):
+//   [0] occupancy  0 auto | 1 one CTA per SM (whole shared memory, deeper pipeline) | 2 two CTAs per SM when they fit
+//   [1] stage cap  2..4 (default 4)
+//   [2] split-K    0 auto | 1 never | 2 whenever the kernel supports it
+extern int g_tc_tune[4];
+// shared-memory budget of one CTA: `fits_half` = two pipeline stages fit in half of the SM
+static inline int tc_smem_budget(bool fits_half, int tiles) {
+  const int half = 112 * 1024, full = 224 * 1024;
+  if (g_tc_tune[0] == 1) return full;
+  if (g_tc_tune[0] == 2) return fits_half ? half : full;
+  return (fits_half && tiles > kNumSMs) ? half : full;
+}
+static inline int tc_stage_cap() { return (g_tc_tune[1] >= 2 && g_tc_tune[1] <= 4) ? g_tc_tune[1] : 4; }
+
 // Launch of a tensor-core conv kernel.  Product build: an ordinary triple-chevron launch.  -DMSMD_TC_PDL (debug build
 // `python -m msmdfusion_b200.build --pdl`): programmatic stream serialization, so that consecutive layers of a
 // chain overlap the next kernel's prologue (barrier init, TMEM allocation, pair-table load, active-chunk list)
