@@ -175,7 +175,8 @@ MSMD_API int msmd_spconv_fwd_tc_ws(const float* features, int n_in, const float*
  *   msmd_spconv_fwd_tc_sorted msmd_spconv_fwd_tc_ws on the permuted table: slot s of a tile computes
  *                             output row row_perm[s] (residual read / result written there), so `out`
  *                             is in the ORIGINAL row order.  Per-row accumulation order is unchanged.
- * Opt-in (msmd_spconv_set_mask_sort / MSMD_MASK_SORT=1): not yet measured on hardware.
+ * Opt-in (msmd_spconv_set_mask_sort / MSMD_MASK_SORT=1): correct on a B200 (profiles/r01h_quick_gpu_check.json),
+ * not yet timed.
  * ---------------------------------------------------------------------------------- */
 MSMD_API size_t msmd_rulebook_mask_sort_workspace(int n);
 MSMD_API int msmd_rulebook_mask_sort(const int* pair_fwd, int kvol, int n, int* row_perm,
@@ -203,7 +204,7 @@ MSMD_API int msmd_spconv_set_mask_sort(int enable);
  * `packed_tc16`: msmd_spconv_tc16_pack_weight image (msmd_spconv_tc16_packed_bytes bytes) of the KRSC weight
  * for the SAME x3.  `row_perm` NULL, or the slot -> row map of a mask-sorted table (msmd_rulebook_mask_sort).
  * Opt-in (MSMD_CONV_PRECISION / MSMD_TRAIN_PRECISION, msmd_conv_layer.weight_tc 2 / 3): checked on the host
- * model of tcgen05 only, not yet run on hardware.
+ * model of tcgen05 and on a B200 (profiles/r01h_quick_gpu_check.json: correctness only, not yet timed).
  * ---------------------------------------------------------------------------------- */
 MSMD_API size_t msmd_spconv_tc16_packed_bytes(int cout, int kvol, int cin, int x3);
 MSMD_API int msmd_spconv_tc16_pack_weight(const float* weight_krsc, int cout, int kvol, int cin, int x3,
@@ -251,7 +252,7 @@ MSMD_API int msmd_spconv_bwd_weight(const float* features, int n_in, const float
  * tensor memory, deterministic slice reduction) instead of exact-fp32 FFMA.  Needs cin, cout multiples of 4,
  * cin <= 256 and 16-byte aligned features / grad_out.  msmd_spconv_set_wgrad_tc(1) (MSMD_WGRAD_TC=1) routes
  * msmd_spconv_bwd_weight / msmd_spconv_bwd_weight_workspace here whenever the shape is supported.  Opt-in:
- * checked on the host model of tcgen05 only, not yet run on hardware. */
+ * checked on the host model of tcgen05 and on a B200 (profiles/r01h_quick_gpu_check.json); not yet timed. */
 MSMD_API int msmd_spconv_bwd_weight_tc_supported(int cin, int cout, int kvol);
 MSMD_API size_t msmd_spconv_bwd_weight_tc_workspace(int n_out, int cin, int cout, int kvol);
 MSMD_API int msmd_spconv_bwd_weight_tc(const float* features, int n_in, const float* grad_out,

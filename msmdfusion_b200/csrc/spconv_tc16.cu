@@ -20,7 +20,8 @@
 // shared memory is the K-major SWIZZLE_128B canonical layout the tf32 kernel uses (same descriptors; only
 // the instruction descriptor's operand format and K = 16 per MMA differ).
 //
-// Status: written without GPU time.  Checked on the host model of tcgen05 (tests/tools/cuda_emul/tc_emul.h,
+// Status: written without GPU time; then confirmed on a B200 by tools/quick_gpu_check.py (correctness at four
+// channel widths, profiles/r01h_quick_gpu_check.json) -- not yet timed.  Checked on the host model of tcgen05 (tests/tools/cuda_emul/tc_emul.h,
 // calibrated on the GPU-verified tf32 kernels): tests/test_cuda_emul.py::test_tc16_*.  GPU tests:
 // tests/test_zz_train_gpu.py::test_tc16_*.
 #include "tc_common.cuh"

@@ -22,7 +22,8 @@
 // workspace [slice][k][co][ci] and a second kernel sums the slices in a fixed order: deterministic, no
 // atomics.  fp32-level accuracy (3xTF32, lo*lo dropped) instead of the SIMT kernel's exact FFMA.
 //
-// Status: written without GPU time; opt-in (msmd_spconv_set_wgrad_tc / MSMD_WGRAD_TC=1).  Checked on the
+// Status: written without GPU time; opt-in (msmd_spconv_set_wgrad_tc / MSMD_WGRAD_TC=1).  Correct on a B200
+// (tools/quick_gpu_check.py, profiles/r01h_quick_gpu_check.json: <= 8e-6 of float64), not yet timed.  Checked on the
 // host model of tcgen05 (tests/test_cuda_emul.py::test_wgrad_tc_*); GPU test
 // tests/test_zz_train_gpu.py::test_wgrad_tc_matches_simt_and_oracle.
 #include "tc.cuh"
