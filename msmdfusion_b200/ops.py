@@ -489,6 +489,21 @@ def ball_query_single(min_radius, max_radius, nsample, xyz, center_xyz):
     return idx
 
 
+def furthest_point_sample(points_xyz, num_points):
+    """Drop-in for ``mmdet3d.ops.furthest_point_sample`` (furthest_point_sample/furthest_point_sample.py:8-37):
+    points_xyz (B, N, 3) f32 contiguous -> (B, num_points) int32, start index 0 per batch element."""
+    assert points_xyz.dim() == 3 and points_xyz.shape[2] == 3 and points_xyz.is_contiguous()
+    return torch.stack([furthest_point_sample_single(points_xyz[b], num_points) for b in range(points_xyz.shape[0])])
+
+
+def ball_query(min_radius, max_radius, sample_num, xyz, center_xyz):
+    """Drop-in for ``mmdet3d.ops.ball_query`` (ball_query/ball_query.py:8-46): xyz (B, N, 3), center_xyz
+    (B, npoint, 3) f32 contiguous -> (B, npoint, sample_num) int32."""
+    assert center_xyz.is_contiguous() and xyz.is_contiguous() and min_radius < max_radius
+    return torch.stack([ball_query_single(min_radius, max_radius, sample_num, xyz[b], center_xyz[b])
+                        for b in range(xyz.shape[0])])
+
+
 def nn_search(query_zyx, key_zyx):
     """(nq,3)/(nk,3) int32 voxel coordinates -> (val f32 (nq), idx i32 (nq))."""
     q, k = query_zyx.contiguous(), key_zyx.contiguous()

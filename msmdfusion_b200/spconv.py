@@ -111,6 +111,18 @@ class IndexSet:
         return rec
 
 
+class _NullTimer:
+    """Stand-in for spconv's CUDAKernelTimer: ``tensor._timer.namespace(name)`` is a no-op context
+    (bug_fix/conv.py:380 enters it unconditionally)."""
+
+    def namespace(self, name):
+        import contextlib
+        return contextlib.nullcontext()
+
+
+_NULL_TIMER = _NullTimer()
+
+
 class SparseConvTensor:
     """spconv.SparseConvTensor(features, indices, spatial_shape, batch_size)."""
 
@@ -126,7 +138,7 @@ class SparseConvTensor:
         self.benchmark = benchmark
         self.benchmark_record = {}
         self.thrust_allocator = None
-        self._timer = None
+        self._timer = _NULL_TIMER
         self._iset = None
 
     # -- features / indices ------------------------------------------------------------

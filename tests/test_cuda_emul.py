@@ -739,3 +739,79 @@ def test_modules_and_autograd_in_16bit_modes_on_emulated_kernels(tc_ops_on_emula
         ri, rw = cpu.spconv_bwd(feat, w, pair, g.numpy())
         assert rel(out.features.detach().numpy(), ref) < tol
         assert rel(f.grad.numpy(), ri) < tol and rel(conv.weight.grad.numpy(), rw) < 1e-5
+
+
+# --------------------------------------------------------------------------------------
+# the spconv-2.x functional boundary (msmdfusion_b200/spconv_v2_api.py): the reference's OWN patched
+# convolution module (bug_fix/conv.py), compiled from its source in place, runs on the two mirrored functions
+# --------------------------------------------------------------------------------------
+def _reference_sparse_convolution():
+    import contextlib
+    import math
+    import sys
+    import time
+    from typing import List, Optional, Tuple, Union
+    import torch
+    from torch import nn
+    from torch.nn import init
+    from torch.nn.init import calculate_gain
+    from torch.nn.parameter import Parameter
+    from msmdfusion_b200 import spconv, spconv_v2_api as api
+    from oracle.ref_inplace import load_def
+    ns = dict(math=math, time=time, sys=sys, np=np, torch=torch, nn=nn, init=init, Parameter=Parameter,
+              calculate_gain=calculate_gain, List=List, Optional=Optional, Tuple=Tuple, Union=Union,
+              SparseModule=spconv.SparseModule, SparseConvTensor=spconv.SparseConvTensor, expand_nd=spconv.expand_nd,
+              IndiceData=spconv.IndiceData, ImplicitGemmIndiceData=api.ImplicitGemmIndiceData, ConvAlgo=api.ConvAlgo,
+              ops=api.ops, Fsp=api.Fsp, CPU_ONLY_BUILD=False, FILTER_HWIO=False, nullcontext=contextlib.nullcontext,
+              spconv_save_debug_data=lambda *a, **k: None)
+    return load_def('bug_fix/conv.py', 'SparseConvolution', ns, keyword='class')
+
+
+@pytest.mark.skipif(not os.path.isdir('/root/reference/bug_fix'), reason='reference tree not mounted')
+def test_reference_conv_module_runs_on_the_v2_functional_boundary(tc_ops_on_emulator):
+    """bug_fix/conv.py:SparseConvolution (the module the reference tells users to copy over spconv's) with
+    ``ops.get_indice_pairs_implicit_gemm`` / ``Fsp.implicit_gemm`` resolved to msmdfusion_b200.spconv_v2_api:
+    forward (SubM with a shared indice_key, strided) and gradients equal this package's own modules / the oracle;
+    the 9-tuple has spconv's structure."""
+    import torch
+    from msmdfusion_b200 import spconv, spconv_v2_api as api
+    Ref = _reference_sparse_convolution()
+    shape, cin, cout = [7, 12, 12], 8, 16
+    idx, feat = random_sparse(21, 1, shape, 260, cin)
+    ti, tf = torch.from_numpy(idx), torch.from_numpy(feat)
+    # the tuple itself
+    res = api.get_indice_pairs_implicit_gemm(ti, 1, shape, api.ConvAlgo.MaskImplicitGemm, [3, 3, 3], [2, 2, 2], [1, 1, 1],
+                                             [1, 1, 1], [0, 0, 0], subm=False, transpose=False, is_train=True)
+    oi, pair, _ = cpu.conv_rulebook(idx, shape, 3, 2, 1, 1)
+    assert len(res) == 9 and np.array_equal(res[0].numpy(), oi) and np.array_equal(res[2].numpy(), pair)
+    assert np.array_equal(res[1].numpy(), (pair >= 0).sum(1)) and np.array_equal(res[3].numpy(), cpu.pair_transpose(pair, 260))
+    m = res[4][0].numpy().astype(np.int64) & 0xFFFFFFFF
+    assert np.array_equal(m, ((pair >= 0).astype(np.int64) << np.arange(27)[:, None]).sum(0))
+    assert np.array_equal(np.sort(res[6][0].numpy()), np.arange(pair.shape[1])) and res[8][0].dtype == np.uint32
+    sub = api.get_indice_pairs_implicit_gemm(ti, 1, shape, api.ConvAlgo.MaskImplicitGemm, 3, 1, 1, 1, 0, subm=True,
+                                             is_train=False)
+    assert sub[0] is ti and sub[3].numel() == 0 and np.array_equal(sub[2].numpy(), cpu.subm_rulebook(idx, shape, 3, 1))
+    # the reference module on top of it
+    for subm in (True, False):
+        torch.manual_seed(0)
+        kw = dict(padding=1) if subm else dict(stride=2, padding=1)
+        ref = Ref(3, cin, cout, 3, bias=False, subm=subm, indice_key='k' if subm else None, **kw)
+        ours = (spconv.SubMConv3d if subm else spconv.SparseConv3d)(cin, cout, 3, bias=False, **kw)
+        assert ref.weight.shape == ours.weight.shape
+        with torch.no_grad():
+            ours.weight.copy_(ref.weight)
+            a = ref(spconv.SparseConvTensor(tf, ti, shape, 1))
+            b = ours(spconv.SparseConvTensor(tf, ti, shape, 1))
+            assert torch.equal(a.indices, b.indices) and a.spatial_shape == b.spatial_shape
+            assert rel(a.features.numpy(), b.features.numpy()) < 1e-6
+            if subm:   # the stored ImplicitGemmIndiceData is reused by a second layer with the same key
+                ref2 = Ref(3, cout, cout, 3, bias=False, subm=True, indice_key='k', padding=1)
+                c = ref2(a)
+                assert c.indice_dict['k'] is a.indice_dict['k'] and c.features.shape == (260, cout)
+        f = tf.clone().requires_grad_(True)
+        out = ref(spconv.SparseConvTensor(f, ti, shape, 1))
+        g = torch.randn(out.features.shape, generator=torch.Generator().manual_seed(1))
+        (out.features * g).sum().backward()
+        pr = cpu.subm_rulebook(idx, shape, 3, 1) if subm else pair
+        ri, rw = cpu.spconv_bwd(feat, ref.weight.detach().numpy(), pr, g.numpy())
+        assert rel(f.grad.numpy(), ri) < 1e-5 and rel(ref.weight.grad.numpy(), rw) < 1e-5
