@@ -296,12 +296,22 @@ def run_ours(args, rank, world, device):
     launches0 = _cabi.lib().msmd_launch_count()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     sync_all()
+    if trainer is not None:
+        trainer.exchange_events = []
     for s, e in ev:
         flush.zero_()
         s.record()
         spatial, feats = step(pts_dev)
         e.record()
     sync_all()
+    exchange = None
+    if trainer is not None:
+        ex_ms, ex_n = trainer.exchange_ms()
+        trainer.exchange_events = None
+        exchange = {'all_reduce_ms_per_step': round(ex_ms / max(ex_n, 1), 4), 'steps': ex_n,
+                    'gradient_bytes': int(trainer.grads.flat.numel() * 4),
+                    'note': 'one NCCL all-reduce of the flat fp32 gradient buffer, issued on the compute stream after '
+                            'the backward pass: its duration is its exposed time (no-op at 1 GPU)'}
     launches = _cabi.lib().msmd_launch_count() - launches0
     ms1 = torch.cuda.memory_stats(device)
     alloc_diag = {k: int(ms1.get(k, 0) - ms0.get(k, 0)) for k in
@@ -417,7 +427,7 @@ def run_ours(args, rank, world, device):
             roof = dict(bound='hbm', achieved=round(gbs, 2), peak=hbm, unit='GB/s', frac=round(gbs / hbm, 4),
                         **common)
     n_vox = int(feats[0].indices.shape[0])
-    return dict(dev_ms=dev_ms, e2e_ms=e2e_ms, launches=int(launches), clocks=clk, roofline=roof, settle_steps=settle_steps,
+    return dict(dev_ms=dev_ms, e2e_ms=e2e_ms, launches=int(launches), exchange=exchange, clocks=clk, roofline=roof, settle_steps=settle_steps,
                 e2e_step_ms=dict(min=round(min(e2e_raw), 4), median=round(sorted(e2e_raw)[len(e2e_raw) // 2], 4),
                                  max=round(max(e2e_raw), 4), all=[round(x, 2) for x in e2e_raw[:32]]),
                 alloc=alloc_diag,
@@ -536,6 +546,8 @@ def main():
         'roofline': res['roofline'],
         'cpu_baseline': cpu_base,
     }
+    if res.get('exchange') is not None:   # --workload train: the exchange step of SURVEY 8(e)
+        line['gradient_exchange'] = res['exchange']
     print(json.dumps(line))
     return 0
 

@@ -80,6 +80,9 @@ class VoxelSpaceTrainStep:
         self.lr, self.weight_decay, self.grad_clip = lr, weight_decay, grad_clip
         self.grads = None
         self.opt = None
+        # when a list, every step appends (start, end) CUDA events around the gradient exchange: the all-reduce is
+        # issued on the compute stream after the backward pass, so its duration IS its exposed time
+        self.exchange_events = None
 
     def _probe(self, loss):
         """First step: see which parameters the step reaches, then lay out the flat buffer."""
@@ -91,6 +94,11 @@ class VoxelSpaceTrainStep:
             p.grad.copy_(g)
         self.opt = torch.optim.AdamW(used, lr=self.lr, weight_decay=self.weight_decay,
                                      fused=used[0].is_cuda)
+
+    def exchange_ms(self):
+        """Sum of the recorded gradient-exchange durations (call after a synchronize); clears the list."""
+        ev, self.exchange_events = self.exchange_events or [], []
+        return sum(a.elapsed_time(b) for a, b in ev), len(ev)
 
     def forward_loss(self, points, img_feats, img_metas):
         bev, self.last_stage_outs = self.det.extract_voxel_space(points, img_feats, img_metas)
@@ -111,7 +119,14 @@ class VoxelSpaceTrainStep:
                 loss.backward()
         finally:
             spconv.CONV_PRECISION = saved
+        timed = self.exchange_events is not None and self.grads.flat.is_cuda
+        if timed:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
         self.grads.all_reduce_mean()
+        if timed:
+            e1.record()
+            self.exchange_events.append((e0, e1))
         self.grads.clip_(self.grad_clip)
         self.opt.step()
         return loss.detach()
