@@ -232,3 +232,29 @@ def test_tc_trace_summary_on_fabricated_record():
     assert abs(d['mma_wait'] - 0.5) < 1e-9 and abs(d['prod0_wait'] - 0.1) < 1e-9 and abs(d['prod0_fill'] - 0.35) < 1e-9
     assert abs(d['b_lead_us'] - 0.2) < 1e-9 and abs(d['setup_us'] - 1.0) < 1e-9 and abs(d['wall_us'] - 14.0) < 1e-9
     assert 'mma_wait_weights' not in d
+
+
+def test_quick_gpu_check_restatements_agree_with_the_oracle():
+    """tools/quick_gpu_check.py (torch-free GPU smoke): its numpy restatements of the rulebook, the convolution,
+    the weight gradient and the mirrored-weight data gradient against the oracle."""
+    import importlib.util
+    from oracle import cpu
+    spec = importlib.util.spec_from_file_location('quick_gpu_check', os.path.join(ROOT, 'tools', 'quick_gpu_check.py'))
+    Q = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(Q)
+    rng = np.random.default_rng(0)
+    shape, n, cin, cout = [9, 40, 40], 800, 8, 12
+    lin = rng.choice(9 * 1600, size=n, replace=False)
+    idx = np.stack([lin * 0, lin // 1600, (lin // 40) % 40, lin % 40], 1).astype(np.int32)
+    pair = Q.subm_pairs(idx, shape)
+    assert np.array_equal(pair, cpu.subm_rulebook(idx, shape, 3, 1))
+    feat = rng.standard_normal((n, cin)).astype(np.float32)
+    w = (rng.standard_normal((cout, 27, cin)) * 0.2).astype(np.float32)
+    go = rng.standard_normal((n, cout)).astype(np.float32)
+    w5 = w.reshape(cout, 3, 3, 3, cin)
+    assert Q.rel(cpu.spconv_fwd(feat, w5, pair), Q.conv_ref(feat, w, pair)) < 1e-6
+    gi, gw = cpu.spconv_bwd(feat, w5, pair, go)
+    assert Q.rel(gw.reshape(cout, 27, cin), Q.wgrad_ref(feat, go, pair, cout, cin)) < 1e-6
+    wt = np.ascontiguousarray(w[:, ::-1, :].transpose(2, 1, 0))
+    assert Q.rel(gi, Q.conv_ref(go, wt, pair)) < 1e-6
+    assert np.array_equal(Q.bf16_round(np.float32([1.0, 1.00390625, 3.1415927])), np.float32([1.0, 1.0, 3.140625]))

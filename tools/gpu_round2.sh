@@ -5,6 +5,9 @@
 set -u
 mkdir -p gpurun_out
 O=gpurun_out
+# 0. torch-free smoke of the late-round-1 kernels (2 s): if this fails, read it before anything else
+timeout 60 python tools/quick_gpu_check.py --out $O/r02a_quick_check.json > $O/r02a_quick_check.txt 2>&1
+echo "quick check exit $?" | tee -a $O/r02a_summary.txt
 # 1. the forward-path suite first (must stay green), then the new backward / mask-sort tests on their own
 timeout 900 python -m pytest tests -m gpu -x -q --deselect tests/test_zz_train_gpu.py > $O/r02a_pytest_forward.log 2>&1
 echo "forward suite exit $?" | tee -a $O/r02a_summary.txt
