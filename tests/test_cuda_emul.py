@@ -815,3 +815,111 @@ def test_reference_conv_module_runs_on_the_v2_functional_boundary(tc_ops_on_emul
         pr = cpu.subm_rulebook(idx, shape, 3, 1) if subm else pair
         ri, rw = cpu.spconv_bwd(feat, ref.weight.detach().numpy(), pr, g.numpy())
         assert rel(f.grad.numpy(), ri) < 1e-5 and rel(ref.weight.grad.numpy(), rw) < 1e-5
+
+
+# --------------------------------------------------------------------------------------
+# the NATIVE EXECUTOR (csrc/executor.cu) on the emulator, driven by the real Python plan builder: bit grids,
+# rulebooks, mask sort, SIMT / tensor-core convolutions, arena, activation descriptors -- in the three
+# configurations whose integration has not run on hardware (default is GPU-verified and calibrates)
+# --------------------------------------------------------------------------------------
+_EXEC = None
+
+
+def exec_emu():
+    global _EXEC
+    if _EXEC is None:
+        spec = importlib.util.spec_from_file_location('emul_build', os.path.join(HERE, 'tools', 'cuda_emul', 'build.py'))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        _EXEC = ctypes.CDLL(mod.build_exec())
+        _EXEC.emu_last_error.restype = ctypes.c_char_p
+    return _EXEC
+
+
+class _ExecLib:
+    """``_cabi.lib()`` look-alike over the emulated executor library (all units in one image)."""
+
+    def __init__(self, cabi):
+        self._cabi, self._cache = cabi, {}
+
+    def msmd_last_error(self):
+        return exec_emu().emu_last_error()
+
+    def __getattr__(self, name):
+        fn = self._cache.get(name)
+        if fn is None:
+            fn = getattr(exec_emu(), 'emu_' + name)
+            fn.restype, fn.argtypes = self._cabi.SIGNATURES[name]
+            self._cache[name] = fn
+        return fn
+
+
+@pytest.fixture()
+def executor_on_emulator(monkeypatch):
+    import torch
+    from msmdfusion_b200 import _cabi, executor, ops
+    shim = _ExecLib(_cabi)
+
+    def ptr(t):
+        if t is None:
+            return None
+        assert t.is_contiguous()
+        return ctypes.c_void_p(t.data_ptr())
+
+    class Scratch:
+        def get(self, device, nbytes, slot='ws'):
+            return torch.empty(max(int(nbytes), 16), dtype=torch.uint8)
+    for mod in (_cabi, ops, executor):
+        monkeypatch.setattr(mod, 'lib', lambda: shim)
+        monkeypatch.setattr(mod, 'ptr', ptr)
+        monkeypatch.setattr(mod, 'stream', lambda device=None: None)
+    for mod in (_cabi, ops):
+        monkeypatch.setattr(mod, 'scratch', Scratch())
+    yield shim
+    shim.msmd_spconv_set_mask_sort(0)
+
+
+def test_native_executor_on_emulator(executor_on_emulator, monkeypatch):
+    """A SparseEncoder (basic blocks: SubM chains with residuals, three strided convs, conv_out) through
+    executor.SparseNetPlan -> msmd_sparse_net_forward, all kernels emulated, against the oracle's encoder:
+    bf16x3 on mask-sorted tiles -- the integration that has not run on hardware (MSMD_EMUL_FULL=1 adds the default
+    configuration, which is GPU-verified, and the two single switches; all four pass)."""
+    import torch
+    import msmdfusion_b200 as m
+    from msmdfusion_b200 import ops, spconv
+    from oracle import model as omodel
+    sys_path_fix = os.path.join(HERE)
+    if sys_path_fix not in __import__('sys').path:
+        __import__('sys').path.insert(0, sys_path_fix)
+    from _fixtures import randomize_bn
+    cfg = dict(type='SparseEncoder', in_channels=5, sparse_shape=[17, 48, 48], output_channels=32, order=('conv', 'norm', 'act'),
+               encoder_channels=((16, 16, 32), (32, 32, 48), (48, 48, 112), (112, 112)),   # 112: variant 3 (N >= 96)
+               encoder_paddings=((0, 0, 1), (0, 0, 1), (0, 0, [0, 1, 1]), (0, 0)), block_type='basicblock')
+    torch.manual_seed(0)
+    enc = m.registry.build_middle_encoder(dict(cfg)).eval()
+    randomize_bn(enc, 1)
+    idx, feat = random_sparse(2, 2, [17, 48, 48], 700, 5)
+    ref_sp, ref_feats, _ = omodel.sparse_encoder(enc.state_dict(), dict(cfg), feat, idx, 2)
+    tf, ti = torch.from_numpy(feat), torch.from_numpy(idx)
+
+    def run():
+        enc._plan = None
+        plan, marks = enc._plan_for()
+        with torch.no_grad():
+            acts = plan.run(tf, ti, enc.sparse_shape, 2)
+        return [acts[i] for i in marks]
+
+    configs = [(1, 'bf16x3', 1e-4)]
+    if os.environ.get('MSMD_EMUL_FULL'):   # all four combinations (~3 min); the default one is GPU-verified
+        configs += [(0, 'tf32x3', 1e-5), (1, 'tf32x3', 1e-5), (0, 'bf16x3', 1e-4)]
+    for mask_sort, precision, tol in configs:
+        executor_on_emulator.msmd_spconv_set_mask_sort(mask_sort)
+        monkeypatch.setattr(spconv, 'CONV_PRECISION', precision)
+        outs = run()
+        assert {L['weight_tc'] for L in enc._plan[1].layers} == {ops.TC_MODES[precision]}
+        for (f, ix, shape), r in zip(outs[:-1], ref_feats):
+            assert np.array_equal(ix.numpy(), r.indices) and list(shape) == list(r.spatial_shape)
+            assert rel(f.numpy(), r.features) < tol, (mask_sort, precision)
+        f, ix, shape = outs[-1]
+        dense = cpu.dense(ix.numpy(), f.numpy(), shape, 2)
+        assert rel(dense.reshape(ref_sp.shape), ref_sp) < tol

@@ -202,6 +202,41 @@ extern "C" int emu_msmd_spconv_bwd_weight_tc_supported(int, int, int);
     return lib
 
 
+def build_exec(verbose=False):
+    """Host-emulated native executor (csrc/executor.cu) with everything it calls: the bit-grid / rulebook
+    kernels, the mask sort, the SIMT and tensor-core convolutions -- one library, entry points emu_msmd_*."""
+    os.makedirs(OUT, exist_ok=True)
+    lib = os.path.join(OUT, 'libmsmd_exec_emul.so')
+    units = ['spconv.cu', 'rulebook.cu', 'fusion.cu', 'spconv_tc.cu', 'spconv_tc16.cu', 'executor.cu']
+    header = os.path.join(ROOT, 'include', 'msmd_b200.h')
+    deps = [os.path.join(CSRC, f) for f in units + ['common.cuh', 'tc_common.cuh', 'tc_trace.cuh', 'scan.cuh', 'sort.cuh']] + \
+        [header, os.path.join(HERE, 'cuda_emul.h'), os.path.join(HERE, 'tc_emul.h'), os.path.abspath(__file__)]
+    if os.path.exists(lib) and all(os.path.getmtime(lib) > os.path.getmtime(d) for d in deps):
+        return lib
+    _INLINED.clear()
+    _INLINED.add('tc.cuh')
+    body = ''
+    for u in units:
+        body += _rewrite_launches(_inline_headers(open(os.path.join(CSRC, u)).read()))
+    _INLINED.clear()
+    body, n = re.subn(r'extern __shared__ uint8_t (\w+)\[\];', r'uint8_t* \1 = ::emu::g_dyn_smem;', body)
+    assert n >= 3
+    text = '#undef MSMD_API\n' + open(header).read() + _device_helpers() + body
+    # every C-ABI name (declarations of the header, definitions, calls) gets the emu_ prefix
+    text = re.sub(r'(?<![\w])msmd_(\w+)\(', r'emu_msmd_\1(', text)
+    text = '#define MSMD_EMUL_WITH_HEADER 1\n' + PRELUDE + TC_PRELUDE + text
+    cpp = os.path.join(OUT, 'emul_exec_unit.cpp')
+    with open(cpp, 'w') as f:
+        f.write(text)
+    cmd = ['g++', '-std=c++20', '-O2', '-g', '-ffp-contract=off', '-Wno-unknown-pragmas', '-shared', '-fPIC',
+           '-pthread', '-I', HERE, cpp, '-o', lib]
+    if verbose:
+        print(' '.join(cmd))
+    subprocess.check_call(cmd)
+    return lib
+
+
 if __name__ == '__main__':
+    print(build_exec(verbose=True))
     print(build_tc(verbose=True))
     print(build(verbose=True))

@@ -38,6 +38,7 @@ static inline float4 make_float4(float x, float y, float z, float w) { return fl
 
 typedef void* cudaStream_t;
 typedef void* msmd_stream_t;
+typedef void* cudaEvent_t;
 typedef int cudaError_t;
 static const cudaError_t cudaSuccess = 0;
 static inline cudaError_t cudaGetLastError() { return 0; }
@@ -47,7 +48,21 @@ static inline cudaError_t cudaMemsetAsync(void* p, int v, size_t n, cudaStream_t
   return 0;
 }
 
+#ifndef MSMD_EMUL_WITH_HEADER   // units that paste include/msmd_b200.h get the status codes from it
 enum { MSMD_OK = 0, MSMD_ERR_INVALID = -1, MSMD_ERR_CUDA = -2, MSMD_ERR_WORKSPACE = -3 };
+#endif
+// streams and events: the emulation is synchronous, every launch has completed when it returns
+enum { cudaStreamNonBlocking = 1, cudaEventDisableTiming = 2, cudaMemcpyDeviceToHost = 2, cudaMemcpyHostToDevice = 1 };
+static inline cudaError_t cudaGetDevice(int* d) { *d = 0; return 0; }
+static inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { *s = (void*)0x5; return 0; }
+static inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) { *e = (void*)0xE; return 0; }
+static inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return 0; }
+static inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned) { return 0; }
+static inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return 0; }
+static inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, int, cudaStream_t) {
+  memcpy(d, s, n);
+  return 0;
+}
 
 namespace emu {
 extern thread_local dim3 t_threadIdx, t_blockIdx;
