@@ -213,6 +213,17 @@ MSMD_API int msmd_spconv_fwd_tc16(const float* features, int n_in, const void* p
                                   const int* pair_fwd, const int* row_perm, int n_out, int cin, int cout,
                                   int kvol, int x3, const float* scale, const float* shift,
                                   const float* residual, int relu, float* out, msmd_stream_t stream);
+/* Kernel variant of the 16-bit modes: 2 (default) = A operand in shared memory; 3 = A operand in TENSOR memory
+ * (two K elements per 32-bit column), weights-only shared memory => two CTAs per SM at Cout >= 96, plus the split-K
+ * CTA pairs of msmd_spconv_fwd_tc_ws (scratch: msmd_spconv_tc16_workspace bytes, 0 = no split).  Variant 3's TMEM
+ * operand layout is taken from the PTX ISA text; it is checked on the host model only (MSMD_TC16_VARIANT=3). */
+MSMD_API int msmd_spconv_tc16_set_variant(int variant);
+MSMD_API size_t msmd_spconv_tc16_workspace(int n_out, int cout);
+MSMD_API int msmd_spconv_fwd_tc16_ws(const float* features, int n_in, const void* packed_tc16,
+                                     const int* pair_fwd, const int* row_perm, int n_out, int cin, int cout,
+                                     int kvol, int x3, const float* scale, const float* shift,
+                                     const float* residual, int relu, float* out, void* workspace,
+                                     size_t workspace_bytes, msmd_stream_t stream);
 
 /* ------------------------------------------------------------------------------------
  * Sparse convolution BACKWARD (config 5, the train step) -- replaces the backward of

@@ -65,6 +65,10 @@ SIGNATURES = {
     'msmd_spconv_tc16_packed_bytes': (_sz, [_i, _i, _i, _i]),
     'msmd_spconv_tc16_pack_weight': (_i, [_vp, _i, _i, _i, _i, _vp, _vp]),
     'msmd_spconv_fwd_tc16': (_i, [_vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _vp]),
+    'msmd_spconv_tc16_set_variant': (_i, [_i]),
+    'msmd_spconv_tc16_workspace': (_sz, [_i, _i]),
+    'msmd_spconv_fwd_tc16_ws': (_i, [_vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _sz,
+                                    _vp]),
     'msmd_rulebook_mask_sort_workspace': (_sz, [_i]),
     'msmd_rulebook_mask_sort': (_i, [_vp, _i, _i, _vp, _vp, _vp, _sz, _vp]),
     'msmd_spconv_fwd_tc_sorted': (_i, [_vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _vp,
@@ -127,6 +131,9 @@ def lib():
                 name, _, val = item.partition('=')
                 if L.msmd_spconv_tc_set_tuning({'occ': 0, 'stages': 1, 'split': 2}[name.strip()], int(val)) != 0:
                     raise RuntimeError('bad MSMD_TC_TUNE')
+        if os.environ.get('MSMD_TC16_VARIANT'):  # 16-bit modes: 2 = A via shared memory (default), 3 = A via tensor memory
+            if L.msmd_spconv_tc16_set_variant(int(os.environ['MSMD_TC16_VARIANT'])) != 0:
+                raise RuntimeError('bad MSMD_TC16_VARIANT')
         if os.environ.get('MSMD_TC_VARIANT'):  # A/B switch of the tensor-core conv kernel (2 | 3)
             if L.msmd_spconv_tc_set_variant(int(os.environ['MSMD_TC_VARIANT'])) != 0:
                 raise RuntimeError('bad MSMD_TC_VARIANT')

@@ -256,10 +256,16 @@ extern "C" MSMD_API int msmd_sparse_net_forward(const msmd_conv_layer* layers, i
         waited_seq = rb.seq;
       }
       if (L.weight_tc == 2 || L.weight_tc == 3) {  // 16-bit operand kernels: bf16x3 / bf16
-        MSMD_TRY(msmd_spconv_fwd_tc16(in.features, in.n, L.weight, rb.pair_sorted ? rb.pair_sorted : rb.pair,
-                                      rb.pair_sorted ? rb.row_perm : nullptr, n_out, L.cin, L.cout, kvol,
-                                      L.weight_tc == 2, L.scale, L.shift, residual, L.relu, out,
-                                      (msmd_stream_t)stream));
+        const size_t ws_bytes = msmd_spconv_tc16_workspace(n_out, L.cout);  // variant 3: split-K hand-off buffer
+        char* ws = nullptr;
+        if (ws_bytes) {
+          MSMD_ARENA(w, char, ws_bytes);
+          ws = w;
+        }
+        MSMD_TRY(msmd_spconv_fwd_tc16_ws(in.features, in.n, L.weight, rb.pair_sorted ? rb.pair_sorted : rb.pair,
+                                         rb.pair_sorted ? rb.row_perm : nullptr, n_out, L.cin, L.cout, kvol,
+                                         L.weight_tc == 2, L.scale, L.shift, residual, L.relu, out, ws, ws_bytes,
+                                         (msmd_stream_t)stream));
       } else if (L.weight_tc) {
         const size_t ws_bytes = msmd_spconv_tc_workspace(n_out, L.cout);  // split-K hand-off buffer
         char* ws = nullptr;

@@ -221,6 +221,11 @@ def set_wgrad_tc(enable):
     check(lib().msmd_spconv_set_wgrad_tc(int(bool(enable))), 'msmd_spconv_set_wgrad_tc')
 
 
+def set_tc16_variant(variant):
+    """16-bit operand modes: 2 (default) = A operand in shared memory, 3 = A operand in tensor memory."""
+    check(lib().msmd_spconv_tc16_set_variant(int(variant)), 'msmd_spconv_tc16_set_variant')
+
+
 def set_tc_variant(variant):
     """0 (default): chosen by Cout; 3: A operand staged in tensor memory; 2: A operand in shared memory."""
     check(lib().msmd_spconv_tc_set_variant(int(variant)), 'msmd_spconv_tc_set_variant')
@@ -296,11 +301,14 @@ def spconv_fwd_tc(features, tcw, pair_fwd, scale=None, shift=None, residual=None
             assert row_perm.dtype == torch.int32 and row_perm.shape[0] == n_out
             row_perm = row_perm.contiguous()
         if tcw.mode != 1:   # 16-bit operand kernels (bf16x3 / bf16)
-            check(lib().msmd_spconv_fwd_tc16(ptr(features), features.shape[0], ptr(tcw.packed), ptr(pair_fwd),
-                                             ptr(row_perm), n_out, tcw.cin, tcw.cout, tcw.kvol,
-                                             int(tcw.mode == 2), ptr(scale), ptr(shift), ptr(residual),
-                                             int(bool(relu)), ptr(out), stream(features.device)),
-                  'msmd_spconv_fwd_tc16')
+            need = lib().msmd_spconv_tc16_workspace(n_out, tcw.cout)   # > 0: variant 3 with split-K pairs
+            ws = scratch.get(features.device, need, slot='tc_ws') if need else None
+            check(lib().msmd_spconv_fwd_tc16_ws(ptr(features), features.shape[0], ptr(tcw.packed), ptr(pair_fwd),
+                                                ptr(row_perm), n_out, tcw.cin, tcw.cout, tcw.kvol,
+                                                int(tcw.mode == 2), ptr(scale), ptr(shift), ptr(residual),
+                                                int(bool(relu)), ptr(out), ptr(ws),
+                                                ws.numel() if ws is not None else 0, stream(features.device)),
+                  'msmd_spconv_fwd_tc16_ws')
             return out
         need = lib().msmd_spconv_tc_workspace(n_out, tcw.cout)  # > 0: split-K pairs (tail balance)
         ws = scratch.get(features.device, need, slot='tc_ws') if need else None

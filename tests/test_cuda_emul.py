@@ -49,6 +49,7 @@ def tc_emu():
         _TC.emu_msmd_spconv_tc_workspace.restype = ctypes.c_size_t
         _TC.emu_msmd_spconv_tc16_packed_bytes.restype = ctypes.c_size_t
         _TC.emu_msmd_spconv_bwd_weight_tc_workspace.restype = ctypes.c_size_t
+        _TC.emu_msmd_spconv_tc16_workspace.restype = ctypes.c_size_t
     return _TC
 
 
@@ -532,8 +533,10 @@ def bf16_round(x):
     return u.astype(np.uint32).view(np.float32).reshape(np.shape(x))
 
 
-def tc16_fwd(feat, w, pair, x3, scale=None, shift=None, residual=None, relu=0, row_perm=None):
+def tc16_fwd(feat, w, pair, x3, scale=None, shift=None, residual=None, relu=0, row_perm=None, variant=2, split=False):
     L = tc_emu()
+    if variant != 2 or split:
+        return _tc16_fwd_v3(feat, w, pair, x3, scale, shift, residual, relu, row_perm, variant, split)
     cout, cin = w.shape[0], w.shape[-1]
     kvol, n_out = pair.shape
     packed = np.full(L.emu_msmd_spconv_tc16_packed_bytes(cout, kvol, cin, x3) // 2, 0x7FC0, np.uint16)  # NaN fill
@@ -923,3 +926,56 @@ def test_native_executor_on_emulator(executor_on_emulator, monkeypatch):
         f, ix, shape = outs[-1]
         dense = cpu.dense(ix.numpy(), f.numpy(), shape, 2)
         assert rel(dense.reshape(ref_sp.shape), ref_sp) < tol
+
+
+# --------------------------------------------------------------------------------------
+# 16-bit modes, variant 3: A operand in TENSOR memory (two K elements per 32-bit column) + split-K pairs
+# --------------------------------------------------------------------------------------
+def _tc16_fwd_v3(feat, w, pair, x3, scale, shift, residual, relu, row_perm, variant, split):
+    L = tc_emu()
+    cout, cin = w.shape[0], w.shape[-1]
+    kvol, n_out = pair.shape
+    packed = np.full(L.emu_msmd_spconv_tc16_packed_bytes(cout, kvol, cin, x3) // 2, 0x7FC0, np.uint16)
+    assert L.emu_msmd_spconv_tc16_pack_weight(P(w), cout, kvol, cin, x3, P(packed), None) == 0, L.emu_last_error()
+    out = np.full((n_out, cout), np.nan, np.float32)
+    assert L.emu_msmd_spconv_tc16_set_variant(variant) == 0
+    try:
+        need = L.emu_msmd_spconv_tc16_workspace(n_out, cout) if split else 0
+        assert (need > 0) == bool(split)
+        ws = np.zeros(need // 4 + 64, np.float32) if need else None
+        st = L.emu_msmd_spconv_fwd_tc16_ws(P(feat), feat.shape[0], P(packed), P(pair), P(row_perm), n_out, cin, cout,
+                                           kvol, x3, P(scale), P(shift), P(residual), relu, P(out), P(ws),
+                                           ctypes.c_size_t(need), None)
+    finally:
+        L.emu_msmd_spconv_tc16_set_variant(2)
+    assert st == 0, L.emu_last_error()
+    return out
+
+
+@pytest.mark.parametrize('x3', [0, 1])
+@pytest.mark.parametrize('cin,cout,n,split', [(16, 16, 300, False),    # three A stages (N <= 64), vector gather
+                                              (5, 24, 200, False),     # scalar gather, padded N
+                                              (20, 144, 150, False),   # N = 144, two A stages
+                                              (32, 128, 200, True)])   # split-K CTA pairs + hand-off
+def test_tc16_variant3_on_emulator(x3, cin, cout, n, split):
+    """spconv_fwd_tc16t_kernel on the host model (16-bit A operand in tensor memory: element 2c in the low half
+    of column c): same results as variant 2 of the same mode; epilogue, mask-sorted table."""
+    shape = [5, 12, 12]
+    idx, feat = random_sparse(0, 1, shape, n, cin)
+    rng = np.random.default_rng(1)
+    w = (rng.standard_normal((cout, 3, 3, 3, cin)) * 0.2).astype(np.float32)
+    pair = cpu.subm_rulebook(idx, shape, 3, 1)
+    if x3:
+        ref, tol = cpu.spconv_fwd(feat, w, pair), 2e-5
+    else:
+        ref, tol = cpu.spconv_fwd(bf16_round(feat), bf16_round(w), pair), 2e-6
+    got = tc16_fwd(feat, w, pair, x3, variant=3, split=split)
+    assert rel(got, ref) < tol
+    assert rel(got, tc16_fwd(feat, w, pair, x3)) < 2e-6       # variant 2 of the same mode
+    scale = rng.uniform(0.5, 1.5, cout).astype(np.float32)
+    shift = rng.standard_normal(cout).astype(np.float32)
+    res = rng.standard_normal(ref.shape).astype(np.float32)
+    perm = rng.permutation(n).astype(np.int32)      # any permutation is a valid slot -> row map
+    got = tc16_fwd(feat, w, np.ascontiguousarray(pair[:, perm]), x3, scale, shift, res, 1, row_perm=perm, variant=3,
+                   split=split)
+    assert rel(got, np.maximum(ref * scale + shift + res, 0)) < tol

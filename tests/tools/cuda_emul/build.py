@@ -189,6 +189,7 @@ extern "C" int emu_msmd_spconv_fwd_tc_ws(const float*, int, const float*, const 
                                          const float*, const float*, int, float*, void*, size_t, msmd_stream_t);
 extern "C" size_t emu_msmd_spconv_tc_workspace(int, int);
 extern "C" int emu_msmd_spconv_bwd_weight_tc_supported(int, int, int);
+extern "C" size_t emu_msmd_spconv_tc16_workspace(int, int);
 '''   # declared by include/msmd_b200.h in the real build
     text = PRELUDE + TC_PRELUDE + _device_helpers() + fwd_decl + unit
     cpp = os.path.join(OUT, 'emul_tc_unit.cpp')

@@ -448,13 +448,13 @@ static inline void mma_commit(uint64_t* bar) {
   ::emu::g_tc_cv.notify_all();   // a waiter re-evaluates (and thereby runs the queue up to here)
 }
 
-static inline void tmem_lane_rule(uint32_t taddr, const char* what) {
+static inline void tmem_lane_rule(uint32_t taddr, const char* what, uint32_t ncols = 16) {
   const int tid = ::emu::emu_lin_tid();
   const uint32_t lane0 = taddr >> 16;
   if (lane0 != (uint32_t)(((tid >> 5) & 3) * 32))
     ::emu::tc_fail("%s: warp %d may only touch TMEM lanes %d.., address names lane %u", what, tid >> 5,
                    ((tid >> 5) & 3) * 32, lane0);
-  if ((taddr & 0xFFFF) + 16 > ::emu::g_tmem_next) ::emu::tc_fail("%s: columns exceed the allocation", what);
+  if ((taddr & 0xFFFF) + ncols > ::emu::g_tmem_next) ::emu::tc_fail("%s: columns exceed the allocation", what);
 }
 static inline void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
   tmem_lane_rule(taddr, "tcgen05.ld");
@@ -466,6 +466,11 @@ static inline void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
   tmem_lane_rule(taddr, "tcgen05.st");
   const int lane = (int)(taddr >> 16) + (::emu::emu_lin_tid() & 31);
   for (int i = 0; i < 16; ++i) ::emu::g_tmem[lane][(taddr & 0xFFFF) + i] = v[i];
+}
+static inline void tmem_st8(uint32_t taddr, const uint32_t (&v)[8]) {
+  tmem_lane_rule(taddr, "tcgen05.st", 8);
+  const int lane = (int)(taddr >> 16) + (::emu::emu_lin_tid() & 31);
+  for (int i = 0; i < 8; ++i) ::emu::g_tmem[lane][(taddr & 0xFFFF) + i] = v[i];
 }
 static inline void tmem_st_wait() {}
 
