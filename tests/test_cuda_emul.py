@@ -896,12 +896,12 @@ def test_native_executor_on_emulator(executor_on_emulator, monkeypatch):
         __import__('sys').path.insert(0, sys_path_fix)
     from _fixtures import randomize_bn
     cfg = dict(type='SparseEncoder', in_channels=5, sparse_shape=[17, 48, 48], output_channels=32, order=('conv', 'norm', 'act'),
-               encoder_channels=((16, 16, 32), (32, 32, 48), (48, 48, 112), (112, 112)),   # 112: variant 3 (N >= 96)
+               encoder_channels=((16, 16, 32), (32, 32, 32), (32, 32, 64), (64, 64)),
                encoder_paddings=((0, 0, 1), (0, 0, 1), (0, 0, [0, 1, 1]), (0, 0)), block_type='basicblock')
     torch.manual_seed(0)
     enc = m.registry.build_middle_encoder(dict(cfg)).eval()
     randomize_bn(enc, 1)
-    idx, feat = random_sparse(2, 2, [17, 48, 48], 700, 5)
+    idx, feat = random_sparse(2, 2, [17, 48, 48], 450, 5)
     ref_sp, ref_feats, _ = omodel.sparse_encoder(enc.state_dict(), dict(cfg), feat, idx, 2)
     tf, ti = torch.from_numpy(feat), torch.from_numpy(idx)
 
