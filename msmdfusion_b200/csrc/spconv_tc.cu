@@ -611,7 +611,7 @@ extern "C" MSMD_API int msmd_tc_trace_record_words(void) { return kTrRecord; }
 int msmd::g_tc_tune[4] = {0, 0, 0, 0};
 
 extern "C" MSMD_API int msmd_spconv_tc_set_tuning(int key, int value) {
-  MSMD_REQUIRE(key >= 0 && key < 4, "spconv_tc_set_tuning: key must be 0 (occupancy), 1 (stage cap) or 2 (split-K)");
+  MSMD_REQUIRE(key >= 0 && key < 4, "spconv_tc_set_tuning: key must be 0 (occupancy), 1 (stage cap), 2 (split-K) or 3 (chunks per stage)");
   g_tc_tune[key] = value;
   return MSMD_OK;
 }

@@ -38,9 +38,10 @@ struct T16Layout {
   int stage_bytes, stages, pair_off, act_off, bar_off, total;
 };
 
-static T16Layout t16_layout(int N, int kvol, int chunks, int tiles, int images) {
+static T16Layout t16_layout(int N, int kvol, int chunks, int tiles, int images, int cps = 1) {
   T16Layout L;
-  L.stage_bytes = images * (kT16ABytes + N * 128);  // A hi [| A lo] | B hi [| B lo], all 1024-B aligned
+  // one chunk block = A hi [| A lo] | B hi [| B lo], all 1024-B aligned; a stage holds `cps` of them
+  L.stage_bytes = cps * images * (kT16ABytes + N * 128);
   const int misc = round_up(kvol * kTcM * 4, 16) + round_up(2 * chunks, 16) + 256 + 8 * N;
   const int budget = tc_smem_budget(2 * L.stage_bytes + misc + 1024 <= 112 * 1024, tiles);  // half: two CTAs per SM
   L.stages = (budget - misc - 1024) / L.stage_bytes;
@@ -56,7 +57,7 @@ template <bool VEC, bool X3>
 __global__ void __launch_bounds__(kTcThreads)
 spconv_fwd_tc16_kernel(const float* __restrict__ feat, const uint16_t* __restrict__ wpk,
                        const int* __restrict__ pair, int n_out, int cin, int cin_pad, int cout, int N,
-                       int kvol, int chunks, int stages, int stage_bytes, int pair_off, int act_off,
+                       int kvol, int chunks, int stages, int stage_bytes, int cps, int pair_off, int act_off,
                        int bar_off, int tmem_cols, const float* __restrict__ scale,
                        const float* __restrict__ shift, const float* __restrict__ residual, int relu,
                        float* __restrict__ out, int cat, const int* __restrict__ row_perm) {
@@ -76,6 +77,8 @@ spconv_fwd_tc16_kernel(const float* __restrict__ feat, const uint16_t* __restric
     ss[N + c] = (shift && c < cout) ? __ldg(shift + c) : 0.f;
   }
   constexpr int kImages = X3 ? 2 : 1;
+  // a pipeline stage holds `cps` (1 or 2) chunk blocks: one mbarrier round trip per cps * 64 K elements
+  const int chunk_bytes = stage_bytes / cps;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int row0 = blockIdx.x * kTcM;
@@ -155,14 +158,15 @@ spconv_fwd_tc16_kernel(const float* __restrict__ feat, const uint16_t* __restric
     const int tr_role = warp == 0 ? 0 : (warp == kTcProducerWarps - 1 ? 1 : -1);  // traced gather warps
     (void)tr_role;
     auto store = [&](int t, const float4 (&v)[RPT]) {
-      const int it = t >> 1, h = t & 1;
+      const int ci = t >> 1, h = t & 1;       // chunk of the active list, half of the chunk
+      const int it = ci / cps, c = ci - it * cps;  // stage use (group of cps chunks), slot inside the stage
       const int s = it % stages;
-      if (h == 0) {
+      if (h == 0 && c == 0) {
         if (lane == 0) TC_TRACE(tr_role, it, 0);
         mbar_wait_warp(&empty_bar[s], ((uint32_t)(it / stages) & 1u) ^ 1u, lane);
         if (lane == 0) TC_TRACE(tr_role, it, 1);
       }
-      const uint32_t a_hi = tc::smem_u32(smem + (size_t)s * stage_bytes);
+      const uint32_t a_hi = tc::smem_u32(smem + (size_t)s * stage_bytes + (size_t)c * chunk_bytes);
       const uint32_t a_lo = a_hi + kT16ABytes;
       const int unit = 4 * h + (p >> 1);
 #pragma unroll
@@ -177,7 +181,7 @@ spconv_fwd_tc16_kernel(const float* __restrict__ feat, const uint16_t* __restric
           tc::st_shared_v2_b32(a_lo + off, tc::pack_bf16x2(lx, ly), tc::pack_bf16x2(lz, lw));
         }
       }
-      if (h == 1) {  // the chunk is complete
+      if (h == 1 && (c == cps - 1 || ci == n_act - 1)) {  // the stage's chunks are complete
         tc::fence_proxy_async();  // every lane: its generic-proxy stores -> async proxy
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(&full_bar[s]);
@@ -207,16 +211,18 @@ spconv_fwd_tc16_kernel(const float* __restrict__ feat, const uint16_t* __restric
     // ===== B loader: one bulk copy (hi [+ lo] image of the chunk) per active chunk ==============
     if (lane == 0) {
       const uint32_t bytes = (uint32_t)(kImages * N * 128);
-      for (int it = 0; it < n_act; ++it) {
-        const int j = alist[it];
+      const int n_groups = (n_act + cps - 1) / cps;
+      for (int it = 0; it < n_groups; ++it) {
+        const int cnt = min(cps, n_act - it * cps);
         const int s = it % stages;
         const uint32_t ph = (uint32_t)(it / stages) & 1u;
         TC_TRACE(2, it, 0);
         tc::mbar_wait(&empty_bar[s], ph ^ 1u);
         TC_TRACE(2, it, 1);
-        tc::mbar_arrive_expect_tx(&full_bar[s], bytes);
-        tc::bulk_g2s(smem + (size_t)s * stage_bytes + kImages * kT16ABytes,
-                     (const uint8_t*)wpk + (size_t)j * bytes, bytes, &full_bar[s]);
+        tc::mbar_arrive_expect_tx(&full_bar[s], bytes * (uint32_t)cnt);
+        for (int c = 0; c < cnt; ++c)
+          tc::bulk_g2s(smem + (size_t)s * stage_bytes + (size_t)c * chunk_bytes + kImages * kT16ABytes,
+                       (const uint8_t*)wpk + (size_t)alist[it * cps + c] * bytes, bytes, &full_bar[s]);
       }
     }
   } else {
@@ -225,37 +231,41 @@ spconv_fwd_tc16_kernel(const float* __restrict__ feat, const uint16_t* __restric
       const uint32_t idesc = tc::idesc_f32acc(tc::kFmtBF16, kTcM, N);
       const uint32_t idesc2 = tc::idesc_f32acc(tc::kFmtBF16, kTcM, 2 * N);
       uint32_t accumulate = 0;
-      for (int it = 0; it < n_act; ++it) {
+      const int n_groups = (n_act + cps - 1) / cps;
+      for (int it = 0; it < n_groups; ++it) {
+        const int cnt = min(cps, n_act - it * cps);
         const int s = it % stages;
         const uint32_t ph = (uint32_t)(it / stages) & 1u;
         TC_TRACE(3, it, 0);
         tc::mbar_wait(&full_bar[s], ph);
         TC_TRACE(3, it, 1);
         tc::fence_after_sync();
-        const uint32_t a_hi = tc::smem_u32(smem + (size_t)s * stage_bytes);
-        const uint32_t a_lo = a_hi + kT16ABytes;
-        const uint32_t b_hi = a_hi + kImages * kT16ABytes;
-        const uint32_t b_lo = b_hi + (uint32_t)N * 128u;
+        for (int c = 0; c < cnt; ++c) {
+          const uint32_t a_hi = tc::smem_u32(smem + (size_t)s * stage_bytes + (size_t)c * chunk_bytes);
+          const uint32_t a_lo = a_hi + kT16ABytes;
+          const uint32_t b_hi = a_hi + kImages * kT16ABytes;
+          const uint32_t b_lo = b_hi + (uint32_t)N * 128u;
 #pragma unroll
-        for (int ks = 0; ks < kT16KC / 16; ++ks) {
-          const uint32_t koff = (uint32_t)ks * 32u;  // 16 bf16 = 32 bytes along K
-          const uint64_t dah = tc::desc_k_sw128(a_hi + koff), dbh = tc::desc_k_sw128(b_hi + koff);
-          if (!X3) {
-            tc::mma_f16(tmem_base, dah, dbh, idesc, accumulate);
-          } else {
-            const uint64_t dal = tc::desc_k_sw128(a_lo + koff), dbl = tc::desc_k_sw128(b_lo + koff);
-            if (cat) {
-              // B_hi and B_lo are adjacent in the stage = ONE K-major operand of 2N rows:
-              //   D[:, 0:2N] += A_hi * [B_hi; B_lo]      D[:, 0:N] += A_lo * B_hi
-              tc::mma_f16(tmem_base, dah, dbh, idesc2, accumulate);
-              tc::mma_f16(tmem_base, dal, dbh, idesc, 1u);
+          for (int ks = 0; ks < kT16KC / 16; ++ks) {
+            const uint32_t koff = (uint32_t)ks * 32u;  // 16 bf16 = 32 bytes along K
+            const uint64_t dah = tc::desc_k_sw128(a_hi + koff), dbh = tc::desc_k_sw128(b_hi + koff);
+            if (!X3) {
+              tc::mma_f16(tmem_base, dah, dbh, idesc, accumulate);
             } else {
-              tc::mma_f16(tmem_base, dal, dbh, idesc, accumulate);  // small terms first
-              tc::mma_f16(tmem_base, dah, dbl, idesc, 1u);
-              tc::mma_f16(tmem_base, dah, dbh, idesc, 1u);
+              const uint64_t dal = tc::desc_k_sw128(a_lo + koff), dbl = tc::desc_k_sw128(b_lo + koff);
+              if (cat) {
+                // B_hi and B_lo are adjacent in the chunk block = ONE K-major operand of 2N rows:
+                //   D[:, 0:2N] += A_hi * [B_hi; B_lo]      D[:, 0:N] += A_lo * B_hi
+                tc::mma_f16(tmem_base, dah, dbh, idesc2, accumulate);
+                tc::mma_f16(tmem_base, dal, dbh, idesc, 1u);
+              } else {
+                tc::mma_f16(tmem_base, dal, dbh, idesc, accumulate);  // small terms first
+                tc::mma_f16(tmem_base, dah, dbl, idesc, 1u);
+                tc::mma_f16(tmem_base, dah, dbh, idesc, 1u);
+              }
             }
+            accumulate = 1u;
           }
-          accumulate = 1u;
         }
         tc::mma_commit(&empty_bar[s]);  // frees the stage once these MMAs have read it
         TC_TRACE(3, it, 2);
@@ -717,7 +727,13 @@ extern "C" MSMD_API int msmd_spconv_fwd_tc16_ws(const float* features, int n_in,
                          residual, relu, out, workspace, workspace_bytes, stream);
   const int tiles = ceil_div(n_out, kTcM);
   const int images = x3 ? 2 : 1;
-  const T16Layout L = t16_layout(g.N, kvol, g.chunks, tiles, images);
+  // A/B switch [3]: two chunk blocks per pipeline stage (half the mbarrier round trips) when two such stages fit
+  int cps = 1;
+  T16Layout L = t16_layout(g.N, kvol, g.chunks, tiles, images, 1);
+  if (g_tc_tune[3] == 2) {
+    const T16Layout L2 = t16_layout(g.N, kvol, g.chunks, tiles, images, 2);
+    if (L2.stages >= 2) { L = L2; cps = 2; }
+  }
   MSMD_REQUIRE(L.stages >= 2, "spconv_fwd_tc16: tile does not fit in shared memory");
   auto kern = x3 ? (vec ? spconv_fwd_tc16_kernel<true, true> : spconv_fwd_tc16_kernel<false, true>)
                  : (vec ? spconv_fwd_tc16_kernel<true, false> : spconv_fwd_tc16_kernel<false, false>);
@@ -731,7 +747,7 @@ extern "C" MSMD_API int msmd_spconv_fwd_tc16_ws(const float* features, int n_in,
   int tmem_cols = 32;
   while (tmem_cols < (cat ? 2 * g.N : g.N)) tmem_cols <<= 1;
   tc_launch(kern, tiles, kTcThreads, L.total, stream, features, (const uint16_t*)packed_tc16, pair_fwd, n_out, cin,
-                                               g.cin_pad, cout, g.N, kvol, g.chunks, L.stages, L.stage_bytes,
+                                               g.cin_pad, cout, g.N, kvol, g.chunks, L.stages, L.stage_bytes, cps,
                                                L.pair_off, L.act_off, L.bar_off, tmem_cols, scale, shift,
                                                residual, relu, out, cat, row_perm);
   MSMD_LAUNCH_OK();

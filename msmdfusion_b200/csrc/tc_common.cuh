@@ -19,6 +19,7 @@ static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 //   [0] occupancy  0 auto | 1 one CTA per SM (whole shared memory, deeper pipeline) | 2 two CTAs per SM when they fit
 //   [1] stage cap  2..4 (default 4)
 //   [2] split-K    0 auto | 1 never | 2 whenever the kernel supports it
+//   [3] chunk blocks per pipeline stage of the 16-bit kernel (variant 2): 0/1 one | 2 two (half the hand-offs)
 extern int g_tc_tune[4];
 // shared-memory budget of one CTA: `fits_half` = two pipeline stages fit in half of the SM
 static inline int tc_smem_budget(bool fits_half, int tiles) {

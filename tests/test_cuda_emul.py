@@ -952,11 +952,11 @@ def _tc16_fwd_v3(feat, w, pair, x3, scale, shift, residual, relu, row_perm, vari
     return out
 
 
-@pytest.mark.parametrize('x3', [0, 1])
-@pytest.mark.parametrize('cin,cout,n,split', [(16, 16, 300, False),    # three A stages (N <= 64), vector gather
-                                              (5, 24, 200, False),     # scalar gather, padded N
-                                              (20, 144, 150, False),   # N = 144, two A stages
-                                              (32, 128, 200, True)])   # split-K CTA pairs + hand-off
+@pytest.mark.parametrize('x3,cin,cout,n,split', [(1, 16, 16, 300, False),    # three A stages (N <= 64), vector gather
+                                                 (0, 5, 24, 200, False),     # scalar gather, padded N, bf16
+                                                 (1, 20, 144, 150, False),   # N = 144, two A stages
+                                                 (1, 32, 128, 200, True),    # split-K CTA pairs + hand-off
+                                                 (0, 32, 128, 200, True)])
 def test_tc16_variant3_on_emulator(x3, cin, cout, n, split):
     """spconv_fwd_tc16t_kernel on the host model (16-bit A operand in tensor memory: element 2c in the low half
     of column c): same results as variant 2 of the same mode; epilogue, mask-sorted table."""
@@ -979,3 +979,30 @@ def test_tc16_variant3_on_emulator(x3, cin, cout, n, split):
     got = tc16_fwd(feat, w, np.ascontiguousarray(pair[:, perm]), x3, scale, shift, res, 1, row_perm=perm, variant=3,
                    split=split)
     assert rel(got, np.maximum(ref * scale + shift + res, 0)) < tol
+
+
+@pytest.mark.parametrize('x3', [0, 1])
+@pytest.mark.parametrize('cin,cout,n', [(16, 16, 300),    # 7 chunks: the last stage holds one chunk block only
+                                        (20, 80, 150)])   # three-MMA x3 mode (2N > 256 is not needed: cat off at N > 128)
+def test_tc16_two_chunk_blocks_per_stage_on_emulator(x3, cin, cout, n):
+    """A/B switch [3] = 2 (MSMD_TC_TUNE=cps=2): a pipeline stage of the 16-bit kernel holds two chunk blocks --
+    half the mbarrier round trips per K element; bit-identical to one block per stage (same MMA order)."""
+    L = tc_emu()
+    shape = [5, 12, 12]
+    idx, feat = random_sparse(0, 1, shape, n, cin)
+    rng = np.random.default_rng(1)
+    w = (rng.standard_normal((cout, 3, 3, 3, cin)) * 0.2).astype(np.float32)
+    pair = cpu.subm_rulebook(idx, shape, 3, 1)
+    pair[3:9, : n // 2] = -1          # some tiles skip chunks: odd / even active counts both occur
+    scale = rng.uniform(0.5, 1.5, cout).astype(np.float32)
+    shift = rng.standard_normal(cout).astype(np.float32)
+    res = rng.standard_normal((n, cout)).astype(np.float32)
+    one = tc16_fwd(feat, w, pair, x3, scale, shift, res, 1)
+    assert L.emu_msmd_spconv_tc_set_tuning(3, 2) == 0
+    try:
+        two = tc16_fwd(feat, w, pair, x3, scale, shift, res, 1)
+    finally:
+        L.emu_msmd_spconv_tc_set_tuning(3, 0)
+    assert np.array_equal(one, two)
+    ref = cpu.spconv_fwd(feat, w, pair) if x3 else cpu.spconv_fwd(bf16_round(feat), bf16_round(w), pair)
+    assert rel(two, np.maximum(ref * scale + shift + res, 0)) < (2e-5 if x3 else 2e-6)
