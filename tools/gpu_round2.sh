@@ -24,6 +24,8 @@ head -n 30 $O/r02a_tc_trace_S.txt
 timeout 300 python bench.py --steps 100 --warmup 30 --precision bf16x3 --no-cpu-baseline > $O/r02a_bench_S_bf16x3.json 2>$O/r02a_bench_S_bf16x3.err
 MSMD_MASK_SORT=1 timeout 300 python bench.py --steps 100 --warmup 30 --precision bf16x3 --no-cpu-baseline > $O/r02a_bench_S_bf16x3_masksort.json 2>&1
 MSMD_TC16_VARIANT=3 timeout 300 python bench.py --steps 100 --warmup 30 --precision bf16x3 --no-cpu-baseline > $O/r02a_bench_S_bf16x3_v3.json 2>&1   # only meaningful if the quick check's variant-3 lines say ok
+MSMD_TC_TUNE=cps=2 timeout 300 python bench.py --steps 100 --warmup 30 --precision bf16x3 --no-cpu-baseline > $O/r02a_bench_S_bf16x3_cps2.json 2>&1
+MSMD_TC_TUNE=cps=2 MSMD_MASK_SORT=1 timeout 300 python bench.py --steps 100 --warmup 30 --precision bf16x3 --no-cpu-baseline > $O/r02a_bench_S_bf16x3_cps2_masksort.json 2>&1
 timeout 300 python bench.py --profile L --steps 50 --warmup 10 --precision bf16x3 --no-cpu-baseline > $O/r02a_bench_L_bf16x3.json 2>&1
 timeout 300 python bench.py --workload LC --steps 30 --warmup 10 --precision bf16x3 --no-cpu-baseline > $O/r02a_bench_LC_bf16x3.json 2>&1
 # programmatic dependent launch of the conv chain (debug build, same ABI): A/B against the default line
@@ -39,7 +41,7 @@ timeout 300 python bench.py --profile L --steps 50 --warmup 10 --no-cpu-baseline
 timeout 300 python bench.py --workload LC --steps 30 --warmup 10 --no-cpu-baseline > $O/r02a_bench_LC.json 2>&1
 MSMD_MASK_SORT=1 timeout 300 python bench.py --workload LC --steps 30 --warmup 10 --no-cpu-baseline > $O/r02a_bench_LC_masksort.json 2>&1
 timeout 300 python bench.py --workload train --steps 20 --warmup 5 --no-cpu-baseline --breakdown $O/r02a_breakdown_train.json > $O/r02a_bench_train.json 2>$O/r02a_bench_train.err
-for f in S S_masksort S_bf16x3 S_bf16x3_masksort S_bf16x3_v3 S_pdl S_batch2 S_batch4 L L_masksort L_bf16x3 LC LC_masksort LC_bf16x3 train train_wgradtc train_bf16_wgradtc; do
+for f in S S_masksort S_bf16x3 S_bf16x3_masksort S_bf16x3_cps2 S_bf16x3_cps2_masksort S_bf16x3_v3 S_pdl S_batch2 S_batch4 L L_masksort L_bf16x3 LC LC_masksort LC_bf16x3 train train_wgradtc train_bf16_wgradtc; do
   echo "== $f"; tail -c 600 $O/r02a_bench_$f.json | python -c "import sys,json
 try:
     d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print(d.get('value'), d.get('ms_per_step'), (d.get('e2e') or {}).get('value'))
