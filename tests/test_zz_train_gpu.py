@@ -483,3 +483,51 @@ def test_tc16_variant3_equals_variant2(mode, cin, cout):
     finally:
         ops.set_tc16_variant(2)
     assert err(b, a) < 1e-5
+
+
+# --------------------------------------------------------------------------------------
+# the late-round-1 kernels at BASELINE.json's full size (10-sweep scene, > 100 k voxels): size-independent
+# properties -- agreement between independent kernels, linearity, adjointness, determinism
+# --------------------------------------------------------------------------------------
+def test_full_size_16bit_modes_mask_sort_and_tc_wgrad_properties():
+    cfg = m.Config.fromfile(os.path.join(ROOT, 'configs', 'msmd_lc_hotpath.py')).hotpath
+    layer = m.Voxelization(**cfg.pts_voxel_layer).eval()
+    mean, coors, num = layer.forward_mean(cuda(synthetic.lidar_scene(123, 10)), 5, batch_idx=0)
+    n = coors.shape[0]
+    assert n > 100000
+    shape = [41, 1440, 1440]
+    grid = ops.grid_build(coors, 1, shape)
+    pair = ops.rulebook_subm(coors, grid, [3, 3, 3], 1)
+    row_perm, pair_sorted = ops.rulebook_mask_sort(pair)
+    assert torch.equal(torch.sort(row_perm.long()).values, torch.arange(n, device=dev()))
+    cin, cout = 64, 64
+    g = torch.Generator().manual_seed(3)
+    x1 = torch.randn(n, cin, generator=g).to(dev())
+    x2 = torch.randn(n, cin, generator=g).to(dev())
+    w = (torch.randn(cout, 3, 3, 3, cin, generator=g) / (cin * 27 * 0.2) ** 0.5).to(dev())
+    w32 = ops.pack_weight_tc(w, 1)
+    y32 = ops.spconv_fwd_tc(x1, w32, pair)
+    # mask-sorted tiles at full size: same rows, same values (no split-K at this tile count)
+    assert torch.equal(ops.spconv_fwd_tc(x1, w32, pair_sorted, row_perm=row_perm), y32)
+    for mode, tol in (('bf16x3', 2e-5), ('bf16', 1e-2)):
+        tcw = ops.pack_weight_tc(w, ops.TC_MODES[mode])
+        y = ops.spconv_fwd_tc(x1, tcw, pair)
+        assert err(y, y32) < tol                                             # agreement with the 3xTF32 kernel
+        assert torch.equal(ops.spconv_fwd_tc(x1, tcw, pair_sorted, row_perm=row_perm), y)
+        assert torch.equal(ops.spconv_fwd_tc(x1, tcw, pair), y)              # determinism
+        if mode == 'bf16x3':                                                 # linearity survives the hi/lo split
+            lhs = ops.spconv_fwd_tc(2.5 * x1 - 0.75 * x2, tcw, pair)
+            assert err(lhs, 2.5 * y - 0.75 * ops.spconv_fwd_tc(x2, tcw, pair)) < 1e-4
+    # weight gradient: tensor-core kernel against the exact-fp32 one; <dY, conv(X; W)> = <dW, W> (bilinear form)
+    go = torch.randn(n, cout, generator=g).to(dev())
+    simt = ops.spconv_bwd_weight(x1, go, pair, tuple(w.shape))
+    try:
+        ops.set_wgrad_tc(True)
+        tcg = ops.spconv_bwd_weight(x1, go, pair, tuple(w.shape))
+        tcg2 = ops.spconv_bwd_weight(x1, go, pair, tuple(w.shape))
+    finally:
+        ops.set_wgrad_tc(False)
+    assert err(tcg, simt) < TOL and torch.equal(tcg, tcg2)
+    lhs = float((go.double() * y32.double()).sum())
+    rhs = float((tcg.double() * w.double()).sum())
+    assert abs(lhs - rhs) < 1e-4 * max(1.0, abs(lhs))
