@@ -530,4 +530,5 @@ def test_full_size_16bit_modes_mask_sort_and_tc_wgrad_properties():
     assert err(tcg, simt) < TOL and torch.equal(tcg, tcg2)
     lhs = float((go.double() * y32.double()).sum())
     rhs = float((tcg.double() * w.double()).sum())
-    assert abs(lhs - rhs) < 1e-4 * max(1.0, abs(lhs))
+    scale = float((go.abs().double() * y32.abs().double()).sum())       # both sides are sums of ~7 M signed terms
+    assert abs(lhs - rhs) < 1e-6 * scale
