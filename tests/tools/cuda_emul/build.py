@@ -95,8 +95,10 @@ PRELUDE = '''#include "cuda_emul.h"
 namespace emu {
 thread_local dim3 t_threadIdx, t_blockIdx;
 dim3 g_blockDim, g_gridDim;
-std::barrier<>* g_block_barrier = nullptr;
-std::vector<WarpBox> g_warps;
+thread_local WarpCtx* t_warp = nullptr;
+thread_local int t_lane = 0;
+BlockSync g_bsync;
+std::function<void()>* g_body = nullptr;
 char g_error[512];
 std::atomic<int> g_or{0};
 uint8_t* g_dyn_smem = nullptr;

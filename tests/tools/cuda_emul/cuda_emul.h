@@ -1,13 +1,16 @@
 // cuda_emul.h -- TEST INFRASTRUCTURE: a minimal CPU emulation of the CUDA execution model, enough to
 // run this repository's SIMT kernels (tensor-core / bulk-copy code: see tc_emul.h; no cluster code) functionally on the host
-// when no GPU is available.  One std::thread per CUDA thread, thread blocks run one after another,
-// __syncthreads() is a std::barrier, warp shuffles go through a per-warp exchange buffer.  It checks
+// when no GPU is available.  One OS thread per warp whose 32 lanes are cooperative fibers, thread blocks run one
+// after another, barriers are polling loops that yield, warp shuffles go through a per-warp exchange buffer.  It checks
 // indexing, barrier placement and arithmetic order -- not performance, not memory-model races.
 // Used only by tests/test_cuda_emul.py (via tests/tools/cuda_emul/build.py); never by the product.
 #pragma once
 #include <algorithm>
 #include <atomic>
 #include <barrier>
+#include <functional>
+#include <mutex>
+#include <ucontext.h>
 #include <cmath>
 #include <cstdarg>
 #include <cstdint>
@@ -65,14 +68,13 @@ static inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, int,
 }
 
 namespace emu {
+// Execution core: one OS thread per WARP; the 32 lanes of a warp are cooperative fibers (ucontext) that the warp's
+// thread schedules round-robin.  Warp-level synchronisation (__syncwarp, shuffles, ballots) never leaves the thread;
+// block-level barriers and mbarrier / flag waits are polling loops that yield to the next lane, and to the OS when
+// no lane of the warp can make progress.  (The previous core ran one OS thread per CUDA thread: 320 threads per CTA
+// of the tensor-core kernels spent most of their time in futex wake-ups.)
 extern thread_local dim3 t_threadIdx, t_blockIdx;
 extern dim3 g_blockDim, g_gridDim;
-extern std::barrier<>* g_block_barrier;
-struct WarpBox {
-  std::unique_ptr<std::barrier<>> bar;
-  long long slot[32];
-};
-extern std::vector<WarpBox> g_warps;
 extern char g_error[512];
 extern std::atomic<int> g_or;
 // dynamic shared memory + per-CTA hooks (set by tc_emul.h's translation unit; null for the SIMT units)
@@ -80,41 +82,149 @@ extern uint8_t* g_dyn_smem;
 extern void (*g_block_begin)(uint32_t dyn_smem_bytes);
 extern void (*g_block_end)();
 
+constexpr size_t kLaneStack = 256 * 1024;
+struct Lane {
+  ucontext_t ctx;
+  bool done = false;
+  dim3 tidx;
+};
+struct WarpCtx {
+  Lane lanes[32];
+  int nlanes = 0, live = 0;
+  ucontext_t sched;
+  int sync_count = 0;
+  unsigned sync_gen = 0;
+  long long slot[32];
+  int blocked = 0;          // lanes that yielded from a wait since the scheduler last saw progress
+  char* stacks = nullptr;   // nlanes x kLaneStack
+};
+struct BlockSync {
+  std::mutex mu;
+  int count = 0, live = 0;
+  std::atomic<unsigned> gen{0};
+};
+extern thread_local WarpCtx* t_warp;
+extern thread_local int t_lane;
+extern BlockSync g_bsync;
+extern std::function<void()>* g_body;
+
+static inline void lane_yield(bool blocked) {   // back to the warp's scheduler
+  WarpCtx& w = *t_warp;
+  if (blocked) ++w.blocked; else w.blocked = 0;
+  const int me = t_lane;
+  swapcontext(&w.lanes[me].ctx, &w.sched);
+}
+// a wait loop's body: let the other lanes (and, if the whole warp is waiting, the other warps) run
+static inline void blocked_yield() { lane_yield(true); }
+
+static inline void warp_barrier_wait() {
+  WarpCtx& w = *t_warp;
+  const unsigned gen = w.sync_gen;
+  if (++w.sync_count >= w.live) {
+    w.sync_count = 0;
+    ++w.sync_gen;
+    w.blocked = 0;
+    return;
+  }
+  while (w.sync_gen == gen) lane_yield(true);
+}
+static inline void block_barrier_wait() {
+  BlockSync& b = g_bsync;
+  unsigned gen;
+  {
+    std::lock_guard<std::mutex> g(b.mu);
+    gen = b.gen.load();
+    if (++b.count >= b.live) {
+      b.count = 0;
+      b.gen.store(gen + 1);
+      t_warp->blocked = 0;
+      return;
+    }
+  }
+  while (b.gen.load() == gen) lane_yield(true);
+}
+static inline void lane_exit() {   // an exited thread leaves the CTA's barriers (arrive_and_drop)
+  WarpCtx& w = *t_warp;
+  w.lanes[t_lane].done = true;
+  --w.live;
+  if (w.live > 0 && w.sync_count >= w.live) {
+    w.sync_count = 0;
+    ++w.sync_gen;
+  }
+  BlockSync& b = g_bsync;
+  std::lock_guard<std::mutex> g(b.mu);
+  --b.live;
+  if (b.live > 0 && b.count >= b.live) {
+    b.count = 0;
+    b.gen.store(b.gen.load() + 1);
+  }
+}
+static void lane_main() {
+  (*g_body)();
+  lane_exit();
+  t_warp->blocked = 0;
+  // returning resumes uc_link = the scheduler
+}
+
 template <typename F>
 void launch(dim3 grid, dim3 block, size_t dyn_smem_bytes, F body) {
-  // The CTA's threads are created ONCE per launch and walk the grid together (thread blocks run one after
-  // another): two launch-level barriers per CTA instead of nthreads thread creations.
   const unsigned nthreads = block.x * block.y * block.z;
   const unsigned nblocks = grid.x * grid.y * grid.z;
   if (nthreads == 0 || nblocks == 0) return;
+  const unsigned nwarps = (nthreads + 31) / 32;
   g_blockDim = block;
   g_gridDim = grid;
-  std::barrier<> cta_done(nthreads), cta_ready(nthreads);
-  std::unique_ptr<std::barrier<>> bar;
+  std::function<void()> fn = body;
+  g_body = &fn;
+  std::vector<WarpCtx> warps(nwarps);
+  for (unsigned w = 0; w < nwarps; ++w) {
+    warps[w].nlanes = (int)std::min(32u, nthreads - w * 32);
+    warps[w].stacks = (char*)aligned_alloc(4096, kLaneStack * warps[w].nlanes);
+  }
+  std::barrier<> cta_done(nwarps), cta_ready(nwarps);
   auto begin_cta = [&]() {
-    bar.reset(new std::barrier<>(nthreads));
-    g_block_barrier = bar.get();
+    g_bsync.count = 0;
+    g_bsync.live = (int)nthreads;
+    g_bsync.gen.store(0);
     if (g_block_begin) g_block_begin((uint32_t)dyn_smem_bytes);
-    g_warps.clear();
-    g_warps.resize((nthreads + 31) / 32);
-    for (unsigned w = 0; w < g_warps.size(); ++w) {
-      const unsigned lanes = std::min(32u, nthreads - w * 32);
-      g_warps[w].bar.reset(new std::barrier<>(lanes));
-    }
   };
   begin_cta();
   std::vector<std::thread> ts;
-  ts.reserve(nthreads);
-  for (unsigned t = 0; t < nthreads; ++t)
-    ts.emplace_back([&, t]() {
-      t_threadIdx = dim3(t % block.x, (t / block.x) % block.y, t / (block.x * block.y));
+  ts.reserve(nwarps);
+  for (unsigned wi = 0; wi < nwarps; ++wi)
+    ts.emplace_back([&, wi]() {
+      WarpCtx& w = warps[wi];
+      t_warp = &w;
       for (unsigned b = 0; b < nblocks; ++b) {
         t_blockIdx = dim3(b % grid.x, (b / grid.x) % grid.y, b / (grid.x * grid.y));
-        body();
-        g_block_barrier->arrive_and_drop();            // exited threads leave the CTA's barriers
-        g_warps[t / 32].bar->arrive_and_drop();
+        w.live = w.nlanes;
+        w.sync_count = 0;
+        w.blocked = 0;
+        for (int l = 0; l < w.nlanes; ++l) {
+          Lane& L = w.lanes[l];
+          const unsigned t = wi * 32 + (unsigned)l;
+          L.done = false;
+          L.tidx = dim3(t % block.x, (t / block.x) % block.y, t / (block.x * block.y));
+          getcontext(&L.ctx);
+          L.ctx.uc_stack.ss_sp = w.stacks + (size_t)l * kLaneStack;
+          L.ctx.uc_stack.ss_size = kLaneStack;
+          L.ctx.uc_link = &w.sched;
+          makecontext(&L.ctx, (void (*)())lane_main, 0);
+        }
+        while (w.live > 0) {
+          for (int l = 0; l < w.nlanes; ++l) {
+            if (w.lanes[l].done) continue;
+            t_lane = l;
+            t_threadIdx = w.lanes[l].tidx;
+            swapcontext(&w.sched, &w.lanes[l].ctx);
+          }
+          if (w.live > 0 && w.blocked >= w.live) {   // every live lane is waiting on another warp
+            w.blocked = 0;
+            std::this_thread::yield();
+          }
+        }
         cta_done.arrive_and_wait();
-        if (t == 0) {                                  // everyone else is parked between the two barriers
+        if (wi == 0) {                                 // everyone else is parked between the two barriers
           if (g_block_end) g_block_end();
           if (b + 1 < nblocks) begin_cta();
         }
@@ -122,6 +232,8 @@ void launch(dim3 grid, dim3 block, size_t dyn_smem_bytes, F body) {
       }
     });
   for (auto& th : ts) th.join();
+  for (auto& w : warps) free(w.stacks);
+  g_body = nullptr;
 }
 template <typename F>
 void launch(dim3 grid, dim3 block, F body) { launch(grid, block, 0, body); }
@@ -132,15 +244,15 @@ void launch(dim3 grid, dim3 block, F body) { launch(grid, block, 0, body); }
 #define blockDim (::emu::g_blockDim)
 #define gridDim (::emu::g_gridDim)
 
-static inline void __syncthreads() { ::emu::g_block_barrier->arrive_and_wait(); }
+static inline void __syncthreads() { ::emu::block_barrier_wait(); }
 
 static inline int __syncthreads_or(int pred) {
   if (pred) ::emu::g_or.store(1);
-  ::emu::g_block_barrier->arrive_and_wait();
+  ::emu::block_barrier_wait();
   const int r = ::emu::g_or.load();
-  ::emu::g_block_barrier->arrive_and_wait();
+  ::emu::block_barrier_wait();
   if (threadIdx.x == 0 && threadIdx.y == 0 && threadIdx.z == 0) ::emu::g_or.store(0);
-  ::emu::g_block_barrier->arrive_and_wait();
+  ::emu::block_barrier_wait();
   return r;
 }
 using std::max;
@@ -149,16 +261,15 @@ using std::min;
 template <typename T>
 static inline T emu_warp_exchange(T v, int src_lane_of_me, bool take) {
   static_assert(sizeof(T) <= sizeof(long long), "shuffle payload");
-  const unsigned lin = threadIdx.x + threadIdx.y * blockDim.x + threadIdx.z * blockDim.x * blockDim.y;
-  auto& box = ::emu::g_warps[lin / 32];
-  const int lane = lin & 31;
+  auto& box = *::emu::t_warp;
+  const int lane = ::emu::t_lane;
   long long raw = 0;
   memcpy(&raw, &v, sizeof(T));
   box.slot[lane] = raw;
-  box.bar->arrive_and_wait();
+  ::emu::warp_barrier_wait();
   T out = v;
   if (take) memcpy(&out, &box.slot[src_lane_of_me], sizeof(T));
-  box.bar->arrive_and_wait();
+  ::emu::warp_barrier_wait();
   return out;
 }
 template <typename T>
@@ -174,15 +285,14 @@ static inline T __shfl_xor_sync(unsigned, T v, int d) {
 template <typename T>
 static inline unsigned __match_any_sync(unsigned, T v) {
   static_assert(sizeof(T) <= sizeof(long long), "match payload");
-  const unsigned lin = threadIdx.x + threadIdx.y * blockDim.x + threadIdx.z * blockDim.x * blockDim.y;
-  auto& box = ::emu::g_warps[lin / 32];
+  auto& box = *::emu::t_warp;
   long long raw = 0;
   memcpy(&raw, &v, sizeof(T));
-  box.slot[lin & 31] = raw;
-  box.bar->arrive_and_wait();
+  box.slot[::emu::t_lane] = raw;
+  ::emu::warp_barrier_wait();
   unsigned m = 0;
-  for (int l = 0; l < 32; ++l) m |= (box.slot[l] == raw ? 1u : 0u) << l;
-  box.bar->arrive_and_wait();
+  for (int l = 0; l < box.nlanes; ++l) m |= ((!box.lanes[l].done && box.slot[l] == raw) ? 1u : 0u) << l;
+  ::emu::warp_barrier_wait();
   return m;
 }
 static inline unsigned __ballot_sync(unsigned, int pred) {
@@ -213,10 +323,7 @@ static inline T atomicMin(T* p, T v) {
   return old;
 }
 static inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
-static inline void __syncwarp(unsigned = 0xffffffffu) {
-  const unsigned lin = threadIdx.x + threadIdx.y * blockDim.x + threadIdx.z * blockDim.x * blockDim.y;
-  ::emu::g_warps[lin / 32].bar->arrive_and_wait();
-}
+static inline void __syncwarp(unsigned = 0xffffffffu) { ::emu::warp_barrier_wait(); }
 static inline float __fmul_rn(float a, float b) { volatile float r = a * b; return r; }
 static inline float __fadd_rn(float a, float b) { volatile float r = a + b; return r; }
 static inline float __uint_as_float(unsigned u) { float f; memcpy(&f, &u, 4); return f; }

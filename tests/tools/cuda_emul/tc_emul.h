@@ -119,6 +119,9 @@ static inline int emu_lin_tid() {
 }  // namespace emu
 
 static inline long long clock64() {
+  // every bounded spin loop of this code base reads the clock in its body: the one place where a raw polling loop
+  // of kernel code hands control to the other lanes of the cooperative warp
+  if (::emu::t_warp) ::emu::blocked_yield();
   return (long long)std::chrono::duration_cast<std::chrono::nanoseconds>(
              std::chrono::steady_clock::now().time_since_epoch()).count();
 }
@@ -153,7 +156,6 @@ static inline void bar_check(::emu::MBar& b) {
   if (b.pending == 0 && b.tx == 0) {
     b.phase ^= 1u;
     b.pending = (int)b.expected;
-    ::emu::g_tc_cv.notify_all();
   }
 }
 static inline void mbar_init(uint64_t* bar, uint32_t count) {
@@ -212,15 +214,17 @@ static inline bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   return (b.phase & 1u) != (parity & 1u);
 }
 static inline void mbar_wait(uint64_t* bar, uint32_t parity) {
-  std::unique_lock<std::mutex> g(::emu::g_tc_mu);
-  auto& b = bar_at(bar);
-  const uint32_t a = smem_u32(bar);
-  if (!::emu::g_tc_cv.wait_for(g, std::chrono::seconds(30), [&] {
-        async_flush_for(a);
-        return (b.phase & 1u) != (parity & 1u);
-      }))
-    ::emu::tc_fail("deadlock: thread %d waited 30 s on the mbarrier at %u (parity %u, pending %d, tx %lld)",
-                   ::emu::emu_lin_tid(), smem_u32(bar), parity, b.pending, b.tx);
+  const auto t0 = std::chrono::steady_clock::now();
+  for (long spin = 0;; ++spin) {
+    if (mbar_try_wait(bar, parity)) return;
+    ::emu::blocked_yield();
+    if ((spin & 0xFFF) == 0xFFF && std::chrono::steady_clock::now() - t0 > std::chrono::seconds(30)) {
+      std::lock_guard<std::mutex> g(::emu::g_tc_mu);
+      auto& b = bar_at(bar);
+      ::emu::tc_fail("deadlock: thread %d waited 30 s on the mbarrier at %u (parity %u, pending %d, tx %lld)",
+                     ::emu::emu_lin_tid(), smem_u32(bar), parity, b.pending, b.tx);
+    }
+  }
 }
 static inline void fence_proxy_async() {}
 
@@ -243,7 +247,6 @@ static inline void bulk_g2s(void* dst_smem, const void* src, uint32_t bytes, uin
   op.tx = bytes;
   op.run = [dst, src, bytes] { memcpy(dst, src, bytes); };
   ::emu::g_copy_queue.push_back(std::move(op));
-  ::emu::g_tc_cv.notify_all();   // a waiter re-evaluates (and thereby completes the copy)
 }
 
 // ---- TMEM -----------------------------------------------------------------------------
@@ -445,7 +448,6 @@ static inline void mma_commit(uint64_t* bar) {
   op.kind = 1;
   op.bar = smem_u32(bar);
   ::emu::g_mma_queue.push_back(std::move(op));
-  ::emu::g_tc_cv.notify_all();   // a waiter re-evaluates (and thereby runs the queue up to here)
 }
 
 static inline void tmem_lane_rule(uint32_t taddr, const char* what, uint32_t ncols = 16) {
@@ -500,17 +502,27 @@ static inline void st_shared_v4_b32(uint32_t addr, uint32_t a, uint32_t b, uint3
 }
 
 static inline void named_bar_sync(int id, int nthreads) {
-  std::unique_lock<std::mutex> g(::emu::g_tc_mu);
-  auto& b = ::emu::g_named[id];
-  const unsigned gen = b.gen;
-  if (++b.count == nthreads) {
-    b.count = 0;
-    ++b.gen;
-    ::emu::g_tc_cv.notify_all();
-    return;
+  unsigned gen;
+  {
+    std::lock_guard<std::mutex> g(::emu::g_tc_mu);
+    auto& b = ::emu::g_named[id];
+    gen = b.gen;
+    if (++b.count == nthreads) {
+      b.count = 0;
+      ++b.gen;
+      return;
+    }
   }
-  if (!::emu::g_tc_cv.wait_for(g, std::chrono::seconds(30), [&] { return b.gen != gen; }))
-    ::emu::tc_fail("deadlock: named barrier %d (%d threads) not reached by everyone", id, nthreads);
+  const auto t0 = std::chrono::steady_clock::now();
+  for (long spin = 0;; ++spin) {
+    {
+      std::lock_guard<std::mutex> g(::emu::g_tc_mu);
+      if (::emu::g_named[id].gen != gen) return;
+    }
+    ::emu::blocked_yield();
+    if ((spin & 0xFFF) == 0xFFF && std::chrono::steady_clock::now() - t0 > std::chrono::seconds(30))
+      ::emu::tc_fail("deadlock: named barrier %d (%d threads) not reached by everyone", id, nthreads);
+  }
 }
 
 static inline float round_tf32(float x) {  // cvt.rna.tf32.f32: nearest, ties away from zero
