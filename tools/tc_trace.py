@@ -38,10 +38,11 @@ def summarize(rec, mhz):
         if r[0] == 0 or r[5] == 0:
             continue
         n_act = int(r[7])
-        n = min(n_act, ITS)
         ev = r[HEAD:].reshape(ROLES, ITS, PHASES).astype(np.float64)
+        # pipeline steps actually traced: one per chunk, or per group of chunks (MSMD_TC_TUNE cps=2), at most ITS
+        n = int(np.count_nonzero(ev[3, :, 2]))
         cyc = 1.0 / mhz  # microseconds per cycle
-        d = dict(cta=int(r[8]), sm=int(r[6]), n_act=n_act, setup_us=(r[1] - r[0]) * cyc,
+        d = dict(cta=int(r[8]), sm=int(r[6]), n_act=n_act, steps=n, setup_us=(r[1] - r[0]) * cyc,
                  total_us=(r[5] - r[0]) * cyc, wall_us=(int(r[10]) - int(r[9])) * 1e-3)
         if r[2] and r[4]:
             d['epilogue_us'] = (r[4] - r[2]) * cyc
