@@ -20,6 +20,9 @@ timeout 300 python tools/tc_trace.py --precision bf16x3 --json $O/r02a_tc_trace_
 timeout 300 python tools/tc_trace.py --mask-sort --json $O/r02a_tc_trace_S_masksort.json > $O/r02a_tc_trace_S_masksort.txt 2>&1
 timeout 300 python tools/tc_trace.py --sweeps 10 --json $O/r02a_tc_trace_L.json > $O/r02a_tc_trace_L.txt 2>&1
 head -n 30 $O/r02a_tc_trace_S.txt
+# 1c. every prepared configuration of the conv kernel, per layer of both profiles (the table that decides defaults)
+timeout 600 python tools/autotune_conv.py --json $O/r02a_autotune.json > $O/r02a_autotune.txt 2>&1
+tail -n 45 $O/r02a_autotune.txt
 # 2. bench lines: default, mask-sorted, 16-bit operand modes, LC, LC mask-sorted, train step (fp32 / bf16 / tc wgrad)
 timeout 300 python bench.py --steps 100 --warmup 30 --precision bf16x3 --no-cpu-baseline > $O/r02a_bench_S_bf16x3.json 2>$O/r02a_bench_S_bf16x3.err
 MSMD_MASK_SORT=1 timeout 300 python bench.py --steps 100 --warmup 30 --precision bf16x3 --no-cpu-baseline > $O/r02a_bench_S_bf16x3_masksort.json 2>&1
