@@ -19,9 +19,82 @@ def _build_oracle():
     build.build_port()
 
 
+EMULATE = os.environ.get('MSMD_EMULATE', '0') not in ('', '0')
+# MSMD_EMULATE=1: run the `-m gpu` tests on the CPU emulation of the CUDA kernels (tests/tools/cuda_emul: every
+# translation unit except the thread-block-cluster kernels of points.cu).  Test infrastructure for sessions without
+# GPU time: it checks the PYTHON side of the GPU tests (wrappers, modules, autograd, the tests' own code) and the
+# kernels' logic; it is not a substitute for the hardware run.  tests/tools/run_gpu_tests_on_emulator.py picks the
+# tests that fit (no FPS / ball query, no full-size scenes).
+
+
+class _EmuLibrary:
+    """``_cabi.lib()`` look-alike over the emulated image: msmd_X -> emu_msmd_X with _cabi's own signatures."""
+
+    def __init__(self, cabi, cdll):
+        self._cabi, self._cdll, self._cache = cabi, cdll, {}
+
+    def __getattr__(self, name):
+        fn = self._cache.get(name)
+        if fn is None:
+            fn = getattr(self._cdll, 'emu_' + name)
+            fn.restype, fn.argtypes = self._cabi.SIGNATURES[name]
+            self._cache[name] = fn
+        return fn
+
+
+@pytest.fixture(scope='session', autouse=True)
+def _emulated_library():
+    if not EMULATE:
+        yield None
+        return
+    import ctypes
+    import importlib.util
+    import torch
+    from msmdfusion_b200 import _cabi, executor, ops
+    spec = importlib.util.spec_from_file_location('emul_build', os.path.join(ROOT, 'tests', 'tools', 'cuda_emul', 'build.py'))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    cdll = ctypes.CDLL(mod.build_full())
+    cdll.emu_msmd_last_error.restype = ctypes.c_char_p
+    shim = _EmuLibrary(_cabi, cdll)
+
+    def ptr(t):
+        if t is None:
+            return None
+        assert t.is_contiguous()
+        return ctypes.c_void_p(t.data_ptr())
+
+    class Scratch:
+        def get(self, device, nbytes, slot='ws'):
+            return torch.empty(max(int(nbytes), 16), dtype=torch.uint8)
+
+    saved = []
+    for m_ in (_cabi, ops, executor):
+        for name, val in (('lib', lambda: shim), ('ptr', ptr), ('stream', lambda device=None: None)):
+            if hasattr(m_, name):
+                saved.append((m_, name, getattr(m_, name)))
+                setattr(m_, name, val)
+    for m_ in (_cabi, ops):
+        saved.append((m_, 'scratch', m_.scratch))
+        m_.scratch = Scratch()
+    saved.append((torch.cuda, 'synchronize', torch.cuda.synchronize))
+    torch.cuda.synchronize = lambda *a, **k: None
+    yield shim
+    for m_, name, val in saved:
+        setattr(m_, name, val)
+
+
+@pytest.fixture(autouse=True)
+def _emulated_device(request, monkeypatch):
+    if EMULATE and hasattr(request.module, 'dev'):
+        import torch
+        monkeypatch.setattr(request.module, 'dev', lambda: torch.device('cpu'))
+    yield
+
+
 def pytest_collection_modifyitems(config, items):
     import torch
-    if torch.cuda.is_available():
+    if torch.cuda.is_available() or EMULATE:
         return
     skip = pytest.mark.skip(reason='no CUDA device in this container (GPU tests run under gpurun)')
     for item in items:

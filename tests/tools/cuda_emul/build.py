@@ -205,12 +205,22 @@ extern "C" size_t emu_msmd_spconv_tc16_workspace(int, int);
     return lib
 
 
-def build_exec(verbose=False):
+def build_full(verbose=False):
+    """Every translation unit except points.cu (thread-block clusters) in ONE emulated image: what
+    tests/tools/emu_plugin.py runs the -m gpu tests on."""
+    return build_exec(verbose, name='libmsmd_full_emul.so',
+                      units=['error_stub', 'voxelize.cu', 'spconv.cu', 'rulebook.cu', 'fusion.cu', 'spconv_tc.cu',
+                             'spconv_tc16.cu', 'spconv_wgrad_tc.cu', 'spconv_bwd.cu', 'executor.cu'])
+
+
+def build_exec(verbose=False, name='libmsmd_exec_emul.so', units=None):
     """Host-emulated native executor (csrc/executor.cu) with everything it calls: the bit-grid / rulebook
     kernels, the mask sort, the SIMT and tensor-core convolutions -- one library, entry points emu_msmd_*."""
     os.makedirs(OUT, exist_ok=True)
-    lib = os.path.join(OUT, 'libmsmd_exec_emul.so')
-    units = ['spconv.cu', 'rulebook.cu', 'fusion.cu', 'spconv_tc.cu', 'spconv_tc16.cu', 'executor.cu']
+    lib = os.path.join(OUT, name)
+    units = units or ['spconv.cu', 'rulebook.cu', 'fusion.cu', 'spconv_tc.cu', 'spconv_tc16.cu', 'executor.cu']
+    stub = 'error_stub' in units
+    units = [u for u in units if u != 'error_stub']
     header = os.path.join(ROOT, 'include', 'msmd_b200.h')
     deps = [os.path.join(CSRC, f) for f in units + ['common.cuh', 'tc_common.cuh', 'tc_trace.cuh', 'scan.cuh', 'sort.cuh']] + \
         [header, os.path.join(HERE, 'cuda_emul.h'), os.path.join(HERE, 'tc_emul.h'), os.path.abspath(__file__)]
@@ -224,11 +234,15 @@ def build_exec(verbose=False):
     _INLINED.clear()
     body, n = re.subn(r'extern __shared__ uint8_t (\w+)\[\];', r'uint8_t* \1 = ::emu::g_dyn_smem;', body)
     assert n >= 3
+    if stub:   # what csrc/error.cu provides
+        body = ('extern "C" int msmd_abi_version(void) { return MSMD_ABI_VERSION; }\n'
+                'extern "C" unsigned long long msmd_launch_count(void) { return 0; }\n'
+                'extern "C" const char* msmd_last_error(void) { return ::emu::g_error; }\n') + body
     text = '#undef MSMD_API\n' + open(header).read() + _device_helpers() + body
     # every C-ABI name (declarations of the header, definitions, calls) gets the emu_ prefix
     text = re.sub(r'(?<![\w])msmd_(\w+)\(', r'emu_msmd_\1(', text)
     text = '#define MSMD_EMUL_WITH_HEADER 1\n' + PRELUDE + TC_PRELUDE + text
-    cpp = os.path.join(OUT, 'emul_exec_unit.cpp')
+    cpp = os.path.join(OUT, name.replace('lib', '').replace('.so', '') + '.cpp')
     with open(cpp, 'w') as f:
         f.write(text)
     cmd = ['g++', '-std=c++20', '-O2', '-g', '-ffp-contract=off', '-Wno-unknown-pragmas', '-shared', '-fPIC',
