@@ -147,6 +147,12 @@ def check(status, what):
         raise RuntimeError(f'{what} failed ({status}): {msg}')
 
 
+def require_cuda(t, what):
+    """There is no CPU fallback: ops that take raw strides / pre-allocated outputs check their tensors here."""
+    if not t.is_cuda:
+        raise RuntimeError(f'{what} (no CPU fallback)')
+
+
 def ptr(t):
     """Device pointer of a tensor (None -> NULL).  The tensor must be contiguous CUDA memory."""
     if t is None:

@@ -621,8 +621,7 @@ def lift_gather(img_feat, pixels, cam_ids, points, lidar2img, downscale, score_w
     assert score_weight.numel() == C + 17 and lidar2img.shape == (ncam, 16)
     M, P = points.shape
     out = torch.empty((M, P + C), dtype=torch.float32, device=points.device)
-    if not img_feat.is_cuda:
-        raise RuntimeError('lift_gather needs CUDA tensors (no CPU fallback)')
+    _cabi.require_cuda(img_feat, 'lift_gather needs CUDA tensors')
     s = img_feat.stride()
     with _Timed('lift_gather', m=M, c=C):
         check(lib().msmd_lift_gather(_cabi.ctypes.c_void_p(img_feat.data_ptr()), s[0], s[1], s[2], s[3],

@@ -6,7 +6,7 @@ import torch
 from torch import nn
 from torch.nn.modules.utils import _pair
 
-from . import ops
+from . import _cabi, ops
 from .registry import VOXEL_ENCODERS
 
 
@@ -19,8 +19,7 @@ def hard_voxelize(points, voxels, coors, num_points_per_voxel, voxel_size, coors
     returned (one device->host read, as the reference does).
     """
     assert NDim == 3
-    if not points.is_cuda:
-        raise RuntimeError('hard_voxelize: points must be a CUDA tensor (no CPU fallback)')
+    _cabi.require_cuda(points, 'hard_voxelize: points must be a CUDA tensor')
     v, c, n, _ = ops.hard_voxelize(points, voxel_size, coors_range, max_points, max_voxels,
                                    want_voxels=True)
     k = v.shape[0]
