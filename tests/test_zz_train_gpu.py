@@ -220,7 +220,8 @@ def test_lc_train_step_runs_and_learns():
     import _fixtures
     from msmdfusion_b200 import train
     det, cfg = _fixtures.build_msmd_detector(seed=0, device=dev())
-    scenes, metas, fpn = _fixtures.lc_scene(1, points=12000, virtual=(1500, 300))
+    small = os.environ.get('MSMD_EMULATE', '0') not in ('', '0')   # the CPU emulation needs a scene it can finish
+    scenes, metas, fpn = _fixtures.lc_scene(1, points=700 if small else 12000, virtual=(120, 40) if small else (1500, 300))
     pts = [cuda(s) for s in scenes]
     fpn = [cuda(f) for f in fpn]
     target = torch.zeros((1, 640, 180, 180), device=dev())
