@@ -20,6 +20,7 @@ def _build_oracle():
     build.build_port()
 
 
+GPU_TEST_TIMEOUT_S = int(os.environ.get('MSMD_GPU_TEST_TIMEOUT', '600'))  # per `-m gpu` test, on hardware only
 EMULATE = os.environ.get('MSMD_EMULATE', '0') not in ('', '0')
 # MSMD_EMULATE=1: run the `-m gpu` tests on the CPU emulation of the CUDA kernels (tests/tools/cuda_emul: every
 # translation unit except the thread-block-cluster kernels of points.cu).  Test infrastructure for sessions without
@@ -111,9 +112,15 @@ def _emulated_device(request, monkeypatch):
 
 def pytest_collection_modifyitems(config, items):
     import torch
+    if torch.cuda.is_available() and not EMULATE and config.pluginmanager.hasplugin('timeout'):
+        # a kernel that never returns must end the test process, not hold the GPU box until the caller's limit:
+        # method 'thread' dumps the stacks and os._exit()s, which also tears the CUDA context down
+        for item in items:
+            if 'gpu' in item.keywords and item.get_closest_marker('timeout') is None:
+                item.add_marker(pytest.mark.timeout(GPU_TEST_TIMEOUT_S, method='thread'))
     if torch.cuda.is_available() or EMULATE:
         return
-    skip = pytest.mark.skip(reason='no CUDA device in this container (GPU tests run under gpurun)')
+    skip =pytest.mark.skip(reason='no CUDA device in this container (GPU tests run under gpurun)')
     for item in items:
         if 'gpu' in item.keywords:
             item.add_marker(skip)
