@@ -533,3 +533,37 @@ def test_full_size_16bit_modes_mask_sort_and_tc_wgrad_properties():
     rhs = float((tcg.double() * w.double()).sum())
     scale = float((go.abs().double() * y32.abs().double()).sum())       # both sides are sums of ~7 M signed terms
     assert abs(lhs - rhs) < 1e-6 * scale
+
+
+# --------------------------------------------------------------------------------------
+# edge case added without GPU time (checked on the CPU emulation only), hence in this file
+# --------------------------------------------------------------------------------------
+def test_empty_index_set_through_the_module_surface():
+    """A sample with no active voxel (the reference pads such samples with 100 zero points before they reach
+    the sparse ops, MSMDFusion.py:376-380; the operators themselves must still take N = 0): SubM and strided
+    convolution, the native executor's encoder, sparse_add with an empty side and dense() return empty /
+    all-zero results of the right shapes instead of failing."""
+    shape = [9, 24, 24]
+    feat = torch.zeros((0, 16), device=dev())
+    idx = torch.zeros((0, 4), dtype=torch.int32, device=dev())
+    x = m.spconv.SparseConvTensor(feat, idx, shape, 1)
+    subm = m.spconv.SubMConv3d(16, 32, 3, padding=1, bias=False, indice_key='e').to(dev())
+    down = m.spconv.SparseConv3d(32, 32, 3, stride=2, padding=1, bias=False).to(dev())
+    with torch.no_grad():
+        y = subm(x)
+        z = down(y)
+    assert y.features.shape == (0, 32) and y.indices.shape == (0, 4)
+    assert z.features.shape == (0, 32) and z.indices.shape == (0, 4) and list(z.spatial_shape) == [5, 12, 12]
+    d = z.dense()
+    assert d.shape == (1, 32, 5, 12, 12) and float(d.abs().sum()) == 0.0
+    ib, fb = random_sparse(0, 1, [5, 12, 12], 11, 32)
+    s = Fsp.sparse_add(z, m.spconv.SparseConvTensor(cuda(fb), cuda(ib), [5, 12, 12], 1))
+    ei, ef = cpu.sparse_add(np.zeros((0, 4), np.int32), np.zeros((0, 32), np.float32), ib, fb, [5, 12, 12])
+    assert np.array_equal(s.indices.cpu().numpy(), ei) and np.array_equal(s.features.cpu().numpy(), ef)
+    # the same through the native executor (one C-ABI call for the 21 layers of SparseEncoder)
+    cfg = m.Config.fromfile(os.path.join(ROOT, 'configs', 'msmd_lc_hotpath.py')).hotpath
+    enc = m.registry.build_middle_encoder(dict(cfg.pts_middle_encoder, sparse_shape=[41, 64, 64])).to(dev()).eval()
+    with torch.no_grad():
+        spatial, stages = enc(torch.zeros((0, 5), device=dev()), idx, 1)
+    assert spatial.shape == (1, 256, 8, 8) and float(spatial.abs().sum()) == 0.0
+    assert [tuple(t.features.shape) for t in stages] == [(0, 16), (0, 32), (0, 64), (0, 128), (0, 128)]
