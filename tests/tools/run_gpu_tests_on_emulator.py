@@ -9,6 +9,8 @@ builder) and the kernels' logic, before a hardware run exists.  What it is not: 
 timing, no memory-model races, emulated tcgen05).  Left out by default: tests that need FPS / ball query
 (cluster kernels), pinned-memory / stream plumbing of the detector, and BASELINE-size scenes (minutes each on the
 emulator).  Sizes in the remaining tests are what the GPU runs, so expect ~10-15 minutes for the whole file.
+`-k lc_train_step` on its own (MSMD_EMULATE=1 python -m pytest tests/test_zz_train_gpu.py -m gpu -k lc_train_step) runs the
+whole train step at a reduced scene size in ~16 minutes and passes.
 """
 import argparse
 import os
