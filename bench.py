@@ -18,6 +18,12 @@ import sys
 import threading
 import time
 
+# torchrun exports OMP_NUM_THREADS=1 and libgomp reads it once, when the first OpenMP runtime is
+# loaded (import torch): the CPU arms (--impl reference / cpu_baseline) are specified to use all
+# the host threads they can, so the variable is fixed BEFORE numpy / torch are imported
+if os.environ.get('OMP_NUM_THREADS', '') in ('', '1'):
+    os.environ['OMP_NUM_THREADS'] = str(os.cpu_count() or 1)
+
 import numpy as np
 import torch
 
@@ -37,9 +43,10 @@ def parse():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--profile', default='S', choices=['S', 'L'],
                     help='S: single 32-beam sweep (~30 k points); L: 10 sweeps (~285 k points)')
-    ap.add_argument('--workload', default='L', choices=['L', 'LC', 'train'],
-                    help='L: transfusion_nusc_voxel_L LiDAR hot path (BASELINE configs[1], the default); '
-                         'LC: MSMDFusion_nusc_voxel_LC voxel-space fusion path (configs[2]); '
+    ap.add_argument('--workload', default='LC', choices=['L', 'LC', 'train'],
+                    help='LC: MSMDFusion_nusc_voxel_LC voxel-space fusion path (BASELINE configs[2]/[3], the workload '
+                         'north_star quotes the metric on; the default); '
+                         'L: transfusion_nusc_voxel_L LiDAR hot path (configs[1]); '
                          'train: LC train step (configs[4]): forward in train mode, backward through the GMA '
                          'encoder, one NCCL gradient all-reduce, clip, AdamW')
     ap.add_argument('--precision', default=None, choices=['tf32x3', 'bf16x3', 'bf16'],
@@ -51,6 +58,8 @@ def parse():
                          'BASELINE configs[1] names; the reference config trains with samples_per_gpu=2).  Reported in '
                          'config.scenes_per_gpu_per_step; value counts scenes, not steps')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-cuda-baseline', action='store_true',
+                    help='skip the `cuda_baseline` leg (the reference\'s own CUDA kernels on the same scene)')
     ap.add_argument('--breakdown', default=None, help='write a per-op CUDA-event breakdown (json) here')
     return ap.parse_args()
 
@@ -395,16 +404,17 @@ def run_ours(args, rank, world, device):
         mma_per_product = 1 if args.precision == 'bf16' else 3
         hbm_time = b / (hbm * 1e9)
         tensor_time = (mma_per_product * f) / (tf32_peak * 1e12) if tc else 0.0
+        # DRAM traffic cannot be measured inside an un-profiled run: it is taken from a committed
+        # `ncu --set full` capture ONLY if one exists for exactly this workload / profile / precision
+        # (profiles/traffic_<workload>_<profile>_<precision>.json, written by tools/ncu_traffic.py from
+        # the capture named inside it); otherwise null
         traffic, traffic_src, ncu_tensor_pct = None, None, None
-        tp = os.path.join(ROOT, 'profiles', 'r01e_ncu_full_spconv_tc_profileS.json')
-        if tc and args.workload == 'L' and args.profile == 'S' and os.path.exists(tp):
-            t = json.load(open(tp))  # one committed `ncu --set full` capture of these 21 launches
-            scale = {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}
-            traffic = (t['sum_dram_read'] + t['sum_dram_write']) * scale[t['unit_bytes']]
-            ncu_tensor_pct = round(sum(l['tensor_active_pct'] * l['us'] for l in t['launches']) / t['sum_time'], 2)
-            traffic_src = ('dram__bytes_read.sum + dram__bytes_write.sum summed over the 21 conv launches of '
-                           'one scene, profiles/r01e_ncu_full_spconv_tc_profileS.json (writes stay in the '
-                           '126 MB L2 at this size)')
+        tp = os.path.join(ROOT, 'profiles', 'traffic_%s_%s_%s.json' % (args.workload, args.profile, args.precision))
+        if os.path.exists(tp):
+            t = json.load(open(tp))
+            traffic = float(t['dram_bytes_per_step'])
+            ncu_tensor_pct = t.get('tensor_active_pct_time_weighted')
+            traffic_src = t.get('source')
         common = {'traffic': traffic, 'traffic_source': traffic_src, 'peak_source': src,
                   'kernel': ('sparse conv forward + data gradient (tcgen05 kind::tf32, 3xTF32) + weight gradient '
                              '(spconv_wgrad_simt_kernel, FFMA)' if args.workload == 'train' else
@@ -426,14 +436,35 @@ def run_ours(args, rank, world, device):
         else:
             roof = dict(bound='hbm', achieved=round(gbs, 2), peak=hbm, unit='GB/s', frac=round(gbs / hbm, 4),
                         **common)
+    # ---- reference CUDA kernels on the same scene (rank 0, N=1): see oracle/cuda_baseline.py ----
+    cuda_base = None
+    if rank == 0 and world == 1 and args.workload in ('L', 'LC') and not args.no_cuda_baseline:
+        try:
+            from oracle import cuda_baseline as _cb
+            if _cb.available():
+                n_cb = max(3, min(args.steps, 10))
+                cb_ms, _ = _cb.time_steps(step, pts_dev, device, n_cb, 3, flush)
+                cb_ms = sorted(cb_ms)
+                cuda_base = {'value': 1e3 / (sum(cb_ms) / len(cb_ms)), 'unit': UNIT, 'ms_per_step': sum(cb_ms) / len(cb_ms),
+                             'step_ms': {'min': round(cb_ms[0], 3), 'median': round(cb_ms[len(cb_ms) // 2], 3),
+                                         'max': round(cb_ms[-1], 3)},
+                             'steps': n_cb, 'warmup': 3, 'kind': _cb.KIND,
+                             'timing': 'same scene, device-resident inputs, L2 flushed between steps, CUDA events '
+                                       '(compare with `value`, not with `e2e`)'}
+            else:
+                cuda_base = {'unavailable': 'oracle/_ref reference CUDA libraries are not built (they are compiled '
+                                            'from /root/reference by __graft_entry__.build())'}
+        except Exception as e:  # noqa: BLE001 - a reported baseline must not take the bench line down
+            cuda_base = {'unavailable': 'reference CUDA baseline failed: %s' % (str(e)[-300:],)}
     n_vox = int(feats[0].indices.shape[0])
-    return dict(dev_ms=dev_ms, e2e_ms=e2e_ms, launches=int(launches), exchange=exchange, clocks=clk, roofline=roof, settle_steps=settle_steps,
+    return dict(cuda_baseline=cuda_base, dev_ms=dev_ms, e2e_ms=e2e_ms, launches=int(launches), exchange=exchange, clocks=clk, roofline=roof, settle_steps=settle_steps,
                 e2e_step_ms=dict(min=round(min(e2e_raw), 4), median=round(sorted(e2e_raw)[len(e2e_raw) // 2], 4),
                                  max=round(max(e2e_raw), 4), all=[round(x, 2) for x in e2e_raw[:32]]),
                 alloc=alloc_diag,
                 step_ms=dict(min=round(step_ms[0], 4), median=round(step_ms[len(step_ms) // 2], 4),
                              max=round(step_ms[-1], 4), all=[round(x, 3) for x in step_raw[:32]]),
                 points=int(pts_np.shape[0]), voxels=n_vox, checksum=checksum,
+                virtual_points=(int(sum(len(x) for x in meta['foreground2D_info']['fg_pixels'])) if args.workload != 'L' else 0),
                 h2d=int(pts_np.nbytes) + int(h2d_extra[0]), d2h=4)
 
 
@@ -441,60 +472,120 @@ def run_ours(args, rank, world, device):
 # CPU arm: the reference's own CPU hard_voxelize (oracle/_ref, compiled from the reference
 # sources) + the oracle port of the un-vendored spconv-2.x arithmetic, all host threads.
 # ------------------------------------------------------------------------------------------
-def cpu_pass(profile, seed=0):
+def cpu_pass(profile, workload='L', seed=0):
+    """One whole-scene pass of the workload on the host cores -> (callable, threads, kind, description,
+    points).  L: voxelize + VFE + SparseEncoder.  LC / train: the whole voxel-space fusion forward
+    (oracle.model.extract_voxel_space = the reference's extract_pts_feat up to the BEV tensor,
+    MSMDFusion.py:421-445; pinned against the reference method run in place, tests/test_oracle.py)."""
     from msmdfusion_b200 import registry, synthetic
     from oracle import build as obuild
     from oracle import cpu
     from oracle import model as omodel
     cfg = hotpath_cfg()
     torch.manual_seed(0)
-    enc = registry.build_middle_encoder(cfg.pts_middle_encoder).eval()  # weights only (host tensors)
-    sd = {k: v.numpy() for k, v in enc.state_dict().items()}
     pts = synthetic.lidar_scene(seed=seed, sweeps=1 if profile == 'S' else 10)
     use_ref = obuild.ref_so_path() is not None
     vox = cpu.hard_voxelize_ref if use_ref else cpu.hard_voxelize
+    kind = 'reference' if use_ref else 'port'
+
+    if workload == 'L':
+        enc = registry.build_middle_encoder(cfg.pts_middle_encoder).eval()  # weights only (host tensors)
+        sd = {k: v.numpy() for k, v in enc.state_dict().items()}
+
+        def one():
+            t0 = time.perf_counter()
+            v, c, n = vox(pts, synthetic.VOXEL_SIZE, synthetic.POINT_CLOUD_RANGE, 10, 160000)
+            t1 = time.perf_counter()
+            mean = cpu.hard_simple_vfe(v, n, 5)
+            coors = np.concatenate([np.zeros((c.shape[0], 1), np.int32), c], 1)
+            omodel.sparse_encoder(sd, dict(cfg.pts_middle_encoder), mean, coors, 1)
+            return time.perf_counter() - t0, t1 - t0
+        desc = ('hard_voxelize = %s; spconv-2.x SparseEncoder arithmetic = oracle/c port (spconv is not '
+                'vendored in the reference), OpenMP' % ('reference CPU op (oracle/_ref)' if use_ref else 'oracle port'))
+        return one, cpu.num_threads(), kind, desc, int(pts.shape[0])
+
+    import msmdfusion_b200 as m
+    det = m.MSMDFusionDetector(**{k: cfg[k] for k in (
+        'pts_voxel_layer', 'pts_voxel_encoder', 'pts_middle_encoder', 'multimodal_middle_encoder',
+        'spatial_shapes', 'downscale_factors', 'fps_num_list', 'radius_list', 'max_cluster_samples_list',
+        'dist_thresh_list')}).eval()
+    with torch.no_grad():
+        det.score_net[0].weight.mul_(0.2)
+        det.score_net[0].bias.fill_(0.05)
+    sd = {k: v.numpy() for k, v in det.state_dict().items()}
+    meta = synthetic.camera_scene(seed, pts)
+    fpn = synthetic.fpn_features(seed, batch=1)
+    rng = np.random.RandomState(77)
+    dummies = [rng.rand(1, c).astype(np.float32) for c in cfg.multimodal_middle_encoder['in_channels_3D']]
 
     def one():
         t0 = time.perf_counter()
-        v, c, n = vox(pts, synthetic.VOXEL_SIZE, synthetic.POINT_CLOUD_RANGE, 10, 160000)
+        vox(pts, synthetic.VOXEL_SIZE, synthetic.POINT_CLOUD_RANGE, 10, 160000)   # the reference's own CPU op, timed alone
         t1 = time.perf_counter()
-        mean = cpu.hard_simple_vfe(v, n, 5)
-        coors = np.concatenate([np.zeros((c.shape[0], 1), np.int32), c], 1)
-        omodel.sparse_encoder(sd, dict(cfg.pts_middle_encoder), mean, coors, 1)
-        return time.perf_counter() - t0, t1 - t0
+        omodel.extract_voxel_space(sd, cfg, [pts], fpn, [meta], dummies)
+        t2 = time.perf_counter()
+        # the fusion pass voxelises the LiDAR points itself (oracle port); the separately timed leg is
+        # reported, not added
+        return t2 - t1, t1 - t0
+    desc = ('the whole voxel-space fusion forward on the CPU (oracle.model.extract_voxel_space: hard_voxelize, '
+            'SparseEncoder, depth-aware compression [torch CPU conv2d], 4x lift + voxelize + modality split, GMA '
+            'encoder with FPS / ball query, dense): C port with OpenMP + numpy; spconv-2.x is not vendored in the '
+            'reference, so its arithmetic is the port\'s')
+    return one, cpu.num_threads(), 'port', desc, int(pts.shape[0])
 
-    kind = 'reference' if use_ref else 'port'
-    desc = ('hard_voxelize = %s; spconv-2.x SparseEncoder arithmetic = oracle/c port (spconv is not '
-            'vendored in the reference), OpenMP' % ('reference CPU op (oracle/_ref)' if use_ref else 'oracle port'))
-    return one, cpu.num_threads(), kind, desc, int(pts.shape[0])
+
+def bench_config(args, world, points, virtual_points):
+    """The `config` object both arms print (identical for the same command line): only what the
+    command line and the seeded synthetic scene determine.  Run-dependent facts (voxel count, settle
+    steps) are top-level keys of our arm's line."""
+    from msmdfusion_b200 import spconv as _spconv
+    precision = args.precision or _spconv.CONV_PRECISION
+    SPS = max(1, args.scenes_per_step) if args.workload == 'L' else 1
+    return {'workload': workload_name(args.profile, args.workload), 'profile': args.profile,
+            'arithmetic': ARITHMETIC[precision], 'points_per_scene': points,
+            'virtual_points_per_scene': virtual_points, 'scenes_per_gpu_per_step': SPS,
+            'parallelism': 'dp%d' % world,
+            'l2': 'flushed between steps (256 MiB memset, outside the per-step events)',
+            'weights': ('random init (spconv default); LiDAR encoder frozen, GMA encoder BN in '
+                        'training mode' if args.workload == 'train' else 'random init (spconv default), BN eval')}
+
+
+def scene_counts(args, seed=0):
+    from msmdfusion_b200 import synthetic
+    B = max(1, args.scenes_per_step) if args.workload == 'L' else 1
+    pts = synthetic.lidar_scene(seed=seed * B, sweeps=1 if args.profile == 'S' else 10)
+    if args.workload == 'L':
+        return int(pts.shape[0]), 0
+    meta = synthetic.camera_scene(seed, pts)
+    fg = meta['foreground2D_info']
+    return int(pts.shape[0]), int(sum(len(x) for x in fg['fg_pixels']))
 
 
 def main():
     args = parse()
-    # torchrun exports OMP_NUM_THREADS=1; the CPU arms (reference / cpu_baseline) are specified to use
-    # all the host threads they can, so undo that before the oracle's OpenMP runtime is loaded
-    if os.environ.get('OMP_NUM_THREADS', '') in ('', '1'):
-        os.environ['OMP_NUM_THREADS'] = str(os.cpu_count() or 1)
     rank = int(os.environ.get('RANK', 0))
     local_rank = int(os.environ.get('LOCAL_RANK', 0))
     world = int(os.environ.get('WORLD_SIZE', 1))
 
     if args.impl == 'reference':
+        # the reference's CPU implementation of the path on the box's host cores; under torchrun
+        # rank 0 alone runs and prints, the other ranks exit without work (contract)
         if rank != 0:
             return 0
-        one, cores, kind, desc, npts = cpu_pass(args.profile)
-        for _ in range(min(args.warmup, 1)):
+        one, cores, kind, desc, npts = cpu_pass(args.profile, args.workload)
+        npts, nvirt = scene_counts(args)
+        for _ in range(args.warmup):
             one()
-        times = [one()[0] for _ in range(max(1, min(args.steps, 8)))]
+        times = [one()[0] for _ in range(args.steps)]   # exactly K timed steps, one whole scene each
         val = 1.0 / float(np.mean(times))
         line = {'impl': 'reference', 'metric': METRIC, 'value': val, 'unit': UNIT, 'n_gpus': args.gpus,
                 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 / val,
                 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
                 'data': 'synthetic',
-                'config': {'workload': workload_name(args.profile), 'points': npts,
-                           'timed_steps': len(times)},
+                'config': bench_config(args, args.gpus, npts, nvirt),
                 'cpu_baseline': {'value': val, 'unit': UNIT, 'cores': cores, 'kind': kind,
-                                 'sample': '%d whole-scene passes; %s' % (len(times), desc)},
+                                 'sample': '%d whole-scene passes on rank 0 (one scene per step whatever N is: the '
+                                           'host cores are shared by the N ranks); %s' % (len(times), desc)},
                 'e2e': {'value': val, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
         print(json.dumps(line))
         return 0
@@ -509,19 +600,22 @@ def main():
         dist.init_process_group('nccl', device_id=device)
     res = run_ours(args, rank, world, device)
 
-    cpu_base = None
-    if rank == 0 and not args.no_cpu_baseline:
-        one, cores, kind, desc, _ = cpu_pass(args.profile)
-        one()
-        tt = [one() for _ in range(2 if args.profile == 'S' else 1)]
-        cpu_base = {'value': 1.0 / float(np.mean([t[0] for t in tt])), 'unit': UNIT, 'cores': cores,
-                    'kind': kind, 'sample': '%d whole-scene passes of the same workload; %s; '
-                    'voxelize leg alone %.1f ms on 1 core' % (len(tt), desc, 1e3 * np.mean([t[1] for t in tt]))}
+    # the other ranks are released BEFORE rank 0 spends seconds on the CPU baseline (they used to spin
+    # in a barrier, which read as GPU activity on GPUs 1..N-1)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     if rank != 0:
         return 0
+    cpu_base = None
+    if world == 1 and not args.no_cpu_baseline:   # contract: on rank 0 at N=1 only
+        one, cores, kind, desc, _ = cpu_pass(args.profile, args.workload)
+        if args.workload == 'L':
+            one()
+        tt = [one() for _ in range(2 if (args.profile == 'S' and args.workload == 'L') else 1)]
+        cpu_base = {'value': 1.0 / float(np.mean([t[0] for t in tt])), 'unit': UNIT, 'cores': cores,
+                    'kind': kind, 'sample': '%d whole-scene passes of the same workload; %s; '
+                    'reference CPU hard_voxelize leg alone %.1f ms on 1 core' % (len(tt), desc, 1e3 * np.mean([t[1] for t in tt]))}
     K = args.steps
     SPS = max(1, args.scenes_per_step) if args.workload == 'L' else 1
     value = world * K * SPS / (res['dev_ms'] * 1e-3)
@@ -529,22 +623,23 @@ def main():
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': K, 'warmup': max(args.warmup, 3),
         'ms_per_step': res['dev_ms'] / K, 'step_ms': res['step_ms'], 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': 'bf16' if args.precision == 'bf16' else 'f32', 'data': 'synthetic',
-        'config': {'workload': workload_name(args.profile, args.workload), 'arithmetic': ARITHMETIC[args.precision], 'points_per_scene': res['points'] // SPS,
-                   'voxels_per_scene': res['voxels'] // SPS, 'scenes_per_gpu_per_step': SPS, 'parallelism': 'dp%d' % world,
-                   'l2': 'flushed between steps (256 MiB memset, outside the per-step events)',
-                   'settle': '%d untimed steps (the first + %.0f ms of wall time) before the %d warm-up steps' % (res['settle_steps'], SETTLE_MS, max(args.warmup, 3)),
-                   'weights': ('random init (spconv default); LiDAR encoder frozen (BN eval), GMA encoder BN in '
-                               'training mode' if args.workload == 'train' else 'random init (spconv default), BN eval')},
+        'config': bench_config(args, world, res['points'] // SPS, res['virtual_points']),
+        'run': {'voxels_per_scene': res['voxels'] // SPS,
+                'settle': '%d untimed steps (the first + %.0f ms of wall time) before the %d warm-up steps' % (res['settle_steps'], SETTLE_MS, max(args.warmup, 3))},
         'e2e': {'value': world * K * SPS / (res['e2e_ms'] * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': res['h2d'],
                 'd2h_bytes_per_step': res['d2h'], 'step_ms': res['e2e_step_ms'],
                 'note': ('pinned host points (+ packed virtual points for LC) -> H2D -> public modules '
                          '(Voxelization.forward_mean/SparseEncoder or MSMDFusionDetector.extract_voxel_space) '
-                         '-> checksum of the BEV tensor read back')},
+                         '-> checksum of the BEV tensor read back.  Limitation: the BEV tensor itself '
+                         '(B x 640 x 180 x 180 f32 = 83 MB for LC) stays on the device, where its consumer '
+                         '(SPPModule / SECOND / TransFusionHead) runs; the FPN image features are device-resident '
+                         'inputs (produced on the device by the image branch in the reference too)')},
         'gpu_launches': res['launches'],
         'allocator_during_timed_steps': res['alloc'],
         'clocks': res['clocks'],
         'roofline': res['roofline'],
         'cpu_baseline': cpu_base,
+        'cuda_baseline': res.get('cuda_baseline'),
     }
     if res.get('exchange') is not None:   # --workload train: the exchange step of SURVEY 8(e)
         line['gradient_exchange'] = res['exchange']

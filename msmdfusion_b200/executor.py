@@ -129,9 +129,18 @@ class SparseNetPlan:
         base = arena.data_ptr()
         out = [(features, indices, list(spatial_shape))]
         for a in acts[1:]:
-            fo, io = a.features - base, a.indices - base
-            f = arena[fo:fo + 4 * a.n * a.channels].view(torch.float32).view(a.n, a.channels)
-            if 0 <= io < nbytes:
+            # a NULL descriptor pointer comes back from ctypes as None: an empty activation (n == 0)
+            # has no arena bytes, and a SubM layer on an empty network input reuses the caller's
+            # (NULL) index pointer
+            if a.features is None or a.n == 0:
+                f = features.new_zeros((int(a.n), int(a.channels)))
+            else:
+                fo = a.features - base
+                f = arena[fo:fo + 4 * a.n * a.channels].view(torch.float32).view(a.n, a.channels)
+            io = -1 if a.indices is None else a.indices - base
+            if a.n == 0:
+                idx = indices.new_zeros((0, 4))
+            elif 0 <= io < nbytes:
                 idx = arena[io:io + 16 * a.n].view(torch.int32).view(a.n, 4)
             else:  # SubM layers on the network input keep the caller's index tensor
                 idx = indices
