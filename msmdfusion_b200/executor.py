@@ -150,7 +150,7 @@ class SparseNetPlan:
 
 def plan_key(modules):
     """Changes whenever a parameter / buffer the plan baked in is replaced or modified in place."""
-    key = [spconv.CONV_PATH, spconv.CONV_PRECISION]
+    key = [spconv.CONV_PATH, spconv.CONV_PRECISION, spconv.cache_epoch()]
     for m in modules:
         for t in list(m.parameters()) + list(m.buffers()):
             key.append((t.data_ptr(), t._version))

@@ -41,6 +41,22 @@ CONV_PRECISION = os.environ.get('MSMD_CONV_PRECISION', 'tf32x3')
 MASK_SORT = os.environ.get('MSMD_MASK_SORT', '0') not in ('', '0')
 
 
+# Kernel-layout weight copies, BatchNorm folds and executor plans are cached and re-derived when a parameter
+# is replaced or modified in place (data_ptr / _version).  Writes through ``.data`` (mmcv EMAHook's parameter
+# swap, ``p.data.copy_()``) bump neither: call ``invalidate_caches()`` after such writes.  ``load_state_dict``
+# on any sparse convolution does it automatically.
+_CACHE_EPOCH = [0]
+
+
+def invalidate_caches():
+    """Drop every derived copy of the parameters (packed weights, BN folds, native-executor plans)."""
+    _CACHE_EPOCH[0] += 1
+
+
+def cache_epoch():
+    return _CACHE_EPOCH[0]
+
+
 def expand_nd(ndim, val):
     if isinstance(val, (list, tuple)):
         assert len(val) == ndim
@@ -241,8 +257,8 @@ def is_spconv_module(module):
 def _bn_scale_shift(bn):
     """Fold an eval-mode BatchNorm1d into y = x*scale + shift (fp32).  Cached on the module,
     keyed by the versions of its parameters/buffers, so inference folds each BN once."""
-    key = tuple((t.data_ptr(), t._version) for t in
-                (bn.weight, bn.bias, bn.running_mean, bn.running_var) if t is not None)
+    key = (_CACHE_EPOCH[0],) + tuple((t.data_ptr(), t._version) for t in
+                                      (bn.weight, bn.bias, bn.running_mean, bn.running_var) if t is not None)
     cached = getattr(bn, '_msmd_fold', None)
     if cached is not None and cached[0] == key:
         return cached[1], cached[2]
@@ -370,6 +386,7 @@ class SparseConvolution(SparseModule):
         self.reset_parameters()
         self._packed = None
         self._packed_key = None
+        self.register_load_state_dict_post_hook(lambda module, incompatible_keys: invalidate_caches())
 
     def extra_repr(self):
         s = f'{self.in_channels}, {self.out_channels}, kernel_size={self.kernel_size}, stride={self.stride}'
@@ -399,7 +416,7 @@ class SparseConvolution(SparseModule):
         kvol = int(math.prod(self.kernel_size))
         use_tc = CONV_PATH == 'tc' and ops.tc_supported(self.out_channels, kvol, self.in_channels)
         mode = ops.TC_MODES[CONV_PRECISION] if use_tc else 0
-        key = (w.data_ptr(), w._version, w.device, mode)
+        key = (_CACHE_EPOCH[0], w.data_ptr(), w._version, w.device, mode)
         if self._packed is None or self._packed_key != key:
             self._packed = ops.pack_weight_tc(w, mode) if use_tc else ops.pack_weight(w)
             self._packed_key = key

@@ -26,6 +26,7 @@ mask-sorted tiles (15-bit digest order of ``msmd_rulebook_mask_sort`` for 3x3x3 
 import enum
 import math
 import types
+import weakref
 
 import numpy as np
 import torch
@@ -111,7 +112,10 @@ def get_indice_pairs_implicit_gemm(indices, batch_size, spatial_shape, algo, ksi
     return (outids, num_inds_per_loc, pair_fwd, pair_bwd, fwd_masks, bwd_masks, fwd_sorts, bwd_sorts, masks)
 
 
-_PACKED = {}   # id(weight) -> (version, data_ptr, packed): the kernel-layout copy follows the parameter
+# id(weight) -> (weakref to the tensor, key, packed): the kernel-layout copy follows the parameter.  The weak
+# reference is compared with `is`, so a new tensor that happens to reuse a dead one's id / address / version
+# cannot hit the old entry.
+_PACKED = {}
 
 
 def _packed_of(weight):
@@ -119,15 +123,15 @@ def _packed_of(weight):
     kvol = int(math.prod(weight.shape[1:-1]))
     use_tc = _sp.CONV_PATH == 'tc' and _ops.tc_supported(weight.shape[0], kvol, weight.shape[-1])
     mode = _ops.TC_MODES[_sp.CONV_PRECISION] if use_tc else 0
-    key = (weight._version, weight.data_ptr(), mode)
+    key = (_sp.cache_epoch(), weight._version, weight.data_ptr(), mode)
     ent = _PACKED.get(id(weight))
-    if ent is None or ent[0] != key:
+    if ent is None or ent[0]() is not weight or ent[1] != key:
         packed = _ops.pack_weight_tc(weight, mode) if use_tc else _ops.pack_weight(weight)
-        _PACKED[id(weight)] = ent = (key, packed)
+        _PACKED[id(weight)] = ent = (weakref.ref(weight), key, packed)
         if len(_PACKED) > 512:   # parameters that went away
-            for k in list(_PACKED)[:256]:
+            for k in [k for k, v in _PACKED.items() if v[0]() is None]:
                 _PACKED.pop(k, None)
-    return ent[1]
+    return ent[2]
 
 
 def implicit_gemm(features, filters, pair_fwd, pair_bwd, pair_mask_fwd_splits, pair_mask_bwd_splits,

@@ -11,25 +11,61 @@ loss as a callable on the tensor the head consumes.
 B200-first: the gradients of all participating parameters are VIEWS of one flat fp32 buffer, so the
 exchange step is ONE NCCL all-reduce over NVLink (no bucketing, no copies: ~10 M parameters = 38 MB, far
 below the size where splitting would buy overlap), the clip is one norm over that buffer and the update
-is the fused multi-tensor AdamW.  Parameters that receive no gradient in the first step (the blocks the
-reference builds but never calls, ``score_net``, ``conv1x1_blocks``: the virtual-point features are
-constants, ``MSMDFusion.py:462-464``) are left out of the buffer and of the optimiser, which is what
-``find_unused_parameters`` amounts to.
+is the fused multi-tensor AdamW.  The buffer covers a STATIC parameter set (``trainable_parameters``): the
+sub-modules of the GMA encoder that its ``forward`` reaches.  The blocks the reference builds but never calls,
+``score_net`` and ``conv1x1_blocks`` (the virtual-point features are constants, ``MSMDFusion.py:462-464``)
+are left out of the buffer and of the optimiser, which is what ``find_unused_parameters`` amounts to.
 """
 import torch
 import torch.distributed as dist
 
 
 def freeze_lidar_components(detector):
-    """tools/train.py:185-211: LiDAR voxel encoder / middle encoder frozen, their BN in eval mode."""
-    for name in ('pts_voxel_encoder', 'pts_middle_encoder'):
+    """tools/train.py:185-211: the parameters of the LiDAR voxel layer / voxel encoder / middle encoder stop
+    requiring gradients and their BatchNorms get ``track_running_stats = False`` (``fix_bn``).  The model stays in
+    TRAIN mode, so -- exactly as in the reference -- those BatchNorms normalise with the statistics of the current
+    batch and never touch their running estimates (torch: ``bn_training`` is True in train mode, and the running
+    buffers are not passed when ``track_running_stats`` is False).  Such a BatchNorm cannot be folded into the
+    convolution (``spconv._bn_foldable``), so the frozen encoder runs conv -> torch BatchNorm -> ReLU module by
+    module under ``no_grad``."""
+    from torch import nn
+
+    def fix_bn(m):
+        if isinstance(m, (nn.BatchNorm1d, nn.BatchNorm2d)):
+            m.track_running_stats = False
+
+    for name in ('pts_voxel_layer', 'pts_voxel_encoder', 'pts_middle_encoder'):
         mod = getattr(detector, name, None)
         if mod is None:
             continue
         for p in mod.parameters():
             p.requires_grad_(False)
-        mod.eval()
+        mod.apply(fix_bn)
     return detector
+
+
+# Sub-modules of SparseMultiModalEncoderPaint that ``forward`` reaches (sparse_multimodal_encoder_painting.py:
+# 325-459).  ``grouped_sp_conv_blocks_2D`` / ``_mix`` are built and never called (:142-156); ``score_net`` and
+# ``conv1x1_blocks`` feed the virtual-point lift, which has no backward (MSMDFusion.py:462-464).
+TRAINED_SUBMODULES = ('grouped_sp_conv_blocks_3D', 'aggregation_blocks', 'downscale_blocks', 'gate_control',
+                      'cross_gate_control')
+
+
+def trainable_parameters(detector):
+    """The STATIC, rank-independent set of parameters the step optimises: every ``requires_grad`` parameter of
+    the sub-modules of the GMA encoder that are on the call path.  Which of them actually receive a gradient in
+    a given step is data dependent (a stage with no mixed voxel skips its ``gate_control``): those keep a zero
+    gradient in the flat buffer, so all ranks exchange buffers of the same layout.  The reference gets the same
+    effect from ``DDP(find_unused_parameters=True)``."""
+    enc = getattr(detector, 'multimodal_middle_encoder', None)
+    assert enc is not None, 'the train step optimises the GMA encoder (multimodal_middle_encoder)'
+    named = [getattr(enc, name) for name in TRAINED_SUBMODULES if hasattr(enc, name)]
+    if not named:   # an encoder with another layout (tests' stand-ins): everything it owns
+        named = [enc]
+    out = []
+    for mod in named:
+        out += [p for p in mod.parameters() if p.requires_grad]
+    return out
 
 
 class FlatGradients:
@@ -84,14 +120,17 @@ class VoxelSpaceTrainStep:
         # issued on the compute stream after the backward pass, so its duration IS its exposed time
         self.exchange_events = None
 
-    def _probe(self, loss):
-        """First step: see which parameters the step reaches, then lay out the flat buffer."""
-        loss.backward()
-        used = [p for p in self.det.parameters() if p.requires_grad and p.grad is not None]
-        first = [p.grad.detach().clone() for p in used]
+    def _layout(self):
+        """Lay out the flat gradient buffer over the static parameter set BEFORE the first backward, so that
+        every rank owns the same layout whatever its first scene looks like."""
+        used = trainable_parameters(self.det)
         self.grads = FlatGradients(used)
-        for p, g in zip(used, first):
-            p.grad.copy_(g)
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            n = torch.tensor([self.grads.flat.numel(), -self.grads.flat.numel()], dtype=torch.int64,
+                             device=self.grads.flat.device)
+            dist.all_reduce(n, op=dist.ReduceOp.MAX)
+            assert int(n[0]) == -int(n[1]) == self.grads.flat.numel(), \
+                'ranks disagree on the gradient buffer layout'
         self.opt = torch.optim.AdamW(used, lr=self.lr, weight_decay=self.weight_decay,
                                      fused=used[0].is_cuda)
 
@@ -106,17 +145,15 @@ class VoxelSpaceTrainStep:
 
     def __call__(self, points, img_feats, img_metas):
         from . import spconv
-        if self.grads is not None:
-            self.grads.zero()
+        if self.grads is None:
+            self._layout()
+        self.grads.zero()
         saved = spconv.CONV_PRECISION
         if self.precision:
             spconv.CONV_PRECISION = self.precision
         try:
             loss = self.forward_loss(points, img_feats, img_metas)
-            if self.grads is None:
-                self._probe(loss)
-            else:
-                loss.backward()
+            loss.backward()
         finally:
             spconv.CONV_PRECISION = saved
         timed = self.exchange_events is not None and self.grads.flat.is_cuda

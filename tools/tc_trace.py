@@ -81,7 +81,12 @@ def main():
     ap.add_argument('--json', default=None)
     args = ap.parse_args()
 
-    from msmdfusion_b200 import build as _build
+    # the library path is read when msmdfusion_b200._cabi is imported, i.e. by ANY import of the package: load the
+    # build script by path, set MSMD_LIB, and only then import the package
+    import importlib.util
+    spec = importlib.util.spec_from_file_location('_msmd_build', os.path.join(ROOT, 'msmdfusion_b200', 'build.py'))
+    _build = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(_build)
     os.environ['MSMD_LIB'] = _build.build_trace()
     import numpy as np
     import torch
