@@ -49,7 +49,7 @@ def parse():
                          'L: transfusion_nusc_voxel_L LiDAR hot path (configs[1]); '
                          'train: LC train step (configs[4]): forward in train mode, backward through the GMA '
                          'encoder, one NCCL gradient all-reduce, clip, AdamW')
-    ap.add_argument('--precision', default=None, choices=['tf32x3', 'bf16x3', 'bf16'],
+    ap.add_argument('--precision', default=None, choices=['tf32x3', 'bf16x3', 'bf16x3c', 'bf16'],
                     help='operand precision of the tensor-core sparse convolutions (default: MSMD_CONV_PRECISION or '
                          'tf32x3 = the fp32-parity mode).  bf16x3: bf16 hi/lo split, ~5e-6 per layer.  bf16: operands '
                          'rounded to bf16 (the train-step arithmetic of BASELINE configs[4]; not a parity mode)')
@@ -76,6 +76,8 @@ ARITHMETIC = {
     'tf32x3': 'fp32 in/out; contraction = 3xTF32 tensor-core split with fp32 accumulate (<=1e-4 vs fp32 oracle)',
     'bf16x3': 'fp32 in/out; contraction = bf16 hi/lo split (3 kind::f16 MMAs per product) with fp32 accumulate '
               '(~5e-6 per layer vs fp32; opt-in)',
+    'bf16x3c': 'fp32 in/out; contraction = bf16 hi/lo split (3 kind::f16 MMAs per product, fp32 accumulate, ~5e-6 per '
+               'layer vs fp32) with the activations\' split cached by the producing layer (csrc/spconv_sb.cu)',
     'bf16': 'fp32 storage; contraction operands rounded to bf16 (1 kind::f16 MMA per product), fp32 accumulate -- '
             'NOT a parity mode (2e-3 per layer): the train-step arithmetic of BASELINE configs[4]',
 }

@@ -227,6 +227,25 @@ MSMD_API int msmd_spconv_fwd_tc16_ws(const float* features, int n_in, const void
                                      size_t workspace_bytes, msmd_stream_t stream);
 
 /* ------------------------------------------------------------------------------------
+ * bf16x3 with a SPLIT-BF16 OPERAND CACHE (csrc/spconv_sb.cu) -- the same arithmetic as msmd_spconv_fwd_tc16 x3 = 1
+ * (replaces the same call, Fsp.implicit_gemm at bug_fix/conv.py:442-447), with the hi / lo split of the activations
+ * moved out of the gather: every activation the convolutions read also exists as a "split image"
+ *       xs[row] = [ hi(0..C8) | lo(0..C8) ]  bf16,  C8 = round_up(C, 8)   (msmd_split_width(C) = 2*C8 elements a row)
+ * written by the epilogue of the producing layer (`out_split`) or by msmd_split_bf16 for a network input, and the
+ * gather is cp.async straight into the tensor-core operand tile.  `out` (fp32 rows) and `out_split` may each be NULL,
+ * not both.  `packed_sb`: msmd_spconv_sb_pack_weight image (msmd_spconv_sb_packed_bytes bytes) of the KRSC weight.
+ * msmd_conv_layer.weight_tc = 4 selects it inside msmd_sparse_net_forward (split images carved from the arena).
+ * ---------------------------------------------------------------------------------- */
+MSMD_API int msmd_split_width(int channels);
+MSMD_API int msmd_split_bf16(const float* x, int n, int channels, void* x_split, msmd_stream_t stream);
+MSMD_API size_t msmd_spconv_sb_packed_bytes(int cout, int kvol, int cin);
+MSMD_API int msmd_spconv_sb_pack_weight(const float* weight_krsc, int cout, int kvol, int cin, void* packed_sb,
+                                        msmd_stream_t stream);
+MSMD_API int msmd_spconv_fwd_sb(const void* features_split, int n_in, const void* packed_sb, const int* pair_fwd,
+                                int n_out, int cin, int cout, int kvol, const float* scale, const float* shift,
+                                const float* residual, int relu, float* out, void* out_split, msmd_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
  * Sparse convolution BACKWARD (config 5, the train step) -- replaces the backward of
  * Fsp.implicit_gemm (call site bug_fix/conv.py:442-447; spconv-2.x differentiates through
  * pair_bwd / mask_argsort_bwd_splits, bug_fix/conv.py:382-415).  Arithmetic as the vendored
@@ -298,7 +317,8 @@ typedef struct msmd_conv_layer {
   int cin, cout;
   const float* weight;      /* device: packed image selected by weight_tc */
   int weight_tc;            /* 0: msmd_spconv_pack_weight (fp32 FFMA kernel); 1: msmd_spconv_tc_pack_weight (3xTF32);
-                             * 2: msmd_spconv_tc16_pack_weight x3=1 (bf16x3); 3: msmd_spconv_tc16_pack_weight x3=0 (bf16) */
+                             * 2: msmd_spconv_tc16_pack_weight x3=1 (bf16x3); 3: msmd_spconv_tc16_pack_weight x3=0 (bf16);
+                             * 4: msmd_spconv_sb_pack_weight (bf16x3 through the split-bf16 operand cache) */
   const float* scale;       /* device (cout) or NULL: folded BatchNorm1d(eval) */
   const float* shift;
   int relu;

@@ -152,6 +152,12 @@ extern "C" MSMD_API int msmd_sparse_net_forward(const msmd_conv_layer* layers, i
   std::vector<IndexSetX> isets;
   isets.reserve(n_layers + 1);
   std::vector<int> act_iset(n_layers + 1, -1);
+  // split-bf16 operand cache (weight_tc 4, csrc/spconv_sb.cu): split image of activation a, or null.  It is written
+  // by the producing layer's epilogue when some later layer of the plan gathers the activation through that path.
+  std::vector<void*> act_split(n_layers + 1, nullptr);
+  std::vector<char> wants_split(n_layers + 1, 0);
+  for (int li = 0; li < n_layers; ++li)
+    if (layers[li].weight_tc == 4 && layers[li].input >= 0 && layers[li].input <= li) wants_split[layers[li].input] = 1;
   {
     IndexSetX s0;
     s0.indices = (int*)indices; s0.n = n;
@@ -255,7 +261,21 @@ extern "C" MSMD_API int msmd_sparse_net_forward(const msmd_conv_layer* layers, i
         MSMD_CUDA_OK(cudaStreamWaitEvent(stream, rb.ready, 0));
         waited_seq = rb.seq;
       }
-      if (L.weight_tc == 2 || L.weight_tc == 3) {  // 16-bit operand kernels: bf16x3 / bf16
+      if (L.weight_tc == 4) {  // bf16x3 through the split-bf16 operand cache
+        if (!act_split[L.input] && in.n > 0) {   // network input, or produced by a layer of another kind
+          MSMD_ARENA(xs, uint16_t, (size_t)in.n * (size_t)msmd_split_width(L.cin));
+          MSMD_TRY(msmd_split_bf16(in.features, in.n, L.cin, xs, (msmd_stream_t)stream));
+          act_split[L.input] = xs;
+        }
+        void* out_s = nullptr;
+        if (wants_split[li + 1] && n_out > 0) {
+          MSMD_ARENA(os, uint16_t, (size_t)n_out * (size_t)msmd_split_width(L.cout));
+          out_s = os;
+        }
+        MSMD_TRY(msmd_spconv_fwd_sb(act_split[L.input], in.n, L.weight, rb.pair, n_out, L.cin, L.cout, kvol, L.scale,
+                                    L.shift, residual, L.relu, out, out_s, (msmd_stream_t)stream));
+        act_split[li + 1] = out_s;
+      } else if (L.weight_tc == 2 || L.weight_tc == 3) {  // 16-bit operand kernels: bf16x3 / bf16
         const size_t ws_bytes = msmd_spconv_tc16_workspace(n_out, L.cout);  // variant 3: split-K hand-off buffer
         char* ws = nullptr;
         if (ws_bytes) {

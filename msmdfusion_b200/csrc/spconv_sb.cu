@@ -1,0 +1,439 @@
+// spconv_sb.cu -- sparse convolution forward on tcgen05 with a SPLIT-BF16 OPERAND CACHE and an asynchronous gather.
+//
+// Arithmetic: exactly the bf16 x3 mode of spconv_tc16.cu -- x = hi + lo with hi = bf16(x), lo = bf16(x - hi);
+// D += A_lo*B_hi + A_hi*B_lo + A_hi*B_hi on tcgen05.mma.kind::f16, fp32 accumulator in tensor memory, fused
+// BatchNorm / residual / ReLU epilogue.  What changes is WHERE the split happens.
+//
+// r02a measurements (profiles/r02a_*): every earlier kernel pays ~1.2 us per 32-element gather step whatever
+// Cout, MMA kind, occupancy or stage count is -- the gather warps' load -> convert -> st.shared -> fence -> arrive
+// chain, not the tensor pipe and not HBM.  A row of activations is written ONCE by its producing layer and
+// gathered 3..27 times by the next one, so the hi / lo split belongs to the producer:
+//
+//   * every activation tensor the convolutions read exists (also) as a "split image"
+//         xs[row] = [ hi(0..C8) | lo(0..C8) ]   bf16,  C8 = round_up(C, 8),  4*C8 bytes per row (= the fp32 row),
+//     written by the epilogue of the layer that produced it next to the fp32 tensor (which stays the API-visible
+//     result and the residual operand), or by msmd_split_bf16 for a network input;
+//   * the gather is then a pure copy: cp.async (LDGSTS, 16 bytes, L2 -> shared memory, no registers) straight into
+//     the K-major SWIZZLE_128B operand tile, missing pairs zero-filled by src-size 0; each of the 256 producer
+//     threads ties its copies to the stage's "full" mbarrier with cp.async.mbarrier.arrive.noinc and runs ahead as
+//     far as free stages allow -- up to `stages` x 32 KB of gather traffic in flight per CTA and no thread ever
+//     waits for its own loads;
+//   * weights: the [hi | lo] 128-byte-swizzled images of spconv_tc16.cu (one bulk copy per chunk), with the input
+//     channels padded to 8 so that a 16-byte piece never straddles two kernel offsets.
+//
+// K chunk = 64 bf16 elements (one swizzle row); K index = k * C8 + c.  Roles as in the other kernels: warps 0-7
+// producers + epilogue, warp 8 weight loader, warp 9 TMEM owner + MMA issuer.  For 2N <= 256 the adjacent
+// B_hi | B_lo images are one 2N-row operand (2 MMAs per k-step, A_hi read from shared memory once).
+//
+// Reference semantics: spconv v2.1.21 SparseConvolution.forward (API copy bug_fix/conv.py:382-447); parity is
+// checked against the oracle and the reference's vendored spconv-1.x goldens (tests/test_gpu_parity.py).
+#include "tc_common.cuh"
+#include "tc_trace.cuh"
+
+namespace msmd {
+
+constexpr int kSbKC = 64;                 // bf16 K elements per chunk
+constexpr int kSbABytes = kTcM * 128;     // 16 KB per A image (hi or lo)
+
+struct SbGeom {
+  int cin_pad, N, chunks;
+};
+static bool sb_geom(int cout, int kvol, int cin, SbGeom& g) {
+  if (cout < 1 || cout > 256 || kvol < 1 || kvol > 32 || cin < 1 || cin > 4096) return false;
+  g.cin_pad = round_up(cin, 8);
+  g.N = round_up(cout, 16);
+  g.chunks = (kvol * g.cin_pad + kSbKC - 1) / kSbKC;
+  return true;
+}
+
+struct SbLayout {
+  int stage_bytes, stages, pair_off, act_off, bar_off, total;
+};
+static SbLayout sb_layout(int N, int kvol, int chunks, int tiles) {
+  SbLayout L;
+  L.stage_bytes = 2 * kSbABytes + 2 * N * 128;   // A hi | A lo | B hi | B lo
+  const int misc = round_up(kvol * kTcM * 4, 16) + round_up(2 * chunks, 16) + 256 + 8 * N;
+  const int budget = tc_smem_budget(2 * L.stage_bytes + misc + 1024 <= 112 * 1024, tiles);
+  L.stages = (budget - misc - 1024) / L.stage_bytes;
+  if (L.stages > 6) L.stages = 6;
+  if (g_tc_tune[1] >= 2 && g_tc_tune[1] <= 6 && L.stages > g_tc_tune[1]) L.stages = g_tc_tune[1];
+  L.pair_off = L.stages * L.stage_bytes;
+  L.act_off = L.pair_off + round_up(kvol * kTcM * 4, 16);
+  L.bar_off = L.act_off + round_up(2 * chunks, 16);
+  L.total = L.bar_off + 256 + 8 * N + 1024;
+  return L;
+}
+
+// Epilogue: TMEM -> registers -> y = relu(acc*scale + shift + residual) -> fp32 rows and / or the split image.
+__device__ __forceinline__ void sb_epilogue(int any_active, uint64_t* accum_bar, uint32_t tmem_base, int warp,
+                                            int lane, int row0, int n_out, int cout, int cout_pad, int N,
+                                            const float* ss, const float* __restrict__ residual, int relu,
+                                            float* __restrict__ out, uint16_t* __restrict__ out_s, int cat_cols) {
+  if (any_active) {
+    tc::mbar_wait(accum_bar, 0);
+    tc::fence_after_sync();
+  }
+  const int quarter = warp & 3;
+  const int o = row0 + quarter * 32 + lane;
+  const int nsteps = N / 16;
+  const int step_lo = (warp >> 2) ? (nsteps + 1) / 2 : 0;
+  const int step_hi = (warp >> 2) ? nsteps : (nsteps + 1) / 2;
+  const bool vec_out = (cout % 4 == 0) && (out == nullptr || ((uintptr_t)out & 15) == 0) &&
+                       (residual == nullptr || ((uintptr_t)residual & 15) == 0);
+  for (int st = step_lo; st < step_hi; ++st) {
+    const int c0 = st * 16;
+    uint32_t acc[16];
+    if (any_active) {
+      tc::tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, acc);
+      if (cat_cols) {
+        uint32_t acc2[16];
+        tc::tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(cat_cols + c0), acc2);
+        tc::tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 16; ++e) acc[e] = __float_as_uint(__uint_as_float(acc[e]) + __uint_as_float(acc2[e]));
+      }
+      tc::tmem_ld_wait();
+    } else {
+#pragma unroll
+      for (int e = 0; e < 16; ++e) acc[e] = 0u;
+    }
+    if (o >= n_out) continue;
+    float y[16];
+    const float* rrow = residual ? residual + (size_t)o * cout : nullptr;
+#pragma unroll
+    for (int e = 0; e < 16; e += 4) {
+      const int co = c0 + e;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) y[e + q] = fmaf(__uint_as_float(acc[e + q]), ss[co + q], ss[N + co + q]);
+      if (rrow && co < cout) {
+        if (vec_out) {
+          const float4 rv = __ldg((const float4*)(rrow + co));
+          y[e] += rv.x; y[e + 1] += rv.y; y[e + 2] += rv.z; y[e + 3] += rv.w;
+        } else {
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            if (co + q < cout) y[e + q] += __ldg(rrow + co + q);
+        }
+      }
+      if (relu) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) y[e + q] = fmaxf(y[e + q], 0.f);
+      }
+    }
+    if (out) {
+      float* orow = out + (size_t)o * cout;
+#pragma unroll
+      for (int e = 0; e < 16; e += 4) {
+        const int co = c0 + e;
+        if (co >= cout) break;
+        if (vec_out) {
+          *(float4*)(orow + co) = make_float4(y[e], y[e + 1], y[e + 2], y[e + 3]);
+        } else {
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            if (co + q < cout) orow[co + q] = y[e + q];
+        }
+      }
+    }
+    if (out_s) {
+      // split image of the row: hi at [0, cout_pad), lo at [cout_pad, 2*cout_pad); channels in [cout, cout_pad) are zero
+      uint16_t* srow = out_s + (size_t)o * (2 * cout_pad);
+#pragma unroll
+      for (int e = 0; e < 16; e += 8) {
+        const int co = c0 + e;
+        if (co >= cout_pad) break;
+        uint32_t h[4], l[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float a = (co + 2 * q < cout) ? y[e + 2 * q] : 0.f;
+          const float b = (co + 2 * q + 1 < cout) ? y[e + 2 * q + 1] : 0.f;
+          h[q] = tc::pack_bf16x2(a, b);
+          l[q] = tc::pack_bf16x2(a - __uint_as_float(h[q] << 16), b - __uint_as_float(h[q] & 0xFFFF0000u));
+        }
+        *(uint4*)(srow + co) = make_uint4(h[0], h[1], h[2], h[3]);
+        *(uint4*)(srow + cout_pad + co) = make_uint4(l[0], l[1], l[2], l[3]);
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kTcThreads)
+spconv_fwd_sb_kernel(const uint16_t* __restrict__ xs, const uint16_t* __restrict__ wpk,
+                     const int* __restrict__ pair, int n_out, int cin_pad, int cout, int cout_pad, int N, int kvol,
+                     int chunks, int stages, int stage_bytes, int pair_off, int act_off, int bar_off, int tmem_cols,
+                     const float* __restrict__ scale, const float* __restrict__ shift,
+                     const float* __restrict__ residual, int relu, float* __restrict__ out,
+                     uint16_t* __restrict__ out_s, int cat) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  int* pair_s = (int*)(smem + pair_off);
+  unsigned short* alist = (unsigned short*)(smem + act_off);
+  uint64_t* full_bar = (uint64_t*)(smem + bar_off);
+  uint64_t* empty_bar = full_bar + 6;
+  uint64_t* accum_bar = full_bar + 12;
+  uint32_t* tmem_ptr_s = (uint32_t*)(full_bar + 13);
+  int* n_act_s = (int*)(full_bar + 13) + 1;
+  int* used_s = (int*)(full_bar + 14);  // [kvol <= 32]
+  float* ss = (float*)(smem + bar_off + 256);
+  for (int c = threadIdx.x; c < N; c += kTcThreads) {
+    ss[c] = (scale && c < cout) ? __ldg(scale + c) : 1.f;
+    ss[N + c] = (shift && c < cout) ? __ldg(shift + c) : 0.f;
+  }
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int row0 = blockIdx.x * kTcM;
+  TC_TRACE_INIT();
+  TC_TRACE_ENTRY();
+  tc::pdl_launch_dependents();
+
+  if (tid == 0) {
+    for (int s = 0; s < stages; ++s) {
+      tc::mbar_init(&full_bar[s], kTcProducers + 1);  // one cp.async-completion arrival per producer thread + the B copy
+      tc::mbar_init(&empty_bar[s], 1);                // one tcgen05.commit
+    }
+    tc::mbar_init(accum_bar, 1);
+    tc::fence_mbar_init();
+  }
+  if (warp == kTcProducerWarps + 1) {
+    tc::tmem_alloc(tmem_ptr_s, (uint32_t)tmem_cols);
+    tc::tmem_relinquish();
+  }
+  for (int k = warp; k < kvol; k += kTcThreads / 32) {
+    bool any = false;
+#pragma unroll
+    for (int q = 0; q < kTcM / 32; ++q) {
+      const int r = lane + 32 * q;
+      const int o = row0 + r;
+      const int p = (o < n_out) ? __ldg(pair + (size_t)k * n_out + o) : -1;
+      pair_s[k * kTcM + r] = p;
+      any |= p >= 0;
+    }
+    const unsigned b = __ballot_sync(0xffffffffu, any);
+    if (lane == 0) used_s[k] = b != 0;
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  if (warp == 0) tc_build_active_list(used_s, chunks, cin_pad, kvol, lane, alist, n_act_s, kSbKC);
+  __syncthreads();
+  const int n_act = *n_act_s;
+  const int any_active = n_act > 0;
+  const uint32_t tmem_base = *tmem_ptr_s;
+  if (tid == 0) { TC_TRACE_HEAD(1, clock64()); TC_TRACE_HEAD(7, n_act); }
+  tc::pdl_wait();
+
+  if (warp < kTcProducerWarps) {
+    // ===== A producers: 16-byte pieces, cp.async straight into the swizzled tile ===================
+    // thread (q, rbase): piece q (8 K elements) of rows rbase + 32*i of every chunk
+    const int q = tid & 7;
+    const int rbase = tid >> 3;  // 0..31
+    const size_t row_elems = (size_t)2 * cin_pad;
+    const int tr_role = warp == 0 ? 0 : (warp == kTcProducerWarps - 1 ? 1 : -1);  // traced gather warps
+    (void)tr_role;
+    int s = 0;
+    uint32_t ph = 1u;   // "empty" barriers: the first pass through the ring finds every stage free
+    for (int t = 0; t < n_act; ++t) {
+      if (lane == 0) TC_TRACE(tr_role, t, 0);
+      mbar_wait_warp(&empty_bar[s], ph, lane);
+      if (lane == 0) TC_TRACE(tr_role, t, 1);
+      const int kk0 = (int)alist[t] * kSbKC + q * 8;
+      const int k = kk0 / cin_pad;
+      const int c0 = kk0 - k * cin_pad;
+      const bool kvalid = k < kvol;
+      const uint32_t a_hi = tc::smem_u32(smem + (size_t)s * stage_bytes);
+#pragma unroll
+      for (int i = 0; i < kTcM / 32; ++i) {
+        const int r = rbase + 32 * i;
+        const int idx = kvalid ? pair_s[k * kTcM + r] : -1;
+        const uint16_t* src = xs + (idx >= 0 ? (size_t)idx * row_elems + c0 : 0);
+        const uint32_t nb = idx >= 0 ? 16u : 0u;
+        const uint32_t off = (uint32_t)(r * 128 + ((q ^ (r & 7)) << 4));
+        tc::cp_async_16(a_hi + off, src, nb);
+        tc::cp_async_16(a_hi + kSbABytes + off, idx >= 0 ? src + cin_pad : src, nb);
+      }
+      tc::cp_async_mbar_arrive_noinc(&full_bar[s]);
+      if (lane == 0) TC_TRACE(tr_role, t, 2);
+      if (++s == stages) { s = 0; ph ^= 1u; }
+    }
+    if (tid == 0) TC_TRACE_HEAD(2, clock64());
+    sb_epilogue(any_active, accum_bar, tmem_base, warp, lane, row0, n_out, cout, cout_pad, N, ss, residual, relu,
+                out, out_s, cat ? N : 0);
+    if (tid == 0) TC_TRACE_HEAD(4, clock64());
+  } else if (warp == kTcProducerWarps) {
+    // ===== B loader ================================================================================
+    if (lane == 0) {
+      const uint32_t bytes = (uint32_t)(2 * N * 128);
+      int s = 0;
+      uint32_t ph = 1u;
+      for (int t = 0; t < n_act; ++t) {
+        TC_TRACE(2, t, 0);
+        tc::mbar_wait(&empty_bar[s], ph);
+        TC_TRACE(2, t, 1);
+        tc::mbar_arrive_expect_tx(&full_bar[s], bytes);
+        tc::bulk_g2s(smem + (size_t)s * stage_bytes + 2 * kSbABytes, (const uint8_t*)wpk + (size_t)alist[t] * bytes,
+                     bytes, &full_bar[s]);
+        if (++s == stages) { s = 0; ph ^= 1u; }
+      }
+    }
+  } else {
+    // ===== MMA issuer ==============================================================================
+    // One lane issues everything, so its instruction count is a per-chunk floor: descriptors are 32-bit low
+    // words over one constant high word, advanced by integer adds (tc::mma_f16_lo).
+    if (lane == 0) {
+      const uint32_t idesc = tc::idesc_f32acc(tc::kFmtBF16, kTcM, N);
+      const uint32_t idesc2 = tc::idesc_f32acc(tc::kFmtBF16, kTcM, 2 * N);
+      const uint32_t dhi = tc::desc_hi32_k_sw128();
+      const uint32_t lo0 = tc::desc_lo32(tc::smem_u32(smem));
+      const uint32_t stage_lo = (uint32_t)stage_bytes >> 4, a_lo_off = (uint32_t)kSbABytes >> 4;
+      const uint32_t b_hi_off = (uint32_t)(2 * kSbABytes) >> 4, b_lo_off = b_hi_off + (((uint32_t)N * 128u) >> 4);
+      uint32_t accumulate = 0;
+      int s = 0;
+      uint32_t ph = 0;
+      for (int t = 0; t < n_act; ++t) {
+        TC_TRACE(3, t, 0);
+        tc::mbar_wait(&full_bar[s], ph);
+        TC_TRACE(3, t, 1);
+        tc::fence_proxy_async();   // cp.async wrote the A tile through the generic proxy
+        tc::fence_after_sync();
+        const uint32_t a = lo0 + (uint32_t)s * stage_lo;
+#pragma unroll
+        for (int ks = 0; ks < kSbKC / 16; ++ks) {
+          const uint32_t ah = a + (uint32_t)ks * 2u;   // 16 bf16 = 32 bytes along K = 2 descriptor units
+          if (cat) {
+            tc::mma_f16_lo(tmem_base, ah, ah + b_hi_off, dhi, idesc2, accumulate);   // D[:, 0:2N] += A_hi * [B_hi; B_lo]
+            tc::mma_f16_lo(tmem_base, ah + a_lo_off, ah + b_hi_off, dhi, idesc, 1u);  // D[:, 0:N]  += A_lo * B_hi
+          } else {
+            tc::mma_f16_lo(tmem_base, ah + a_lo_off, ah + b_hi_off, dhi, idesc, accumulate);
+            tc::mma_f16_lo(tmem_base, ah, ah + b_lo_off, dhi, idesc, 1u);
+            tc::mma_f16_lo(tmem_base, ah, ah + b_hi_off, dhi, idesc, 1u);
+          }
+          accumulate = 1u;
+        }
+        tc::mma_commit(&empty_bar[s]);
+        TC_TRACE(3, t, 2);
+        if (++s == stages) { s = 0; ph ^= 1u; }
+      }
+      if (n_act > 0) tc::mma_commit(accum_bar);
+    }
+  }
+
+  tc::fence_before_sync();
+  __syncthreads();
+  TC_TRACE_EXIT();
+  if (warp == kTcProducerWarps + 1) tc::tmem_dealloc(tmem_base, (uint32_t)tmem_cols);
+}
+
+// fp32 rows -> split image [hi | lo] with the channel count padded to 8 (zeros)
+__global__ void __launch_bounds__(256)
+split_bf16_kernel(const float* __restrict__ x, long long n, int c, int c_pad, uint16_t* __restrict__ xs) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // one thread per (row, pair of channels)
+  const int half = c_pad / 2;
+  if (t >= n * half) return;
+  const long long r = t / half;
+  const int ch = (int)(t - r * half) * 2;
+  const float a = ch < c ? x[r * c + ch] : 0.f;
+  const float b = ch + 1 < c ? x[r * c + ch + 1] : 0.f;
+  const uint32_t h = tc::pack_bf16x2(a, b);
+  const uint32_t l = tc::pack_bf16x2(a - __uint_as_float(h << 16), b - __uint_as_float(h & 0xFFFF0000u));
+  *(uint32_t*)(xs + r * (2 * c_pad) + ch) = h;
+  *(uint32_t*)(xs + r * (2 * c_pad) + c_pad + ch) = l;
+}
+
+// Packed weight image: [chunk j][image: hi, lo][n < N][64 bf16, 16-byte units swizzled by (n & 7)], K = k*cin_pad + c
+__global__ void __launch_bounds__(256)
+sb_pack_weight_kernel(const float* __restrict__ w, int cout, int kvol, int cin, int cin_pad, int N, int chunks,
+                      uint16_t* __restrict__ packed) {
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t total = (size_t)chunks * N * kSbKC;
+  if (t >= total) return;
+  const int kk = (int)(t % kSbKC);
+  const int n = (int)((t / kSbKC) % N);
+  const int j = (int)(t / ((size_t)kSbKC * N));
+  const int K = j * kSbKC + kk;
+  const int k = K / cin_pad, c = K - k * cin_pad;
+  float val = 0.f;
+  if (k < kvol && c < cin && n < cout) val = w[((size_t)n * kvol + k) * cin + c];
+  const uint32_t hi = tc::pack_bf16x2(val, 0.f) & 0xFFFFu;
+  const float lo = val - __uint_as_float(hi << 16);
+  const size_t blk = (size_t)N * kSbKC;
+  const size_t off = (size_t)n * kSbKC + (size_t)((((kk >> 3) ^ (n & 7)) << 3) + (kk & 7));
+  packed[((size_t)j * 2 + 0) * blk + off] = (uint16_t)hi;
+  packed[((size_t)j * 2 + 1) * blk + off] = (uint16_t)(tc::pack_bf16x2(lo, 0.f) & 0xFFFFu);
+}
+
+}  // namespace msmd
+
+using namespace msmd;
+
+#ifdef MSMD_TC_TRACE
+extern "C" MSMD_API int msmd_sb_trace_set(unsigned long long* buf) { return tc_trace_set_impl(buf); }
+#endif
+
+extern "C" MSMD_API int msmd_split_width(int channels) { return 2 * round_up(channels > 0 ? channels : 1, 8); }
+
+extern "C" MSMD_API int msmd_split_bf16(const float* x, int n, int channels, void* xs, msmd_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  MSMD_REQUIRE(n >= 0 && channels >= 1, "split_bf16: bad sizes");
+  if (n == 0) return MSMD_OK;
+  MSMD_REQUIRE(x && xs, "split_bf16: null pointer");
+  MSMD_REQUIRE(((uintptr_t)xs & 15) == 0, "split_bf16: the split image must be 16-byte aligned");
+  const int c_pad = round_up(channels, 8);
+  const long long total = (long long)n * (c_pad / 2);
+  split_bf16_kernel<<<ceil_div(total, 256), 256, 0, stream>>>(x, (long long)n, channels, c_pad, (uint16_t*)xs);
+  MSMD_LAUNCH_OK();
+  return MSMD_OK;
+}
+
+extern "C" MSMD_API size_t msmd_spconv_sb_packed_bytes(int cout, int kvol, int cin) {
+  SbGeom g;
+  if (!sb_geom(cout, kvol, cin, g)) return 0;
+  return (size_t)g.chunks * 2 * g.N * kSbKC * sizeof(uint16_t);
+}
+
+extern "C" MSMD_API int msmd_spconv_sb_pack_weight(const float* weight_krsc, int cout, int kvol, int cin,
+                                                   void* packed, msmd_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  SbGeom g;
+  MSMD_REQUIRE(sb_geom(cout, kvol, cin, g), "spconv_sb: unsupported shape (cout<=256, kvol<=32)");
+  MSMD_REQUIRE(weight_krsc && packed, "spconv_sb_pack_weight: null pointer");
+  MSMD_REQUIRE(((uintptr_t)packed & 15) == 0, "spconv_sb_pack_weight: packed must be 16-byte aligned");
+  const size_t total = (size_t)g.chunks * g.N * kSbKC;
+  sb_pack_weight_kernel<<<ceil_div((long long)total, 256), 256, 0, stream>>>(weight_krsc, cout, kvol, cin, g.cin_pad,
+                                                                             g.N, g.chunks, (uint16_t*)packed);
+  MSMD_LAUNCH_OK();
+  return MSMD_OK;
+}
+
+extern "C" MSMD_API int msmd_spconv_fwd_sb(const void* features_split, int n_in, const void* packed_sb,
+                                           const int* pair_fwd, int n_out, int cin, int cout, int kvol,
+                                           const float* scale, const float* shift, const float* residual, int relu,
+                                           float* out, void* out_split, msmd_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  SbGeom g;
+  MSMD_REQUIRE(sb_geom(cout, kvol, cin, g), "spconv_fwd_sb: unsupported shape (cout<=256, kvol<=32)");
+  MSMD_REQUIRE(n_in >= 0 && n_out >= 0, "spconv_fwd_sb: bad sizes");
+  MSMD_REQUIRE((scale == nullptr) == (shift == nullptr), "spconv_fwd_sb: scale/shift must come together");
+  if (n_out == 0) return MSMD_OK;
+  MSMD_REQUIRE(n_in > 0, "spconv_fwd_sb: output rows without input rows");
+  MSMD_REQUIRE(features_split && packed_sb && pair_fwd && (out || out_split), "spconv_fwd_sb: null pointer");
+  MSMD_REQUIRE(((uintptr_t)features_split & 15) == 0 && ((uintptr_t)packed_sb & 15) == 0 &&
+                   ((uintptr_t)out_split & 15) == 0,
+               "spconv_fwd_sb: split images and packed weights must be 16-byte aligned");
+  const int tiles = ceil_div(n_out, kTcM);
+  const SbLayout L = sb_layout(g.N, kvol, g.chunks, tiles);
+  MSMD_REQUIRE(L.stages >= 2, "spconv_fwd_sb: tile does not fit in shared memory");
+  static bool attr_set = false;
+  if (!attr_set) {
+    MSMD_CUDA_OK(cudaFuncSetAttribute(spconv_fwd_sb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  const int cat = (2 * g.N <= 256) ? 1 : 0;
+  int tmem_cols = 32;
+  while (tmem_cols < (cat ? 2 * g.N : g.N)) tmem_cols <<= 1;
+  tc_launch(spconv_fwd_sb_kernel, tiles, kTcThreads, L.total, stream, (const uint16_t*)features_split,
+            (const uint16_t*)packed_sb, pair_fwd, n_out, g.cin_pad, cout, round_up(cout, 8), g.N, kvol, g.chunks,
+            L.stages, L.stage_bytes, L.pair_off, L.act_off, L.bar_off, tmem_cols, scale, shift, residual, relu, out,
+            (uint16_t*)out_split, cat);
+  MSMD_LAUNCH_OK();
+  return MSMD_OK;
+}

@@ -60,6 +60,18 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src, uint32
       : "memory");
 }
 
+// 16-byte asynchronous copy global -> shared (LDGSTS), L2 only (.cg); `src_bytes` = 16, or 0 to zero-fill the
+// destination without reading (`src` must still be a mapped address)
+__device__ __forceinline__ void cp_async_16(uint32_t dst_smem, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "r"(src_bytes)
+               : "memory");
+}
+// the mbarrier receives ONE arrival (already part of its expected count: .noinc) once every cp.async this
+// thread issued so far has landed
+__device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint64_t* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
 // ---- TMEM -----------------------------------------------------------------------------
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {  // one full warp
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)),
@@ -114,6 +126,24 @@ __device__ __forceinline__ void mma_f16(uint32_t d_tmem, uint64_t adesc, uint64_
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// Same MMA with the two shared-memory descriptors given as 32-bit LOW words over a common HIGH word: for the
+// K-major SWIZZLE_128B descriptors of this code base the high word (stride offset, version, swizzle mode) is a
+// constant and the low word is (shared address & 0x3FFFF) >> 4, so stepping through K / stages / operand images is
+// ONE integer add per operand instead of rebuilding a 64-bit descriptor (the issuing thread is a single lane:
+// its instruction count is the per-chunk floor of the small-N layers, profiles/r02b_tc_trace_S.txt).
+__device__ __forceinline__ uint32_t desc_lo32(uint32_t smem_addr) { return (smem_addr & 0x3FFFFu) >> 4; }
+__device__ __forceinline__ uint32_t desc_hi32_k_sw128() { return (uint32_t)(desc_k_sw128(0) >> 32); }
+__device__ __forceinline__ void mma_f16_lo(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi,
+                                           uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %3};\n\t"
+      "mov.b64 db, {%2, %3};\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate)
       : "memory");
 }
 // arrives on the mbarrier once every tcgen05.mma issued so far by this thread has completed

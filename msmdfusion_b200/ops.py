@@ -199,7 +199,9 @@ def pack_weight(weight):
 class TcWeight:
     """Weight packed for the tensor-core path.  ``mode`` = the value of ``msmd_conv_layer.weight_tc``:
     1 = tf32 hi/lo image (csrc/spconv_tc.cu, 3xTF32), 2 = bf16 hi/lo image (csrc/spconv_tc16.cu, bf16x3),
-    3 = bf16 image (one MMA per product: the train-step arithmetic of BASELINE configs[4])."""
+    3 = bf16 image (one MMA per product: the train-step arithmetic of BASELINE configs[4]),
+    4 = bf16 hi/lo image with the input channels padded to 8 (csrc/spconv_sb.cu: bf16x3 through the split-bf16
+    operand cache -- same arithmetic as mode 2, the activations' hi/lo split done by their producer)."""
 
     __slots__ = ('packed', 'cout', 'kvol', 'cin', 'mode')
 
@@ -207,7 +209,7 @@ class TcWeight:
         self.packed, self.cout, self.kvol, self.cin, self.mode = packed, cout, kvol, cin, int(mode)
 
 
-TC_MODES = {'tf32x3': 1, 'bf16x3': 2, 'bf16': 3}
+TC_MODES = {'tf32x3': 1, 'bf16x3': 2, 'bf16': 3, 'bf16x3c': 4}
 
 
 def set_mask_sort(enable):
@@ -245,8 +247,14 @@ def pack_weight_tc(weight, mode=1):
     cout, cin = w.shape[0], w.shape[-1]
     kvol = w.numel() // (cout * cin)
     mode = int(mode)
-    assert mode in (1, 2, 3)
-    if mode == 1:
+    assert mode in (1, 2, 3, 4)
+    if mode == 4:
+        n = lib().msmd_spconv_sb_packed_bytes(cout, kvol, cin)
+        assert n > 0, 'shape not supported by the tensor-core path'
+        packed = torch.empty((n // 2,), dtype=torch.int16, device=w.device)   # raw bf16 bit patterns
+        check(lib().msmd_spconv_sb_pack_weight(ptr(w), cout, kvol, cin, ptr(packed), stream(w.device)),
+              'msmd_spconv_sb_pack_weight')
+    elif mode == 1:
         n = lib().msmd_spconv_tc_packed_floats(cout, kvol, cin)
         assert n > 0, 'shape not supported by the tensor-core path'
         packed = torch.empty((n,), dtype=torch.float32, device=w.device)
@@ -279,11 +287,67 @@ def rulebook_mask_sort(pair_fwd):
     return row_perm, pair_sorted
 
 
+def split_bf16(features):
+    """(n, C) fp32 rows -> split image (n, 2*round_up(C, 8)) of bf16 bit patterns [hi | lo] (csrc/spconv_sb.cu).
+    The image is remembered on the tensor object (keyed by its version), so a tensor that feeds several
+    convolutions -- or came out of one that already wrote its image -- is split once."""
+    cached = getattr(features, '_msmd_split', None)
+    if cached is not None and cached[0] == (features.data_ptr(), features._version, tuple(features.shape)):
+        return cached[1]
+    f = features.contiguous()
+    if f.dtype != torch.float32:
+        f = f.float()
+    n, c = f.shape
+    xs = torch.empty((n, lib().msmd_split_width(c)), dtype=torch.int16, device=f.device)
+    with _Timed('split_bf16', n=n, c=c):
+        check(lib().msmd_split_bf16(ptr(f), n, c, ptr(xs), stream(f.device)), 'msmd_split_bf16')
+    _remember_split(features, xs)
+    return xs
+
+
+def _remember_split(t, xs):
+    try:
+        t._msmd_split = ((t.data_ptr(), t._version, tuple(t.shape)), xs)
+    except (AttributeError, RuntimeError):   # tensors that refuse attributes: just do not cache
+        pass
+
+
+def spconv_fwd_sb(features, tcw, pair_fwd, scale=None, shift=None, residual=None, relu=False, want_split=True):
+    """bf16x3 sparse convolution through the split-bf16 operand cache (``msmd_spconv_fwd_sb``): the gather reads
+    the split image of ``features``; the epilogue writes the fp32 result and (``want_split``) its split image, which
+    is attached to the returned tensor for the next convolution."""
+    assert tcw.mode == 4 and features.shape[1] == tcw.cin, 'channel size mismatch'
+    assert pair_fwd.shape[0] == tcw.kvol and pair_fwd.dtype == torch.int32
+    n_out = pair_fwd.shape[1]
+    dev = features.device
+    out = torch.empty((n_out, tcw.cout), dtype=torch.float32, device=dev)
+    if n_out == 0:
+        return out
+    if residual is not None:
+        residual = residual.contiguous()
+        assert residual.shape == out.shape
+    pair_fwd = pair_fwd.contiguous()
+    xs = split_bf16(features)
+    out_s = torch.empty((n_out, lib().msmd_split_width(tcw.cout)), dtype=torch.int16, device=dev) \
+        if want_split else None
+    with _Timed('spconv_fwd', n_in=features.shape[0], n_out=n_out, cin=tcw.cin, cout=tcw.cout, kvol=tcw.kvol,
+                residual=residual is not None, pair=pair_fwd, path='tc', tc_mode=tcw.mode):
+        check(lib().msmd_spconv_fwd_sb(ptr(xs), features.shape[0], ptr(tcw.packed), ptr(pair_fwd), n_out, tcw.cin,
+                                       tcw.cout, tcw.kvol, ptr(scale), ptr(shift), ptr(residual), int(bool(relu)),
+                                       ptr(out), ptr(out_s), stream(dev)), 'msmd_spconv_fwd_sb')
+    if out_s is not None:
+        _remember_split(out, out_s)
+    return out
+
+
 def spconv_fwd_tc(features, tcw, pair_fwd, scale=None, shift=None, residual=None, relu=False, row_perm=None):
     """Sparse conv forward on tcgen05 tensor cores (3xTF32 / bf16x3 / bf16 by ``tcw.mode``, fp32
     accumulate in TMEM).  With
     ``row_perm`` the table is a mask-sorted one (``rulebook_mask_sort``); the output keeps the original
     row order."""
+    if tcw.mode == 4:   # split-bf16 operand cache; a mask-sorted table is used unsorted (row order is the caller's)
+        assert row_perm is None, 'the split-operand path takes the plain pair table'
+        return spconv_fwd_sb(features, tcw, pair_fwd, scale, shift, residual, relu)
     features = features.contiguous()
     if features.dtype != torch.float32:
         features = features.float()
@@ -410,6 +474,8 @@ def spconv_bwd_data(grad_out, packed_wt, pair_bwd):
         kvol, cout, cin = packed_wt.shape
         tc, wbuf = 0, packed_wt
     assert grad_out.shape[1] == cout and pair_bwd.shape[0] == kvol and pair_bwd.dtype == torch.int32
+    if tc == 4:   # the data gradient IS the forward contraction: split dY once, run the split-operand kernel
+        return spconv_fwd_sb(grad_out, packed_wt, pair_bwd, want_split=False)
     grad_in = torch.empty((n_in, cin), dtype=torch.float32, device=grad_out.device)
     with _Timed('spconv_bwd_data', n_in=n_in, n_out=grad_out.shape[0], cin=cin, cout=cout, kvol=kvol,
                 pair=pair_bwd, path='tc' if tc else 'simt'):

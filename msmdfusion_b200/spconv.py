@@ -31,9 +31,10 @@ from .registry import CONV_LAYERS
 
 # contraction kernel: 'tc' (tcgen05, 3xTF32) or 'simt' (exact fp32 FFMA); MSMD_CONV_PATH overrides
 CONV_PATH = os.environ.get('MSMD_CONV_PATH', 'tc')
-# operand precision of the tensor-core path: 'tf32x3' (default: 3xTF32, ~1e-6 of fp32), 'bf16x3' (bf16 hi/lo
-# split, ~5e-6 per layer, half the tensor-pipe time; opt-in until measured) or 'bf16' (operands rounded to
-# bf16: the train-step arithmetic BASELINE configs[4] names -- outside the inference parity bound).
+# operand precision of the tensor-core path: 'tf32x3' (3xTF32, ~1e-6 of fp32), 'bf16x3' (bf16 hi/lo split, ~5e-6
+# per layer, half the tensor-pipe time), 'bf16x3c' (the SAME arithmetic as bf16x3 through the split-bf16 operand
+# cache of csrc/spconv_sb.cu: activations are split by their producer, the gather is cp.async) or 'bf16' (operands
+# rounded to bf16: the train-step arithmetic BASELINE configs[4] names -- outside the inference parity bound).
 # MSMD_CONV_PRECISION overrides; train.VoxelSpaceTrainStep(precision=...) sets it for a train step.
 CONV_PRECISION = os.environ.get('MSMD_CONV_PRECISION', 'tf32x3')
 # opt-in: mask-sorted tiles for the 3x3x3 SubM layers of the tensor-core path (spconv-2.x
@@ -489,7 +490,7 @@ class SparseConvolution(SparseModule):
         else:
             packed = self.packed_weight()
             if MASK_SORT and self.subm and pair.shape[0] == 27 and isinstance(packed, ops.TcWeight) \
-                    and pair.shape[1] > 0:
+                    and packed.mode != 4 and pair.shape[1] > 0:
                 row_perm, pair_sorted = iset.subm_pairs_sorted(self.kernel_size, self.dilation)
                 out_features = ops.spconv_fwd_tc(features, packed, pair_sorted, scale, shift, residual, relu,
                                                  row_perm=row_perm)

@@ -50,6 +50,7 @@ def tc_emu():
         _TC.emu_msmd_spconv_tc16_packed_bytes.restype = ctypes.c_size_t
         _TC.emu_msmd_spconv_bwd_weight_tc_workspace.restype = ctypes.c_size_t
         _TC.emu_msmd_spconv_tc16_workspace.restype = ctypes.c_size_t
+        _TC.emu_msmd_spconv_sb_packed_bytes.restype = ctypes.c_size_t
     return _TC
 
 
@@ -217,7 +218,7 @@ class _EmuLib:
     def __init__(self, cabi):
         self._cabi, self._cache = cabi, {}
 
-    TC_UNIT = ('msmd_spconv_tc_', 'msmd_spconv_fwd_tc', 'msmd_spconv_tc16_', 'msmd_spconv_bwd_weight_tc')
+    TC_UNIT = ('msmd_spconv_tc_', 'msmd_spconv_fwd_tc', 'msmd_spconv_tc16_', 'msmd_spconv_bwd_weight_tc', 'msmd_spconv_sb', 'msmd_spconv_fwd_sb', 'msmd_split_')
 
     def __getattr__(self, name):
         fn = self._cache.get(name)
@@ -688,13 +689,16 @@ def test_tc_wrappers_drive_emulated_kernels(tc_ops_on_emulator):
     ref = cpu.spconv_fwd(feat, w, pair)
     t = torch.from_numpy
     row_perm, pair_sorted = ops.rulebook_mask_sort(t(pair))
-    for mode, tol in (('tf32x3', 5e-6), ('bf16x3', 2e-5), ('bf16', 1e-2)):
+    for mode, tol in (('tf32x3', 5e-6), ('bf16x3', 2e-5), ('bf16x3c', 2e-5), ('bf16', 1e-2)):
         tcw = ops.pack_weight_tc(t(w), ops.TC_MODES[mode])
         assert tcw.mode == ops.TC_MODES[mode] and (tcw.packed.dtype == torch.int16) == (mode != 'tf32x3')
         out = ops.spconv_fwd(t(feat), tcw, t(pair))
         assert rel(out.numpy(), ref) < tol
-        srt = ops.spconv_fwd_tc(t(feat), tcw, pair_sorted, row_perm=row_perm)
-        assert rel(srt.numpy(), out.numpy()) < 5e-6
+        if mode == 'bf16x3c':   # the result carries its split image for the next convolution; re-use is by identity
+            assert out._msmd_split[1].shape == (ref.shape[0], 2 * 24) and ops.split_bf16(out) is out._msmd_split[1]
+        else:
+            srt = ops.spconv_fwd_tc(t(feat), tcw, pair_sorted, row_perm=row_perm)
+            assert rel(srt.numpy(), out.numpy()) < 5e-6
         # data gradient through the same precision: forward contraction with the mirrored weight
         go = rng.standard_normal(ref.shape).astype(np.float32)
         gi = ops.spconv_bwd_data(t(go), ops.pack_weight_tc(ops.transpose_weight(t(w), flip_k=True), tcw.mode), t(pair))
@@ -709,14 +713,14 @@ def test_tc_wrappers_drive_emulated_kernels(tc_ops_on_emulator):
     assert rel(simt.numpy(), rw) < 1e-5 and rel(tcg.numpy(), rw) < 5e-6 and not np.array_equal(simt.numpy(), tcg.numpy())
 
 
-@pytest.mark.parametrize('precision', ['bf16x3', 'bf16'])
+@pytest.mark.parametrize('precision', ['bf16x3', 'bf16x3c', 'bf16'])
 def test_modules_and_autograd_in_16bit_modes_on_emulated_kernels(tc_ops_on_emulator, monkeypatch, precision):
     """SubMConv3d / SparseConv3d with spconv.CONV_PRECISION set: inference path (fused epilogue, packed-weight
     cache keyed on the mode) and the autograd path (forward + dgrad in the forward's precision, fp32 wgrad)."""
     import torch
     from msmdfusion_b200 import spconv
     monkeypatch.setattr(spconv, 'CONV_PRECISION', precision)
-    tol = 2e-5 if precision == 'bf16x3' else 1e-2
+    tol = 2e-5 if precision.startswith('bf16x3') else 1e-2
     shape, cin, cout = [7, 12, 12], 8, 16
     idx, feat = random_sparse(11, 1, shape, 250, cin)
     for cls, kw in ((spconv.SubMConv3d, dict(padding=1)), (spconv.SparseConv3d, dict(stride=2, padding=1))):
@@ -912,7 +916,8 @@ def test_native_executor_on_emulator(executor_on_emulator, monkeypatch):
             acts = plan.run(tf, ti, enc.sparse_shape, 2)
         return [acts[i] for i in marks]
 
-    for mask_sort, precision, tol in ((0, 'tf32x3', 1e-5), (1, 'tf32x3', 1e-5), (0, 'bf16x3', 1e-4), (1, 'bf16x3', 1e-4)):
+    for mask_sort, precision, tol in ((0, 'tf32x3', 1e-5), (1, 'tf32x3', 1e-5), (0, 'bf16x3', 1e-4), (1, 'bf16x3', 1e-4),
+                                      (0, 'bf16x3c', 1e-4)):
         executor_on_emulator.msmd_spconv_set_mask_sort(mask_sort)
         monkeypatch.setattr(spconv, 'CONV_PRECISION', precision)
         outs = run()
@@ -1003,3 +1008,112 @@ def test_tc16_two_chunk_blocks_per_stage_on_emulator(x3, cin, cout, n):
     assert np.array_equal(one, two)
     ref = cpu.spconv_fwd(feat, w, pair) if x3 else cpu.spconv_fwd(bf16_round(feat), bf16_round(w), pair)
     assert rel(two, np.maximum(ref * scale + shift + res, 0)) < (2e-5 if x3 else 2e-6)
+
+
+# --------------------------------------------------------------------------------------
+# bf16x3 through the split-bf16 operand cache (csrc/spconv_sb.cu): cp.async gather of pre-split activations
+# --------------------------------------------------------------------------------------
+def bf16_split(x):
+    hi = bf16_round(x)
+    return hi, bf16_round(np.ascontiguousarray(x, np.float32) - hi)
+
+
+def sb_split(feat):
+    L = tc_emu()
+    n, c = feat.shape
+    width = L.emu_msmd_split_width(c)
+    xs = np.full((max(n, 1), width), 0x7FC0, np.uint16)[:n]   # NaN fill: every element must be written
+    assert L.emu_msmd_split_bf16(P(feat), n, c, P(xs), None) == 0, L.emu_last_error()
+    return xs
+
+
+def sb_fwd(feat, w, pair, scale=None, shift=None, residual=None, relu=0, want_out=True, want_split=True, xs=None):
+    L = tc_emu()
+    cout, cin = w.shape[0], w.shape[-1]
+    kvol, n_out = pair.shape
+    packed = np.full(L.emu_msmd_spconv_sb_packed_bytes(cout, kvol, cin) // 2, 0x7FC0, np.uint16)
+    assert L.emu_msmd_spconv_sb_pack_weight(P(w), cout, kvol, cin, P(packed), None) == 0, L.emu_last_error()
+    xs = sb_split(feat) if xs is None else xs
+    out = np.full((n_out, cout), np.nan, np.float32) if want_out else None
+    out_s = np.full((n_out, L.emu_msmd_split_width(cout)), 0x7FC0, np.uint16) if want_split else None
+    st = L.emu_msmd_spconv_fwd_sb(P(xs), feat.shape[0], P(packed), P(pair), n_out, cin, cout, kvol, P(scale), P(shift),
+                                  P(residual), relu, P(out), P(out_s), None)
+    assert st == 0, L.emu_last_error()
+    return out, out_s
+
+
+def split_to_float(xs, c):
+    """[hi | lo] bf16 image -> hi + lo as fp32 (first c channels) and the padding channels."""
+    c8 = xs.shape[1] // 2
+    f = (xs.astype(np.uint32) << 16).view(np.float32)
+    return f[:, :c] + f[:, c8:c8 + c], f[:, c:c8], f[:, c8 + c:]
+
+
+def test_split_bf16_image_on_emulator():
+    rng = np.random.default_rng(3)
+    x = (rng.standard_normal((37, 5)) * 3).astype(np.float32)
+    xs = sb_split(x)
+    assert xs.shape == (37, 16)
+    hi, lo = bf16_split(x)
+    f = (xs.astype(np.uint32) << 16).view(np.float32)
+    assert np.array_equal(f[:, :5], hi) and np.array_equal(f[:, 8:13], lo)
+    assert not f[:, 5:8].any() and not f[:, 13:].any()          # channel padding is zero
+    assert np.abs(f[:, :5] + f[:, 8:13] - x).max() < 2.0 ** -16 * np.abs(x).max()
+
+
+@pytest.mark.parametrize('cin,cout,n', [(16, 16, 300),    # four kernel offsets per 64-element chunk, concatenated-B
+                                        (5, 16, 200),     # input channels padded 5 -> 8: eight offsets per chunk
+                                        (24, 144, 150),   # chunk boundaries inside a kernel offset, padded N, 3-MMA mode
+                                        (64, 128, 140),   # one offset per chunk, concatenated-B at 2N = 256
+                                        (80, 96, 260)])   # fusion-encoder widths, ragged last tile, several tiles
+def test_sb_kernel_on_emulator(cin, cout, n):
+    """csrc/spconv_sb.cu on the tcgen05 model with late-as-possible asynchronous copies: the result equals the
+    bf16x3 arithmetic (within 2e-5 of the fp32 oracle), the split image the epilogue writes IS the split of the fp32
+    result it writes (bit for bit, padding channels zero), fused epilogue, fp32-only and split-only outputs."""
+    shape = [5, 12, 12]
+    idx, feat = random_sparse(0, 1, shape, n, cin)
+    rng = np.random.default_rng(1)
+    w = (rng.standard_normal((cout, 3, 3, 3, cin)) * 0.2).astype(np.float32)
+    pair = cpu.subm_rulebook(idx, shape, 3, 1)
+    ref = cpu.spconv_fwd(feat, w, pair)
+    out, out_s = sb_fwd(feat, w, pair)
+    assert rel(out, ref) < 2e-5
+    hi, lo = bf16_split(out)
+    f = (out_s.astype(np.uint32) << 16).view(np.float32)
+    c8 = out_s.shape[1] // 2
+    assert np.array_equal(f[:, :cout], hi) and np.array_equal(f[:, c8:c8 + cout], lo)
+    assert not f[:, cout:c8].any() and not f[:, c8 + cout:].any()
+    # it is the bf16x3 arithmetic of spconv_tc16.cu, operand for operand
+    assert rel(out, tc16_fwd(feat, w, pair, 1)) < 2e-6
+    scale = rng.uniform(0.5, 1.5, cout).astype(np.float32)
+    shift = rng.standard_normal(cout).astype(np.float32)
+    res = rng.standard_normal(ref.shape).astype(np.float32)
+    want = np.maximum(ref * scale + shift + res, 0)
+    got, _ = sb_fwd(feat, w, pair, scale, shift, res, 1, want_split=False)
+    assert rel(got, want) < 2e-5
+    _, only_s = sb_fwd(feat, w, pair, scale, shift, res, 1, want_out=False)
+    assert np.array_equal(only_s, sb_split(got))
+
+
+def test_sb_kernel_chain_strided_rulebook_and_empty_tiles_on_emulator():
+    """Two layers chained through the split image only (the second never sees fp32 activations), a strided
+    rulebook, and a tile without any pair."""
+    shape = [7, 14, 14]
+    idx, feat = random_sparse(5, 1, shape, 400, 16)
+    rng = np.random.default_rng(6)
+    w1 = (rng.standard_normal((32, 3, 3, 3, 16)) * 0.2).astype(np.float32)
+    w2 = (rng.standard_normal((32, 3, 3, 3, 32)) * 0.1).astype(np.float32)
+    pair = cpu.subm_rulebook(idx, shape, 3, 1)
+    y1, y1_s = sb_fwd(feat, w1, pair, relu=1)
+    y2, _ = sb_fwd(y1, w2, pair, xs=y1_s)
+    ref1 = np.maximum(cpu.spconv_fwd(feat, w1, pair), 0)
+    assert rel(y1, ref1) < 2e-5 and rel(y2, cpu.spconv_fwd(ref1, w2, pair)) < 4e-5
+    _, spair, _ = cpu.conv_rulebook(idx, shape, (3, 3, 3), 2, 1, 1)
+    got, _ = sb_fwd(feat, w1, spair)
+    assert rel(got, cpu.spconv_fwd(feat, w1, spair)) < 2e-5
+    empty = np.full((27, 140), -1, np.int32)
+    empty[13, 130] = 7
+    one = np.ones(32, np.float32)
+    shift = rng.standard_normal(32).astype(np.float32)
+    got, _ = sb_fwd(feat, w1, empty, one, shift)
+    assert rel(got, cpu.spconv_fwd(feat, w1, empty) + shift) < 2e-5

@@ -24,20 +24,23 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 FEAT_TOL = 1e-4
 
 
-def feat_err(got, ref):
-    """Feature error in units of the tensor's scale: max|got-ref| / max(1, max|ref|).
+PARITY_LOG = []   # (test id, observed max-abs error, max|ref|): dumped to gpurun_out/ by conftest at session end
 
-    north_star's tolerance is 1e-4 on fp32 features.  Features here are O(1)-O(10) (random BN
-    affine up to 1.5x per layer); an fp32 result carries ~6e-8 relative rounding per accumulation
-    step, so the bound is applied relative to the tensor's magnitude once that exceeds 1 (for
-    |ref| <= 1 it is the plain absolute 1e-4).  Both the CUDA path (tensor-core 3xTF32, fp32
-    accumulate in TMEM) and the oracle (sequential fp32 sums) sit inside this band of the exact
-    value; see DESIGN.md section 3."""
+
+def feat_err(got, ref):
+    """north_star's tolerance on fp32 features is an ABSOLUTE 1e-4.  It is applied as such wherever the tensor is
+    O(1)-O(10): the value returned is max|got-ref| itself when max|ref| <= 10.  Above that the bound is scaled with
+    the tensor (max|got-ref| / (max|ref| / 10), i.e. 1e-5 of the tensor's scale): both the CUDA path (fp32
+    accumulation in TMEM in the tensor core's order) and the oracle (sequential fp32 sums over up to 5184 terms)
+    carry ~sqrt(K) * 6e-8 * |x| of rounding, which alone passes 1e-4 absolute once |x| reaches the hundreds.
+    The observed absolute error of every call is logged (PARITY_LOG -> gpurun_out/parity_abs_err.json)."""
     got = np.asarray(got, np.float64)
     ref = np.asarray(ref, np.float64)
     if got.size == 0:
         return 0.0
-    return float(np.abs(got - ref).max() / max(1.0, np.abs(ref).max()))
+    abs_err, scale = float(np.abs(got - ref).max()), float(np.abs(ref).max())
+    PARITY_LOG.append((os.environ.get('PYTEST_CURRENT_TEST', '?').split(' ')[0], abs_err, scale))
+    return abs_err / max(1.0, scale / 10.0)
 
 
 def dev():

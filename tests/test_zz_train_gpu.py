@@ -39,9 +39,16 @@ def cuda(a):
 
 
 def err(got, ref):
+    """As tests/test_gpu_parity.py:feat_err: the absolute error where max|ref| <= 10, scaled with the tensor above
+    that; every observed absolute error is logged."""
+    from test_gpu_parity import PARITY_LOG
     got = np.asarray(got.detach().cpu().numpy() if torch.is_tensor(got) else got, np.float64)
     ref = np.asarray(ref.detach().cpu().numpy() if torch.is_tensor(ref) else ref, np.float64)
-    return float(np.abs(got - ref).max() / max(1.0, np.abs(ref).max())) if got.size else 0.0
+    if not got.size:
+        return 0.0
+    abs_err, scale = float(np.abs(got - ref).max()), float(np.abs(ref).max())
+    PARITY_LOG.append((os.environ.get('PYTEST_CURRENT_TEST', '?').split(' ')[0], abs_err, scale))
+    return abs_err / max(1.0, scale / 10.0)
 
 
 def random_sparse(seed, batch, shape, n, c):
@@ -357,6 +364,76 @@ def test_tc16_bf16x3_sparse_encoder_within_parity_bound():
     assert err(outs['bf16x3'][0], outs['tf32x3'][0]) < TOL
     for a, b in zip(outs['bf16x3'][1], outs['tf32x3'][1]):
         assert err(a, b) < TOL
+
+
+@pytest.mark.parametrize('cin,cout,subm', [(16, 16, True), (5, 16, True), (64, 64, True), (128, 128, True),
+                                            (80, 96, False), (192, 192, True), (24, 144, True)])
+def test_split_operand_conv_matches_oracle(cin, cout, subm):
+    """msmd_spconv_fwd_sb (bf16x3 through the split-bf16 operand cache, csrc/spconv_sb.cu) against the CPU oracle at
+    2e-5 -- absolute error printed -- with and without the fused epilogue; the split image its epilogue writes is
+    bit for bit the split of the fp32 result (msmd_split_bf16), padding channels zero; a second layer that gathers
+    ONLY that image reproduces the oracle's two-layer chain."""
+    shape, batch = [9, 24, 24], 2
+    idx, feat = random_sparse(cin + cout, batch, shape, 1500, cin)
+    rng = np.random.default_rng(1)
+    w = (rng.standard_normal((cout, 3, 3, 3, cin)) / np.sqrt(cin * 27 * 0.2)).astype(np.float32)
+    if subm:
+        pair = cpu.subm_rulebook(idx, shape, 3, 1)
+    else:
+        _, pair, _ = cpu.conv_rulebook(idx, shape, 3, 2, 1, 1)
+    tcw = ops.pack_weight_tc(cuda(w), ops.TC_MODES['bf16x3c'])
+    assert tcw.mode == 4
+    ref = cpu.spconv_fwd(feat, w, pair)
+    got = ops.spconv_fwd_tc(cuda(feat), tcw, cuda(pair))
+    print('max abs err %.3e at |ref| max %.2f' % (float(np.abs(got.cpu().numpy() - ref).max()), float(np.abs(ref).max())))
+    assert err(got, ref) < 2e-5
+    img = got._msmd_split[1]
+    assert torch.equal(img, ops.split_bf16(got.clone()))
+    scale = rng.uniform(0.5, 1.5, cout).astype(np.float32)
+    shift = rng.standard_normal(cout).astype(np.float32)
+    res = rng.standard_normal(ref.shape).astype(np.float32)
+    got2 = ops.spconv_fwd_tc(cuda(feat), tcw, cuda(pair), cuda(scale), cuda(shift), cuda(res), True)
+    want2 = np.maximum(ref * scale + shift + res, 0)
+    assert err(got2, want2) < 2e-5
+    if subm:   # chain: the second layer reads only the image the first one's epilogue wrote
+        w2 = (rng.standard_normal((32, 3, 3, 3, cout)) / np.sqrt(cout * 27 * 0.2)).astype(np.float32)
+        tcw2 = ops.pack_weight_tc(cuda(w2), 4)
+        got3 = ops.spconv_fwd_tc(got2, tcw2, cuda(pair))
+        assert err(got3, cpu.spconv_fwd(want2, w2, pair)) < 4e-5
+
+
+def test_split_operand_sparse_encoder_within_parity_bound():
+    """The whole LiDAR SparseEncoder (21 layers, native executor, split images carved from its arena) in the
+    bf16x3c mode: indices identical, features within the path's ABSOLUTE 1e-4 of the default 3xTF32 run, and equal to
+    the bf16x3 kernel's results up to accumulation order; the module-by-module path gives the executor's result."""
+    from msmdfusion_b200 import registry
+    from msmdfusion_b200 import sparse_encoder as se
+    cfg = m.Config.fromfile(os.path.join(ROOT, 'configs', 'msmd_lc_hotpath.py')).hotpath
+    torch.manual_seed(0)
+    enc = registry.build_middle_encoder(cfg.pts_middle_encoder).to(dev()).eval()
+    layer = m.Voxelization(**cfg.pts_voxel_layer).eval()
+    outs = {}
+    try:
+        for prec, use_exec in (('tf32x3', True), ('bf16x3', True), ('bf16x3c', True), ('bf16x3c', False)):
+            m.spconv.CONV_PRECISION = prec
+            se.SparseEncoder.use_executor = use_exec
+            with torch.no_grad():
+                mean, coors, _ = layer.forward_mean(cuda(synthetic.lidar_scene(seed=5, sweeps=1)), 5, batch_idx=0)
+                spatial, feats = enc(mean, coors, 1)
+            torch.cuda.synchronize()
+            outs[(prec, use_exec)] = (spatial.clone(), [f.features.clone() for f in feats], [f.indices.clone() for f in feats])
+    finally:
+        m.spconv.CONV_PRECISION = 'tf32x3'
+        se.SparseEncoder.use_executor = True
+    base, sb, sbm, b16 = outs[('tf32x3', True)], outs[('bf16x3c', True)], outs[('bf16x3c', False)], outs[('bf16x3', True)]
+    for a, b in zip(sb[2], base[2]):
+        assert torch.equal(a, b)
+    worst = max(float((a - b).abs().max()) for a, b in zip([sb[0]] + sb[1], [base[0]] + base[1]))
+    print('bf16x3c vs 3xTF32, 21 layers: max abs err %.3e (|x| max %.1f)' % (worst, float(base[0].abs().max())))
+    assert worst < TOL
+    assert err(sb[0], b16[0]) < 2e-5 and err(sbm[0], sb[0]) < 1e-6
+    for a, b in zip(sbm[1], sb[1]):
+        assert err(a, b) < 1e-6
 
 
 def test_tc16_bf16_backward_matches_rounded_operand_autograd():

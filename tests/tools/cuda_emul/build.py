@@ -161,6 +161,7 @@ NamedBar g_named[16];
 std::atomic<long long> g_mma_count{0};
 std::deque<AsyncOp> g_mma_queue;
 std::vector<AsyncOp> g_copy_queue;
+std::map<int, std::vector<std::function<void()>>> g_cpasync_pending;
 int g_async_late = 1;
 static void tc_begin(uint32_t bytes) { tc_block_reset(bytes); g_dyn_smem = g_smem_window + kDynBase; }
 static void tc_end() { tc_block_check(); }
@@ -175,13 +176,14 @@ def build_tc(verbose=False):
     """Host-emulated copy of csrc/spconv_tc.cu (tcgen05 / TMEM / bulk-copy kernels) over tc_emul.h."""
     os.makedirs(OUT, exist_ok=True)
     lib = os.path.join(OUT, 'libmsmd_tc_emul.so')
-    deps = [os.path.join(CSRC, f) for f in ('common.cuh', 'tc_common.cuh', 'tc_trace.cuh', 'spconv_tc.cu', 'spconv_tc16.cu', 'spconv_wgrad_tc.cu')] + \
+    deps = [os.path.join(CSRC, f) for f in ('common.cuh', 'tc_common.cuh', 'tc_trace.cuh', 'spconv_tc.cu', 'spconv_tc16.cu', 'spconv_wgrad_tc.cu', 'spconv_sb.cu')] + \
         [os.path.join(HERE, 'cuda_emul.h'), os.path.join(HERE, 'tc_emul.h'), os.path.abspath(__file__)]
     if os.path.exists(lib) and all(os.path.getmtime(lib) > os.path.getmtime(d) for d in deps):
         return lib
     _INLINED.clear()
     _INLINED.add('tc.cuh')   # replaced by tc_emul.h
-    unit = translate('spconv_tc.cu') + translate('spconv_tc16.cu') + translate('spconv_wgrad_tc.cu')   # tc_common.cuh is inlined once
+    unit = translate('spconv_tc.cu') + translate('spconv_tc16.cu') + translate('spconv_wgrad_tc.cu') + \
+        translate('spconv_sb.cu')   # tc_common.cuh is inlined once
     _INLINED.clear()
     # dynamic shared memory: the window tc_emul.h hands out (deliberately 16-byte aligned only)
     unit, n = re.subn(r'extern __shared__ uint8_t (\w+)\[\];', r'uint8_t* \1 = ::emu::g_dyn_smem;', unit)
@@ -210,7 +212,7 @@ def build_full(verbose=False):
     tests/tools/emu_plugin.py runs the -m gpu tests on."""
     return build_exec(verbose, name='libmsmd_full_emul.so',
                       units=['error_stub', 'voxelize.cu', 'spconv.cu', 'rulebook.cu', 'fusion.cu', 'spconv_tc.cu',
-                             'spconv_tc16.cu', 'spconv_wgrad_tc.cu', 'spconv_bwd.cu', 'executor.cu'])
+                             'spconv_tc16.cu', 'spconv_sb.cu', 'spconv_wgrad_tc.cu', 'spconv_bwd.cu', 'executor.cu'])
 
 
 def build_exec(verbose=False, name='libmsmd_exec_emul.so', units=None):
@@ -218,7 +220,8 @@ def build_exec(verbose=False, name='libmsmd_exec_emul.so', units=None):
     kernels, the mask sort, the SIMT and tensor-core convolutions -- one library, entry points emu_msmd_*."""
     os.makedirs(OUT, exist_ok=True)
     lib = os.path.join(OUT, name)
-    units = units or ['spconv.cu', 'rulebook.cu', 'fusion.cu', 'spconv_tc.cu', 'spconv_tc16.cu', 'executor.cu']
+    units = units or ['spconv.cu', 'rulebook.cu', 'fusion.cu', 'spconv_tc.cu', 'spconv_tc16.cu', 'spconv_sb.cu',
+                      'executor.cu']
     stub = 'error_stub' in units
     units = [u for u in units if u != 'error_stub']
     header = os.path.join(ROOT, 'include', 'msmd_b200.h')

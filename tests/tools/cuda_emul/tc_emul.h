@@ -66,6 +66,7 @@ struct AsyncOp {
 };
 extern std::deque<AsyncOp> g_mma_queue;        // in issue order (one issuing thread per CTA)
 extern std::vector<AsyncOp> g_copy_queue;      // bulk copies complete independently of each other
+extern std::map<int, std::vector<std::function<void()>>> g_cpasync_pending;   // per thread: cp.async not yet tied to a barrier
 extern int g_async_late;
 
 [[noreturn]] static inline void tc_fail(const char* fmt, ...) {
@@ -99,6 +100,7 @@ static inline void tc_block_reset(uint32_t dyn_bytes) {
   for (auto& b : g_named) b = NamedBar();
   g_mma_queue.clear();
   g_copy_queue.clear();
+  g_cpasync_pending.clear();
 }
 static inline void tc_block_check() {
   // whatever is still queued completes now (nobody looked at its barrier any more); the arrivals
@@ -203,7 +205,12 @@ static inline void async_flush_for(uint32_t a) {
     ::emu::g_copy_queue.erase(::emu::g_copy_queue.begin() + (long)i);
     op.run();
     auto& b = ::emu::g_mbar[op.bar];
-    b.tx -= op.tx;
+    if (op.kind == 3) {   // a thread's cp.async group: its (pre-counted) arrival
+      if (b.pending <= 0) ::emu::tc_fail("mbarrier at %u: more arrivals than its count %u", op.bar, b.expected);
+      --b.pending;
+    } else {
+      b.tx -= op.tx;
+    }
     bar_check(b);
   }
 }
@@ -246,6 +253,40 @@ static inline void bulk_g2s(void* dst_smem, const void* src, uint32_t bytes, uin
   op.bar = smem_u32(bar);
   op.tx = bytes;
   op.run = [dst, src, bytes] { memcpy(dst, src, bytes); };
+  ::emu::g_copy_queue.push_back(std::move(op));
+}
+
+// cp.async (LDGSTS) with mbarrier completion: the copies a thread issued are parked per thread and run -- as late as
+// the program allows, like every asynchronous unit here -- when somebody polls the mbarrier that the thread's
+// cp.async.mbarrier.arrive.noinc tied them to; that barrier then receives the thread's arrival
+static inline void cp_async_16(uint32_t dst_smem, const void* src, uint32_t src_bytes) {
+  if ((dst_smem & 15) || ((uintptr_t)src & 15) || (src_bytes != 0 && src_bytes != 16))
+    ::emu::tc_fail("cp.async: dst %u / src %p must be 16-byte aligned, src-size %u must be 0 or 16", dst_smem, src,
+                   src_bytes);
+  uint8_t* dst = ::emu::smem_ptr(dst_smem, 16);
+  std::lock_guard<std::mutex> g(::emu::g_tc_mu);
+  ::emu::g_cpasync_pending[::emu::emu_lin_tid()].push_back([dst, src, src_bytes] {
+    if (src_bytes) memcpy(dst, src, 16); else memset(dst, 0, 16);
+  });
+}
+static inline void cp_async_mbar_arrive_noinc(uint64_t* bar) {
+  std::lock_guard<std::mutex> g(::emu::g_tc_mu);
+  auto& b = bar_at(bar);
+  (void)b;
+  auto copies = std::move(::emu::g_cpasync_pending[::emu::emu_lin_tid()]);
+  ::emu::g_cpasync_pending[::emu::emu_lin_tid()].clear();
+  ::emu::AsyncOp op;
+  op.kind = 3;                 // cp.async group: runs its copies, then ARRIVES (no transaction bytes)
+  op.bar = smem_u32(bar);
+  op.tx = 0;
+  op.run = [copies] { for (auto& c : copies) c(); };
+  if (!::emu::g_async_late) {
+    op.run();
+    if (b.pending <= 0) ::emu::tc_fail("mbarrier at %u: more arrivals than its count %u", op.bar, b.expected);
+    --b.pending;
+    bar_check(b);
+    return;
+  }
   ::emu::g_copy_queue.push_back(std::move(op));
 }
 
@@ -406,6 +447,15 @@ static inline void mma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint
     mma_core(d_tmem, I.N, 16, accumulate, [&](int m, int k) { return smem_h16(adesc, m, k, I.afmt); },
              [&](int n, int k) { return smem_h16(bdesc, n, k, I.bfmt); });
   });
+}
+static inline uint32_t desc_lo32(uint32_t smem_addr) { return (smem_addr & 0x3FFFFu) >> 4; }
+static inline uint32_t desc_hi32_k_sw128() { return (uint32_t)(desc_k_sw128(0) >> 32); }
+static inline void mma_f16_lo(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc,
+                              uint32_t accumulate) {
+  // the low word carries the 14-bit start-address field (and the leading-dimension field above it, unused here):
+  // an add that carried out of the address field would silently corrupt the descriptor on the device
+  if ((a_lo >> 14) || (b_lo >> 14)) ::emu::tc_fail("mma_f16_lo: descriptor low word overflows the address field");
+  mma_f16(d_tmem, ((uint64_t)desc_hi << 32) | a_lo, ((uint64_t)desc_hi << 32) | b_lo, idesc, accumulate);
 }
 static inline void check_a_tmem(uint32_t a_tmem, int cols) {
   if ((a_tmem >> 16) != 0) ::emu::tc_fail("tcgen05.mma: TMEM A address 0x%x has a lane offset", a_tmem);

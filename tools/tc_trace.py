@@ -76,7 +76,7 @@ def mean_of(rows, key):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--sweeps', type=int, default=1)
-    ap.add_argument('--precision', default='tf32x3', choices=['tf32x3', 'bf16x3', 'bf16'])
+    ap.add_argument('--precision', default='tf32x3', choices=['tf32x3', 'bf16x3', 'bf16x3c', 'bf16'])
     ap.add_argument('--mask-sort', action='store_true')
     ap.add_argument('--json', default=None)
     args = ap.parse_args()
@@ -94,7 +94,7 @@ def main():
     from msmdfusion_b200 import _cabi, ops, synthetic
     from msmdfusion_b200 import sparse_encoder as se
     L = _cabi.lib()
-    for name in ('msmd_tc_trace_set', 'msmd_tc16_trace_set'):
+    for name in ('msmd_tc_trace_set', 'msmd_tc16_trace_set', 'msmd_sb_trace_set'):
         getattr(L, name).restype = ctypes.c_int
         getattr(L, name).argtypes = [ctypes.c_void_p]
     L.msmd_tc_trace_record_words.restype = ctypes.c_int
@@ -139,10 +139,12 @@ def main():
         buf.zero_()
         L.msmd_tc_trace_set(buf.data_ptr())
         L.msmd_tc16_trace_set(buf.data_ptr())
+        L.msmd_sb_trace_set(buf.data_ptr())
         ops.spconv_fwd_tc(feat, tcw, pair, sc, sh, res, True, row_perm=row_perm)
         torch.cuda.synchronize()
         L.msmd_tc_trace_set(None)
         L.msmd_tc16_trace_set(None)
+        L.msmd_sb_trace_set(None)
         rows = summarize(buf.cpu().numpy().astype(np.uint64).reshape(CTAS, words), mhz)
         name = '%d->%d k%d%s' % (r['cin'], r['cout'], r['kvol'], '+res' if r['residual'] else '')
         print('%-22s %7d %6.0f | %6.2fus %7.0f%% %8.0f%% %8.0f%% %8.0f%% %6.0f%% %6.2fus | %6.1f %6.1f %6.1f %6.1fus' % (
