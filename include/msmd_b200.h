@@ -340,6 +340,12 @@ MSMD_API int msmd_sparse_net_forward(const msmd_conv_layer* layers, int n_layers
                                      msmd_sparse_desc* acts /* host [n_layers + 1] */,
                                      msmd_stream_t stream);
 
+/* The executor's geometry stream (a cudaStream_t) of the current device.  Index sets and rulebooks of a
+ * msmd_sparse_net_forward call are complete once everything queued on it at the call's return has run: consumers of
+ * the COORDINATES only (MSMDFusion.py:251-325 voxel_modality_split, :276-323 fps_NN_fast) may wait for an event
+ * recorded there instead of for the feature convolutions on the caller's stream. */
+MSMD_API int msmd_executor_geometry_stream(void** stream_out);
+
 /* SparseConvTensor.dense(): (n,c) rows -> (batch, c, D, H, W), zero-filled inside.
  * spconv-1.x equivalent mmdet3d/ops/spconv/structure.py:54-66. */
 MSMD_API int msmd_to_dense(const int* indices, const float* features, int n, int c, int batch_size,

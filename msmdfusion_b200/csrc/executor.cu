@@ -122,6 +122,20 @@ static int ensure_grid(IndexSetX& s, int batch, Arena& arena, void* scan_ws, siz
   return MSMD_OK;
 }
 
+// The library-owned geometry stream of the current device (created on first use).  A caller that wants to start
+// work which depends on an executor call's COORDINATES only (index sets, rulebooks) -- not on its features -- records
+// an event on this stream right after the call returns and waits for that instead of for its own stream.
+extern "C" MSMD_API int msmd_executor_geometry_stream(void** stream_out) {
+  MSMD_REQUIRE(stream_out, "executor_geometry_stream: null argument");
+  int dev = 0;
+  MSMD_CUDA_OK(cudaGetDevice(&dev));
+  MSMD_REQUIRE(dev >= 0 && dev < 16, "executor_geometry_stream: device ordinal %d unsupported", dev);
+  AuxStreams* aux = &g_aux[dev];
+  if (!aux->geom) MSMD_CUDA_OK(cudaStreamCreateWithFlags(&aux->geom, cudaStreamNonBlocking));
+  *stream_out = (void*)aux->geom;
+  return MSMD_OK;
+}
+
 extern "C" MSMD_API int msmd_spconv_set_mask_sort(int enable) {
   g_mask_sort = enable ? 1 : 0;
   return MSMD_OK;

@@ -261,17 +261,20 @@ spconv_fwd_sb_kernel(const uint16_t* __restrict__ xs, const uint16_t* __restrict
     if (tid == 0) TC_TRACE_HEAD(4, clock64());
   } else if (warp == kTcProducerWarps) {
     // ===== B loader ================================================================================
-    if (lane == 0) {
+    {
       const uint32_t bytes = (uint32_t)(2 * N * 128);
       int s = 0;
       uint32_t ph = 1u;
       for (int t = 0; t < n_act; ++t) {
-        TC_TRACE(2, t, 0);
+        if (lane == 0) TC_TRACE(2, t, 0);
         tc::mbar_wait(&empty_bar[s], ph);
-        TC_TRACE(2, t, 1);
-        tc::mbar_arrive_expect_tx(&full_bar[s], bytes);
-        tc::bulk_g2s(smem + (size_t)s * stage_bytes + 2 * kSbABytes, (const uint8_t*)wpk + (size_t)alist[t] * bytes,
-                     bytes, &full_bar[s]);
+        if (lane == 0) TC_TRACE(2, t, 1);
+        const uint8_t* src = (const uint8_t*)wpk + (size_t)alist[t] * bytes;
+        if (tc::elect_one()) {
+          tc::mbar_arrive_expect_tx(&full_bar[s], bytes);
+          tc::bulk_g2s(smem + (size_t)s * stage_bytes + 2 * kSbABytes, src, bytes, &full_bar[s]);
+        }
+        __syncwarp();
         if (++s == stages) { s = 0; ph ^= 1u; }
       }
     }
@@ -279,7 +282,8 @@ spconv_fwd_sb_kernel(const uint16_t* __restrict__ xs, const uint16_t* __restrict
     // ===== MMA issuer ==============================================================================
     // One lane issues everything, so its instruction count is a per-chunk floor: descriptors are 32-bit low
     // words over one constant high word, advanced by integer adds (tc::mma_f16_lo).
-    if (lane == 0) {
+    // The whole warp runs the loop (converged); the asynchronous-unit instructions are issued by the elected lane.
+    {
       const uint32_t idesc = tc::idesc_f32acc(tc::kFmtBF16, kTcM, N);
       const uint32_t idesc2 = tc::idesc_f32acc(tc::kFmtBF16, kTcM, 2 * N);
       const uint32_t dhi = tc::desc_hi32_k_sw128();
@@ -290,30 +294,34 @@ spconv_fwd_sb_kernel(const uint16_t* __restrict__ xs, const uint16_t* __restrict
       int s = 0;
       uint32_t ph = 0;
       for (int t = 0; t < n_act; ++t) {
-        TC_TRACE(3, t, 0);
+        if (lane == 0) TC_TRACE(3, t, 0);
         tc::mbar_wait(&full_bar[s], ph);
-        TC_TRACE(3, t, 1);
+        if (lane == 0) TC_TRACE(3, t, 1);
         tc::fence_proxy_async();   // cp.async wrote the A tile through the generic proxy
         tc::fence_after_sync();
         const uint32_t a = lo0 + (uint32_t)s * stage_lo;
+        if (tc::elect_one()) {
 #pragma unroll
-        for (int ks = 0; ks < kSbKC / 16; ++ks) {
-          const uint32_t ah = a + (uint32_t)ks * 2u;   // 16 bf16 = 32 bytes along K = 2 descriptor units
-          if (cat) {
-            tc::mma_f16_lo(tmem_base, ah, ah + b_hi_off, dhi, idesc2, accumulate);   // D[:, 0:2N] += A_hi * [B_hi; B_lo]
-            tc::mma_f16_lo(tmem_base, ah + a_lo_off, ah + b_hi_off, dhi, idesc, 1u);  // D[:, 0:N]  += A_lo * B_hi
-          } else {
-            tc::mma_f16_lo(tmem_base, ah + a_lo_off, ah + b_hi_off, dhi, idesc, accumulate);
-            tc::mma_f16_lo(tmem_base, ah, ah + b_lo_off, dhi, idesc, 1u);
-            tc::mma_f16_lo(tmem_base, ah, ah + b_hi_off, dhi, idesc, 1u);
+          for (int ks = 0; ks < kSbKC / 16; ++ks) {
+            const uint32_t ah = a + (uint32_t)ks * 2u;   // 16 bf16 = 32 bytes along K = 2 descriptor units
+            if (cat) {
+              tc::mma_f16_lo(tmem_base, ah, ah + b_hi_off, dhi, idesc2, accumulate);   // D[:, 0:2N] += A_hi * [B_hi; B_lo]
+              tc::mma_f16_lo(tmem_base, ah + a_lo_off, ah + b_hi_off, dhi, idesc, 1u);  // D[:, 0:N]  += A_lo * B_hi
+            } else {
+              tc::mma_f16_lo(tmem_base, ah + a_lo_off, ah + b_hi_off, dhi, idesc, accumulate);
+              tc::mma_f16_lo(tmem_base, ah, ah + b_lo_off, dhi, idesc, 1u);
+              tc::mma_f16_lo(tmem_base, ah, ah + b_hi_off, dhi, idesc, 1u);
+            }
+            accumulate = 1u;
           }
-          accumulate = 1u;
+          tc::mma_commit(&empty_bar[s]);
+          if (t == n_act - 1) tc::mma_commit(accum_bar);   // accumulator complete -> epilogue
         }
-        tc::mma_commit(&empty_bar[s]);
-        TC_TRACE(3, t, 2);
+        __syncwarp();
+        accumulate = 1u;
+        if (lane == 0) TC_TRACE(3, t, 2);
         if (++s == stages) { s = 0; ph ^= 1u; }
       }
-      if (n_act > 0) tc::mma_commit(accum_bar);
     }
   }
 

@@ -12,6 +12,21 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return (uint32_t)__cvta_generic_to_shared(p);
 }
 
+// One lane of a CONVERGED warp (all 32 lanes must execute it).  Single-thread instructions of the asynchronous units
+// (tcgen05.mma / commit, bulk copies) are issued under this predicate rather than under `lane == 0`: ptxas then knows
+// exactly one thread is active and moves their operands to uniform registers once, instead of wrapping every such
+// instruction in a per-lane "waterfall" loop (ELECT / R2UR.BROADCAST x7 / BRA.U.ANY, ~15 instructions per MMA in the
+// round-1 kernels, which made the MMA issuer the per-chunk bottleneck of the small-N layers).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred)::"memory");
+  return pred != 0;
+}
+
 // ---- mbarrier -------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");

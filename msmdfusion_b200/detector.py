@@ -18,6 +18,7 @@ B200-first differences that cannot change results:
   of GPU sort -> CPU numba merge -> GPU.
 """
 import contextlib
+import os
 
 import numpy as np
 import torch
@@ -384,8 +385,8 @@ class MSMDFusionDetector(nn.Module, _VoxelPathMixin):
 
     # -- :400-418 ---------------------------------------------------------------------------
     def extract_multiscale_voxel_feat(self, img_feats, encode_features, img_metas, spatial_shapes,
-                                      downscale_factors, batch_size):
-        img_feats = self.depth_aware_channel_compression(img_feats, img_metas)
+                                      downscale_factors, batch_size, compressed=None):
+        img_feats = compressed if compressed is not None else self.depth_aware_channel_compression(img_feats, img_metas)
         img_feat_list = [img_feats[0]] + list(img_feats)
         v3l, v2l, s3l, s2l = [], [], [], []
         for i in range(4):
@@ -401,19 +402,66 @@ class MSMDFusionDetector(nn.Module, _VoxelPathMixin):
         return v3l, v2l, s3l, s2l
 
     # -- :421-452 ---------------------------------------------------------------------------
+    # Inference schedule (CUDA, no grad, LiDAR encoder on the native executor): everything on the image side
+    # of the fusion -- depth-aware compression, 4x (lift, voxelize, modality split) and the FPS / nearest-voxel
+    # assignment chains (2047 serial rounds each) -- depends on the LiDAR branch through voxel COORDINATES only.
+    # Those are complete on the executor's geometry stream ~0.4 ms into the encoder call, long before its 21
+    # convolutions have run, so that work is issued on a side stream that waits for the geometry and overlaps
+    # the LiDAR convolutions instead of queueing behind them (the reference runs all of it in sequence,
+    # MSMDFusion.py:421-445).  Same kernels, same operands: results are unchanged.
+    overlap_image_side = os.environ.get('MSMD_LC_OVERLAP', '1') not in ('', '0')   # A/B switch
+
+    def _side(self, device):
+        st = self.__dict__.get('_image_side_stream')
+        if st is None or st.device != device:
+            st = self.__dict__['_image_side_stream'] = torch.cuda.Stream(device=device)
+        return st
+
     def extract_voxel_space(self, pts, img_feats, img_metas):
         """The voxel-space fusion hot path: returns the (B, 256 + 384, 180, 180) BEV tensor that
         ``bev_fusion`` consumes, plus the multimodal stage outputs."""
         batch_size = len(pts)
         nf = min(self.pts_voxel_encoder.num_features, pts[0].shape[1])  # [:64] of 5 dims after :386
+        dev = pts[0].device
+        overlap = (self.overlap_image_side and dev.type == 'cuda' and not torch.is_grad_enabled() and
+                   getattr(self.pts_middle_encoder, 'use_executor', False))
+        compressed = None
+        if overlap:
+            # the compression convolutions (cuDNN) do not depend on the LiDAR branch: issue them first so that the
+            # side stream below never waits behind the LiDAR convolutions for them
+            compressed = self.depth_aware_channel_compression(img_feats, img_metas)
         voxel_features, coors, _ = self.voxelize_mean(pts, nf)
         # a frozen LiDAR encoder (tools/train.py:185-211) has no grad-requiring input either (voxelize is
         # no_grad, :462-464), so autograd would skip it anyway: run it on the inference path
         frozen = torch.is_grad_enabled() and not any(p.requires_grad for p in self.pts_middle_encoder.parameters())
+        main = torch.cuda.current_stream(dev) if overlap else None
+        if overlap:
+            inputs_ready = torch.cuda.Event()
+            inputs_ready.record(main)
         with (torch.no_grad() if frozen else contextlib.nullcontext()):
             x, encode_features = self.pts_middle_encoder(voxel_features, coors, batch_size)
-        v3l, v2l, s3l, s2l = self.extract_multiscale_voxel_feat(
-            img_feats, encode_features, img_metas, self.spatial_shapes, self.downscale_factors, batch_size)
+        if overlap and getattr(self.pts_middle_encoder, 'ran_on_executor', False):
+            from . import executor
+            geom_done = torch.cuda.Event()
+            geom_done.record(executor.geometry_stream(dev))
+            side = self._side(dev)
+            side.wait_event(inputs_ready)   # compressed image features, the packed virtual points
+            side.wait_event(geom_done)      # index sets of the four LiDAR scales
+            # Allocator note: tensors created under `side` and read later on `main` are safe without record_stream.
+            # `main` waits for `image_side_done` before it reads them, and the side stream only ever starts a step's
+            # work after waiting for an event recorded on `main` (inputs_ready), i.e. after every main-stream reader
+            # of the previous step's blocks has been queued AND finished before the blocks can be rewritten.
+            with torch.cuda.stream(side):
+                v3l, v2l, s3l, s2l = self.extract_multiscale_voxel_feat(
+                    img_feats, encode_features, img_metas, self.spatial_shapes, self.downscale_factors, batch_size,
+                    compressed=compressed)
+                image_side_done = torch.cuda.Event()
+                image_side_done.record(side)
+            main.wait_event(image_side_done)
+        else:
+            v3l, v2l, s3l, s2l = self.extract_multiscale_voxel_feat(
+                img_feats, encode_features, img_metas, self.spatial_shapes, self.downscale_factors, batch_size,
+                compressed=compressed)
         stage_outs = self.multimodal_middle_encoder(
             v3l, v2l, s3l, s2l, self.fps_num_list, self.radius_list, self.max_cluster_samples_list,
             self.dist_thresh_list)

@@ -156,3 +156,11 @@ def plan_key(modules):
             key.append((t.data_ptr(), t._version))
         key.append(m.training)
     return tuple(key)
+
+
+def geometry_stream(device):
+    """The executor's library-owned geometry stream of ``device`` as a torch stream (``msmd_executor_geometry_stream``)."""
+    with torch.cuda.device(device):
+        h = ctypes.c_void_p()
+        check(lib().msmd_executor_geometry_stream(ctypes.byref(h)), 'msmd_executor_geometry_stream')
+    return torch.cuda.ExternalStream(h.value, device=device)

@@ -73,6 +73,7 @@ class SparseEncoder(nn.Module):
     def forward(self, voxel_features, coors, batch_size):
         """sparse_encoder.py:96-133 -> (spatial_features (B, C*D, H, W), encode_features)."""
         coors = coors.int()
+        self.ran_on_executor = False   # True: the geometry of this call ran on the executor's geometry stream
         if self.use_executor and voxel_features.is_cuda and not torch.is_grad_enabled():
             try:
                 plan, marks = self._plan_for()
@@ -86,6 +87,7 @@ class SparseEncoder(nn.Module):
                 f, idx, shape = acts[marks[-1]]
                 spatial_features = ops.to_dense(idx, f, shape, B)
                 N, C, D, H, W = spatial_features.shape
+                self.ran_on_executor = True
                 return spatial_features.view(N, C * D, H, W), encode_features
         x = spconv.SparseConvTensor(voxel_features, coors, self.sparse_shape, batch_size)
         x = self.conv_input(x)

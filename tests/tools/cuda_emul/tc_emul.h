@@ -145,6 +145,11 @@ static inline uint32_t smem_u32(const void* p) {
   return (uint32_t)d;
 }
 
+static inline bool elect_one() {   // a converged warp elects one lane: the model always picks lane 0
+  __syncwarp();
+  return (::emu::emu_lin_tid() & 31) == 0;
+}
+
 // ---- mbarrier -------------------------------------------------------------------------
 static inline ::emu::MBar& bar_at(uint64_t* bar, bool must_exist = true) {
   const uint32_t a = smem_u32(bar);
