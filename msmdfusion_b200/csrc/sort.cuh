@@ -18,7 +18,7 @@ constexpr int kSortItems = 8;  // keys per thread per tile
 constexpr int kSortTile = kSortThreads * kSortItems;
 constexpr int kSortRadix = 256;
 
-__global__ void __launch_bounds__(kSortThreads)
+static __global__ void __launch_bounds__(kSortThreads)
 sort_hist_kernel(const uint32_t* __restrict__ keys, int n, int shift, int* __restrict__ hist,
                  int nblocks) {
   __shared__ int h[kSortRadix];
@@ -42,7 +42,7 @@ struct StoreInt {
   __device__ void operator()(int i, int ex, int) const { p[i] = ex; }
 };
 
-__global__ void __launch_bounds__(kSortThreads)
+static __global__ void __launch_bounds__(kSortThreads)
 sort_scatter_kernel(const uint32_t* __restrict__ keys_in, const int* __restrict__ vals_in, int n,
                     int shift, const int* __restrict__ offsets, int nblocks,
                     uint32_t* __restrict__ keys_out, int* __restrict__ vals_out) {

@@ -587,7 +587,7 @@ def test_full_size_16bit_modes_mask_sort_and_tc_wgrad_properties():
     y32 = ops.spconv_fwd_tc(x1, w32, pair)
     # mask-sorted tiles at full size: same rows, same values (no split-K at this tile count)
     assert torch.equal(ops.spconv_fwd_tc(x1, w32, pair_sorted, row_perm=row_perm), y32)
-    for mode, tol in (('bf16x3', 5e-5), ('bf16', 1e-2)):
+    for mode, tol in (('bf16x3', 5e-5), ('bf16', 3e-2)):   # absolute at |y| ~ 8; bf16 is not a parity mode
         tcw = ops.pack_weight_tc(w, ops.TC_MODES[mode])
         y = ops.spconv_fwd_tc(x1, tcw, pair)
         assert err(y, y32) < tol                                             # agreement with the 3xTF32 kernel
