@@ -358,9 +358,6 @@ MSMD_API int msmd_to_dense(const int* indices, const float* features, int n, int
  *   One batch element per call: xyz (n,3), idx (m).
  * ---------------------------------------------------------------------------------- */
 MSMD_API size_t msmd_fps_workspace(int n);
-/* 0 (default): bucketed exact FPS (csrc/points.cu) where it applies; 1: the brute-force kernels only (A/B switch;
- * both produce the reference's picks bit for bit) */
-MSMD_API int msmd_fps_set_algorithm(int algo);
 MSMD_API int msmd_fps(const float* xyz, int n, int m, int* idx, void* workspace,
                       size_t workspace_bytes, msmd_stream_t stream);
 

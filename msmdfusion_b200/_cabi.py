@@ -94,7 +94,6 @@ SIGNATURES = {
     'msmd_sparse_net_forward': (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _c_int_p, _vp, _sz, _vp, _vp]),
     'msmd_to_dense': (_i, [_vp, _vp, _i, _i, _i, _c_int_p, _vp, _vp]),
     'msmd_fps_workspace': (_sz, [_i]),
-    'msmd_fps_set_algorithm': (_i, [_i]),
     'msmd_fps': (_i, [_vp, _i, _i, _vp, _vp, _sz, _vp]),
     'msmd_ball_query': (_i, [_vp, _i, _vp, _i, ctypes.c_float, ctypes.c_float, _i, _vp, _vp]),
     'msmd_nn_search': (_i, [_vp, _i, _i, _vp, _i, _i, _vp, _vp, _vp]),

@@ -4,7 +4,7 @@
 #include <cooperative_groups.h>
 #include <math.h>
 
-#include "sort.cuh"
+#include "common.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -27,8 +27,9 @@ namespace msmd {
 // hundred cycles instead of a 50 k-point single-SM sweep.
 // ------------------------------------------------------------------------------------
 constexpr int kFpsCluster = 8;
-constexpr int kFpsThreads = 512;
-constexpr int kFpsMaxPerThread = 24;  // 8*512*24 = 98304 points in registers
+constexpr int kFpsThreadsWide = 1024;  // <= 8 points per thread (64 registers): 8*1024*8 = 65536 points
+constexpr int kFpsThreadsDeep = 512;   // up to 24 points per thread: 8*512*24 = 98304 points in registers
+constexpr int kFpsMaxPerThread = 24;
 
 __device__ __forceinline__ unsigned long long u64max(unsigned long long a, unsigned long long b) {
   return a > b ? a : b;
@@ -74,7 +75,7 @@ __device__ __forceinline__ unsigned long long fps_warp_max(unsigned long long ke
   return ((unsigned long long)mhi << 32) | mlo;
 }
 
-template <int PPT>
+template <int PPT, int kFpsThreads>
 __global__ void __cluster_dims__(kFpsCluster, 1, 1) __launch_bounds__(kFpsThreads, 1)
 fps_cluster_kernel(const float* __restrict__ xyz, int n, int m, int block, int log2block,
                    int* __restrict__ idx) {
@@ -248,259 +249,6 @@ fps_single_kernel(const float* __restrict__ xyz, int n, int m, int block, int lo
     if (tid == 0) idx[r] = old;
   }
 }
-
-
-// ------------------------------------------------------------------------------------
-// Bucketed EXACT furthest point sampling (the default for 1024 <= n <= 65536).
-//
-// The brute-force kernels above touch every point in every one of the m-1 serial rounds.  But a round only
-// changes temp[k] = min(temp[k], d(k, last)) for points closer to the new sample than to every earlier one, and
-// after the first few dozen samples that is a small neighbourhood.  So the points are sorted once into spatially
-// coherent buckets of 32 (16-bit Morton key of the bounding-box-normalised coordinates, stable radix sort), each
-// with its bounding box and the packed arg-max key (float_bits(temp) << 32 | ~priority) of its best point.  A
-// round then is
-//   A  every thread tests ~nb/1024 buckets: lower bound of d(sample, box) -- the SAME expression as the point
-//      distance evaluated at the box's nearest coordinates, which is a lower bound of every member's distance
-//      under fp32 rounding (subtraction, squaring and the sums are monotone), relaxed by 1e-5 -- against the
-//      bucket's largest temp; buckets that cannot change are skipped;
-//   B  one warp per dirty bucket: the reference's update of its 32 points, new bucket key + best point's xyz;
-//   C  block-wide arg-max over the bucket keys (the same total order as the reference's tie-break, so ANY
-//      grouping of the points gives the reference's pick, bit for bit).
-// One CTA, three __syncthreads per round, no inter-SM traffic on the serial chain; the work per round falls
-// from n points to a few buckets.  Bucket tables live in shared memory, the sorted points in global memory
-// (L2) or, for n <= 8192, in shared memory too.
-// ------------------------------------------------------------------------------------
-constexpr int kFpsBThreads = 1024;
-constexpr int kFpsBMaxN = 65536;
-constexpr int kFpsBMaxBuckets = kFpsBMaxN / 32;
-constexpr int kFpsBSmemPoints = 8192;
-
-__global__ void __launch_bounds__(1024)
-fps_bbox_kernel(const float* __restrict__ xyz, int n, float* __restrict__ bbox) {
-  __shared__ float red[6][32];
-  float lo[3] = {3.4e38f, 3.4e38f, 3.4e38f}, hi[3] = {-3.4e38f, -3.4e38f, -3.4e38f};
-  for (int k = threadIdx.x; k < n; k += blockDim.x) {
-#pragma unroll
-    for (int a = 0; a < 3; ++a) {
-      const float v = xyz[3 * k + a];
-      lo[a] = fminf(lo[a], v);
-      hi[a] = fmaxf(hi[a], v);
-    }
-  }
-#pragma unroll
-  for (int a = 0; a < 3; ++a) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      lo[a] = fminf(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], o));
-      hi[a] = fmaxf(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], o));
-    }
-    if ((threadIdx.x & 31) == 0) { red[a][threadIdx.x >> 5] = lo[a]; red[3 + a][threadIdx.x >> 5] = hi[a]; }
-  }
-  __syncthreads();
-  if (threadIdx.x < 32) {
-    const int nw = blockDim.x >> 5;
-#pragma unroll
-    for (int a = 0; a < 3; ++a) {
-      float l = threadIdx.x < nw ? red[a][threadIdx.x] : 3.4e38f;
-      float h = threadIdx.x < nw ? red[3 + a][threadIdx.x] : -3.4e38f;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        l = fminf(l, __shfl_xor_sync(0xffffffffu, l, o));
-        h = fmaxf(h, __shfl_xor_sync(0xffffffffu, h, o));
-      }
-      if (threadIdx.x == 0) { bbox[a] = l; bbox[3 + a] = h; }
-    }
-  }
-}
-
-__device__ __forceinline__ uint32_t fps_spread3(uint32_t v) {   // 6 bits -> every third bit
-  v &= 0x3Fu;
-  v = (v | (v << 8)) & 0x300Fu;
-  v = (v | (v << 4)) & 0x30C3u;
-  v = (v | (v << 2)) & 0x9249u;
-  return v;
-}
-
-__global__ void __launch_bounds__(256)
-fps_cell_key_kernel(const float* __restrict__ xyz, int n, const float* __restrict__ bbox,
-                    uint32_t* __restrict__ keys) {
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= n) return;
-  uint32_t q[3];
-#pragma unroll
-  for (int a = 0; a < 3; ++a) {
-    const float lo = bbox[a], ext = bbox[3 + a] - lo;
-    float t = ext > 0.f ? (xyz[3 * k + a] - lo) / ext : 0.f;
-    t = fminf(fmaxf(t, 0.f), 1.f);       // NaN coordinates land in cell 0: any bucketing is valid
-    const int c = (int)(t * (a == 2 ? 15.999f : 63.999f));
-    q[a] = (uint32_t)(c < 0 ? 0 : c);
-  }
-  // 16-bit key: the 4 z bits on top of a 12-bit (x, y) Morton code -- two radix passes
-  const uint32_t xy = (fps_spread3(q[0]) | (fps_spread3(q[1]) << 1));   // bits 3i, 3i+1: compact below
-  uint32_t m = 0;
-#pragma unroll
-  for (int i = 0; i < 6; ++i) m |= ((xy >> (3 * i)) & 3u) << (2 * i);
-  keys[k] = ((q[2] & 15u) << 12) | m;
-}
-
-// sorted order -> SoA copies + per-bucket bounding boxes (one warp per bucket of 32 sorted points)
-__global__ void __launch_bounds__(256)
-fps_gather_kernel(const float* __restrict__ xyz, const int* __restrict__ order, int n, float* __restrict__ sx,
-                  float* __restrict__ sy, float* __restrict__ sz, float* __restrict__ temp,
-                  float* __restrict__ bbox6 /* [6][nb] */, int nb) {
-  const int p = blockIdx.x * blockDim.x + threadIdx.x;
-  const int b = p >> 5;
-  float x = 0.f, y = 0.f, z = 0.f;
-  const bool valid = p < n;
-  if (valid) {
-    const int k = order[p];
-    x = xyz[3 * k + 0]; y = xyz[3 * k + 1]; z = xyz[3 * k + 2];
-    sx[p] = x; sy[p] = y; sz[p] = z;
-    temp[p] = 1e10f;   // furthest_point_sample.py:28
-  }
-  float lo[3] = {valid ? x : 3.4e38f, valid ? y : 3.4e38f, valid ? z : 3.4e38f};
-  float hi[3] = {valid ? x : -3.4e38f, valid ? y : -3.4e38f, valid ? z : -3.4e38f};
-#pragma unroll
-  for (int a = 0; a < 3; ++a) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      lo[a] = fminf(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], o));
-      hi[a] = fmaxf(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], o));
-    }
-  }
-  if ((threadIdx.x & 31) == 0 && b < nb) {
-#pragma unroll
-    for (int a = 0; a < 3; ++a) { bbox6[a * nb + b] = lo[a]; bbox6[(3 + a) * nb + b] = hi[a]; }
-  }
-}
-
-__global__ void __launch_bounds__(kFpsBThreads, 1)
-fps_bucket_kernel(const float* __restrict__ xyz, int n, int m, int block, int log2block, const int* __restrict__ order,
-                  float* sx_g, float* sy_g, float* sz_g, float* temp_g, const float* __restrict__ bbox6, int nb,
-                  int points_in_smem, int* __restrict__ idx) {
-  extern __shared__ unsigned long long fps_smem[];
-  unsigned long long* bkey = fps_smem;                       // [nb]
-  float* bb = (float*)(bkey + nb);                           // [6][nb] bucket boxes
-  float* bbest = bb + 6 * nb;                                // [nb][3] xyz of the bucket's best point
-  int* dirty = (int*)(bbest + 3 * nb);                       // [nb]
-  float* pts = (float*)(dirty + nb);                         // optional [4][n]: sx | sy | sz | temp
-  __shared__ unsigned long long warp_best[2][kFpsBThreads / 32];
-  __shared__ int warp_bkt[2][kFpsBThreads / 32];
-  __shared__ int ndirty[2];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-
-  float *sx = sx_g, *sy = sy_g, *sz = sz_g, *temp = temp_g;
-  if (points_in_smem) {
-    sx = pts; sy = pts + n; sz = pts + 2 * n; temp = pts + 3 * n;
-    for (int p = tid; p < n; p += kFpsBThreads) {
-      sx[p] = sx_g[p]; sy[p] = sy_g[p]; sz[p] = sz_g[p]; temp[p] = 1e10f;
-    }
-  }
-  const unsigned long long key0 = (unsigned long long)__float_as_uint(1e10f) << 32;
-  for (int b = tid; b < nb; b += kFpsBThreads) {
-    bkey[b] = key0;   // every bucket is dirty in the first round
-#pragma unroll
-    for (int a = 0; a < 6; ++a) bb[a * nb + b] = bbox6[a * nb + b];
-  }
-  if (tid < 2) ndirty[tid] = 0;
-  float x1 = __ldg(xyz + 0), y1 = __ldg(xyz + 1), z1 = __ldg(xyz + 2);   // round 0 picks point 0
-  if (tid == 0) idx[0] = 0;
-  __syncthreads();
-
-  for (int r = 1; r < m; ++r) {
-    const int par = r & 1;
-    // ---- A: which buckets can change? ---------------------------------------------------------
-    for (int b0 = 0; b0 < nb; b0 += kFpsBThreads) {
-      const int b = b0 + tid;
-      bool d = false;
-      if (b < nb) {
-        const float dx = fmaxf(fmaxf(bb[b] - x1, x1 - bb[3 * nb + b]), 0.f);
-        const float dy = fmaxf(fmaxf(bb[nb + b] - y1, y1 - bb[4 * nb + b]), 0.f);
-        const float dz = fmaxf(fmaxf(bb[2 * nb + b] - z1, z1 - bb[5 * nb + b]), 0.f);
-        const float lb = dx * dx + dy * dy + dz * dz;
-        d = lb * 0.99999f <= __uint_as_float((unsigned)(bkey[b] >> 32));
-      }
-      const unsigned mask = __ballot_sync(0xffffffffu, d);
-      if (mask) {
-        int base = 0;
-        if (lane == 0) base = atomicAdd(&ndirty[par], __popc(mask));
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (d) dirty[base + __popc(mask & ((1u << lane) - 1u))] = b;
-      }
-    }
-    __syncthreads();
-    // ---- B: the reference's update, for the points of the dirty buckets -----------------------
-    const int nd = ndirty[par];
-    for (int i = warp; i < nd; i += kFpsBThreads / 32) {
-      const int b = dirty[i];
-      const int p = b * 32 + lane;
-      unsigned long long key = 0ull;
-      float px = 0.f, py = 0.f, pz = 0.f;
-      if (p < n) {
-        px = sx[p]; py = sy[p]; pz = sz[p];
-        const float t = temp[p];
-        const float dd = (px - x1) * (px - x1) + (py - y1) * (py - y1) + (pz - z1) * (pz - z1);
-        const float d2 = fminf(dd, t);
-        if (d2 != t) temp[p] = d2;
-        key = ((unsigned long long)__float_as_uint(d2) << 32) |
-              (unsigned long long)(~fps_priority(__ldg(order + p), block, log2block));
-      }
-      const unsigned long long g = fps_warp_max(key);
-      if (key == g && p < n) {   // priorities are unique: exactly one lane
-        bkey[b] = g;
-        bbest[3 * b + 0] = px; bbest[3 * b + 1] = py; bbest[3 * b + 2] = pz;
-      }
-    }
-    __syncthreads();
-    // ---- C: arg-max over the bucket keys -----------------------------------------------------
-    unsigned long long best = 0ull;
-    int bestb = 0;
-    for (int b = tid; b < nb; b += kFpsBThreads) {
-      const unsigned long long k = bkey[b];
-      if (k > best) { best = k; bestb = b; }
-    }
-    const unsigned long long wm = fps_warp_max(best);
-    const int src = __ffs(__ballot_sync(0xffffffffu, best == wm)) - 1;
-    const int wb = __shfl_sync(0xffffffffu, bestb, src);
-    if (lane == 0) { warp_best[par][warp] = wm; warp_bkt[par][warp] = wb; }
-    if (tid == 0) ndirty[par ^ 1] = 0;   // last read in the previous round, next written after this barrier
-    __syncthreads();
-    const unsigned long long v = warp_best[par][lane];
-    const int vb = warp_bkt[par][lane];
-    const unsigned long long g = fps_warp_max(v);
-    const int src2 = __ffs(__ballot_sync(0xffffffffu, v == g)) - 1;
-    const int gb = __shfl_sync(0xffffffffu, vb, src2);
-    x1 = bbest[3 * gb + 0]; y1 = bbest[3 * gb + 1]; z1 = bbest[3 * gb + 2];
-    if (tid == 0) {
-      const unsigned pr = ~(unsigned)(g & 0xffffffffull);
-      const unsigned rev = pr >> 22, q = pr & ((1u << 22) - 1u);
-      const unsigned t = log2block ? (__brev(rev) >> (32 - log2block)) : 0u;
-      idx[r] = (int)((q << log2block) | t);
-    }
-  }
-}
-
-struct FpsBWs {
-  float* bbox;
-  uint32_t* keys;
-  int* order;
-  float *sx, *sy, *sz, *temp, *bbox6;
-  SortWs sort;
-  bool carve(Workspace& ws, int n) {
-    const int nb = ceil_div(n > 0 ? n : 1, 32);
-    bbox = ws.take<float>(8);
-    keys = ws.take<uint32_t>(n > 0 ? n : 1);
-    order = ws.take<int>(n > 0 ? n : 1);
-    sx = ws.take<float>(n > 0 ? n : 1);
-    sy = ws.take<float>(n > 0 ? n : 1);
-    sz = ws.take<float>(n > 0 ? n : 1);
-    temp = ws.take<float>(n > 0 ? n : 1);
-    bbox6 = ws.take<float>((size_t)6 * nb);
-    return sort.carve(ws, n);
-  }
-};
-
-static int g_fps_algo = 0;   // 0 auto (bucketed where it applies) | 1 brute force (the round-1 kernels)
 
 // Fallback for point sets that do not fit the register-resident cluster kernel: one CTA,
 // temp[] in global memory, same tie-break rule.
@@ -684,20 +432,7 @@ static int fps_block_size(int n, int* log2block) {
 
 using namespace msmd;
 
-extern "C" MSMD_API size_t msmd_fps_workspace(int n) {
-  Workspace ws((void*)256, ~(size_t)0 >> 1);
-  FpsBWs b;
-  b.carve(ws, n);
-  const size_t brute = (size_t)(n > 0 ? n : 1) * sizeof(float) + 256;
-  return (ws.used > brute ? ws.used : brute) + 256;
-}
-
-// 0 (default): bucketed exact FPS for 1024 <= n <= 65536, the brute-force kernels elsewhere; 1: brute force only
-extern "C" MSMD_API int msmd_fps_set_algorithm(int algo) {
-  MSMD_REQUIRE(algo == 0 || algo == 1, "fps_set_algorithm: 0 (auto) or 1 (brute force)");
-  g_fps_algo = algo;
-  return MSMD_OK;
-}
+extern "C" MSMD_API size_t msmd_fps_workspace(int n) { return (size_t)(n > 0 ? n : 1) * sizeof(float) + 256; }
 
 extern "C" MSMD_API int msmd_fps(const float* xyz, int n, int m, int* idx, void* workspace,
                                  size_t workspace_bytes, msmd_stream_t stream_) {
@@ -706,32 +441,8 @@ extern "C" MSMD_API int msmd_fps(const float* xyz, int n, int m, int* idx, void*
   int log2block = 0;
   const int block = fps_block_size(n, &log2block);
   MSMD_REQUIRE((n >> log2block) < (1 << 22), "fps: too many points");
-  const long long cap = (long long)kFpsCluster * kFpsThreads;
-  if (g_fps_algo == 0 && n >= 1024 && n <= kFpsBMaxN && m > 1 && workspace &&
-      workspace_bytes >= msmd_fps_workspace(n)) {
-    Workspace ws(workspace, workspace_bytes);
-    FpsBWs b;
-    MSMD_REQUIRE(b.carve(ws, n), "fps: workspace too small");
-    const int nb = ceil_div(n, 32);
-    fps_bbox_kernel<<<1, 1024, 0, stream>>>(xyz, n, b.bbox);
-    MSMD_LAUNCH_OK();
-    fps_cell_key_kernel<<<ceil_div(n, 256), 256, 0, stream>>>(xyz, n, b.bbox, b.keys);
-    MSMD_LAUNCH_OK();
-    MSMD_CUDA_OK(radix_sort_pairs(b.keys, b.order, n, 16, true, b.sort, stream));
-    fps_gather_kernel<<<ceil_div(nb * 32, 256), 256, 0, stream>>>(xyz, b.order, n, b.sx, b.sy, b.sz, b.temp, b.bbox6,
-                                                                nb);
-    MSMD_LAUNCH_OK();
-    const int in_smem = n <= kFpsBSmemPoints ? 1 : 0;
-    const size_t smem = (size_t)nb * (8 + 24 + 12 + 4) + (in_smem ? (size_t)n * 16 : 0) + 16;
-    static bool attr_done = false;
-    if (!attr_done) {
-      MSMD_CUDA_OK(cudaFuncSetAttribute(fps_bucket_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-      attr_done = true;
-    }
-    fps_bucket_kernel<<<1, kFpsBThreads, smem, stream>>>(xyz, n, m, block, log2block, b.order, b.sx, b.sy, b.sz,
-                                                         b.temp, b.bbox6, nb, in_smem, idx);
-    MSMD_LAUNCH_OK();
-  } else if (n <= kFpsSingleThreads * kFpsSingleMaxPerThread) {
+  const long long cap_wide = (long long)kFpsCluster * kFpsThreadsWide, cap_deep = (long long)kFpsCluster * kFpsThreadsDeep;
+  if (n <= kFpsSingleThreads * kFpsSingleMaxPerThread) {
     // the round is instruction-issue bound (every warp repeats the block-level reduction), so
     // use as few warps as keep <= 8 points per thread
     int threads = ceil_div(ceil_div(n, kFpsSingleMaxPerThread), 32) * 32;
@@ -746,25 +457,34 @@ extern "C" MSMD_API int msmd_fps(const float* xyz, int n, int m, int* idx, void*
     }
     fps_single_kernel<kFpsSingleMaxPerThread><<<1, threads, smem, stream>>>(xyz, n, m, block, log2block, idx);
     MSMD_LAUNCH_OK();
-  } else if (n <= cap * kFpsMaxPerThread) {
-    const int ppt = ceil_div(n, cap);
-#define MSMD_FPS(P)                                                                             \
+  } else if (n <= cap_deep * kFpsMaxPerThread) {
+    // the per-round cost is (points per thread) x ~13 instructions + a fixed reduction / exchange chain, and the
+    // guarded iterations of a template that is deeper than needed are not free: 1024-thread CTAs with an exact
+    // per-thread depth whenever the points fit 8 per thread, the 512-thread deep variants above that
+#define MSMD_FPS(P, T)                                                                          \
   do {                                                                                          \
-    const size_t smem = (size_t)(P) * kFpsThreads * 3 * sizeof(float);                          \
+    const size_t smem = (size_t)(P) * (T) * 3 * sizeof(float);                                  \
     static bool attr_done = false; /* dynamic + 640 B static must fit: raise the limit once */  \
     if (!attr_done) {                                                                           \
-      MSMD_CUDA_OK(cudaFuncSetAttribute(fps_cluster_kernel<P>,                                  \
+      MSMD_CUDA_OK(cudaFuncSetAttribute(fps_cluster_kernel<P, T>,                               \
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
       attr_done = true;                                                                         \
     }                                                                                           \
-    fps_cluster_kernel<P><<<kFpsCluster, kFpsThreads, smem, stream>>>(xyz, n, m, block, log2block, idx); \
+    fps_cluster_kernel<P, T><<<kFpsCluster, T, smem, stream>>>(xyz, n, m, block, log2block, idx); \
   } while (0)
-    if (ppt <= 1) MSMD_FPS(1);
-    else if (ppt <= 2) MSMD_FPS(2);
-    else if (ppt <= 4) MSMD_FPS(4);
-    else if (ppt <= 8) MSMD_FPS(8);
-    else if (ppt <= 16) MSMD_FPS(16);
-    else MSMD_FPS(kFpsMaxPerThread);
+    if (n <= cap_wide * 8) {
+      const int ppt = ceil_div(n, cap_wide);
+      if (ppt <= 1) MSMD_FPS(1, kFpsThreadsWide);
+      else if (ppt <= 2) MSMD_FPS(2, kFpsThreadsWide);
+      else if (ppt <= 3) MSMD_FPS(3, kFpsThreadsWide);
+      else if (ppt <= 4) MSMD_FPS(4, kFpsThreadsWide);
+      else if (ppt <= 6) MSMD_FPS(6, kFpsThreadsWide);
+      else MSMD_FPS(8, kFpsThreadsWide);
+    } else {
+      const int ppt = ceil_div(n, cap_deep);
+      if (ppt <= 16) MSMD_FPS(16, kFpsThreadsDeep);
+      else MSMD_FPS(kFpsMaxPerThread, kFpsThreadsDeep);
+    }
 #undef MSMD_FPS
     MSMD_LAUNCH_OK();
   } else {

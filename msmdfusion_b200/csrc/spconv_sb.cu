@@ -232,6 +232,13 @@ spconv_fwd_sb_kernel(const uint16_t* __restrict__ xs, const uint16_t* __restrict
     (void)tr_role;
     int s = 0;
     uint32_t ph = 1u;   // "empty" barriers: the first pass through the ring finds every stage free
+    // A (row, kernel offset) without a pair must read as zeros.  A tile touches 23-27 of the 27 offsets while a row
+    // uses 12 % (16 channels) to 50 % (128 channels) of them, so most pieces of a chunk are zero-fill -- and every
+    // LDGSTS costs shared-memory and L1 wavefronts whether it moves data or zeros (the producers were the per-chunk
+    // limit, profiles/r02d_tc_trace_S_sb.txt).  Each thread owns the SAME four (row, piece) slots of every stage, so
+    // it remembers which of them hold data (4 bits per stage) and zero-fills a slot only if its previous tenant did:
+    // slots that stay empty are not touched again.  First pass through the ring: everything counts as dirty.
+    uint32_t dirty = 0xFFFFFFFFu;
     for (int t = 0; t < n_act; ++t) {
       if (lane == 0) TC_TRACE(tr_role, t, 0);
       mbar_wait_warp(&empty_bar[s], ph, lane);
@@ -241,16 +248,24 @@ spconv_fwd_sb_kernel(const uint16_t* __restrict__ xs, const uint16_t* __restrict
       const int c0 = kk0 - k * cin_pad;
       const bool kvalid = k < kvol;
       const uint32_t a_hi = tc::smem_u32(smem + (size_t)s * stage_bytes);
+      const uint32_t was = (dirty >> (4 * s)) & 15u;
+      uint32_t now = 0;
 #pragma unroll
       for (int i = 0; i < kTcM / 32; ++i) {
         const int r = rbase + 32 * i;
         const int idx = kvalid ? pair_s[k * kTcM + r] : -1;
-        const uint16_t* src = xs + (idx >= 0 ? (size_t)idx * row_elems + c0 : 0);
-        const uint32_t nb = idx >= 0 ? 16u : 0u;
         const uint32_t off = (uint32_t)(r * 128 + ((q ^ (r & 7)) << 4));
-        tc::cp_async_16(a_hi + off, src, nb);
-        tc::cp_async_16(a_hi + kSbABytes + off, idx >= 0 ? src + cin_pad : src, nb);
+        if (idx >= 0) {
+          const uint16_t* src = xs + (size_t)idx * row_elems + c0;
+          tc::cp_async_16(a_hi + off, src, 16u);
+          tc::cp_async_16(a_hi + kSbABytes + off, src + cin_pad, 16u);
+          now |= 1u << i;
+        } else if ((was >> i) & 1u) {
+          tc::cp_async_16(a_hi + off, xs, 0u);
+          tc::cp_async_16(a_hi + kSbABytes + off, xs, 0u);
+        }
       }
+      dirty = (dirty & ~(15u << (4 * s))) | (now << (4 * s));
       tc::cp_async_mbar_arrive_noinc(&full_bar[s]);
       if (lane == 0) TC_TRACE(tr_role, t, 2);
       if (++s == stages) { s = 0; ph ^= 1u; }

@@ -410,35 +410,6 @@ def test_fps_bit_exact_on_voxel_coordinates(n, m):
     assert np.array_equal(got, cpu.furthest_point_sample(xyz, m))
 
 
-@pytest.mark.parametrize('n,m,kind', [(1024, 600, 'voxel'), (3249, 2048, 'voxel'), (8192, 2048, 'voxel'),
-                                      (17567, 2048, 'voxel'), (46831, 2048, 'voxel'), (65536, 300, 'voxel'),
-                                      (30000, 2048, 'real'), (5000, 5000, 'real'), (9000, 1500, 'planar')])
-def test_bucketed_fps_equals_brute_force_and_oracle(n, m, kind):
-    """The bucketed exact FPS (csrc/points.cu: Morton-sorted buckets of 32 points, bounding-box pruning; the default
-    for 1024 <= n <= 65536) picks what the brute-force kernels and the CPU oracle pick, bit for bit: integer voxel
-    coordinates (ties everywhere), real-valued coordinates (rounded distances: the pruning bound must stay a lower
-    bound under fp32 rounding), m = n (every temp reaches 0), and a planar cloud (degenerate bounding box)."""
-    rng = np.random.default_rng(n + m)
-    if kind == 'voxel':
-        xyz = voxel_cloud(rng, n, [41, 1440, 1440]).astype(np.float32)
-    elif kind == 'real':
-        xyz = (rng.standard_normal((n, 3)) * np.array([20.0, 20.0, 2.0])).astype(np.float32)
-    else:
-        xyz = np.concatenate([rng.uniform(-50, 50, (n, 2)), np.full((n, 1), 1.25)], 1).astype(np.float32)
-    n = xyz.shape[0]
-    m = min(m, n)
-    t = cuda(xyz)
-    try:
-        ops.check(ops.lib().msmd_fps_set_algorithm(1), 'msmd_fps_set_algorithm')
-        brute = ops.furthest_point_sample_single(t, m).cpu().numpy()
-    finally:
-        ops.check(ops.lib().msmd_fps_set_algorithm(0), 'msmd_fps_set_algorithm')
-    got = ops.furthest_point_sample_single(t, m).cpu().numpy()
-    assert np.array_equal(got, brute)
-    if n <= 20000 or m <= 512:
-        assert np.array_equal(got, cpu.furthest_point_sample(xyz, m))
-
-
 def test_fps_reference_known_answer():
     """tests/test_models/test_common_modules/test_pointnet_ops.py:9-23 of the reference."""
     from test_oracle import BQ_XYZ  # noqa: F401  (same module-level fixtures)
