@@ -340,6 +340,29 @@ MSMD_API int msmd_sparse_net_forward(const msmd_conv_layer* layers, int n_layers
                                      msmd_sparse_desc* acts /* host [n_layers + 1] */,
                                      msmd_stream_t stream);
 
+/* ------------------------------------------------------------------------------------
+ * Gating + concatenation of one Gated Modality-Aware stage (csrc/gma.cu) -- replaces, for one sample per GPU,
+ * sparse_multimodal_encoder_painting.py:371-377 (cross gate of the only-2D voxels), :391-401 (gate of the mixed
+ * voxels) and :414-425 (zero-padded concatenation into the unified voxel list) with ONE kernel.
+ *   unified rows: [0, n_only3)            [ y_only3 | 0 x 64 ]                      coords idx_only3
+ *                 next max(n_only2, 1)     [ 0 x c3 | relu(W_cross g + b) * feat2[only2_rows[j]] ],  g = feat3[nn_idx[j]]
+ *                                          or the dummy embedding when nn_idx[j] < 0; coords only2_bzyx
+ *                 next max(n_mix, 1)       [ feat3[syn3[p]] | relu(W_gate feat3[syn3[p]] + b) * feat2[syn2[p]] ], coords
+ *                                          bz2[syn2[p]]
+ *   An empty group (only2_rows == NULL, or n_mix == 0) contributes the one all-zero voxel pad_missing_batch_id appends
+ *   (:208-225).  w_* are nn.Linear weights [64][c3], c2 must be 64.
+ * msmd_gather_rows: out[i] = features[rows[i]] (+ the (b,z,y,x) rows when coords4 is given).
+ * ---------------------------------------------------------------------------------- */
+MSMD_API int msmd_gather_rows(const float* features, int channels, const int* coords4, const long long* rows, int n,
+                              float* out_features, int* out_coords4, msmd_stream_t stream);
+MSMD_API int msmd_gma_assemble(const float* y_only3, const int* idx_only3, int n_only3, const float* feat3, int n3,
+                               int c3, const float* feat2, const int* bz2, int n2, int c2,
+                               const long long* only2_rows, const int* only2_bzyx, const long long* nn_idx,
+                               int n_only2, const long long* syn3, const long long* syn2, int n_mix,
+                               const float* dummy, const float* w_cross, const float* b_cross, const float* w_gate,
+                               const float* b_gate, float* unified_features, int* unified_indices,
+                               msmd_stream_t stream);
+
 /* The executor's geometry stream (a cudaStream_t) of the current device.  Index sets and rulebooks of a
  * msmd_sparse_net_forward call are complete once everything queued on it at the call's return has run: consumers of
  * the COORDINATES only (MSMDFusion.py:251-325 voxel_modality_split, :276-323 fps_NN_fast) may wait for an event

@@ -65,6 +65,9 @@ SIGNATURES = {
     'msmd_spconv_tc16_packed_bytes': (_sz, [_i, _i, _i, _i]),
     'msmd_spconv_tc16_pack_weight': (_i, [_vp, _i, _i, _i, _i, _vp, _vp]),
     'msmd_spconv_fwd_tc16': (_i, [_vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _vp]),
+    'msmd_gather_rows': (_i, [_vp, _i, _vp, _vp, _i, _vp, _vp, _vp]),
+    'msmd_gma_assemble': (_i, [_vp, _vp, _i, _vp, _i, _i, _vp, _vp, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _vp,
+                               _vp, _vp, _vp, _vp, _vp]),
     'msmd_executor_geometry_stream': (_i, [ctypes.POINTER(ctypes.c_void_p)]),
     'msmd_split_width': (_i, [_i]),
     'msmd_split_bf16': (_i, [_vp, _i, _i, _vp, _vp]),

@@ -159,13 +159,16 @@ __device__ __forceinline__ void sb_epilogue(int any_active, uint64_t* accum_bar,
 
 __global__ void __launch_bounds__(kTcThreads)
 spconv_fwd_sb_kernel(const uint16_t* __restrict__ xs, const uint16_t* __restrict__ wpk,
-                     const int* __restrict__ pair, int n_out, int cin_pad, int cout, int cout_pad, int N, int kvol,
+                     const int* __restrict__ pair, int n_out, int cin_pad, uint32_t cin_magic, int cout, int cout_pad,
+                     int N, int kvol,
                      int chunks, int stages, int stage_bytes, int pair_off, int act_off, int bar_off, int tmem_cols,
                      const float* __restrict__ scale, const float* __restrict__ shift,
                      const float* __restrict__ residual, int relu, float* __restrict__ out,
                      uint16_t* __restrict__ out_s, int cat) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  // round up to 1024 bytes INSIDE the shared window (an integer round-trip of the generic address makes ptxas
+  // emit generic LD.E instead of LDS for everything derived from it: seen in the r02f SASS of the producer loop)
+  uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
   int* pair_s = (int*)(smem + pair_off);
   unsigned short* alist = (unsigned short*)(smem + act_off);
   uint64_t* full_bar = (uint64_t*)(smem + bar_off);
@@ -232,40 +235,33 @@ spconv_fwd_sb_kernel(const uint16_t* __restrict__ xs, const uint16_t* __restrict
     (void)tr_role;
     int s = 0;
     uint32_t ph = 1u;   // "empty" barriers: the first pass through the ring finds every stage free
-    // A (row, kernel offset) without a pair must read as zeros.  A tile touches 23-27 of the 27 offsets while a row
-    // uses 12 % (16 channels) to 50 % (128 channels) of them, so most pieces of a chunk are zero-fill -- and every
-    // LDGSTS costs shared-memory and L1 wavefronts whether it moves data or zeros (the producers were the per-chunk
-    // limit, profiles/r02d_tc_trace_S_sb.txt).  Each thread owns the SAME four (row, piece) slots of every stage, so
-    // it remembers which of them hold data (4 bits per stage) and zero-fills a slot only if its previous tenant did:
-    // slots that stay empty are not touched again.  First pass through the ring: everything counts as dirty.
-    uint32_t dirty = 0xFFFFFFFFu;
+    // The loop body is one latency chain per warp (chunk id -> kernel offset -> 4 pair indices -> 4 addresses ->
+    // 8 copies), and only two producer warps share a scheduler: keep it short and wide -- the division by cin_pad is
+    // a multiply-high by a host-computed reciprocal, the four index loads are independent, invalid pairs are
+    // zero-filled by predication (src-size 0), no branches.  (An attempt to skip slots that stay empty, r02f, cost
+    // more in divergence than the zero-fill copies it saved.)
     for (int t = 0; t < n_act; ++t) {
       if (lane == 0) TC_TRACE(tr_role, t, 0);
       mbar_wait_warp(&empty_bar[s], ph, lane);
       if (lane == 0) TC_TRACE(tr_role, t, 1);
-      const int kk0 = (int)alist[t] * kSbKC + q * 8;
-      const int k = kk0 / cin_pad;
-      const int c0 = kk0 - k * cin_pad;
-      const bool kvalid = k < kvol;
-      const uint32_t a_hi = tc::smem_u32(smem + (size_t)s * stage_bytes);
-      const uint32_t was = (dirty >> (4 * s)) & 15u;
-      uint32_t now = 0;
+      const uint32_t kk0 = (uint32_t)alist[t] * kSbKC + (uint32_t)q * 8u;
+      const uint32_t k = __umulhi(kk0, cin_magic);          // kk0 / cin_pad (exact for kk0 < 2^16, checked on the host)
+      const uint32_t c0 = kk0 - k * (uint32_t)cin_pad;
+      const bool kvalid = k < (uint32_t)kvol;
+      const int* prow = pair_s + (kvalid ? k : 0u) * kTcM + rbase;
+      int idx[kTcM / 32];
+#pragma unroll
+      for (int i = 0; i < kTcM / 32; ++i) idx[i] = prow[32 * i];
+      const uint32_t a_hi = tc::smem_u32(smem) + (uint32_t)s * (uint32_t)stage_bytes + (uint32_t)(rbase * 128) +
+                            (uint32_t)((q ^ (rbase & 7)) << 4);   // rows rbase + 32 i share (row & 7)
 #pragma unroll
       for (int i = 0; i < kTcM / 32; ++i) {
-        const int r = rbase + 32 * i;
-        const int idx = kvalid ? pair_s[k * kTcM + r] : -1;
-        const uint32_t off = (uint32_t)(r * 128 + ((q ^ (r & 7)) << 4));
-        if (idx >= 0) {
-          const uint16_t* src = xs + (size_t)idx * row_elems + c0;
-          tc::cp_async_16(a_hi + off, src, 16u);
-          tc::cp_async_16(a_hi + kSbABytes + off, src + cin_pad, 16u);
-          now |= 1u << i;
-        } else if ((was >> i) & 1u) {
-          tc::cp_async_16(a_hi + off, xs, 0u);
-          tc::cp_async_16(a_hi + kSbABytes + off, xs, 0u);
-        }
+        const bool v = kvalid && idx[i] >= 0;
+        const uint16_t* src = xs + (v ? (size_t)idx[i] * row_elems + c0 : 0);
+        const uint32_t nb = v ? 16u : 0u;
+        tc::cp_async_16(a_hi + (uint32_t)(i * 32 * 128), src, nb);
+        tc::cp_async_16(a_hi + (uint32_t)(i * 32 * 128) + kSbABytes, v ? src + cin_pad : src, nb);
       }
-      dirty = (dirty & ~(15u << (4 * s))) | (now << (4 * s));
       tc::cp_async_mbar_arrive_noinc(&full_bar[s]);
       if (lane == 0) TC_TRACE(tr_role, t, 2);
       if (++s == stages) { s = 0; ph ^= 1u; }
@@ -450,11 +446,19 @@ extern "C" MSMD_API int msmd_spconv_fwd_sb(const void* features_split, int n_in,
     MSMD_CUDA_OK(cudaFuncSetAttribute(spconv_fwd_sb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
+  // kk0 / cin_pad as __umulhi(kk0, magic): exact for every K index of the packed image (< 2^16), verified here once
+  // per shape class -- the loop is over at most chunks * 8 values and runs on the host
+  const uint32_t cin_magic = (uint32_t)((((uint64_t)1 << 32) + (uint64_t)g.cin_pad - 1) / (uint64_t)g.cin_pad);
+  for (uint32_t kk = 0; kk < (uint32_t)g.chunks * kSbKC; kk += 8) {
+    MSMD_REQUIRE((uint32_t)(((uint64_t)kk * cin_magic) >> 32) == kk / (uint32_t)g.cin_pad,
+                 "spconv_fwd_sb: reciprocal of cin_pad %d is inexact at %u", g.cin_pad, kk);
+  }
   const int cat = (2 * g.N <= 256) ? 1 : 0;
   int tmem_cols = 32;
   while (tmem_cols < (cat ? 2 * g.N : g.N)) tmem_cols <<= 1;
   tc_launch(spconv_fwd_sb_kernel, tiles, kTcThreads, L.total, stream, (const uint16_t*)features_split,
-            (const uint16_t*)packed_sb, pair_fwd, n_out, g.cin_pad, cout, round_up(cout, 8), g.N, kvol, g.chunks,
+            (const uint16_t*)packed_sb, pair_fwd, n_out, g.cin_pad, cin_magic, cout, round_up(cout, 8), g.N, kvol,
+            g.chunks,
             L.stages, L.stage_bytes, L.pair_off, L.act_off, L.bar_off, tmem_cols, scale, shift, residual, relu, out,
             (uint16_t*)out_split, cat);
   MSMD_LAUNCH_OK();

@@ -148,14 +148,41 @@ class SparseNetPlan:
         return out
 
 
+class PlanWatch:
+    """What a cached plan depends on, flattened ONCE: the parameter / buffer tensors of the module tree and its
+    BatchNorm modules.  ``key()`` changes whenever one of them is replaced or modified in place, a BatchNorm changes
+    mode, the conv path / precision switches or ``spconv.invalidate_caches()`` is called.  (Walking
+    ``module.parameters()`` on every forward cost 1.4 ms of host time per LC scene -- profiles/r02f_lc_hostprofile.txt;
+    the flat lists cost ~30 us.)  A parameter REPLACED by assignment is seen through ``_parameters`` identity."""
+
+    def __init__(self, modules):
+        self.owners, self.tensors, self.norms = [], [], []
+        for m in modules:
+            for sub in m.modules():
+                for d in (sub._parameters, sub._buffers):
+                    for name, t in d.items():
+                        if t is not None:
+                            self.owners.append((d, name))
+                            self.tensors.append(t)
+                if isinstance(sub, nn.modules.batchnorm._BatchNorm):
+                    self.norms.append(sub)
+        self.roots = list(modules)
+
+    def key(self):
+        ts = self.tensors
+        for i, (d, name) in enumerate(self.owners):
+            t = d.get(name)
+            if t is not ts[i]:          # parameter object replaced (load with assign=True, manual assignment)
+                return None
+        return (spconv.CONV_PATH, spconv.CONV_PRECISION, spconv.cache_epoch(),
+                tuple([t._version for t in ts]), tuple([t.data_ptr() for t in ts]),
+                tuple([(b.training, b.track_running_stats) for b in self.norms]),
+                tuple([m.training for m in self.roots]))
+
+
 def plan_key(modules):
     """Changes whenever a parameter / buffer the plan baked in is replaced or modified in place."""
-    key = [spconv.CONV_PATH, spconv.CONV_PRECISION, spconv.cache_epoch()]
-    for m in modules:
-        for t in list(m.parameters()) + list(m.buffers()):
-            key.append((t.data_ptr(), t._version))
-        key.append(m.training)
-    return tuple(key)
+    return PlanWatch(modules).key()
 
 
 def geometry_stream(device):

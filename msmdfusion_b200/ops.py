@@ -696,3 +696,37 @@ def lift_gather(img_feat, pixels, cam_ids, points, lidar2img, downscale, score_w
                                      float(score_bias), ptr(out), stream(points.device)),
               'msmd_lift_gather')
     return out
+
+
+# --------------------------------------------------------------------------------------
+# Gated Modality-Aware stage: row gather + fused gates / concatenation (csrc/gma.cu)
+# reference: sparse_multimodal_encoder_painting.py:371-377, :391-401, :414-425
+# --------------------------------------------------------------------------------------
+def gather_rows(features, rows, coords=None):
+    """features[rows] (and coords[rows]) in one launch; rows int64."""
+    features = features.contiguous()
+    n, c = rows.shape[0], features.shape[1]
+    out = torch.empty((n, c), dtype=torch.float32, device=features.device)
+    oc = torch.empty((n, 4), dtype=torch.int32, device=features.device) if coords is not None else None
+    with _Timed('gather_rows', n=n, c=c):
+        check(lib().msmd_gather_rows(ptr(features), c, ptr(coords), ptr(rows), n, ptr(out), ptr(oc),
+                                     stream(features.device)), 'msmd_gather_rows')
+    return (out, oc) if coords is not None else out
+
+
+def gma_assemble(y_only3, idx_only3, feat3, feat2, bz2, only2_rows, only2_bzyx, nn_idx, syn3, syn2, dummy,
+                 w_cross, b_cross, w_gate, b_gate):
+    """Unified voxel list of one GMA stage (one sample per GPU): (features (n, c3 + 64), indices (n, 4))."""
+    dev = feat3.device
+    n_o3, c3 = y_only3.shape
+    n_o2, n_mix = only2_bzyx.shape[0], syn3.shape[0]
+    total = n_o3 + max(n_o2, 1) + max(n_mix, 1)
+    out = torch.empty((total, c3 + feat2.shape[1]), dtype=torch.float32, device=dev)
+    oidx = torch.empty((total, 4), dtype=torch.int32, device=dev)
+    with _Timed('gma_assemble', n=total, c3=c3):
+        check(lib().msmd_gma_assemble(ptr(y_only3), ptr(idx_only3), n_o3, ptr(feat3), feat3.shape[0], c3, ptr(feat2),
+                                      ptr(bz2), feat2.shape[0], feat2.shape[1], ptr(only2_rows), ptr(only2_bzyx),
+                                      ptr(nn_idx), n_o2, ptr(syn3) if n_mix else None, ptr(syn2) if n_mix else None,
+                                      n_mix, ptr(dummy), ptr(w_cross), ptr(b_cross), ptr(w_gate), ptr(b_gate),
+                                      ptr(out), ptr(oidx), stream(dev)), 'msmd_gma_assemble')
+    return out, oidx

@@ -54,11 +54,14 @@ class SparseEncoder(nn.Module):
     use_executor = True
 
     def _plan_for(self):
-        mods = [self.conv_input, self.encoder_layers, self.conv_out]
-        key = executor.plan_key(mods)
         cached = getattr(self, '_plan', None)
-        if cached is not None and cached[0] == key:
-            return cached[1], cached[2]
+        if cached is not None and len(cached) == 4:
+            key = cached[3].key()
+            if key is not None and cached[0] == key:
+                return cached[1], cached[2]
+        mods = [self.conv_input, self.encoder_layers, self.conv_out]
+        watch = executor.PlanWatch(mods)
+        key = watch.key()
         plan = executor.SparseNetPlan()
         cur = plan.add(self.conv_input, 0)
         marks = [cur]
@@ -67,7 +70,7 @@ class SparseEncoder(nn.Module):
             marks.append(cur)
         marks.append(plan.add(self.conv_out, cur))
         plan.finalize()
-        self._plan = (key, plan, marks)
+        self._plan = (key, plan, marks, watch)
         return plan, marks
 
     def forward(self, voxel_features, coors, batch_size):

@@ -637,6 +637,33 @@ def test_lift_matches_reference_golden():
     assert np.array_equal(nz, g['canvas_index']) and np.array_equal(canvas[nz], g['canvas_value'])
 
 
+def test_fused_gma_gates_equal_eager_path():
+    """One kernel for the gates + zero-padded concatenation of a GMA stage (csrc/gma.cu) against the eager torch
+    formulation of the same stage (nn.Linear over all rows, index_select, cat): identical unified voxel lists, features
+    within fp32 rounding of each other (the dot products run in channel order in both), for all four stages of a scene
+    with every group populated."""
+    from msmdfusion_b200 import fusion_encoder as fe
+    det, cfg = build_msmd_detector(1)
+    scenes, metas, fpn_np = _fixtures.lc_scene(1)
+    fpn = [cuda(f) for f in fpn_np]
+    pts_t = [cuda(s) for s in scenes]
+    outs = {}
+    try:
+        for fused in (True, False):
+            fe.SparseMultiModalEncoderPaint.fused_gates = fused
+            torch.manual_seed(77)   # the dummy embeddings are drawn from the CPU generator
+            with torch.no_grad():
+                bev, stage_outs = det.extract_voxel_space(pts_t, fpn, metas)
+            torch.cuda.synchronize()
+            outs[fused] = (bev.clone(), [(t.indices.clone(), t.features.clone()) for t in stage_outs])
+    finally:
+        fe.SparseMultiModalEncoderPaint.fused_gates = True
+    for (ia, fa), (ib, fb) in zip(outs[True][1], outs[False][1]):
+        assert torch.equal(ia, ib)
+        assert feat_err(fa.cpu().numpy(), fb.cpu().numpy()) < 1e-5
+    assert feat_err(outs[True][0].cpu().numpy(), outs[False][0].cpu().numpy()) < 1e-5
+
+
 @pytest.mark.parametrize('batch', [1, 2])
 def test_msmd_voxel_space_end_to_end(batch):
     """configs[2] slice: LiDAR encoder + 4-scale virtual-point voxels + modality split + GMA encoder
