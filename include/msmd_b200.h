@@ -369,6 +369,39 @@ MSMD_API int msmd_gma_assemble(const float* y_only3, const int* idx_only3, int n
  * recorded there instead of for the feature convolutions on the caller's stream. */
 MSMD_API int msmd_executor_geometry_stream(void** stream_out);
 
+/* Same, reporting how many bytes of the arena the call carved (the caller may keep bump-allocating behind them). */
+MSMD_API int msmd_sparse_net_forward_ex(const msmd_conv_layer* layers, int n_layers, const float* features,
+                                        const int* indices, int n, int channels, int batch_size,
+                                        const int* spatial_shape, void* arena, size_t arena_bytes,
+                                        msmd_sparse_desc* acts, size_t* arena_used, msmd_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * One whole stage of the Gated Modality-Aware convolution in ONE call (csrc/gma.cu) -- the body of
+ * SparseMultiModalEncoderPaint.forward's loop (sparse_multimodal_encoder_painting.py:433-459) for one sample per GPU:
+ *   only-3D rows gathered -> grouped_sp_conv_blocks_3D chain -> gates + concatenation (msmd_gma_assemble)
+ *   -> aggregation_blocks chain -> Fsp.sparse_add with the previous stage's output (when given) -> downscale chain.
+ * The three chains are msmd_conv_layer lists as for msmd_sparse_net_forward; all intermediates and the result are
+ * carved from `arena` (MSMD_ERR_WORKSPACE: too small); `out` describes the stage output.  Host synchronisations: the
+ * N_out read-backs of sparse_add and of the strided convolution.
+ * ---------------------------------------------------------------------------------- */
+typedef struct msmd_gma_stage {
+  const msmd_conv_layer* only3d; int n_only3d;
+  const msmd_conv_layer* agg;    int n_agg;
+  const msmd_conv_layer* down;   int n_down;
+  const float* w_cross; const float* b_cross;   /* cross_gate_control[stage][0]: nn.Linear(c3 -> 64) */
+  const float* w_gate;  const float* b_gate;    /* gate_control[stage][0] */
+  int c3, c2;
+} msmd_gma_stage;
+
+MSMD_API int msmd_gma_stage_forward(const msmd_gma_stage* stage, const float* feat3, const int* bz3, int n3,
+                                    const float* feat2, const int* bz2, int n2, const long long* only3_rows,
+                                    int n_only3, const long long* only2_rows, const int* only2_bzyx,
+                                    const long long* nn_idx, int n_only2, const long long* syn3,
+                                    const long long* syn2, int n_mix, const float* dummy, const float* prev_features,
+                                    const int* prev_indices, int n_prev, int batch_size,
+                                    const int* spatial_shape /* host [3] */, void* arena, size_t arena_bytes,
+                                    msmd_sparse_desc* out, msmd_stream_t stream);
+
 /* SparseConvTensor.dense(): (n,c) rows -> (batch, c, D, H, W), zero-filled inside.
  * spconv-1.x equivalent mmdet3d/ops/spconv/structure.py:54-66. */
 MSMD_API int msmd_to_dense(const int* indices, const float* features, int n, int c, int batch_size,

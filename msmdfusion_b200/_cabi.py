@@ -35,6 +35,16 @@ class SparseDesc(ctypes.Structure):
                 ('channels', ctypes.c_int), ('spatial_shape', ctypes.c_int * 3)]
 
 
+class GmaStage(ctypes.Structure):
+    """msmd_gma_stage (include/msmd_b200.h)."""
+    _fields_ = [('only3d', ctypes.POINTER(ConvLayer)), ('n_only3d', ctypes.c_int),
+                ('agg', ctypes.POINTER(ConvLayer)), ('n_agg', ctypes.c_int),
+                ('down', ctypes.POINTER(ConvLayer)), ('n_down', ctypes.c_int),
+                ('w_cross', ctypes.c_void_p), ('b_cross', ctypes.c_void_p),
+                ('w_gate', ctypes.c_void_p), ('b_gate', ctypes.c_void_p),
+                ('c3', ctypes.c_int), ('c2', ctypes.c_int)]
+
+
 # name -> (restype, argtypes).  Device pointers travel as void*; host arrays as int*/float*.
 SIGNATURES = {
     'msmd_last_error': (ctypes.c_char_p, []),
@@ -68,6 +78,8 @@ SIGNATURES = {
     'msmd_gather_rows': (_i, [_vp, _i, _vp, _vp, _i, _vp, _vp, _vp]),
     'msmd_gma_assemble': (_i, [_vp, _vp, _i, _vp, _i, _i, _vp, _vp, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _vp,
                                _vp, _vp, _vp, _vp, _vp]),
+    'msmd_gma_stage_forward': (_i, [ctypes.POINTER(GmaStage), _vp, _vp, _i, _vp, _vp, _i, _vp, _i, _vp, _vp, _vp, _i, _vp,
+                                    _vp, _i, _vp, _vp, _vp, _i, _i, _c_int_p, _vp, _sz, ctypes.POINTER(SparseDesc), _vp]),
     'msmd_executor_geometry_stream': (_i, [ctypes.POINTER(ctypes.c_void_p)]),
     'msmd_split_width': (_i, [_i]),
     'msmd_split_bf16': (_i, [_vp, _i, _i, _vp, _vp]),
@@ -95,6 +107,7 @@ SIGNATURES = {
     'msmd_from_dense': (_i, [_vp, _vp, _i, _i, _i, _c_int_p, _vp, _vp]),
     'msmd_grid_rows': (_i, [_vp, _i, _i, _c_int_p, _vp, _vp, _vp, _vp]),
     'msmd_sparse_net_forward': (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _c_int_p, _vp, _sz, _vp, _vp]),
+    'msmd_sparse_net_forward_ex': (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _c_int_p, _vp, _sz, _vp, ctypes.POINTER(_sz), _vp]),
     'msmd_to_dense': (_i, [_vp, _vp, _i, _i, _i, _c_int_p, _vp, _vp]),
     'msmd_fps_workspace': (_sz, [_i]),
     'msmd_fps': (_i, [_vp, _i, _i, _vp, _vp, _sz, _vp]),

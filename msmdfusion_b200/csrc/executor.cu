@@ -146,7 +146,18 @@ extern "C" MSMD_API int msmd_sparse_net_forward(const msmd_conv_layer* layers, i
                                                 int channels, int batch_size, const int* spatial_shape,
                                                 void* arena_ptr, size_t arena_bytes,
                                                 msmd_sparse_desc* acts, msmd_stream_t stream_) {
+  return msmd_sparse_net_forward_ex(layers, n_layers, features, indices, n, channels, batch_size, spatial_shape,
+                                    arena_ptr, arena_bytes, acts, nullptr, stream_);
+}
+
+extern "C" MSMD_API int msmd_sparse_net_forward_ex(const msmd_conv_layer* layers, int n_layers,
+                                                   const float* features, const int* indices, int n,
+                                                   int channels, int batch_size, const int* spatial_shape,
+                                                   void* arena_ptr, size_t arena_bytes,
+                                                   msmd_sparse_desc* acts, size_t* arena_used,
+                                                   msmd_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
+  if (arena_used) *arena_used = 0;
   MSMD_REQUIRE(layers && n_layers > 0 && acts && arena_ptr, "sparse_net_forward: null argument");
   MSMD_REQUIRE(n >= 0 && channels > 0 && batch_size > 0, "sparse_net_forward: bad input sizes");
   Arena arena{(char*)arena_ptr, arena_bytes, 0};
@@ -333,5 +344,6 @@ extern "C" MSMD_API int msmd_sparse_net_forward(const msmd_conv_layer* layers, i
     cudaEventRecord(ev_out, geom);
     cudaStreamWaitEvent(stream, ev_out, 0);
   }
+  if (arena_used) *arena_used = arena.used;
   return rc;
 }

@@ -43,8 +43,8 @@ gma_assemble_kernel(const float* __restrict__ y_only3, const int4* __restrict__ 
                     const float* __restrict__ dummy, const float* __restrict__ w_cross,
                     const float* __restrict__ b_cross, const float* __restrict__ w_gate,
                     const float* __restrict__ b_gate, float* __restrict__ out, int4* __restrict__ out_idx) {
-  extern __shared__ float gma_smem[];
-  float* wt_cross = gma_smem;                       // [c3][64]
+  extern __shared__ uint8_t gma_smem_raw[];
+  float* wt_cross = (float*)gma_smem_raw;                       // [c3][64]
   float* wt_gate = wt_cross + c3 * kGmaGate;        // [c3][64]
   float* xrow = wt_gate + c3 * kGmaGate;            // [warps][c3]
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -169,5 +169,110 @@ extern "C" MSMD_API int msmd_gma_assemble(const float* y_only3, const int* idx_o
       (const int4*)only2_bzyx, nn_idx, n_only2, rows_o2, syn3, syn2, n_mix, rows_mix, dummy, w_cross, b_cross, w_gate,
       b_gate, unified_features, (int4*)unified_indices);
   MSMD_LAUNCH_OK();
+  return MSMD_OK;
+}
+
+namespace {
+struct StageArena {
+  char* base;
+  size_t size, used;
+  template <typename T>
+  T* take(size_t count) {
+    const size_t off = msmd::align_up(used, 256);
+    const size_t end = off + sizeof(T) * (count ? count : 1);
+    used = end;
+    if (end > size) return nullptr;
+    return (T*)(base + off);
+  }
+};
+}  // namespace
+
+#define MSMD_STAGE_TAKE(ptr, T, count)                                                          \
+  T* ptr = arena.take<T>(count);                                                                \
+  if (!ptr) {                                                                                   \
+    set_error("gma_stage_forward: arena too small (%zu bytes needed so far, %zu given)",        \
+              arena.used, arena.size);                                                          \
+    return MSMD_ERR_WORKSPACE;                                                                  \
+  }
+#define MSMD_STAGE_TRY(expr)          \
+  do {                                \
+    int _r = (expr);                  \
+    if (_r != MSMD_OK) return _r;     \
+  } while (0)
+
+// a conv chain on the remaining part of the stage's arena; `last` = the chain's final activation
+static int run_chain(const msmd_conv_layer* layers, int n_layers, const float* feat, const int* idx, int n, int c,
+                     int batch, const int* shape, StageArena& arena, msmd_sparse_desc* last, cudaStream_t stream) {
+  msmd_sparse_desc acts[8];
+  MSMD_REQUIRE(n_layers >= 1 && n_layers < 8, "gma_stage_forward: a chain has 1..7 layers");
+  const size_t off = align_up(arena.used, 256);
+  if (off >= arena.size) {
+    set_error("gma_stage_forward: arena too small");
+    return MSMD_ERR_WORKSPACE;
+  }
+  size_t used = 0;
+  MSMD_STAGE_TRY(msmd_sparse_net_forward_ex(layers, n_layers, feat, idx, n, c, batch, shape, arena.base + off,
+                                            arena.size - off, acts, &used, (msmd_stream_t)stream));
+  arena.used = off + used;
+  *last = acts[n_layers];
+  return MSMD_OK;
+}
+
+extern "C" MSMD_API int msmd_gma_stage_forward(const msmd_gma_stage* st, const float* feat3, const int* bz3, int n3,
+                                               const float* feat2, const int* bz2, int n2,
+                                               const long long* only3_rows, int n_only3,
+                                               const long long* only2_rows, const int* only2_bzyx,
+                                               const long long* nn_idx, int n_only2, const long long* syn3,
+                                               const long long* syn2, int n_mix, const float* dummy,
+                                               const float* prev_features, const int* prev_indices, int n_prev,
+                                               int batch_size, const int* shape, void* arena_ptr, size_t arena_bytes,
+                                               msmd_sparse_desc* out, msmd_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  MSMD_REQUIRE(st && out && arena_ptr && shape && batch_size == 1, "gma_stage_forward: bad arguments (one sample per GPU)");
+  MSMD_REQUIRE(n3 > 0 && n_only3 > 0 && feat3 && bz3 && only3_rows, "gma_stage_forward: needs 3-D voxels");
+  StageArena arena{(char*)arena_ptr, arena_bytes, 0};
+  const int c3 = st->c3, cu = st->c3 + st->c2;
+  // 1. only-3D voxels -> their SubM chain
+  MSMD_STAGE_TAKE(f_o3, float, (size_t)n_only3 * c3);
+  MSMD_STAGE_TAKE(i_o3, int, (size_t)n_only3 * 4);
+  MSMD_STAGE_TRY(msmd_gather_rows(feat3, c3, bz3, only3_rows, n_only3, f_o3, i_o3, stream_));
+  msmd_sparse_desc y3;
+  MSMD_STAGE_TRY(run_chain(st->only3d, st->n_only3d, f_o3, i_o3, n_only3, c3, batch_size, shape, arena, &y3, stream));
+  MSMD_REQUIRE(y3.n == n_only3 && y3.channels == c3, "gma_stage_forward: the only-3D chain must keep rows and channels");
+  // 2. gates + zero-padded concatenation -> the unified voxel list
+  const int n_uni = n_only3 + (n_only2 > 0 ? n_only2 : 1) + (n_mix > 0 ? n_mix : 1);
+  MSMD_STAGE_TAKE(uf, float, (size_t)n_uni * cu);
+  MSMD_STAGE_TAKE(ui, int, (size_t)n_uni * 4);
+  MSMD_STAGE_TRY(msmd_gma_assemble(y3.features, y3.indices, n_only3, feat3, n3, c3, feat2, bz2, n2, st->c2, only2_rows,
+                                   only2_bzyx, nn_idx, n_only2, syn3, syn2, n_mix, dummy, st->w_cross, st->b_cross,
+                                   st->w_gate, st->b_gate, uf, ui, stream_));
+  // 3. aggregation block
+  msmd_sparse_desc agg;
+  MSMD_STAGE_TRY(run_chain(st->agg, st->n_agg, uf, ui, n_uni, cu, batch_size, shape, arena, &agg, stream));
+  // 4. + the previous stage's output (Fsp.sparse_add, :455)
+  const float* sf = agg.features;
+  const int* si = agg.indices;
+  int sn = agg.n;
+  if (prev_features) {
+    MSMD_REQUIRE(prev_indices && n_prev >= 0, "gma_stage_forward: previous stage without indices");
+    const size_t words = msmd_grid_num_words(batch_size, shape);
+    MSMD_STAGE_TAKE(bits, uint32_t, words);
+    MSMD_STAGE_TAKE(prefix, int, words);
+    MSMD_STAGE_TAKE(count, int, 1);
+    const size_t ws_bytes = msmd_scan_workspace();
+    MSMD_STAGE_TAKE(ws, char, ws_bytes);
+    MSMD_STAGE_TRY(msmd_sparse_add_outputs(agg.indices, agg.n, prev_indices, n_prev, batch_size, shape, bits, prefix,
+                                           count, ws, ws_bytes, stream_));
+    int h_count = 0;
+    MSMD_CUDA_OK(cudaMemcpyAsync(&h_count, count, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    MSMD_CUDA_OK(cudaStreamSynchronize(stream));
+    MSMD_STAGE_TAKE(of, float, (size_t)h_count * cu);
+    MSMD_STAGE_TAKE(oi, int, (size_t)h_count * 4);
+    MSMD_STAGE_TRY(msmd_sparse_add_finish(bits, prefix, h_count, agg.indices, agg.features, agg.n, prev_indices,
+                                          prev_features, n_prev, cu, batch_size, shape, oi, of, stream_));
+    sf = of; si = oi; sn = h_count;
+  }
+  // 5. downscale convolution
+  MSMD_STAGE_TRY(run_chain(st->down, st->n_down, sf, si, sn, cu, batch_size, shape, arena, out, stream));
   return MSMD_OK;
 }

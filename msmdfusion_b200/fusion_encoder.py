@@ -323,6 +323,89 @@ class SparseMultiModalEncoderPaint(nn.Module):
         unified_voxel = spconv.SparseConvTensor(unified_feat, unified_coors, voxel_2D.spatial_shape, 1)
         return self._run_chain(('agg', stage_id), getattr(self.aggregation_blocks, stage_name), unified_voxel)
 
+    # -- one stage = one C-ABI call (csrc/gma.cu: msmd_gma_stage_forward) ------------------------------------
+    native_stage = os.environ.get('MSMD_GMA_NATIVE', '1') not in ('', '0')
+
+    def _stage_plan(self, stage_id):
+        """The three conv chains of a stage as native-executor plans + the msmd_gma_stage record; None when a chain
+        is not in fused-inference form."""
+        stage_name = f'stage_{stage_id + 1}'
+        mods = [getattr(self.grouped_sp_conv_blocks_3D, stage_name), getattr(self.aggregation_blocks, stage_name),
+                getattr(self.downscale_blocks, stage_name), self.cross_gate_control[stage_id],
+                self.gate_control[stage_id]]
+        cache = self.__dict__.setdefault('_stage_plans', {})
+        ent = cache.get(stage_id)
+        k = ent[2].key() if ent is not None else None
+        if ent is None or k is None or ent[0] != k:
+            from ._cabi import GmaStage
+            watch = executor.PlanWatch(mods)
+            k = watch.key()
+            rec = None
+            try:
+                plans = []
+                for mod in mods[:3]:
+                    p = executor.SparseNetPlan()
+                    p.add(mod, 0)
+                    plans.append(p.finalize())
+                cg, gg = mods[3][0], mods[4][0]
+                st = GmaStage()
+                st.only3d, st.n_only3d = plans[0].carray, len(plans[0].layers)
+                st.agg, st.n_agg = plans[1].carray, len(plans[1].layers)
+                st.down, st.n_down = plans[2].carray, len(plans[2].layers)
+                keep = [t.detach().float().contiguous() for t in (cg.weight, cg.bias, gg.weight, gg.bias)]
+                st.w_cross, st.b_cross, st.w_gate, st.b_gate = [t.data_ptr() for t in keep]
+                st.c3, st.c2 = int(cg.weight.shape[1]), int(cg.weight.shape[0])
+                rec = dict(stage=st, plans=plans, keep=keep, arena_bytes=0)
+            except executor.Unsupported:
+                rec = None
+            cache[stage_id] = ent = (k, rec, watch)
+        return ent[1]
+
+    def _stage_native(self, rec, voxel_3D, voxel_2D, syn3, syn2, assign, stage_id, prev):
+        """-> stage output (SparseConvTensor whose tensors are views of one arena allocation)."""
+        import ctypes
+        from ._cabi import SparseDesc, check, lib, ptr, stream
+        feat3, feat2 = voxel_3D.features.contiguous(), voxel_2D.features.contiguous()
+        bz3, bz2 = voxel_3D._bzyx, voxel_2D._bzyx
+        dev = feat3.device
+        n3, n2, P = feat3.shape[0], feat2.shape[0], syn3.shape[0]
+        only3, only2, nn_idx = assign['only3_rows'], assign['only2_rows'], assign['nn_idx']
+        only2_bzyx = assign['only2_bzyx']
+        dummy = self._dummy_embedding(stage_id, feat3.shape[1], dev)
+        shape = (ctypes.c_int * 3)(*[int(v) for v in voxel_2D.spatial_shape])
+        cu = rec['stage'].c3 + rec['stage'].c2
+        nbytes = max(rec['arena_bytes'], (96 << 20) + 4096 * (n3 + n2 + (prev.features.shape[0] if prev is not None else 0)))
+        out = SparseDesc()
+        for _ in range(6):
+            arena = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
+            with ops._Timed('gma_stage_forward', stage=stage_id, n3=n3, n2=n2):
+                rc = lib().msmd_gma_stage_forward(
+                    ctypes.byref(rec['stage']), ptr(feat3), ptr(bz3), n3, ptr(feat2), ptr(bz2), n2, ptr(only3),
+                    only3.shape[0], ptr(only2), ptr(only2_bzyx), ptr(nn_idx), only2_bzyx.shape[0],
+                    ptr(syn3) if P else None, ptr(syn2) if P else None, P, ptr(dummy),
+                    ptr(prev.features) if prev is not None else None,
+                    ptr(prev.indices) if prev is not None else None,
+                    prev.features.shape[0] if prev is not None else 0, 1, shape, ptr(arena), nbytes,
+                    ctypes.byref(out), stream(dev))
+            if rc == -3:   # MSMD_ERR_WORKSPACE: grow the arena and run again
+                nbytes *= 2
+                continue
+            check(rc, 'msmd_gma_stage_forward')
+            break
+        else:
+            raise RuntimeError('msmd_gma_stage_forward: arena keeps overflowing')
+        rec['arena_bytes'] = nbytes
+        base = arena.data_ptr()
+        n, c = int(out.n), int(out.channels)
+        if n == 0 or out.features is None:
+            f = feat3.new_zeros((0, c))
+            idx = bz3.new_zeros((0, 4))
+        else:
+            fo, io = out.features - base, out.indices - base
+            f = arena[fo:fo + 4 * n * c].view(torch.float32).view(n, c)
+            idx = arena[io:io + 16 * n].view(torch.int32).view(n, 4)
+        return spconv.SparseConvTensor(f, idx, [int(v) for v in out.spatial_shape], 1)
+
     def _side_stream(self, stage_id, dev, n=4):
         if self._side_streams is None or self._side_streams[0].device != dev or \
                 len(self._side_streams) < max(n, stage_id + 1):
@@ -387,9 +470,21 @@ class SparseMultiModalEncoderPaint(nn.Module):
             stage_name = f'stage_{stage_id + 1}'
             if pre is not None:
                 assign, done = pre[stage_id]
-                torch.cuda.current_stream(voxel_3D_list[stage_id].features.device).wait_event(done)
+                v3, v2 = voxel_3D_list[stage_id], voxel_2D_list[stage_id]
+                torch.cuda.current_stream(v3.features.device).wait_event(done)
+                rec = None
+                if (self.native_stage and self.fused_gates and self.use_executor and not torch.is_grad_enabled()
+                        and v2.features.shape[1] == 64 and assign['only3_rows'].shape[0] > 0):
+                    rec = self._stage_plan(stage_id)
+                if rec is not None:
+                    # gather -> only-3D chain -> gates + concatenation -> aggregation block -> sparse_add -> downscale
+                    # conv: one call, one arena (csrc/gma.cu)
+                    stage_outs.append(self._stage_native(rec, v3, v2, syn_mix_3D_list[stage_id],
+                                                         syn_mix_2D_list[stage_id], assign, stage_id,
+                                                         stage_outs[stage_id - 1] if stage_id > 0 else None))
+                    continue
                 out = self._grouped_sparse_conv_b1(
-                    voxel_3D_list[stage_id], voxel_2D_list[stage_id], syn_mix_3D_list[stage_id],
+                    v3, v2, syn_mix_3D_list[stage_id],
                     syn_mix_2D_list[stage_id], stage_id, fps_num_list[stage_id], radius_list[stage_id],
                     max_cluster_samples_list[stage_id], dist_thresh_list[stage_id], assign=assign)
             else:

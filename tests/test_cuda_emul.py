@@ -1117,3 +1117,78 @@ def test_sb_kernel_chain_strided_rulebook_and_empty_tiles_on_emulator():
     shift = rng.standard_normal(32).astype(np.float32)
     got, _ = sb_fwd(feat, w1, empty, one, shift)
     assert rel(got, cpu.spconv_fwd(feat, w1, empty) + shift) < 2e-5
+
+
+# --------------------------------------------------------------------------------------
+# one Gated Modality-Aware stage in one C-ABI call (csrc/gma.cu) on the emulated image
+# --------------------------------------------------------------------------------------
+@pytest.mark.parametrize('precision', ['tf32x3', 'bf16x3c'])
+def test_native_gma_stage_on_emulator(executor_on_emulator, monkeypatch, precision):
+    """msmd_gma_stage_forward (row gather, only-3D chain, fused gates + concatenation, aggregation block, sparse_add
+    with the previous stage, strided downscale conv -- all carved from one arena) against the Python module path of
+    the same encoder (eager nn.Linear gates, index_select / cat, one executor call per chain), stage after stage:
+    identical index sets, features within fp32 rounding; including a stage with NO only-2D voxel and NO mixed pair
+    (the all-zero padding voxels) and unassigned only-2D voxels (nn_idx = -1 -> the dummy embedding)."""
+    import sys
+    import torch
+    sys.path.insert(0, HERE)
+    import _cpu_ops
+    from test_train_host import _encoder_inputs
+    from msmdfusion_b200 import functional as Fsp
+    from msmdfusion_b200 import fusion_encoder as fe
+    from msmdfusion_b200 import ops, spconv
+    from _fixtures import randomize_bn
+    monkeypatch.setattr(spconv, 'CONV_PRECISION', precision)
+    monkeypatch.setattr(ops, 'tc_supported', lambda cout, kvol, cin: cout <= 256 and kvol <= 32)
+    torch.manual_seed(12)
+    enc = fe.SparseMultiModalEncoderPaint(in_channels_3D=(4, 8, 8, 8), in_channels_2D=(64,) * 4,
+                                          out_channels=(8, 8, 8, 8), padding=(1, 1, [0, 1, 1], 0)).eval()
+    randomize_bn(enc, 3)
+    v3l, v2l, s3l, s2l = _encoder_inputs(31, 1)
+    rng = np.random.default_rng(5)
+    tol = 1e-5 if precision == 'tf32x3' else 1e-4
+    prev_native = prev_python = None
+    for stage_id in range(4):
+        (i3, f3, shape), (i2, f2, _) = v3l[stage_id], v2l[stage_id]
+        syn3, syn2 = s3l[stage_id], s2l[stage_id]
+        if stage_id == 2:          # no only-2D voxel, no mixed pair: both groups are the all-zero padding voxel
+            keep = torch.ones(i2.shape[0], dtype=torch.bool)
+            keep[:] = False
+            keep[syn2] = True
+            i2, f2 = i2[keep], f2[keep]
+            i3 = i3.clone(); i3[:, 1] = 0
+            i2 = i2.clone(); i2[:, 1] = 1   # every 2-D voxel is "mixed" by flag, but the pair lists are empty below
+            syn3, syn2 = syn3[:0], syn2[:0]
+        v3 = spconv.SparseConvTensor(f3.clone(), i3.clone(), shape, 1)
+        v2 = spconv.SparseConvTensor(f2.clone(), i2.clone(), shape, 1)
+        for t in (v3, v2):
+            t._mix = t.indices[:, 1].contiguous().int()
+            t._bzyx = t.indices[:, [0, 2, 3, 4]].contiguous()
+        only3 = torch.nonzero(v3._mix == 0).flatten()
+        only2 = torch.nonzero(v2._mix == 0).flatten()
+        if stage_id == 2:
+            only2 = only2[:0]
+        if only2.shape[0]:
+            only2_rows, only2_bzyx = only2, v2._bzyx.index_select(0, only2)
+        else:
+            only2_rows, only2_bzyx = None, torch.zeros((1, 4), dtype=torch.int32)
+        nn_idx = torch.from_numpy(rng.integers(-1, f3.shape[0], only2_bzyx.shape[0])).long()
+        assign = dict(only3_rows=only3, only2_rows=only2_rows, only2_bzyx=only2_bzyx, nn_idx=nn_idx)
+        rec = enc._stage_plan(stage_id)
+        assert rec is not None
+        with torch.no_grad():
+            torch.manual_seed(100 + stage_id)
+            got = enc._stage_native(rec, v3, v2, syn3, syn2, assign, stage_id, prev_native)
+            torch.manual_seed(100 + stage_id)
+            enc.fused_gates = False
+            try:
+                out = enc._grouped_sparse_conv_b1(v3, v2, syn3, syn2, stage_id, 6, 6, 20, 13.3, assign=assign)
+            finally:
+                enc.fused_gates = True
+            if prev_python is not None:
+                out = Fsp.sparse_add(out, prev_python)
+            want = enc._run_chain(('down', stage_id), getattr(enc.downscale_blocks, f'stage_{stage_id + 1}'), out)
+        assert got.spatial_shape == want.spatial_shape
+        assert np.array_equal(got.indices.numpy(), want.indices.numpy()), stage_id
+        assert rel(got.features.numpy(), want.features.numpy()) < tol, stage_id
+        prev_native, prev_python = got, want

@@ -664,6 +664,35 @@ def test_fused_gma_gates_equal_eager_path():
     assert feat_err(outs[True][0].cpu().numpy(), outs[False][0].cpu().numpy()) < 1e-5
 
 
+@pytest.mark.parametrize('overlap', [True, False])
+def test_native_gma_stage_and_overlapped_schedule_equal_module_path(overlap):
+    """One C-ABI call per GMA stage (csrc/gma.cu: msmd_gma_stage_forward) and the overlapped image-side schedule of
+    MSMDFusionDetector.extract_voxel_space against the module-by-module, in-sequence path: identical index sets,
+    features and BEV tensor within fp32 rounding (same kernels, same operands, same order)."""
+    from msmdfusion_b200 import fusion_encoder as fe
+    det, cfg = build_msmd_detector(1)
+    scenes, metas, fpn_np = _fixtures.lc_scene(1)
+    fpn = [cuda(f) for f in fpn_np]
+    pts_t = [cuda(s) for s in scenes]
+    outs = {}
+    saved = (fe.SparseMultiModalEncoderPaint.native_stage, type(det).overlap_image_side)
+    try:
+        for native in (True, False):
+            fe.SparseMultiModalEncoderPaint.native_stage = native
+            type(det).overlap_image_side = overlap if native else False
+            torch.manual_seed(77)
+            with torch.no_grad():
+                bev, stage_outs = det.extract_voxel_space(pts_t, fpn, metas)
+            torch.cuda.synchronize()
+            outs[native] = (bev.clone(), [(t.indices.clone(), t.features.clone()) for t in stage_outs])
+    finally:
+        fe.SparseMultiModalEncoderPaint.native_stage, type(det).overlap_image_side = saved
+    for (ia, fa), (ib, fb) in zip(outs[True][1], outs[False][1]):
+        assert torch.equal(ia, ib)
+        assert feat_err(fa.cpu().numpy(), fb.cpu().numpy()) < 1e-5
+    assert feat_err(outs[True][0].cpu().numpy(), outs[False][0].cpu().numpy()) < 1e-5
+
+
 @pytest.mark.parametrize('batch', [1, 2])
 def test_msmd_voxel_space_end_to_end(batch):
     """configs[2] slice: LiDAR encoder + 4-scale virtual-point voxels + modality split + GMA encoder

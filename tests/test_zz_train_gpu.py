@@ -605,7 +605,8 @@ def test_full_size_16bit_modes_mask_sort_and_tc_wgrad_properties():
         tcg2 = ops.spconv_bwd_weight(x1, go, pair, tuple(w.shape))
     finally:
         ops.set_wgrad_tc(False)
-    assert err(tcg, simt) < TOL and torch.equal(tcg, tcg2)
+    # a weight gradient is a sum over ~1e5 pairs (|dW| ~ 200 here): compared RELATIVE to the tensor's scale
+    assert float((tcg - simt).abs().max() / simt.abs().max()) < 1e-5 and torch.equal(tcg, tcg2)
     lhs = float((go.double() * y32.double()).sum())
     rhs = float((tcg.double() * w.double()).sum())
     scale = float((go.abs().double() * y32.abs().double()).sum())       # both sides are sums of ~7 M signed terms

@@ -212,7 +212,8 @@ def build_full(verbose=False):
     tests/tools/emu_plugin.py runs the -m gpu tests on."""
     return build_exec(verbose, name='libmsmd_full_emul.so',
                       units=['error_stub', 'voxelize.cu', 'spconv.cu', 'rulebook.cu', 'fusion.cu', 'spconv_tc.cu',
-                             'spconv_tc16.cu', 'spconv_sb.cu', 'spconv_wgrad_tc.cu', 'spconv_bwd.cu', 'executor.cu'])
+                             'spconv_tc16.cu', 'spconv_sb.cu', 'spconv_wgrad_tc.cu', 'spconv_bwd.cu', 'executor.cu',
+                             'gma.cu'])
 
 
 def build_exec(verbose=False, name='libmsmd_exec_emul.so', units=None):
@@ -221,7 +222,7 @@ def build_exec(verbose=False, name='libmsmd_exec_emul.so', units=None):
     os.makedirs(OUT, exist_ok=True)
     lib = os.path.join(OUT, name)
     units = units or ['spconv.cu', 'rulebook.cu', 'fusion.cu', 'spconv_tc.cu', 'spconv_tc16.cu', 'spconv_sb.cu',
-                      'executor.cu']
+                      'executor.cu', 'gma.cu']
     stub = 'error_stub' in units
     units = [u for u in units if u != 'error_stub']
     header = os.path.join(ROOT, 'include', 'msmd_b200.h')
