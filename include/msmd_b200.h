@@ -361,7 +361,7 @@ MSMD_API int msmd_gma_assemble(const float* y_only3, const int* idx_only3, int n
                                int n_only2, const long long* syn3, const long long* syn2, int n_mix,
                                const float* dummy, const float* w_cross, const float* b_cross, const float* w_gate,
                                const float* b_gate, float* unified_features, int* unified_indices,
-                               msmd_stream_t stream);
+                               msmd_stream_t stream);   /* unified_features or unified_indices may be NULL (not both) */
 
 /* The executor's geometry stream (a cudaStream_t) of the current device.  Index sets and rulebooks of a
  * msmd_sparse_net_forward call are complete once everything queued on it at the call's return has run: consumers of
@@ -369,11 +369,14 @@ MSMD_API int msmd_gma_assemble(const float* y_only3, const int* idx_only3, int n
  * recorded there instead of for the feature convolutions on the caller's stream. */
 MSMD_API int msmd_executor_geometry_stream(void** stream_out);
 
-/* Same, reporting how many bytes of the arena the call carved (the caller may keep bump-allocating behind them). */
+/* Same, reporting how many bytes of the arena the call carved (the caller may keep bump-allocating behind them).
+ * flags: MSMD_NET_INDICES_ON_GEOMETRY_STREAM = `indices` were produced on msmd_executor_geometry_stream() (not on
+ * `stream`): the call's rulebook chain does not wait for `stream` and may run ahead of the convolutions queued there. */
+#define MSMD_NET_INDICES_ON_GEOMETRY_STREAM 1
 MSMD_API int msmd_sparse_net_forward_ex(const msmd_conv_layer* layers, int n_layers, const float* features,
                                         const int* indices, int n, int channels, int batch_size,
                                         const int* spatial_shape, void* arena, size_t arena_bytes,
-                                        msmd_sparse_desc* acts, size_t* arena_used, msmd_stream_t stream);
+                                        msmd_sparse_desc* acts, size_t* arena_used, int flags, msmd_stream_t stream);
 
 /* ------------------------------------------------------------------------------------
  * One whole stage of the Gated Modality-Aware convolution in ONE call (csrc/gma.cu) -- the body of
@@ -381,8 +384,12 @@ MSMD_API int msmd_sparse_net_forward_ex(const msmd_conv_layer* layers, int n_lay
  *   only-3D rows gathered -> grouped_sp_conv_blocks_3D chain -> gates + concatenation (msmd_gma_assemble)
  *   -> aggregation_blocks chain -> Fsp.sparse_add with the previous stage's output (when given) -> downscale chain.
  * The three chains are msmd_conv_layer lists as for msmd_sparse_net_forward; all intermediates and the result are
- * carved from `arena` (MSMD_ERR_WORKSPACE: too small); `out` describes the stage output.  Host synchronisations: the
- * N_out read-backs of sparse_add and of the strided convolution.
+ * carved from `arena` (MSMD_ERR_WORKSPACE: too small); `out` describes the stage output.  Everything that depends on
+ * COORDINATES only (row-list gathers of coordinates, the unified coordinate list, bit grids, rulebooks, the union of
+ * sparse_add and both N_out read-backs) runs on msmd_executor_geometry_stream(), after `indices_ready_event` (the
+ * event behind which only3_rows / only2_* / nn_idx / syn* / bz2 are complete; NULL: after `stream`); the gathers of
+ * features, the gate kernel and the convolutions run on `stream`.  The host blocks on the geometry stream only, so
+ * the rulebooks of a stage -- and of the next stages -- are built while earlier convolutions still run.
  * ---------------------------------------------------------------------------------- */
 typedef struct msmd_gma_stage {
   const msmd_conv_layer* only3d; int n_only3d;
@@ -400,7 +407,8 @@ MSMD_API int msmd_gma_stage_forward(const msmd_gma_stage* stage, const float* fe
                                     const long long* syn2, int n_mix, const float* dummy, const float* prev_features,
                                     const int* prev_indices, int n_prev, int batch_size,
                                     const int* spatial_shape /* host [3] */, void* arena, size_t arena_bytes,
-                                    msmd_sparse_desc* out, msmd_stream_t stream);
+                                    msmd_sparse_desc* out, void* indices_ready_event /* cudaEvent_t or NULL */,
+                                    msmd_stream_t stream);
 
 /* SparseConvTensor.dense(): (n,c) rows -> (batch, c, D, H, W), zero-filled inside.
  * spconv-1.x equivalent mmdet3d/ops/spconv/structure.py:54-66. */

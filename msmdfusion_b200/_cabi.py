@@ -79,7 +79,8 @@ SIGNATURES = {
     'msmd_gma_assemble': (_i, [_vp, _vp, _i, _vp, _i, _i, _vp, _vp, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _vp,
                                _vp, _vp, _vp, _vp, _vp]),
     'msmd_gma_stage_forward': (_i, [ctypes.POINTER(GmaStage), _vp, _vp, _i, _vp, _vp, _i, _vp, _i, _vp, _vp, _vp, _i, _vp,
-                                    _vp, _i, _vp, _vp, _vp, _i, _i, _c_int_p, _vp, _sz, ctypes.POINTER(SparseDesc), _vp]),
+                                    _vp, _i, _vp, _vp, _vp, _i, _i, _c_int_p, _vp, _sz, ctypes.POINTER(SparseDesc), _vp,
+                                    _vp]),
     'msmd_executor_geometry_stream': (_i, [ctypes.POINTER(ctypes.c_void_p)]),
     'msmd_split_width': (_i, [_i]),
     'msmd_split_bf16': (_i, [_vp, _i, _i, _vp, _vp]),
@@ -107,7 +108,8 @@ SIGNATURES = {
     'msmd_from_dense': (_i, [_vp, _vp, _i, _i, _i, _c_int_p, _vp, _vp]),
     'msmd_grid_rows': (_i, [_vp, _i, _i, _c_int_p, _vp, _vp, _vp, _vp]),
     'msmd_sparse_net_forward': (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _c_int_p, _vp, _sz, _vp, _vp]),
-    'msmd_sparse_net_forward_ex': (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _c_int_p, _vp, _sz, _vp, ctypes.POINTER(_sz), _vp]),
+    'msmd_sparse_net_forward_ex': (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _c_int_p, _vp, _sz, _vp, ctypes.POINTER(_sz), _i,
+                                        _vp]),
     'msmd_to_dense': (_i, [_vp, _vp, _i, _i, _i, _c_int_p, _vp, _vp]),
     'msmd_fps_workspace': (_sz, [_i]),
     'msmd_fps': (_i, [_vp, _i, _i, _vp, _vp, _sz, _vp]),

@@ -147,14 +147,14 @@ extern "C" MSMD_API int msmd_sparse_net_forward(const msmd_conv_layer* layers, i
                                                 void* arena_ptr, size_t arena_bytes,
                                                 msmd_sparse_desc* acts, msmd_stream_t stream_) {
   return msmd_sparse_net_forward_ex(layers, n_layers, features, indices, n, channels, batch_size, spatial_shape,
-                                    arena_ptr, arena_bytes, acts, nullptr, stream_);
+                                    arena_ptr, arena_bytes, acts, nullptr, 0, stream_);
 }
 
 extern "C" MSMD_API int msmd_sparse_net_forward_ex(const msmd_conv_layer* layers, int n_layers,
                                                    const float* features, const int* indices, int n,
                                                    int channels, int batch_size, const int* spatial_shape,
                                                    void* arena_ptr, size_t arena_bytes,
-                                                   msmd_sparse_desc* acts, size_t* arena_used,
+                                                   msmd_sparse_desc* acts, size_t* arena_used, int flags,
                                                    msmd_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   if (arena_used) *arena_used = 0;
@@ -167,7 +167,10 @@ extern "C" MSMD_API int msmd_sparse_net_forward_ex(const msmd_conv_layer* layers
   AuxStreams* aux = nullptr;
   MSMD_TRY(aux_for_current_device(&aux));
   cudaStream_t geom = aux->geom;
-  {  // the geometry stream starts after everything already queued on the caller's stream
+  if (!(flags & MSMD_NET_INDICES_ON_GEOMETRY_STREAM)) {
+    // the geometry stream starts after everything already queued on the caller's stream (which produced `indices`);
+    // with the flag the caller produced them ON the geometry stream, and the rulebooks may run ahead of the caller's
+    // stream -- i.e. ahead of the previous chain's convolutions -- as they do inside one call
     cudaEvent_t ev_in;
     MSMD_TRY(next_event(*aux, &ev_in));
     MSMD_CUDA_OK(cudaEventRecord(ev_in, stream));

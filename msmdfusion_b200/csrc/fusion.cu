@@ -368,11 +368,16 @@ extern "C" MSMD_API int msmd_sparse_add_finish(const uint32_t* bits, const int* 
                                                float* out_features, msmd_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   if (n_out == 0) return MSMD_OK;
-  MSMD_REQUIRE(c > 0 && out_indices && out_features, "sparse_add: bad arguments");
+  // out_indices / out_features may each be NULL (not both): the coordinates and the features of the sum can be
+  // produced by two calls on two streams (csrc/gma.cu: coordinates on the geometry stream)
+  MSMD_REQUIRE(c > 0 && (out_indices || out_features), "sparse_add: bad arguments");
   const size_t words = msmd_grid_num_words(batch_size, shape);
-  union_enumerate_kernel<<<ceil_div((long long)words, 256), 256, 0, stream>>>(
-      bits, prefix, (int)words, shape[0], shape[1], shape[2], (int4*)out_indices);
-  MSMD_LAUNCH_OK();
+  if (out_indices) {
+    union_enumerate_kernel<<<ceil_div((long long)words, 256), 256, 0, stream>>>(
+        bits, prefix, (int)words, shape[0], shape[1], shape[2], (int4*)out_indices);
+    MSMD_LAUNCH_OK();
+  }
+  if (!out_features) return MSMD_OK;
   MSMD_CUDA_OK(cudaMemsetAsync(out_features, 0, (size_t)n_out * c * sizeof(float), stream));
   if (na) {
     scatter_add_rows_kernel<<<ceil_div((long long)na * c, 256), 256, 0, stream>>>(

@@ -27,10 +27,12 @@ gather_rows_kernel(const float* __restrict__ feat, int c, const int4* __restrict
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
   for (int i = warp; i < n; i += nwarps) {
     const long long r = rows[i];
-    const float* src = feat + (size_t)r * c;
-    float* dst = out_feat + (size_t)i * c;
-    for (int ch = lane; ch < c; ch += 32) dst[ch] = __ldg(src + ch);
-    if (lane == 0 && coords) out_coords[i] = __ldg(coords + r);
+    if (out_feat) {
+      const float* src = feat + (size_t)r * c;
+      float* dst = out_feat + (size_t)i * c;
+      for (int ch = lane; ch < c; ch += 32) dst[ch] = __ldg(src + ch);
+    }
+    if (lane == 0 && out_coords) out_coords[i] = __ldg(coords + r);
   }
 }
 
@@ -63,10 +65,12 @@ gma_assemble_kernel(const float* __restrict__ y_only3, const int4* __restrict__ 
     float* dst = out + (size_t)row * cu;
     if (row < n_o3) {
       // only-3D voxel: [convolved 3-D feature | 0]
-      for (int ch = lane; ch < c3; ch += 32) dst[ch] = __ldg(y_only3 + (size_t)row * c3 + ch);
-      dst[c3 + lane] = 0.f;
-      dst[c3 + 32 + lane] = 0.f;
-      if (lane == 0) out_idx[row] = __ldg(idx_only3 + row);
+      if (out) {
+        for (int ch = lane; ch < c3; ch += 32) dst[ch] = __ldg(y_only3 + (size_t)row * c3 + ch);
+        dst[c3 + lane] = 0.f;
+        dst[c3 + 32 + lane] = 0.f;
+      }
+      if (lane == 0 && out_idx) out_idx[row] = __ldg(idx_only3 + row);
       continue;
     }
     const bool is_o2 = row < n_o3 + rows_o2;
@@ -89,7 +93,8 @@ gma_assemble_kernel(const float* __restrict__ y_only3, const int4* __restrict__ 
       f2 = feat2 + (size_t)r2 * kGmaGate;
       coord = __ldg(bz2 + r2);
     }
-    if (lane == 0) out_idx[row] = coord;
+    if (lane == 0 && out_idx) out_idx[row] = coord;
+    if (!out) continue;   // coordinates only
     if (!real || f2 == nullptr) {   // the all-zero voxel pad_missing_batch_id appends for an empty group (:208-225)
       for (int ch = lane; ch < cu; ch += 32) dst[ch] = 0.f;
       continue;
@@ -127,7 +132,8 @@ extern "C" MSMD_API int msmd_gather_rows(const float* features, int channels, co
   cudaStream_t stream = (cudaStream_t)stream_;
   MSMD_REQUIRE(n >= 0 && channels > 0, "gather_rows: bad sizes");
   if (n == 0) return MSMD_OK;
-  MSMD_REQUIRE(features && rows && out_features && (coords4 == nullptr) == (out_coords4 == nullptr),
+  // features / coordinates may be gathered by separate calls (out_features or out_coords4 NULL, not both)
+  MSMD_REQUIRE(rows && (out_features || out_coords4) && (!out_features || features) && (!out_coords4 || coords4),
                "gather_rows: null pointer");
   int blocks = ceil_div((long long)n * 32, kGmaThreads);
   if (blocks > 8 * kNumSMs) blocks = 8 * kNumSMs;
@@ -148,9 +154,10 @@ extern "C" MSMD_API int msmd_gma_assemble(const float* y_only3, const int* idx_o
   MSMD_REQUIRE(c2 == kGmaGate, "gma_assemble: the 2-D features must have 64 channels (got %d)", c2);
   MSMD_REQUIRE(c3 >= 1 && c3 <= 256 && n_only3 >= 0 && n_only2 >= 0 && n_mix >= 0 && n3 >= 0 && n2 >= 0,
                "gma_assemble: bad sizes");
-  MSMD_REQUIRE(unified_features && unified_indices && dummy && w_cross && b_cross && w_gate && b_gate,
+  MSMD_REQUIRE((unified_features || unified_indices) && dummy && w_cross && b_cross && w_gate && b_gate,
                "gma_assemble: null pointer");
-  MSMD_REQUIRE(n_only3 == 0 || (y_only3 && idx_only3), "gma_assemble: only-3D rows without data");
+  MSMD_REQUIRE(n_only3 == 0 || ((y_only3 || !unified_features) && (idx_only3 || !unified_indices)),
+               "gma_assemble: only-3D rows without data");
   MSMD_REQUIRE(n_only2 == 0 || (only2_bzyx && nn_idx), "gma_assemble: only-2D rows without data");
   MSMD_REQUIRE(n_mix == 0 || (syn3 && syn2 && feat3 && feat2 && bz2), "gma_assemble: mixed rows without data");
   // an empty only-2D / mixed group still contributes one all-zero voxel (pad_missing_batch_id, one sample per GPU)
@@ -200,7 +207,8 @@ struct StageArena {
     if (_r != MSMD_OK) return _r;     \
   } while (0)
 
-// a conv chain on the remaining part of the stage's arena; `last` = the chain's final activation
+// a conv chain on the remaining part of the stage's arena; `last` = the chain's final activation.  The chain's input
+// indices were produced on the geometry stream (MSMD_NET_INDICES_ON_GEOMETRY_STREAM).
 static int run_chain(const msmd_conv_layer* layers, int n_layers, const float* feat, const int* idx, int n, int c,
                      int batch, const int* shape, StageArena& arena, msmd_sparse_desc* last, cudaStream_t stream) {
   msmd_sparse_desc acts[8];
@@ -212,11 +220,14 @@ static int run_chain(const msmd_conv_layer* layers, int n_layers, const float* f
   }
   size_t used = 0;
   MSMD_STAGE_TRY(msmd_sparse_net_forward_ex(layers, n_layers, feat, idx, n, c, batch, shape, arena.base + off,
-                                            arena.size - off, acts, &used, (msmd_stream_t)stream));
+                                            arena.size - off, acts, &used, MSMD_NET_INDICES_ON_GEOMETRY_STREAM,
+                                            (msmd_stream_t)stream));
   arena.used = off + used;
   *last = acts[n_layers];
   return MSMD_OK;
 }
+
+static cudaEvent_t g_stage_event[16] = {};   // per device: "the union grid of sparse_add is on the geometry stream"
 
 extern "C" MSMD_API int msmd_gma_stage_forward(const msmd_gma_stage* st, const float* feat3, const int* bz3, int n3,
                                                const float* feat2, const int* bz2, int n2,
@@ -226,33 +237,55 @@ extern "C" MSMD_API int msmd_gma_stage_forward(const msmd_gma_stage* st, const f
                                                const long long* syn2, int n_mix, const float* dummy,
                                                const float* prev_features, const int* prev_indices, int n_prev,
                                                int batch_size, const int* shape, void* arena_ptr, size_t arena_bytes,
-                                               msmd_sparse_desc* out, msmd_stream_t stream_) {
+                                               msmd_sparse_desc* out, void* indices_ready_event,
+                                               msmd_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   MSMD_REQUIRE(st && out && arena_ptr && shape && batch_size == 1, "gma_stage_forward: bad arguments (one sample per GPU)");
   MSMD_REQUIRE(n3 > 0 && n_only3 > 0 && feat3 && bz3 && only3_rows, "gma_stage_forward: needs 3-D voxels");
+  void* geom_v = nullptr;
+  MSMD_STAGE_TRY(msmd_executor_geometry_stream(&geom_v));
+  cudaStream_t geom = (cudaStream_t)geom_v;
+  int dev = 0;
+  MSMD_CUDA_OK(cudaGetDevice(&dev));
+  MSMD_REQUIRE(dev >= 0 && dev < 16, "gma_stage_forward: device ordinal %d unsupported", dev);
+  if (!g_stage_event[dev]) MSMD_CUDA_OK(cudaEventCreateWithFlags(&g_stage_event[dev], cudaEventDisableTiming));
+  // what the geometry stream reads (row lists, 2-D coordinates) is complete behind `indices_ready_event`; the LiDAR
+  // index sets and the previous stage's coordinates were produced on the geometry stream itself
+  if (indices_ready_event) {
+    MSMD_CUDA_OK(cudaStreamWaitEvent(geom, (cudaEvent_t)indices_ready_event, 0));
+  } else {
+    MSMD_CUDA_OK(cudaEventRecord(g_stage_event[dev], stream));
+    MSMD_CUDA_OK(cudaStreamWaitEvent(geom, g_stage_event[dev], 0));
+  }
   StageArena arena{(char*)arena_ptr, arena_bytes, 0};
   const int c3 = st->c3, cu = st->c3 + st->c2;
-  // 1. only-3D voxels -> their SubM chain
+  const msmd_stream_t geom_ = (msmd_stream_t)geom;
+  // 1. only-3D voxels -> their SubM chain (coordinates on the geometry stream, features on the caller's)
   MSMD_STAGE_TAKE(f_o3, float, (size_t)n_only3 * c3);
   MSMD_STAGE_TAKE(i_o3, int, (size_t)n_only3 * 4);
-  MSMD_STAGE_TRY(msmd_gather_rows(feat3, c3, bz3, only3_rows, n_only3, f_o3, i_o3, stream_));
+  MSMD_STAGE_TRY(msmd_gather_rows(nullptr, c3, bz3, only3_rows, n_only3, nullptr, i_o3, geom_));
+  MSMD_STAGE_TRY(msmd_gather_rows(feat3, c3, nullptr, only3_rows, n_only3, f_o3, nullptr, stream_));
   msmd_sparse_desc y3;
   MSMD_STAGE_TRY(run_chain(st->only3d, st->n_only3d, f_o3, i_o3, n_only3, c3, batch_size, shape, arena, &y3, stream));
   MSMD_REQUIRE(y3.n == n_only3 && y3.channels == c3, "gma_stage_forward: the only-3D chain must keep rows and channels");
-  // 2. gates + zero-padded concatenation -> the unified voxel list
+  // 2. the unified voxel list: coordinates (geometry stream), gates + zero-padded concatenation (caller's stream)
   const int n_uni = n_only3 + (n_only2 > 0 ? n_only2 : 1) + (n_mix > 0 ? n_mix : 1);
   MSMD_STAGE_TAKE(uf, float, (size_t)n_uni * cu);
   MSMD_STAGE_TAKE(ui, int, (size_t)n_uni * 4);
-  MSMD_STAGE_TRY(msmd_gma_assemble(y3.features, y3.indices, n_only3, feat3, n3, c3, feat2, bz2, n2, st->c2, only2_rows,
+  MSMD_STAGE_TRY(msmd_gma_assemble(nullptr, i_o3, n_only3, feat3, n3, c3, feat2, bz2, n2, st->c2, only2_rows,
                                    only2_bzyx, nn_idx, n_only2, syn3, syn2, n_mix, dummy, st->w_cross, st->b_cross,
-                                   st->w_gate, st->b_gate, uf, ui, stream_));
+                                   st->w_gate, st->b_gate, nullptr, ui, geom_));
+  MSMD_STAGE_TRY(msmd_gma_assemble(y3.features, nullptr, n_only3, feat3, n3, c3, feat2, bz2, n2, st->c2, only2_rows,
+                                   only2_bzyx, nn_idx, n_only2, syn3, syn2, n_mix, dummy, st->w_cross, st->b_cross,
+                                   st->w_gate, st->b_gate, uf, nullptr, stream_));
   // 3. aggregation block
   msmd_sparse_desc agg;
   MSMD_STAGE_TRY(run_chain(st->agg, st->n_agg, uf, ui, n_uni, cu, batch_size, shape, arena, &agg, stream));
-  // 4. + the previous stage's output (Fsp.sparse_add, :455)
+  // 4. + the previous stage's output (Fsp.sparse_add, :455): union grid, count and coordinates on the geometry
+  //    stream (the SubM aggregation block keeps the unified coordinates), the feature sum on the caller's
   const float* sf = agg.features;
-  const int* si = agg.indices;
-  int sn = agg.n;
+  const int* si = ui;
+  int sn = n_uni;
   if (prev_features) {
     MSMD_REQUIRE(prev_indices && n_prev >= 0, "gma_stage_forward: previous stage without indices");
     const size_t words = msmd_grid_num_words(batch_size, shape);
@@ -261,15 +294,19 @@ extern "C" MSMD_API int msmd_gma_stage_forward(const msmd_gma_stage* st, const f
     MSMD_STAGE_TAKE(count, int, 1);
     const size_t ws_bytes = msmd_scan_workspace();
     MSMD_STAGE_TAKE(ws, char, ws_bytes);
-    MSMD_STAGE_TRY(msmd_sparse_add_outputs(agg.indices, agg.n, prev_indices, n_prev, batch_size, shape, bits, prefix,
-                                           count, ws, ws_bytes, stream_));
+    MSMD_STAGE_TRY(msmd_sparse_add_outputs(ui, n_uni, prev_indices, n_prev, batch_size, shape, bits, prefix, count, ws,
+                                           ws_bytes, geom_));
     int h_count = 0;
-    MSMD_CUDA_OK(cudaMemcpyAsync(&h_count, count, sizeof(int), cudaMemcpyDeviceToHost, stream));
-    MSMD_CUDA_OK(cudaStreamSynchronize(stream));
+    MSMD_CUDA_OK(cudaMemcpyAsync(&h_count, count, sizeof(int), cudaMemcpyDeviceToHost, geom));
+    MSMD_CUDA_OK(cudaStreamSynchronize(geom));   // drains the geometry stream only
     MSMD_STAGE_TAKE(of, float, (size_t)h_count * cu);
     MSMD_STAGE_TAKE(oi, int, (size_t)h_count * 4);
-    MSMD_STAGE_TRY(msmd_sparse_add_finish(bits, prefix, h_count, agg.indices, agg.features, agg.n, prev_indices,
-                                          prev_features, n_prev, cu, batch_size, shape, oi, of, stream_));
+    MSMD_STAGE_TRY(msmd_sparse_add_finish(bits, prefix, h_count, ui, nullptr, n_uni, prev_indices, nullptr, n_prev, cu,
+                                          batch_size, shape, oi, nullptr, geom_));
+    MSMD_CUDA_OK(cudaEventRecord(g_stage_event[dev], geom));
+    MSMD_CUDA_OK(cudaStreamWaitEvent(stream, g_stage_event[dev], 0));
+    MSMD_STAGE_TRY(msmd_sparse_add_finish(bits, prefix, h_count, ui, agg.features, n_uni, prev_indices, prev_features,
+                                          n_prev, cu, batch_size, shape, nullptr, of, stream_));
     sf = of; si = oi; sn = h_count;
   }
   // 5. downscale convolution

@@ -202,22 +202,6 @@ class _VoxelPathMixin:
         return torch.cat(voxels, 0), torch.cat(num_points, 0), torch.cat(coors, 0)
 
     @torch.no_grad()
-    def voxelize_coords(self, points, downscale_factor=1.0):
-        """The COORDINATES ``voxelize`` would return for these points (same order, same ``max_voxels`` cut): the
-        voxel list of hard_voxelize is a function of the points' xyz and order only, so the index-only consumers
-        (modality split, FPS / nearest-voxel assignment) can start before the point FEATURES exist."""
-        self.pts_voxel_layer.voxel_size = [0.075, 0.075, 0.2]
-        self.pts_voxel_layer.voxel_size = [x * downscale_factor for x in self.pts_voxel_layer.voxel_size]
-        layer = self.pts_voxel_layer
-        coors = []
-        for i, res in enumerate(points):
-            _, c, _, _ = ops.hard_voxelize(res, layer.voxel_size, layer.point_cloud_range, layer.max_num_points,
-                                           layer.current_max_voxels(), want_voxels=False, mean_features=0,
-                                           batch_idx=i)
-            coors.append(c)
-        return coors[0] if len(coors) == 1 else torch.cat(coors, 0)
-
-    @torch.no_grad()
     def voxelize_mean(self, points, num_features, downscale_factor=1.0):
         """voxelize + HardSimpleVFE fused: (mean (V,F), coors (V,4) int32, per-sample counts)."""
         self.pts_voxel_layer.voxel_size = [0.075, 0.075, 0.2]
@@ -401,8 +385,8 @@ class MSMDFusionDetector(nn.Module, _VoxelPathMixin):
 
     # -- :400-418 ---------------------------------------------------------------------------
     def extract_multiscale_voxel_feat(self, img_feats, encode_features, img_metas, spatial_shapes,
-                                      downscale_factors, batch_size):
-        img_feats = self.depth_aware_channel_compression(img_feats, img_metas)
+                                      downscale_factors, batch_size, compressed=None):
+        img_feats = compressed if compressed is not None else self.depth_aware_channel_compression(img_feats, img_metas)
         img_feat_list = [img_feats[0]] + list(img_feats)
         v3l, v2l, s3l, s2l = [], [], [], []
         for i in range(4):
@@ -418,83 +402,22 @@ class MSMDFusionDetector(nn.Module, _VoxelPathMixin):
         return v3l, v2l, s3l, s2l
 
     # -- :421-452 ---------------------------------------------------------------------------
-    # Inference schedule (CUDA, no grad, one sample per GPU, LiDAR encoder on the native executor).  The reference
-    # runs the path in sequence (MSMDFusion.py:421-445).  Its longest dependency chain, however, touches only voxel
-    # COORDINATES:   LiDAR index sets -> virtual-point voxel list -> modality split -> FPS (2047 serial rounds)
-    #                -> nearest 3-D voxel / ball query -> assignment,
-    # and coordinates exist early: the LiDAR index sets are complete on the executor's geometry stream ~0.4 ms into
-    # the encoder call, and the voxel LIST of hard_voxelize depends on the points' xyz and order, not on their
-    # features.  So three strands are issued:
-    #   main     voxelize -> LiDAR encoder (21 convolutions) ............... -> GMA encoder
-    #   coords   [after the geometry] 4 x (coordinate voxelisation, modality split, FPS / assignment chain)
-    #   feats    depth-aware compression (cuDNN) -> 4 x (lift, voxelize + mean)   [needs nothing from the LiDAR side]
-    # Same kernels on the same operands, joined by events: results are unchanged.
+    # Inference schedule (CUDA, no grad, LiDAR encoder on the native executor): everything on the image side of the
+    # fusion -- 4 x (lift, voxelize, modality split) and the FPS / nearest-voxel assignment chains (2047 serial
+    # rounds each) -- depends on the LiDAR branch through voxel COORDINATES only.  Those are complete on the
+    # executor's geometry stream ~0.4 ms into the encoder call, long before its 21 convolutions have run, so that
+    # work is issued on a side stream that waits for the geometry and overlaps the LiDAR convolutions instead of
+    # queueing behind them (the reference runs all of it in sequence, MSMDFusion.py:421-445).  Same kernels, same
+    # operands: results are unchanged.  (A three-strand variant that also starts the FPS chains from a
+    # coordinates-only voxelisation was measured slower, profiles/r02h_lc_timeline.txt: the step is bound by the host
+    # issuing ~400 launches, and the extra voxelisation calls cost more host time than the earlier FPS start saves.)
     overlap_image_side = os.environ.get('MSMD_LC_OVERLAP', '1') not in ('', '0')   # A/B switch
 
-    def _side(self, device, which=0):
-        sts = self.__dict__.setdefault('_image_side_streams', {})
-        st = sts.get(which)
+    def _side(self, device):
+        st = self.__dict__.get('_image_side_stream')
         if st is None or st.device != device:
-            st = sts[which] = torch.cuda.Stream(device=device)
+            st = self.__dict__['_image_side_stream'] = torch.cuda.Stream(device=device)
         return st
-
-    def _extract_voxel_space_overlapped(self, pts, img_feats, img_metas, nf):
-        """-> (x, v3l, v2l, s3l, s2l) or None when the fast schedule does not apply to this call."""
-        from . import executor
-        dev = pts[0].device
-        enc = self.multimodal_middle_encoder
-        main = torch.cuda.current_stream(dev)
-        pk = self.packed_foreground(img_metas, dev)      # one pinned upload, shared by both image-side strands
-        if pk.points.shape[0] == 0:
-            return None                                   # empty sample: the generic path pads it (:376-380)
-        start = torch.cuda.Event()
-        start.record(main)
-        feats_side, coords_side = self._side(dev, 0), self._side(dev, 1)
-        # ---- feats strand: nothing here depends on the LiDAR branch --------------------------------------
-        feats_side.wait_event(start)
-        with torch.cuda.stream(feats_side):
-            compressed = self.depth_aware_channel_compression(img_feats, img_metas)
-            img_feat_list = [compressed[0]] + list(compressed)
-            v2_feats = []
-            for i in range(4):
-                t = self.fetch_2D_voxels(img_feat_list[i], img_metas, self.spatial_shapes[i], self.downscale_factors[i], 1)
-                v2_feats.append(t)
-            feats_done = torch.cuda.Event()
-            feats_done.record(feats_side)
-        # ---- main strand: the LiDAR branch -----------------------------------------------------------------
-        voxel_features, coors, _ = self.voxelize_mean(pts, nf)
-        x, encode_features = self.pts_middle_encoder(voxel_features, coors, 1)
-        if not getattr(self.pts_middle_encoder, 'ran_on_executor', False):
-            geom_done = torch.cuda.Event()
-            geom_done.record(main)
-        else:
-            geom_done = torch.cuda.Event()
-            geom_done.record(executor.geometry_stream(dev))
-        # ---- coords strand: index-only work, as soon as the LiDAR index sets exist ----------------------------
-        coords_side.wait_event(start)
-        coords_side.wait_event(geom_done)
-        v3l, v2l, s3l, s2l = [], [], [], []
-        with torch.cuda.stream(coords_side):
-            pts15 = [pk.points]
-            for i in range(4):
-                c2 = self.voxelize_coords(pts15, self.downscale_factors[i])
-                v2 = spconv.SparseConvTensor(None, c2, self.spatial_shapes[i], 1)
-                v3, v2, s3, s2 = self.voxel_modality_split(encode_features[i], v2, 1)
-                v3l.append(v3); v2l.append(v2); s3l.append(s3); s2l.append(s2)
-                enc.prelaunch_assign(i, v3, v2, s3.shape[0], self.fps_num_list[i], self.radius_list[i],
-                                     self.max_cluster_samples_list[i], self.dist_thresh_list[i])
-            coords_done = torch.cuda.Event()
-            coords_done.record(coords_side)
-        # ---- join ---------------------------------------------------------------------------------------------
-        # Allocator note: tensors created under a side stream and read later on `main` are safe without
-        # record_stream: `main` waits for the strand's event before reading them, and a side stream only starts a
-        # step's work after waiting for `start`, recorded on `main` behind every reader of the previous step.
-        main.wait_event(feats_done)
-        main.wait_event(coords_done)
-        for i in range(4):
-            assert v2_feats[i].features.shape[0] == v2l[i]._bzyx.shape[0], 'coordinate / feature voxel lists differ'
-            v2l[i].features = v2_feats[i].features
-        return x, v3l, v2l, s3l, s2l
 
     def extract_voxel_space(self, pts, img_feats, img_metas):
         """The voxel-space fusion hot path: returns the (B, 256 + 384, 180, 180) BEV tensor that
@@ -502,22 +425,45 @@ class MSMDFusionDetector(nn.Module, _VoxelPathMixin):
         batch_size = len(pts)
         nf = min(self.pts_voxel_encoder.num_features, pts[0].shape[1])  # [:64] of 5 dims after :386
         dev = pts[0].device
-        fast = None
-        if (self.overlap_image_side and batch_size == 1 and dev.type == 'cuda' and not torch.is_grad_enabled() and
-                getattr(self.pts_middle_encoder, 'use_executor', False) and self.fps_num_list is not None and
-                hasattr(getattr(self, 'multimodal_middle_encoder', None), 'prelaunch_assign')):
-            fast = self._extract_voxel_space_overlapped(pts, img_feats, img_metas, nf)
-        if fast is not None:
-            x, v3l, v2l, s3l, s2l = fast
+        overlap = (self.overlap_image_side and dev.type == 'cuda' and not torch.is_grad_enabled() and
+                   getattr(self.pts_middle_encoder, 'use_executor', False))
+        compressed = None
+        if overlap:
+            # the compression convolutions (cuDNN) do not depend on the LiDAR branch: issue them first so that the
+            # side stream below never waits behind the LiDAR convolutions for them
+            compressed = self.depth_aware_channel_compression(img_feats, img_metas)
+        voxel_features, coors, _ = self.voxelize_mean(pts, nf)
+        # a frozen LiDAR encoder (tools/train.py:185-211) has no grad-requiring input either (voxelize is
+        # no_grad, :462-464), so autograd would skip it anyway: run it on the inference path
+        frozen = torch.is_grad_enabled() and not any(p.requires_grad for p in self.pts_middle_encoder.parameters())
+        main = torch.cuda.current_stream(dev) if overlap else None
+        if overlap:
+            inputs_ready = torch.cuda.Event()
+            inputs_ready.record(main)
+        with (torch.no_grad() if frozen else contextlib.nullcontext()):
+            x, encode_features = self.pts_middle_encoder(voxel_features, coors, batch_size)
+        if overlap and getattr(self.pts_middle_encoder, 'ran_on_executor', False):
+            from . import executor
+            geom_done = torch.cuda.Event()
+            geom_done.record(executor.geometry_stream(dev))
+            side = self._side(dev)
+            side.wait_event(inputs_ready)   # compressed image features, the packed virtual points
+            side.wait_event(geom_done)      # index sets of the four LiDAR scales
+            # Allocator note: tensors created under `side` and read later on `main` are safe without record_stream.
+            # `main` waits for `image_side_done` before it reads them, and the side stream only ever starts a step's
+            # work after waiting for an event recorded on `main` (inputs_ready), i.e. after every main-stream reader
+            # of the previous step's blocks has been queued AND finished before the blocks can be rewritten.
+            with torch.cuda.stream(side):
+                v3l, v2l, s3l, s2l = self.extract_multiscale_voxel_feat(
+                    img_feats, encode_features, img_metas, self.spatial_shapes, self.downscale_factors, batch_size,
+                    compressed=compressed)
+                image_side_done = torch.cuda.Event()
+                image_side_done.record(side)
+            main.wait_event(image_side_done)
         else:
-            voxel_features, coors, _ = self.voxelize_mean(pts, nf)
-            # a frozen LiDAR encoder (tools/train.py:185-211) has no grad-requiring input either (voxelize is
-            # no_grad, :462-464), so autograd would skip it anyway: run it on the inference path
-            frozen = torch.is_grad_enabled() and not any(p.requires_grad for p in self.pts_middle_encoder.parameters())
-            with (torch.no_grad() if frozen else contextlib.nullcontext()):
-                x, encode_features = self.pts_middle_encoder(voxel_features, coors, batch_size)
             v3l, v2l, s3l, s2l = self.extract_multiscale_voxel_feat(
-                img_feats, encode_features, img_metas, self.spatial_shapes, self.downscale_factors, batch_size)
+                img_feats, encode_features, img_metas, self.spatial_shapes, self.downscale_factors, batch_size,
+                compressed=compressed)
         stage_outs = self.multimodal_middle_encoder(
             v3l, v2l, s3l, s2l, self.fps_num_list, self.radius_list, self.max_cluster_samples_list,
             self.dist_thresh_list)

@@ -361,8 +361,10 @@ class SparseMultiModalEncoderPaint(nn.Module):
             cache[stage_id] = ent = (k, rec, watch)
         return ent[1]
 
-    def _stage_native(self, rec, voxel_3D, voxel_2D, syn3, syn2, assign, stage_id, prev):
-        """-> stage output (SparseConvTensor whose tensors are views of one arena allocation)."""
+    def _stage_native(self, rec, voxel_3D, voxel_2D, syn3, syn2, assign, stage_id, prev, ready=None):
+        """-> stage output (SparseConvTensor whose tensors are views of one arena allocation).  ``ready``: the CUDA
+        event behind which the stage's row lists and 2-D coordinates are complete (the assignment chain's); the
+        stage's coordinate-only work runs on the executor's geometry stream after it."""
         import ctypes
         from ._cabi import SparseDesc, check, lib, ptr, stream
         feat3, feat2 = voxel_3D.features.contiguous(), voxel_2D.features.contiguous()
@@ -386,7 +388,7 @@ class SparseMultiModalEncoderPaint(nn.Module):
                     ptr(prev.features) if prev is not None else None,
                     ptr(prev.indices) if prev is not None else None,
                     prev.features.shape[0] if prev is not None else 0, 1, shape, ptr(arena), nbytes,
-                    ctypes.byref(out), stream(dev))
+                    ctypes.byref(out), ctypes.c_void_p(ready.cuda_event) if ready is not None else None, stream(dev))
             if rc == -3:   # MSMD_ERR_WORKSPACE: grow the arena and run again
                 nbytes *= 2
                 continue
@@ -481,7 +483,8 @@ class SparseMultiModalEncoderPaint(nn.Module):
                     # conv: one call, one arena (csrc/gma.cu)
                     stage_outs.append(self._stage_native(rec, v3, v2, syn_mix_3D_list[stage_id],
                                                          syn_mix_2D_list[stage_id], assign, stage_id,
-                                                         stage_outs[stage_id - 1] if stage_id > 0 else None))
+                                                         stage_outs[stage_id - 1] if stage_id > 0 else None,
+                                                         ready=done))
                     continue
                 out = self._grouped_sparse_conv_b1(
                     v3, v2, syn_mix_3D_list[stage_id],
