@@ -453,9 +453,16 @@ MSMD_API int msmd_group_assign(const int* group, int m, int nsample, const float
  *   coord3 (n3,4) / coord2 (n2,4) i32 (b,z,y,x) rows of this sample
  *   mix3 (n3) / mix2 (n2) i32: 1 = voxel exists in both modalities
  *   syn3 / syn2: int64 row ids (+offset) of the paired voxels in sorted-key order; capacity
- *   min(n3,n2); *num_mix (device) = number of pairs
+ *   min(n3,n2); num_mix (device, TWO ints): [0] = number of pairs, [1] = overflow flag
+ * msmd_modality_split: hash table on the float key (counts + up to 8 row ids per key and set) + a shared-memory sort of
+ * the paired rows only -- 5 launches; sets num_mix[1] = 1 when a key run exceeds 8 rows or there are more than 4096
+ * pairs: the caller then runs msmd_modality_split_sort (two stable radix sorts + binary-search merge, any size; it
+ * writes num_mix[0] only).  Both produce the reference's result bit for bit.
  * ---------------------------------------------------------------------------------- */
 MSMD_API size_t msmd_modality_split_workspace(int n3, int n2);
+MSMD_API int msmd_modality_split_sort(const int* coord3, int n3, const int* coord2, int n2, long long offset3,
+                                      long long offset2, int* mix3, int* mix2, long long* syn3, long long* syn2,
+                                      int* num_mix, void* workspace, size_t workspace_bytes, msmd_stream_t stream);
 MSMD_API int msmd_modality_split(const int* coord3, int n3, const int* coord2, int n2,
                                  long long offset3, long long offset2, int* mix3, int* mix2,
                                  long long* syn3, long long* syn2, int* num_mix, void* workspace,

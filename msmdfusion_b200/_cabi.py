@@ -119,6 +119,8 @@ SIGNATURES = {
     'msmd_modality_split_workspace': (_sz, [_i, _i]),
     'msmd_modality_split': (_i, [_vp, _i, _vp, _i, ctypes.c_longlong, ctypes.c_longlong, _vp, _vp,
                                  _vp, _vp, _vp, _vp, _sz, _vp]),
+    'msmd_modality_split_sort': (_i, [_vp, _i, _vp, _i, ctypes.c_longlong, ctypes.c_longlong, _vp, _vp,
+                                      _vp, _vp, _vp, _vp, _sz, _vp]),
     'msmd_compact_unflagged': (_i, [_vp, _i, _vp, _vp, _vp, _sz, _vp]),
     'msmd_sparse_add_outputs': (_i, [_vp, _i, _vp, _i, _i, _c_int_p, _vp, _vp, _vp, _vp, _sz, _vp]),
     'msmd_sparse_add_finish': (_i, [_vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _c_int_p, _vp,

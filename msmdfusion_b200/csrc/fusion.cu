@@ -63,6 +63,136 @@ split_flag_kernel(const uint32_t* __restrict__ own, const int* __restrict__ own_
   mix_rows[own_rows[i]] = f;
 }
 
+// ---- hash path (default) -----------------------------------------------------------------------------
+// The sort above costs ~35 launches (two 4-pass radix sorts, binary-search flags, scans) = 0.26 ms per call, all of
+// it on the serial path in front of the FPS chains.  What the merge needs is (a) for every row the number of rows of
+// the OTHER set with the same key, (b) its rank among the rows of its OWN set with that key (runs are 1..5 rows:
+// keys collide only through fp32 rounding above 2^24 and through x >= 1000), (c) the flagged rows in sorted-key
+// order.  (a) and (b) come from an open-addressing table keyed by the float key: a slot counts the rows of either
+// set and remembers up to kRunCap row ids per set, in whatever order the atomics land -- the rank is the number of
+// remembered ids BELOW the row's own, which does not depend on that order.  (c) only concerns the flagged rows (the
+// voxels present in both modalities, a few hundred): they are compacted and sorted by (key, row) in shared memory by
+// one CTA per set.  Five launches.  A run longer than kRunCap or more than kSplitSortCap pairs raise `overflow` and
+// the caller falls back to the sort path.
+constexpr int kRunCap = 8;
+constexpr int kSplitSortCap = 4096;   // 32 KB of static shared memory
+constexpr uint32_t kEmptyKey = 0xFFFFFFFFu;
+
+__device__ __forceinline__ uint32_t split_hash(uint32_t k) {
+  k ^= k >> 16; k *= 0x7feb352dU; k ^= k >> 15; k *= 0x846ca68bU; k ^= k >> 16;
+  return k;
+}
+
+__global__ void __launch_bounds__(256)
+split_insert_kernel(const int* __restrict__ coord3, int n3, const int* __restrict__ coord2, int n2, uint32_t mask,
+                    uint32_t* __restrict__ keys, int* __restrict__ cnt /* [2][cap] */, int* __restrict__ ids /* [2][cap][kRunCap] */,
+                    int* __restrict__ slot_of /* [n3 + n2] */, uint32_t* __restrict__ key_of, int* __restrict__ overflow) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n3 + n2) return;
+  const int set = t >= n3;
+  const int row = set ? t - n3 : t;
+  const int* c = (set ? coord2 : coord3) + (size_t)row * 4;
+  const uint32_t key = float_key(c[1], c[2], c[3]);
+  uint32_t h = split_hash(key) & mask;
+  for (;;) {
+    const uint32_t old = atomicCAS(&keys[h], kEmptyKey, key);
+    if (old == kEmptyKey || old == key) break;
+    h = (h + 1) & mask;
+  }
+  const size_t cap = (size_t)mask + 1;
+  const int pos = atomicAdd(&cnt[set * cap + h], 1);
+  if (pos < kRunCap) ids[((size_t)set * cap + h) * kRunCap + pos] = row;
+  else atomicExch(overflow, 1);
+  slot_of[t] = (int)h;
+  key_of[t] = key;
+}
+
+__global__ void __launch_bounds__(256)
+split_flag_hash_kernel(int n3, int n2, uint32_t mask, const int* __restrict__ cnt, const int* __restrict__ ids,
+                       const int* __restrict__ slot_of, const uint32_t* __restrict__ key_of, int* __restrict__ mix3,
+                       int* __restrict__ mix2, unsigned long long* __restrict__ flagged /* [2][min(n3,n2)] */, int cap_pairs,
+                       int* __restrict__ num_flag /* [2] */, int* __restrict__ overflow) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n3 + n2) return;
+  const int set = t >= n3;
+  const int row = set ? t - n3 : t;
+  const size_t cap = (size_t)mask + 1;
+  const int h = slot_of[t];
+  int own = cnt[set * cap + h];
+  if (own > kRunCap) own = kRunCap;
+  const int other = cnt[(1 - set) * cap + h];
+  int rank = 0;
+  const int* run = ids + ((size_t)set * cap + h) * kRunCap;
+  for (int j = 0; j < own; ++j) rank += run[j] < row;
+  const int f = rank < other;
+  (set ? mix2 : mix3)[row] = f;
+  if (f) {
+    const int p = atomicAdd(&num_flag[set], 1);
+    if (p < cap_pairs) flagged[(size_t)set * cap_pairs + p] = ((unsigned long long)key_of[t] << 32) | (unsigned)row;
+    else atomicExch(overflow, 1);
+  }
+}
+
+// one CTA per set: bitonic sort of the flagged (key, row) pairs in shared memory -> syn list (+ offset)
+__global__ void __launch_bounds__(1024)
+split_sort_flagged_kernel(const unsigned long long* __restrict__ flagged, int cap_pairs, const int* __restrict__ num_flag,
+                          long long offset3, long long offset2, long long* __restrict__ syn3,
+                          long long* __restrict__ syn2, int* __restrict__ num_mix, int* __restrict__ overflow) {
+  __shared__ unsigned long long v[kSplitSortCap];
+  const int set = blockIdx.x;
+  const int p = num_flag[set];
+  if (set == 0 && threadIdx.x == 0) *num_mix = p;
+  if (p > kSplitSortCap || p > cap_pairs || num_flag[0] != num_flag[1]) {
+    if (threadIdx.x == 0 && (p > kSplitSortCap || p > cap_pairs)) atomicExch(overflow, 1);
+    if (num_flag[0] != num_flag[1] && threadIdx.x == 0) atomicExch(overflow, 1);   // cannot happen: caught, not trusted
+    return;
+  }
+  int n = 1;
+  while (n < p) n <<= 1;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) v[i] = i < p ? flagged[(size_t)set * cap_pairs + i] : ~0ull;
+  __syncthreads();
+  for (int k = 2; k <= n; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int l = i ^ j;
+        if (l > i) {
+          const unsigned long long a = v[i], b = v[l];
+          const bool up = (i & k) == 0;
+          if ((a > b) == up) { v[i] = b; v[l] = a; }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  long long* syn = set ? syn2 : syn3;
+  const long long off = set ? offset2 : offset3;
+  for (int i = threadIdx.x; i < p; i += blockDim.x) syn[i] = (long long)(unsigned)(v[i] & 0xffffffffull) + off;
+}
+
+struct SplitHashWs {
+  uint32_t* keys;
+  int *cnt, *ids, *slot_of, *num_flag;
+  uint32_t* key_of;
+  unsigned long long* flagged;
+  uint32_t cap;
+  int cap_pairs;
+  bool carve(Workspace& ws, int n3, int n2) {
+    const long long n = (long long)n3 + n2;
+    cap = 1024;
+    while ((long long)cap < 2 * n) cap <<= 1;
+    cap_pairs = n3 < n2 ? n3 : n2;
+    if (cap_pairs < 1) cap_pairs = 1;
+    keys = ws.take<uint32_t>(cap);
+    cnt = ws.take<int>((size_t)2 * cap);
+    ids = ws.take<int>((size_t)2 * cap * kRunCap);
+    slot_of = ws.take<int>(n > 0 ? n : 1);
+    key_of = ws.take<uint32_t>(n > 0 ? n : 1);
+    flagged = ws.take<unsigned long long>((size_t)2 * cap_pairs);
+    num_flag = ws.take<int>(2);
+    return ws.ok();
+  }
+};
+
 struct SplitCompact {
   const int* rows;
   long long offset;
@@ -263,10 +393,52 @@ extern "C" MSMD_API size_t msmd_modality_split_workspace(int n3, int n2) {
   Workspace ws((void*)256, ~(size_t)0 >> 1);
   SplitWs s;
   s.carve(ws, n3, n2);
-  return ws.used + 256;
+  Workspace wh((void*)256, ~(size_t)0 >> 1);
+  SplitHashWs h;
+  h.carve(wh, n3, n2);
+  return (ws.used > wh.used ? ws.used : wh.used) + 256;
 }
 
+// Hash path (see above).  num_mix[0] = number of pairs, num_mix[1] = 1 when the table / pair buffers overflowed: the
+// outputs are then undefined and the caller re-runs msmd_modality_split_sort (same arguments).
 extern "C" MSMD_API int msmd_modality_split(const int* coord3, int n3, const int* coord2, int n2,
+                                            long long offset3, long long offset2, int* mix3,
+                                            int* mix2, long long* syn3, long long* syn2,
+                                            int* num_mix, void* workspace, size_t workspace_bytes,
+                                            msmd_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  MSMD_REQUIRE(n3 >= 0 && n2 >= 0 && num_mix, "modality_split: bad arguments");
+  MSMD_CUDA_OK(cudaMemsetAsync(num_mix, 0, 2 * sizeof(int), stream));
+  if (n3 == 0 || n2 == 0) {
+    if (n3) MSMD_CUDA_OK(cudaMemsetAsync(mix3, 0, (size_t)n3 * sizeof(int), stream));
+    if (n2) MSMD_CUDA_OK(cudaMemsetAsync(mix2, 0, (size_t)n2 * sizeof(int), stream));
+    return MSMD_OK;
+  }
+  Workspace ws(workspace, workspace_bytes);
+  SplitHashWs h;
+  if (!h.carve(ws, n3, n2)) {
+    set_error("modality_split: workspace too small (%zu < %zu)", workspace_bytes,
+              msmd_modality_split_workspace(n3, n2));
+    return MSMD_ERR_WORKSPACE;
+  }
+  MSMD_CUDA_OK(cudaMemsetAsync(h.keys, 0xFF, (size_t)h.cap * sizeof(uint32_t), stream));
+  MSMD_CUDA_OK(cudaMemsetAsync(h.cnt, 0, (size_t)2 * h.cap * sizeof(int), stream));
+  MSMD_CUDA_OK(cudaMemsetAsync(h.num_flag, 0, 2 * sizeof(int), stream));
+  const int n = n3 + n2;
+  split_insert_kernel<<<ceil_div(n, 256), 256, 0, stream>>>(coord3, n3, coord2, n2, h.cap - 1, h.keys, h.cnt, h.ids,
+                                                           h.slot_of, h.key_of, num_mix + 1);
+  MSMD_LAUNCH_OK();
+  split_flag_hash_kernel<<<ceil_div(n, 256), 256, 0, stream>>>(n3, n2, h.cap - 1, h.cnt, h.ids, h.slot_of, h.key_of,
+                                                              mix3, mix2, h.flagged, h.cap_pairs, h.num_flag,
+                                                              num_mix + 1);
+  MSMD_LAUNCH_OK();
+  split_sort_flagged_kernel<<<2, 1024, 0, stream>>>(h.flagged, h.cap_pairs, h.num_flag, offset3, offset2, syn3, syn2,
+                                                    num_mix, num_mix + 1);
+  MSMD_LAUNCH_OK();
+  return MSMD_OK;
+}
+
+extern "C" MSMD_API int msmd_modality_split_sort(const int* coord3, int n3, const int* coord2, int n2,
                                             long long offset3, long long offset2, int* mix3,
                                             int* mix2, long long* syn3, long long* syn2,
                                             int* num_mix, void* workspace, size_t workspace_bytes,

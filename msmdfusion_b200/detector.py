@@ -428,31 +428,34 @@ class MSMDFusionDetector(nn.Module, _VoxelPathMixin):
         overlap = (self.overlap_image_side and dev.type == 'cuda' and not torch.is_grad_enabled() and
                    getattr(self.pts_middle_encoder, 'use_executor', False))
         compressed = None
+        main = torch.cuda.current_stream(dev) if overlap else None
         if overlap:
-            # the compression convolutions (cuDNN) do not depend on the LiDAR branch: issue them first so that the
-            # side stream below never waits behind the LiDAR convolutions for them
-            compressed = self.depth_aware_channel_compression(img_feats, img_metas)
+            # the compression convolutions (cuDNN, ~1.2 ms) depend on nothing from the LiDAR branch: they open the
+            # side stream, so the LiDAR voxelisation's read-back on `main` does not wait behind them
+            side = self._side(dev)
+            start = torch.cuda.Event()
+            start.record(main)
+            side.wait_event(start)
+            with torch.cuda.stream(side):
+                compressed = self.depth_aware_channel_compression(img_feats, img_metas)
         voxel_features, coors, _ = self.voxelize_mean(pts, nf)
         # a frozen LiDAR encoder (tools/train.py:185-211) has no grad-requiring input either (voxelize is
         # no_grad, :462-464), so autograd would skip it anyway: run it on the inference path
         frozen = torch.is_grad_enabled() and not any(p.requires_grad for p in self.pts_middle_encoder.parameters())
-        main = torch.cuda.current_stream(dev) if overlap else None
-        if overlap:
-            inputs_ready = torch.cuda.Event()
-            inputs_ready.record(main)
         with (torch.no_grad() if frozen else contextlib.nullcontext()):
             x, encode_features = self.pts_middle_encoder(voxel_features, coors, batch_size)
-        if overlap and getattr(self.pts_middle_encoder, 'ran_on_executor', False):
+        if overlap:
             from . import executor
             geom_done = torch.cuda.Event()
-            geom_done.record(executor.geometry_stream(dev))
-            side = self._side(dev)
-            side.wait_event(inputs_ready)   # compressed image features, the packed virtual points
-            side.wait_event(geom_done)      # index sets of the four LiDAR scales
+            if getattr(self.pts_middle_encoder, 'ran_on_executor', False):
+                geom_done.record(executor.geometry_stream(dev))   # index sets of the four LiDAR scales
+            else:
+                geom_done.record(main)
+            side.wait_event(geom_done)
             # Allocator note: tensors created under `side` and read later on `main` are safe without record_stream.
             # `main` waits for `image_side_done` before it reads them, and the side stream only ever starts a step's
-            # work after waiting for an event recorded on `main` (inputs_ready), i.e. after every main-stream reader
-            # of the previous step's blocks has been queued AND finished before the blocks can be rewritten.
+            # work after waiting for an event recorded on `main` (start), i.e. after every main-stream reader of the
+            # previous step's blocks has been queued AND finished before the blocks can be rewritten.
             with torch.cuda.stream(side):
                 v3l, v2l, s3l, s2l = self.extract_multiscale_voxel_feat(
                     img_feats, encode_features, img_metas, self.spatial_shapes, self.downscale_factors, batch_size,

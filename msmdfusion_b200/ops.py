@@ -616,6 +616,9 @@ def group_assign(group, val, nn_idx, dist_thresh, nq, base=0):
 # --------------------------------------------------------------------------------------
 # voxel_modality_split (one sample), sparse_add, lift gather
 # --------------------------------------------------------------------------------------
+FORCE_SPLIT_SORT = False   # tests: run the sort path of voxel_modality_split as well
+
+
 def modality_split_single(coord3, coord2, offset3=0, offset2=0):
     """coord3 (n3,4) / coord2 (n2,4) int32 rows of one sample ->
     (mix3 (n3) i32, mix2 (n2) i32, syn3 (P) i64, syn2 (P) i64)."""
@@ -627,13 +630,17 @@ def modality_split_single(coord3, coord2, offset3=0, offset2=0):
     cap = max(1, min(n3, n2))
     syn3 = torch.empty((cap,), dtype=torch.int64, device=dev)
     syn2 = torch.empty((cap,), dtype=torch.int64, device=dev)
-    count = torch.zeros((1,), dtype=torch.int32, device=dev)
+    count = torch.empty((2,), dtype=torch.int32, device=dev)   # [pairs, overflow]: zeroed by the call
     ws = scratch.get(dev, lib().msmd_modality_split_workspace(n3, n2))
+    args = (ptr(coord3), n3, ptr(coord2), n2, int(offset3), int(offset2), ptr(mix3), ptr(mix2), ptr(syn3), ptr(syn2),
+            ptr(count), ptr(ws), ws.numel(), stream(dev))
     with _Timed('modality_split', n3=n3, n2=n2):
-        check(lib().msmd_modality_split(ptr(coord3), n3, ptr(coord2), n2, int(offset3), int(offset2),
-                                        ptr(mix3), ptr(mix2), ptr(syn3), ptr(syn2), ptr(count), ptr(ws),
-                                        ws.numel(), stream(dev)), 'msmd_modality_split')
-    p = int(count.item())
+        check(lib().msmd_modality_split(*args), 'msmd_modality_split')
+    p, overflow = count.tolist()
+    if overflow or FORCE_SPLIT_SORT:   # a key run longer than 8 rows / more than 8192 pairs: the general (sort) path
+        with _Timed('modality_split_sort', n3=n3, n2=n2):
+            check(lib().msmd_modality_split_sort(*args), 'msmd_modality_split_sort')
+        p = int(count[0].item())
     return mix3, mix2, syn3[:p], syn2[:p]
 
 

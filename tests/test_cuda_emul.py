@@ -348,31 +348,47 @@ def digest_key(mask):
     return key
 
 
-def test_emulator_calibration_modality_split_sort_and_scan():
-    """The GPU-verified voxel_modality_split (stable radix sort + device scan + merge) on the emulator
-    reproduces the oracle bit for bit: sort.cuh / scan.cuh execute faithfully."""
-    rng = np.random.default_rng(0)
-    shape = [41, 60, 60]
-    def coords(n):
-        lin = rng.choice(int(np.prod(shape)), size=n, replace=False)
-        return np.stack([np.zeros(n, np.int64), lin // 3600, (lin // 60) % 60, lin % 60], 1).astype(np.int32)
-    c3, c2 = coords(2500), coords(3100)
-    c2[:800] = c3[rng.choice(2500, 800, replace=False)]
-    m3 = np.full(2500, -1, np.int32)
-    m2 = np.full(3100, -1, np.int32)
-    s3 = np.full(2500, -1, np.int64)
-    s2 = np.full(2500, -1, np.int64)
-    cnt = np.zeros(1, np.int32)
+@pytest.mark.parametrize('case', ['plain', 'collisions'])
+def test_modality_split_hash_and_sort_paths_on_emulator(case):
+    """voxel_modality_split on the emulator, both implementations against the oracle bit for bit: the hash path
+    (table on the float key + shared-memory sort of the paired rows; the default) and the sort path (stable radix
+    sorts + binary-search merge; the GPU-verified round-1 code, also the overflow fall-back).  'collisions': z >= 17
+    and x >= 1000, where distinct voxels share a float32 key (runs of several rows per key in BOTH sets)."""
+    rng = np.random.default_rng(0 if case == 'plain' else 7)
+    if case == 'plain':
+        shape = [41, 60, 60]
+        def coords(n):
+            lin = rng.choice(int(np.prod(shape)), size=n, replace=False)
+            return np.stack([np.zeros(n, np.int64), lin // 3600, (lin // 60) % 60, lin % 60], 1).astype(np.int32)
+        n3, n2 = 2500, 3100
+        c3, c2 = coords(n3), coords(n2)
+        c2[:800] = c3[rng.choice(n3, 800, replace=False)]
+    else:
+        def coords(n):   # dense little patches high up and far right: neighbouring x collide, x >= 1000 wraps into y + 1
+            z = rng.integers(17, 41, n)
+            y = rng.integers(100, 104, n)
+            x = rng.integers(990, 1040, n)
+            c = np.unique(np.stack([np.zeros(n, np.int64), z, y, x], 1), axis=0)
+            return c[rng.permutation(c.shape[0])].astype(np.int32)
+        c3, c2 = coords(1500), coords(1800)
+        n3, n2 = c3.shape[0], c2.shape[0]
+    e3, e2, es3, es2 = cpu.voxel_modality_split(c3, c2, 1)
     L = emu()
     L.emu_msmd_modality_split_workspace.restype = ctypes.c_size_t
-    need = L.emu_msmd_modality_split_workspace(2500, 3100)
-    ws = np.zeros(need, np.uint8)
-    ok(L.emu_msmd_modality_split(P(c3), 2500, P(c2), 3100, ctypes.c_longlong(0), ctypes.c_longlong(0), P(m3), P(m2),
-                                 P(s3), P(s2), P(cnt), P(ws), ctypes.c_size_t(need), None))
-    e3, e2, es3, es2 = cpu.voxel_modality_split(c3, c2, 1)
-    assert np.array_equal(m3, e3[:, 1]) and np.array_equal(m2, e2[:, 1])
-    p = int(cnt[0])
-    assert p == es3.shape[0] and np.array_equal(s3[:p], es3) and np.array_equal(s2[:p], es2)
+    need = L.emu_msmd_modality_split_workspace(n3, n2)
+    for fn in (L.emu_msmd_modality_split, L.emu_msmd_modality_split_sort):
+        m3, m2 = np.full(n3, -1, np.int32), np.full(n2, -1, np.int32)
+        s3, s2 = np.full(min(n3, n2), -1, np.int64), np.full(min(n3, n2), -1, np.int64)
+        cnt = np.zeros(2, np.int32)
+        ws = np.zeros(need, np.uint8)
+        ok(fn(P(c3), n3, P(c2), n2, ctypes.c_longlong(0), ctypes.c_longlong(0), P(m3), P(m2), P(s3), P(s2), P(cnt),
+              P(ws), ctypes.c_size_t(need), None))
+        assert cnt[1] == 0, 'unexpected overflow'
+        assert np.array_equal(m3, e3[:, 1]) and np.array_equal(m2, e2[:, 1])
+        p = int(cnt[0])
+        assert p == es3.shape[0] and np.array_equal(s3[:p], es3) and np.array_equal(s2[:p], es2)
+    if case == 'collisions':
+        assert es3.shape[0] > 0 and (e3[:, 1].sum() != np.isin(c3.view([('', c3.dtype)] * 4), c2.view([('', c2.dtype)] * 4)).sum())
 
 
 @pytest.mark.parametrize('n', [700, 5000])

@@ -476,13 +476,23 @@ def test_fps_nn_fast_matches_reference_golden(name):
     assert got.dtype == np.int64 and np.array_equal(got, g['assign'])
 
 
-def test_modality_split_bit_exact():
+@pytest.fixture(params=['hash', 'sort'])
+def split_path(request):
+    """Both implementations of voxel_modality_split: the hash path (default; falls back to the sort path on its own
+    when a key run or the pair count overflows) and the sort path forced."""
+    ops.FORCE_SPLIT_SORT = request.param == 'sort'
+    yield request.param
+    ops.FORCE_SPLIT_SORT = False
+
+
+@pytest.mark.parametrize('pairs', [6000, 900])
+def test_modality_split_bit_exact(split_path, pairs):
     rng = np.random.default_rng(5)
     shape = [41, 1440, 1440]
     i3 = voxel_cloud(rng, 20000, shape, clusters=40, spread=30)
     i2 = voxel_cloud(rng, 30000, shape, clusters=40, spread=30)
-    take = rng.choice(i3.shape[0], 6000, replace=False)
-    i2[:6000] = i3[take]
+    take = rng.choice(i3.shape[0], pairs, replace=False)
+    i2[:pairs] = i3[take]
     i2 = i2[rng.permutation(i2.shape[0])]
     # duplicates inside one set and float-key near-misses (z >= 17: neighbouring x collide)
     i2[100:110] = i2[90:100]
@@ -498,11 +508,11 @@ def test_modality_split_bit_exact():
         assert np.array_equal(mix2.cpu().numpy(), e2[:, 1])
         assert np.array_equal(syn3.cpu().numpy(), es3 + 7)
         assert np.array_equal(syn2.cpu().numpy(), es2 + 11)
-        assert syn3.shape[0] >= 6000
+        assert syn3.shape[0] >= pairs   # 6000 pairs exceed the hash path's shared-memory sort: its fall-back runs
 
 
 @pytest.mark.parametrize('name', ['split_dense_overlap', 'split_lidar_grid', 'split_disjoint'])
-def test_modality_split_matches_reference_golden(name):
+def test_modality_split_matches_reference_golden(split_path, name):
     """CUDA path against committed outputs of the reference's OWN numba merge + float-key / sort
     expressions (MSMDFusion.py:26-45,271-300; fixtures by tests/golden/make_golden_split.py)."""
     g = np.load(os.path.join(GOLDEN, name + '.npz'))
