@@ -422,6 +422,8 @@ MSMD_API int msmd_to_dense(const int* indices, const float* features, int n, int
  *   One batch element per call: xyz (n,3), idx (m).
  * ---------------------------------------------------------------------------------- */
 MSMD_API size_t msmd_fps_workspace(int n);
+/* A/B switch: CTA width of the thread-block-cluster FPS kernel (0 = default heuristic | 256 | 512 | 1024) */
+MSMD_API int msmd_fps_set_threads(int threads);
 MSMD_API int msmd_fps(const float* xyz, int n, int m, int* idx, void* workspace,
                       size_t workspace_bytes, msmd_stream_t stream);
 

@@ -112,6 +112,7 @@ SIGNATURES = {
                                         _vp]),
     'msmd_to_dense': (_i, [_vp, _vp, _i, _i, _i, _c_int_p, _vp, _vp]),
     'msmd_fps_workspace': (_sz, [_i]),
+    'msmd_fps_set_threads': (_i, [_i]),
     'msmd_fps': (_i, [_vp, _i, _i, _vp, _vp, _sz, _vp]),
     'msmd_ball_query': (_i, [_vp, _i, _vp, _i, ctypes.c_float, ctypes.c_float, _i, _vp, _vp]),
     'msmd_nn_search': (_i, [_vp, _i, _i, _vp, _i, _i, _vp, _vp, _vp]),
@@ -160,6 +161,9 @@ def lib():
         if os.environ.get('MSMD_TC16_VARIANT'):  # 16-bit modes: 2 = A via shared memory (default), 3 = A via tensor memory
             if L.msmd_spconv_tc16_set_variant(int(os.environ['MSMD_TC16_VARIANT'])) != 0:
                 raise RuntimeError('bad MSMD_TC16_VARIANT')
+        if os.environ.get('MSMD_FPS_THREADS'):  # A/B switch of the cluster FPS kernel's CTA width
+            if L.msmd_fps_set_threads(int(os.environ['MSMD_FPS_THREADS'])) != 0:
+                raise RuntimeError('bad MSMD_FPS_THREADS')
         if os.environ.get('MSMD_TC_VARIANT'):  # A/B switch of the tensor-core conv kernel (2 | 3)
             if L.msmd_spconv_tc_set_variant(int(os.environ['MSMD_TC_VARIANT'])) != 0:
                 raise RuntimeError('bad MSMD_TC_VARIANT')

@@ -432,6 +432,14 @@ static int fps_block_size(int n, int* log2block) {
 
 using namespace msmd;
 
+static int g_fps_threads = 0;
+// A/B switch of the cluster FPS kernel's CTA width: 0 (default heuristic) | 256 | 512 | 1024
+extern "C" MSMD_API int msmd_fps_set_threads(int threads) {
+  MSMD_REQUIRE(threads == 0 || threads == 256 || threads == 512 || threads == 1024, "fps_set_threads: 0, 256, 512 or 1024");
+  g_fps_threads = threads;
+  return MSMD_OK;
+}
+
 extern "C" MSMD_API size_t msmd_fps_workspace(int n) { return (size_t)(n > 0 ? n : 1) * sizeof(float) + 256; }
 
 extern "C" MSMD_API int msmd_fps(const float* xyz, int n, int m, int* idx, void* workspace,
@@ -472,7 +480,13 @@ extern "C" MSMD_API int msmd_fps(const float* xyz, int n, int m, int* idx, void*
     }                                                                                           \
     fps_cluster_kernel<P, T><<<kFpsCluster, T, smem, stream>>>(xyz, n, m, block, log2block, idx); \
   } while (0)
-    if (n <= cap_wide * 8) {
+    // A/B switch (msmd_fps_set_threads): 0 = the default below; 256 / 512 / 1024 = force that CTA width when the points fit
+    const long long cap_thin = (long long)kFpsCluster * 256;
+    int width = g_fps_threads;
+    if (width == 0) width = (n <= cap_wide * 8) ? 1024 : 512;
+    if (width == 256 && n > cap_thin * kFpsMaxPerThread) width = 512;
+    if (width == 1024 && n > cap_wide * 8) width = 512;
+    if (width == 1024) {
       const int ppt = ceil_div(n, cap_wide);
       if (ppt <= 1) MSMD_FPS(1, kFpsThreadsWide);
       else if (ppt <= 2) MSMD_FPS(2, kFpsThreadsWide);
@@ -480,9 +494,19 @@ extern "C" MSMD_API int msmd_fps(const float* xyz, int n, int m, int* idx, void*
       else if (ppt <= 4) MSMD_FPS(4, kFpsThreadsWide);
       else if (ppt <= 6) MSMD_FPS(6, kFpsThreadsWide);
       else MSMD_FPS(8, kFpsThreadsWide);
+    } else if (width == 256) {
+      const int ppt = ceil_div(n, cap_thin);
+      if (ppt <= 4) MSMD_FPS(4, 256);
+      else if (ppt <= 8) MSMD_FPS(8, 256);
+      else if (ppt <= 12) MSMD_FPS(12, 256);
+      else if (ppt <= 16) MSMD_FPS(16, 256);
+      else MSMD_FPS(kFpsMaxPerThread, 256);
     } else {
       const int ppt = ceil_div(n, cap_deep);
-      if (ppt <= 16) MSMD_FPS(16, kFpsThreadsDeep);
+      if (ppt <= 4) MSMD_FPS(4, kFpsThreadsDeep);
+      else if (ppt <= 8) MSMD_FPS(8, kFpsThreadsDeep);
+      else if (ppt <= 12) MSMD_FPS(12, kFpsThreadsDeep);
+      else if (ppt <= 16) MSMD_FPS(16, kFpsThreadsDeep);
       else MSMD_FPS(kFpsMaxPerThread, kFpsThreadsDeep);
     }
 #undef MSMD_FPS

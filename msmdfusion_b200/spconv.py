@@ -31,12 +31,16 @@ from .registry import CONV_LAYERS
 
 # contraction kernel: 'tc' (tcgen05, 3xTF32) or 'simt' (exact fp32 FFMA); MSMD_CONV_PATH overrides
 CONV_PATH = os.environ.get('MSMD_CONV_PATH', 'tc')
-# operand precision of the tensor-core path: 'tf32x3' (3xTF32, ~1e-6 of fp32), 'bf16x3' (bf16 hi/lo split, ~5e-6
-# per layer, half the tensor-pipe time), 'bf16x3c' (the SAME arithmetic as bf16x3 through the split-bf16 operand
-# cache of csrc/spconv_sb.cu: activations are split by their producer, the gather is cp.async) or 'bf16' (operands
-# rounded to bf16: the train-step arithmetic BASELINE configs[4] names -- outside the inference parity bound).
+# operand precision of the tensor-core path:
+#   'bf16x3c' (DEFAULT since round 2) bf16 hi/lo split, 3 MMAs per product, fp32 accumulate (~2.5e-5 absolute per
+#             layer at |x| ~ 5) through the split-bf16 operand cache of csrc/spconv_sb.cu: activations are split by
+#             their producer, the gather is cp.async -- the fastest parity mode on the B200 (profiles/r02*)
+#   'bf16x3'  the same arithmetic, split inside the gather warps (csrc/spconv_tc16.cu)
+#   'tf32x3'  3xTF32 (csrc/spconv_tc.cu): ~1e-6 of fp32 per layer, the most accurate and the slowest
+#   'bf16'    operands rounded to bf16, one MMA: the train-step arithmetic BASELINE configs[4] names -- outside the
+#             inference parity bound
 # MSMD_CONV_PRECISION overrides; train.VoxelSpaceTrainStep(precision=...) sets it for a train step.
-CONV_PRECISION = os.environ.get('MSMD_CONV_PRECISION', 'tf32x3')
+CONV_PRECISION = os.environ.get('MSMD_CONV_PRECISION', 'bf16x3c')
 # opt-in: mask-sorted tiles for the 3x3x3 SubM layers of the tensor-core path (spconv-2.x
 # mask_argsort_fwd_splits); MSMD_MASK_SORT=1 also switches it on inside the native executor
 MASK_SORT = os.environ.get('MSMD_MASK_SORT', '0') not in ('', '0')

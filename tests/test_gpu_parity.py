@@ -668,10 +668,13 @@ def test_fused_gma_gates_equal_eager_path():
             outs[fused] = (bev.clone(), [(t.indices.clone(), t.features.clone()) for t in stage_outs])
     finally:
         fe.SparseMultiModalEncoderPaint.fused_gates = True
+    # the two formulations sum the 16..128-term gate dot products in different orders (1 ulp); the convolutions behind
+    # them round their operands to 16 significant bits in the default bf16x3c mode, which can turn an ulp into 2^-17
+    # of an operand: observed 3.5e-5 absolute after four stages (4.8e-6 in the tf32x3 mode)
     for (ia, fa), (ib, fb) in zip(outs[True][1], outs[False][1]):
         assert torch.equal(ia, ib)
-        assert feat_err(fa.cpu().numpy(), fb.cpu().numpy()) < 1e-5
-    assert feat_err(outs[True][0].cpu().numpy(), outs[False][0].cpu().numpy()) < 1e-5
+        assert feat_err(fa.cpu().numpy(), fb.cpu().numpy()) < FEAT_TOL
+    assert feat_err(outs[True][0].cpu().numpy(), outs[False][0].cpu().numpy()) < FEAT_TOL
 
 
 @pytest.mark.parametrize('overlap', [True, False])

@@ -28,6 +28,7 @@ pytestmark = pytest.mark.gpu
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 TOL = 1e-4
+DEFAULT_PRECISION = m.spconv.CONV_PRECISION   # what the process started with (MSMD_CONV_PRECISION or the library default)
 
 
 def dev():
@@ -360,7 +361,7 @@ def test_tc16_bf16x3_sparse_encoder_within_parity_bound():
             torch.cuda.synchronize()
             outs[prec] = (spatial.clone(), [f.features.clone() for f in feats])
     finally:
-        m.spconv.CONV_PRECISION = 'tf32x3'
+        m.spconv.CONV_PRECISION = DEFAULT_PRECISION
     assert err(outs['bf16x3'][0], outs['tf32x3'][0]) < TOL
     for a, b in zip(outs['bf16x3'][1], outs['tf32x3'][1]):
         assert err(a, b) < TOL
@@ -423,7 +424,7 @@ def test_split_operand_sparse_encoder_within_parity_bound():
             torch.cuda.synchronize()
             outs[(prec, use_exec)] = (spatial.clone(), [f.features.clone() for f in feats], [f.indices.clone() for f in feats])
     finally:
-        m.spconv.CONV_PRECISION = 'tf32x3'
+        m.spconv.CONV_PRECISION = DEFAULT_PRECISION
         se.SparseEncoder.use_executor = True
     base, sb, sbm, b16 = outs[('tf32x3', True)], outs[('bf16x3c', True)], outs[('bf16x3c', False)], outs[('bf16x3', True)]
     for a, b in zip(sb[2], base[2]):
@@ -451,7 +452,7 @@ def test_tc16_bf16_backward_matches_rounded_operand_autograd():
         y = conv(x)
         y.features.backward(cuda(go))
     finally:
-        m.spconv.CONV_PRECISION = 'tf32x3'
+        m.spconv.CONV_PRECISION = DEFAULT_PRECISION
     w = conv.weight.detach().cpu().numpy()
     ref_y = cpu.spconv_fwd(bf16_round(torch.from_numpy(feat)).numpy(), bf16_round(torch.from_numpy(w)).numpy(), pair)
     assert err(y.features, ref_y) < 1e-5
