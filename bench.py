@@ -51,7 +51,8 @@ def parse():
                          'encoder, one NCCL gradient all-reduce, clip, AdamW')
     ap.add_argument('--precision', default=None, choices=['tf32x3', 'bf16x3', 'bf16x3c', 'bf16'],
                     help='operand precision of the tensor-core sparse convolutions (default: MSMD_CONV_PRECISION or '
-                         'tf32x3 = the fp32-parity mode).  bf16x3: bf16 hi/lo split, ~5e-6 per layer.  bf16: operands '
+                         'bf16x3c = the library default: bf16 hi/lo split with the split cached by the producing layer, ~5e-6 per '
+                         'layer vs fp32).  tf32x3 / bf16x3: the round-1 kernels with the same error class.  bf16: operands '
                          'rounded to bf16 (the train-step arithmetic of BASELINE configs[4]; not a parity mode)')
     ap.add_argument('--scenes-per-step', type=int, default=1,
                     help='workload L only: scenes batched into one step on each GPU (default 1 = the workload '

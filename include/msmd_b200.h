@@ -244,6 +244,12 @@ MSMD_API int msmd_spconv_sb_pack_weight(const float* weight_krsc, int cout, int 
 MSMD_API int msmd_spconv_fwd_sb(const void* features_split, int n_in, const void* packed_sb, const int* pair_fwd,
                                 int n_out, int cin, int cout, int kvol, const float* scale, const float* shift,
                                 const float* residual, int relu, float* out, void* out_split, msmd_stream_t stream);
+/* Schedule of msmd_spconv_fwd_sb (A/B switch, same results): 0 = default = 2; 1 = one 128-row tile per CTA; 2 = the
+ * persistent kernel: one CTA per SM slot over an equal share of the launch's (tile, K chunk) units, tiles that
+ * straddle a share are summed through an L2 hand-off in fixed CTA order, epilogue overlapped with the next tile's
+ * main loop.  The hand-off slots (<= 19 MB) belong to the library, one set per (device, stream), allocated on the
+ * first launch on that stream. */
+MSMD_API int msmd_spconv_sb_set_variant(int variant);
 
 /* ------------------------------------------------------------------------------------
  * Sparse convolution BACKWARD (config 5, the train step) -- replaces the backward of

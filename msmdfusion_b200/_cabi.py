@@ -85,6 +85,7 @@ SIGNATURES = {
     'msmd_split_width': (_i, [_i]),
     'msmd_split_bf16': (_i, [_vp, _i, _i, _vp, _vp]),
     'msmd_spconv_sb_packed_bytes': (_sz, [_i, _i, _i]),
+    'msmd_spconv_sb_set_variant': (_i, [_i]),
     'msmd_spconv_sb_pack_weight': (_i, [_vp, _i, _i, _i, _vp, _vp]),
     'msmd_spconv_fwd_sb': (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp]),
     'msmd_spconv_tc16_set_variant': (_i, [_i]),
@@ -161,6 +162,9 @@ def lib():
         if os.environ.get('MSMD_TC16_VARIANT'):  # 16-bit modes: 2 = A via shared memory (default), 3 = A via tensor memory
             if L.msmd_spconv_tc16_set_variant(int(os.environ['MSMD_TC16_VARIANT'])) != 0:
                 raise RuntimeError('bad MSMD_TC16_VARIANT')
+        if os.environ.get('MSMD_SB_VARIANT'):  # schedule of the split-operand conv kernel: 1 tile per CTA | 2 persistent
+            if L.msmd_spconv_sb_set_variant(int(os.environ['MSMD_SB_VARIANT'])) != 0:
+                raise RuntimeError('bad MSMD_SB_VARIANT')
         if os.environ.get('MSMD_FPS_THREADS'):  # A/B switch of the cluster FPS kernel's CTA width
             if L.msmd_fps_set_threads(int(os.environ['MSMD_FPS_THREADS'])) != 0:
                 raise RuntimeError('bad MSMD_FPS_THREADS')

@@ -483,7 +483,9 @@ extern "C" MSMD_API int msmd_fps(const float* xyz, int n, int m, int* idx, void*
     // A/B switch (msmd_fps_set_threads): 0 = the default below; 256 / 512 / 1024 = force that CTA width when the points fit
     const long long cap_thin = (long long)kFpsCluster * 256;
     int width = g_fps_threads;
-    if (width == 0) width = (n <= cap_wide * 8) ? 1024 : 512;
+    // measured on the LC scene (profiles/r02k_lc_timeline_fps*.txt): 46.8k points 2.36 ms at 512 threads vs 2.68 at
+    // 1024 and 2.95 at 256; 35k points 1.82 vs 1.96; 24k points equal -> the wide CTA only up to 3 points per thread
+    if (width == 0) width = (n <= cap_wide * 3) ? 1024 : 512;
     if (width == 256 && n > cap_thin * kFpsMaxPerThread) width = 512;
     if (width == 1024 && n > cap_wide * 8) width = 512;
     if (width == 1024) {

@@ -30,6 +30,10 @@
 #include "tc_common.cuh"
 #include "tc_trace.cuh"
 
+#include <map>
+#include <mutex>
+#include <utility>
+
 namespace msmd {
 
 constexpr int kSbKC = 64;                 // bf16 K elements per chunk
@@ -342,6 +346,436 @@ spconv_fwd_sb_kernel(const uint16_t* __restrict__ xs, const uint16_t* __restrict
   if (warp == kTcProducerWarps + 1) tc::tmem_dealloc(tmem_base, (uint32_t)tmem_cols);
 }
 
+// ======================================================================================================
+// Persistent, work-balanced variant (r02l).
+//
+// The kernel above is at the measured tensor rate INSIDE its main loop (0.53 us per 128 x 384 x 64 chunk of the
+// 128 -> 128 layers = 11 TFLOP/s per SM = MEASURED_PEAKS' dense bf16 rate / 148), and loses the rest around it
+// (profiles/r02j ncu list): a grid of 169 tiles on 148 SMs runs two waves for 1.14 waves of work, and the
+// 1.5 us set-up + 8 us epilogue of every tile are serial with its 24 us main loop.  This variant keeps the tile
+// code and changes the schedule:
+//   * one CTA per SM slot, each given an equal, contiguous range of the launch's (tile, K chunk) units.  A tile
+//     that straddles a range boundary is finished by the CTA holding its FIRST chunk (its owner, which reaches it
+//     last); the CTAs holding the rest reach their fragment first, and hand the owner raw fp32 partial sums
+//     through an L2-resident slot + one release/acquire flag per epilogue warp.  The owner adds the partials in
+//     CTA order, so the result does not depend on timing;
+//   * two accumulators in tensor memory and dedicated epilogue warps: the epilogue of segment i runs under the
+//     main loop of segment i + 1; a loader warp fetches the next segment's pair rows (cp.async) and builds its
+//     active-chunk list one segment ahead.
+// Warp roles: 0-7 A producers, 8 B loader, 9 MMA issuer + TMEM owner, 10 segment loader, 11.. epilogue (4 or 8).
+// ======================================================================================================
+constexpr int kSbpWarpB = kTcProducerWarps;
+constexpr int kSbpWarpMma = kTcProducerWarps + 1;
+constexpr int kSbpWarpSeg = kTcProducerWarps + 2;
+constexpr int kSbpWarpEpi = kTcProducerWarps + 3;
+constexpr int kSbpBarBytes = 320;   // 20 mbarriers | tmem pointer, n_act[2] | used[32]
+
+struct SbpLayout {
+  int stage_bytes, stages, pair_off, pair_bytes, act_off, act_bytes, bar_off, total;
+};
+static SbpLayout sbp_layout(int N, int kvol, int chunks, int budget) {
+  SbpLayout L;
+  L.stage_bytes = 2 * kSbABytes + 2 * N * 128;
+  L.pair_bytes = round_up(kvol * kTcM * 4, 16);
+  L.act_bytes = round_up(2 * chunks, 16);
+  const int misc = 2 * L.pair_bytes + 2 * L.act_bytes + kSbpBarBytes + 8 * N + 1024;
+  L.stages = (budget - misc) / L.stage_bytes;
+  if (L.stages > 6) L.stages = 6;
+  if (g_tc_tune[1] >= 2 && g_tc_tune[1] <= 6 && L.stages > g_tc_tune[1]) L.stages = g_tc_tune[1];
+  if (L.stages < 0) L.stages = 0;
+  L.pair_off = L.stages * L.stage_bytes;
+  L.act_off = L.pair_off + 2 * L.pair_bytes;
+  L.bar_off = L.act_off + 2 * L.act_bytes;
+  L.total = L.bar_off + kSbpBarBytes + 8 * N + 1024;
+  return L;
+}
+
+__device__ __forceinline__ void flag_wait(const uint32_t* flag) {
+  if (tc::ld_acquire_gpu(flag) != 0u) return;
+  const long long t0 = clock64();
+  while (tc::ld_acquire_gpu(flag) == 0u) {
+    if (clock64() - t0 > 4000000000LL) __trap();   // a protocol bug must surface as an error, never hang the GPU
+  }
+}
+
+template <int kEpiWarps>   // 8: one CTA per SM | 4: two CTAs per SM (<= 68 registers)
+__global__ void __launch_bounds__((kSbpWarpEpi + kEpiWarps) * 32, kEpiWarps == 4 ? 2 : 1)
+spconv_fwd_sbp_kernel(const uint16_t* __restrict__ xs, const uint16_t* __restrict__ wpk,
+                      const int* __restrict__ pair, const int* __restrict__ row_perm, int n_out, int cin_pad,
+                      uint32_t cin_magic, int cout, int cout_pad, int N, int kvol, int chunks, int stages,
+                      int stage_bytes, int pair_off, int pair_bytes, int act_off, int act_bytes, int bar_off,
+                      int tmem_cols, const float* __restrict__ scale, const float* __restrict__ shift,
+                      const float* __restrict__ residual, int relu, float* __restrict__ out,
+                      uint16_t* __restrict__ out_s, int cat, int total_units, float* __restrict__ ws,
+                      uint32_t* __restrict__ flags) {
+  constexpr int epi_warps = kEpiWarps;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t* full_bar = (uint64_t*)(smem + bar_off);
+  uint64_t* empty_bar = full_bar + 6;
+  uint64_t* acc_full = full_bar + 12;    // [2] MMA issuer -> epilogue: accumulator complete
+  uint64_t* acc_empty = full_bar + 14;   // [2] epilogue -> MMA issuer: accumulator read
+  uint64_t* seg_full = full_bar + 16;    // [2] segment loader -> everyone: pair rows + active list ready
+  uint64_t* seg_empty = full_bar + 18;   // [2] everyone -> segment loader
+  uint32_t* tmem_ptr_s = (uint32_t*)(full_bar + 20);
+  int* n_act_s = (int*)(full_bar + 20) + 2;   // [2]
+  int* used_s = (int*)(full_bar + 22);        // [32]
+  float* ss = (float*)(smem + bar_off + kSbpBarBytes);
+  for (int c = threadIdx.x; c < N; c += blockDim.x) {
+    ss[c] = (scale && c < cout) ? __ldg(scale + c) : 1.f;
+    ss[N + c] = (shift && c < cout) ? __ldg(shift + c) : 0.f;
+  }
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int G = gridDim.x, cta = blockIdx.x;
+  const int u_begin = (int)((long long)total_units * cta / G);
+  const int u_end = (int)((long long)total_units * (cta + 1) / G);
+
+  if (tid == 0) {
+    for (int s = 0; s < stages; ++s) {
+      tc::mbar_init(&full_bar[s], kTcProducers + 1);
+      tc::mbar_init(&empty_bar[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      tc::mbar_init(&acc_full[b], 1);
+      tc::mbar_init(&acc_empty[b], (uint32_t)epi_warps);
+      tc::mbar_init(&seg_full[b], 1);
+      tc::mbar_init(&seg_empty[b], (uint32_t)(kTcProducerWarps + 2 + epi_warps));
+    }
+    tc::fence_mbar_init();
+  }
+  if (warp == kSbpWarpMma) {
+    tc::tmem_alloc(tmem_ptr_s, (uint32_t)(2 * tmem_cols));
+    tc::tmem_relinquish();
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem_base = *tmem_ptr_s;
+
+// every role walks the same segment list: (tile, [j0, j1) of its K chunks), derived from the CTA's unit range
+#define SBP_FOR_SEGMENTS                                                        \
+  for (int u = u_begin, seg = 0, tile = 0, j0 = 0, j1 = 0;                      \
+       u < u_end && (tile = u / chunks, j0 = u - tile * chunks,                 \
+                     j1 = min(chunks, j0 + (u_end - u)), true);                 \
+       u += j1 - j0, ++seg)
+
+  if (warp < kTcProducerWarps) {
+    // ===== A producers (the loop body of spconv_fwd_sb_kernel; the stage ring runs on across segments) =====
+    const int q = tid & 7;
+    const int rbase = tid >> 3;
+    const size_t row_elems = (size_t)2 * cin_pad;
+    int s = 0;
+    uint32_t ph = 1u;
+    SBP_FOR_SEGMENTS {
+      const int b = seg & 1;
+      mbar_wait_warp(&seg_full[b], (uint32_t)(seg >> 1) & 1u, lane);
+      const int n_act = n_act_s[b];
+      const int* pair_s = (const int*)(smem + pair_off + b * pair_bytes);
+      const unsigned short* alist = (const unsigned short*)(smem + act_off + b * act_bytes);
+      for (int t = 0; t < n_act; ++t) {
+        mbar_wait_warp(&empty_bar[s], ph, lane);
+        const uint32_t kk0 = (uint32_t)alist[t] * kSbKC + (uint32_t)q * 8u;
+        const uint32_t k = __umulhi(kk0, cin_magic);
+        const uint32_t c0 = kk0 - k * (uint32_t)cin_pad;
+        const bool kvalid = k < (uint32_t)kvol;
+        const int* prow = pair_s + (kvalid ? k : 0u) * kTcM + rbase;
+        int idx[kTcM / 32];
+#pragma unroll
+        for (int i = 0; i < kTcM / 32; ++i) idx[i] = prow[32 * i];
+        const uint32_t a_hi = tc::smem_u32(smem) + (uint32_t)s * (uint32_t)stage_bytes + (uint32_t)(rbase * 128) +
+                              (uint32_t)((q ^ (rbase & 7)) << 4);
+#pragma unroll
+        for (int i = 0; i < kTcM / 32; ++i) {
+          const bool v = kvalid && idx[i] >= 0;
+          const uint16_t* src = xs + (v ? (size_t)idx[i] * row_elems + c0 : 0);
+          const uint32_t nb = v ? 16u : 0u;
+          tc::cp_async_16(a_hi + (uint32_t)(i * 32 * 128), src, nb);
+          tc::cp_async_16(a_hi + (uint32_t)(i * 32 * 128) + kSbABytes, v ? src + cin_pad : src, nb);
+        }
+        tc::cp_async_mbar_arrive_noinc(&full_bar[s]);
+        if (++s == stages) { s = 0; ph ^= 1u; }
+      }
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&seg_empty[b]);
+    }
+  } else if (warp == kSbpWarpB) {
+    // ===== B loader ================================================================================
+    const uint32_t bytes = (uint32_t)(2 * N * 128);
+    int s = 0;
+    uint32_t ph = 1u;
+    SBP_FOR_SEGMENTS {
+      const int b = seg & 1;
+      mbar_wait_warp(&seg_full[b], (uint32_t)(seg >> 1) & 1u, lane);
+      const int n_act = n_act_s[b];
+      const unsigned short* alist = (const unsigned short*)(smem + act_off + b * act_bytes);
+      for (int t = 0; t < n_act; ++t) {
+        tc::mbar_wait(&empty_bar[s], ph);
+        const uint8_t* src = (const uint8_t*)wpk + (size_t)alist[t] * bytes;
+        if (tc::elect_one()) {
+          tc::mbar_arrive_expect_tx(&full_bar[s], bytes);
+          tc::bulk_g2s(smem + (size_t)s * stage_bytes + 2 * kSbABytes, src, bytes, &full_bar[s]);
+        }
+        __syncwarp();
+        if (++s == stages) { s = 0; ph ^= 1u; }
+      }
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&seg_empty[b]);
+    }
+  } else if (warp == kSbpWarpMma) {
+    // ===== MMA issuer ==============================================================================
+    const uint32_t idesc = tc::idesc_f32acc(tc::kFmtBF16, kTcM, N);
+    const uint32_t idesc2 = tc::idesc_f32acc(tc::kFmtBF16, kTcM, 2 * N);
+    const uint32_t dhi = tc::desc_hi32_k_sw128();
+    const uint32_t lo0 = tc::desc_lo32(tc::smem_u32(smem));
+    const uint32_t stage_lo = (uint32_t)stage_bytes >> 4, a_lo_off = (uint32_t)kSbABytes >> 4;
+    const uint32_t b_hi_off = (uint32_t)(2 * kSbABytes) >> 4, b_lo_off = b_hi_off + (((uint32_t)N * 128u) >> 4);
+    int s = 0;
+    uint32_t ph = 0;
+    SBP_FOR_SEGMENTS {
+      const int b = seg & 1;
+      const uint32_t sph = (uint32_t)(seg >> 1) & 1u;
+      tc::mbar_wait(&seg_full[b], sph);
+      const int n_act = n_act_s[b];
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&seg_empty[b]);
+      tc::mbar_wait(&acc_empty[b], sph ^ 1u);   // the epilogue has read the accumulator used two segments ago
+      tc::fence_after_sync();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(b * tmem_cols);
+      if (n_act == 0) {
+        if (lane == 0) tc::mbar_arrive(&acc_full[b]);   // nothing to multiply: the epilogue takes zeros
+        __syncwarp();
+      }
+      uint32_t accumulate = 0;
+      for (int t = 0; t < n_act; ++t) {
+        tc::mbar_wait(&full_bar[s], ph);
+        tc::fence_proxy_async();
+        tc::fence_after_sync();
+        const uint32_t a = lo0 + (uint32_t)s * stage_lo;
+        if (tc::elect_one()) {
+#pragma unroll
+          for (int ks = 0; ks < kSbKC / 16; ++ks) {
+            const uint32_t ah = a + (uint32_t)ks * 2u;
+            if (cat) {
+              tc::mma_f16_lo(d_tmem, ah, ah + b_hi_off, dhi, idesc2, accumulate);
+              tc::mma_f16_lo(d_tmem, ah + a_lo_off, ah + b_hi_off, dhi, idesc, 1u);
+            } else {
+              tc::mma_f16_lo(d_tmem, ah + a_lo_off, ah + b_hi_off, dhi, idesc, accumulate);
+              tc::mma_f16_lo(d_tmem, ah, ah + b_lo_off, dhi, idesc, 1u);
+              tc::mma_f16_lo(d_tmem, ah, ah + b_hi_off, dhi, idesc, 1u);
+            }
+            accumulate = 1u;
+          }
+          tc::mma_commit(&empty_bar[s]);
+          if (t == n_act - 1) tc::mma_commit(&acc_full[b]);
+        }
+        __syncwarp();
+        accumulate = 1u;
+        if (++s == stages) { s = 0; ph ^= 1u; }
+      }
+    }
+  } else if (warp == kSbpWarpSeg) {
+    // ===== segment loader: pair rows of the tile + the list of its K chunks in [j0, j1) that have a pair =====
+    SBP_FOR_SEGMENTS {
+      const int b = seg & 1;
+      mbar_wait_warp(&seg_empty[b], ((uint32_t)(seg >> 1) & 1u) ^ 1u, lane);
+      int* pair_s = (int*)(smem + pair_off + b * pair_bytes);
+      unsigned short* alist = (unsigned short*)(smem + act_off + b * act_bytes);
+      const int row0 = tile * kTcM;
+      for (int k = 0; k < kvol; ++k) {
+#pragma unroll
+        for (int i = 0; i < kTcM / 32; ++i) {
+          const int r = lane + 32 * i;
+          const int o = row0 + r;
+          if (o < n_out) tc::cp_async_4(tc::smem_u32(pair_s + k * kTcM + r), pair + (size_t)k * n_out + o);
+          else pair_s[k * kTcM + r] = -1;
+        }
+      }
+      tc::cp_async_wait_all();
+      __syncwarp();
+      for (int k = 0; k < kvol; ++k) {
+        bool any = false;
+#pragma unroll
+        for (int i = 0; i < kTcM / 32; ++i) any |= pair_s[k * kTcM + lane + 32 * i] >= 0;
+        const unsigned bal = __ballot_sync(0xffffffffu, any);
+        if (lane == 0) used_s[k] = bal != 0;
+      }
+      __syncwarp();
+      int cnt = 0;
+      for (int base = j0; base < j1; base += 32) {
+        const int j = base + lane;
+        int a = 0;
+        if (j < j1) {
+          const int k_lo = (j * kSbKC) / cin_pad;
+          int k_hi = (j * kSbKC + kSbKC - 1) / cin_pad;
+          if (k_hi > kvol - 1) k_hi = kvol - 1;
+          for (int k = k_lo; k <= k_hi; ++k) a |= used_s[k];
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, a != 0);
+        if (a) alist[cnt + __popc(bal & ((1u << lane) - 1u))] = (unsigned short)j;
+        cnt += __popc(bal);
+      }
+      if (lane == 0) n_act_s[b] = cnt;
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&seg_full[b]);
+    }
+  } else if (warp < kSbpWarpEpi + epi_warps) {
+    // ===== epilogue ================================================================================
+    const int ew = warp - kSbpWarpEpi;
+    const int quarter = warp & 3;                 // the TMEM lanes (accumulator rows) this warp may read
+    const int halves = epi_warps >> 2;            // 1 or 2 warps per quarter split the columns
+    const int half = ew >> 2;
+    const int nsteps = N / 16;
+    const int per = (nsteps + halves - 1) / halves;
+    const int step_lo = half * per, step_hi = min(nsteps, step_lo + per);
+    const bool vec_out = (cout % 4 == 0) && (out == nullptr || ((uintptr_t)out & 15) == 0) &&
+                         (residual == nullptr || ((uintptr_t)residual & 15) == 0);
+    const int prow = quarter * 32 + lane;
+    const size_t slot = (size_t)kTcM * N;         // floats per partial slot, [16-column step][row][16]
+    SBP_FOR_SEGMENTS {
+      const int b = seg & 1;
+      const uint32_t sph = (uint32_t)(seg >> 1) & 1u;
+      tc::mbar_wait(&seg_full[b], sph);
+      const int n_act = n_act_s[b];
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&seg_empty[b]);
+      tc::mbar_wait(&acc_full[b], sph);
+      tc::fence_after_sync();
+      const uint32_t t_addr = tmem_base + (uint32_t)(b * tmem_cols) + ((uint32_t)(quarter * 32) << 16);
+      const bool owner = j0 == 0;
+      const int tile_end = (tile + 1) * chunks;
+      int slot_o = tile * kTcM + prow;
+      int o = slot_o;
+      if (row_perm) o = (slot_o < n_out) ? __ldg(row_perm + slot_o) : n_out;
+      if (owner && j1 < chunks) {
+        // wait (once per contributor) before the column loop; the flags are consumed below, after the reads
+        for (int cc = cta + 1; cc < G; ++cc) {
+          if ((int)((long long)total_units * cc / G) >= tile_end) break;
+          if (lane == 0) flag_wait(flags + (size_t)cc * 8 + ew);
+        }
+        __syncwarp();
+      }
+      for (int st = step_lo; st < step_hi; ++st) {
+        const int c0 = st * 16;
+        uint32_t acc[16];
+        if (n_act > 0) {
+          tc::tmem_ld16(t_addr + (uint32_t)c0, acc);
+          if (cat) {
+            uint32_t acc2[16];
+            tc::tmem_ld16(t_addr + (uint32_t)(N + c0), acc2);
+            tc::tmem_ld_wait();
+#pragma unroll
+            for (int e = 0; e < 16; ++e) acc[e] = __float_as_uint(__uint_as_float(acc[e]) + __uint_as_float(acc2[e]));
+          }
+          tc::tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int e = 0; e < 16; ++e) acc[e] = 0u;
+        }
+        if (!owner) {   // raw partial sums for the tile's owner
+          float4* dst = (float4*)(ws + (size_t)cta * slot + ((size_t)st * kTcM + prow) * 16);
+#pragma unroll
+          for (int e = 0; e < 16; e += 4)
+            __stcg(dst + (e >> 2), make_float4(__uint_as_float(acc[e]), __uint_as_float(acc[e + 1]),
+                                               __uint_as_float(acc[e + 2]), __uint_as_float(acc[e + 3])));
+          continue;
+        }
+        if (j1 < chunks) {
+          for (int cc = cta + 1; cc < G; ++cc) {
+            if ((int)((long long)total_units * cc / G) >= tile_end) break;
+            const float4* src = (const float4*)(ws + (size_t)cc * slot + ((size_t)st * kTcM + prow) * 16);
+#pragma unroll
+            for (int e = 0; e < 16; e += 4) {
+              const float4 pv = __ldcg(src + (e >> 2));
+              acc[e] = __float_as_uint(__uint_as_float(acc[e]) + pv.x);
+              acc[e + 1] = __float_as_uint(__uint_as_float(acc[e + 1]) + pv.y);
+              acc[e + 2] = __float_as_uint(__uint_as_float(acc[e + 2]) + pv.z);
+              acc[e + 3] = __float_as_uint(__uint_as_float(acc[e + 3]) + pv.w);
+            }
+          }
+        }
+        if (o >= n_out) continue;
+        float y[16];
+        const float* rrow = residual ? residual + (size_t)o * cout : nullptr;
+#pragma unroll
+        for (int e = 0; e < 16; e += 4) {
+          const int co = c0 + e;
+#pragma unroll
+          for (int qq = 0; qq < 4; ++qq) y[e + qq] = fmaf(__uint_as_float(acc[e + qq]), ss[co + qq], ss[N + co + qq]);
+          if (rrow && co < cout) {
+            if (vec_out) {
+              const float4 rv = __ldg((const float4*)(rrow + co));
+              y[e] += rv.x; y[e + 1] += rv.y; y[e + 2] += rv.z; y[e + 3] += rv.w;
+            } else {
+#pragma unroll
+              for (int qq = 0; qq < 4; ++qq)
+                if (co + qq < cout) y[e + qq] += __ldg(rrow + co + qq);
+            }
+          }
+          if (relu) {
+#pragma unroll
+            for (int qq = 0; qq < 4; ++qq) y[e + qq] = fmaxf(y[e + qq], 0.f);
+          }
+        }
+        if (out) {
+          float* orow = out + (size_t)o * cout;
+#pragma unroll
+          for (int e = 0; e < 16; e += 4) {
+            const int co = c0 + e;
+            if (co >= cout) break;
+            if (vec_out) {
+              *(float4*)(orow + co) = make_float4(y[e], y[e + 1], y[e + 2], y[e + 3]);
+            } else {
+#pragma unroll
+              for (int qq = 0; qq < 4; ++qq)
+                if (co + qq < cout) orow[co + qq] = y[e + qq];
+            }
+          }
+        }
+        if (out_s) {
+          uint16_t* srow = out_s + (size_t)o * (2 * cout_pad);
+#pragma unroll
+          for (int e = 0; e < 16; e += 8) {
+            const int co = c0 + e;
+            if (co >= cout_pad) break;
+            uint32_t h[4], l[4];
+#pragma unroll
+            for (int qq = 0; qq < 4; ++qq) {
+              const float av = (co + 2 * qq < cout) ? y[e + 2 * qq] : 0.f;
+              const float bv = (co + 2 * qq + 1 < cout) ? y[e + 2 * qq + 1] : 0.f;
+              h[qq] = tc::pack_bf16x2(av, bv);
+              l[qq] = tc::pack_bf16x2(av - __uint_as_float(h[qq] << 16), bv - __uint_as_float(h[qq] & 0xFFFF0000u));
+            }
+            *(uint4*)(srow + co) = make_uint4(h[0], h[1], h[2], h[3]);
+            *(uint4*)(srow + cout_pad + co) = make_uint4(l[0], l[1], l[2], l[3]);
+          }
+        }
+      }
+      // the accumulator is free again; publish / consume the hand-off flags of this warp's share
+      tc::fence_before_sync();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&acc_empty[b]);
+      if (!owner) {
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) tc::st_release_gpu(flags + (size_t)cta * 8 + ew, 1u);
+      } else if (j1 < chunks) {
+        __syncwarp();
+        if (lane == 0) {
+          for (int cc = cta + 1; cc < G; ++cc) {
+            if ((int)((long long)total_units * cc / G) >= tile_end) break;
+            tc::st_relaxed_gpu(flags + (size_t)cc * 8 + ew, 0u);   // back to zero for the next launch on this stream
+          }
+        }
+      }
+    }
+  }
+#undef SBP_FOR_SEGMENTS
+
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == kSbpWarpMma) tc::tmem_dealloc(tmem_base, (uint32_t)(2 * tmem_cols));
+}
+
 // fp32 rows -> split image [hi | lo] with the channel count padded to 8 (zeros)
 __global__ void __launch_bounds__(256)
 split_bf16_kernel(const float* __restrict__ x, long long n, int c, int c_pad, uint16_t* __restrict__ xs) {
@@ -388,6 +822,58 @@ using namespace msmd;
 extern "C" MSMD_API int msmd_sb_trace_set(unsigned long long* buf) { return tc_trace_set_impl(buf); }
 #endif
 
+// ---- persistent variant: schedule switch + the per-stream hand-off workspace -------------------------------
+static int g_sb_variant = 0;   // 0 = default (persistent) | 1 = one tile per CTA (spconv_fwd_sb_kernel) | 2 = persistent
+extern "C" MSMD_API int msmd_spconv_sb_set_variant(int variant) {
+  MSMD_REQUIRE(variant >= 0 && variant <= 2, "spconv_sb_set_variant: 0 (default), 1 (tile per CTA) or 2 (persistent)");
+  g_sb_variant = variant;
+  return MSMD_OK;
+}
+
+namespace {
+// Launches on one stream are serial, so one slot set per (device, stream) is enough; the flags are zero between
+// launches (their consumer resets them).  Allocated on first use, grown when a launch needs more.
+struct SbpWorkspace {
+  float* ws = nullptr;
+  size_t ws_bytes = 0;
+  uint32_t* flags = nullptr;
+  int flag_ctas = 0;
+};
+std::mutex g_sbp_mu;
+std::map<std::pair<int, cudaStream_t>, SbpWorkspace> g_sbp_ws;
+
+int sbp_workspace(cudaStream_t stream, int ctas, size_t ws_bytes, SbpWorkspace* out) {
+  int dev = 0;
+  MSMD_CUDA_OK(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lock(g_sbp_mu);
+  SbpWorkspace& w = g_sbp_ws[std::make_pair(dev, stream)];
+  if (w.ws_bytes < ws_bytes) {
+    if (w.ws) {
+      MSMD_CUDA_OK(cudaStreamSynchronize(stream));   // earlier launches on the stream may still use the old slots
+      MSMD_CUDA_OK(cudaFree(w.ws));
+      w.ws = nullptr;
+      w.ws_bytes = 0;
+    }
+    MSMD_CUDA_OK(cudaMalloc((void**)&w.ws, ws_bytes));
+    w.ws_bytes = ws_bytes;
+  }
+  if (w.flag_ctas < ctas) {
+    if (w.flags) {
+      MSMD_CUDA_OK(cudaStreamSynchronize(stream));
+      MSMD_CUDA_OK(cudaFree(w.flags));
+      w.flags = nullptr;
+      w.flag_ctas = 0;
+    }
+    const int n = ctas < 2 * kNumSMs ? 2 * kNumSMs : ctas;
+    MSMD_CUDA_OK(cudaMalloc((void**)&w.flags, (size_t)n * 8 * sizeof(uint32_t)));
+    MSMD_CUDA_OK(cudaMemsetAsync(w.flags, 0, (size_t)n * 8 * sizeof(uint32_t), stream));   // ordered before the launch
+    w.flag_ctas = n;
+  }
+  *out = w;
+  return MSMD_OK;
+}
+}  // namespace
+
 extern "C" MSMD_API int msmd_split_width(int channels) { return 2 * round_up(channels > 0 ? channels : 1, 8); }
 
 extern "C" MSMD_API int msmd_split_bf16(const float* x, int n, int channels, void* xs, msmd_stream_t stream_) {
@@ -423,6 +909,66 @@ extern "C" MSMD_API int msmd_spconv_sb_pack_weight(const float* weight_krsc, int
   return MSMD_OK;
 }
 
+// Launch of the persistent kernel: occupancy (1 or 2 CTAs per SM), grid = the SM slots (never more CTAs than
+// units of work), equal unit ranges.
+static int sbp_launch(const SbGeom& g, const void* features_split, const void* packed_sb, const int* pair_fwd,
+                      const int* row_perm, int n_out, int cout, int kvol, const float* scale, const float* shift,
+                      const float* residual, int relu, float* out, void* out_split, cudaStream_t stream) {
+  const int tiles = ceil_div(n_out, kTcM);
+  const long long units = (long long)tiles * g.chunks;
+  MSMD_REQUIRE(units < (1ll << 31), "spconv_fwd_sb: too many (tile, chunk) units");
+  const int cat = (2 * g.N <= 256) ? 1 : 0;
+  int tmem_cols = 32;
+  while (tmem_cols < (cat ? 2 * g.N : g.N)) tmem_cols <<= 1;
+  // two CTAs per SM when each still gets >= 3 stages in half of the shared memory and half of tensor memory, and
+  // there is more than one SM's worth of work per slot; the tuning switch [0] forces either
+  const SbpLayout half = sbp_layout(g.N, kvol, g.chunks, 112 * 1024);
+  bool two = half.stages >= 3 && 2 * tmem_cols <= 256 && units >= 4ll * 2 * kNumSMs;
+  if (g_tc_tune[0] == 1) two = false;
+  if (g_tc_tune[0] == 2) two = half.stages >= 2 && 2 * tmem_cols <= 256;
+  const SbpLayout L = two ? half : sbp_layout(g.N, kvol, g.chunks, 227 * 1024);
+  MSMD_REQUIRE(L.stages >= 2, "spconv_fwd_sb: tile does not fit in shared memory");
+  const int epi_warps = two ? 4 : 8;
+  const int threads = (kSbpWarpEpi + epi_warps) * 32;
+  static bool attr_set = false;
+  static int resident[2] = {0, 0};   // CTAs per SM the hardware really co-schedules, [one, two]
+  if (!attr_set) {
+    MSMD_CUDA_OK(cudaFuncSetAttribute(spconv_fwd_sbp_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    MSMD_CUDA_OK(cudaFuncSetAttribute(spconv_fwd_sbp_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+    attr_set = true;
+  }
+  if (resident[two] == 0) {
+    int n = 0;
+    if (two) MSMD_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, spconv_fwd_sbp_kernel<4>, threads, (size_t)L.total));
+    else MSMD_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, spconv_fwd_sbp_kernel<8>, threads, (size_t)L.total));
+    MSMD_REQUIRE(n >= 1, "spconv_fwd_sb: the persistent kernel does not fit on an SM");
+    resident[two] = n > 2 ? 2 : n;
+  }
+  long long slots = (long long)kNumSMs * (two ? resident[1] : 1);
+  // a range shorter than a few chunks is all hand-off: never more CTAs than units / 4
+  if (slots > (units + 3) / 4) slots = (units + 3) / 4;
+  if (slots < 1) slots = 1;
+  const int grid = (int)slots;
+  SbpWorkspace w;
+  const int rc = sbp_workspace(stream, grid, (size_t)grid * kTcM * g.N * sizeof(float), &w);
+  if (rc != MSMD_OK) return rc;
+  const uint32_t cin_magic = (uint32_t)((((uint64_t)1 << 32) + (uint64_t)g.cin_pad - 1) / (uint64_t)g.cin_pad);
+  for (uint32_t kk = 0; kk < (uint32_t)g.chunks * kSbKC; kk += 8) {
+    MSMD_REQUIRE((uint32_t)(((uint64_t)kk * cin_magic) >> 32) == kk / (uint32_t)g.cin_pad,
+                 "spconv_fwd_sb: reciprocal of cin_pad %d is inexact at %u", g.cin_pad, kk);
+  }
+#define MSMD_SBP_ARGS                                                                                             \
+  (const uint16_t*)features_split, (const uint16_t*)packed_sb, pair_fwd, row_perm, n_out, g.cin_pad, cin_magic, cout, \
+      round_up(cout, 8), g.N, kvol, g.chunks, L.stages, L.stage_bytes, L.pair_off, L.pair_bytes, L.act_off,           \
+      L.act_bytes, L.bar_off, tmem_cols, scale, shift, residual, relu, out, (uint16_t*)out_split, cat, (int)units,    \
+      w.ws, w.flags
+  if (two) spconv_fwd_sbp_kernel<4><<<grid, threads, L.total, stream>>>(MSMD_SBP_ARGS);
+  else spconv_fwd_sbp_kernel<8><<<grid, threads, L.total, stream>>>(MSMD_SBP_ARGS);
+#undef MSMD_SBP_ARGS
+  MSMD_LAUNCH_OK();
+  return MSMD_OK;
+}
+
 extern "C" MSMD_API int msmd_spconv_fwd_sb(const void* features_split, int n_in, const void* packed_sb,
                                            const int* pair_fwd, int n_out, int cin, int cout, int kvol,
                                            const float* scale, const float* shift, const float* residual, int relu,
@@ -439,6 +985,9 @@ extern "C" MSMD_API int msmd_spconv_fwd_sb(const void* features_split, int n_in,
                    ((uintptr_t)out_split & 15) == 0,
                "spconv_fwd_sb: split images and packed weights must be 16-byte aligned");
   const int tiles = ceil_div(n_out, kTcM);
+  if (g_sb_variant != 1)
+    return sbp_launch(g, features_split, packed_sb, pair_fwd, nullptr, n_out, cout, kvol, scale, shift, residual, relu,
+                      out, out_split, stream);
   const SbLayout L = sb_layout(g.N, kvol, g.chunks, tiles);
   MSMD_REQUIRE(L.stages >= 2, "spconv_fwd_sb: tile does not fit in shared memory");
   static bool attr_set = false;

@@ -1058,6 +1058,21 @@ def sb_fwd(feat, w, pair, scale=None, shift=None, residual=None, relu=0, want_ou
     return out, out_s
 
 
+@pytest.fixture(params=['tile_per_cta', 'persistent', 'persistent_two_per_sm'])
+def sb_schedule(request):
+    """The three schedules of csrc/spconv_sb.cu: one tile per CTA (r02c kernel), the persistent work-balanced kernel
+    with one CTA per SM (8 epilogue warps), and its two-CTAs-per-SM instantiation (4 epilogue warps).  The small
+    test shapes give the persistent kernel ranges of ~4 chunks, so nearly every tile is split over 2-3 CTAs."""
+    L = tc_emu()
+    assert L.emu_msmd_spconv_sb_set_variant({'tile_per_cta': 1}.get(request.param, 2)) == 0
+    assert L.emu_msmd_spconv_tc_set_tuning(0, 2 if request.param == 'persistent_two_per_sm' else 1) == 0
+    try:
+        yield request.param
+    finally:
+        L.emu_msmd_spconv_sb_set_variant(0)
+        L.emu_msmd_spconv_tc_set_tuning(0, 0)
+
+
 def split_to_float(xs, c):
     """[hi | lo] bf16 image -> hi + lo as fp32 (first c channels) and the padding channels."""
     c8 = xs.shape[1] // 2
@@ -1082,7 +1097,7 @@ def test_split_bf16_image_on_emulator():
                                         (24, 144, 150),   # chunk boundaries inside a kernel offset, padded N, 3-MMA mode
                                         (64, 128, 140),   # one offset per chunk, concatenated-B at 2N = 256
                                         (80, 96, 260)])   # fusion-encoder widths, ragged last tile, several tiles
-def test_sb_kernel_on_emulator(cin, cout, n):
+def test_sb_kernel_on_emulator(cin, cout, n, sb_schedule):
     """csrc/spconv_sb.cu on the tcgen05 model with late-as-possible asynchronous copies: the result equals the
     bf16x3 arithmetic (within 2e-5 of the fp32 oracle), the split image the epilogue writes IS the split of the fp32
     result it writes (bit for bit, padding channels zero), fused epilogue, fp32-only and split-only outputs."""
@@ -1111,7 +1126,7 @@ def test_sb_kernel_on_emulator(cin, cout, n):
     assert np.array_equal(only_s, sb_split(got))
 
 
-def test_sb_kernel_chain_strided_rulebook_and_empty_tiles_on_emulator():
+def test_sb_kernel_chain_strided_rulebook_and_empty_tiles_on_emulator(sb_schedule):
     """Two layers chained through the split image only (the second never sees fp32 activations), a strided
     rulebook, and a tile without any pair."""
     shape = [7, 14, 14]

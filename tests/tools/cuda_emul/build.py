@@ -104,6 +104,7 @@ std::atomic<int> g_or{0};
 uint8_t* g_dyn_smem = nullptr;
 void (*g_block_begin)(uint32_t) = nullptr;
 void (*g_block_end)() = nullptr;
+bool g_blocks_descending = false;
 }
 extern "C" const char* emu_last_error() { return ::emu::g_error; }
 '''
@@ -165,10 +166,11 @@ std::map<int, std::vector<std::function<void()>>> g_cpasync_pending;
 int g_async_late = 1;
 static void tc_begin(uint32_t bytes) { tc_block_reset(bytes); g_dyn_smem = g_smem_window + kDynBase; }
 static void tc_end() { tc_block_check(); }
-static struct TcHooks { TcHooks() { g_block_begin = tc_begin; g_block_end = tc_end; } } g_tc_hooks;
+static struct TcHooks { TcHooks() { g_block_begin = tc_begin; g_block_end = tc_end; g_blocks_descending = true; } } g_tc_hooks;
 }
 extern "C" long long emu_tc_mma_count() { return ::emu::g_mma_count.load(); }
 extern "C" void emu_tc_set_async_late(int v) { ::emu::g_async_late = v; }
+extern "C" void emu_set_blocks_descending(int v) { ::emu::g_blocks_descending = v != 0; }
 '''
 
 

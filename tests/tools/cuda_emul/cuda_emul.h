@@ -61,6 +61,10 @@ enum { MSMD_OK = 0, MSMD_ERR_INVALID = -1, MSMD_ERR_CUDA = -2, MSMD_ERR_WORKSPAC
 // streams and events: the emulation is synchronous, every launch has completed when it returns
 enum { cudaStreamNonBlocking = 1, cudaEventDisableTiming = 2, cudaMemcpyDeviceToHost = 2, cudaMemcpyHostToDevice = 1 };
 static inline cudaError_t cudaGetDevice(int* d) { *d = 0; return 0; }
+static inline cudaError_t cudaMalloc(void** p, size_t n) { *p = malloc(n ? n : 1); return *p ? 0 : 2; }
+static inline cudaError_t cudaFree(void* p) { free(p); return 0; }
+template <typename F>
+static inline cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessor(int* n, F, int, size_t) { *n = 2; return 0; }
 static inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { *s = (void*)0x5; return 0; }
 static inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) { *e = (void*)0xE; return 0; }
 static inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return 0; }
@@ -84,6 +88,7 @@ extern std::atomic<int> g_or;
 // dynamic shared memory + per-CTA hooks (set by tc_emul.h's translation unit; null for the SIMT units)
 extern uint8_t* g_dyn_smem;
 extern void (*g_block_begin)(uint32_t dyn_smem_bytes);
+extern bool g_blocks_descending;   // order in which emu::launch runs the thread blocks of a grid
 extern void (*g_block_end)();
 
 constexpr size_t kLaneStack = 256 * 1024;
@@ -199,7 +204,10 @@ void launch(dim3 grid, dim3 block, size_t dyn_smem_bytes, F body) {
     ts.emplace_back([&, wi]() {
       WarpCtx& w = warps[wi];
       t_warp = &w;
-      for (unsigned b = 0; b < nblocks; ++b) {
+      for (unsigned bi = 0; bi < nblocks; ++bi) {
+        // thread blocks run one after another; a persistent kernel whose CTA c consumes what CTAs > c produced
+        // first (csrc/spconv_sb.cu) needs them in DESCENDING order -- any order is a legal CUDA schedule
+        const unsigned b = g_blocks_descending ? nblocks - 1 - bi : bi;
         t_blockIdx = dim3(b % grid.x, (b / grid.x) % grid.y, b / (grid.x * grid.y));
         w.live = w.nlanes;
         w.sync_count = 0;
@@ -230,7 +238,7 @@ void launch(dim3 grid, dim3 block, size_t dyn_smem_bytes, F body) {
         cta_done.arrive_and_wait();
         if (wi == 0) {                                 // everyone else is parked between the two barriers
           if (g_block_end) g_block_end();
-          if (b + 1 < nblocks) begin_cta();
+          if (bi + 1 < nblocks) begin_cta();
         }
         cta_ready.arrive_and_wait();
       }

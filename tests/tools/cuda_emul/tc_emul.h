@@ -274,6 +274,26 @@ static inline void cp_async_16(uint32_t dst_smem, const void* src, uint32_t src_
     if (src_bytes) memcpy(dst, src, 16); else memset(dst, 0, 16);
   });
 }
+static inline void cp_async_4(uint32_t dst_smem, const void* src) {
+  if ((dst_smem & 3) || ((uintptr_t)src & 3)) ::emu::tc_fail("cp.async 4: dst %u / src %p must be 4-byte aligned", dst_smem, src);
+  uint8_t* dst = ::emu::smem_ptr(dst_smem, 4);
+  std::lock_guard<std::mutex> g(::emu::g_tc_mu);
+  ::emu::g_cpasync_pending[::emu::emu_lin_tid()].push_back([dst, src] { memcpy(dst, src, 4); });
+}
+// cp.async.wait_all: the calling thread's copies land now (the latest legal moment)
+static inline void cp_async_wait_all() {
+  std::vector<std::function<void()>> copies;
+  {
+    std::lock_guard<std::mutex> g(::emu::g_tc_mu);
+    copies = std::move(::emu::g_cpasync_pending[::emu::emu_lin_tid()]);
+    ::emu::g_cpasync_pending[::emu::emu_lin_tid()].clear();
+  }
+  for (auto& c : copies) c();
+}
+// flags between CTAs: thread blocks run one after another here, so these are plain atomics
+static inline uint32_t ld_acquire_gpu(const uint32_t* p) { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
+static inline void st_release_gpu(uint32_t* p, uint32_t v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
+static inline void st_relaxed_gpu(uint32_t* p, uint32_t v) { __atomic_store_n(p, v, __ATOMIC_RELAXED); }
 static inline void cp_async_mbar_arrive_noinc(uint64_t* bar) {
   std::lock_guard<std::mutex> g(::emu::g_tc_mu);
   auto& b = bar_at(bar);

@@ -66,8 +66,10 @@ def main():
     ops.PROFILE = None
     seen, report = set(), []
     tot = dict(tf32x3=0.0, bf16x3=0.0, sb=0.0)
-    print('%-30s %9s %9s | %9s %9s %9s %9s | %7s %9s' % ('layer', 'tf32x3', 'bf16x3', 'sb auto', 'sb occ1', 'sb occ2',
-                                                        'sb st=2', 'split', 'err'))
+    tot['sb_tile'] = 0.0
+    print('%-30s %9s %9s | %9s | %9s %9s %9s %9s | %7s %9s %9s' % ('layer', 'tf32x3', 'bf16x3', 'sb tile', 'sbp auto',
+                                                                    'sbp occ1', 'sbp occ2', 'sbp st=2', 'split', 'err',
+                                                                    'vs tile'))
     for r in recs:
         key = (r['cin'], r['cout'], r['kvol'], r['n_out'], r['residual'])
         mult = sum(1 for q in recs if (q['cin'], q['cout'], q['kvol'], q['n_out'], q['residual']) == key)
@@ -87,8 +89,15 @@ def main():
         row['tf32x3'] = time_call(lambda: ops.spconv_fwd_tc(feat, packed['tf32x3'], pair, sc, sh, res, True))
         row['bf16x3'] = time_call(lambda: ops.spconv_fwd_tc(feat, packed['bf16x3'], pair, sc, sh, res, True))
         xs = ops.split_bf16(feat)          # cached on `feat`: the timed calls below gather the existing image
+        ops.check(L.msmd_spconv_sb_set_variant(1), 'msmd_spconv_sb_set_variant')   # one tile per CTA (r02c-k kernel)
+        out_tile = ops.spconv_fwd_sb(feat, packed['bf16x3c'], pair, sc, sh, res, True)
+        row['sb_tile'] = time_call(lambda: ops.spconv_fwd_sb(feat, packed['bf16x3c'], pair, sc, sh, res, True))
+        ops.check(L.msmd_spconv_sb_set_variant(0), 'msmd_spconv_sb_set_variant')   # persistent, work-balanced
         out = ops.spconv_fwd_sb(feat, packed['bf16x3c'], pair, sc, sh, res, True)
         row['err'] = float((out - ref).abs().max()) / scale
+        row['vs_tile'] = float((out - out_tile).abs().max()) / scale
+        again = ops.spconv_fwd_sb(feat, packed['bf16x3c'], pair, sc, sh, res, True)
+        row['deterministic'] = bool(torch.equal(out, again))
         img = out._msmd_split[1]
         chk = ops.split_bf16(out.clone())
         row['split_image_ok'] = bool(torch.equal(img, chk))
@@ -104,12 +113,13 @@ def main():
         row['split'] = time_call(lambda: (f2.__dict__.pop('_msmd_split', None), ops.split_bf16(f2)))
         for k in tot:
             tot[k] += mult * row[k]
-        print('%-30s %8.1fu %8.1fu | %8.1fu %8.1fu %8.1fu %8.1fu | %6.1fu %9.2e %s x%d' % (
-            row['layer'], row['tf32x3'], row['bf16x3'], row['sb'], row['sb_occ1'], row['sb_occ2'], row['sb_st2'],
-            row['split'], row['err'], 'img-ok' if row['split_image_ok'] else 'IMG-MISMATCH', mult))
+        print('%-30s %8.1fu %8.1fu | %8.1fu | %8.1fu %8.1fu %8.1fu %8.1fu | %6.1fu %9.2e %9.2e %s %s x%d' % (
+            row['layer'], row['tf32x3'], row['bf16x3'], row['sb_tile'], row['sb'], row['sb_occ1'], row['sb_occ2'],
+            row['sb_st2'], row['split'], row['err'], row['vs_tile'],
+            'img-ok' if row['split_image_ok'] else 'IMG-MISMATCH', 'det' if row['deterministic'] else 'NONDET', mult))
         report.append(row)
-    print('sum over the %d conv launches of one scene: tf32x3 %.1f us, bf16x3 %.1f us, bf16x3c %.1f us' % (
-        len(recs), tot['tf32x3'], tot['bf16x3'], tot['sb']))
+    print('sum over the %d conv launches of one scene: tf32x3 %.1f us, bf16x3 %.1f us, bf16x3c tile-per-CTA %.1f us, '
+          'bf16x3c persistent %.1f us' % (len(recs), tot['tf32x3'], tot['bf16x3'], tot['sb_tile'], tot['sb']))
     if args.json:
         os.makedirs(os.path.dirname(os.path.abspath(args.json)), exist_ok=True)
         json.dump(dict(layers=report, totals_us=tot, launches=len(recs)), open(args.json, 'w'), indent=1)
