@@ -282,7 +282,17 @@ def run_ours(args, rank, world, device):
     # time before the W warm-up steps the caller asked for; untimed, reported in config.settle_ms
     t_settle = None
     settle_steps = 0
-    while t_settle is None or (time.perf_counter() - t_settle) * 1e3 < SETTLE_MS:
+    def keep_settling():
+        more = t_settle is None or (time.perf_counter() - t_settle) * 1e3 < SETTLE_MS
+        if world > 1 and trainer is not None:
+            # the train step holds a collective (the gradient all-reduce): every rank must run the SAME number of
+            # steps, so the wall-clock decision is taken jointly (r02l: rank-local counts dead-locked the N=2 run)
+            flag = torch.tensor([int(more)], device=device)
+            dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+            more = bool(int(flag.item()))
+        return more
+
+    while keep_settling():
         flush.zero_()
         spatial, feats = step(pts_dev)
         torch.cuda.synchronize(device)

@@ -250,6 +250,20 @@ MSMD_API int msmd_spconv_fwd_sb(const void* features_split, int n_in, const void
  * main loop.  The hand-off slots (<= 19 MB) belong to the library, one set per (device, stream), allocated on the
  * first launch on that stream. */
 MSMD_API int msmd_spconv_sb_set_variant(int variant);
+MSMD_API int msmd_spconv_sb_uses_tile_masks(void);   /* 1 under variant 0: callers that keep rulebooks build tile masks */
+/* Per-rulebook side table for the persistent schedule: bit k of tile_mask[t] (t = 128-row tile, ceil(n_out/128) words) is
+ * set when some row of the tile has a pair at kernel offset k.  Built once per rulebook (spconv-2.x keeps the analogous
+ * mask_argsort / pair masks next to its indice pairs, bug_fix/conv.py:382-415). */
+MSMD_API int msmd_rulebook_tile_masks(const int* pair_fwd, int kvol, int n_out, unsigned* tile_mask,
+                                      msmd_stream_t stream);
+/* msmd_spconv_fwd_sb with the two optional tables of the persistent schedule (either may be NULL):
+ *   row_perm   the pair table is a mask-sorted one (msmd_rulebook_mask_sort): tile slot i holds output row row_perm[i];
+ *   tile_mask  msmd_rulebook_tile_masks of `pair_fwd`: K chunks without a pair in a tile are neither gathered nor
+ *              multiplied, and the CTAs' work shares are balanced over the chunks that remain. */
+MSMD_API int msmd_spconv_fwd_sb_ex(const void* features_split, int n_in, const void* packed_sb, const int* pair_fwd,
+                                   const int* row_perm, const unsigned* tile_mask, int n_out, int cin, int cout,
+                                   int kvol, const float* scale, const float* shift, const float* residual, int relu,
+                                   float* out, void* out_split, msmd_stream_t stream);
 
 /* ------------------------------------------------------------------------------------
  * Sparse convolution BACKWARD (config 5, the train step) -- replaces the backward of

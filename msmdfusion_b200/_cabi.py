@@ -86,6 +86,9 @@ SIGNATURES = {
     'msmd_split_bf16': (_i, [_vp, _i, _i, _vp, _vp]),
     'msmd_spconv_sb_packed_bytes': (_sz, [_i, _i, _i]),
     'msmd_spconv_sb_set_variant': (_i, [_i]),
+    'msmd_spconv_sb_uses_tile_masks': (_i, []),
+    'msmd_rulebook_tile_masks': (_i, [_vp, _i, _i, _vp, _vp]),
+    'msmd_spconv_fwd_sb_ex': (_i, [_vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp]),
     'msmd_spconv_sb_pack_weight': (_i, [_vp, _i, _i, _i, _vp, _vp]),
     'msmd_spconv_fwd_sb': (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp]),
     'msmd_spconv_tc16_set_variant': (_i, [_i]),

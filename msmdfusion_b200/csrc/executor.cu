@@ -26,6 +26,7 @@ struct RulebookX {
   int* pair = nullptr;
   int* pair_sorted = nullptr;   // mask-sorted copy of the table + its slot -> row map (opt-in)
   int* row_perm = nullptr;
+  unsigned* tile_mask = nullptr;   // msmd_rulebook_tile_masks of the table the split-operand kernel tiles
   cudaEvent_t ready = nullptr;  // recorded on the geometry stream after the rulebook kernels
   int seq = -1;                 // position of `ready` among the events recorded on the geometry stream
 };
@@ -235,6 +236,12 @@ extern "C" MSMD_API int msmd_sparse_net_forward_ex(const msmd_conv_layer* layers
             rb.row_perm = rp;
             rb.pair_sorted = ps;
           }
+          if (L.weight_tc == 4 && msmd_spconv_sb_uses_tile_masks() && s.n > 0) {
+            MSMD_ARENA(tm, unsigned, (size_t)((s.n + 127) / 128));
+            MSMD_TRY(msmd_rulebook_tile_masks(rb.pair_sorted ? rb.pair_sorted : rb.pair, kvol, s.n, tm,
+                                              (msmd_stream_t)geom));
+            rb.tile_mask = tm;
+          }
           MSMD_TRY(next_event(*aux, &rb.ready));
           MSMD_CUDA_OK(cudaEventRecord(rb.ready, geom));
           rb.seq = ++ready_seq;
@@ -267,6 +274,11 @@ extern "C" MSMD_API int msmd_sparse_net_forward_ex(const msmd_conv_layer* layers
                                           L.padding, L.dilation, s.bits, s.prefix, s.perm, oidx, p,
                                           (msmd_stream_t)geom));
         rb.pair = p;
+        if (L.weight_tc == 4 && msmd_spconv_sb_uses_tile_masks() && n_out > 0) {
+          MSMD_ARENA(tm, unsigned, (size_t)((n_out + 127) / 128));
+          MSMD_TRY(msmd_rulebook_tile_masks(p, kvol, n_out, tm, (msmd_stream_t)geom));
+          rb.tile_mask = tm;
+        }
         MSMD_TRY(next_event(*aux, &rb.ready));
         MSMD_CUDA_OK(cudaEventRecord(rb.ready, geom));
         rb.seq = ++ready_seq;
@@ -300,8 +312,9 @@ extern "C" MSMD_API int msmd_sparse_net_forward_ex(const msmd_conv_layer* layers
           MSMD_ARENA(os, uint16_t, (size_t)n_out * (size_t)msmd_split_width(L.cout));
           out_s = os;
         }
-        MSMD_TRY(msmd_spconv_fwd_sb(act_split[L.input], in.n, L.weight, rb.pair, n_out, L.cin, L.cout, kvol, L.scale,
-                                    L.shift, residual, L.relu, out, out_s, (msmd_stream_t)stream));
+        MSMD_TRY(msmd_spconv_fwd_sb_ex(act_split[L.input], in.n, L.weight, rb.pair_sorted ? rb.pair_sorted : rb.pair,
+                                       rb.pair_sorted ? rb.row_perm : nullptr, rb.tile_mask, n_out, L.cin, L.cout, kvol,
+                                       L.scale, L.shift, residual, L.relu, out, out_s, (msmd_stream_t)stream));
         act_split[li + 1] = out_s;
       } else if (L.weight_tc == 2 || L.weight_tc == 3) {  // 16-bit operand kernels: bf16x3 / bf16
         const size_t ws_bytes = msmd_spconv_tc16_workspace(n_out, L.cout);  // variant 3: split-K hand-off buffer

@@ -368,24 +368,27 @@ constexpr int kSbpWarpB = kTcProducerWarps;
 constexpr int kSbpWarpMma = kTcProducerWarps + 1;
 constexpr int kSbpWarpSeg = kTcProducerWarps + 2;
 constexpr int kSbpWarpEpi = kTcProducerWarps + 3;
-constexpr int kSbpBarBytes = 320;   // 20 mbarriers | tmem pointer, n_act[2] | used[32]
+constexpr int kSbpBarBytes = 320;   // 20 mbarriers | tmem pointer | segment records [2][8] | start record [4]
 
 struct SbpLayout {
-  int stage_bytes, stages, pair_off, pair_bytes, act_off, act_bytes, bar_off, total;
+  int stage_bytes, stages, pair_off, pair_bytes, act_off, act_bytes, kmask_off, bar_off, total;
 };
-static SbpLayout sbp_layout(int N, int kvol, int chunks, int budget) {
+static SbpLayout sbp_layout(int N, int kvol, int chunks, int budget, int epi_warps) {
   SbpLayout L;
   L.stage_bytes = 2 * kSbABytes + 2 * N * 128;
   L.pair_bytes = round_up(kvol * kTcM * 4, 16);
+  if (L.pair_bytes < epi_warps * 2048) L.pair_bytes = epi_warps * 2048;   // doubles as the epilogue's staging blocks
   L.act_bytes = round_up(2 * chunks, 16);
-  const int misc = 2 * L.pair_bytes + 2 * L.act_bytes + kSbpBarBytes + 8 * N + 1024;
+  const int kmask_bytes = round_up(4 * chunks, 16);
+  const int misc = 2 * L.pair_bytes + 2 * L.act_bytes + kmask_bytes + kSbpBarBytes + 8 * N + 1024;
   L.stages = (budget - misc) / L.stage_bytes;
   if (L.stages > 6) L.stages = 6;
   if (g_tc_tune[1] >= 2 && g_tc_tune[1] <= 6 && L.stages > g_tc_tune[1]) L.stages = g_tc_tune[1];
   if (L.stages < 0) L.stages = 0;
   L.pair_off = L.stages * L.stage_bytes;
   L.act_off = L.pair_off + 2 * L.pair_bytes;
-  L.bar_off = L.act_off + 2 * L.act_bytes;
+  L.kmask_off = L.act_off + 2 * L.act_bytes;
+  L.bar_off = L.kmask_off + kmask_bytes;
   L.total = L.bar_off + kSbpBarBytes + 8 * N + 1024;
   return L;
 }
@@ -401,12 +404,13 @@ __device__ __forceinline__ void flag_wait(const uint32_t* flag) {
 template <int kEpiWarps>   // 8: one CTA per SM | 4: two CTAs per SM (<= 68 registers)
 __global__ void __launch_bounds__((kSbpWarpEpi + kEpiWarps) * 32, kEpiWarps == 4 ? 2 : 1)
 spconv_fwd_sbp_kernel(const uint16_t* __restrict__ xs, const uint16_t* __restrict__ wpk,
-                      const int* __restrict__ pair, const int* __restrict__ row_perm, int n_out, int cin_pad,
+                      const int* __restrict__ pair, const int* __restrict__ row_perm,
+                      const uint32_t* __restrict__ tile_mask, int n_out, int tiles, int cin_pad,
                       uint32_t cin_magic, int cout, int cout_pad, int N, int kvol, int chunks, int stages,
-                      int stage_bytes, int pair_off, int pair_bytes, int act_off, int act_bytes, int bar_off,
-                      int tmem_cols, const float* __restrict__ scale, const float* __restrict__ shift,
+                      int stage_bytes, int pair_off, int pair_bytes, int act_off, int act_bytes, int kmask_off,
+                      int bar_off, int tmem_cols, const float* __restrict__ scale, const float* __restrict__ shift,
                       const float* __restrict__ residual, int relu, float* __restrict__ out,
-                      uint16_t* __restrict__ out_s, int cat, int total_units, float* __restrict__ ws,
+                      uint16_t* __restrict__ out_s, int cat, float* __restrict__ ws,
                       uint32_t* __restrict__ flags) {
   constexpr int epi_warps = kEpiWarps;
   extern __shared__ uint8_t smem_raw[];
@@ -415,20 +419,29 @@ spconv_fwd_sbp_kernel(const uint16_t* __restrict__ xs, const uint16_t* __restric
   uint64_t* empty_bar = full_bar + 6;
   uint64_t* acc_full = full_bar + 12;    // [2] MMA issuer -> epilogue: accumulator complete
   uint64_t* acc_empty = full_bar + 14;   // [2] epilogue -> MMA issuer: accumulator read
-  uint64_t* seg_full = full_bar + 16;    // [2] segment loader -> everyone: pair rows + active list ready
+  uint64_t* seg_full = full_bar + 16;    // [2] segment loader -> everyone: pair rows + active list + record ready
   uint64_t* seg_empty = full_bar + 18;   // [2] everyone -> segment loader
   uint32_t* tmem_ptr_s = (uint32_t*)(full_bar + 20);
-  int* n_act_s = (int*)(full_bar + 20) + 2;   // [2]
-  int* used_s = (int*)(full_bar + 22);        // [32]
+  // segment record: 0 chunks to multiply | 1 tile | 2 bit 0 = holds the tile's first unit (owner), bit 1 = reaches its
+  // last unit | 3 unit index one past the tile's last unit | 4 units of the CTA's range this segment covers
+  int* seg_info = (int*)(smem + bar_off + 176);   // [2][8]
+  int* start_s = (int*)(smem + bar_off + 240);    // total units | first tile of the range | first unit inside it
+  uint32_t* kmask_s = (uint32_t*)(smem + kmask_off);   // [chunks]: the kernel offsets chunk j covers, one bit each
   float* ss = (float*)(smem + bar_off + kSbpBarBytes);
   for (int c = threadIdx.x; c < N; c += blockDim.x) {
     ss[c] = (scale && c < cout) ? __ldg(scale + c) : 1.f;
     ss[N + c] = (shift && c < cout) ? __ldg(shift + c) : 0.f;
   }
+  for (int j = threadIdx.x; j < chunks; j += blockDim.x) {
+    const int k_lo = (j * kSbKC) / cin_pad;
+    int k_hi = (j * kSbKC + kSbKC - 1) / cin_pad;
+    if (k_hi > kvol - 1) k_hi = kvol - 1;
+    kmask_s[j] = (0xffffffffu >> (31 - k_hi)) & (0xffffffffu << k_lo);
+  }
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int G = gridDim.x, cta = blockIdx.x;
-  const int u_begin = (int)((long long)total_units * cta / G);
-  const int u_end = (int)((long long)total_units * (cta + 1) / G);
+  TC_TRACE_INIT();
+  TC_TRACE_ENTRY();
 
   if (tid == 0) {
     for (int s = 0; s < stages; ++s) {
@@ -452,28 +465,94 @@ spconv_fwd_sbp_kernel(const uint16_t* __restrict__ xs, const uint16_t* __restric
   tc::fence_after_sync();
   const uint32_t tmem_base = *tmem_ptr_s;
 
-// every role walks the same segment list: (tile, [j0, j1) of its K chunks), derived from the CTA's unit range
-#define SBP_FOR_SEGMENTS                                                        \
-  for (int u = u_begin, seg = 0, tile = 0, j0 = 0, j1 = 0;                      \
-       u < u_end && (tile = u / chunks, j0 = u - tile * chunks,                 \
-                     j1 = min(chunks, j0 + (u_end - u)), true);                 \
-       u += j1 - j0, ++seg)
+  // ---- the CTA's share of the launch --------------------------------------------------------------------------
+  // A tile is worth one unit per K chunk it has to multiply: all of them without `tile_mask`, otherwise the chunks
+  // in which at least one of its rows has a pair (at least 1, so that every tile has an owner for its epilogue).
+  // Every CTA takes units [W*cta/G, W*(cta+1)/G) of the launch's W.  With tile masks the position of the first unit
+  // needs the prefix over the tiles: block-wide, once, in the (still idle) pipeline stages.
+  auto tile_units = [&](int t) {
+    const uint32_t m = __ldg(tile_mask + t);
+    int cnt = 0;
+    for (int j = 0; j < chunks; ++j) cnt += (kmask_s[j] & m) != 0u;
+    return cnt > 0 ? cnt : 1;
+  };
+  int total_units, u_begin, u_end;
+  if (tile_mask) {
+    int* part = (int*)smem;
+    const int T = (int)blockDim.x;
+    const int per = (tiles + T - 1) / T;
+    const int tb = min(tiles, tid * per), te = min(tiles, tb + per);
+    int sum = 0;
+    for (int t = tb; t < te; ++t) sum += tile_units(t);
+    part[tid] = sum;
+    __syncthreads();
+    if (warp == 0) {
+      const int per_l = (T + 31) / 32;
+      const int ib = min(T, lane * per_l), ie = min(T, ib + per_l);
+      int acc = 0;
+      for (int i = ib; i < ie; ++i) { const int v = part[i]; part[i] = acc; acc += v; }
+      int incl = acc;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += v;
+      }
+      const int excl = incl - acc;
+      for (int i = ib; i < ie; ++i) part[i] += excl;
+      if (lane == 31) start_s[0] = incl;
+    }
+    __syncthreads();
+    total_units = start_s[0];
+    u_begin = (int)((long long)total_units * cta / G);
+    u_end = (int)((long long)total_units * (cta + 1) / G);
+    const int ex = part[tid];
+    if (u_begin < u_end && u_begin >= ex && u_begin < ex + sum) {
+      int t = tb, acc = ex;
+      for (;;) {
+        const int w = tile_units(t);
+        if (acc + w > u_begin) break;
+        acc += w;
+        ++t;
+      }
+      start_s[1] = t;
+      start_s[2] = u_begin - acc;
+    }
+    __syncthreads();
+  } else {
+    total_units = tiles * chunks;
+    u_begin = (int)((long long)total_units * cta / G);
+    u_end = (int)((long long)total_units * (cta + 1) / G);
+  }
+  if (tid == 0) { TC_TRACE_HEAD(1, clock64()); TC_TRACE_HEAD(7, u_end - u_begin); }
+
+// every role walks the CTA's segments in step: the loader publishes a record per segment, the others read it
+#define SBP_SEGMENT_LOOP for (int u = u_begin, seg = 0; u < u_end; ++seg)
+#define SBP_SEGMENT_RECORD(wait_stmt)                             \
+  const int b = seg & 1;                                          \
+  const uint32_t sph = (uint32_t)(seg >> 1) & 1u;                 \
+  wait_stmt;                                                      \
+  const int* const si = seg_info + b * 8;                         \
+  const int n_act = si[0], tile = si[1], sflags = si[2], tile_end = si[3]; \
+  u += si[4];                                                     \
+  (void)tile; (void)sflags; (void)tile_end; (void)sph
 
   if (warp < kTcProducerWarps) {
     // ===== A producers (the loop body of spconv_fwd_sb_kernel; the stage ring runs on across segments) =====
     const int q = tid & 7;
     const int rbase = tid >> 3;
     const size_t row_elems = (size_t)2 * cin_pad;
-    int s = 0;
+    const int tr_role = warp == 0 ? 0 : (warp == kTcProducerWarps - 1 ? 1 : -1);
+    (void)tr_role;
+    int s = 0, it = 0;
     uint32_t ph = 1u;
-    SBP_FOR_SEGMENTS {
-      const int b = seg & 1;
-      mbar_wait_warp(&seg_full[b], (uint32_t)(seg >> 1) & 1u, lane);
-      const int n_act = n_act_s[b];
+    SBP_SEGMENT_LOOP {
+      SBP_SEGMENT_RECORD(mbar_wait_warp(&seg_full[b], sph, lane));
       const int* pair_s = (const int*)(smem + pair_off + b * pair_bytes);
       const unsigned short* alist = (const unsigned short*)(smem + act_off + b * act_bytes);
-      for (int t = 0; t < n_act; ++t) {
+      for (int t = 0; t < n_act; ++t, ++it) {
+        if (lane == 0) TC_TRACE(tr_role, it, 0);
         mbar_wait_warp(&empty_bar[s], ph, lane);
+        if (lane == 0) TC_TRACE(tr_role, it, 1);
         const uint32_t kk0 = (uint32_t)alist[t] * kSbKC + (uint32_t)q * 8u;
         const uint32_t k = __umulhi(kk0, cin_magic);
         const uint32_t c0 = kk0 - k * (uint32_t)cin_pad;
@@ -493,23 +572,25 @@ spconv_fwd_sbp_kernel(const uint16_t* __restrict__ xs, const uint16_t* __restric
           tc::cp_async_16(a_hi + (uint32_t)(i * 32 * 128) + kSbABytes, v ? src + cin_pad : src, nb);
         }
         tc::cp_async_mbar_arrive_noinc(&full_bar[s]);
+        if (lane == 0) TC_TRACE(tr_role, it, 2);
         if (++s == stages) { s = 0; ph ^= 1u; }
       }
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(&seg_empty[b]);
     }
+    if (tid == 0) TC_TRACE_HEAD(2, clock64());
   } else if (warp == kSbpWarpB) {
     // ===== B loader ================================================================================
     const uint32_t bytes = (uint32_t)(2 * N * 128);
-    int s = 0;
+    int s = 0, it = 0;
     uint32_t ph = 1u;
-    SBP_FOR_SEGMENTS {
-      const int b = seg & 1;
-      mbar_wait_warp(&seg_full[b], (uint32_t)(seg >> 1) & 1u, lane);
-      const int n_act = n_act_s[b];
+    SBP_SEGMENT_LOOP {
+      SBP_SEGMENT_RECORD(mbar_wait_warp(&seg_full[b], sph, lane));
       const unsigned short* alist = (const unsigned short*)(smem + act_off + b * act_bytes);
-      for (int t = 0; t < n_act; ++t) {
+      for (int t = 0; t < n_act; ++t, ++it) {
+        if (lane == 0) TC_TRACE(2, it, 0);
         tc::mbar_wait(&empty_bar[s], ph);
+        if (lane == 0) TC_TRACE(2, it, 1);
         const uint8_t* src = (const uint8_t*)wpk + (size_t)alist[t] * bytes;
         if (tc::elect_one()) {
           tc::mbar_arrive_expect_tx(&full_bar[s], bytes);
@@ -529,13 +610,10 @@ spconv_fwd_sbp_kernel(const uint16_t* __restrict__ xs, const uint16_t* __restric
     const uint32_t lo0 = tc::desc_lo32(tc::smem_u32(smem));
     const uint32_t stage_lo = (uint32_t)stage_bytes >> 4, a_lo_off = (uint32_t)kSbABytes >> 4;
     const uint32_t b_hi_off = (uint32_t)(2 * kSbABytes) >> 4, b_lo_off = b_hi_off + (((uint32_t)N * 128u) >> 4);
-    int s = 0;
+    int s = 0, it = 0;
     uint32_t ph = 0;
-    SBP_FOR_SEGMENTS {
-      const int b = seg & 1;
-      const uint32_t sph = (uint32_t)(seg >> 1) & 1u;
-      tc::mbar_wait(&seg_full[b], sph);
-      const int n_act = n_act_s[b];
+    SBP_SEGMENT_LOOP {
+      SBP_SEGMENT_RECORD(tc::mbar_wait(&seg_full[b], sph));
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(&seg_empty[b]);
       tc::mbar_wait(&acc_empty[b], sph ^ 1u);   // the epilogue has read the accumulator used two segments ago
@@ -546,8 +624,10 @@ spconv_fwd_sbp_kernel(const uint16_t* __restrict__ xs, const uint16_t* __restric
         __syncwarp();
       }
       uint32_t accumulate = 0;
-      for (int t = 0; t < n_act; ++t) {
+      for (int t = 0; t < n_act; ++t, ++it) {
+        if (lane == 0) TC_TRACE(3, it, 0);
         tc::mbar_wait(&full_bar[s], ph);
+        if (lane == 0) TC_TRACE(3, it, 1);
         tc::fence_proxy_async();
         tc::fence_after_sync();
         const uint32_t a = lo0 + (uint32_t)s * stage_lo;
@@ -570,17 +650,28 @@ spconv_fwd_sbp_kernel(const uint16_t* __restrict__ xs, const uint16_t* __restric
         }
         __syncwarp();
         accumulate = 1u;
+        if (lane == 0) TC_TRACE(3, it, 2);
         if (++s == stages) { s = 0; ph ^= 1u; }
       }
     }
   } else if (warp == kSbpWarpSeg) {
-    // ===== segment loader: pair rows of the tile + the list of its K chunks in [j0, j1) that have a pair =====
-    SBP_FOR_SEGMENTS {
+    // ===== segment loader: pair rows of the tile, the list of its K chunks to multiply, the segment record =====
+    int t = 0, off = 0;
+    if (tile_mask) {
+      t = start_s[1];
+      off = start_s[2];
+    } else if (u_begin < u_end) {
+      t = u_begin / chunks;
+      off = u_begin - t * chunks;
+    }
+    SBP_SEGMENT_LOOP {
       const int b = seg & 1;
+      if (lane == 0) TC_TRACE(5, seg, 0);
       mbar_wait_warp(&seg_empty[b], ((uint32_t)(seg >> 1) & 1u) ^ 1u, lane);
+      if (lane == 0) TC_TRACE(5, seg, 1);
       int* pair_s = (int*)(smem + pair_off + b * pair_bytes);
       unsigned short* alist = (unsigned short*)(smem + act_off + b * act_bytes);
-      const int row0 = tile * kTcM;
+      const int row0 = t * kTcM;
       for (int k = 0; k < kvol; ++k) {
 #pragma unroll
         for (int i = 0; i < kTcM / 32; ++i) {
@@ -590,33 +681,67 @@ spconv_fwd_sbp_kernel(const uint16_t* __restrict__ xs, const uint16_t* __restric
           else pair_s[k * kTcM + r] = -1;
         }
       }
-      tc::cp_async_wait_all();
-      __syncwarp();
-      for (int k = 0; k < kvol; ++k) {
-        bool any = false;
+      uint32_t m;
+      if (tile_mask) {
+        m = __ldg(tile_mask + t);   // the list does not wait for the pair rows
+      } else {
+        tc::cp_async_wait_all();
+        __syncwarp();
+        m = 0u;
+        for (int k = 0; k < kvol; ++k) {
+          bool any = false;
 #pragma unroll
-        for (int i = 0; i < kTcM / 32; ++i) any |= pair_s[k * kTcM + lane + 32 * i] >= 0;
-        const unsigned bal = __ballot_sync(0xffffffffu, any);
-        if (lane == 0) used_s[k] = bal != 0;
-      }
-      __syncwarp();
-      int cnt = 0;
-      for (int base = j0; base < j1; base += 32) {
-        const int j = base + lane;
-        int a = 0;
-        if (j < j1) {
-          const int k_lo = (j * kSbKC) / cin_pad;
-          int k_hi = (j * kSbKC + kSbKC - 1) / cin_pad;
-          if (k_hi > kvol - 1) k_hi = kvol - 1;
-          for (int k = k_lo; k <= k_hi; ++k) a |= used_s[k];
+          for (int i = 0; i < kTcM / 32; ++i) any |= pair_s[k * kTcM + lane + 32 * i] >= 0;
+          m |= (any ? 1u : 0u) << k;
         }
-        const unsigned bal = __ballot_sync(0xffffffffu, a != 0);
-        if (a) alist[cnt + __popc(bal & ((1u << lane) - 1u))] = (unsigned short)j;
-        cnt += __popc(bal);
+        m = __reduce_or_sync(0xffffffffu, m);
       }
-      if (lane == 0) n_act_s[b] = cnt;
+      int units_t = chunks, take, n_list = 0;
+      if (tile_mask) {
+        int total = 0;
+        for (int base = 0; base < chunks; base += 32) {
+          const int j = base + lane;
+          total += __popc(__ballot_sync(0xffffffffu, j < chunks && (kmask_s[j] & m) != 0u));
+        }
+        units_t = total > 0 ? total : 1;
+        take = min(units_t - off, u_end - u);
+        int ord = 0;   // position in the tile's list of chunks with a pair: the segment takes [off, off + take)
+        for (int base = 0; base < chunks; base += 32) {
+          const int j = base + lane;
+          const bool a = j < chunks && (kmask_s[j] & m) != 0u;
+          const unsigned bal = __ballot_sync(0xffffffffu, a);
+          const int mine = ord + __popc(bal & ((1u << lane) - 1u));
+          if (a && mine >= off && mine < off + take) alist[mine - off] = (unsigned short)j;
+          ord += __popc(bal);
+        }
+        n_list = total > 0 ? take : 0;
+      } else {
+        take = min(chunks - off, u_end - u);
+        for (int base = off; base < off + take; base += 32) {
+          const int j = base + lane;
+          const bool a = j < off + take && (kmask_s[j] & m) != 0u;
+          const unsigned bal = __ballot_sync(0xffffffffu, a);
+          if (a) alist[n_list + __popc(bal & ((1u << lane) - 1u))] = (unsigned short)j;
+          n_list += __popc(bal);
+        }
+      }
+      if (tile_mask) {
+        tc::cp_async_wait_all();
+        __syncwarp();
+      }
+      if (lane == 0) TC_TRACE(5, seg, 2);
+      if (lane == 0) {
+        int* si = seg_info + b * 8;
+        si[0] = n_list;
+        si[1] = t;
+        si[2] = (off == 0 ? 1 : 0) | (off + take == units_t ? 2 : 0);
+        si[3] = u - off + units_t;
+        si[4] = take;
+      }
       __syncwarp();
-      if (lane == 0) tc::mbar_arrive(&seg_full[b]);
+      if (lane == 0) { tc::mbar_arrive(&seg_full[b]); TC_TRACE(5, seg, 3); }
+      u += take;
+      if (off + take == units_t) { ++t; off = 0; } else { off += take; }
     }
   } else if (warp < kSbpWarpEpi + epi_warps) {
     // ===== epilogue ================================================================================
@@ -631,29 +756,42 @@ spconv_fwd_sbp_kernel(const uint16_t* __restrict__ xs, const uint16_t* __restric
                          (residual == nullptr || ((uintptr_t)residual & 15) == 0);
     const int prow = quarter * 32 + lane;
     const size_t slot = (size_t)kTcM * N;         // floats per partial slot, [16-column step][row][16]
-    SBP_FOR_SEGMENTS {
-      const int b = seg & 1;
-      const uint32_t sph = (uint32_t)(seg >> 1) & 1u;
-      tc::mbar_wait(&seg_full[b], sph);
-      const int n_act = n_act_s[b];
-      __syncwarp();
-      if (lane == 0) tc::mbar_arrive(&seg_empty[b]);
+    const int total_w = total_units;
+    SBP_SEGMENT_LOOP {
+      SBP_SEGMENT_RECORD(tc::mbar_wait(&seg_full[b], sph));
+      if (ew == 0 && lane == 0) TC_TRACE(4, seg, 0);
       tc::mbar_wait(&acc_full[b], sph);
       tc::fence_after_sync();
+      if (ew == 0 && lane == 0) TC_TRACE(4, seg, 1);
       const uint32_t t_addr = tmem_base + (uint32_t)(b * tmem_cols) + ((uint32_t)(quarter * 32) << 16);
-      const bool owner = j0 == 0;
-      const int tile_end = (tile + 1) * chunks;
+      const bool owner = (sflags & 1) != 0;
+      const bool split = owner && (sflags & 2) == 0;   // other CTAs hold the rest of this tile
       int slot_o = tile * kTcM + prow;
       int o = slot_o;
       if (row_perm) o = (slot_o < n_out) ? __ldg(row_perm + slot_o) : n_out;
-      if (owner && j1 < chunks) {
+      // the row-contiguous half of the epilogue: this lane's four rows, and the staging block -- the segment's pair
+      // rows are dead once its accumulator is complete, so the block lives in that buffer (held until the end of
+      // this epilogue: the segment loader refills it only after this warp's seg_empty arrival)
+      int orow[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int sl = tile * kTcM + quarter * 32 + (lane >> 2) + 8 * i;
+        orow[i] = sl < n_out ? (row_perm ? __ldg(row_perm + sl) : sl) : n_out;
+      }
+      const uint32_t stg = tc::smem_u32(smem + pair_off + b * pair_bytes) + (uint32_t)(ew * 2048);
+      // the CTAs after this one whose (non-empty) range starts inside the tile hold its other fragments
+#define SBP_FOR_CONTRIBUTORS                                                                         \
+  for (int cc = cta + 1, cs = 0;                                                                     \
+       cc < G && (cs = (int)((long long)total_w * cc / G)) < tile_end; ++cc)                        \
+    if ((int)((long long)total_w * (cc + 1) / G) > cs)
+      if (split) {
         // wait (once per contributor) before the column loop; the flags are consumed below, after the reads
-        for (int cc = cta + 1; cc < G; ++cc) {
-          if ((int)((long long)total_units * cc / G) >= tile_end) break;
+        SBP_FOR_CONTRIBUTORS {
           if (lane == 0) flag_wait(flags + (size_t)cc * 8 + ew);
         }
         __syncwarp();
       }
+      if (ew == 0 && lane == 0) TC_TRACE(4, seg, 2);
       for (int st = step_lo; st < step_hi; ++st) {
         const int c0 = st * 16;
         uint32_t acc[16];
@@ -679,9 +817,8 @@ spconv_fwd_sbp_kernel(const uint16_t* __restrict__ xs, const uint16_t* __restric
                                                __uint_as_float(acc[e + 2]), __uint_as_float(acc[e + 3])));
           continue;
         }
-        if (j1 < chunks) {
-          for (int cc = cta + 1; cc < G; ++cc) {
-            if ((int)((long long)total_units * cc / G) >= tile_end) break;
+        if (split) {
+          SBP_FOR_CONTRIBUTORS {
             const float4* src = (const float4*)(ws + (size_t)cc * slot + ((size_t)st * kTcM + prow) * 16);
 #pragma unroll
             for (int e = 0; e < 16; e += 4) {
@@ -692,6 +829,51 @@ spconv_fwd_sbp_kernel(const uint16_t* __restrict__ xs, const uint16_t* __restric
               acc[e + 3] = __float_as_uint(__uint_as_float(acc[e + 3]) + pv.w);
             }
           }
+        }
+        if (vec_out) {
+          // lane = row  ->  lane = (row, 16-byte piece) through this warp's 2 KB staging block, so that every global
+          // access of the epilogue is row-contiguous: 8 rows x 64 bytes per instruction instead of 32 rows x 16 bytes
+          // (the r02n timeline: 8-9.5 us of epilogue per 128 x 128 tile, all of it LSU wavefronts of strided accesses)
+#pragma unroll
+          for (int pc = 0; pc < 4; ++pc)
+            tc::st_shared_v4(stg + (uint32_t)(lane * 64) + (uint32_t)((pc ^ ((lane >> 1) & 3)) << 4),
+                             __uint_as_float(acc[4 * pc]), __uint_as_float(acc[4 * pc + 1]),
+                             __uint_as_float(acc[4 * pc + 2]), __uint_as_float(acc[4 * pc + 3]));
+          __syncwarp();
+          const int pc = lane & 3;
+          const int co = c0 + 4 * pc;
+          if (co < cout) {
+            const float4 sc = *(const float4*)(ss + co), sh = *(const float4*)(ss + N + co);
+            float4 rv[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              rv[i] = (residual && orow[i] < n_out) ? __ldg((const float4*)(residual + (size_t)orow[i] * cout + co))
+                                                    : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int r = (lane >> 2) + 8 * i;
+              const float4 v = tc::ld_shared_v4(stg + (uint32_t)(r * 64) + (uint32_t)((pc ^ ((r >> 1) & 3)) << 4));
+              if (orow[i] >= n_out) continue;
+              float y0 = fmaf(v.x, sc.x, sh.x) + rv[i].x, y1 = fmaf(v.y, sc.y, sh.y) + rv[i].y;
+              float y2 = fmaf(v.z, sc.z, sh.z) + rv[i].z, y3 = fmaf(v.w, sc.w, sh.w) + rv[i].w;
+              if (relu) { y0 = fmaxf(y0, 0.f); y1 = fmaxf(y1, 0.f); y2 = fmaxf(y2, 0.f); y3 = fmaxf(y3, 0.f); }
+              if (out) *(float4*)(out + (size_t)orow[i] * cout + co) = make_float4(y0, y1, y2, y3);
+              if (out_s) {
+                uint16_t* srow = out_s + (size_t)orow[i] * (2 * cout_pad) + co;
+                const uint32_t h01 = tc::pack_bf16x2(y0, y1), h23 = tc::pack_bf16x2(y2, y3);
+                const uint32_t l01 = tc::pack_bf16x2(y0 - __uint_as_float(h01 << 16), y1 - __uint_as_float(h01 & 0xFFFF0000u));
+                const uint32_t l23 = tc::pack_bf16x2(y2 - __uint_as_float(h23 << 16), y3 - __uint_as_float(h23 & 0xFFFF0000u));
+                *(uint2*)srow = make_uint2(h01, h23);
+                *(uint2*)(srow + cout_pad) = make_uint2(l01, l23);
+                if (co + 4 == cout && cout_pad > cout) {   // channel padding of the split image stays zero
+                  *(uint2*)(srow + 4) = make_uint2(0u, 0u);
+                  *(uint2*)(srow + cout_pad + 4) = make_uint2(0u, 0u);
+                }
+              }
+            }
+          }
+          __syncwarp();   // the block is rewritten by the next step
+          continue;
         }
         if (o >= n_out) continue;
         float y[16];
@@ -753,26 +935,33 @@ spconv_fwd_sbp_kernel(const uint16_t* __restrict__ xs, const uint16_t* __restric
       // the accumulator is free again; publish / consume the hand-off flags of this warp's share
       tc::fence_before_sync();
       __syncwarp();
-      if (lane == 0) tc::mbar_arrive(&acc_empty[b]);
+      if (lane == 0) {
+        tc::mbar_arrive(&acc_empty[b]);
+        tc::mbar_arrive(&seg_empty[b]);
+      }
+      if (ew == 0 && lane == 0) TC_TRACE(4, seg, 3);
       if (!owner) {
         __threadfence();
         __syncwarp();
         if (lane == 0) tc::st_release_gpu(flags + (size_t)cta * 8 + ew, 1u);
-      } else if (j1 < chunks) {
+      } else if (split) {
         __syncwarp();
         if (lane == 0) {
-          for (int cc = cta + 1; cc < G; ++cc) {
-            if ((int)((long long)total_units * cc / G) >= tile_end) break;
+          SBP_FOR_CONTRIBUTORS {
             tc::st_relaxed_gpu(flags + (size_t)cc * 8 + ew, 0u);   // back to zero for the next launch on this stream
           }
         }
       }
+#undef SBP_FOR_CONTRIBUTORS
     }
   }
-#undef SBP_FOR_SEGMENTS
+#undef SBP_SEGMENT_LOOP
+#undef SBP_SEGMENT_RECORD
 
   tc::fence_before_sync();
   __syncthreads();
+  if (tid == 0) TC_TRACE_HEAD(4, clock64());
+  TC_TRACE_EXIT();
   if (warp == kSbpWarpMma) tc::tmem_dealloc(tmem_base, (uint32_t)(2 * tmem_cols));
 }
 
@@ -823,12 +1012,15 @@ extern "C" MSMD_API int msmd_sb_trace_set(unsigned long long* buf) { return tc_t
 #endif
 
 // ---- persistent variant: schedule switch + the per-stream hand-off workspace -------------------------------
-static int g_sb_variant = 0;   // 0 = default (persistent) | 1 = one tile per CTA (spconv_fwd_sb_kernel) | 2 = persistent
+// 0 = default (persistent, work shares from the rulebooks' tile masks) | 1 = one tile per CTA (spconv_fwd_sb_kernel) |
+// 2 = persistent with nominal shares (callers that keep rulebooks do not build tile masks)
+static int g_sb_variant = 0;
 extern "C" MSMD_API int msmd_spconv_sb_set_variant(int variant) {
-  MSMD_REQUIRE(variant >= 0 && variant <= 2, "spconv_sb_set_variant: 0 (default), 1 (tile per CTA) or 2 (persistent)");
+  MSMD_REQUIRE(variant >= 0 && variant <= 2, "spconv_sb_set_variant: 0 (default), 1 (tile per CTA) or 2 (persistent, no masks)");
   g_sb_variant = variant;
   return MSMD_OK;
 }
+extern "C" MSMD_API int msmd_spconv_sb_uses_tile_masks(void) { return g_sb_variant == 0 ? 1 : 0; }
 
 namespace {
 // Launches on one stream are serial, so one slot set per (device, stream) is enough; the flags are zero between
@@ -912,7 +1104,8 @@ extern "C" MSMD_API int msmd_spconv_sb_pack_weight(const float* weight_krsc, int
 // Launch of the persistent kernel: occupancy (1 or 2 CTAs per SM), grid = the SM slots (never more CTAs than
 // units of work), equal unit ranges.
 static int sbp_launch(const SbGeom& g, const void* features_split, const void* packed_sb, const int* pair_fwd,
-                      const int* row_perm, int n_out, int cout, int kvol, const float* scale, const float* shift,
+                      const int* row_perm, const uint32_t* tile_mask, int n_out, int cout, int kvol, const float* scale,
+                      const float* shift,
                       const float* residual, int relu, float* out, void* out_split, cudaStream_t stream) {
   const int tiles = ceil_div(n_out, kTcM);
   const long long units = (long long)tiles * g.chunks;
@@ -922,12 +1115,13 @@ static int sbp_launch(const SbGeom& g, const void* features_split, const void* p
   while (tmem_cols < (cat ? 2 * g.N : g.N)) tmem_cols <<= 1;
   // two CTAs per SM when each still gets >= 3 stages in half of the shared memory and half of tensor memory, and
   // there is more than one SM's worth of work per slot; the tuning switch [0] forces either
-  const SbpLayout half = sbp_layout(g.N, kvol, g.chunks, 112 * 1024);
+  const SbpLayout half = sbp_layout(g.N, kvol, g.chunks, 112 * 1024, 4);
   bool two = half.stages >= 3 && 2 * tmem_cols <= 256 && units >= 4ll * 2 * kNumSMs;
   if (g_tc_tune[0] == 1) two = false;
   if (g_tc_tune[0] == 2) two = half.stages >= 2 && 2 * tmem_cols <= 256;
-  const SbpLayout L = two ? half : sbp_layout(g.N, kvol, g.chunks, 227 * 1024);
+  const SbpLayout L = two ? half : sbp_layout(g.N, kvol, g.chunks, 227 * 1024, 8);
   MSMD_REQUIRE(L.stages >= 2, "spconv_fwd_sb: tile does not fit in shared memory");
+  MSMD_REQUIRE(tiles <= L.stages * L.stage_bytes / 4, "spconv_fwd_sb: too many tiles for the in-kernel prefix");
   const int epi_warps = two ? 4 : 8;
   const int threads = (kSbpWarpEpi + epi_warps) * 32;
   static bool attr_set = false;
@@ -958,10 +1152,10 @@ static int sbp_launch(const SbGeom& g, const void* features_split, const void* p
                  "spconv_fwd_sb: reciprocal of cin_pad %d is inexact at %u", g.cin_pad, kk);
   }
 #define MSMD_SBP_ARGS                                                                                             \
-  (const uint16_t*)features_split, (const uint16_t*)packed_sb, pair_fwd, row_perm, n_out, g.cin_pad, cin_magic, cout, \
-      round_up(cout, 8), g.N, kvol, g.chunks, L.stages, L.stage_bytes, L.pair_off, L.pair_bytes, L.act_off,           \
-      L.act_bytes, L.bar_off, tmem_cols, scale, shift, residual, relu, out, (uint16_t*)out_split, cat, (int)units,    \
-      w.ws, w.flags
+  (const uint16_t*)features_split, (const uint16_t*)packed_sb, pair_fwd, row_perm, tile_mask, n_out, tiles,         \
+      g.cin_pad, cin_magic, cout, round_up(cout, 8), g.N, kvol, g.chunks, L.stages, L.stage_bytes, L.pair_off,       \
+      L.pair_bytes, L.act_off, L.act_bytes, L.kmask_off, L.bar_off, tmem_cols, scale, shift, residual, relu, out,    \
+      (uint16_t*)out_split, cat, w.ws, w.flags
   if (two) spconv_fwd_sbp_kernel<4><<<grid, threads, L.total, stream>>>(MSMD_SBP_ARGS);
   else spconv_fwd_sbp_kernel<8><<<grid, threads, L.total, stream>>>(MSMD_SBP_ARGS);
 #undef MSMD_SBP_ARGS
@@ -986,8 +1180,8 @@ extern "C" MSMD_API int msmd_spconv_fwd_sb(const void* features_split, int n_in,
                "spconv_fwd_sb: split images and packed weights must be 16-byte aligned");
   const int tiles = ceil_div(n_out, kTcM);
   if (g_sb_variant != 1)
-    return sbp_launch(g, features_split, packed_sb, pair_fwd, nullptr, n_out, cout, kvol, scale, shift, residual, relu,
-                      out, out_split, stream);
+    return sbp_launch(g, features_split, packed_sb, pair_fwd, nullptr, nullptr, n_out, cout, kvol, scale, shift,
+                      residual, relu, out, out_split, stream);
   const SbLayout L = sb_layout(g.N, kvol, g.chunks, tiles);
   MSMD_REQUIRE(L.stages >= 2, "spconv_fwd_sb: tile does not fit in shared memory");
   static bool attr_set = false;
@@ -1012,4 +1206,55 @@ extern "C" MSMD_API int msmd_spconv_fwd_sb(const void* features_split, int n_in,
             (uint16_t*)out_split, cat);
   MSMD_LAUNCH_OK();
   return MSMD_OK;
+}
+
+// ---- tile masks + the extended entry (row permutation of mask-sorted tiles, weighted work shares) ----------------
+namespace msmd {
+// bit k of tile_mask[t]: some row of tile t has a pair at kernel offset k
+__global__ void __launch_bounds__(kTcM)
+tile_mask_kernel(const int* __restrict__ pair, int kvol, int n_out, uint32_t* __restrict__ tile_mask) {
+  __shared__ uint32_t warp_or[kTcM / 32];
+  const int o = blockIdx.x * kTcM + threadIdx.x;
+  uint32_t m = 0u;
+  if (o < n_out)
+    for (int k = 0; k < kvol; ++k) m |= (__ldg(pair + (size_t)k * n_out + o) >= 0 ? 1u : 0u) << k;
+  m = __reduce_or_sync(0xffffffffu, m);
+  if ((threadIdx.x & 31) == 0) warp_or[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) tile_mask[blockIdx.x] = warp_or[0] | warp_or[1] | warp_or[2] | warp_or[3];
+}
+}  // namespace msmd
+
+extern "C" MSMD_API int msmd_rulebook_tile_masks(const int* pair_fwd, int kvol, int n_out, unsigned* tile_mask,
+                                                 msmd_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  MSMD_REQUIRE(kvol >= 1 && kvol <= 32 && n_out >= 0, "rulebook_tile_masks: bad sizes");
+  if (n_out == 0) return MSMD_OK;
+  MSMD_REQUIRE(pair_fwd && tile_mask, "rulebook_tile_masks: null pointer");
+  tile_mask_kernel<<<ceil_div(n_out, kTcM), kTcM, 0, stream>>>(pair_fwd, kvol, n_out, tile_mask);
+  MSMD_LAUNCH_OK();
+  return MSMD_OK;
+}
+
+extern "C" MSMD_API int msmd_spconv_fwd_sb_ex(const void* features_split, int n_in, const void* packed_sb,
+                                              const int* pair_fwd, const int* row_perm, const unsigned* tile_mask,
+                                              int n_out, int cin, int cout, int kvol, const float* scale,
+                                              const float* shift, const float* residual, int relu, float* out,
+                                              void* out_split, msmd_stream_t stream_) {
+  if (!row_perm && (!tile_mask || g_sb_variant == 1))
+    return msmd_spconv_fwd_sb(features_split, n_in, packed_sb, pair_fwd, n_out, cin, cout, kvol, scale, shift,
+                              residual, relu, out, out_split, stream_);
+  cudaStream_t stream = (cudaStream_t)stream_;
+  SbGeom g;
+  MSMD_REQUIRE(sb_geom(cout, kvol, cin, g), "spconv_fwd_sb: unsupported shape (cout<=256, kvol<=32)");
+  MSMD_REQUIRE(n_in >= 0 && n_out >= 0, "spconv_fwd_sb: bad sizes");
+  MSMD_REQUIRE((scale == nullptr) == (shift == nullptr), "spconv_fwd_sb: scale/shift must come together");
+  if (n_out == 0) return MSMD_OK;
+  MSMD_REQUIRE(n_in > 0, "spconv_fwd_sb: output rows without input rows");
+  MSMD_REQUIRE(features_split && packed_sb && pair_fwd && (out || out_split), "spconv_fwd_sb: null pointer");
+  MSMD_REQUIRE(((uintptr_t)features_split & 15) == 0 && ((uintptr_t)packed_sb & 15) == 0 &&
+                   ((uintptr_t)out_split & 15) == 0,
+               "spconv_fwd_sb: split images and packed weights must be 16-byte aligned");
+  return sbp_launch(g, features_split, packed_sb, pair_fwd, row_perm, tile_mask, n_out, cout, kvol, scale, shift,
+                    residual, relu, out, out_split, stream);
 }

@@ -36,7 +36,7 @@ class SparseNetPlan:
             raise Unsupported(type(conv).__name__)
         scale = shift = None
         if bn is not None:
-            if not _bn_foldable(bn):
+            if not _bn_foldable(bn, inference=True):
                 raise Unsupported('BatchNorm1d is not in eval mode with running statistics')
             scale, shift = _bn_scale_shift(bn)
         if conv.bias is not None:

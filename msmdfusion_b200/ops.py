@@ -314,10 +314,27 @@ def _remember_split(t, xs):
         pass
 
 
-def spconv_fwd_sb(features, tcw, pair_fwd, scale=None, shift=None, residual=None, relu=False, want_split=True):
-    """bf16x3 sparse convolution through the split-bf16 operand cache (``msmd_spconv_fwd_sb``): the gather reads
+def rulebook_tile_masks(pair_fwd):
+    """``msmd_rulebook_tile_masks``: one uint32 per 128-row tile of the pair table, bit k = the tile has a pair at
+    kernel offset k.  Built once per table and kept on the tensor (rulebooks are never written in place)."""
+    cached = pair_fwd.__dict__.get('_msmd_tile_mask')
+    if cached is not None:
+        return cached
+    kvol, n_out = pair_fwd.shape
+    tm = torch.empty(((n_out + 127) // 128,), dtype=torch.int32, device=pair_fwd.device)
+    if n_out:
+        with _Timed('rulebook_tile_masks', n=n_out, kvol=kvol):
+            check(lib().msmd_rulebook_tile_masks(ptr(pair_fwd), kvol, n_out, ptr(tm), stream(pair_fwd.device)),
+                  'msmd_rulebook_tile_masks')
+    pair_fwd._msmd_tile_mask = tm
+    return tm
+
+
+def spconv_fwd_sb(features, tcw, pair_fwd, scale=None, shift=None, residual=None, relu=False, want_split=True,
+                  row_perm=None):
+    """bf16x3 sparse convolution through the split-bf16 operand cache (``msmd_spconv_fwd_sb_ex``): the gather reads
     the split image of ``features``; the epilogue writes the fp32 result and (``want_split``) its split image, which
-    is attached to the returned tensor for the next convolution."""
+    is attached to the returned tensor for the next convolution.  ``row_perm``: the table is a mask-sorted one."""
     assert tcw.mode == 4 and features.shape[1] == tcw.cin, 'channel size mismatch'
     assert pair_fwd.shape[0] == tcw.kvol and pair_fwd.dtype == torch.int32
     n_out = pair_fwd.shape[1]
@@ -328,14 +345,17 @@ def spconv_fwd_sb(features, tcw, pair_fwd, scale=None, shift=None, residual=None
     if residual is not None:
         residual = residual.contiguous()
         assert residual.shape == out.shape
-    pair_fwd = pair_fwd.contiguous()
+    if not pair_fwd.is_contiguous():
+        pair_fwd = pair_fwd.contiguous()
     xs = split_bf16(features)
     out_s = torch.empty((n_out, lib().msmd_split_width(tcw.cout)), dtype=torch.int16, device=dev) \
         if want_split else None
+    tm = rulebook_tile_masks(pair_fwd) if lib().msmd_spconv_sb_uses_tile_masks() else None
     def launch():
-        check(lib().msmd_spconv_fwd_sb(ptr(xs), features.shape[0], ptr(tcw.packed), ptr(pair_fwd), n_out, tcw.cin,
-                                       tcw.cout, tcw.kvol, ptr(scale), ptr(shift), ptr(residual), int(bool(relu)),
-                                       ptr(out), ptr(out_s), stream(dev)), 'msmd_spconv_fwd_sb')
+        check(lib().msmd_spconv_fwd_sb_ex(ptr(xs), features.shape[0], ptr(tcw.packed), ptr(pair_fwd), ptr(row_perm),
+                                          ptr(tm), n_out, tcw.cin, tcw.cout, tcw.kvol, ptr(scale), ptr(shift),
+                                          ptr(residual), int(bool(relu)), ptr(out), ptr(out_s), stream(dev)),
+              'msmd_spconv_fwd_sb_ex')
     with _Timed('spconv_fwd', replay=launch, n_in=features.shape[0], n_out=n_out, cin=tcw.cin, cout=tcw.cout,
                 kvol=tcw.kvol, residual=residual is not None, pair=pair_fwd, path='tc', tc_mode=tcw.mode):
         launch()
@@ -349,9 +369,8 @@ def spconv_fwd_tc(features, tcw, pair_fwd, scale=None, shift=None, residual=None
     accumulate in TMEM).  With
     ``row_perm`` the table is a mask-sorted one (``rulebook_mask_sort``); the output keeps the original
     row order."""
-    if tcw.mode == 4:   # split-bf16 operand cache; a mask-sorted table is used unsorted (row order is the caller's)
-        assert row_perm is None, 'the split-operand path takes the plain pair table'
-        return spconv_fwd_sb(features, tcw, pair_fwd, scale, shift, residual, relu)
+    if tcw.mode == 4:   # split-bf16 operand cache
+        return spconv_fwd_sb(features, tcw, pair_fwd, scale, shift, residual, relu, row_perm=row_perm)
     features = features.contiguous()
     if features.dtype != torch.float32:
         features = features.float()

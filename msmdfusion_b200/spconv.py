@@ -281,9 +281,17 @@ def _bn_scale_shift_compute(bn):
     return scale, shift
 
 
-def _bn_foldable(m):
-    return isinstance(m, nn.BatchNorm1d) and not m.training and m.track_running_stats and \
-        m.running_var is not None
+def _bn_foldable(m, inference=False):
+    """Eval-mode BatchNorm1d whose y = x*scale + shift can ride in a conv epilogue.  Not while autograd would need a
+    gradient for its affine parameters (frozen statistics, trainable weight / bias): the fold detaches them, so
+    such a BN runs as the torch op.  ``inference``: the caller only ever runs without autograd (the executor plans)."""
+    if not (isinstance(m, nn.BatchNorm1d) and not m.training and m.track_running_stats and
+            m.running_var is not None):
+        return False
+    if not inference and torch.is_grad_enabled() and \
+            any(p is not None and p.requires_grad for p in (m.weight, m.bias)):
+        return False
+    return True
 
 
 class SparseSequential(SparseModule):
@@ -452,7 +460,8 @@ class SparseConvolution(SparseModule):
             return t
         iset = _iset_of(input)
         indice_dict = input.indice_dict.copy()
-        if self.bias is not None:
+        bias_grad = self.bias is not None and with_grad and self.bias.requires_grad
+        if self.bias is not None and not bias_grad:
             # y = (conv + b)*scale + shift  ==  conv*scale + (b*scale + shift)
             b = self.bias.detach().float()
             if scale is None:
@@ -484,7 +493,11 @@ class SparseConvolution(SparseModule):
                     self.kernel_size, self.stride, self.padding, self.dilation)
         if with_grad:
             rb = iset.rulebook_record(pair, self.subm, self.kernel_size, self.dilation, CONV_PATH)
+            if self.subm:   # the data gradient reuses pair_fwd with the offsets mirrored: k <-> K-1-k needs odd sizes
+                assert all(k % 2 == 1 for k in self.kernel_size), 'SubM backward: odd kernel sizes only'
             out_features = _ag.SparseConvFunction.apply(features, self.weight, self.packed_weight(), rb)
+            if bias_grad:   # a trainable bias stays a torch op, so that autograd reaches it
+                out_features = out_features + self.bias
             if scale is not None:
                 out_features = out_features * scale + shift
             if residual is not None:
@@ -494,7 +507,7 @@ class SparseConvolution(SparseModule):
         else:
             packed = self.packed_weight()
             if MASK_SORT and self.subm and pair.shape[0] == 27 and isinstance(packed, ops.TcWeight) \
-                    and packed.mode != 4 and pair.shape[1] > 0:
+                    and pair.shape[1] > 0:
                 row_perm, pair_sorted = iset.subm_pairs_sorted(self.kernel_size, self.dilation)
                 out_features = ops.spconv_fwd_tc(features, packed, pair_sorted, scale, shift, residual, relu,
                                                  row_perm=row_perm)

@@ -218,7 +218,7 @@ class _EmuLib:
     def __init__(self, cabi):
         self._cabi, self._cache = cabi, {}
 
-    TC_UNIT = ('msmd_spconv_tc_', 'msmd_spconv_fwd_tc', 'msmd_spconv_tc16_', 'msmd_spconv_bwd_weight_tc', 'msmd_spconv_sb', 'msmd_spconv_fwd_sb', 'msmd_split_')
+    TC_UNIT = ('msmd_spconv_tc_', 'msmd_spconv_fwd_tc', 'msmd_spconv_tc16_', 'msmd_spconv_bwd_weight_tc', 'msmd_spconv_sb', 'msmd_spconv_fwd_sb', 'msmd_split_', 'msmd_rulebook_tile_masks')
 
     def __getattr__(self, name):
         fn = self._cache.get(name)
@@ -332,6 +332,30 @@ def test_conv_autograd_function_on_emulated_kernels(ops_on_emulator, monkeypatch
         assert rel(out.features.detach().numpy(), cpu.spconv_fwd(feat, w, pair)) < 1e-5
         assert rel(f.grad.numpy(), ri) < 1e-5
         assert rel(conv.weight.grad.numpy(), rw) < 1e-5
+    # a trainable bias and a frozen-statistics BatchNorm with trainable affine stay torch ops under autograd, so
+    # they receive their gradients (they are folded into the conv epilogue only when nothing asks for one)
+    torch.manual_seed(0)
+    block = spconv.SparseSequential(spconv.SubMConv3d(cin, cout, 3, padding=1, bias=True),
+                                    torch.nn.BatchNorm1d(cout), torch.nn.ReLU())
+    block[1].running_mean.normal_()
+    block[1].running_var.uniform_(0.5, 2.0)
+    block.eval()
+    f = torch.from_numpy(feat).clone()
+    out = block(spconv.SparseConvTensor(f, torch.from_numpy(idx), shape, batch))
+    g = torch.randn(out.features.shape, generator=torch.Generator().manual_seed(2))
+    (out.features * g).sum().backward()
+    conv, bn = block[0], block[1]
+    pair = cpu.subm_rulebook(idx, shape, 3, 1)
+    pre = torch.from_numpy(cpu.spconv_fwd(feat, conv.weight.detach().numpy(), pair)) + conv.bias.detach()
+    inv = torch.rsqrt(bn.running_var + bn.eps)
+    xhat = (pre - bn.running_mean) * inv
+    gate = ((xhat * bn.weight.detach() + bn.bias.detach()) > 0).float() * g
+    assert rel(bn.bias.grad.numpy(), gate.sum(0).numpy()) < 1e-5
+    assert rel(bn.weight.grad.numpy(), (gate * xhat).sum(0).numpy()) < 1e-5
+    assert rel(conv.bias.grad.numpy(), (gate * bn.weight.detach() * inv).sum(0).numpy()) < 1e-5
+    with torch.no_grad():   # and the fused inference form of the same block agrees with it
+        fused = block(spconv.SparseConvTensor(f, torch.from_numpy(idx), shape, batch))
+    assert rel(fused.features.numpy(), out.features.detach().numpy()) < 1e-5
 
 
 # --------------------------------------------------------------------------------------
@@ -1096,7 +1120,8 @@ def test_split_bf16_image_on_emulator():
                                         (5, 16, 200),     # input channels padded 5 -> 8: eight offsets per chunk
                                         (24, 144, 150),   # chunk boundaries inside a kernel offset, padded N, 3-MMA mode
                                         (64, 128, 140),   # one offset per chunk, concatenated-B at 2N = 256
-                                        (80, 96, 260)])   # fusion-encoder widths, ragged last tile, several tiles
+                                        (80, 96, 260),    # fusion-encoder widths, ragged last tile, several tiles
+                                        (16, 20, 150)])   # Cout % 8 == 4: zero padding of the split image from the row-contiguous epilogue
 def test_sb_kernel_on_emulator(cin, cout, n, sb_schedule):
     """csrc/spconv_sb.cu on the tcgen05 model with late-as-possible asynchronous copies: the result equals the
     bf16x3 arithmetic (within 2e-5 of the fp32 oracle), the split image the epilogue writes IS the split of the fp32
@@ -1148,6 +1173,70 @@ def test_sb_kernel_chain_strided_rulebook_and_empty_tiles_on_emulator(sb_schedul
     shift = rng.standard_normal(32).astype(np.float32)
     got, _ = sb_fwd(feat, w1, empty, one, shift)
     assert rel(got, cpu.spconv_fwd(feat, w1, empty) + shift) < 2e-5
+
+
+def sb_fwd_ex(feat, w, pair, row_perm=None, masks=True, scale=None, shift=None, residual=None, relu=0):
+    """msmd_spconv_fwd_sb_ex: the persistent kernel with tile masks (weighted work shares, skipped chunks) and / or a
+    mask-sorted pair table."""
+    L = tc_emu()
+    cout, cin = w.shape[0], w.shape[-1]
+    kvol, n_out = pair.shape
+    packed = np.full(L.emu_msmd_spconv_sb_packed_bytes(cout, kvol, cin) // 2, 0x7FC0, np.uint16)
+    assert L.emu_msmd_spconv_sb_pack_weight(P(w), cout, kvol, cin, P(packed), None) == 0, L.emu_last_error()
+    xs = sb_split(feat)
+    tm = None
+    if masks:
+        tm = np.full((n_out + 127) // 128, 0xFFFFFFFF, np.uint32)
+        assert L.emu_msmd_rulebook_tile_masks(P(pair), kvol, n_out, P(tm), None) == 0, L.emu_last_error()
+        used = np.concatenate([pair >= 0, np.zeros((kvol, len(tm) * 128 - n_out), bool)], 1).reshape(kvol, len(tm), 128).any(2)
+        assert np.array_equal(tm, (used.astype(np.uint64) << np.arange(kvol, dtype=np.uint64)[:, None]).sum(0).astype(np.uint32))
+    out = np.full((n_out, cout), np.nan, np.float32)
+    out_s = np.full((n_out, L.emu_msmd_split_width(cout)), 0x7FC0, np.uint16)
+    st = L.emu_msmd_spconv_fwd_sb_ex(P(xs), feat.shape[0], P(packed), P(pair), P(row_perm), P(tm), n_out, cin, cout, kvol,
+                                     P(scale), P(shift), P(residual), relu, P(out), P(out_s), None)
+    assert st == 0, L.emu_last_error()
+    return out, out_s
+
+
+@pytest.mark.parametrize('cin,cout', [(16, 32), (64, 64), (80, 96)])
+def test_sb_persistent_kernel_with_tile_masks_and_mask_sorted_rows_on_emulator(cin, cout):
+    """The persistent schedule with its two side tables, on a LiDAR-like index set (many tiles miss most kernel
+    offsets): tile masks only (work shares counted in chunks that have a pair, the others skipped), and tile masks
+    of a mask-sorted table with the row permutation; a table with tiles that have no pair at all."""
+    from msmdfusion_b200 import synthetic
+    pts = synthetic.lidar_scene(seed=4, sweeps=1)[:2400]
+    _, c, _ = cpu.hard_voxelize(pts, synthetic.VOXEL_SIZE, synthetic.POINT_CLOUD_RANGE, 10, 160000)
+    idx = np.concatenate([np.zeros((c.shape[0], 1), np.int32), c], 1)[:900]
+    n = idx.shape[0]
+    rng = np.random.default_rng(2)
+    feat = rng.standard_normal((n, cin)).astype(np.float32)
+    w = (rng.standard_normal((cout, 3, 3, 3, cin)) * 0.2).astype(np.float32)
+    pair = cpu.subm_rulebook(idx, [41, 1440, 1440], 3, 1)
+    scale = rng.uniform(0.5, 1.5, cout).astype(np.float32)
+    shift = rng.standard_normal(cout).astype(np.float32)
+    res = rng.standard_normal((n, cout)).astype(np.float32)
+    want = np.maximum(cpu.spconv_fwd(feat, w, pair) * scale + shift + res, 0)
+    plain, plain_s = sb_fwd(feat, w, pair, scale, shift, res, 1)
+    assert rel(plain, want) < 2e-5
+    got, got_s = sb_fwd_ex(feat, w, pair, None, True, scale, shift, res, 1)
+    assert rel(got, want) < 2e-5 and rel(got, plain) < 2e-6
+    assert np.array_equal(got_s, sb_split(got))
+    E = emu()
+    E.emu_msmd_rulebook_mask_sort_workspace.restype = ctypes.c_size_t
+    need = E.emu_msmd_rulebook_mask_sort_workspace(n)
+    ws = np.zeros(need, np.uint8)
+    perm = np.full(n, -1, np.int32)
+    pair_sorted = np.full_like(pair, -9)
+    ok(E.emu_msmd_rulebook_mask_sort(P(pair), 27, n, P(perm), P(pair_sorted), P(ws), ctypes.c_size_t(need), None))
+    for masks in (True, False):
+        got, got_s = sb_fwd_ex(feat, w, pair_sorted, perm, masks, scale, shift, res, 1)
+        assert rel(got, want) < 2e-5 and rel(got, plain) < 2e-6
+        assert np.array_equal(got_s, sb_split(got))
+    empty = np.full((27, 700), -1, np.int32)     # tiles 0, 2, 3 and 5 have no pair: one unit each, epilogue only
+    empty[13, 130] = 7
+    empty[2, 600:640] = np.arange(40)
+    got, _ = sb_fwd_ex(feat, w, empty, None, True, scale, shift)
+    assert rel(got, cpu.spconv_fwd(feat, w, empty) * scale + shift) < 2e-5
 
 
 # --------------------------------------------------------------------------------------

@@ -41,6 +41,8 @@ static inline float4 make_float4(float x, float y, float z, float w) { return fl
 static inline uint32_t __umulhi(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
 static inline int4 make_int4(int x, int y, int z, int w) { return int4{x, y, z, w}; }
 struct alignas(16) uint4 { uint32_t x, y, z, w; };
+struct alignas(8) uint2 { uint32_t x, y; };
+static inline uint2 make_uint2(uint32_t x, uint32_t y) { return uint2{x, y}; }
 static inline uint4 make_uint4(uint32_t x, uint32_t y, uint32_t z, uint32_t w) { return uint4{x, y, z, w}; }
 
 typedef void* cudaStream_t;
@@ -306,6 +308,10 @@ static inline unsigned __match_any_sync(unsigned, T v) {
   for (int l = 0; l < box.nlanes; ++l) m |= ((!box.lanes[l].done && box.slot[l] == raw) ? 1u : 0u) << l;
   ::emu::warp_barrier_wait();
   return m;
+}
+static inline unsigned __reduce_or_sync(unsigned, unsigned v) {
+  for (int d = 16; d > 0; d >>= 1) v |= __shfl_xor_sync(0xffffffffu, v, d);
+  return v;
 }
 static inline unsigned __ballot_sync(unsigned, int pred) {
   unsigned m = __match_any_sync(0xffffffffu, pred ? 1 : 0);

@@ -67,6 +67,7 @@ def main():
     seen, report = set(), []
     tot = dict(tf32x3=0.0, bf16x3=0.0, sb=0.0)
     tot['sb_tile'] = 0.0
+    tot_ms = {}
     print('%-30s %9s %9s | %9s | %9s %9s %9s %9s | %7s %9s %9s' % ('layer', 'tf32x3', 'bf16x3', 'sb tile', 'sbp auto',
                                                                     'sbp occ1', 'sbp occ2', 'sbp st=2', 'split', 'err',
                                                                     'vs tile'))
@@ -109,17 +110,32 @@ def main():
                 row[name] = float('nan')
                 row[name + '_error'] = str(e)[:100]
             tune()
+        row['sb_msort'] = float('nan')
+        row['msort_err'] = float('nan')
+        if r['kvol'] == 27 and r['n_in'] == r['n_out']:   # SubM 3x3x3: mask-sorted tiles (row permutation in the epilogue)
+            row_perm, pair_sorted = ops.rulebook_mask_sort(pair)
+            o2 = ops.spconv_fwd_sb(feat, packed['bf16x3c'], pair_sorted, sc, sh, res, True, row_perm=row_perm)
+            row['msort_err'] = float((o2 - ref).abs().max()) / scale
+            row['sb_msort'] = time_call(lambda: ops.spconv_fwd_sb(feat, packed['bf16x3c'], pair_sorted, sc, sh, res, True,
+                                                                  row_perm=row_perm))
+            row['msort_build'] = time_call(lambda: ops.rulebook_mask_sort(pair))
+        pc = pair.clone()
+        row['tile_masks_build'] = time_call(lambda: (pc.__dict__.pop('_msmd_tile_mask', None), ops.rulebook_tile_masks(pc)))
         f2 = feat.clone()
         row['split'] = time_call(lambda: (f2.__dict__.pop('_msmd_split', None), ops.split_bf16(f2)))
         for k in tot:
             tot[k] += mult * row[k]
+        tot_ms['sb_msort'] = tot_ms.get('sb_msort', 0.0) + mult * (row['sb_msort'] if row['sb_msort'] == row['sb_msort'] else row['sb'])
+        print('%-30s mask-sorted %8.1fu (err %.2e; sort %.1fu per rulebook), tile masks %.1fu per rulebook' % (
+            '', row['sb_msort'], row['msort_err'], row.get('msort_build', float('nan')), row['tile_masks_build']))
         print('%-30s %8.1fu %8.1fu | %8.1fu | %8.1fu %8.1fu %8.1fu %8.1fu | %6.1fu %9.2e %9.2e %s %s x%d' % (
             row['layer'], row['tf32x3'], row['bf16x3'], row['sb_tile'], row['sb'], row['sb_occ1'], row['sb_occ2'],
             row['sb_st2'], row['split'], row['err'], row['vs_tile'],
             'img-ok' if row['split_image_ok'] else 'IMG-MISMATCH', 'det' if row['deterministic'] else 'NONDET', mult))
         report.append(row)
     print('sum over the %d conv launches of one scene: tf32x3 %.1f us, bf16x3 %.1f us, bf16x3c tile-per-CTA %.1f us, '
-          'bf16x3c persistent %.1f us' % (len(recs), tot['tf32x3'], tot['bf16x3'], tot['sb_tile'], tot['sb']))
+          'bf16x3c persistent %.1f us, persistent + mask-sorted SubM layers %.1f us' % (
+              len(recs), tot['tf32x3'], tot['bf16x3'], tot['sb_tile'], tot['sb'], tot_ms.get('sb_msort', float('nan'))))
     if args.json:
         os.makedirs(os.path.dirname(os.path.abspath(args.json)), exist_ok=True)
         json.dump(dict(layers=report, totals_us=tot, launches=len(recs)), open(args.json, 'w'), indent=1)

@@ -27,7 +27,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-HEAD, ROLES, ITS, PHASES, CTAS = 16, 4, 128, 4, 16
+HEAD, ROLES, ITS, PHASES, CTAS = 16, 6, 128, 4, 16
 
 
 def summarize(rec, mhz):
@@ -64,6 +64,19 @@ def summarize(rec, mhz):
             if b[:, 1].all():
                 d['b_wait'] = float(np.mean(b[1:, 1] - b[1:, 0]) / period)
                 d['b_lead_us'] = float(np.mean(mma[1:, 0] - b[1:, 1]) * cyc)  # copy issued -> MMA starts waiting
+            d['mma_gaps_us'] = [round(float(x) * cyc, 3) for x in np.diff(mma[:, 2])]
+        # persistent kernel: one record per segment from epilogue warp 0 (role 4) and the segment loader (role 5)
+        nseg = int(np.count_nonzero(ev[4, :, 3]))
+        if nseg:
+            e, sl = ev[4, :nseg], ev[5, :nseg]
+            t0 = float(r[0])
+            d['segments'] = [dict(acc_wait_from=round((e[i, 0] - t0) * cyc, 2), acc_full=round((e[i, 1] - t0) * cyc, 2),
+                                  flags_seen=round((e[i, 2] - t0) * cyc, 2), rows_written=round((e[i, 3] - t0) * cyc, 2),
+                                  loader_wait_from=round((sl[i, 0] - t0) * cyc, 2), loader_free=round((sl[i, 1] - t0) * cyc, 2),
+                                  pairs_landed=round((sl[i, 2] - t0) * cyc, 2), published=round((sl[i, 3] - t0) * cyc, 2))
+                             for i in range(nseg)]
+            d['first_mma_us'] = round((ev[3, 0, 1] - t0) * cyc, 2) if n else None
+            d['last_mma_us'] = round((ev[3, n - 1, 2] - t0) * cyc, 2) if n else None
         out.append(d)
     return out
 
@@ -79,6 +92,9 @@ def main():
     ap.add_argument('--precision', default='tf32x3', choices=['tf32x3', 'bf16x3', 'bf16x3c', 'bf16'])
     ap.add_argument('--mask-sort', action='store_true')
     ap.add_argument('--json', default=None)
+    ap.add_argument('--sb-variant', type=int, default=0, help='bf16x3c: 1 = tile per CTA, 2 / 0 = persistent')
+    ap.add_argument('--only', default=None, help='comma list of layer names to trace, e.g. "128->128 k27"')
+    ap.add_argument('--dump-cta', action='store_true', help='print the per-segment timeline of the first traced CTAs')
     args = ap.parse_args()
 
     # the library path is read when msmdfusion_b200._cabi is imported, i.e. by ANY import of the package: load the
@@ -97,6 +113,8 @@ def main():
     for name in ('msmd_tc_trace_set', 'msmd_tc16_trace_set', 'msmd_sb_trace_set'):
         getattr(L, name).restype = ctypes.c_int
         getattr(L, name).argtypes = [ctypes.c_void_p]
+    L.msmd_spconv_sb_set_variant.argtypes = [ctypes.c_int]
+    assert L.msmd_spconv_sb_set_variant(args.sb_variant) == 0
     L.msmd_tc_trace_record_words.restype = ctypes.c_int
     words = L.msmd_tc_trace_record_words()
     assert words == HEAD + ROLES * ITS * PHASES
@@ -124,6 +142,8 @@ def main():
         if key in seen:
             continue
         seen.add(key)
+        if args.only and ('%d->%d k%d' % (r['cin'], r['cout'], r['kvol'])) not in args.only.split(','):
+            continue
         pair = r['pair']
         feat = torch.randn(r['n_in'], r['cin'], device=dev)
         w = torch.randn(r['cout'], r['kvol'], 1, 1, r['cin'], device=dev) * 0.05
@@ -152,6 +172,18 @@ def main():
             100 * mean_of(rows, 'mma_wait_weights'), 100 * mean_of(rows, 'prod0_wait'), 100 * mean_of(rows, 'prod0_fill'),
             100 * mean_of(rows, 'b_wait'), mean_of(rows, 'b_lead_us'), mean_of(rows, 'setup_us'),
             mean_of(rows, 'main_us'), mean_of(rows, 'epilogue_us'), mean_of(rows, 'total_us')))
+        if args.dump_cta:
+            for row in rows[:3] + rows[-1:]:
+                print('   cta %d sm %d: chunks %d, setup %.1f us, first mma %s, last mma %s, total %.1f us' % (
+                    row['cta'], row['sm'], row['n_act'], row['setup_us'], row.get('first_mma_us'), row.get('last_mma_us'),
+                    row['total_us']))
+                for i, sg in enumerate(row.get('segments', [])):
+                    print('      seg %d: loader wait %.1f free %.1f landed %.1f published %.1f | acc wait from %.1f full %.1f '
+                          'flags %.1f written %.1f' % (i, sg['loader_wait_from'], sg['loader_free'], sg['pairs_landed'],
+                                                       sg['published'], sg['acc_wait_from'], sg['acc_full'],
+                                                       sg['flags_seen'], sg['rows_written']))
+                gaps = row.get('mma_gaps_us', [])
+                print('      mma batch gaps (us):', ' '.join('%.2f' % g for g in gaps[:64]))
         report.append(dict(layer=name, n_out=r['n_out'], ctas=rows))
     if args.json:
         json.dump(dict(precision=args.precision, mask_sort=args.mask_sort, sweeps=args.sweeps, sm_mhz=mhz,
