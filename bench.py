@@ -448,10 +448,14 @@ def run_ours(args, rank, world, device):
             ncu_tensor_pct = t.get('tensor_active_pct_time_weighted')
             traffic_src = t.get('source')
         common = {'traffic': traffic, 'traffic_source': traffic_src, 'peak_source': src,
-                  'kernel': ('sparse conv forward + data gradient (tcgen05 kind::tf32, 3xTF32) + weight gradient '
-                             '(spconv_wgrad_simt_kernel, FFMA)' if args.workload == 'train' else
+                  'kernel': ('sparse conv forward + data gradient (%s) + weight gradient '
+                             '(spconv_wgrad_simt_kernel, FFMA)' % {
+                                 'tf32x3': 'tcgen05 kind::tf32, 3xTF32', 'bf16x3c': 'tcgen05 kind::f16, split-bf16 operand '
+                                 'cache', 'bf16x3': 'tcgen05 kind::f16, bf16 x3', 'bf16': 'tcgen05 kind::f16, bf16 operands'
+                             }[args.precision] if args.workload == 'train' else
                              'spconv_fwd_tc_kernel (tcgen05 kind::tf32, 3xTF32)' if tc and args.precision == 'tf32x3' else
-                             'spconv_fwd_sb_kernel (tcgen05 kind::f16 on cached split-bf16 operands, cp.async gather)'
+                             'spconv_fwd_sbp_kernel (persistent; tcgen05 kind::f16 on cached split-bf16 operands, cp.async '
+                             'gather, work shares from tile masks)'
                              if tc and args.precision == 'bf16x3c' else
                              'spconv_fwd_tc16_kernel (tcgen05 kind::f16 on bf16 operands, %s)' % args.precision if tc else
                              'spconv_fwd_simt_kernel') + ' (%d launches/scene, summed)' % (len(conv) // 3),

@@ -144,7 +144,8 @@ MSMD_API int msmd_spconv_tc_set_variant(int variant);
 /* A/B switches of the host-side launch heuristics (defaults 0 = the measured rules): key 0 occupancy
  * (1 = one CTA per SM with the deepest pipeline, 2 = two CTAs per SM whenever they fit), key 1 pipeline-stage
  * cap (2..4), key 2 split-K pairs (1 = never, 2 = whenever supported), key 3 chunk blocks per pipeline stage of the
- * 16-bit kernel (2 = two: half the mbarrier round trips).  MSMD_TC_TUNE="occ=1,stages=3,split=1,cps=2". */
+ * 16-bit kernel (2 = two: half the mbarrier round trips), key 4 the persistent split-operand kernel's weight of a
+ * tile's epilogue in K-chunk times, plus one.  MSMD_TC_TUNE="occ=1,stages=3,split=1,cps=2,epi=9". */
 MSMD_API int msmd_spconv_tc_set_tuning(int key, int value);
 MSMD_API size_t msmd_spconv_tc_packed_floats(int cout, int kvol, int cin);
 MSMD_API int msmd_spconv_tc_pack_weight(const float* weight_krsc, int cout, int kvol, int cin,

@@ -160,7 +160,7 @@ def lib():
         if os.environ.get('MSMD_TC_TUNE'):  # e.g. "occ=1,stages=3,split=1,cps=2": launch-heuristic A/B switches
             for item in os.environ['MSMD_TC_TUNE'].split(','):
                 name, _, val = item.partition('=')
-                if L.msmd_spconv_tc_set_tuning({'occ': 0, 'stages': 1, 'split': 2, 'cps': 3}[name.strip()], int(val)) != 0:
+                if L.msmd_spconv_tc_set_tuning({'occ': 0, 'stages': 1, 'split': 2, 'cps': 3, 'epi': 4}[name.strip()], int(val)) != 0:
                     raise RuntimeError('bad MSMD_TC_TUNE')
         if os.environ.get('MSMD_TC16_VARIANT'):  # 16-bit modes: 2 = A via shared memory (default), 3 = A via tensor memory
             if L.msmd_spconv_tc16_set_variant(int(os.environ['MSMD_TC16_VARIANT'])) != 0:

@@ -410,7 +410,7 @@ spconv_fwd_sbp_kernel(const uint16_t* __restrict__ xs, const uint16_t* __restric
                       int stage_bytes, int pair_off, int pair_bytes, int act_off, int act_bytes, int kmask_off,
                       int bar_off, int tmem_cols, const float* __restrict__ scale, const float* __restrict__ shift,
                       const float* __restrict__ residual, int relu, float* __restrict__ out,
-                      uint16_t* __restrict__ out_s, int cat, float* __restrict__ ws,
+                      uint16_t* __restrict__ out_s, int cat, int epi_units, float* __restrict__ ws,
                       uint32_t* __restrict__ flags) {
   constexpr int epi_warps = kEpiWarps;
   extern __shared__ uint8_t smem_raw[];
@@ -466,15 +466,17 @@ spconv_fwd_sbp_kernel(const uint16_t* __restrict__ xs, const uint16_t* __restric
   const uint32_t tmem_base = *tmem_ptr_s;
 
   // ---- the CTA's share of the launch --------------------------------------------------------------------------
-  // A tile is worth one unit per K chunk it has to multiply: all of them without `tile_mask`, otherwise the chunks
-  // in which at least one of its rows has a pair (at least 1, so that every tile has an owner for its epilogue).
-  // Every CTA takes units [W*cta/G, W*(cta+1)/G) of the launch's W.  With tile masks the position of the first unit
-  // needs the prefix over the tiles: block-wide, once, in the (still idle) pipeline stages.
+  // A tile is worth `epi_units` (its epilogue, in chunk times; they come first and belong to the tile's owner) plus
+  // one unit per K chunk it has to multiply: all of them without `tile_mask`, otherwise the chunks in which at least
+  // one of its rows has a pair.  Every CTA takes units [W*cta/G, W*(cta+1)/G) of the launch's W.  With tile masks the
+  // position of the first unit needs the prefix over the tiles: block-wide, once, in the (still idle) pipeline stages.
+  const int whole = (cin_pad % kSbKC == 0) ? cin_pad / kSbKC : 0;   // chunks per kernel offset when they nest
   auto tile_units = [&](int t) {
     const uint32_t m = __ldg(tile_mask + t);
     int cnt = 0;
-    for (int j = 0; j < chunks; ++j) cnt += (kmask_s[j] & m) != 0u;
-    return cnt > 0 ? cnt : 1;
+    if (whole) cnt = __popc(m) * whole;
+    else for (int j = 0; j < chunks; ++j) cnt += (kmask_s[j] & m) != 0u;
+    return epi_units + cnt;
   };
   int total_units, u_begin, u_end;
   if (tile_mask) {
@@ -519,7 +521,7 @@ spconv_fwd_sbp_kernel(const uint16_t* __restrict__ xs, const uint16_t* __restric
     }
     __syncthreads();
   } else {
-    total_units = tiles * chunks;
+    total_units = tiles * (epi_units + chunks);
     u_begin = (int)((long long)total_units * cta / G);
     u_end = (int)((long long)total_units * (cta + 1) / G);
   }
@@ -546,7 +548,7 @@ spconv_fwd_sbp_kernel(const uint16_t* __restrict__ xs, const uint16_t* __restric
     int s = 0, it = 0;
     uint32_t ph = 1u;
     SBP_SEGMENT_LOOP {
-      SBP_SEGMENT_RECORD(mbar_wait_warp(&seg_full[b], sph, lane));
+      SBP_SEGMENT_RECORD(mbar_wait_warp_long(&seg_full[b], sph, lane));
       const int* pair_s = (const int*)(smem + pair_off + b * pair_bytes);
       const unsigned short* alist = (const unsigned short*)(smem + act_off + b * act_bytes);
       for (int t = 0; t < n_act; ++t, ++it) {
@@ -585,7 +587,7 @@ spconv_fwd_sbp_kernel(const uint16_t* __restrict__ xs, const uint16_t* __restric
     int s = 0, it = 0;
     uint32_t ph = 1u;
     SBP_SEGMENT_LOOP {
-      SBP_SEGMENT_RECORD(mbar_wait_warp(&seg_full[b], sph, lane));
+      SBP_SEGMENT_RECORD(mbar_wait_warp_long(&seg_full[b], sph, lane));
       const unsigned short* alist = (const unsigned short*)(smem + act_off + b * act_bytes);
       for (int t = 0; t < n_act; ++t, ++it) {
         if (lane == 0) TC_TRACE(2, it, 0);
@@ -613,10 +615,10 @@ spconv_fwd_sbp_kernel(const uint16_t* __restrict__ xs, const uint16_t* __restric
     int s = 0, it = 0;
     uint32_t ph = 0;
     SBP_SEGMENT_LOOP {
-      SBP_SEGMENT_RECORD(tc::mbar_wait(&seg_full[b], sph));
+      SBP_SEGMENT_RECORD(tc::mbar_wait_long(&seg_full[b], sph));
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(&seg_empty[b]);
-      tc::mbar_wait(&acc_empty[b], sph ^ 1u);   // the epilogue has read the accumulator used two segments ago
+      tc::mbar_wait_long(&acc_empty[b], sph ^ 1u);   // the epilogue has read the accumulator used two segments ago
       tc::fence_after_sync();
       const uint32_t d_tmem = tmem_base + (uint32_t)(b * tmem_cols);
       if (n_act == 0) {
@@ -661,13 +663,13 @@ spconv_fwd_sbp_kernel(const uint16_t* __restrict__ xs, const uint16_t* __restric
       t = start_s[1];
       off = start_s[2];
     } else if (u_begin < u_end) {
-      t = u_begin / chunks;
-      off = u_begin - t * chunks;
+      t = u_begin / (epi_units + chunks);
+      off = u_begin - t * (epi_units + chunks);
     }
     SBP_SEGMENT_LOOP {
       const int b = seg & 1;
       if (lane == 0) TC_TRACE(5, seg, 0);
-      mbar_wait_warp(&seg_empty[b], ((uint32_t)(seg >> 1) & 1u) ^ 1u, lane);
+      mbar_wait_warp_long(&seg_empty[b], ((uint32_t)(seg >> 1) & 1u) ^ 1u, lane);
       if (lane == 0) TC_TRACE(5, seg, 1);
       int* pair_s = (int*)(smem + pair_off + b * pair_bytes);
       unsigned short* alist = (unsigned short*)(smem + act_off + b * act_bytes);
@@ -696,30 +698,35 @@ spconv_fwd_sbp_kernel(const uint16_t* __restrict__ xs, const uint16_t* __restric
         }
         m = __reduce_or_sync(0xffffffffu, m);
       }
-      int units_t = chunks, take, n_list = 0;
+      // the tile's units: [0, epi_units) its epilogue, then one per chunk of its list; the segment takes
+      // [off, off + take) of them, i.e. list positions [lo, hi)
+      int units_t, take, n_list = 0;
       if (tile_mask) {
         int total = 0;
         for (int base = 0; base < chunks; base += 32) {
           const int j = base + lane;
           total += __popc(__ballot_sync(0xffffffffu, j < chunks && (kmask_s[j] & m) != 0u));
         }
-        units_t = total > 0 ? total : 1;
+        units_t = epi_units + total;
         take = min(units_t - off, u_end - u);
-        int ord = 0;   // position in the tile's list of chunks with a pair: the segment takes [off, off + take)
+        const int lo = max(off, epi_units) - epi_units, hi = off + take - epi_units;
+        int ord = 0;   // position in the tile's list of chunks with a pair
         for (int base = 0; base < chunks; base += 32) {
           const int j = base + lane;
           const bool a = j < chunks && (kmask_s[j] & m) != 0u;
           const unsigned bal = __ballot_sync(0xffffffffu, a);
           const int mine = ord + __popc(bal & ((1u << lane) - 1u));
-          if (a && mine >= off && mine < off + take) alist[mine - off] = (unsigned short)j;
+          if (a && mine >= lo && mine < hi) alist[mine - lo] = (unsigned short)j;
           ord += __popc(bal);
         }
-        n_list = total > 0 ? take : 0;
+        n_list = hi > lo ? hi - lo : 0;
       } else {
-        take = min(chunks - off, u_end - u);
-        for (int base = off; base < off + take; base += 32) {
+        units_t = epi_units + chunks;
+        take = min(units_t - off, u_end - u);
+        const int lo = max(off, epi_units) - epi_units, hi = off + take - epi_units;
+        for (int base = lo; base < hi; base += 32) {
           const int j = base + lane;
-          const bool a = j < off + take && (kmask_s[j] & m) != 0u;
+          const bool a = j < hi && (kmask_s[j] & m) != 0u;
           const unsigned bal = __ballot_sync(0xffffffffu, a);
           if (a) alist[n_list + __popc(bal & ((1u << lane) - 1u))] = (unsigned short)j;
           n_list += __popc(bal);
@@ -758,9 +765,9 @@ spconv_fwd_sbp_kernel(const uint16_t* __restrict__ xs, const uint16_t* __restric
     const size_t slot = (size_t)kTcM * N;         // floats per partial slot, [16-column step][row][16]
     const int total_w = total_units;
     SBP_SEGMENT_LOOP {
-      SBP_SEGMENT_RECORD(tc::mbar_wait(&seg_full[b], sph));
+      SBP_SEGMENT_RECORD(tc::mbar_wait_long(&seg_full[b], sph));
       if (ew == 0 && lane == 0) TC_TRACE(4, seg, 0);
-      tc::mbar_wait(&acc_full[b], sph);
+      tc::mbar_wait_long(&acc_full[b], sph);
       tc::fence_after_sync();
       if (ew == 0 && lane == 0) TC_TRACE(4, seg, 1);
       const uint32_t t_addr = tmem_base + (uint32_t)(b * tmem_cols) + ((uint32_t)(quarter * 32) << 16);
@@ -809,6 +816,7 @@ spconv_fwd_sbp_kernel(const uint16_t* __restrict__ xs, const uint16_t* __restric
 #pragma unroll
           for (int e = 0; e < 16; ++e) acc[e] = 0u;
         }
+        if (ew == 0 && lane == 0) TC_TRACE(6, seg * 8 + (st - step_lo), 0);
         if (!owner) {   // raw partial sums for the tile's owner
           float4* dst = (float4*)(ws + (size_t)cta * slot + ((size_t)st * kTcM + prow) * 16);
 #pragma unroll
@@ -840,6 +848,7 @@ spconv_fwd_sbp_kernel(const uint16_t* __restrict__ xs, const uint16_t* __restric
                              __uint_as_float(acc[4 * pc]), __uint_as_float(acc[4 * pc + 1]),
                              __uint_as_float(acc[4 * pc + 2]), __uint_as_float(acc[4 * pc + 3]));
           __syncwarp();
+          if (ew == 0 && lane == 0) TC_TRACE(6, seg * 8 + (st - step_lo), 1);
           const int pc = lane & 3;
           const int co = c0 + 4 * pc;
           if (co < cout) {
@@ -873,6 +882,7 @@ spconv_fwd_sbp_kernel(const uint16_t* __restrict__ xs, const uint16_t* __restric
             }
           }
           __syncwarp();   // the block is rewritten by the next step
+          if (ew == 0 && lane == 0) TC_TRACE(6, seg * 8 + (st - step_lo), 3);
           continue;
         }
         if (o >= n_out) continue;
@@ -1108,7 +1118,7 @@ static int sbp_launch(const SbGeom& g, const void* features_split, const void* p
                       const float* shift,
                       const float* residual, int relu, float* out, void* out_split, cudaStream_t stream) {
   const int tiles = ceil_div(n_out, kTcM);
-  const long long units = (long long)tiles * g.chunks;
+  const long long units = (long long)tiles * (g.chunks + 8);
   MSMD_REQUIRE(units < (1ll << 31), "spconv_fwd_sb: too many (tile, chunk) units");
   const int cat = (2 * g.N <= 256) ? 1 : 0;
   int tmem_cols = 32;
@@ -1123,6 +1133,12 @@ static int sbp_launch(const SbGeom& g, const void* features_split, const void* p
   MSMD_REQUIRE(L.stages >= 2, "spconv_fwd_sb: tile does not fit in shared memory");
   MSMD_REQUIRE(tiles <= L.stages * L.stage_bytes / 4, "spconv_fwd_sb: too many tiles for the in-kernel prefix");
   const int epi_warps = two ? 4 : 8;
+  // what a tile's epilogue costs in chunk times (r02o timelines: ~4 us against 0.55 us per chunk at N = 128, ~1.5 us
+  // against 0.45 us at N = 32); the tuning switch [4] overrides it for A/B runs
+  int epi_units = g.N / 16;
+  if (epi_units < 2) epi_units = 2;
+  if (epi_units > 8) epi_units = 8;
+  if (g_tc_tune[4] >= 1 && g_tc_tune[4] <= 64) epi_units = g_tc_tune[4] - 1;
   const int threads = (kSbpWarpEpi + epi_warps) * 32;
   static bool attr_set = false;
   static int resident[2] = {0, 0};   // CTAs per SM the hardware really co-schedules, [one, two]
@@ -1155,7 +1171,7 @@ static int sbp_launch(const SbGeom& g, const void* features_split, const void* p
   (const uint16_t*)features_split, (const uint16_t*)packed_sb, pair_fwd, row_perm, tile_mask, n_out, tiles,         \
       g.cin_pad, cin_magic, cout, round_up(cout, 8), g.N, kvol, g.chunks, L.stages, L.stage_bytes, L.pair_off,       \
       L.pair_bytes, L.act_off, L.act_bytes, L.kmask_off, L.bar_off, tmem_cols, scale, shift, residual, relu, out,    \
-      (uint16_t*)out_split, cat, w.ws, w.flags
+      (uint16_t*)out_split, cat, epi_units, w.ws, w.flags
   if (two) spconv_fwd_sbp_kernel<4><<<grid, threads, L.total, stream>>>(MSMD_SBP_ARGS);
   else spconv_fwd_sbp_kernel<8><<<grid, threads, L.total, stream>>>(MSMD_SBP_ARGS);
 #undef MSMD_SBP_ARGS

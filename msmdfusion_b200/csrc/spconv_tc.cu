@@ -608,10 +608,10 @@ extern "C" MSMD_API int msmd_tc_trace_set(unsigned long long* buf) { return tc_t
 extern "C" MSMD_API int msmd_tc_trace_record_words(void) { return kTrRecord; }
 #endif
 
-int msmd::g_tc_tune[4] = {0, 0, 0, 0};
+int msmd::g_tc_tune[5] = {0, 0, 0, 0, 0};
 
 extern "C" MSMD_API int msmd_spconv_tc_set_tuning(int key, int value) {
-  MSMD_REQUIRE(key >= 0 && key < 4, "spconv_tc_set_tuning: key must be 0 (occupancy), 1 (stage cap), 2 (split-K) or 3 (chunks per stage)");
+  MSMD_REQUIRE(key >= 0 && key < 5, "spconv_tc_set_tuning: key must be 0 (occupancy), 1 (stage cap), 2 (split-K), 3 (chunks per stage) or 4 (epilogue units)");
   g_tc_tune[key] = value;
   return MSMD_OK;
 }

@@ -20,7 +20,8 @@ static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 //   [1] stage cap  2..4 (default 4)
 //   [2] split-K    0 auto | 1 never | 2 whenever the kernel supports it
 //   [3] chunk blocks per pipeline stage of the 16-bit kernel (variant 2): 0/1 one | 2 two (half the hand-offs)
-extern int g_tc_tune[4];
+//   [4] persistent split-operand kernel: weight of a tile's epilogue in K-chunk times, plus one (0 = by N)
+extern int g_tc_tune[5];
 // shared-memory budget of one CTA: `fits_half` = two pipeline stages fit in half of the SM
 static inline int tc_smem_budget(bool fits_half, int tiles) {
   const int half = 112 * 1024, full = 224 * 1024;
@@ -57,6 +58,10 @@ static inline void tc_launch(Kern kern, int grid, int block, int smem, cudaStrea
 // warp: the producers are instruction-issue bound, profiles/r01e_ncu_full_spconv_tc_profileS.json).
 __device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity, int lane) {
   if (lane == 0) tc::mbar_wait(bar, parity);
+  __syncwarp();
+}
+__device__ __forceinline__ void mbar_wait_warp_long(uint64_t* bar, uint32_t parity, int lane) {
+  if (lane == 0) tc::mbar_wait_long(bar, parity);
   __syncwarp();
 }
 

@@ -13,12 +13,14 @@
 //   persistent kernel (spconv_fwd_sbp_kernel) only -- `it` = segment index:
 //     role 4      epilogue warp 0:           0 about to wait for the accumulator | 1 accumulator complete |
 //                                            2 hand-off flags seen (owner of a split tile) | 3 rows written
+//     role 6      epilogue warp 0, it = 8 * segment + column step: 0 TMEM read done | 1 staged (after __syncwarp) |
+//                                            2 staged block read back | 3 rows stored
 //     role 5      segment loader:            0 about to wait for the free slot | 1 slot free | 2 pair rows landed | 3 published
 // Traced CTAs: kTrCtas of them, evenly spaced over the grid.
 #pragma once
 #ifdef MSMD_TC_TRACE
 namespace msmd {
-constexpr int kTrCtas = 16, kTrRoles = 6, kTrIts = 128, kTrPhases = 4, kTrHead = 16;
+constexpr int kTrCtas = 16, kTrRoles = 7, kTrIts = 128, kTrPhases = 4, kTrHead = 16;
 constexpr int kTrRecord = kTrHead + kTrRoles * kTrIts * kTrPhases;
 static __device__ unsigned long long* g_tc_trace = nullptr;
 __device__ __forceinline__ unsigned long long* tc_trace_base() {

@@ -27,7 +27,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-HEAD, ROLES, ITS, PHASES, CTAS = 16, 6, 128, 4, 16
+HEAD, ROLES, ITS, PHASES, CTAS = 16, 7, 128, 4, 16
 
 
 def summarize(rec, mhz):
@@ -75,6 +75,9 @@ def summarize(rec, mhz):
                                   loader_wait_from=round((sl[i, 0] - t0) * cyc, 2), loader_free=round((sl[i, 1] - t0) * cyc, 2),
                                   pairs_landed=round((sl[i, 2] - t0) * cyc, 2), published=round((sl[i, 3] - t0) * cyc, 2))
                              for i in range(nseg)]
+            st6 = ev[6]
+            d['epi_steps'] = [[i // 8, i % 8] + [round((st6[i, ph] - t0) * cyc, 2) if st6[i, ph] else None for ph in (0, 1, 3)]
+                              for i in range(ITS) if st6[i, 0]]
             d['first_mma_us'] = round((ev[3, 0, 1] - t0) * cyc, 2) if n else None
             d['last_mma_us'] = round((ev[3, n - 1, 2] - t0) * cyc, 2) if n else None
         out.append(d)
@@ -182,6 +185,8 @@ def main():
                           'flags %.1f written %.1f' % (i, sg['loader_wait_from'], sg['loader_free'], sg['pairs_landed'],
                                                        sg['published'], sg['acc_wait_from'], sg['acc_full'],
                                                        sg['flags_seen'], sg['rows_written']))
+                for e in row.get('epi_steps', []):
+                    print('         epilogue seg %d step %d: tmem read %s staged %s stored %s' % tuple(e))
                 gaps = row.get('mma_gaps_us', [])
                 print('      mma batch gaps (us):', ' '.join('%.2f' % g for g in gaps[:64]))
         report.append(dict(layer=name, n_out=r['n_out'], ctas=rows))
