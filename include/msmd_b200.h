@@ -251,6 +251,7 @@ MSMD_API int msmd_spconv_fwd_sb(const void* features_split, int n_in, const void
  * main loop.  The hand-off slots (<= 19 MB) belong to the library, one set per (device, stream), allocated on the
  * first launch on that stream. */
 MSMD_API int msmd_spconv_sb_set_variant(int variant);
+MSMD_API int msmd_spconv_sb_set_pdl(int enable);     /* programmatic dependent launch of the persistent kernel (default 0: measured slower end to end) */
 MSMD_API int msmd_spconv_sb_uses_tile_masks(void);   /* 1 under variant 0: callers that keep rulebooks build tile masks */
 /* Per-rulebook side table for the persistent schedule: bit k of tile_mask[t] (t = 128-row tile, ceil(n_out/128) words) is
  * set when some row of the tile has a pair at kernel offset k.  Built once per rulebook (spconv-2.x keeps the analogous

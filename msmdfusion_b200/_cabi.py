@@ -87,6 +87,7 @@ SIGNATURES = {
     'msmd_spconv_sb_packed_bytes': (_sz, [_i, _i, _i]),
     'msmd_spconv_sb_set_variant': (_i, [_i]),
     'msmd_spconv_sb_uses_tile_masks': (_i, []),
+    'msmd_spconv_sb_set_pdl': (_i, [_i]),
     'msmd_rulebook_tile_masks': (_i, [_vp, _i, _i, _vp, _vp]),
     'msmd_spconv_fwd_sb_ex': (_i, [_vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp]),
     'msmd_spconv_sb_pack_weight': (_i, [_vp, _i, _i, _i, _vp, _vp]),
@@ -168,6 +169,8 @@ def lib():
         if os.environ.get('MSMD_SB_VARIANT'):  # schedule of the split-operand conv kernel: 1 tile per CTA | 2 persistent
             if L.msmd_spconv_sb_set_variant(int(os.environ['MSMD_SB_VARIANT'])) != 0:
                 raise RuntimeError('bad MSMD_SB_VARIANT')
+        if os.environ.get('MSMD_SB_PDL'):  # programmatic dependent launch of the persistent conv kernel (default off)
+            L.msmd_spconv_sb_set_pdl(int(os.environ['MSMD_SB_PDL']))
         if os.environ.get('MSMD_FPS_THREADS'):  # A/B switch of the cluster FPS kernel's CTA width
             if L.msmd_fps_set_threads(int(os.environ['MSMD_FPS_THREADS'])) != 0:
                 raise RuntimeError('bad MSMD_FPS_THREADS')

@@ -442,6 +442,10 @@ spconv_fwd_sbp_kernel(const uint16_t* __restrict__ xs, const uint16_t* __restric
   const int G = gridDim.x, cta = blockIdx.x;
   TC_TRACE_INIT();
   TC_TRACE_ENTRY();
+  // Programmatic dependent launch: the next kernel of the stream may start its CTAs as SMs free up; everything up
+  // to griddep_wait() below reads only what no kernel of the chain writes (weights' scale / shift, the rulebook, its
+  // tile masks), so this kernel's own prologue overlaps its predecessor's tail the same way.
+  tc::griddep_launch_dependents();
 
   if (tid == 0) {
     for (int s = 0; s < stages; ++s) {
@@ -526,6 +530,9 @@ spconv_fwd_sbp_kernel(const uint16_t* __restrict__ xs, const uint16_t* __restric
     u_end = (int)((long long)total_units * (cta + 1) / G);
   }
   if (tid == 0) { TC_TRACE_HEAD(1, clock64()); TC_TRACE_HEAD(7, u_end - u_begin); }
+  // activations, residual, outputs and the hand-off slots are touched only behind this point; the segment loader
+  // (pair rows, tile masks: geometry-stream data the launching stream already waited for) runs ahead
+  if (warp != kSbpWarpSeg) tc::griddep_wait();
 
 // every role walks the CTA's segments in step: the loader publishes a record per segment, the others read it
 #define SBP_SEGMENT_LOOP for (int u = u_begin, seg = 0; u < u_end; ++seg)
@@ -1031,6 +1038,15 @@ extern "C" MSMD_API int msmd_spconv_sb_set_variant(int variant) {
   return MSMD_OK;
 }
 extern "C" MSMD_API int msmd_spconv_sb_uses_tile_masks(void) { return g_sb_variant == 0 ? 1 : 0; }
+// Programmatic dependent launch of the persistent kernel (A/B switch; default OFF).  r02r on a B200: back-to-back
+// launches of one layer get 6 % faster with it (the prologue hides under the predecessor's tail), but the whole L / LC
+// steps get 14 % / 3 % SLOWER: with no gap left between the conv kernels, the rulebook kernels of the geometry stream
+// (which later layers wait for) find no free SM -- a 608-thread CTA leaves room for nothing else.
+static int g_sb_pdl = 0;
+extern "C" MSMD_API int msmd_spconv_sb_set_pdl(int enable) {
+  g_sb_pdl = enable ? 1 : 0;
+  return MSMD_OK;
+}
 
 namespace {
 // Launches on one stream are serial, so one slot set per (device, stream) is enough; the flags are zero between
@@ -1111,6 +1127,15 @@ extern "C" MSMD_API int msmd_spconv_sb_pack_weight(const float* weight_krsc, int
   return MSMD_OK;
 }
 
+// Which schedule a shape gets under the default variant (r02q per-layer A/B on the LC scene, profiles/): the persistent
+// kernel wins wherever a tile's main loop is long against its fixed costs -- N >= 64 and >= 16 K chunks per tile
+// (Cin >= 38 at 27 offsets); the narrow and the 3-offset layers keep one tile per CTA, where two CTAs share an SM.
+static bool sb_use_persistent(const SbGeom& g) {
+  if (g_sb_variant == 1) return false;
+  if (g_sb_variant == 2) return true;
+  return g.N >= 64 && g.chunks >= 16;
+}
+
 // Launch of the persistent kernel: occupancy (1 or 2 CTAs per SM), grid = the SM slots (never more CTAs than
 // units of work), equal unit ranges.
 static int sbp_launch(const SbGeom& g, const void* features_split, const void* packed_sb, const int* pair_fwd,
@@ -1172,8 +1197,26 @@ static int sbp_launch(const SbGeom& g, const void* features_split, const void* p
       g.cin_pad, cin_magic, cout, round_up(cout, 8), g.N, kvol, g.chunks, L.stages, L.stage_bytes, L.pair_off,       \
       L.pair_bytes, L.act_off, L.act_bytes, L.kmask_off, L.bar_off, tmem_cols, scale, shift, residual, relu, out,    \
       (uint16_t*)out_split, cat, epi_units, w.ws, w.flags
+#ifdef MSMD_EMUL
   if (two) spconv_fwd_sbp_kernel<4><<<grid, threads, L.total, stream>>>(MSMD_SBP_ARGS);
   else spconv_fwd_sbp_kernel<8><<<grid, threads, L.total, stream>>>(MSMD_SBP_ARGS);
+#else
+  {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3((unsigned)threads);
+    cfg.dynamicSmemBytes = (size_t)L.total;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = g_sb_pdl ? 1 : 0;
+    const cudaError_t launch_err = two ? cudaLaunchKernelEx(&cfg, spconv_fwd_sbp_kernel<4>, MSMD_SBP_ARGS)
+                                       : cudaLaunchKernelEx(&cfg, spconv_fwd_sbp_kernel<8>, MSMD_SBP_ARGS);
+    MSMD_CUDA_OK(launch_err);
+  }
+#endif
 #undef MSMD_SBP_ARGS
   MSMD_LAUNCH_OK();
   return MSMD_OK;
@@ -1195,7 +1238,7 @@ extern "C" MSMD_API int msmd_spconv_fwd_sb(const void* features_split, int n_in,
                    ((uintptr_t)out_split & 15) == 0,
                "spconv_fwd_sb: split images and packed weights must be 16-byte aligned");
   const int tiles = ceil_div(n_out, kTcM);
-  if (g_sb_variant != 1)
+  if (sb_use_persistent(g))
     return sbp_launch(g, features_split, packed_sb, pair_fwd, nullptr, nullptr, n_out, cout, kvol, scale, shift,
                       residual, relu, out, out_split, stream);
   const SbLayout L = sb_layout(g.N, kvol, g.chunks, tiles);
@@ -1257,7 +1300,8 @@ extern "C" MSMD_API int msmd_spconv_fwd_sb_ex(const void* features_split, int n_
                                               int n_out, int cin, int cout, int kvol, const float* scale,
                                               const float* shift, const float* residual, int relu, float* out,
                                               void* out_split, msmd_stream_t stream_) {
-  if (!row_perm && (!tile_mask || g_sb_variant == 1))
+  SbGeom g0;
+  if (!row_perm && (!tile_mask || !sb_geom(cout, kvol, cin, g0) || !sb_use_persistent(g0)))
     return msmd_spconv_fwd_sb(features_split, n_in, packed_sb, pair_fwd, n_out, cin, cout, kvol, scale, shift,
                               residual, relu, out, out_split, stream_);
   cudaStream_t stream = (cudaStream_t)stream_;

@@ -268,6 +268,13 @@ __device__ __forceinline__ void pdl_wait() {
 #endif
 }
 
+// Unconditional forms (the persistent split-operand kernel is always launched with the attribute; without it both
+// instructions are no-ops)
+__device__ __forceinline__ void griddep_launch_dependents() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 __device__ __forceinline__ float4 ld_shared_v4(uint32_t addr) {
   float4 v;
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));

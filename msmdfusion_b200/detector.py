@@ -413,6 +413,19 @@ class MSMDFusionDetector(nn.Module, _VoxelPathMixin):
     # issuing ~400 launches, and the extra voxelisation calls cost more host time than the earlier FPS start saves.)
     overlap_image_side = os.environ.get('MSMD_LC_OVERLAP', '1') not in ('', '0')   # A/B switch
 
+    # The compression block is ~35 small torch launches (0.7 ms of host time, profiles/r02k_lc_timeline_fps512.txt) that
+    # depend on nothing the calling thread does next (LiDAR voxelisation + encoder call, ~1 ms of host time, most of it
+    # inside C calls that release the GIL): a helper thread issues them on the side stream meanwhile.  Same stream, same
+    # kernels, same order on that stream as before -- only the host work overlaps.  MSMD_LC_HOST_THREAD=0 switches it off.
+    host_thread = os.environ.get('MSMD_LC_HOST_THREAD', '1') not in ('', '0')
+
+    def _helper(self):
+        ex = self.__dict__.get('_host_helper')
+        if ex is None:
+            from concurrent.futures import ThreadPoolExecutor
+            ex = self.__dict__['_host_helper'] = ThreadPoolExecutor(max_workers=1, thread_name_prefix='msmd-image-side')
+        return ex
+
     def _side(self, device):
         st = self.__dict__.get('_image_side_stream')
         if st is None or st.device != device:
@@ -436,8 +449,18 @@ class MSMDFusionDetector(nn.Module, _VoxelPathMixin):
             start = torch.cuda.Event()
             start.record(main)
             side.wait_event(start)
-            with torch.cuda.stream(side):
-                compressed = self.depth_aware_channel_compression(img_feats, img_metas)
+            pending = None
+            if self.host_thread:
+                with torch.cuda.stream(side):
+                    self.packed_foreground(img_metas, dev)   # the upload (and its cache entry) from this thread
+
+                def compress():
+                    with torch.no_grad(), torch.cuda.stream(side):   # grad mode and current stream are per thread
+                        return self.depth_aware_channel_compression(img_feats, img_metas)
+                pending = self._helper().submit(compress)
+            else:
+                with torch.cuda.stream(side):
+                    compressed = self.depth_aware_channel_compression(img_feats, img_metas)
         voxel_features, coors, _ = self.voxelize_mean(pts, nf)
         # a frozen LiDAR encoder (tools/train.py:185-211) has no grad-requiring input either (voxelize is
         # no_grad, :462-464), so autograd would skip it anyway: run it on the inference path
@@ -446,6 +469,8 @@ class MSMDFusionDetector(nn.Module, _VoxelPathMixin):
             x, encode_features = self.pts_middle_encoder(voxel_features, coors, batch_size)
         if overlap:
             from . import executor
+            if pending is not None:
+                compressed = pending.result()   # re-raises whatever the helper thread raised
             geom_done = torch.cuda.Event()
             if getattr(self.pts_middle_encoder, 'ran_on_executor', False):
                 geom_done.record(executor.geometry_stream(dev))   # index sets of the four LiDAR scales

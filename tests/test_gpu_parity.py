@@ -677,7 +677,7 @@ def test_fused_gma_gates_equal_eager_path():
     assert feat_err(outs[True][0].cpu().numpy(), outs[False][0].cpu().numpy()) < FEAT_TOL
 
 
-@pytest.mark.parametrize('overlap', [True, False])
+@pytest.mark.parametrize('overlap', [True, 'no_helper_thread', False])
 def test_native_gma_stage_and_overlapped_schedule_equal_module_path(overlap):
     """One C-ABI call per GMA stage (csrc/gma.cu: msmd_gma_stage_forward) and the overlapped image-side schedule of
     MSMDFusionDetector.extract_voxel_space against the module-by-module, in-sequence path: identical index sets,
@@ -688,18 +688,19 @@ def test_native_gma_stage_and_overlapped_schedule_equal_module_path(overlap):
     fpn = [cuda(f) for f in fpn_np]
     pts_t = [cuda(s) for s in scenes]
     outs = {}
-    saved = (fe.SparseMultiModalEncoderPaint.native_stage, type(det).overlap_image_side)
+    saved = (fe.SparseMultiModalEncoderPaint.native_stage, type(det).overlap_image_side, type(det).host_thread)
     try:
         for native in (True, False):
             fe.SparseMultiModalEncoderPaint.native_stage = native
-            type(det).overlap_image_side = overlap if native else False
+            type(det).overlap_image_side = bool(overlap) if native else False
+            type(det).host_thread = overlap is True   # the compression block issued from the helper thread
             torch.manual_seed(77)
             with torch.no_grad():
                 bev, stage_outs = det.extract_voxel_space(pts_t, fpn, metas)
             torch.cuda.synchronize()
             outs[native] = (bev.clone(), [(t.indices.clone(), t.features.clone()) for t in stage_outs])
     finally:
-        fe.SparseMultiModalEncoderPaint.native_stage, type(det).overlap_image_side = saved
+        fe.SparseMultiModalEncoderPaint.native_stage, type(det).overlap_image_side, type(det).host_thread = saved
     for (ia, fa), (ib, fb) in zip(outs[True][1], outs[False][1]):
         assert torch.equal(ia, ib)
         assert feat_err(fa.cpu().numpy(), fb.cpu().numpy()) < 1e-5

@@ -91,7 +91,8 @@ def translate(cu_name):
     return src
 
 
-PRELUDE = '''#include "cuda_emul.h"
+PRELUDE = '''#define MSMD_EMUL 1
+#include "cuda_emul.h"
 namespace emu {
 thread_local dim3 t_threadIdx, t_blockIdx;
 dim3 g_blockDim, g_gridDim;

@@ -239,6 +239,8 @@ static inline void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 static inline void mbar_wait_long(uint64_t* bar, uint32_t parity) { mbar_wait(bar, parity); }
+static inline void griddep_launch_dependents() {}
+static inline void griddep_wait() {}
 static inline void fence_proxy_async() {}
 
 static inline void bulk_g2s(void* dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
