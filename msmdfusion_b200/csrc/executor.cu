@@ -66,12 +66,27 @@ struct AuxStreams {
 };
 static AuxStreams g_aux[16];
 
+// The geometry stream carries the short kernels everything else waits for (index sets, rulebooks, tile masks) while
+// the convolutions keep every SM busy: it gets the highest stream priority, so that its thread blocks are the first to
+// be placed whenever an SM frees up (MSMD_GEOM_PRIORITY=0 in the environment: default priority, for A/B runs).
+static int create_geometry_stream(cudaStream_t* out) {
+  int least = 0, greatest = 0;
+  MSMD_CUDA_OK(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+  const char* e = getenv("MSMD_GEOM_PRIORITY");
+  const int prio = (e && e[0] == '0') ? least : greatest;
+  MSMD_CUDA_OK(cudaStreamCreateWithPriority(out, cudaStreamNonBlocking, prio));
+  return MSMD_OK;
+}
+
 static int aux_for_current_device(AuxStreams** out) {
   int dev = 0;
   MSMD_CUDA_OK(cudaGetDevice(&dev));
   MSMD_REQUIRE(dev >= 0 && dev < 16, "sparse_net_forward: device ordinal %d unsupported", dev);
   AuxStreams& a = g_aux[dev];
-  if (!a.geom) MSMD_CUDA_OK(cudaStreamCreateWithFlags(&a.geom, cudaStreamNonBlocking));
+  if (!a.geom) {
+    const int rc = create_geometry_stream(&a.geom);
+    if (rc != MSMD_OK) return rc;
+  }
   a.next = 0;
   *out = &a;
   return MSMD_OK;
@@ -132,7 +147,10 @@ extern "C" MSMD_API int msmd_executor_geometry_stream(void** stream_out) {
   MSMD_CUDA_OK(cudaGetDevice(&dev));
   MSMD_REQUIRE(dev >= 0 && dev < 16, "executor_geometry_stream: device ordinal %d unsupported", dev);
   AuxStreams* aux = &g_aux[dev];
-  if (!aux->geom) MSMD_CUDA_OK(cudaStreamCreateWithFlags(&aux->geom, cudaStreamNonBlocking));
+  if (!aux->geom) {
+    const int rc = create_geometry_stream(&aux->geom);
+    if (rc != MSMD_OK) return rc;
+  }
   *stream_out = (void*)aux->geom;
   return MSMD_OK;
 }
