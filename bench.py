@@ -369,6 +369,13 @@ def run_ours(args, rank, world, device):
 
     # ---- per-kernel timing of the dominant kernel (sparse conv), live, CUDA events ----
     roof = None
+    if rank != 0 and trainer is not None and world > 1:
+        # the train step holds a collective: the 4 instrumented steps rank 0 runs below need their partners
+        # (r02l / r02u: without them rank 0 waited in the gradient all-reduce for ranks that had already left)
+        for _ in range(4):
+            flush.zero_()
+            step(pts_dev)
+        torch.cuda.synchronize(device)
     if rank == 0:
         # per-kernel timing needs one C-ABI call per convolution: run the module-by-module path
         # (same kernels, same operands) instead of the one-call native executor for these 4 steps

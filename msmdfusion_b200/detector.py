@@ -315,7 +315,7 @@ class MSMDFusionDetector(nn.Module, _VoxelPathMixin):
         return list(torch.split(out, pk.counts, dim=0)) if B > 1 else [out]
 
     # -- :335-369 ---------------------------------------------------------------------------
-    def depth_aware_channel_compression(self, feat_list, img_metas):
+    def depth_aware_channel_compression(self, feat_list, img_metas, _static_ok=False):
         B = len(img_metas)
         device = feat_list[0].device
         H, W = img_metas[0]['pad_shape'][:2]
@@ -332,6 +332,16 @@ class MSMDFusionDetector(nn.Module, _VoxelPathMixin):
             depth = pk.real_pixels[:, 2].contiguous()
             canvas = torch.where(winner >= 0, depth[winner.clamp_min(0)], canvas)  # no host sync
         canvas = canvas.view(ncanvas, 1, H, W)
+        # `_static_ok`: the caller consumes the result within the step (extract_voxel_space); everybody else gets
+        # tensors of their own
+        if (_static_ok and self.compress_graph and canvas.is_cuda and not torch.is_grad_enabled() and
+                not self.conv1x1_blocks.training and all(f.is_cuda and f.dtype == torch.float32 for f in feat_list[:3])):
+            return self._compress_graphed(feat_list[:3], canvas)
+        return self._compress_static(feat_list, canvas)
+
+    def _compress_static(self, feat_list, canvas):
+        """The shape-static half of the block (:360-369): depth map resampled to each FPN level, concatenated,
+        Conv2d(257 -> 49) + BatchNorm2d + ReLU (cuDNN)."""
         out = []
         for i in range(3):
             img_feat = feat_list[i]
@@ -339,6 +349,39 @@ class MSMDFusionDetector(nn.Module, _VoxelPathMixin):
             sp_depth_map = F.interpolate(canvas, (h, w), mode='bilinear')
             out.append(self.conv1x1_blocks[i](torch.cat([img_feat, sp_depth_map], dim=1)))
         return out
+
+    # Those ~20 launches have the same shapes every step, and the step is bound by the host issuing launches
+    # (DESIGN.md 3d): in the inference form they are captured once into a CUDA graph (inputs copied into the graph's
+    # static buffers: 45 MB of device-to-device copies, ~30 us) and replayed with one launch.  Same cuDNN kernels on
+    # the same operands.  MSMD_COMPRESS_GRAPH=0 switches it off; the graph is rebuilt when a shape or a parameter's
+    # storage changes (parameter VALUES are read at replay, so in-place updates need nothing).
+    compress_graph = os.environ.get('MSMD_COMPRESS_GRAPH', '1') not in ('', '0')
+
+    def _compress_graphed(self, feat_list, canvas):
+        key = (tuple((tuple(f.shape), f.device) for f in feat_list), tuple(canvas.shape),
+               tuple(t.data_ptr() for t in list(self.conv1x1_blocks.parameters()) + list(self.conv1x1_blocks.buffers())))
+        rec = self.__dict__.get('_compress_graph_rec')
+        if rec is None or rec['key'] != key:
+            cur = torch.cuda.current_stream(canvas.device)
+            static_in = [torch.empty_like(f, memory_format=torch.contiguous_format) for f in feat_list]
+            static_canvas = torch.empty_like(canvas)
+            for dst, src in zip(static_in, feat_list):
+                dst.copy_(src)
+            static_canvas.copy_(canvas)
+            self._compress_static(static_in, static_canvas)     # lazy cuDNN initialisation happens outside the capture
+            cur.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, capture_error_mode='thread_local'):   # other threads / streams keep working
+                static_out = self._compress_static(static_in, static_canvas)
+            rec = self.__dict__['_compress_graph_rec'] = dict(key=key, graph=graph, static_in=static_in,
+                                                              static_canvas=static_canvas, static_out=static_out)
+        for dst, src in zip(rec['static_in'], feat_list):
+            dst.copy_(src)
+        rec['static_canvas'].copy_(canvas)
+        rec['graph'].replay()
+        # the graph owns its outputs and rewrites them at the next replay: consumers are stream-ordered before it (the
+        # side stream waits for an event of the main stream at the start of every step)
+        return list(rec['static_out'])
 
     # -- :371-393 ---------------------------------------------------------------------------
     def fetch_2D_voxels(self, img_feat, img_metas, voxel_size, downscale_factor, B):
@@ -456,11 +499,11 @@ class MSMDFusionDetector(nn.Module, _VoxelPathMixin):
 
                 def compress():
                     with torch.no_grad(), torch.cuda.stream(side):   # grad mode and current stream are per thread
-                        return self.depth_aware_channel_compression(img_feats, img_metas)
+                        return self.depth_aware_channel_compression(img_feats, img_metas, _static_ok=True)
                 pending = self._helper().submit(compress)
             else:
                 with torch.cuda.stream(side):
-                    compressed = self.depth_aware_channel_compression(img_feats, img_metas)
+                    compressed = self.depth_aware_channel_compression(img_feats, img_metas, _static_ok=True)
         voxel_features, coors, _ = self.voxelize_mean(pts, nf)
         # a frozen LiDAR encoder (tools/train.py:185-211) has no grad-requiring input either (voxelize is
         # no_grad, :462-464), so autograd would skip it anyway: run it on the inference path
