@@ -613,6 +613,9 @@ def scene_counts(args, seed=0):
 
 def main():
     args = parse()
+    if os.environ.get('MSMD_BENCH_HANG_DUMP'):   # diagnostic: Python stacks of every thread after that many seconds
+        import faulthandler
+        faulthandler.dump_traceback_later(int(os.environ['MSMD_BENCH_HANG_DUMP']), exit=False)
     rank = int(os.environ.get('RANK', 0))
     local_rank = int(os.environ.get('LOCAL_RANK', 0))
     world = int(os.environ.get('WORLD_SIZE', 1))
