@@ -459,8 +459,10 @@ class MSMDFusionDetector(nn.Module, _VoxelPathMixin):
     # The compression block is ~35 small torch launches (0.7 ms of host time, profiles/r02k_lc_timeline_fps512.txt) that
     # depend on nothing the calling thread does next (LiDAR voxelisation + encoder call, ~1 ms of host time, most of it
     # inside C calls that release the GIL): a helper thread issues them on the side stream meanwhile.  Same stream, same
-    # kernels, same order on that stream as before -- only the host work overlaps.  MSMD_LC_HOST_THREAD=0 switches it off.
-    host_thread = os.environ.get('MSMD_LC_HOST_THREAD', '1') not in ('', '0')
+    # kernels, same order on that stream as before -- only the host work overlaps.  Worth 0.1 ms of the step (r02s), and
+    # nothing once the block's static half is a CUDA graph (r02v: 7.441 vs 7.444 ms): OFF by default, MSMD_LC_HOST_THREAD=1
+    # switches it on.
+    host_thread = os.environ.get('MSMD_LC_HOST_THREAD', '0') not in ('', '0')
 
     def _helper(self):
         ex = self.__dict__.get('_host_helper')
