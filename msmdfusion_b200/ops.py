@@ -53,12 +53,14 @@ def _triple(v):
 # reference: mmdet3d/ops/voxel/voxelize.py:13-59, src/voxelization_cpu.cpp:43-142
 # --------------------------------------------------------------------------------------
 def hard_voxelize(points, voxel_size, coors_range, max_points, max_voxels, want_voxels=True,
-                  mean_features=0, batch_idx=None):
+                  mean_features=0, batch_idx=None, out=None):
     """Returns (voxels|None, coors, num_points_per_voxel, mean|None), sliced to voxel_num.
 
     coors is (V,3) (z,y,x) or, when ``batch_idx`` is given, (V,4) (batch_idx,z,y,x).
     One host read-back (voxel_num) at the end -- the reference does the same
     (voxelization_cuda.cu:322-323) after four device synchronisations.
+    ``out``: the caller's pre-allocated (voxels, coors, num_points_per_voxel) of the reference's calling convention
+    (voxelize.py:44-52), filled in place when they are contiguous CUDA tensors of the right type and capacity.
     """
     if points.dtype != torch.float32:
         points = points.float()
@@ -68,9 +70,19 @@ def hard_voxelize(points, voxel_size, coors_range, max_points, max_voxels, want_
     max_voxels_eff = max_voxels if max_voxels >= 0 else n
     cap = max(1, min(n, max_voxels_eff))
     ncol = 3 if batch_idx is None else 4
-    voxels = torch.empty((cap, max_points, c), dtype=torch.float32, device=dev) if want_voxels else None
-    coors = torch.empty((cap, ncol), dtype=torch.int32, device=dev)
-    num = torch.empty((cap,), dtype=torch.int32, device=dev)
+    direct = False
+    if out is not None and want_voxels and batch_idx is None and not mean_features:
+        ov, oc, on = out
+        direct = (all(t.is_cuda and t.is_contiguous() and t.device == dev for t in out) and
+                  ov.dtype == torch.float32 and oc.dtype == torch.int32 and on.dtype == torch.int32 and
+                  tuple(ov.shape[1:]) == (max_points, c) and oc.dim() == 2 and oc.shape[1] == 3 and
+                  min(ov.shape[0], oc.shape[0], on.shape[0]) >= cap)
+    if direct:
+        voxels, coors, num = out
+    else:
+        voxels = torch.empty((cap, max_points, c), dtype=torch.float32, device=dev) if want_voxels else None
+        coors = torch.empty((cap, ncol), dtype=torch.int32, device=dev)
+        num = torch.empty((cap,), dtype=torch.int32, device=dev)
     mean = (torch.empty((cap, mean_features), dtype=torch.float32, device=dev)
             if mean_features else None)
     voxel_num = torch.zeros((1,), dtype=torch.int32, device=dev)

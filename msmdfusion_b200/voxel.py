@@ -21,11 +21,12 @@ def hard_voxelize(points, voxels, coors, num_points_per_voxel, voxel_size, coors
     assert NDim == 3
     _cabi.require_cuda(points, 'hard_voxelize: points must be a CUDA tensor')
     v, c, n, _ = ops.hard_voxelize(points, voxel_size, coors_range, max_points, max_voxels,
-                                   want_voxels=True)
+                                   want_voxels=True, out=(voxels, coors, num_points_per_voxel))
     k = v.shape[0]
-    voxels[:k].copy_(v)
-    coors[:k].copy_(c)
-    num_points_per_voxel[:k].copy_(n)
+    if v.data_ptr() != voxels.data_ptr():   # buffers the kernels cannot write directly (dtype, strides, capacity)
+        voxels[:k].copy_(v)
+        coors[:k].copy_(c)
+        num_points_per_voxel[:k].copy_(n)
     return k
 
 
