@@ -461,8 +461,9 @@ def run_ours(args, rank, world, device):
                                  'cache', 'bf16x3': 'tcgen05 kind::f16, bf16 x3', 'bf16': 'tcgen05 kind::f16, bf16 operands'
                              }[args.precision] if args.workload == 'train' else
                              'spconv_fwd_tc_kernel (tcgen05 kind::tf32, 3xTF32)' if tc and args.precision == 'tf32x3' else
-                             'spconv_fwd_sbp_kernel (persistent; tcgen05 kind::f16 on cached split-bf16 operands, cp.async '
-                             'gather, work shares from tile masks)'
+                             'spconv_fwd_sbp_kernel / spconv_fwd_sb_kernel (tcgen05 kind::f16 on cached split-bf16 operands, '
+                             'cp.async gather; persistent work-balanced schedule for N >= 64 and >= 16 K chunks per tile, one '
+                             'tile per CTA for the narrow layers)'
                              if tc and args.precision == 'bf16x3c' else
                              'spconv_fwd_tc16_kernel (tcgen05 kind::f16 on bf16 operands, %s)' % args.precision if tc else
                              'spconv_fwd_simt_kernel') + ' (%d launches/scene, summed)' % (len(conv) // 3),
