@@ -354,7 +354,8 @@ spconv_fwd_sb_kernel(const uint16_t* __restrict__ xs, const uint16_t* __restrict
 // (profiles/r02j ncu list): a grid of 169 tiles on 148 SMs runs two waves for 1.14 waves of work, and the
 // 1.5 us set-up + 8 us epilogue of every tile are serial with its 24 us main loop.  This variant keeps the tile
 // code and changes the schedule:
-//   * one CTA per SM slot, each given an equal, contiguous range of the launch's (tile, K chunk) units.  A tile
+//   * one CTA per SM slot, each given an equal, contiguous range of the launch's units -- per tile `epi_units` for
+//     its epilogue plus one per K chunk that has a pair in the tile (tile masks; all chunks without them).  A tile
 //     that straddles a range boundary is finished by the CTA holding its FIRST chunk (its owner, which reaches it
 //     last); the CTAs holding the rest reach their fragment first, and hand the owner raw fp32 partial sums
 //     through an L2-resident slot + one release/acquire flag per epilogue warp.  The owner adds the partials in
