@@ -38,8 +38,10 @@ SETTLE_MS = 200.0  # untimed pipeline run before the warm-up steps (see run_ours
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=100)
-    ap.add_argument('--warmup', type=int, default=30)  # a fresh box needs ~25 steps to reach steady clocks (profiles/r01f_bench_S.json)
+    # defaults (flags absent): 100 / 30 for this implementation (a fresh box needs ~25 steps to reach steady clocks,
+    # profiles/r01f_bench_S.json); 3 / 1 for --impl reference, whose step is one whole scene on the host cores (5-7 s)
+    ap.add_argument('--steps', type=int, default=None)
+    ap.add_argument('--warmup', type=int, default=None)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--profile', default='S', choices=['S', 'L'],
                     help='S: single 32-beam sweep (~30 k points); L: 10 sweeps (~285 k points)')
@@ -62,7 +64,12 @@ def parse():
     ap.add_argument('--no-cuda-baseline', action='store_true',
                     help='skip the `cuda_baseline` leg (the reference\'s own CUDA kernels on the same scene)')
     ap.add_argument('--breakdown', default=None, help='write a per-op CUDA-event breakdown (json) here')
-    return ap.parse_args()
+    args = ap.parse_args()
+    if args.steps is None:
+        args.steps = 3 if args.impl == 'reference' else 100
+    if args.warmup is None:
+        args.warmup = 1 if args.impl == 'reference' else 30
+    return args
 
 
 def peaks():
