@@ -206,6 +206,22 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert silent.returncode == 0 and silent.stdout.strip() == ''
 
 
+def test_bench_step_defaults_depend_on_the_arm(monkeypatch):
+    """Without --steps / --warmup: 100 + 30 device steps for this implementation, 3 + 1 whole-scene host passes for
+    --impl reference (5-7 s each); explicit flags are taken as given in both arms."""
+    import importlib.util
+    import sys
+    spec = importlib.util.spec_from_file_location('bench_for_test', os.path.join(ROOT, 'bench.py'))
+    B = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(B)
+    for argv, want in ((['bench.py'], (100, 30)), (['bench.py', '--impl', 'reference'], (3, 1)),
+                       (['bench.py', '--impl', 'reference', '--steps', '20', '--warmup', '5'], (20, 5)),
+                       (['bench.py', '--steps', '7'], (7, 30))):
+        monkeypatch.setattr(sys, 'argv', argv)
+        a = B.parse()
+        assert (a.steps, a.warmup) == want and a.workload == 'LC'
+
+
 def test_tc_trace_summary_on_fabricated_record():
     """tools/tc_trace.py (GPU debug tool): the record layout of csrc/tc_trace.cuh and the per-chunk
     period / wait-share arithmetic, on a fabricated timeline (2000 cycles per chunk at 2000 MHz)."""
