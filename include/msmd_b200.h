@@ -5,11 +5,16 @@
  * Conventions
  *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless a comment
  *     says "host".  No torch types cross this boundary.
- *   - the library never allocates: outputs and scratch ("workspace") are provided by the
- *     caller; every op with scratch has a *_workspace() size query.
- *   - all work is enqueued on `stream` (a cudaStream_t passed as void*); nothing
- *     synchronises.  Counts produced on the device (voxel_num, N_out) are written to a
- *     device int the caller reads back when it needs the value on the host.
+ *   - operands, outputs and scratch ("workspace") are provided by the caller; every op with
+ *     scratch has a *_workspace() size query.  The library owns three things, created on first
+ *     use: the executor's geometry stream + event pool (per device) and the partial-sum hand-off
+ *     slots of the persistent convolution (<= 19 MB per (device, stream); see
+ *     msmd_spconv_sb_set_variant).
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*); the single-kernel
+ *     entries never synchronise.  Counts produced on the device (voxel_num, N_out) are written
+ *     to a device int the caller reads back when it needs the value on the host; the two
+ *     multi-layer entries (msmd_sparse_net_forward, msmd_gma_stage_forward) read N_out of their
+ *     strided convolutions themselves and drain ONLY their geometry stream for it.
  *   - return value: 0 (MSMD_OK) or a negative msmd_status; msmd_last_error() returns a
  *     thread-local message for the last failure.
  *   - there is NO CPU fallback: without a CUDA device every compute entry point fails
